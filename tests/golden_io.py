@@ -1,0 +1,41 @@
+"""Loader for the committed golden step vectors (tests/golden/step_*.npz)."""
+import os
+import glob
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def case_names():
+    return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, 'step_*.npz')))
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN_DIR, 'step_%s.npz' % name))
+    nt = int(z['n_traits'])
+    traits = []
+    for t in range(nt):
+        traits.append(dict(loci=z['trait%i_loci' % t], alpha=z['trait%i_alpha' % t],
+                           phi=float(z['trait%i_phi' % t]), gamma=float(z['trait%i_gamma' % t]),
+                           lyr_num=int(z['trait%i_lyr' % t]),
+                           univ_adv=bool(z['trait%i_univ_adv' % t])))
+    arch = dict(land_dim=tuple(int(v) for v in z['land_dim']), rasters=z['rasters'], K=z['K'],
+                ww=float(z['ww']), traits=traits, dom=z['dom'], paths=z['paths'],
+                move_surf=z['move_surf'] if 'move_surf' in z.files else None,
+                disp_surf=z['disp_surf'] if 'disp_surf' in z.files else None)
+    if arch['ww'] == int(arch['ww']):
+        arch['ww'] = int(arch['ww'])
+    prm = dict(b=float(z['prm_b']), R=float(z['prm_R']), lam=float(z['prm_n_births_distr_lambda']),
+               n_births_fixed=bool(z['prm_n_births_fixed']),
+               mating_radius=float(z['prm_mating_radius']), d_min=float(z['prm_d_min']),
+               d_max=float(z['prm_d_max']), sex=bool(z['prm_sex']),
+               sex_ratio_p=float(z['prm_sex_ratio_p']),
+               max_age=None if z['prm_max_age'] < 0 else int(z['prm_max_age']),
+               direction_mu=float(z['prm_direction_distr_mu']),
+               direction_kappa=float(z['prm_direction_distr_kappa']))
+    if prm['lam'] == int(prm['lam']):
+        prm['lam'] = int(prm['lam'])
+    state = dict(x=z['in_x'], y=z['in_y'], age=z['in_age'], sex=z['in_sex'], idx=z['in_idx'],
+                 g=z['in_g'], z=z['in_z'], max_ind_idx=int(z['in_max_ind_idx']))
+    draws = {k[5:]: z[k] for k in z.files if k.startswith('draw_')}
+    return z, arch, prm, state, draws
