@@ -1,0 +1,873 @@
+// gnx_api.cu -- C-ABI of libgnxb200.so (see include/gnx_b200.h).  Host-side orchestration
+// of the sm_100a kernels in gnx_kernels.cuh: one ctx per Species, all state resident in
+// HBM, one stream, no host round trip inside a time step.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "gnx_kernels.cuh"
+
+static thread_local std::string g_last_error;
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char buf_[512];                                                                        \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,       \
+               cudaGetErrorString(e_));                                                      \
+      g_last_error = buf_;                                                                   \
+      return GNX_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define ARG(cond, msg)                                                                       \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      g_last_error = std::string("invalid argument: ") + msg;                                \
+      return GNX_ERR_ARG;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+struct gnx_ctx {
+  gnx_config_t cfg;
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  int num_sms = 148;
+  int Wq = 0, Wwords = 0;
+  int ncell = 0;
+  Pop pop{};
+  Land land{};
+  Traits traits{};
+  Dens dens{};
+  Work work{};
+  Params prm{};
+  DevDraws draws{};
+  Counters* d_c = nullptr;
+  std::vector<void*> allocs;        // everything cudaMalloc'ed for the ctx lifetime
+  std::vector<void*> draw_allocs;   // injected-draw buffers
+  std::vector<void*> trait_allocs;
+  std::vector<void*> dens_allocs;
+  double* d_rasters = nullptr;
+  double* d_K = nullptr;
+  uint4* d_stage_genomes = nullptr;   // species-order staging for upload/download
+  bool have_density = false, have_paths = false, have_traits = false;
+  int64_t launches = 0;
+  int burn = 0;
+  int host_n_hint = 0;
+};
+
+template <class T>
+static int dmalloc(gnx_ctx* ctx, T** p, size_t count, std::vector<void*>* bucket = nullptr) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CK(cudaMalloc(&q, bytes));
+  CK(cudaMemsetAsync(q, 0, bytes, ctx->stream));
+  (bucket ? *bucket : ctx->allocs).push_back(q);
+  *p = (T*)q;
+  return GNX_OK;
+}
+#define DM(...)                                   \
+  do {                                            \
+    int r_ = dmalloc(__VA_ARGS__);                \
+    if (r_ != GNX_OK) return r_;                  \
+  } while (0)
+
+static inline int grid_for(const gnx_ctx* ctx, int per_sm) { return ctx->num_sms * per_sm; }
+
+extern "C" const char* gnx_strerror(int code) {
+  switch (code) {
+    case GNX_OK: return "ok";
+    case GNX_ERR_CUDA: return "CUDA runtime error";
+    case GNX_ERR_ARG: return "invalid argument";
+    case GNX_ERR_CAPACITY: return "population outgrew ctx capacity";
+    case GNX_ERR_DRAWS: return "injected draw buffer exhausted";
+    case GNX_ERR_STATE: return "call made in the wrong state";
+    default: return "unknown error";
+  }
+}
+extern "C" const char* gnx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int gnx_abi_version(void) { return GNX_ABI_VERSION; }
+
+static void mating_grid(const gnx_config_t& c, double* cs, int* ncx, int* ncy) {
+  // Cells of side >= radius*(1+1e-7), doubled until <= 2^22 cells (DESIGN.md "mating grid")
+  double s = c.mating_radius > 0 ? c.mating_radius * 1.0000001 : (double)std::max(c.dim_x, c.dim_y);
+  while (((long long)(c.dim_x / s) + 1) * ((long long)(c.dim_y / s) + 1) > (1ll << 22)) s *= 2.0;
+  *cs = s;
+  *ncx = (int)(c.dim_x / s) + 1;
+  *ncy = (int)(c.dim_y / s) + 1;
+}
+
+extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
+  ARG(cfg && out, "null cfg/out");
+  ARG(cfg->abi_version == GNX_ABI_VERSION, "abi_version mismatch");
+  ARG(cfg->dim_x > 0 && cfg->dim_y > 0 && cfg->n_layers > 0 && cfg->n_layers <= GNX_MAX_LAYERS, "landscape dims");
+  ARG(cfg->capacity > 0 && cfg->capacity < (1ll << 31) - 4096, "capacity");
+  ARG(cfg->n_traits >= 0 && cfg->n_traits <= GNX_MAX_TRAITS, "n_traits");
+  ARG(cfg->L >= 0, "L");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) { g_last_error = "no CUDA device"; return GNX_ERR_CUDA; }
+  gnx_ctx* ctx = new gnx_ctx();
+  ctx->cfg = *cfg;
+  CK(cudaGetDevice(&ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const int64_t cap = cfg->capacity;
+  ctx->Wq = std::max(1, (cfg->L + 127) / 128);
+  ctx->Wwords = 4 * ctx->Wq;
+  Pop& P = ctx->pop;
+  P.cap = (int)cap;
+  P.Wq = ctx->Wq;
+  P.T = cfg->n_traits;
+  for (int h = 0; h < 2; ++h) {
+    DM(ctx, &P.x[h], cap);
+    DM(ctx, &P.y[h], cap);
+    DM(ctx, &P.age[h], cap);
+    DM(ctx, &P.sex[h], cap);
+    DM(ctx, &P.idx[h], cap);
+    DM(ctx, &P.gslot[h], cap);
+    DM(ctx, &P.z[h], cap * std::max(1, cfg->n_traits));
+    DM(ctx, &P.fit[h], cap);
+  }
+  DM(ctx, &P.G, (size_t)cap * 2 * ctx->Wq);
+  DM(ctx, &P.free_slots, cap);
+  DM(ctx, &ctx->d_stage_genomes, (size_t)cap * 2 * ctx->Wq);
+  // landscape
+  Land& Ld = ctx->land;
+  Ld.X = cfg->dim_x;
+  Ld.Y = cfg->dim_y;
+  Ld.n_layers = cfg->n_layers;
+  Ld.max_x = cfg->dim_x - 0.001;
+  Ld.max_y = cfg->dim_y - 0.001;
+  mating_grid(*cfg, &Ld.cell_size, &Ld.ncx, &Ld.ncy);
+  ctx->ncell = Ld.ncx * Ld.ncy;
+  const size_t plane = (size_t)cfg->dim_x * cfg->dim_y;
+  DM(ctx, &ctx->d_rasters, plane * cfg->n_layers);
+  DM(ctx, &ctx->d_K, plane);
+  Ld.rasters = ctx->d_rasters;
+  Ld.K = ctx->d_K;
+  // work
+  Work& W = ctx->work;
+  DM(ctx, &W.cell_count, (size_t)ctx->ncell + 1);
+  DM(ctx, &W.cell_start, (size_t)ctx->ncell + 1);
+  DM(ctx, &W.cellkey, cap);
+  DM(ctx, &W.cellrank, cap);
+  DM(ctx, &W.perm, cap);
+  DM(ctx, &W.sx, cap);
+  DM(ctx, &W.sy, cap);
+  DM(ctx, &W.mate, cap);
+  DM(ctx, &W.n_nbrs, cap);
+  DM(ctx, &W.pairs, 2 * cap);
+  DM(ctx, &W.nb, cap);
+  DM(ctx, &W.off_start, cap);
+  DM(ctx, &W.off_pair, cap);
+  DM(ctx, &W.mid_x, cap);
+  DM(ctx, &W.mid_y, cap);
+  DM(ctx, &W.alive, cap);
+  DM(ctx, &W.death_p, cap);
+  DM(ctx, &W.disp_tries, cap);
+  DM(ctx, &W.tile_sums, (size_t)std::max<int64_t>(cap, ctx->ncell) / SCAN_TILE + 2);
+  DM(ctx, &W.N_rast, plane);
+  DM(ctx, &W.NP_rast, plane);
+  DM(ctx, &W.d_rast, plane);
+  DM(ctx, &W.e_out, (size_t)cap * cfg->n_layers);
+  W.max_records = 1 << 16;
+  DM(ctx, &W.records, (size_t)W.max_records);
+  DM(ctx, &ctx->d_c, 1);
+  // params
+  Params& pr = ctx->prm;
+  pr.c = *cfg;
+  pr.r2 = cfg->mating_radius * cfg->mating_radius;
+  pr.burn = 0;
+  pr.selection = cfg->n_traits > 0;
+  pr.n_paths = cfg->n_recomb_paths;
+  pr.paths = nullptr;
+  pr.move_tab = pr.disp_tab = nullptr;
+  pr.seed_lo = (uint32_t)cfg->seed;
+  pr.seed_hi = (uint32_t)(cfg->seed >> 32);
+  pr.store_debug = 1;
+  memset(&ctx->draws, 0, sizeof ctx->draws);
+  ctx->draws.disp_R = std::max(1, cfg->disp_max_tries_injected);
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return GNX_OK;
+}
+
+static void free_bucket(std::vector<void*>& b) {
+  for (void* p : b) cudaFree(p);
+  b.clear();
+}
+
+extern "C" int gnx_destroy(gnx_ctx* ctx) {
+  if (!ctx) return GNX_OK;
+  cudaStreamSynchronize(ctx->stream);
+  free_bucket(ctx->allocs);
+  free_bucket(ctx->draw_allocs);
+  free_bucket(ctx->trait_allocs);
+  free_bucket(ctx->dens_allocs);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GNX_OK;
+}
+
+static int set_K(gnx_ctx* ctx) {
+  const int ncell = ctx->cfg.dim_x * ctx->cfg.dim_y;
+  k_K_from_layer<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(
+      ctx->d_rasters + (size_t)ctx->cfg.K_layer * ncell, ctx->d_K, ctx->cfg.K_factor, ncell);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters) {
+  ARG(ctx && host_rasters, "null");
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  CK(cudaMemcpyAsync(ctx->d_rasters, host_rasters, plane * ctx->cfg.n_layers * sizeof(double),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return set_K(ctx);
+}
+
+extern "C" int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_raster) {
+  ARG(ctx && host_raster && layer >= 0 && layer < ctx->cfg.n_layers, "layer");
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  CK(cudaMemcpyAsync(ctx->d_rasters + plane * layer, host_raster, plane * sizeof(double), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  if (layer == ctx->cfg.K_layer) return set_K(ctx);      // model.py:651-652 (Species._set_K)
+  return GNX_OK;
+}
+
+template <class T>
+static int upload_vec(gnx_ctx* ctx, const std::vector<T>& v, const T** dev, std::vector<void*>& bucket) {
+  T* d = nullptr;
+  int r = dmalloc(ctx, &d, v.size(), &bucket);
+  if (r != GNX_OK) return r;
+  if (!v.empty()) CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *dev = d;
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t* traits, const int8_t* host_dom) {
+  ARG(ctx, "null ctx");
+  ARG(n_traits == ctx->cfg.n_traits, "n_traits differs from config");
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_bucket(ctx->trait_allocs);
+  Traits& T = ctx->traits;
+  memset(&T, 0, sizeof T);
+  const int Wq = ctx->Wq;
+  std::vector<int32_t> te_locus;
+  std::vector<double> te_alpha, te_dom;
+  std::vector<int32_t> chunk_ptr((size_t)std::max(1, n_traits) * (Wq + 1), 0);
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  for (int t = 0; t < n_traits; ++t) {
+    const gnx_trait_t& tr = traits[t];
+    ARG(tr.n_loci >= 0 && (tr.n_loci == 0 || (tr.host_loci && tr.host_alpha)), "trait loci");
+    ARG(tr.layer >= 0 && tr.layer < ctx->cfg.n_layers, "trait layer");
+    std::vector<int> order(tr.n_loci);
+    for (int k = 0; k < tr.n_loci; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tr.host_loci[a] < tr.host_loci[b]; });
+    int q = 0;
+    chunk_ptr[(size_t)t * (Wq + 1)] = (int32_t)te_locus.size();
+    for (int kk = 0; kk < tr.n_loci; ++kk) {
+      const int k = order[kk];
+      const int locus = tr.host_loci[k];
+      ARG(locus >= 0 && locus < ctx->cfg.L, "trait locus out of range");
+      while (q < locus / 128) chunk_ptr[(size_t)t * (Wq + 1) + (++q)] = (int32_t)te_locus.size();
+      te_locus.push_back(locus);
+      te_alpha.push_back(tr.host_alpha[k]);
+      te_dom.push_back(host_dom ? 1.0 + (double)host_dom[locus] : 1.0);
+    }
+    while (q < Wq) chunk_ptr[(size_t)t * (Wq + 1) + (++q)] = (int32_t)te_locus.size();
+    T.n_loci[t] = tr.n_loci;
+    T.phi[t] = tr.phi;
+    T.gamma[t] = tr.gamma;
+    T.layer[t] = tr.layer;
+    T.univ_adv[t] = tr.univ_adv;
+    T.phi_rast[t] = nullptr;
+    if (tr.host_phi_raster) {
+      double* d = nullptr;
+      DM(ctx, &d, plane, &ctx->trait_allocs);
+      CK(cudaMemcpyAsync(d, tr.host_phi_raster, plane * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      T.phi_rast[t] = d;
+    }
+  }
+  int r;
+  if ((r = upload_vec(ctx, te_locus, &T.te_locus, ctx->trait_allocs)) != GNX_OK) return r;
+  if ((r = upload_vec(ctx, te_alpha, &T.te_alpha, ctx->trait_allocs)) != GNX_OK) return r;
+  if (ctx->cfg.use_dom && host_dom) {
+    if ((r = upload_vec(ctx, te_dom, &T.te_dom, ctx->trait_allocs)) != GNX_OK) return r;
+  } else {
+    T.te_dom = nullptr;
+  }
+  if ((r = upload_vec(ctx, chunk_ptr, &T.chunk_ptr, ctx->trait_allocs)) != GNX_OK) return r;
+  ctx->have_traits = true;
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_paths) {
+  ARG(ctx && host_packed_paths, "null");
+  ARG(ctx->cfg.n_recomb_paths > 0, "n_recomb_paths");
+  uint4* d = nullptr;
+  const size_t n = (size_t)ctx->cfg.n_recomb_paths * ctx->Wq;
+  DM(ctx, &d, n);
+  CK(cudaMemcpyAsync(d, host_packed_paths, n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->prm.paths = d;
+  ctx->have_paths = true;
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_surface_tables(gnx_ctx* ctx, const uint16_t* host_move_f16, const uint16_t* host_disp_f16) {
+  ARG(ctx, "null ctx");
+  const size_t n = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y * std::max(1, ctx->cfg.surf_approx_len);
+  if (host_move_f16) {
+    __half* d = nullptr;
+    DM(ctx, &d, n);
+    CK(cudaMemcpyAsync(d, host_move_f16, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prm.move_tab = d;
+  }
+  if (host_disp_f16) {
+    __half* d = nullptr;
+    DM(ctx, &d, n);
+    CK(cudaMemcpyAsync(d, host_disp_f16, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prm.disp_tab = d;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
+  ARG(ctx && dn, "null");
+  ARG(dn->n_points > 0 && dn->n_tri > 0, "empty triangulation");
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_bucket(ctx->dens_allocs);
+  Dens& D = ctx->dens;
+  memset(&D, 0, sizeof D);
+  D.ww = dn->window_width;
+  D.hww = dn->window_width / 2.;
+  D.npts = dn->n_points;
+  D.ntri = dn->n_tri;
+  int off = 0;
+  for (int g = 0; g < 4; ++g) {
+    D.g_ni[g] = dn->grid_ni[g];
+    D.g_nj[g] = dn->grid_nj[g];
+    D.g_i0[g] = dn->grid_i0[g];
+    D.g_j0[g] = dn->grid_j0[g];
+    D.g_xe[g] = dn->grid_x_edge[g];
+    D.g_ye[g] = dn->grid_y_edge[g];
+    D.g_off[g] = off;
+    off += dn->grid_ni[g] * dn->grid_nj[g];
+  }
+  ARG(off == dn->n_points, "grid shapes do not add up to n_points");
+  D.lat_ni = dn->lat_ni;
+  D.lat_nj = dn->lat_nj;
+  D.colourable = dn->colourable;
+  auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+    void* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+    ctx->dens_allocs.push_back(d);
+    CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dst = d;
+    return GNX_OK;
+  };
+  int r;
+  if ((r = up(dn->host_points, sizeof(double) * 2 * D.npts, (const void**)&D.points))) return r;
+  if ((r = up(dn->host_areas, sizeof(double) * D.npts, (const void**)&D.areas))) return r;
+  if ((r = up(dn->host_simplices, sizeof(int32_t) * 3 * D.ntri, (const void**)&D.simplices))) return r;
+  if ((r = up(dn->host_neighbors, sizeof(int32_t) * 3 * D.ntri, (const void**)&D.neighbors))) return r;
+  if ((r = up(dn->host_nbr_indptr, sizeof(int32_t) * (D.npts + 1), (const void**)&D.nbr_indptr))) return r;
+  const int nnz = dn->host_nbr_indptr[D.npts];
+  if ((r = up(dn->host_nbr_indices, sizeof(int32_t) * nnz, (const void**)&D.nbr_indices))) return r;
+  if ((r = up(dn->host_square_tri, sizeof(int32_t) * 2 * (D.lat_ni - 1) * (D.lat_nj - 1),
+              (const void**)&D.square_tri)))
+    return r;
+  DM(ctx, &D.counts, (size_t)2 * D.npts, &ctx->dens_allocs);
+  DM(ctx, &D.vals, (size_t)2 * D.npts, &ctx->dens_allocs);
+  DM(ctx, &D.grad, (size_t)4 * D.npts, &ctx->dens_allocs);
+  DM(ctx, &D.coef, (size_t)2 * D.ntri * 19, &ctx->dens_allocs);
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_density = true;
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
+  ARG(ctx, "null ctx");
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_bucket(ctx->draw_allocs);
+  const int R = ctx->draws.disp_R;
+  memset(&ctx->draws, 0, sizeof ctx->draws);
+  ctx->draws.disp_R = R;
+  if (!dr) return GNX_OK;
+  const size_t n = (size_t)dr->n;
+  ctx->draws.n = dr->n;
+  auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+    if (!src) { *dst = nullptr; return GNX_OK; }
+    void* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+    ctx->draw_allocs.push_back(d);
+    CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dst = d;
+    return GNX_OK;
+  };
+  DevDraws& D = ctx->draws;
+  int r;
+  if ((r = up(dr->move_dir, n * 8, (const void**)&D.move_dir))) return r;
+  if ((r = up(dr->move_choice, n * 4, (const void**)&D.move_choice))) return r;
+  if ((r = up(dr->move_dist, n * 8, (const void**)&D.move_dist))) return r;
+  if ((r = up(dr->mate_R, n * 4, (const void**)&D.mate_R))) return r;
+  if ((r = up(dr->mate_inv_u, n * 8, (const void**)&D.mate_inv_u))) return r;
+  if ((r = up(dr->mate_u, n * 8, (const void**)&D.mate_u))) return r;
+  if ((r = up(dr->poisson, n * 4, (const void**)&D.poisson))) return r;
+  if ((r = up(dr->recomb_keys, 2 * n * 4, (const void**)&D.recomb_keys))) return r;
+  if ((r = up(dr->start_homs, 2 * n * 4, (const void**)&D.start_homs))) return r;
+  if ((r = up(dr->disp_dir, n * R * 8, (const void**)&D.disp_dir))) return r;
+  if ((r = up(dr->disp_choice, n * R * 4, (const void**)&D.disp_choice))) return r;
+  if ((r = up(dr->disp_dist, n * R * 8, (const void**)&D.disp_dist))) return r;
+  if ((r = up(dr->sex_u, n * 8, (const void**)&D.sex_u))) return r;
+  if ((r = up(dr->sex_redraw_u, n * 8, (const void**)&D.sex_redraw_u))) return r;
+  if ((r = up(dr->death_u, n * 8, (const void**)&D.death_u))) return r;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+extern "C" int gnx_set_burn(gnx_ctx* ctx, int32_t burn) {
+  ARG(ctx, "null ctx");
+  ctx->burn = burn ? 1 : 0;
+  ctx->prm.burn = ctx->burn;
+  ctx->prm.selection = (!ctx->burn && ctx->cfg.n_traits > 0) ? 1 : 0;
+  return GNX_OK;
+}
+
+static int read_counters(gnx_ctx* ctx, Counters* h) {
+  CK(cudaMemcpyAsync(h, ctx->d_c, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+static int check_device_err(const Counters& h) {
+  if (h.err & GNX_ERRBIT_CAPACITY) { g_last_error = "population outgrew ctx capacity"; return GNX_ERR_CAPACITY; }
+  if (h.err & GNX_ERRBIT_DRAWS) { g_last_error = "injected dispersal draws exhausted"; return GNX_ERR_DRAWS; }
+  return GNX_OK;
+}
+
+// ---- population upload / download -------------------------------------------------------
+extern "C" int gnx_phenotype(gnx_ctx* ctx);
+
+extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) {
+  ARG(ctx && pop, "null");
+  ARG(pop->n >= 0 && pop->n <= ctx->cfg.capacity, "population larger than capacity");
+  ARG(pop->x && pop->y, "x/y required");
+  const size_t n = (size_t)pop->n;
+  cudaStream_t s = ctx->stream;
+  Pop& P = ctx->pop;
+  Counters h;
+  memset(&h, 0, sizeof h);
+  h.n = h.n_pre = (int)n;
+  h.cur = 0;
+  h.n_free = 0;
+  h.n_slots = (int)n;
+  h.max_idx = pop->max_ind_idx;
+  // keep the running time-step counter across uploads (Philox counter)
+  Counters old;
+  int r = read_counters(ctx, &old);
+  if (r != GNX_OK) return r;
+  h.t = old.t;
+  h.n_rec = old.n_rec;
+  CK(cudaMemcpyAsync(P.x[0], pop->x, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(P.y[0], pop->y, n * 8, cudaMemcpyHostToDevice, s));
+  if (pop->age) CK(cudaMemcpyAsync(P.age[0], pop->age, n * 4, cudaMemcpyHostToDevice, s));
+  else CK(cudaMemsetAsync(P.age[0], 0, n * 4, s));
+  if (pop->sex) CK(cudaMemcpyAsync(P.sex[0], pop->sex, n, cudaMemcpyHostToDevice, s));
+  else CK(cudaMemsetAsync(P.sex[0], 0, n, s));
+  std::vector<int64_t> ids;
+  std::vector<int32_t> slots(n);
+  for (size_t i = 0; i < n; ++i) slots[i] = (int32_t)i;
+  if (pop->idx) CK(cudaMemcpyAsync(P.idx[0], pop->idx, n * 8, cudaMemcpyHostToDevice, s));
+  else {
+    ids.resize(n);
+    for (size_t i = 0; i < n; ++i) ids[i] = (int64_t)i;
+    CK(cudaMemcpyAsync(P.idx[0], ids.data(), n * 8, cudaMemcpyHostToDevice, s));
+    if (h.max_idx < (int64_t)n - 1) h.max_idx = (int64_t)n - 1;
+  }
+  CK(cudaMemcpyAsync(P.gslot[0], slots.data(), n * 4, cudaMemcpyHostToDevice, s));
+  if (pop->genomes) {
+    CK(cudaMemcpyAsync(P.G, pop->genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  }
+  if (pop->fit) CK(cudaMemcpyAsync(P.fit[0], pop->fit, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_c, &h, sizeof h, cudaMemcpyHostToDevice, s));
+  if (pop->z && ctx->cfg.n_traits > 0) {
+    // host z is [n][T]; device z is [T][cap]
+    std::vector<double> zt(n);
+    for (int t = 0; t < ctx->cfg.n_traits; ++t) {
+      for (size_t i = 0; i < n; ++i) zt[i] = pop->z[i * ctx->cfg.n_traits + t];
+      CK(cudaMemcpyAsync(P.z[0] + (size_t)t * P.cap, zt.data(), n * 8, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  } else if (pop->genomes && ctx->cfg.n_traits > 0 && ctx->have_traits) {
+    r = gnx_phenotype(ctx);
+    if (r != GNX_OK) return r;
+  }
+  CK(cudaStreamSynchronize(s));
+  ctx->host_n_hint = (int)n;
+  return GNX_OK;
+}
+
+extern "C" int gnx_population_size(gnx_ctx* ctx, int64_t* n) {
+  ARG(ctx && n, "null");
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  *n = h.n;
+  return check_device_err(h);
+}
+
+extern "C" int gnx_sample_env(gnx_ctx* ctx);
+
+extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
+  ARG(ctx && pop, "null");
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  const size_t n = (size_t)h.n;
+  const int cur = h.cur;
+  cudaStream_t s = ctx->stream;
+  Pop& P = ctx->pop;
+  pop->n = h.n;
+  pop->max_ind_idx = h.max_idx;
+  if (pop->x) CK(cudaMemcpyAsync(pop->x, P.x[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->y) CK(cudaMemcpyAsync(pop->y, P.y[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->age) CK(cudaMemcpyAsync(pop->age, P.age[cur], n * 4, cudaMemcpyDeviceToHost, s));
+  if (pop->sex) CK(cudaMemcpyAsync(pop->sex, P.sex[cur], n, cudaMemcpyDeviceToHost, s));
+  if (pop->idx) CK(cudaMemcpyAsync(pop->idx, P.idx[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->fit) CK(cudaMemcpyAsync(pop->fit, P.fit[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->genomes && !ctx->burn) {
+    k_gather_genomes<<<grid_for(ctx, 8), 256, 0, s>>>(P, ctx->d_stage_genomes, ctx->d_c);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pop->genomes, ctx->d_stage_genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyDeviceToHost, s));
+  }
+  if (pop->z && ctx->cfg.n_traits > 0) {
+    std::vector<double> zt(n);
+    for (int t = 0; t < ctx->cfg.n_traits; ++t) {
+      CK(cudaMemcpyAsync(zt.data(), P.z[cur] + (size_t)t * P.cap, n * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      for (size_t i = 0; i < n; ++i) pop->z[i * ctx->cfg.n_traits + t] = zt[i];
+    }
+  }
+  if (pop->e) {
+    r = gnx_sample_env(ctx);
+    if (r != GNX_OK) return r;
+    CK(cudaMemcpyAsync(pop->e, ctx->work.e_out, n * ctx->cfg.n_layers * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return check_device_err(h);
+}
+
+// ---- stages -----------------------------------------------------------------------------
+#define LAUNCHED(ctx)        \
+  do {                       \
+    (ctx)->launches++;       \
+    CK(cudaGetLastError());  \
+  } while (0)
+
+template <class F>
+static int run_scan(gnx_ctx* ctx, F f) {
+  cudaStream_t s = ctx->stream;
+  scan_reduce_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  LAUNCHED(ctx);
+  scan_spine_kernel<F><<<1, SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  LAUNCHED(ctx);
+  scan_apply_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+static int age_move_bin(gnx_ctx* ctx, int do_age, int do_move, int do_bin) {
+  if (do_bin) CK(cudaMemsetAsync(ctx->work.cell_count, 0, ((size_t)ctx->ncell + 1) * 4, ctx->stream));
+  if (do_move && ctx->cfg.move_surf_mode == GNX_SURF_TABLE && !ctx->prm.move_tab) {
+    g_last_error = "movement surface table not set";
+    return GNX_ERR_STATE;
+  }
+  k_age_move_bin<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+                                                           ctx->d_c, do_age, do_move, do_bin);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_age_step(gnx_ctx* ctx) { ARG(ctx, "null ctx"); return age_move_bin(ctx, 1, 0, 0); }
+extern "C" int gnx_move(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->cfg.move) return GNX_OK;
+  return age_move_bin(ctx, 0, 1, 0);
+}
+
+static int finish_binning(gnx_ctx* ctx) {
+  CellScan cs{ctx->work.cell_count, ctx->work.cell_start, ctx->ncell};
+  int r = run_scan(ctx, cs);
+  if (r != GNX_OK) return r;
+  cudaStream_t s = ctx->stream;
+  k_scatter_perm<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  k_cell_sort<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->ncell);
+  LAUNCHED(ctx);
+  k_gather_sorted<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  int r = age_move_bin(ctx, 0, 0, 1);
+  if (r != GNX_OK) return r;
+  return finish_binning(ctx);
+}
+
+extern "C" int gnx_find_mates(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  ARG(ctx->cfg.mating_radius > 0, "panmixia is not implemented in this build");
+  k_find_mates<<<grid_for(ctx, 16), 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+                                                          ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  const bool fixed = ctx->cfg.n_births_fixed != 0;
+  PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0};
+  if (fixed) ARG(ps.fixed_nb >= 1, "n_births_fixed needs n_births_distr_lambda >= 1");
+  int r = run_scan(ctx, ps);
+  if (r != GNX_OK) return r;
+  if (!fixed) {
+    k_draw_births<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
+    LAUNCHED(ctx);
+    BirthScan bs{ctx->work, ctx->pop.cap};
+    r = run_scan(ctx, bs);
+    if (r != GNX_OK) return r;
+  }
+  return GNX_OK;
+}
+
+extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->burn) {
+    if (!ctx->have_paths) { g_last_error = "recombination paths not set"; return GNX_ERR_STATE; }
+    if (ctx->cfg.n_traits > 0 && !ctx->have_traits) { g_last_error = "traits not set"; return GNX_ERR_STATE; }
+  }
+  cudaStream_t s = ctx->stream;
+  const int Wq = ctx->Wq;
+  const int g = grid_for(ctx, 8);
+#define MO(GW) k_make_offspring<GW><<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c)
+  if (Wq <= 1) MO(1);
+  else if (Wq <= 2) MO(2);
+  else if (Wq <= 4) MO(4);
+  else if (Wq <= 8) MO(8);
+  else if (Wq <= 16) MO(16);
+  else MO(32);
+#undef MO
+  LAUNCHED(ctx);
+  k_after_births<<<1, 1, 0, s>>>(ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_phenotype(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (ctx->cfg.n_traits == 0) return GNX_OK;
+  if (!ctx->have_traits) { g_last_error = "traits not set"; return GNX_ERR_STATE; }
+  k_phenotype_all<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->traits, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_density_counts(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(ctx->dens.counts, 0, (size_t)2 * ctx->dens.npts * 4, s));
+  k_density_counts<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 0);
+  LAUNCHED(ctx);
+  k_density_counts<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 1);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_density_eval(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
+  cudaStream_t s = ctx->stream;
+  // scipy defaults reached through griddata: CloughTocher2DInterpolator(tol=1e-6, maxiter=400)
+  k_ct_gradients<<<2, GS_BLOCK, 0, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
+  LAUNCHED(ctx);
+  k_ct_coefficients<<<std::max(1, (2 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
+  LAUNCHED(ctx);
+  k_raster_N<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  k_raster_d<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_death_prob(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  k_death<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
+                                                    ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_mortality(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
+  int r = run_scan(ctx, ms);
+  if (r != GNX_OK) return r;
+  k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_sample_env(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  k_sample_env<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+// One time step for this species = the reference's queue (model.py:603-667):
+//   _set_age_stage -> _do_movement -> _do_pop_dynamics -> _set_Nt
+static int one_step(gnx_ctx* ctx) {
+  int r;
+  // a1 + a2 + a4 fused: age, movement, cell keys + histogram
+  if ((r = age_move_bin(ctx, 1, ctx->cfg.move ? 1 : 0, 1))) return r;
+  if ((r = finish_binning(ctx))) return r;
+  if ((r = gnx_find_mates(ctx))) return r;
+  if ((r = gnx_dedup_pairs(ctx))) return r;
+  if ((r = gnx_make_offspring(ctx))) return r;
+  if ((r = gnx_density_counts(ctx))) return r;
+  if ((r = gnx_density_eval(ctx))) return r;
+  if ((r = gnx_death_prob(ctx))) return r;
+  if ((r = gnx_mortality(ctx))) return r;
+  return GNX_OK;
+}
+
+extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
+  ARG(ctx && n_steps >= 0, "n_steps");
+  for (int k = 0; k < n_steps; ++k) {
+    int r = one_step(ctx);
+    if (r != GNX_OK) return r;
+  }
+  return GNX_OK;
+}
+
+extern "C" int gnx_sync(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  CK(cudaStreamSynchronize(ctx->stream));
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  return check_device_err(h);
+}
+
+extern "C" int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps) {
+  int r = gnx_upload_population(ctx, pop);
+  if (r != GNX_OK) return r;
+  r = gnx_step(ctx, n_steps);
+  if (r != GNX_OK) return r;
+  return gnx_download_population(ctx, pop);
+}
+
+extern "C" int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out) {
+  ARG(ctx && n_out, "null");
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  int n = std::min(h.n_rec, ctx->work.max_records);
+  n = std::min(n, max_records);
+  if (n > 0 && out)
+    CK(cudaMemcpyAsync(out, ctx->work.records, (size_t)n * sizeof(gnx_step_record_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  h.n_rec = 0;
+  CK(cudaMemcpyAsync(&ctx->d_c->n_rec, &h.n_rec, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n_out = n;
+  return check_device_err(h);
+}
+
+extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64_t* nbytes) {
+  ARG(ctx && dev_ptr && nbytes, "null");
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  const int cur = h.cur;
+  const size_t n = (size_t)std::max(h.n, h.n_pre), cap = (size_t)ctx->pop.cap;
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  Pop& P = ctx->pop;
+  Work& W = ctx->work;
+  Dens& D = ctx->dens;
+  void* p = nullptr;
+  size_t b = 0;
+  switch (field) {
+    case GNX_F_X: p = P.x[cur]; b = n * 8; break;
+    case GNX_F_Y: p = P.y[cur]; b = n * 8; break;
+    case GNX_F_AGE: p = P.age[cur]; b = n * 4; break;
+    case GNX_F_SEX: p = P.sex[cur]; b = n; break;
+    case GNX_F_IDX: p = P.idx[cur]; b = n * 8; break;
+    case GNX_F_Z: p = P.z[cur]; b = cap * std::max(1, ctx->cfg.n_traits) * 8; break;
+    case GNX_F_FIT: p = P.fit[cur]; b = n * 8; break;
+    case GNX_F_GSLOT: p = P.gslot[cur]; b = n * 4; break;
+    case GNX_F_N_NBRS: p = W.n_nbrs; b = n * 4; break;
+    case GNX_F_MATE: p = W.mate; b = n * 4; break;
+    case GNX_F_PAIRS: p = W.pairs; b = (size_t)h.P * 8; break;
+    case GNX_F_NB: p = W.nb; b = (size_t)h.P * 4; break;
+    case GNX_F_PERM: p = W.perm; b = n * 4; break;
+    case GNX_F_CELL_START: p = W.cell_start; b = ((size_t)ctx->ncell + 1) * 4; break;
+    case GNX_F_COUNTS_N: p = D.counts; b = (size_t)D.npts * 4; break;
+    case GNX_F_COUNTS_P: p = D.counts + D.npts; b = (size_t)D.npts * 4; break;
+    case GNX_F_VALS_N: p = D.vals; b = (size_t)D.npts * 8; break;
+    case GNX_F_VALS_P: p = D.vals + D.npts; b = (size_t)D.npts * 8; break;
+    case GNX_F_GRAD_N: p = D.grad; b = (size_t)D.npts * 16; break;
+    case GNX_F_GRAD_P: p = D.grad + 2 * (size_t)D.npts; b = (size_t)D.npts * 16; break;
+    case GNX_F_N_RAST: p = W.N_rast; b = plane * 8; break;
+    case GNX_F_NPAIRS_RAST: p = W.NP_rast; b = plane * 8; break;
+    case GNX_F_D_RAST: p = W.d_rast; b = plane * 8; break;
+    case GNX_F_K_RAST: p = ctx->d_K; b = plane * 8; break;
+    case GNX_F_DEATH_P: p = W.death_p; b = n * 8; break;
+    case GNX_F_ALIVE: p = W.alive; b = n; break;
+    case GNX_F_DISP_TRIES: p = W.disp_tries; b = (size_t)h.B * 4; break;
+    case GNX_F_E: p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
+    case GNX_F_COUNTERS: p = ctx->d_c; b = sizeof(Counters); break;
+    case GNX_F_GENOMES: p = ctx->d_stage_genomes; b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4); break;
+    default: g_last_error = "unknown field"; return GNX_ERR_ARG;
+  }
+  *dev_ptr = p;
+  *nbytes = (int64_t)b;
+  return GNX_OK;
+}
+
+extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64_t nbytes) {
+  ARG(ctx && host_out, "null");
+  if (field == GNX_F_GENOMES) {
+    k_gather_genomes<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_stage_genomes, ctx->d_c);
+    LAUNCHED(ctx);
+  }
+  if (field == GNX_F_E) {
+    int r = gnx_sample_env(ctx);
+    if (r != GNX_OK) return r;
+  }
+  void* p;
+  int64_t avail;
+  int r = gnx_device_ptr(ctx, field, &p, &avail);
+  if (r != GNX_OK) return r;
+  const int64_t b = std::min(avail, nbytes);
+  if (b > 0) CK(cudaMemcpyAsync(host_out, p, (size_t)b, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+extern "C" void* gnx_stream(gnx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int64_t gnx_launch_count(gnx_ctx* ctx) { return ctx ? ctx->launches : 0; }

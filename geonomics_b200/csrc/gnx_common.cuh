@@ -1,0 +1,316 @@
+// gnx_common.cuh -- device-side data layout, Philox RNG and distribution samplers.
+// Part of libgnxb200.so (sm_100a).  See DESIGN.md for the HBM layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/gnx_b200.h"
+
+#define GNX_PI 3.14159265358979323846
+
+// ----------------------------------------------------------------------------------------
+// device-resident step counters (one per ctx).  Kernels read sizes from here so a whole
+// time step runs without a host round trip.
+// ----------------------------------------------------------------------------------------
+struct Counters {
+  int32_t n;         // live individuals (species-order length) at stage entry
+  int32_t n_pre;     // n + B: individuals alive before mortality
+  int32_t P;         // mating pairs this step
+  int32_t B;         // births this step
+  int32_t deaths;    // deaths this step
+  int32_t n_free;    // genome-slot free-list length
+  int32_t n_slots;   // genome-slot high-water mark
+  int32_t cur;       // which half of the double-buffered scalar SoA is current
+  int64_t max_idx;   // species.py:360 max_ind_idx
+  int64_t t;         // time-step counter (Philox counter word)
+  int32_t err;       // sticky error bits (GNX_ERRBIT_*)
+  int32_t n_rec;     // per-step records written
+  int32_t gs_iters[2];
+  unsigned long long nmax_bits;   // bits of max(N raster) (N >= 0 so unsigned order works)
+  int32_t pad[2];
+};
+#define GNX_ERRBIT_CAPACITY 1
+#define GNX_ERRBIT_DRAWS 2
+#define GNX_ERRBIT_GS 4
+
+// Double-buffered scalar SoA in species order + slot-indexed genome rows.
+struct Pop {
+  double* x[2];
+  double* y[2];
+  int32_t* age[2];
+  int8_t* sex[2];
+  int64_t* idx[2];
+  int32_t* gslot[2];
+  double* z[2];        // [T][cap]
+  double* fit[2];
+  uint4* G;            // [cap][2][Wq]
+  int32_t* free_slots; // [cap]
+  int32_t cap;
+  int32_t Wq;          // 128-bit units per homologue
+  int32_t T;
+};
+
+struct Traits {
+  // merged trait-locus table sorted by (trait, locus); entries of trait t for 128-bit
+  // unit q are [chunk_ptr[t*(Wq+1)+q], chunk_ptr[t*(Wq+1)+q+1])
+  const int32_t* te_locus;
+  const double* te_alpha;
+  const double* te_dom;        // (1 + dom[locus]) factor, or NULL
+  const int32_t* chunk_ptr;
+  int32_t n_loci[GNX_MAX_TRAITS];
+  double phi[GNX_MAX_TRAITS];
+  const double* phi_rast[GNX_MAX_TRAITS];
+  double gamma[GNX_MAX_TRAITS];
+  int32_t layer[GNX_MAX_TRAITS];
+  int32_t univ_adv[GNX_MAX_TRAITS];
+};
+
+struct Land {
+  const double* rasters;   // [n_layers][Y][X]
+  const double* K;         // [Y][X]
+  int32_t X, Y, n_layers;
+  double max_x, max_y;     // dim - 0.001 (movement.py:89-92)
+  // mating grid
+  double cell_size;
+  int32_t ncx, ncy;
+};
+
+struct Dens {
+  double ww, hww;
+  int32_t npts, ntri;
+  const double* points;    // [npts][2] (i, j)
+  const double* areas;
+  int32_t g_ni[4], g_nj[4], g_i0[4], g_j0[4], g_xe[4], g_ye[4], g_off[4];
+  const int32_t* simplices;
+  const int32_t* neighbors;
+  const int32_t* nbr_indptr;
+  const int32_t* nbr_indices;
+  int32_t lat_ni, lat_nj;
+  const int32_t* square_tri;
+  int32_t colourable;
+  // work
+  int32_t* counts;   // [2][npts]
+  double* vals;      // [2][npts]
+  double* grad;      // [2][npts][2]
+  double* coef;      // [2][ntri][19]
+};
+
+struct Work {
+  uint32_t* cell_count;
+  uint32_t* cell_start;    // [ncell + 1]
+  uint32_t* cellkey;
+  uint32_t* cellrank;
+  int32_t* perm;
+  double* sx;
+  double* sy;
+  int32_t* mate;
+  int32_t* n_nbrs;
+  int32_t* pairs;          // [cap][2]
+  int32_t* nb;
+  int32_t* off_start;
+  int32_t* off_pair;
+  double* mid_x;
+  double* mid_y;
+  uint8_t* alive;
+  double* death_p;
+  int32_t* disp_tries;
+  unsigned long long* tile_sums;
+  double* N_rast;
+  double* NP_rast;
+  double* d_rast;
+  double* e_out;
+  gnx_step_record_t* records;
+  int32_t max_records;
+};
+
+struct DevDraws {
+  int64_t n;
+  const double* move_dir;
+  const int32_t* move_choice;
+  const double* move_dist;
+  const uint32_t* mate_R;
+  const double* mate_inv_u;
+  const double* mate_u;
+  const int32_t* poisson;
+  const int32_t* recomb_keys;
+  const int32_t* start_homs;
+  const double* disp_dir;
+  const int32_t* disp_choice;
+  const double* disp_dist;
+  const double* sex_u;
+  const double* sex_redraw_u;
+  const double* death_u;
+  int32_t disp_R;
+};
+
+struct Params {
+  gnx_config_t c;
+  double r2;             // mating_radius^2
+  int32_t burn;
+  int32_t selection;     // fitness enters death probability (species.py:825)
+  int32_t n_paths;
+  const uint4* paths;    // [n_paths][Wq]
+  const __half* move_tab;
+  const __half* disp_tab;
+  uint32_t seed_lo, seed_hi;
+  int32_t store_debug;   // keep n_nbrs / death_p / NP_rast for parity tests
+};
+
+// ----------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: no state in HBM.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+enum {
+  SITE_MOVE = 1, SITE_MATE = 2, SITE_BIRTHS = 3, SITE_GAMETE = 4, SITE_DISP = 5, SITE_SEX = 6,
+  SITE_DEATH = 7, SITE_PANMIXIA = 8
+};
+
+// A stream of random words addressed by (seed; entity id, call site, time step).
+struct RngStream {
+  uint2 key;
+  uint4 ctr;
+  uint4 out;
+  int pos;
+  __device__ __forceinline__ RngStream(uint32_t seed_lo, uint32_t seed_hi, int64_t id, int site,
+                                       int64_t t) {
+    key = make_uint2(seed_lo, seed_hi);
+    ctr = make_uint4((uint32_t)id, (uint32_t)((uint64_t)id >> 32) ^ ((uint32_t)site << 24),
+                     (uint32_t)t, 0u);
+    pos = 4;
+    out = make_uint4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ uint32_t u32() {
+    if (pos == 4) {
+      out = philox4x32_10(ctr, key);
+      ctr.w += 1;
+      pos = 0;
+    }
+    uint32_t v = pos == 0 ? out.x : pos == 1 ? out.y : pos == 2 ? out.z : out.w;
+    pos += 1;
+    return v;
+  }
+  // uniform in [0, 1), 53 bits (same construction as numpy's legacy double)
+  __device__ __forceinline__ double uniform() {
+    uint32_t a = u32() >> 5, b = u32() >> 6;
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+  __device__ __forceinline__ double normal() {
+    double u1 = 1.0 - uniform();           // (0, 1]
+    double u2 = uniform();
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return sqrt(-2.0 * log(u1)) * c;
+  }
+};
+
+__device__ __forceinline__ uint32_t choose_k(uint32_t R, uint32_t n) { return __umulhi(R, n); }
+
+// numpy legacy_vonmises (Best & Fisher); distributions.c
+__device__ inline double sample_vonmises(RngStream& g, double mu, double kappa) {
+  if (kappa < 1e-8) return GNX_PI * (2.0 * g.uniform() - 1.0);
+  double s;
+  if (kappa < 1e-5) {
+    s = 1.0 / kappa + kappa;
+  } else {
+    double r = 1.0 + sqrt(1.0 + 4.0 * kappa * kappa);
+    double rho = (r - sqrt(2.0 * r)) / (2.0 * kappa);
+    s = (1.0 + rho * rho) / (2.0 * rho);
+  }
+  double W;
+  for (int it = 0; it < 1000; ++it) {
+    double U = g.uniform();
+    double Z = cospi(U);
+    W = (1.0 + s * Z) / (s + Z);
+    double Y = kappa * (s - W);
+    double V = g.uniform();
+    if ((Y * (2.0 - Y) - V >= 0.0) || (log(Y / V) + 1.0 - Y >= 0.0)) break;
+  }
+  double U = g.uniform();
+  double result = acos(W);
+  if (U < 0.5) result = -result;
+  result += mu;
+  bool neg = result < 0.0;
+  double mod = fabs(result);
+  mod = fmod(mod + GNX_PI, 2.0 * GNX_PI) - GNX_PI;
+  if (neg) mod = -mod;
+  return mod;
+}
+
+// numpy legacy wald (inverse Gaussian), lognormal; scipy levy (loc + scale / Z^2)
+__device__ inline double sample_distance(RngStream& g, int distr, double p1, double p2) {
+  if (distr == GNX_DISTR_WALD) {
+    double mean = p1, scale = p2;
+    double mu_2l = mean / (2.0 * scale);
+    double Y = g.normal();
+    Y = mean * Y * Y;
+    double X = mean + mu_2l * (Y - sqrt(4.0 * scale * Y + Y * Y));
+    double U = g.uniform();
+    return (U <= mean / (mean + X)) ? X : mean * mean / X;
+  } else if (distr == GNX_DISTR_LOGNORMAL) {
+    return exp(p1 + p2 * g.normal());
+  } else {
+    double Z = g.normal();
+    return p1 + p2 / (Z * Z);
+  }
+}
+
+// numpy legacy poisson: multiplication method below lam = 10, PTRS above
+__device__ inline int sample_poisson(RngStream& g, double lam) {
+  if (lam <= 0.0) return 0;
+  if (lam < 10.0) {
+    double enlam = exp(-lam), prod = 1.0;
+    int X = 0;
+    for (;;) {
+      prod *= g.uniform();
+      if (prod > enlam) X += 1; else return X;
+    }
+  }
+  double slam = sqrt(lam), loglam = log(lam);
+  double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (;;) {
+    double U = g.uniform() - 0.5, V = g.uniform();
+    double us = 0.5 - fabs(U);
+    double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return (int)kf;
+    if (kf < 0 || (us < 0.013 && V > us)) continue;
+    if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + kf * loglam - lgamma(kf + 1.0)))
+      return (int)kf;
+  }
+}
+
+// exact floor(a / b) for finite doubles, b > 0 (numpy floor_divide semantics, spatial.py:79-82)
+__device__ __forceinline__ double floordiv_exact(double a, double b) {
+  double q = floor(a / b);
+  double r = fma(-q, b, a);
+  if (r < 0.0) q -= 1.0;
+  else if (r >= b) q += 1.0;
+  return q;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) {
+  return v < lo ? lo : (v > hi ? hi : v);    // NaN-propagating like np.clip is not needed here
+}
+
+// cos/sin of a float16 direction exactly as numpy evaluates them on a float16 array:
+// half -> float, libm cosf (correctly rounded), -> half (movement.py:75-76 with a
+// float16 `direction`, spatial.py:184,447)
+__device__ __forceinline__ void sincos_half(__half h, double* s, double* c) {
+  double a = (double)__half2float(h);
+  float cf = (float)cos(a), sf = (float)sin(a);
+  *c = (double)__half2float(__float2half_rn(cf));
+  *s = (double)__half2float(__float2half_rn(sf));
+}

@@ -1,0 +1,907 @@
+// gnx_kernels.cuh -- the per-timestep kernels (sm_100a).  Every kernel is a grid-stride /
+// persistent kernel that reads its problem size from the device-resident Counters, so a
+// whole time step is launched without a host round trip (and is CUDA-graph capturable).
+#pragma once
+#include "gnx_common.cuh"
+#include "gnx_scan.cuh"
+
+#define GTID (blockIdx.x * blockDim.x + threadIdx.x)
+#define GSTRIDE (gridDim.x * blockDim.x)
+
+// ========================================================================================
+// a1 + a2 + a4: age, movement, mating-grid key + per-cell histogram
+//   species.py:567-569 (age); movement.py:34-95 (movement); spatial.py:182-184 (surface
+//   lookup); species.py:937-939 (cells).  Flags select which parts run so the stage-level
+//   C-ABI entry points and the fused step share one kernel.
+// ========================================================================================
+__device__ inline double surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
+                                                    int cx, int cy, int mixture, double kappa) {
+  // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
+  // dropped; queen directions in raster row-major order.
+  const double dirs[8] = {-3 * GNX_PI / 4, -GNX_PI / 2, -GNX_PI / 4, GNX_PI, 0.0,
+                          3 * GNX_PI / 4, GNX_PI / 2, GNX_PI / 4};
+  const int di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  const int dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  double nv[8];
+  double sum = 0.0, mx = -1.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int i = cy + di[k], j = cx + dj[k];
+    double v = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0;
+    nv[k] = v;
+    sum += v;
+    mx = v > mx ? v : mx;
+  }
+  double loc;
+  if (mixture) {
+    double u = g.uniform();
+    int pick = 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double p = sum > 0.0 ? nv[k] / sum : 0.125;
+      acc += p;
+      if (u < acc) { pick = k; break; }
+    }
+    loc = dirs[pick];
+  } else {
+    double s = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (nv[k] == mx) { s += dirs[k]; cnt += 1; }
+    loc = s / cnt;
+  }
+  // scipy vonmises.rvs(kappa, loc): loc + vonmises(0, kappa), not re-wrapped; stored as
+  // float16 in the reference table (spatial.py:447)
+  double d = loc + sample_vonmises(g, 0.0, kappa);
+  return (double)__half2float(__float2half_rn((float)d));
+}
+
+__global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params prm, DevDraws dr,
+                                                       Work w, Counters* c, int do_age, int do_move,
+                                                       int do_bin) {
+  const int n = c->n, cur = c->cur;
+  const int64_t t = c->t;
+  double* __restrict__ X = pop.x[cur];
+  double* __restrict__ Yc = pop.y[cur];
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    if (do_age) pop.age[cur][i] += 1;
+    double x = X[i], y = Yc[i];
+    if (do_move) {
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MOVE, t);
+      double cs, sn;
+      if (prm.c.move_surf_mode == GNX_SURF_TABLE) {
+        int cx = (int)x, cy = (int)y;
+        int col = dr.move_choice ? dr.move_choice[i] : (int)choose_k(g.u32(), prm.c.surf_approx_len);
+        __half h = prm.move_tab[((size_t)cy * land.X + cx) * prm.c.surf_approx_len + col];
+        sincos_half(h, &sn, &cs);
+      } else if (prm.c.move_surf_mode == GNX_SURF_ONTHEFLY) {
+        int cx = (int)x, cy = (int)y;
+        double d = surface_direction_onthefly(
+            g, land.rasters + (size_t)prm.c.move_surf_layer * land.X * land.Y, land.X, land.Y, cx, cy,
+            prm.c.move_surf_mixture, prm.c.move_surf_kappa);
+        sincos_half(__float2half_rn((float)d), &sn, &cs);
+      } else {
+        double d = dr.move_dir ? dr.move_dir[i] : sample_vonmises(g, prm.c.dir_mu, prm.c.dir_kappa);
+        sincos(d, &sn, &cs);
+      }
+      double dist = dr.move_dist ? dr.move_dist[i]
+                                 : sample_distance(g, prm.c.move_distr, prm.c.move_p1, prm.c.move_p2);
+      double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
+      if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
+      if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
+      x = clampd(__dadd_rn(x, dx), 0.0, land.max_x);
+      y = clampd(__dadd_rn(y, dy), 0.0, land.max_y);
+      X[i] = x;
+      Yc[i] = y;
+    }
+    if (do_bin) {
+      int cx = (int)floor(x / land.cell_size), cy = (int)floor(y / land.cell_size);
+      cx = min(cx, land.ncx - 1);
+      cy = min(cy, land.ncy - 1);
+      uint32_t key = (uint32_t)cy * land.ncx + cx;
+      w.cellkey[i] = key;
+      w.cellrank[i] = atomicAdd(&w.cell_count[key], 1u);
+    }
+  }
+}
+
+// exclusive scan of the per-cell histogram -> cell_start
+struct CellScan {
+  const uint32_t* cnt;
+  uint32_t* start;
+  int ncell;
+  __device__ int size(const Counters*) const { return ncell; }
+  __device__ u64 value(int i) const { return cnt[i]; }
+  __device__ void apply(int i, u64, u64 ex) const { start[i] = (uint32_t)ex; }
+  __device__ void total(Counters*, u64 tot) const { start[ncell] = (uint32_t)tot; }
+};
+
+__global__ void __launch_bounds__(256) k_scatter_perm(Work w, const Counters* c) {
+  const int n = c->n;
+  for (int i = GTID; i < n; i += GSTRIDE) w.perm[w.cell_start[w.cellkey[i]] + w.cellrank[i]] = i;
+}
+
+// per-cell ordering by species-order ordinal: makes the binned order a *stable* counting
+// sort (deterministic whatever order the histogram atomics retired in).
+__global__ void __launch_bounds__(256) k_cell_sort(Work w, int ncell) {
+  for (int cell = GTID; cell < ncell; cell += GSTRIDE) {
+    const int s = w.cell_start[cell], e = w.cell_start[cell + 1];
+    for (int a = s + 1; a < e; ++a) {
+      int v = w.perm[a];
+      int b = a - 1;
+      while (b >= s && w.perm[b] > v) {
+        w.perm[b + 1] = w.perm[b];
+        --b;
+      }
+      w.perm[b + 1] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Counters* c) {
+  const int n = c->n, cur = c->cur;
+  for (int p = GTID; p < n; p += GSTRIDE) {
+    int i = w.perm[p];
+    w.sx[p] = pop.x[cur][i];
+    w.sy[p] = pop.y[cur][i];
+  }
+}
+
+// ========================================================================================
+// a5: neighbour scan + mate choice.  species.py:2157-2215, spatial.py:191-245.
+//   One thread per focal, walking the three contiguous row-ranges of the cell-sorted
+//   coordinate arrays that cover its 3x3 cell block.  Closed ball on squared distances,
+//   products and sum rounded separately (as the reference's cKDTree does).
+// ========================================================================================
+__global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
+                                                     const Counters* c) {
+  const int n = c->n, cur = c->cur;
+  const int64_t t = c->t;
+  const double r2 = prm.r2, radius = prm.c.mating_radius;
+  for (int p = GTID; p < n; p += GSTRIDE) {
+    const int i = w.perm[p];
+    const double fx = w.sx[p], fy = w.sy[p];
+    const uint32_t key = w.cellkey[i];
+    const int cy = key / land.ncx, cx = key - cy * land.ncx;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
+    int lo[3], hi[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int row = cy - 1 + r;
+      if (row < 0 || row >= land.ncy) { lo[r] = hi[r] = 0; continue; }
+      lo[r] = w.cell_start[row * land.ncx + x0];
+      hi[r] = w.cell_start[row * land.ncx + x1 + 1];
+    }
+    // pass 1: count (and nearest / weight sum)
+    int cnt = 0;
+    double best = 1e300, wsum = 0.0;
+    int best_q = -1, n_w = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      for (int q = lo[r]; q < hi[r]; ++q) {
+        if (q == p) continue;
+        double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
+        double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d2 <= r2) {
+          cnt += 1;
+          if (d2 < best) { best = d2; best_q = q; }
+          if (prm.c.inverse_dist) {
+            double d = sqrt(d2);
+            if (d != 0.0) { wsum += radius - d; n_w += 1; }
+          }
+        }
+      }
+    if (prm.store_debug) w.n_nbrs[i] = cnt;
+    int mate = -1;
+    if (cnt > 0) {
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MATE, t);
+      int sel_q = -1;
+      if (prm.c.choose_nearest) {
+        sel_q = best_q;
+      } else if (prm.c.inverse_dist) {
+        if (n_w > 0) {
+          double u = dr.mate_inv_u ? dr.mate_inv_u[i] : g.uniform();
+          double target = u * wsum, acc = 0.0;
+          int last = -1;
+#pragma unroll
+          for (int r = 0; r < 3 && sel_q < 0; ++r)
+            for (int q = lo[r]; q < hi[r]; ++q) {
+              if (q == p) continue;
+              double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
+              double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              if (d2 <= r2) {
+                double d = sqrt(d2);
+                acc += (d != 0.0) ? radius - d : 0.0;
+                last = q;
+                if (target < acc) { sel_q = q; break; }
+              }
+            }
+          if (sel_q < 0) sel_q = last;
+        }
+      } else {
+        uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
+        int k = (int)choose_k(R, (uint32_t)cnt);
+#pragma unroll
+        for (int r = 0; r < 3 && sel_q < 0; ++r)
+          for (int q = lo[r]; q < hi[r]; ++q) {
+            if (q == p) continue;
+            double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
+            double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 <= r2) {
+              if (k == 0) { sel_q = q; break; }
+              k -= 1;
+            }
+          }
+      }
+      if (sel_q >= 0) {
+        double u = dr.mate_u ? dr.mate_u[i] : g.uniform();
+        if (u < prm.c.b) mate = w.perm[sel_q];       // species.py:2212-2214
+      }
+    }
+    w.mate[i] = mate;
+  }
+}
+
+// ========================================================================================
+// a6 + a8: sex filter / reciprocal de-dup (mating.py:41-63), stream compaction into the
+// canonical pair list, births per pair (species.py:604-609, mating.py:120-126), offspring
+// table, pair midpoints (demography.py:60-72).
+// ========================================================================================
+struct PairScan {
+  Pop pop;
+  Work w;
+  const Counters* cc;
+  int32_t sexed;
+  int32_t fixed_nb;      // > 0: n_births_fixed
+  __device__ int size(const Counters* c) const { return c->n; }
+  __device__ bool keep(int i) const {
+    int m = w.mate[i];
+    if (m < 0) return false;
+    if (sexed) {
+      const int8_t* sx = pop.sex[cc->cur];
+      return sx[i] == 0 && sx[m] == 1;                 // mating.py:41-55
+    }
+    return !(w.mate[m] == i && m < i);                 // mating.py:62-63 (canonical)
+  }
+  __device__ u64 value(int i) const { return keep(i) ? ((u64)1 << 32) : 0; }
+  __device__ void apply(int i, u64 v, u64 ex) const {
+    if (!v) return;
+    const int p = (int)(ex >> 32);
+    const int m = w.mate[i];
+    const int cur = cc->cur;
+    w.pairs[2 * p] = i;
+    w.pairs[2 * p + 1] = m;
+    w.mid_x[p] = (pop.x[cur][i] + pop.x[cur][m]) / 2;     // species.py:640-641
+    w.mid_y[p] = (pop.y[cur][i] + pop.y[cur][m]) / 2;
+    if (fixed_nb > 0) {
+      w.nb[p] = fixed_nb;
+      w.off_start[p] = p * fixed_nb;
+      for (int j = 0; j < fixed_nb; ++j)
+        if ((long long)p * fixed_nb + j < pop.cap) w.off_pair[p * fixed_nb + j] = p;
+    }
+  }
+  __device__ void total(Counters* c, u64 tot) const {
+    int P = (int)(tot >> 32);
+    c->P = P;
+    if (fixed_nb > 0) {
+      long long B = (long long)P * fixed_nb;
+      if (c->n + B > pop.cap) { B = pop.cap - c->n; c->err |= GNX_ERRBIT_CAPACITY; }
+      c->B = (int)B;
+    }
+  }
+};
+
+// Poisson births: second scan over the P pairs
+__global__ void __launch_bounds__(256) k_draw_births(Pop pop, Params prm, DevDraws dr, Work w, const Counters* c) {
+  const int P = c->P, cur = c->cur;
+  for (int p = GTID; p < P; p += GSTRIDE) {
+    int nbv;
+    if (dr.poisson) nbv = dr.poisson[p];
+    else {
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][w.pairs[2 * p]], SITE_BIRTHS, c->t);
+      nbv = sample_poisson(g, prm.c.n_births_lambda);
+    }
+    w.nb[p] = max(nbv, 1);                   // mating.py:125
+  }
+}
+struct BirthScan {
+  Work w;
+  int32_t cap;
+  __device__ int size(const Counters* c) const { return c->P; }
+  __device__ u64 value(int p) const { return (u64)w.nb[p]; }
+  __device__ void apply(int p, u64 v, u64 ex) const {
+    w.off_start[p] = (int)ex;
+    for (int j = 0; j < (int)v; ++j)
+      if ((long long)ex + j < cap) w.off_pair[ex + j] = p;
+  }
+  __device__ void total(Counters* c, u64 tot) const {
+    long long B = (long long)tot;
+    if (c->n + B > cap) { B = cap - c->n; c->err |= GNX_ERRBIT_CAPACITY; }
+    c->B = (int)B;
+  }
+};
+
+// ========================================================================================
+// a9 + a12 + a11 + a8: gamete formation over bit-packed genotypes (mating.py:130-172),
+// newborn phenotype (selection.py:22-48), natal dispersal (movement.py:98-141), newborn
+// record (species.py:638-688, individual.py:100-124).
+//   A group of GW lanes (power of two <= 32) owns one offspring; lane q streams the q-th
+//   128-bit unit of both parents' homologues and of the two cached recombination paths,
+//   forms the two gametes with pure bitwise selects, stores the child's row, and
+//   accumulates the trait-locus dosages that fall in its unit.
+// ========================================================================================
+__device__ __forceinline__ uint4 bitsel(uint4 a0, uint4 a1, uint4 m) {
+  return make_uint4((a0.x & ~m.x) | (a1.x & m.x), (a0.y & ~m.y) | (a1.y & m.y),
+                    (a0.z & ~m.z) | (a1.z & m.z), (a0.w & ~m.w) | (a1.w & m.w));
+}
+__device__ __forceinline__ uint32_t unit_bit(const uint4& v, int bit) {
+  uint32_t wd = (bit >> 5) == 0 ? v.x : (bit >> 5) == 1 ? v.y : (bit >> 5) == 2 ? v.z : v.w;
+  return (wd >> (bit & 31)) & 1u;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// phenotype contribution of one 128-bit unit pair (h0, h1) of trait t
+__device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, int Wq, const uint4& h0,
+                                                const uint4& h1) {
+  const int s = tr.chunk_ptr[t * (Wq + 1) + q], e = tr.chunk_ptr[t * (Wq + 1) + q + 1];
+  double acc = 0.0;
+  for (int k = s; k < e; ++k) {
+    const int bit = tr.te_locus[k] & 127;
+    double geno = 0.5 * (double)(unit_bit(h0, bit) + unit_bit(h1, bit));   // selection.py:30-33
+    if (tr.te_dom) geno = fmin(geno * tr.te_dom[k], 1.0);                    // selection.py:35-39
+    acc += (tr.n_loci[t] > 1) ? geno * tr.te_alpha[k] : geno;               // selection.py:43-47
+  }
+  return acc;
+}
+
+template <int GW>
+__global__ void __launch_bounds__(256) k_make_offspring(Pop pop, Land land, Params prm, Traits tr, DevDraws dr,
+                                                         Work w, const Counters* c) {
+  const int n = c->n, B = c->B, cur = c->cur, n_free = c->n_free, n_slots = c->n_slots;
+  const int64_t t = c->t, max_idx = c->max_idx;
+  const int Wq = pop.Wq, T = pop.T;
+  const int lane = threadIdx.x & (GW - 1);
+  const int ngroups = GSTRIDE / GW;
+  const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << ((threadIdx.x & 31) & ~(GW - 1)));
+  for (int o = GTID / GW; o < B; o += ngroups) {
+    const int p = w.off_pair[o];
+    const int i0 = w.pairs[2 * p], i1 = w.pairs[2 * p + 1];
+    const int64_t oid = max_idx + 1 + o;                               // species.py:614-619
+    const int dst = n + o;
+    int cslot = -1;
+    if (!prm.burn) {
+      cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
+      int k0, k1, h0, h1;
+      RngStream gg(prm.seed_lo, prm.seed_hi, oid, SITE_GAMETE, t);
+      if (dr.recomb_keys) {
+        // mating.py:176-181, 204-209: the pair's key slice is popped from its END
+        const int j = o - w.off_start[p];
+        const int e = 2 * (w.off_start[p] + w.nb[p]);
+        k0 = dr.recomb_keys[e - 1 - 2 * j];
+        k1 = dr.recomb_keys[e - 2 - 2 * j];
+      } else {
+        k0 = (int)choose_k(gg.u32(), prm.n_paths);      // species.py:625-627
+        k1 = (int)choose_k(gg.u32(), prm.n_paths);
+      }
+      if (dr.start_homs) {
+        h0 = dr.start_homs[2 * o];
+        h1 = dr.start_homs[2 * o + 1];
+      } else {
+        uint32_t bits = gg.u32();                        // mating.py:133
+        h0 = bits & 1;
+        h1 = (bits >> 1) & 1;
+      }
+      const uint4* P0 = pop.G + (size_t)pop.gslot[cur][i0] * 2 * Wq;
+      const uint4* P1 = pop.G + (size_t)pop.gslot[cur][i1] * 2 * Wq;
+      const uint4* M0 = prm.paths + (size_t)k0 * Wq;
+      const uint4* M1 = prm.paths + (size_t)k1 * Wq;
+      uint4* C = pop.G + (size_t)cslot * 2 * Wq;
+      const uint32_t f0 = h0 ? 0xffffffffu : 0u, f1 = h1 ? 0xffffffffu : 0u;
+      double zacc[GNX_MAX_TRAITS];
+#pragma unroll
+      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) zacc[tt] = 0.0;
+      for (int q = lane; q < Wq; q += GW) {
+        uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
+        uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
+        uint4 m0 = __ldg(M0 + q), m1 = __ldg(M1 + q);
+        m0 = make_uint4(m0.x ^ f0, m0.y ^ f0, m0.z ^ f0, m0.w ^ f0);
+        m1 = make_uint4(m1.x ^ f1, m1.y ^ f1, m1.z ^ f1, m1.w ^ f1);
+        // gamete_c[l] = g_parent_c[l, path[l] XOR start_c]  (mating.py:161-168)
+        uint4 g0 = bitsel(a0, a1, m0), g1 = bitsel(b0, b1, m1);
+        st_stream(C + q, g0);
+        st_stream(C + Wq + q, g1);
+#pragma unroll
+        for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
+          if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
+      }
+#pragma unroll
+      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) {
+        if (tt < T) {
+          double v = zacc[tt];
+#pragma unroll
+          for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
+          if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + dst] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
+        }
+      }
+    }
+    if (lane == 0) {
+      // ---- natal dispersal (movement.py:98-141)
+      const double mx = w.mid_x[p], my = w.mid_y[p];
+      RngStream g(prm.seed_lo, prm.seed_hi, oid, SITE_DISP, t);
+      double ox = 0.0, oy = 0.0;
+      int tries = 0;
+      const int max_tries = (dr.disp_dist || dr.disp_dir || dr.disp_choice) ? dr.disp_R : 1000;
+      bool ok = false;
+      while (!ok && tries < max_tries) {
+        double cs, sn;
+        if (prm.c.disp_surf_mode == GNX_SURF_TABLE) {
+          int col = dr.disp_choice ? dr.disp_choice[(size_t)o * dr.disp_R + tries]
+                                   : (int)choose_k(g.u32(), prm.c.surf_approx_len);
+          __half h = prm.disp_tab[((size_t)((int)my) * land.X + (int)mx) * prm.c.surf_approx_len + col];
+          sincos_half(h, &sn, &cs);
+        } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
+          double d = surface_direction_onthefly(
+              g, land.rasters + (size_t)prm.c.disp_surf_layer * land.X * land.Y, land.X, land.Y, (int)mx,
+              (int)my, prm.c.disp_surf_mixture, prm.c.disp_surf_kappa);
+          sincos_half(__float2half_rn((float)d), &sn, &cs);
+        } else {
+          // NB reference passes mu=0, kappa=0 whatever the species' params (species.py:650-653)
+          double d = dr.disp_dir ? dr.disp_dir[(size_t)o * dr.disp_R + tries] : sample_vonmises(g, 0.0, 0.0);
+          sincos(d, &sn, &cs);
+        }
+        double dist = dr.disp_dist ? dr.disp_dist[(size_t)o * dr.disp_R + tries]
+                                   : sample_distance(g, prm.c.disp_distr, prm.c.disp_p1, prm.c.disp_p2);
+        double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
+        if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
+        if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
+        ox = clampd(__dadd_rn(mx, dx), 0.0, land.max_x);
+        oy = clampd(__dadd_rn(my, dy), 0.0, land.max_y);
+        ok = (ox > 0.0 && ox < (double)land.X) && (oy > 0.0 && oy < (double)land.Y);
+        tries += 1;
+      }
+      if (!ok) { tries = max_tries + 1; atomicOr((int*)&c->err, GNX_ERRBIT_DRAWS); }
+      if (prm.store_debug) w.disp_tries[o] = tries;
+      // ---- sex (species.py:657-662 + the re-draw quirk of individual.py:110-115)
+      RngStream gs(prm.seed_lo, prm.seed_hi, oid, SITE_SEX, t);
+      int first = 0;
+      if (prm.c.sex) {
+        double u = dr.sex_u ? dr.sex_u[o] : gs.uniform();
+        first = u < prm.c.sex_ratio_p;
+      }
+      int sex = 1;
+      if (!first) {
+        double u = dr.sex_redraw_u ? dr.sex_redraw_u[o] : gs.uniform();
+        sex = u < 0.5;
+      }
+      pop.x[cur][dst] = ox;
+      pop.y[cur][dst] = oy;
+      pop.age[cur][dst] = 0;
+      pop.sex[cur][dst] = (int8_t)sex;
+      pop.idx[cur][dst] = oid;
+      pop.gslot[cur][dst] = cslot;
+    }
+  }
+}
+
+__global__ void k_after_births(Counters* c) {
+  const int B = c->B;
+  c->n_pre = c->n + B;
+  const int nf = c->n_free;
+  if (B <= nf) c->n_free = nf - B;
+  else { c->n_free = 0; c->n_slots += B - nf; }
+}
+
+// phenotype of every live individual from its stored genome (Species._set_z species.py:925;
+// used after upload / genome assignment)
+__global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const Counters* c) {
+  const int n = c->n, cur = c->cur, Wq = pop.Wq, T = pop.T;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const uint4* Gi = pop.G + (size_t)pop.gslot[cur][i] * 2 * Wq;
+    for (int tt = 0; tt < T; ++tt) {
+      double acc = 0.0;
+      for (int q = 0; q < Wq; ++q) {
+        const int s = tr.chunk_ptr[tt * (Wq + 1) + q], e = tr.chunk_ptr[tt * (Wq + 1) + q + 1];
+        if (s == e) continue;
+        uint4 h0 = Gi[q], h1 = Gi[Wq + q];
+        acc += trait_partial(tr, tt, q, Wq, h0, h1);
+      }
+      pop.z[cur][(size_t)tt * pop.cap + i] = (tr.n_loci[tt] > 1) ? 0.5 + acc : acc;
+    }
+  }
+}
+
+// ========================================================================================
+// a10 (counts): _DensityGrid._calc_density spatial.py:73-97.  Four offset coarse grids;
+// cell = (x - edge*ww/2) // ww + edge.  Per-CTA shared-memory histograms, merged with
+// global atomics.
+// ========================================================================================
+#define DENS_SMEM_BINS 4096
+__global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const Counters* c, Dens d, int which) {
+  // which = 0: all individuals alive before mortality; 1: pair midpoints
+  const double* __restrict__ xs = which == 0 ? pop.x[c->cur] : w.mid_x;
+  const double* __restrict__ ys = which == 0 ? pop.y[c->cur] : w.mid_y;
+  __shared__ int hist[DENS_SMEM_BINS];
+  const bool use_smem = d.npts <= DENS_SMEM_BINS;
+  if (use_smem)
+    for (int k = threadIdx.x; k < d.npts; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  const int n = which == 0 ? c->n_pre : c->P;
+  int* gcounts = d.counts + (size_t)which * d.npts;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const double x = xs[i], y = ys[i];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double xc = floordiv_exact(x - d.g_xe[g] * d.ww / 2., d.ww) + d.g_xe[g];
+      double yc = floordiv_exact(y - d.g_ye[g] * d.ww / 2., d.ww) + d.g_ye[g];
+      int a = (int)yc - d.g_i0[g], b = (int)xc - d.g_j0[g];
+      if (a >= 0 && a < d.g_ni[g] && b >= 0 && b < d.g_nj[g]) {
+        int bin = d.g_off[g] + a * d.g_nj[g] + b;
+        if (use_smem) atomicAdd(&hist[bin], 1);
+        else atomicAdd(&gcounts[bin], 1);
+      }
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < d.npts; k += blockDim.x)
+      if (hist[k]) atomicAdd(&gcounts[k], hist[k]);
+  }
+}
+
+// ========================================================================================
+// a10 (interpolation): scipy.interpolate.griddata(method='cubic') spatial.py:144 =
+// Qhull Delaunay (setup) + global gradient estimate + Clough-Tocher patches
+// (scipy/interpolate/interpnd.pyx).
+// ========================================================================================
+// Gradient estimate (`_estimate_gradients_2d_global`): Gauss-Seidel sweeps in vertex order.
+// The 4 offset grids are independent sets of the lattice triangulation, so a sweep is 4
+// fully parallel phases with exactly the sequential algorithm's arithmetic.
+__device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, double* yv, int i) {
+  double Q0 = 0, Q1 = 0, Q3 = 0, s0 = 0, s1 = 0;
+  const double pi0 = d.points[2 * i], pi1 = d.points[2 * i + 1];
+  const double f1 = f[i];
+  for (int jj = d.nbr_indptr[i]; jj < d.nbr_indptr[i + 1]; ++jj) {
+    const int j = d.nbr_indices[jj];
+    const double ex = d.points[2 * j] - pi0, ey = d.points[2 * j + 1] - pi1;
+    const double L = sqrt(ex * ex + ey * ey);
+    const double L3 = L * L * L;
+    const double f2 = f[j];
+    const double df2 = -ex * yv[2 * j] - ey * yv[2 * j + 1];
+    Q0 += 4 * ex * ex / L3;
+    Q1 += 4 * ex * ey / L3;
+    Q3 += 4 * ey * ey / L3;
+    s0 += (6 * (f1 - f2) - 2 * df2) * ex / L3;
+    s1 += (6 * (f1 - f2) - 2 * df2) * ey / L3;
+  }
+  const double Q2 = Q1;
+  const double det = Q0 * Q3 - Q1 * Q2;
+  const double r0 = (Q3 * s0 - Q1 * s1) / det;
+  const double r1 = (-Q2 * s0 + Q0 * s1) / det;
+  double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
+  yv[2 * i] = -r0;
+  yv[2 * i + 1] = -r1;
+  change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
+  return change;
+}
+
+#define GS_BLOCK 512
+__global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, int maxiter, double tol) {
+  // blockIdx.x: 0 = species density N, 1 = pair-midpoint density
+  const int which = blockIdx.x;
+  const int* counts = d.counts + (size_t)which * d.npts;
+  double* f = d.vals + (size_t)which * d.npts;
+  double* yv = d.grad + (size_t)which * d.npts * 2;
+  __shared__ double red[GS_BLOCK / 32];
+  __shared__ double s_err;
+  for (int k = threadIdx.x; k < d.npts; k += blockDim.x) {
+    f[k] = (double)counts[k] / d.areas[k];                 // spatial.py:95
+    yv[2 * k] = 0.0;
+    yv[2 * k + 1] = 0.0;
+  }
+  __syncthreads();
+  int iters = 0;
+  for (int it = 0; it < maxiter; ++it) {
+    double err = 0.0;
+    if (d.colourable) {
+      for (int g = 0; g < 4; ++g) {
+        const int s = d.g_off[g], e = s + d.g_ni[g] * d.g_nj[g];
+        for (int v = s + threadIdx.x; v < e; v += blockDim.x) err = fmax(err, gs_vertex(d, f, yv, v));
+        __syncthreads();
+      }
+    } else {
+      if (threadIdx.x == 0)
+        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex(d, f, yv, v));
+      __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int k = 0; k < GS_BLOCK / 32; ++k) m = fmax(m, red[k]);
+      s_err = m;
+    }
+    __syncthreads();
+    if (s_err < tol) { iters = it + 1; break; }
+  }
+  if (threadIdx.x == 0) {
+    c->gs_iters[which] = iters;
+    if (iters == 0) atomicOr((int*)&c->err, 0);   // scipy only warns; result still used
+  }
+}
+
+// Bezier ordinates of every triangle (`_clough_tocher_2d_single`, point-independent part)
+__global__ void __launch_bounds__(128) k_ct_coefficients(Dens d) {
+  const int total = 2 * d.ntri;
+  for (int id = GTID; id < total; id += GSTRIDE) {
+    const int which = id / d.ntri, t = id - which * d.ntri;
+    const double* f = d.vals + (size_t)which * d.npts;
+    const double* gr = d.grad + (size_t)which * d.npts * 2;
+    const double* P = d.points;
+    const int v0 = d.simplices[3 * t], v1 = d.simplices[3 * t + 1], v2 = d.simplices[3 * t + 2];
+    const double e12x = P[2 * v1] - P[2 * v0], e12y = P[2 * v1 + 1] - P[2 * v0 + 1];
+    const double e23x = P[2 * v2] - P[2 * v1], e23y = P[2 * v2 + 1] - P[2 * v1 + 1];
+    const double e31x = P[2 * v0] - P[2 * v2], e31y = P[2 * v0 + 1] - P[2 * v2 + 1];
+    const double f1 = f[v0], f2 = f[v1], f3 = f[v2];
+    const double df12 = +(gr[2 * v0] * e12x + gr[2 * v0 + 1] * e12y);
+    const double df21 = -(gr[2 * v1] * e12x + gr[2 * v1 + 1] * e12y);
+    const double df23 = +(gr[2 * v1] * e23x + gr[2 * v1 + 1] * e23y);
+    const double df32 = -(gr[2 * v2] * e23x + gr[2 * v2 + 1] * e23y);
+    const double df31 = +(gr[2 * v2] * e31x + gr[2 * v2 + 1] * e31y);
+    const double df13 = -(gr[2 * v0] * e31x + gr[2 * v0 + 1] * e31y);
+    const double c3000 = f1;
+    const double c2100 = (df12 + 3 * c3000) / 3;
+    const double c2010 = (df13 + 3 * c3000) / 3;
+    const double c0300 = f2;
+    const double c1200 = (df21 + 3 * c0300) / 3;
+    const double c0210 = (df23 + 3 * c0300) / 3;
+    const double c0030 = f3;
+    const double c1020 = (df31 + 3 * c0030) / 3;
+    const double c0120 = (df32 + 3 * c0030) / 3;
+    const double c2001 = (c2100 + c2010 + c3000) / 3;
+    const double c0201 = (c1200 + c0300 + c0210) / 3;
+    const double c0021 = (c1020 + c0120 + c0030) / 3;
+    // barycentric transform of this triangle: b = Ainv (p - v2)
+    const double a00 = P[2 * v0] - P[2 * v2], a01 = P[2 * v1] - P[2 * v2];
+    const double a10 = P[2 * v0 + 1] - P[2 * v2 + 1], a11 = P[2 * v1 + 1] - P[2 * v2 + 1];
+    const double det = a00 * a11 - a01 * a10;
+    double g[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int itri = d.neighbors[3 * t + k];
+      if (itri == -1) { g[k] = -0.5; continue; }
+      const int w0 = d.simplices[3 * itri], w1 = d.simplices[3 * itri + 1], w2 = d.simplices[3 * itri + 2];
+      const double y0 = (P[2 * w0] + P[2 * w1] + P[2 * w2]) / 3;
+      const double y1 = (P[2 * w0 + 1] + P[2 * w1 + 1] + P[2 * w2 + 1]) / 3;
+      const double dx = y0 - P[2 * v2], dy = y1 - P[2 * v2 + 1];
+      double cc[3];
+      cc[0] = (a11 * dx - a01 * dy) / det;
+      cc[1] = (-a10 * dx + a00 * dy) / det;
+      cc[2] = 1 - cc[0] - cc[1];
+      if (k == 0) g[k] = (2 * cc[2] + cc[1] - 1) / (2 - 3 * cc[2] - 3 * cc[1]);
+      else if (k == 1) g[k] = (2 * cc[0] + cc[2] - 1) / (2 - 3 * cc[0] - 3 * cc[2]);
+      else g[k] = (2 * cc[1] + cc[0] - 1) / (2 - 3 * cc[1] - 3 * cc[0]);
+    }
+    const double c0111 = (g[0] * (-c0300 + 3 * c0210 - 3 * c0120 + c0030) + (-c0300 + 2 * c0210 - c0120 + c0021 + c0201)) / 2;
+    const double c1011 = (g[1] * (-c0030 + 3 * c1020 - 3 * c2010 + c3000) + (-c0030 + 2 * c1020 - c2010 + c2001 + c0021)) / 2;
+    const double c1101 = (g[2] * (-c3000 + 3 * c2100 - 3 * c1200 + c0300) + (-c3000 + 2 * c2100 - c1200 + c2001 + c0201)) / 2;
+    const double c1002 = (c1101 + c1011 + c2001) / 3;
+    const double c0102 = (c1101 + c0111 + c0201) / 3;
+    const double c0012 = (c1011 + c0111 + c0021) / 3;
+    const double c0003 = (c1002 + c0102 + c0012) / 3;
+    double* o = d.coef + ((size_t)which * d.ntri + t) * 19;
+    o[0] = c3000; o[1] = c0300; o[2] = c0030; o[3] = c0003; o[4] = c2100; o[5] = c2010; o[6] = c2001;
+    o[7] = c0210; o[8] = c0201; o[9] = c0021; o[10] = c1200; o[11] = c1020; o[12] = c1002; o[13] = c0120;
+    o[14] = c0102; o[15] = c0012; o[16] = c1101; o[17] = c1011; o[18] = c0111;
+  }
+}
+
+// point-dependent part of `_clough_tocher_2d_single` at (qi, qj)
+__device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double qi, double qj) {
+  int si = (int)floor(qi / d.hww), sj = (int)floor(qj / d.hww);
+  si = min(max(si, 0), d.lat_ni - 2);
+  sj = min(max(sj, 0), d.lat_nj - 2);
+  const int* st = d.square_tri + 2 * (si * (d.lat_nj - 1) + sj);
+  const double* P = d.points;
+  int t = st[0];
+  double b0, b1, b2;
+  for (int k = 0; k < 2; ++k) {
+    t = st[k];
+    const int v0 = d.simplices[3 * t], v1 = d.simplices[3 * t + 1], v2 = d.simplices[3 * t + 2];
+    const double a00 = P[2 * v0] - P[2 * v2], a01 = P[2 * v1] - P[2 * v2];
+    const double a10 = P[2 * v0 + 1] - P[2 * v2 + 1], a11 = P[2 * v1 + 1] - P[2 * v2 + 1];
+    const double det = a00 * a11 - a01 * a10;
+    const double dx = qi - P[2 * v2], dy = qj - P[2 * v2 + 1];
+    b0 = (a11 * dx - a01 * dy) / det;
+    b1 = (-a10 * dx + a00 * dy) / det;
+    b2 = 1 - b0 - b1;
+    if (fmin(b0, fmin(b1, b2)) >= -1e-12 || k == 1) break;
+  }
+  const double* cf = d.coef + ((size_t)which * d.ntri + t) * 19;
+  const double minval = fmin(b0, fmin(b1, b2));
+  const double B1 = b0 - minval, B2 = b1 - minval, B3 = b2 - minval, B4 = 3 * minval;
+  const double c3000 = cf[0], c0300 = cf[1], c0030 = cf[2], c0003 = cf[3], c2100 = cf[4], c2010 = cf[5],
+               c2001 = cf[6], c0210 = cf[7], c0201 = cf[8], c0021 = cf[9], c1200 = cf[10], c1020 = cf[11],
+               c1002 = cf[12], c0120 = cf[13], c0102 = cf[14], c0012 = cf[15], c1101 = cf[16], c1011 = cf[17],
+               c0111 = cf[18];
+  return (B1 * B1 * B1 * c3000 + 3 * B1 * B1 * B2 * c2100 + 3 * B1 * B1 * B3 * c2010 + 3 * B1 * B1 * B4 * c2001 +
+          3 * B1 * B2 * B2 * c1200 + 6 * B1 * B2 * B4 * c1101 + 3 * B1 * B3 * B3 * c1020 + 6 * B1 * B3 * B4 * c1011 +
+          3 * B1 * B4 * B4 * c1002 + B2 * B2 * B2 * c0300 + 3 * B2 * B2 * B3 * c0210 + 3 * B2 * B2 * B4 * c0201 +
+          3 * B2 * B3 * B3 * c0120 + 6 * B2 * B3 * B4 * c0111 + 3 * B2 * B4 * B4 * c0102 + B3 * B3 * B3 * c0030 +
+          3 * B3 * B3 * B4 * c0021 + 3 * B3 * B4 * B4 * c0012 + B4 * B4 * B4 * c0003);
+}
+
+// N raster (Species._calc_density species.py:845-882, clip >= 0) + its maximum
+__global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Counters* c) {
+  const int ncell = land.X * land.Y;
+  double mx = 0.0;
+  for (int id = GTID; id < ncell; id += GSTRIDE) {
+    const int i = id / land.X, j = id - i * land.X;
+    double v = ct_eval_point(d, 0, i + 0.5, j + 0.5);
+    v = v < 0.0 ? 0.0 : v;                    // np.clip(dens, a_min=0)
+    w.N_rast[id] = v;
+    mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&c->nmax_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+// a7 + a14: n_pairs raster (demography.py:60-91) and the logistic d raster
+// (demography.py:104-172), never materialising dNdt / N_b / N_d.
+__global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c) {
+  const int ncell = land.X * land.Y;
+  const double Nmax = __longlong_as_double((long long)c->nmax_bits);
+  const double R = prm.c.R, b = prm.c.b, lam = prm.c.n_births_lambda;
+  for (int id = GTID; id < ncell; id += GSTRIDE) {
+    const int i = id / land.X, j = id - i * land.X;
+    double np = ct_eval_point(d, 1, i + 0.5, j + 0.5);
+    np = np < 0.0 ? 0.0 : np;
+    if (isnan(np)) np = 0.0;
+    if (prm.store_debug) w.NP_rast[id] = np;
+    const double N = w.N_rast[id], K = land.K[id];
+    double dNdt = R * (1 - (N / K)) * N;              // demography.py:95-97
+    if (dNdt < -Nmax) dNdt = -Nmax;                   // np.clip(a_min=-N.max())
+    if (isnan(dNdt) || isinf(dNdt)) dNdt = -Nmax;
+    const double N_b = b * lam * np;                  // demography.py:142
+    const double N_d = N_b - dNdt;                    // demography.py:149
+    double dv = N_d / N;                              // demography.py:159-160
+    if (isnan(dv)) dv = 0.0;
+    dv = dv < prm.c.d_min ? prm.c.d_min : (dv > prm.c.d_max ? prm.c.d_max : dv);
+    w.d_rast[id] = dv;
+  }
+}
+
+// ========================================================================================
+// a3 + a15 + a16 (draw): environment gather (species.py:913-922), fitness
+// (selection.py:51-112), death probability (selection.py:119-125, demography.py:306-321),
+// Bernoulli mortality draw (demography.py:175-176).
+// ========================================================================================
+__global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
+                                                const Counters* c) {
+  const int n = c->n_pre, cur = c->cur, T = pop.T;
+  const int64_t t = c->t;
+  const size_t plane = (size_t)land.X * land.Y;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const double x = pop.x[cur][i], y = pop.y[cur][i];
+    const int cx = (int)x, cy = (int)y;
+    const size_t cell = (size_t)cy * land.X + cx;
+    double p = w.d_rast[cell];                                   // demography.py:306
+    if (prm.selection) {
+      double wfit = 1.0;
+      for (int tt = 0; tt < T; ++tt) {
+        const double e = tr.univ_adv[tt] ? 1.0 : __ldg(&land.rasters[(size_t)tr.layer[tt] * plane + cell]);
+        const double z = pop.z[cur][(size_t)tt * pop.cap + i];
+        const double phi = tr.phi_rast[tt] ? __ldg(&tr.phi_rast[tt][cell]) : tr.phi[tt];
+        const double diff = fabs(e - z);
+        const double gm = tr.gamma[tt];
+        const double pw = gm == 1.0 ? diff : (gm == 2.0 ? diff * diff : pow(diff, gm));
+        wfit *= 1 - phi * pw;                                     // selection.py:51-54
+      }
+      if (T > 0) wfit = wfit < 0.001 ? 0.001 : wfit;             // selection.py:74
+      pop.fit[cur][i] = wfit;
+      p = 1 - (1 - p) * wfit;                                     // selection.py:122
+    }
+    if (prm.c.max_age >= 0 && pop.age[cur][i] > prm.c.max_age) p = 1.0;    // demography.py:319-321
+    if (prm.store_debug) w.death_p[i] = p;
+    double u;
+    if (dr.death_u) u = dr.death_u[i];
+    else {
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_DEATH, t);
+      u = g.uniform();
+    }
+    w.alive[i] = !(u < p);
+  }
+}
+
+// a16 (removal): stable compaction of survivors into the other half of the SoA; the dead
+// hand their genome slots back to the free list (no genome bytes move).
+struct MortalityScan {
+  Pop pop;
+  Work w;
+  const Counters* cc;
+  int32_t burn;
+  __device__ int size(const Counters* c) const { return c->n_pre; }
+  __device__ u64 value(int i) const { return w.alive[i] ? ((u64)1 << 32) : (u64)1; }
+  __device__ void apply(int i, u64 v, u64 ex) const {
+    const int s = cc->cur, d = s ^ 1;
+    if (v >> 32) {
+      const int dst = (int)(ex >> 32);
+      pop.x[d][dst] = pop.x[s][i];
+      pop.y[d][dst] = pop.y[s][i];
+      pop.age[d][dst] = pop.age[s][i];
+      pop.sex[d][dst] = pop.sex[s][i];
+      pop.idx[d][dst] = pop.idx[s][i];
+      pop.gslot[d][dst] = pop.gslot[s][i];
+      pop.fit[d][dst] = pop.fit[s][i];
+      for (int tt = 0; tt < pop.T; ++tt)
+        pop.z[d][(size_t)tt * pop.cap + dst] = pop.z[s][(size_t)tt * pop.cap + i];
+    } else if (!burn) {
+      // n_free was already lowered by this step's births (k_after_births)
+      pop.free_slots[cc->n_free + (int)(ex & 0xffffffffu)] = pop.gslot[s][i];
+    }
+  }
+  __device__ void total(Counters* c, u64 tot) const {
+    // spine runs before apply: stash totals where apply does not read them
+    c->deaths = (int)(tot & 0xffffffffu);
+    c->pad[0] = (int)(tot >> 32);          // survivors
+  }
+};
+
+__global__ void k_end_step(Counters* c, Work w, int burn) {
+  const int survivors = c->pad[0];
+  gnx_step_record_t r;
+  r.t = c->t;
+  r.Nt = survivors;
+  r.n_births = c->B;
+  r.n_deaths = c->deaths;
+  r.n_pairs = c->P;
+  if (c->n_rec < w.max_records) w.records[c->n_rec] = r;
+  c->n_rec += 1;
+  if (!burn) c->n_free += c->deaths;
+  c->n = survivors;
+  c->n_pre = survivors;
+  c->max_idx += c->B;
+  c->cur ^= 1;
+  c->t += 1;
+  c->P = 0;
+  c->B = 0;
+  c->deaths = 0;
+  c->nmax_bits = 0ull;
+}
+
+// environment values for every live individual (API view of ind.e, species.py:913-922)
+__global__ void __launch_bounds__(256) k_sample_env(Pop pop, Land land, Work w, const Counters* c) {
+  const int n = c->n, cur = c->cur;
+  const size_t plane = (size_t)land.X * land.Y;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const size_t cell = (size_t)((int)pop.y[cur][i]) * land.X + (int)pop.x[cur][i];
+    for (int l = 0; l < land.n_layers; ++l) w.e_out[(size_t)i * land.n_layers + l] = land.rasters[l * plane + cell];
+  }
+}
+
+// genome rows gathered into species order (download) / scattered from it (upload)
+__global__ void __launch_bounds__(256) k_gather_genomes(Pop pop, uint4* out, const Counters* c) {
+  const int n = c->n, cur = c->cur, row = 2 * pop.Wq;
+  const long long total = (long long)n * row;
+  for (long long k = GTID; k < total; k += GSTRIDE) {
+    const int i = (int)(k / row), q = (int)(k - (long long)i * row);
+    out[k] = pop.G[(size_t)pop.gslot[cur][i] * row + q];
+  }
+}
+
+__global__ void k_K_from_layer(const double* rast, double* K, double factor, int ncell) {
+  for (int id = GTID; id < ncell; id += GSTRIDE) K[id] = rast[id] * factor;   // species.py:546-547
+}

@@ -1,0 +1,102 @@
+// gnx_scan.cuh -- device-wide exclusive scan of packed (hi, lo) u32 pairs, sized from
+// device-resident counters (no host round trip).  Three launches: per-tile reduce,
+// single-CTA spine, per-tile apply.  The functor supplies:
+//   int  size(const Counters*)                     number of elements
+//   u64  value(int i)                              packed (hi << 32 | lo) contribution
+//   void apply(int i, u64 value, u64 exclusive)    consume the exclusive prefix
+//   void total(Counters*, u64 total)               called once by the spine
+#pragma once
+#include "gnx_common.cuh"
+
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 warp_incl_scan(u64 v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u64 o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// exclusive scan across the block of one value per thread; returns exclusive prefix and the
+// block total through *total.
+__device__ __forceinline__ u64 block_excl_scan(u64 v, u64* total) {
+  __shared__ u64 warp_tot[SCAN_BLOCK / 32];
+  __shared__ u64 blk_tot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u64 inc = warp_incl_scan(v);
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    u64 t = lane < SCAN_BLOCK / 32 ? warp_tot[lane] : 0;
+    u64 ti = warp_incl_scan(t);
+    if (lane < SCAN_BLOCK / 32) warp_tot[lane] = ti - t;
+    if (lane == SCAN_BLOCK / 32 - 1) blk_tot = ti;
+  }
+  __syncthreads();
+  u64 excl = inc - v + warp_tot[w];
+  *total = blk_tot;
+  __syncthreads();
+  return excl;
+}
+
+template <class F>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Counters* c, u64* tile_sums) {
+  const int n = f.size(c);
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+      if (base + k < n) s += f.value(base + k);
+    u64 tot;
+    block_excl_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sums[tile] = tot;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_spine_kernel(F f, Counters* c, u64* tile_sums) {
+  const int n = f.size(c);
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  u64 carry = 0;
+  for (int base = 0; base < ntiles; base += SCAN_BLOCK) {
+    const int i = base + threadIdx.x;
+    u64 v = i < ntiles ? tile_sums[i] : 0;
+    u64 tot;
+    u64 ex = block_excl_scan(v, &tot);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) f.total(c, carry);
+}
+
+template <class F>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(F f, const Counters* c, const u64* tile_sums) {
+  const int n = f.size(c);
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    u64 v[SCAN_ITEMS];
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      v[k] = (base + k < n) ? f.value(base + k) : 0;
+      s += v[k];
+    }
+    u64 tot;
+    u64 ex = block_excl_scan(s, &tot) + tile_sums[tile];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      if (base + k < n) f.apply(base + k, v[k], ex);
+      ex += v[k];
+    }
+  }
+}

@@ -1,0 +1,366 @@
+"""DeviceSpecies: the structure-of-arrays, HBM-resident state of one Species plus the calls
+that advance it, bound to libgnxb200.so through ctypes (include/gnx_b200.h).
+
+This is the thin host layer between the reference-shaped API objects
+(geonomics_b200.api: Species / Landscape / GenomicArchitecture / Model) and the CUDA
+kernels.  All per-timestep arithmetic happens in the shared library; nothing here computes
+on the CPU, and constructing a DeviceSpecies without the library or without a CUDA device
+raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .density import DensityGridSetup
+from . import genome_pack as gp
+
+_DT = {
+    'X': np.float64, 'Y': np.float64, 'AGE': np.int32, 'SEX': np.int8, 'IDX': np.int64, 'FIT': np.float64,
+    'GSLOT': np.int32, 'N_NBRS': np.int32, 'MATE': np.int32, 'PAIRS': np.int32, 'NB': np.int32,
+    'PERM': np.int32, 'CELL_START': np.uint32, 'COUNTS_N': np.int32, 'COUNTS_P': np.int32,
+    'VALS_N': np.float64, 'VALS_P': np.float64, 'GRAD_N': np.float64, 'GRAD_P': np.float64,
+    'N_RAST': np.float64, 'NPAIRS_RAST': np.float64, 'D_RAST': np.float64, 'K_RAST': np.float64,
+    'DEATH_P': np.float64, 'ALIVE': np.uint8, 'DISP_TRIES': np.int32, 'E': np.float64, 'Z': np.float64,
+    'COUNTERS': np.int32, 'GENOMES': np.uint32,
+}
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+class DeviceSpecies:
+    """One Species resident on the GPU.
+
+    Parameters mirror what the reference's ops read off `Species`, `Landscape` and
+    `GenomicArchitecture`:
+
+    land_dim : (dim_x, dim_y)                       landscape.py:245
+    rasters  : float64[n_layers, dim_y, dim_x]      land[l].rast
+    prm      : dict with b, R, lam, n_births_fixed, mating_radius, d_min, d_max, sex,
+               sex_ratio_p, max_age, K_layer, K_factor, move, move_distr (name, p1, p2),
+               disp_distr (name, p1, p2), direction_mu, direction_kappa, choose_nearest,
+               inverse_dist, density_grid_window_width, move_surf / disp_surf (dicts or None)
+    gen_arch : dict with L, paths (uint8[n_paths, L]), traits (list of dicts loci/alpha/phi/
+               gamma/lyr_num/univ_adv), dom (int8[L])   or None (no genomes)
+    """
+
+    def __init__(self, land_dim, rasters, prm, gen_arch=None, capacity=None, seed=0,
+                 disp_tries_injected=6, res_ratio=(1.0, 1.0)):
+        L = _lib.lib()
+        self._L = L
+        self.land_dim = (int(land_dim[0]), int(land_dim[1]))
+        rasters = np.ascontiguousarray(rasters, dtype=np.float64)
+        assert rasters.ndim == 3 and rasters.shape[1:] == (self.land_dim[1], self.land_dim[0]), \
+            'rasters must be [n_layers, dim_y, dim_x]'
+        self.n_layers = rasters.shape[0]
+        self.prm = dict(prm)
+        self.gen_arch = gen_arch
+        traits = (gen_arch or {}).get('traits') or []
+        self.n_traits = len(traits)
+        self.Lg = int(gen_arch['L']) if gen_arch is not None else 0
+        self.W = gp.words_per_hap(self.Lg)
+        if capacity is None:
+            ksum = float(np.sum(rasters[int(prm.get('K_layer', 0))]) * float(prm.get('K_factor', 1.0)))
+            capacity = int(max(4096, 3.0 * ksum))
+        self.capacity = int(capacity)
+
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.GNX_ABI_VERSION
+        cfg.dim_x, cfg.dim_y = self.land_dim
+        cfg.n_layers = self.n_layers
+        cfg.capacity = self.capacity
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.L = self.Lg
+        cfg.n_recomb_paths = int(len(gen_arch['paths'])) if gen_arch is not None else 0
+        cfg.n_traits = self.n_traits
+        dom = None
+        if gen_arch is not None and gen_arch.get('dom') is not None and np.any(gen_arch['dom']):
+            dom = np.ascontiguousarray(gen_arch['dom'], dtype=np.int8)
+        cfg.use_dom = int(dom is not None)
+        mr = prm.get('mating_radius')
+        cfg.mating_radius = -1.0 if mr is None else float(mr)
+        cfg.b = float(prm['b'])
+        cfg.R = float(prm['R'])
+        cfg.n_births_lambda = float(prm['lam'])
+        cfg.n_births_fixed = int(bool(prm['n_births_fixed']))
+        cfg.sex = int(bool(prm.get('sex', False)))
+        cfg.sex_ratio_p = float(prm.get('sex_ratio_p', 0.5))
+        cfg.choose_nearest = int(bool(prm.get('choose_nearest', False)))
+        cfg.inverse_dist = int(bool(prm.get('inverse_dist', False)))
+        cfg.d_min = float(prm.get('d_min', 0.0))
+        cfg.d_max = float(prm.get('d_max', 1.0))
+        cfg.max_age = -1 if prm.get('max_age') is None else int(prm['max_age'])
+        cfg.K_layer = int(prm.get('K_layer', 0))
+        cfg.K_factor = float(prm.get('K_factor', 1.0))
+        cfg.move = int(bool(prm.get('move', True)))
+        mname, mp1, mp2 = prm.get('move_distr', ('wald', 1.0, 1.0))
+        dname, dp1, dp2 = prm.get('disp_distr', ('wald', 1.0, 1.0))
+        cfg.move_distr = _lib.DISTR[mname]
+        cfg.disp_distr = _lib.DISTR[dname]
+        cfg.move_p1, cfg.move_p2, cfg.disp_p1, cfg.disp_p2 = float(mp1), float(mp2), float(dp1), float(dp2)
+        cfg.dir_mu = float(prm.get('direction_mu', 0.0))
+        cfg.dir_kappa = float(prm.get('direction_kappa', 0.0))
+        cfg.res_ratio_x, cfg.res_ratio_y = float(res_ratio[0]), float(res_ratio[1])
+        self._surf_tabs = [None, None]
+        approx_len = 0
+        for k, (name, pre) in enumerate((('move_surf', 'move'), ('disp_surf', 'disp'))):
+            s = prm.get(name)
+            mode = _lib.SURF_NONE
+            if s is not None:
+                if s.get('table') is not None:
+                    mode = _lib.SURF_TABLE
+                    tab = np.ascontiguousarray(s['table'], dtype=np.float16)
+                    assert tab.shape[:2] == (self.land_dim[1], self.land_dim[0])
+                    assert approx_len in (0, tab.shape[2]), 'surface tables must share approx_len'
+                    approx_len = tab.shape[2]
+                    self._surf_tabs[k] = tab
+                else:
+                    mode = _lib.SURF_ONTHEFLY
+                setattr(cfg, pre + '_surf_layer', int(s.get('layer', 0)))
+                setattr(cfg, pre + '_surf_mixture', int(bool(s.get('mixture', True))))
+                setattr(cfg, pre + '_surf_kappa', float(s.get('kappa', 12.0)))
+            setattr(cfg, pre + '_surf_mode', mode)
+        cfg.surf_approx_len = approx_len
+        cfg.disp_max_tries_injected = int(disp_tries_injected)
+        self.disp_R = int(disp_tries_injected)
+        self._cfg = cfg
+
+        self._ctx = C.c_void_p()
+        _lib.check(L.gnx_create(C.byref(cfg), C.byref(self._ctx)), 'gnx_create')
+        _lib.check(L.gnx_set_rasters(self._ctx, _ptr(rasters, _lib.c_double_p)), 'gnx_set_rasters')
+        self._rasters_host = rasters
+
+        self.density = DensityGridSetup(self.land_dim, prm.get('density_grid_window_width'))
+        dstruct = self.density.to_struct()
+        _lib.check(L.gnx_set_density(self._ctx, C.byref(dstruct)), 'gnx_set_density')
+
+        if gen_arch is not None:
+            packed = gp.pack_paths(gen_arch['paths'])
+            _lib.check(L.gnx_set_recomb_paths(self._ctx, _ptr(packed, _lib.c_uint32_p)), 'gnx_set_recomb_paths')
+            self.set_traits(traits, dom)
+        if self._surf_tabs[0] is not None or self._surf_tabs[1] is not None:
+            mv = None if self._surf_tabs[0] is None else self._surf_tabs[0].view(np.uint16)
+            dv = None if self._surf_tabs[1] is None else self._surf_tabs[1].view(np.uint16)
+            _lib.check(L.gnx_set_surface_tables(self._ctx, _ptr(mv, _lib.c_uint16_p), _ptr(dv, _lib.c_uint16_p)),
+                       'gnx_set_surface_tables')
+        self._keep = []
+
+    # ---- setup -----------------------------------------------------------------------
+    def set_traits(self, traits, dom=None):
+        arr = (_lib.Trait * max(1, len(traits)))()
+        keep = []
+        for t, tr in enumerate(traits):
+            loci = np.ascontiguousarray(tr['loci'], dtype=np.int32)
+            alpha = np.ascontiguousarray(tr['alpha'], dtype=np.float64)
+            keep += [loci, alpha]
+            arr[t].n_loci = len(loci)
+            arr[t].host_loci = _ptr(loci, _lib.c_int32_p)
+            arr[t].host_alpha = _ptr(alpha, _lib.c_double_p)
+            phi = tr['phi']
+            if np.ndim(phi) == 2:
+                ph = np.ascontiguousarray(phi, dtype=np.float64)
+                keep.append(ph)
+                arr[t].host_phi_raster = _ptr(ph, _lib.c_double_p)
+                arr[t].phi = 0.0
+            else:
+                arr[t].host_phi_raster = None
+                arr[t].phi = float(phi)
+            arr[t].gamma = float(tr['gamma'])
+            arr[t].layer = int(tr['lyr_num'])
+            arr[t].univ_adv = int(bool(tr['univ_adv']))
+        _lib.check(self._L.gnx_set_traits(self._ctx, len(traits), arr, _ptr(dom, _lib.c_int8_p)),
+                   'gnx_set_traits')
+
+    def set_burn(self, burn):
+        _lib.check(self._L.gnx_set_burn(self._ctx, int(bool(burn))), 'gnx_set_burn')
+
+    def set_raster(self, layer, rast):
+        """Landscape._set_raster (landscape.py:353) for an environmental-change event."""
+        r = np.ascontiguousarray(rast, dtype=np.float64)
+        assert r.shape == (self.land_dim[1], self.land_dim[0])
+        _lib.check(self._L.gnx_set_raster(self._ctx, int(layer), _ptr(r, _lib.c_double_p)), 'gnx_set_raster')
+
+    def set_draws(self, draws):
+        """Inject replayed random draws (dict of arrays, see gnx_draws_t) or None for Philox."""
+        if draws is None:
+            _lib.check(self._L.gnx_set_draws(self._ctx, None), 'gnx_set_draws')
+            return
+        d = _lib.Draws()
+        keep = []
+        n = None
+
+        def put(name, key, dtype, typ, width=1):
+            nonlocal n
+            a = draws.get(key)
+            if a is None:
+                return
+            a = np.ascontiguousarray(a, dtype=dtype)
+            rows = a.size // width
+            n = rows if n is None else min(n, rows)
+            keep.append(a)
+            setattr(d, name, _ptr(a, typ))
+        R = self.disp_R
+        put('move_dir', 'move_dir', np.float64, _lib.c_double_p)
+        put('move_choice', 'move_choice', np.int32, _lib.c_int32_p)
+        put('move_dist', 'move_dist', np.float64, _lib.c_double_p)
+        put('mate_R', 'mate_R', np.uint32, _lib.c_uint32_p)
+        put('mate_inv_u', 'mate_inv_u', np.float64, _lib.c_double_p)
+        put('mate_u', 'mate_u', np.float64, _lib.c_double_p)
+        put('poisson', 'poisson', np.int32, _lib.c_int32_p)
+        put('recomb_keys', 'recomb_keys', np.int32, _lib.c_int32_p, 2)
+        put('start_homs', 'start_homs', np.int32, _lib.c_int32_p, 2)
+        for key in ('disp_dir', 'disp_choice', 'disp_dist'):
+            a = draws.get(key)
+            if a is not None:
+                assert np.asarray(a).shape[1] == R, '%s must have %d columns' % (key, R)
+        put('disp_dir', 'disp_dir', np.float64, _lib.c_double_p, R)
+        put('disp_choice', 'disp_choice', np.int32, _lib.c_int32_p, R)
+        put('disp_dist', 'disp_dist', np.float64, _lib.c_double_p, R)
+        put('sex_u', 'sex_u', np.float64, _lib.c_double_p)
+        put('sex_redraw_u', 'sex_redraw_u', np.float64, _lib.c_double_p)
+        put('death_u', 'death_u', np.float64, _lib.c_double_p)
+        d.n = int(n or 0)
+        _lib.check(self._L.gnx_set_draws(self._ctx, C.byref(d)), 'gnx_set_draws')
+
+    # ---- population in / out ---------------------------------------------------------------
+    def _pop_struct(self, bufs):
+        p = _lib.Population()
+        p.n = int(bufs.get('n', 0))
+        p.x = _ptr(bufs.get('x'), _lib.c_double_p)
+        p.y = _ptr(bufs.get('y'), _lib.c_double_p)
+        p.age = _ptr(bufs.get('age'), _lib.c_int32_p)
+        p.sex = _ptr(bufs.get('sex'), _lib.c_int8_p)
+        p.idx = _ptr(bufs.get('idx'), _lib.c_int64_p)
+        p.genomes = _ptr(bufs.get('genomes'), _lib.c_uint32_p)
+        p.z = _ptr(bufs.get('z'), _lib.c_double_p)
+        p.fit = _ptr(bufs.get('fit'), _lib.c_double_p)
+        p.e = _ptr(bufs.get('e'), _lib.c_double_p)
+        p.max_ind_idx = int(bufs.get('max_ind_idx', -1))
+        return p
+
+    def upload(self, x, y, age=None, sex=None, idx=None, g=None, z=None, max_ind_idx=None,
+               genomes_packed=None):
+        """Upload a population in species order.  g: int8[N, L, 2] (reference layout) or
+        genomes_packed: u32[N, 2, W]."""
+        n = len(x)
+        bufs = dict(n=n, x=np.ascontiguousarray(x, dtype=np.float64), y=np.ascontiguousarray(y, dtype=np.float64))
+        if age is not None:
+            bufs['age'] = np.ascontiguousarray(age, dtype=np.int32)
+        if sex is not None:
+            bufs['sex'] = np.ascontiguousarray(sex, dtype=np.int8)
+        if idx is not None:
+            bufs['idx'] = np.ascontiguousarray(idx, dtype=np.int64)
+        if genomes_packed is None and g is not None:
+            genomes_packed = gp.pack_genomes(g)
+        if genomes_packed is not None:
+            gpk = np.ascontiguousarray(genomes_packed, dtype=np.uint32)
+            assert gpk.shape == (n, 2, self.W), (gpk.shape, (n, 2, self.W))
+            bufs['genomes'] = gpk
+        if z is not None and self.n_traits:
+            bufs['z'] = np.ascontiguousarray(z, dtype=np.float64).reshape(n, self.n_traits)
+        if max_ind_idx is None:
+            max_ind_idx = int(np.max(idx)) if idx is not None and n else n - 1
+        bufs['max_ind_idx'] = max_ind_idx
+        p = self._pop_struct(bufs)
+        _lib.check(self._L.gnx_upload_population(self._ctx, C.byref(p)), 'gnx_upload_population')
+
+    def population_size(self):
+        n = C.c_int64()
+        _lib.check(self._L.gnx_population_size(self._ctx, C.byref(n)), 'gnx_population_size')
+        return int(n.value)
+
+    def download(self, genomes=True, unpack=True, e=False):
+        n = self.population_size()
+        bufs = dict(n=n, x=np.empty(n), y=np.empty(n), age=np.empty(n, np.int32), sex=np.empty(n, np.int8),
+                    idx=np.empty(n, np.int64), fit=np.empty(n))
+        if self.n_traits:
+            bufs['z'] = np.empty((n, self.n_traits))
+        if genomes and self.gen_arch is not None:
+            bufs['genomes'] = np.empty((n, 2, self.W), np.uint32)
+        if e:
+            bufs['e'] = np.empty((n, self.n_layers))
+        p = self._pop_struct(bufs)
+        _lib.check(self._L.gnx_download_population(self._ctx, C.byref(p)), 'gnx_download_population')
+        out = {k: v for k, v in bufs.items() if k != 'n'}
+        out['max_ind_idx'] = int(p.max_ind_idx)
+        if 'genomes' in out and unpack:
+            out['g'] = gp.unpack_genomes(out['genomes'], self.Lg)
+        return out
+
+    def walk_host(self, bufs, n_steps):
+        """gnx_walk_host: host buffers in, n_steps on the device, host buffers out."""
+        p = self._pop_struct(bufs)
+        _lib.check(self._L.gnx_walk_host(self._ctx, C.byref(p), int(n_steps)), 'gnx_walk_host')
+        bufs['n'] = int(p.n)
+        bufs['max_ind_idx'] = int(p.max_ind_idx)
+        return bufs
+
+    # ---- stepping ------------------------------------------------------------------------
+    def step(self, n_steps=1, sync=False):
+        _lib.check(self._L.gnx_step(self._ctx, int(n_steps)), 'gnx_step')
+        if sync:
+            self.sync()
+
+    def sync(self):
+        _lib.check(self._L.gnx_sync(self._ctx), 'gnx_sync')
+
+    def stage(self, name):
+        fn = getattr(self._L, 'gnx_' + name)
+        _lib.check(fn(self._ctx), 'gnx_' + name)
+
+    def step_records(self, max_records=1 << 16):
+        arr = (_lib.StepRecord * max_records)()
+        n = C.c_int32()
+        _lib.check(self._L.gnx_read_step_records(self._ctx, arr, max_records, C.byref(n)), 'gnx_read_step_records')
+        return [dict(t=r.t, Nt=r.Nt, n_births=r.n_births, n_deaths=r.n_deaths, n_pairs=r.n_pairs)
+                for r in arr[:n.value]]
+
+    def counters(self):
+        c = self.read('COUNTERS', 24)
+        names = ['n', 'n_pre', 'P', 'B', 'deaths', 'n_free', 'n_slots', 'cur']
+        out = {k: int(c[i]) for i, k in enumerate(names)}
+        out['max_idx'] = int(c[8:10].view(np.int64)[0])
+        out['t'] = int(c[10:12].view(np.int64)[0])
+        out['err'] = int(c[12])
+        out['n_rec'] = int(c[13])
+        out['gs_iters'] = (int(c[14]), int(c[15]))
+        return out
+
+    def read(self, field, count):
+        """Copy `count` elements of a device field to the host (parity tests, API views)."""
+        dt = np.dtype(_DT[field])
+        out = np.zeros(int(count), dtype=dt)
+        _lib.check(self._L.gnx_read_field(self._ctx, _lib.FIELDS[field], out.ctypes.data_as(C.c_void_p),
+                                          out.nbytes), 'gnx_read_field')
+        return out
+
+    def read_z(self, n):
+        """z as [n, n_traits] (device layout is [n_traits][capacity])."""
+        if not self.n_traits:
+            return np.zeros((n, 0))
+        full = self.read('Z', self.capacity * self.n_traits).reshape(self.n_traits, self.capacity)
+        return np.ascontiguousarray(full[:, :n].T)
+
+    def raster(self, field):
+        return self.read(field, self.land_dim[0] * self.land_dim[1]).reshape(self.land_dim[1], self.land_dim[0])
+
+    @property
+    def launch_count(self):
+        return int(self._L.gnx_launch_count(self._ctx))
+
+    @property
+    def stream_ptr(self):
+        return int(self._L.gnx_stream(self._ctx) or 0)
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value is not None:
+            self._L.gnx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

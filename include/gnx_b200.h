@@ -1,0 +1,246 @@
+/* gnx_b200.h -- C-ABI of libgnxb200.so: the B200-native (sm_100a) implementation of
+ * Geonomics' per-timestep individual-based update loop.
+ *
+ * The reference (erthward/geonomics v1.4.9) is pure Python and has no FFI; its seam for this
+ * path is the per-species method set that Model._make_fn_queue (sim/model.py:603-667) queues
+ * each time step.  Every entry point below names the reference interface it replaces
+ * (file:line relative to /root/reference/geonomics/).  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (gnx_strerror); no exceptions;
+ *   - one gnx_ctx per Species; it owns all device buffers and one CUDA stream; calls on a
+ *     ctx must come from one host thread at a time;
+ *   - pointers named host_* are caller-owned HOST buffers; nothing in the ABI is a torch
+ *     type; device pointers are exposed only through gnx_device_ptr (for zero-copy views);
+ *   - step functions are asynchronous on the ctx stream unless stated; gnx_sync waits;
+ *   - individuals are held structure-of-arrays in *species order* (iteration order of the
+ *     reference's Species OrderedDict); genotypes are bit-packed, one row per individual:
+ *     [homologue 0 | homologue 1], each homologue 16*ceil(L/128) bytes, locus l = bit (l%32)
+ *     of u32 word l/32;
+ *   - randomness is counter-based Philox4x32-10 keyed by (seed; individual id, call site,
+ *     time step); every call site can instead replay caller-injected draws (gnx_set_draws),
+ *     which is how integer/index parity with the reference is tested.
+ */
+#ifndef GNX_B200_H
+#define GNX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNX_ABI_VERSION 1
+#define GNX_MAX_TRAITS 8
+#define GNX_MAX_LAYERS 16
+
+typedef struct gnx_ctx gnx_ctx;
+
+enum { GNX_DISTR_WALD = 0, GNX_DISTR_LOGNORMAL = 1, GNX_DISTR_LEVY = 2 };
+enum { GNX_SURF_NONE = 0, GNX_SURF_TABLE = 1, GNX_SURF_ONTHEFLY = 2 };
+
+/* error codes */
+enum {
+  GNX_OK = 0,
+  GNX_ERR_CUDA = -1,        /* a CUDA runtime call failed (message in gnx_last_error) */
+  GNX_ERR_ARG = -2,         /* invalid argument */
+  GNX_ERR_CAPACITY = -3,    /* population outgrew ctx capacity */
+  GNX_ERR_DRAWS = -4,       /* an injected draw buffer was exhausted */
+  GNX_ERR_STATE = -5        /* call made in the wrong state (e.g. genomes not set) */
+};
+
+/* Species + landscape parameters the hot path reads.  Mirrors the attributes the reference
+ * ops read off the Species (`spp.b`, `spp.mating_radius`, ... species.py:405-425) and the
+ * Landscape (`land.dim`, landscape.py:245-314). */
+typedef struct {
+  int32_t abi_version;        /* GNX_ABI_VERSION */
+  int32_t dim_x, dim_y;       /* land.dim = (x, y) = (cols, rows) */
+  int32_t n_layers;
+  int64_t capacity;           /* max individuals alive at once (incl. newborns) */
+  uint64_t seed;
+  /* genome */
+  int32_t L;                  /* loci carried per individual (gen_arch.L, use_tskit=False) */
+  int32_t n_recomb_paths;     /* Recombinations._n (genome.py:69) */
+  int32_t n_traits;
+  int32_t use_dom;            /* gen_arch._use_dom (genome.py:556) */
+  /* mating (species.py:2157-2215, mating.py:24-126) */
+  double mating_radius;       /* < 0: panmixia (mating_radius=None) */
+  double b;
+  double R;
+  double n_births_lambda;
+  int32_t n_births_fixed;
+  int32_t sex;
+  double sex_ratio_p;         /* spp.sex_ratio (probability of drawing a male) */
+  int32_t choose_nearest;
+  int32_t inverse_dist;
+  /* mortality (demography.py:153-180, 319-321) */
+  double d_min, d_max;
+  int32_t max_age;            /* -1: None */
+  int32_t K_layer;
+  double K_factor;
+  /* movement (movement.py:34-141) */
+  int32_t move;               /* spp._move */
+  int32_t move_distr, disp_distr;
+  double move_p1, move_p2, disp_p1, disp_p2;
+  double dir_mu, dir_kappa;
+  double res_ratio_x, res_ratio_y;
+  int32_t move_surf_mode, disp_surf_mode;     /* GNX_SURF_* */
+  int32_t move_surf_layer, disp_surf_layer;
+  int32_t move_surf_mixture, disp_surf_mixture;
+  double move_surf_kappa, disp_surf_kappa;
+  int32_t surf_approx_len;    /* table mode: third dim of the float16 tables */
+  int32_t disp_max_tries_injected;   /* columns of the injected dispersal draw arrays */
+} gnx_config_t;
+
+/* One trait (genome.py:284-437): loci are row indices into the genotype array. */
+typedef struct {
+  int32_t n_loci;
+  const int32_t* host_loci;     /* [n_loci], ascending */
+  const double* host_alpha;     /* [n_loci] */
+  double phi;                   /* scalar phi; ignored when host_phi_raster != NULL */
+  const double* host_phi_raster;/* [dim_y][dim_x] or NULL (genome.py:391-396) */
+  double gamma;
+  int32_t layer;                /* trait.lyr_num */
+  int32_t univ_adv;
+} gnx_trait_t;
+
+/* Density-grid stack + its Delaunay triangulation (spatial.py:100-146, 270-360).  The
+ * lattice is built by the caller exactly as the reference builds it; the triangulation is
+ * the one scipy.interpolate.griddata builds (Qhull) for those points. */
+typedef struct {
+  double window_width;
+  int32_t n_points;
+  const double* host_points;        /* [n_points][2] as (i, j) = (y, x) */
+  const double* host_areas;         /* [n_points] window-landscape intersection areas */
+  int32_t grid_ni[4], grid_nj[4];   /* shape of each of the 4 offset grids */
+  int32_t grid_i0[4], grid_j0[4];   /* cell id of each grid's first point */
+  int32_t grid_x_edge[4], grid_y_edge[4];
+  int32_t n_tri;
+  const int32_t* host_simplices;    /* [n_tri][3] */
+  const int32_t* host_neighbors;    /* [n_tri][3] */
+  const int32_t* host_nbr_indptr;   /* [n_points+1] vertex_neighbor_vertices CSR */
+  const int32_t* host_nbr_indices;
+  int32_t lat_ni, lat_nj;           /* lattice points per axis (spacing window_width/2) */
+  const int32_t* host_square_tri;   /* [(lat_ni-1)*(lat_nj-1)][2] triangles per lattice square */
+  int32_t colourable;               /* 1: the 4 grids are independent sets of the triangulation */
+} gnx_density_t;
+
+/* Injected draws (all HOST pointers, any may be NULL = use Philox at that site).
+ * Sites follow SURVEY.md Appendix A. */
+typedef struct {
+  int64_t n;                        /* rows available in per-individual arrays */
+  const double* move_dir;           /* A1 vonmises outputs [n] */
+  const int32_t* move_choice;       /* A1 surface-table column [n] */
+  const double* move_dist;          /* A2 [n] */
+  const uint32_t* mate_R;           /* A4 [n]: k = (R * n_nbrs) >> 32 */
+  const double* mate_inv_u;         /* A4 inverse-distance mode [n] */
+  const double* mate_u;             /* A5 [n]: pair kept iff u < b */
+  const int32_t* poisson;           /* A6 [n] per canonical pair */
+  const int32_t* recomb_keys;       /* A7 [2n] */
+  const int32_t* start_homs;        /* A8 [n][2] */
+  const double* disp_dir;           /* A9 [n][tries] */
+  const int32_t* disp_choice;       /* A9 surface-table column [n][tries] */
+  const double* disp_dist;          /* A10 [n][tries] */
+  const double* sex_u;              /* A11 [n] */
+  const double* sex_redraw_u;       /* A12 [n] */
+  const double* death_u;            /* A16 [n] */
+} gnx_draws_t;
+
+/* Host-side SoA view of a population (upload / download). Any pointer may be NULL. */
+typedef struct {
+  int64_t n;
+  double* x; double* y;             /* individual.py:107-108 */
+  int32_t* age; int8_t* sex; int64_t* idx;
+  uint32_t* genomes;                /* [n][2][4*ceil(L/128)] packed rows */
+  double* z;                        /* [n][n_traits] */
+  double* fit;                      /* [n] */
+  double* e;                        /* [n][n_layers]  (download only; species.py:913-922) */
+  int64_t max_ind_idx;              /* species.py:360 */
+} gnx_population_t;
+
+/* Per-step counters (species.py:374-380: Nt, n_births, n_deaths). */
+typedef struct {
+  int64_t t; int64_t Nt; int64_t n_births; int64_t n_deaths; int64_t n_pairs;
+} gnx_step_record_t;
+
+const char* gnx_strerror(int code);
+const char* gnx_last_error(void);
+int gnx_abi_version(void);
+
+/* ---- lifecycle / setup (replaces the object state the reference keeps on Species /
+ *      Landscape / GenomicArchitecture; setup is not on the hot path) -------------------- */
+int gnx_create(const gnx_config_t* cfg, gnx_ctx** out);
+int gnx_destroy(gnx_ctx* ctx);
+int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters /* [n_layers][dim_y][dim_x] */);
+int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t* traits,
+                   const int8_t* host_dom /* [L] or NULL */);
+int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_paths /* [n_paths][W] */);
+int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dens);
+int gnx_set_surface_tables(gnx_ctx* ctx, const uint16_t* host_move_f16, const uint16_t* host_disp_f16);
+int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* draws /* NULL: clear, back to Philox */);
+int gnx_set_burn(gnx_ctx* ctx, int32_t burn);   /* burn-in: no genomes, no selection (species.py:825) */
+int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop);
+int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop /* buffers sized >= gnx_population_size */);
+int gnx_population_size(gnx_ctx* ctx, int64_t* n);          /* synchronises */
+
+/* ---- hot path, stage by stage (each is asynchronous on the ctx stream) ----------------- */
+/* Species._set_age_stage  species.py:567-569 */
+int gnx_age_step(gnx_ctx* ctx);
+/* ops.movement._do_movement  movement.py:34-95 (+ _ConductanceSurface._draw_directions spatial.py:182) */
+int gnx_move(gnx_ctx* ctx);
+/* Species._set_e  species.py:913-922 (materialises e[n][n_layers] on demand) */
+int gnx_sample_env(gnx_ctx* ctx);
+/* Species._set_coords_and_cells + cKDTree rebuild  species.py:937-939, 2170: counting-sort binning */
+int gnx_bin_cells(gnx_ctx* ctx);
+/* Species._get_mating_pairs + _KDTree._get_mating_pairs  species.py:2157-2215, spatial.py:191-245 */
+int gnx_find_mates(gnx_ctx* ctx);
+/* ops.mating._find_mates (sex filter / de-dup)  mating.py:24-117;  _draw_n_births mating.py:120-126;
+ * offspring ids species.py:614-619;  pair-midpoint counts for demography._calc_n_pairs :60-91 */
+int gnx_dedup_pairs(gnx_ctx* ctx);
+/* ops.mating._do_mating (gametes) mating.py:130-214 + ops.selection._calc_phenotype selection.py:22-48
+ * + ops.movement._do_dispersal movement.py:98-141 + newborn records species.py:638-688 */
+int gnx_make_offspring(gnx_ctx* ctx);
+/* _DensityGridStack._calc_density counts  spatial.py:73-97 */
+int gnx_density_counts(gnx_ctx* ctx);
+/* scipy griddata(method='cubic') spatial.py:144: gradient estimate + Clough-Tocher evaluation;
+ * demography._calc_dNdt/_calc_N_b/_calc_Nd/_calc_d  demography.py:104-172 */
+int gnx_density_eval(gnx_ctx* ctx);
+/* selection._calc_fitness/_calc_prob_death selection.py:51-125; demography.py:306-321 */
+int gnx_death_prob(gnx_ctx* ctx);
+/* demography._do_mortality demography.py:175-180 (+ stable compaction, genome-slot recycling) */
+int gnx_mortality(gnx_ctx* ctx);
+/* Landscape._set_raster landscape.py:353 + Species._set_K species.py:546 (env change, change.py:56-84) */
+int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_raster);
+
+/* ---- whole steps ------------------------------------------------------------------------ */
+/* n_steps iterations of the main/burn queue for this species:
+ * _set_age_stage -> _do_movement -> _do_pop_dynamics -> _set_Nt  (model.py:603-667) */
+int gnx_step(gnx_ctx* ctx, int32_t n_steps);
+int gnx_sync(gnx_ctx* ctx);
+/* Same, with HOST buffers in and out: upload pop, run n_steps, download into pop (synchronous). */
+int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps);
+/* Drain the per-step records accumulated since the last call (synchronises). */
+int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out);
+
+/* ---- introspection (parity tests, lazy API views) -------------------------------------- */
+enum {
+  GNX_F_X = 1, GNX_F_Y, GNX_F_AGE, GNX_F_SEX, GNX_F_IDX, GNX_F_Z, GNX_F_FIT, GNX_F_GSLOT,
+  GNX_F_N_NBRS, GNX_F_MATE, GNX_F_PAIRS, GNX_F_NB, GNX_F_PERM, GNX_F_CELL_START,
+  GNX_F_COUNTS_N, GNX_F_COUNTS_P, GNX_F_VALS_N, GNX_F_VALS_P, GNX_F_GRAD_N, GNX_F_GRAD_P,
+  GNX_F_N_RAST, GNX_F_NPAIRS_RAST, GNX_F_D_RAST, GNX_F_K_RAST, GNX_F_DEATH_P, GNX_F_ALIVE,
+  GNX_F_DISP_TRIES, GNX_F_E, GNX_F_COUNTERS, GNX_F_GENOMES
+};
+/* Copies a device field into a host buffer (synchronises).  For per-individual fields the
+ * first `count` elements in species order are returned. */
+int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64_t nbytes);
+int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64_t* nbytes);
+void* gnx_stream(gnx_ctx* ctx);     /* cudaStream_t of the ctx */
+
+/* kernel launch accounting (bench.py "gpu_launches") */
+int64_t gnx_launch_count(gnx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNX_B200_H */

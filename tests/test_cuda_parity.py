@@ -1,0 +1,73 @@
+"""GPU parity: libgnxb200.so (through the C-ABI) vs the oracle and vs the vectors recorded
+from the reference, with identical injected draws.  Integer / index work must be bit-exact;
+floating point within 1e-6 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from golden_io import case_names, load_case
+from parity_util import run_device_step, compare_step
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', params=case_names())
+def stepped(request):
+    from oracle import step_oracle as so
+    z, arch, prm, state, draws = load_case(request.param)
+    new_o, im_o = so.step(state, arch, prm, draws)
+    out = run_device_step(arch, prm, state, draws, staged=True)
+    return request.param, z, out, new_o, im_o
+
+
+def test_staged_step_matches_oracle(stepped):
+    _, z, out, new_o, im_o = stepped
+    compare_step(out, new_o, im_o)
+
+
+def test_staged_step_matches_reference_vectors(stepped):
+    """Directly against what the reference itself produced (tests/golden/make_golden.py)."""
+    _, z, out, new_o, im_o = stepped
+    assert np.array_equal(out['n_nbrs'], z['n_nbrs'])
+    assert np.array_equal(out['pairs'], z['pairs'])
+    assert np.array_equal(out['nb'], z['nb'])
+    assert np.array_equal(out['pre']['idx'], z['pre_idx'])
+    assert np.array_equal(out['pre']['sex'], z['pre_sex'])
+    new = out['new']
+    assert np.array_equal(new['idx'], z['out_idx'])
+    assert np.array_equal(new['g'], z['out_g'])
+    assert np.array_equal(new['sex'], z['out_sex'])
+    assert np.array_equal(new['age'], z['out_age'])
+    np.testing.assert_allclose(new['x'], z['out_x'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(new['y'], z['out_y'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(new['z'], z['out_z'], rtol=1e-6)
+    np.testing.assert_allclose(new['fit'], z['out_fit'], rtol=1e-6)
+    np.testing.assert_allclose(out['N_rast'], z['N_rast'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out['d_rast'], z['d_rast'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out['death_p'], z['death_p'], rtol=1e-6, atol=1e-9)
+    assert out['records'][-1]['Nt'] == int(z['out_Nt'])
+    assert out['records'][-1]['n_deaths'] == int(z['out_n_deaths'])
+
+
+def test_density_counts_exact(stepped):
+    from oracle import step_oracle as so
+    name, z, out, new_o, im_o = stepped
+    _, arch, prm, state, draws = load_case(name)[0:5]
+    dgs = so.DensityGridStack(arch['land_dim'], arch['ww'])
+    pre = im_o['pre']
+    cN = np.concatenate([c.ravel() for c in dgs.counts(pre['x'], pre['y'])])
+    assert np.array_equal(out['counts_N'], cN)
+    pairs = im_o['pairs']
+    x, y = im_o['mv_x'], im_o['mv_y']
+    px = (x[pairs[:, 0]] + x[pairs[:, 1]]) / 2
+    py = (y[pairs[:, 0]] + y[pairs[:, 1]]) / 2
+    cP = np.concatenate([c.ravel() for c in dgs.counts(px, py)])
+    assert np.array_equal(out['counts_P'], cP)
+
+
+@pytest.mark.parametrize('name', case_names())
+def test_fused_step_equals_staged(name):
+    from oracle import step_oracle as so
+    z, arch, prm, state, draws = load_case(name)
+    new_o, im_o = so.step(state, arch, prm, draws)
+    out = run_device_step(arch, prm, state, draws, staged=False)
+    compare_step(out, new_o, im_o)
