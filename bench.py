@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- individual-generations/second of the per-timestep update loop on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4] [--impl reference]
+
+A "step" is one full time step (model.py:603-667 queue for one species: age, movement,
+mate search, births with recombination, density, logistic mortality) over the synthetic
+population of the named workload.  `value` is whole-job throughput with the state resident
+in HBM; `e2e` is the same metric through the C-ABI host-buffer call gnx_walk_host (host->
+device copy of the population, one step, device->host copy back, every step).  With N>1
+(torchrun, one rank per GPU) every rank advances its own replicate population of the same
+workload -- the path shards by independent replicate iterations, so
+there is no data-path collective and scaling is "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'individual_generations_per_second'
+UNIT = 'individual-generations/s'
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic HBM bytes per kernel launch (DESIGN.md "Kernels")
+#   n = individuals at step start, B = births, P = pairs, npre = n + B, W = bytes per packed
+#   homologue, T = traits, cells = mating-grid cells, YX = landscape cells
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(W, T, cells, YX):
+    return {
+        'k_age_move_bin': lambda s: s['n'] * (32 + 8 + 8 + 8),          # x,y rw; age rw; id r; key+rank w
+        'scan_cells.reduce': lambda s: cells * 4,
+        'scan_cells.apply': lambda s: cells * 8,
+        'k_scatter_perm': lambda s: s['n'] * (4 + 4 + 4 + 4),
+        'k_cell_sort': lambda s: cells * 8 + s['n'] * 8,
+        'k_gather_sorted': lambda s: s['n'] * (4 + 16 + 16),
+        'k_find_mates': lambda s: s['n'] * (16 + 4 + 4 + 8 + 4),       # sorted x,y; perm; key; id; mate w
+        'scan_pairs.reduce': lambda s: s['n'] * 8,
+        'scan_pairs.apply': lambda s: s['n'] * 8 + s['P'] * (8 + 32 + 16 + 12),
+        'k_make_offspring': lambda s: s['B'] * (4 * W + 2 * W + 8 + 29 + 8 * T + 16 + 12),
+        'k_density_counts': lambda s: s['npre'] * 16,
+        'k_raster_N': lambda s: YX * 8,
+        'k_raster_d': lambda s: YX * 24,
+        'k_death': lambda s: s['npre'] * (16 + 8 * T + 8 + 8 * T + 8 + 4 + 8 + 1),
+        'scan_mortality.reduce': lambda s: s['npre'] * 1,
+        'scan_mortality.apply': lambda s: s['npre'] * 1 + (s['npre'] - s['deaths']) * 2 * (41 + 8 * T),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(smax)) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of the reference algorithm) on a bounded sample
+# ------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+    cfg, n_sample, steps, seed = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from geonomics_b200 import workloads, genome_pack
+    from oracle import step_oracle as so
+    from oracle import draws as od
+    c = workloads.scaled(cfg, n_sample)
+    c['surfaces'] = False            # the reference's surface tables are O(Y*X*approx_len) setup
+    w = workloads.build(c, seed)
+    n = c['N']
+    L = w['L']
+    g = genome_pack.unpack_genomes(workloads.random_packed_genomes(n, L, seed + 1), L)
+    prm = dict(w['prm'])
+    arch = dict(land_dim=w['land_dim'], rasters=w['rasters'],
+                K=w['rasters'][prm['K_layer']] * prm['K_factor'], ww=None,
+                traits=w['gen_arch']['traits'], dom=None, paths=w['gen_arch']['paths'])
+    z = so.phenotype(g, arch['traits'])
+    state = dict(x=w['pop']['x'], y=w['pop']['y'], age=w['pop']['age'], sex=w['pop']['sex'],
+                 idx=w['pop']['idx'], g=g, z=z, max_ind_idx=n - 1)
+    dgs = so.DensityGridStack(arch['land_dim'], None)
+    rng = np.random.default_rng(seed + 2)
+    total = 0
+    t_total = 0.0
+    for s in range(steps + 1):
+        n_now = len(state['x'])
+        d = od.make_draws(rng, prm, n_now, n_now, len(arch['paths']))
+        t0 = time.perf_counter()
+        state, im = so.step(state, arch, prm, d, dgs=dgs)
+        dt = time.perf_counter() - t0
+        if s > 0:                     # first step warms caches / imports
+            total += n_now
+            t_total += dt
+    return total, t_total
+
+
+def cpu_baseline(cfg, n_sample, steps, procs, seed=123):
+    if procs <= 1:
+        res = [_oracle_worker((cfg, n_sample, steps, seed))]
+        wall = res[0][1]
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context('spawn')
+        t0 = time.perf_counter()
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_oracle_worker, [(cfg, n_sample, steps, seed + 10 * k) for k in range(procs)])
+        wall = max(r[1] for r in res)
+        del t0
+    total = sum(r[0] for r in res)
+    return total / wall, total, wall
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    n_sample = args.cpu_sample
+    t0 = time.perf_counter()
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        pass
+    value, total, wall = cpu_baseline(cfg, n_sample, max(1, args.steps), procs)
+    elapsed = time.perf_counter() - t0
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64+u32 bitsets',
+        'data': 'synthetic',
+        'config': {'workload': args.workload + ' ' + workload_desc(cfg), 'cpu_sample_individuals': n_sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+                         'sample': '%d processes x %d steps of a %d-individual replica of the workload '
+                                   '(same per-capita parameters and density), numpy oracle port of the '
+                                   'reference algorithm; the reference itself is pure Python and does '
+                                   'not exist on the GPU box' % (procs, args.steps, n_sample)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': elapsed,
+    }
+    print(json.dumps(line))
+
+
+def workload_desc(cfg):
+    return '%d individuals, %d loci, %d traits x %d loci, %dx%d landscape, mating_radius %g%s' % (
+        cfg['N'], cfg['L'], cfg['n_traits'], cfg['loci_per_trait'], cfg['dim'][0], cfg['dim'][1],
+        cfg['mating_radius'], ', on-the-fly conductance surfaces' if cfg['surfaces'] else '')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default='c2')
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (debug only)')
+    ap.add_argument('--cpu-sample', type=int, default=20000)
+    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    args = ap.parse_args()
+    from geonomics_b200 import workloads
+    cfg = dict(workloads.CONFIGS[args.workload])
+    if args.scale != 1.0:
+        cfg = workloads.scaled(cfg, int(cfg['N'] * args.scale))
+    if args.impl == 'reference':
+        run_reference(args, cfg)
+        return
+
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    from geonomics_b200.device import DeviceSpecies
+    w = workloads.build(cfg, cfg['seed'] + rank)            # one replicate population per rank
+    N0, L = cfg['N'], w['L']
+    cap = int(1.5 * N0) + 4096
+    dev = DeviceSpecies(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=cap,
+                        seed=cfg['seed'] + 7919 * rank)
+    genomes = workloads.random_packed_genomes(N0, L, cfg['seed'] + 1 + rank)
+    dev.upload(w['pop']['x'], w['pop']['y'], w['pop']['age'], w['pop']['sex'], w['pop']['idx'],
+               genomes_packed=genomes)
+    stream = torch.cuda.ExternalStream(dev.stream_ptr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    dev.step(args.warmup)
+    dev.sync()
+    dev.step_records()
+    launches0 = dev.launch_count
+    # ---- timed region: K steps, state resident in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    dev.step(args.steps)
+    e1.record(stream)
+    dev.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = dev.launch_count - launches0
+    recs = dev.step_records()
+    assert len(recs) == args.steps, (len(recs), args.steps)
+    # individuals processed per step = population at step start
+    n_start = []
+    prev = None
+    for r in recs:
+        n_start.append(r['Nt'] - r['n_births'] + r['n_deaths'])
+    ind_gens = float(sum(n_start))
+    births = float(sum(r['n_births'] for r in recs))
+    t = torch.tensor([ms, ind_gens, births], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_all, ind_all, births_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        ms_all, ind_all, births_all = ms, ind_gens, births
+    value = ind_all / (ms_all * 1e-3)
+
+    # ---- per-kernel timing pass (CUDA events around every launch) for the roofline
+    dev.profile(True)
+    dev.step(args.steps)
+    dev.sync()
+    prof = dev.profile_report()
+    dev.profile(False)
+    precs = dev.step_records()
+    W = 4 * dev.W
+    T = dev.n_traits
+    cells = int(dev.read('CELL_START', 1).size and 0) or 0
+    import math
+    cs = w['prm']['mating_radius'] * 1.0000001
+    ncx, ncy = int(w['land_dim'][0] / cs) + 1, int(w['land_dim'][1] / cs) + 1
+    cells = ncx * ncy
+    YX = w['land_dim'][0] * w['land_dim'][1]
+    ab = algorithmic_bytes(W, T, cells, YX)
+    mean = {k: float(np.mean([r[k] for r in precs])) for k in ('Nt', 'n_births', 'n_deaths', 'n_pairs')}
+    s = dict(n=mean['Nt'] - mean['n_births'] + mean['n_deaths'], B=mean['n_births'], P=mean['n_pairs'],
+             deaths=mean['n_deaths'])
+    s['npre'] = s['n'] + s['B']
+    peak, peak_src = load_peaks()
+    table = []
+    step_ms = sum(v[1] for v in prof.values()) / args.steps
+    for name, (cnt, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per_launch_ms = tot_ms / cnt
+        row = {'kernel': name, 'launches_per_step': cnt / args.steps, 'ms_per_launch': per_launch_ms,
+               'share_of_step': tot_ms / args.steps / step_ms}
+        if name in ab:
+            b = ab[name](s)
+            row['algorithmic_bytes'] = b
+            row['achieved_GBs'] = b / (per_launch_ms * 1e-3) / 1e9
+            row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
+        table.append(row)
+    top = next((r for r in table if 'achieved_GBs' in r), None)
+    gam = next((r for r in table if r['kernel'] == 'k_make_offspring'), None)
+    roofline = None
+    if top is not None:
+        roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_GBs'], 'peak': peak,
+                    'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': None, 'peak_source': peak_src,
+                    'share_of_step': top['share_of_step']}
+        if gam is not None:
+            roofline['genotype_streaming_kernel'] = {'kernel': 'k_make_offspring',
+                                                     'achieved': gam.get('achieved_GBs'),
+                                                     'frac': gam.get('frac_of_hbm_peak'),
+                                                     'ms_per_launch': gam['ms_per_launch']}
+
+    # ---- e2e: host buffers through gnx_walk_host, every step (pinned host memory)
+    e2e = None
+    if args.e2e_steps > 0:
+        def pinned(shape, dtype):
+            return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+        bufs = dict(x=pinned(cap, torch.float64), y=pinned(cap, torch.float64), age=pinned(cap, torch.int32),
+                    sex=pinned(cap, torch.int8), idx=pinned(cap, torch.int64),
+                    genomes=pinned((cap, 2, dev.W), torch.int32).view(np.uint32),
+                    z=pinned((cap, max(1, T)), torch.float64), fit=pinned(cap, torch.float64))
+        st = dev.download(unpack=False)
+        n = len(st['x'])
+        for k in ('x', 'y', 'age', 'sex', 'idx', 'fit'):
+            bufs[k][:n] = st[k]
+        bufs['genomes'][:n] = st['genomes']
+        if T:
+            bufs['z'].reshape(-1)[:n * T] = st['z'].reshape(-1)
+        bufs['n'] = n
+        bufs['max_ind_idx'] = st['max_ind_idx']
+        per_ind = 8 + 8 + 4 + 1 + 8 + 8 * dev.W + 8 * T + 8
+        dev.walk_host(bufs, 1)                              # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        e2e_ind = 0
+        h2d = d2h = 0
+        for _ in range(args.e2e_steps):
+            n_in = bufs['n']
+            dev.walk_host(bufs, 1)
+            e2e_ind += n_in
+            h2d += n_in * per_ind
+            d2h += bufs['n'] * per_ind
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(e2e_ind)], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            a = tt.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b_ = tt.clone()
+            dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+            dt, e2e_ind = float(a[0]), float(b_[1])
+        e2e = {'value': e2e_ind / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d / args.e2e_steps,
+               'd2h_bytes_per_step': d2h / args.e2e_steps, 'steps': args.e2e_steps,
+               'api': 'gnx_walk_host (C-ABI, pinned host SoA buffers in and out every step)'}
+        dev.step_records()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, total, wall = cpu_baseline(cfg, args.cpu_sample, args.cpu_steps, 1)
+        cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+               'sample': '%d steps of a %d-individual replica of the workload (same per-capita parameters '
+                         'and density), numpy oracle port of the reference algorithm, 1 process; the pure-'
+                         'Python reference itself measured ~2.5e3 individual-generations/s in the build '
+                         'container (BASELINE.md section 2)' % (args.cpu_steps, args.cpu_sample),
+               'seconds': wall}
+
+    if rank == 0:
+        footprint_mb = (N0 * (2 * (8 + 8 + 4 + 1 + 8 + 4 + 8 * T + 8) + 8 * dev.W + 60) + 8 * YX * 6) / 1e6
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_all / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 coordinates/phenotypes + u32 bit-packed genotypes',
+            'data': 'synthetic',
+            'config': {'workload': args.workload + ': ' + workload_desc(cfg),
+                       'replicates': world, 'parallelism': 'one replicate population per GPU, no collective',
+                       'births_per_individual': births_all / ind_all,
+                       'l2': 'not flushed between steps: a step streams ~%.0f MB of state and work arrays '
+                             '(> 126 MB L2)' % footprint_mb,
+                       'rng': 'Philox4x32-10'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
+            'cpu_baseline': cpu, 'kernels': table[:12],
+        }
+        print(json.dumps(line))
+    dev.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

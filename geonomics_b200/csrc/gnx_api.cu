@@ -31,8 +31,15 @@ static thread_local std::string g_last_error;
     }                                                                                        \
   } while (0)
 
+struct ProfSpan {
+  std::string name;
+  cudaEvent_t e0, e1;
+};
+
 struct gnx_ctx {
   gnx_config_t cfg;
+  bool profiling = false;
+  std::vector<ProfSpan> spans;
   cudaStream_t stream = nullptr;
   int device = 0;
   int num_sms = 148;
@@ -76,6 +83,29 @@ static int dmalloc(gnx_ctx* ctx, T** p, size_t count, std::vector<void*>* bucket
   } while (0)
 
 static inline int grid_for(const gnx_ctx* ctx, int per_sm) { return ctx->num_sms * per_sm; }
+
+// ---- optional per-kernel timing (bench.py roofline): CUDA events on the ctx stream around
+// every launch, accumulated by kernel name.
+static void prof_begin(gnx_ctx* ctx, const char* name) {
+  if (!ctx->profiling) return;
+  ProfSpan sp;
+  sp.name = name;
+  cudaEventCreate(&sp.e0);
+  cudaEventCreate(&sp.e1);
+  cudaEventRecord(sp.e0, ctx->stream);
+  ctx->spans.push_back(sp);
+}
+static void prof_end(gnx_ctx* ctx) {
+  if (!ctx->profiling || ctx->spans.empty()) return;
+  cudaEventRecord(ctx->spans.back().e1, ctx->stream);
+}
+#define PROF(ctx, name) prof_begin(ctx, name)
+#define LAUNCHED(ctx)        \
+  do {                       \
+    prof_end(ctx);           \
+    (ctx)->launches++;       \
+    CK(cudaGetLastError());  \
+  } while (0)
 
 extern "C" const char* gnx_strerror(int code) {
   switch (code) {
@@ -217,10 +247,10 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
 
 static int set_K(gnx_ctx* ctx) {
   const int ncell = ctx->cfg.dim_x * ctx->cfg.dim_y;
+  PROF(ctx, "k_K_from_layer");
   k_K_from_layer<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(
       ctx->d_rasters + (size_t)ctx->cfg.K_layer * ncell, ctx->d_K, ctx->cfg.K_factor, ncell);
-  ctx->launches++;
-  CK(cudaGetLastError());
+  LAUNCHED(ctx);
   return GNX_OK;
 }
 
@@ -546,9 +576,9 @@ extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
   if (pop->idx) CK(cudaMemcpyAsync(pop->idx, P.idx[cur], n * 8, cudaMemcpyDeviceToHost, s));
   if (pop->fit) CK(cudaMemcpyAsync(pop->fit, P.fit[cur], n * 8, cudaMemcpyDeviceToHost, s));
   if (pop->genomes && !ctx->burn) {
+    PROF(ctx, "k_gather_genomes");
     k_gather_genomes<<<grid_for(ctx, 8), 256, 0, s>>>(P, ctx->d_stage_genomes, ctx->d_c);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    LAUNCHED(ctx);
     CK(cudaMemcpyAsync(pop->genomes, ctx->d_stage_genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyDeviceToHost, s));
   }
   if (pop->z && ctx->cfg.n_traits > 0) {
@@ -569,19 +599,21 @@ extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
 }
 
 // ---- stages -----------------------------------------------------------------------------
-#define LAUNCHED(ctx)        \
-  do {                       \
-    (ctx)->launches++;       \
-    CK(cudaGetLastError());  \
-  } while (0)
 
 template <class F>
-static int run_scan(gnx_ctx* ctx, F f) {
+static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   cudaStream_t s = ctx->stream;
+  char nm[64];
+  snprintf(nm, sizeof nm, "%s.reduce", name);
+  PROF(ctx, nm);
   scan_reduce_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
+  snprintf(nm, sizeof nm, "%s.spine", name);
+  PROF(ctx, nm);
   scan_spine_kernel<F><<<1, SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
+  snprintf(nm, sizeof nm, "%s.apply", name);
+  PROF(ctx, nm);
   scan_apply_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -593,6 +625,7 @@ static int age_move_bin(gnx_ctx* ctx, int do_age, int do_move, int do_bin) {
     g_last_error = "movement surface table not set";
     return GNX_ERR_STATE;
   }
+  PROF(ctx, "k_age_move_bin");
   k_age_move_bin<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
                                                            ctx->d_c, do_age, do_move, do_bin);
   LAUNCHED(ctx);
@@ -608,13 +641,16 @@ extern "C" int gnx_move(gnx_ctx* ctx) {
 
 static int finish_binning(gnx_ctx* ctx) {
   CellScan cs{ctx->work.cell_count, ctx->work.cell_start, ctx->ncell};
-  int r = run_scan(ctx, cs);
+  int r = run_scan(ctx, cs, "scan_cells");
   if (r != GNX_OK) return r;
   cudaStream_t s = ctx->stream;
+  PROF(ctx, "k_scatter_perm");
   k_scatter_perm<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->d_c);
   LAUNCHED(ctx);
+  PROF(ctx, "k_cell_sort");
   k_cell_sort<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->ncell);
   LAUNCHED(ctx);
+  PROF(ctx, "k_gather_sorted");
   k_gather_sorted<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -630,6 +666,7 @@ extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
 extern "C" int gnx_find_mates(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   ARG(ctx->cfg.mating_radius > 0, "panmixia is not implemented in this build");
+  PROF(ctx, "k_find_mates");
   k_find_mates<<<grid_for(ctx, 16), 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
                                                           ctx->d_c);
   LAUNCHED(ctx);
@@ -641,13 +678,14 @@ extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
   const bool fixed = ctx->cfg.n_births_fixed != 0;
   PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0};
   if (fixed) ARG(ps.fixed_nb >= 1, "n_births_fixed needs n_births_distr_lambda >= 1");
-  int r = run_scan(ctx, ps);
+  int r = run_scan(ctx, ps, "scan_pairs");
   if (r != GNX_OK) return r;
   if (!fixed) {
+    PROF(ctx, "k_draw_births");
     k_draw_births<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
     LAUNCHED(ctx);
     BirthScan bs{ctx->work, ctx->pop.cap};
-    r = run_scan(ctx, bs);
+    r = run_scan(ctx, bs, "scan_births");
     if (r != GNX_OK) return r;
   }
   return GNX_OK;
@@ -663,6 +701,7 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   const int Wq = ctx->Wq;
   const int g = grid_for(ctx, 8);
 #define MO(GW) k_make_offspring<GW><<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c)
+  PROF(ctx, "k_make_offspring");
   if (Wq <= 1) MO(1);
   else if (Wq <= 2) MO(2);
   else if (Wq <= 4) MO(4);
@@ -671,6 +710,7 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   else MO(32);
 #undef MO
   LAUNCHED(ctx);
+  PROF(ctx, "k_after_births");
   k_after_births<<<1, 1, 0, s>>>(ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -680,6 +720,7 @@ extern "C" int gnx_phenotype(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   if (ctx->cfg.n_traits == 0) return GNX_OK;
   if (!ctx->have_traits) { g_last_error = "traits not set"; return GNX_ERR_STATE; }
+  PROF(ctx, "k_phenotype_all");
   k_phenotype_all<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->traits, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -690,8 +731,10 @@ extern "C" int gnx_density_counts(gnx_ctx* ctx) {
   if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(ctx->dens.counts, 0, (size_t)2 * ctx->dens.npts * 4, s));
+  PROF(ctx, "k_density_counts");
   k_density_counts<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 0);
   LAUNCHED(ctx);
+  PROF(ctx, "k_density_counts");
   k_density_counts<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 1);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -702,12 +745,16 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
   cudaStream_t s = ctx->stream;
   // scipy defaults reached through griddata: CloughTocher2DInterpolator(tol=1e-6, maxiter=400)
+  PROF(ctx, "k_ct_gradients");
   k_ct_gradients<<<2, GS_BLOCK, 0, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
   LAUNCHED(ctx);
+  PROF(ctx, "k_ct_coefficients");
   k_ct_coefficients<<<std::max(1, (2 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
   LAUNCHED(ctx);
+  PROF(ctx, "k_raster_N");
   k_raster_N<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
+  PROF(ctx, "k_raster_d");
   k_raster_d<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -715,6 +762,7 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
 
 extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  PROF(ctx, "k_death");
   k_death<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
                                                     ctx->work, ctx->d_c);
   LAUNCHED(ctx);
@@ -724,8 +772,9 @@ extern "C" int gnx_death_prob(gnx_ctx* ctx) {
 extern "C" int gnx_mortality(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
-  int r = run_scan(ctx, ms);
+  int r = run_scan(ctx, ms, "scan_mortality");
   if (r != GNX_OK) return r;
+  PROF(ctx, "k_end_step");
   k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -733,6 +782,7 @@ extern "C" int gnx_mortality(gnx_ctx* ctx) {
 
 extern "C" int gnx_sample_env(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  PROF(ctx, "k_sample_env");
   k_sample_env<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -852,6 +902,7 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
 extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64_t nbytes) {
   ARG(ctx && host_out, "null");
   if (field == GNX_F_GENOMES) {
+    PROF(ctx, "k_gather_genomes");
     k_gather_genomes<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_stage_genomes, ctx->d_c);
     LAUNCHED(ctx);
   }
@@ -871,3 +922,41 @@ extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64
 
 extern "C" void* gnx_stream(gnx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int64_t gnx_launch_count(gnx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+
+// ---- per-kernel timing ------------------------------------------------------------------
+extern "C" int gnx_profile(gnx_ctx* ctx, int32_t enable) {
+  ARG(ctx, "null ctx");
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto& sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+  ctx->spans.clear();
+  ctx->profiling = enable != 0;
+  return GNX_OK;
+}
+
+// Writes "name\tlaunches\ttotal_ms\n" lines for every kernel launched since gnx_profile(ctx, 1).
+extern "C" int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen) {
+  ARG(ctx && buf && buflen > 0, "null");
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int64_t> cnt;
+  for (auto& sp : ctx->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.e0, sp.e1) != cudaSuccess) continue;
+    size_t k = 0;
+    for (; k < names.size(); ++k) if (names[k] == sp.name) break;
+    if (k == names.size()) { names.push_back(sp.name); ms.push_back(0); cnt.push_back(0); }
+    ms[k] += t;
+    cnt[k] += 1;
+  }
+  std::string out;
+  char line[256];
+  for (size_t k = 0; k < names.size(); ++k) {
+    snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", names[k].c_str(), (long long)cnt[k], ms[k]);
+    out += line;
+  }
+  if ((int64_t)out.size() + 1 > buflen) { g_last_error = "profile buffer too small"; return GNX_ERR_ARG; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return GNX_OK;
+}

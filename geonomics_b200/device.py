@@ -346,6 +346,19 @@ class DeviceSpecies:
     def raster(self, field):
         return self.read(field, self.land_dim[0] * self.land_dim[1]).reshape(self.land_dim[1], self.land_dim[0])
 
+    def profile(self, enable=True):
+        _lib.check(self._L.gnx_profile(self._ctx, int(bool(enable))), 'gnx_profile')
+
+    def profile_report(self):
+        """{kernel: (launches, total_ms)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self._L.gnx_profile_report(self._ctx, buf, len(buf)), 'gnx_profile_report')
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split('\t')
+            out[name] = (int(cnt), float(ms))
+        return out
+
     @property
     def launch_count(self):
         return int(self._L.gnx_launch_count(self._ctx))

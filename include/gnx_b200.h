@@ -239,6 +239,11 @@ void* gnx_stream(gnx_ctx* ctx);     /* cudaStream_t of the ctx */
 
 /* kernel launch accounting (bench.py "gpu_launches") */
 int64_t gnx_launch_count(gnx_ctx* ctx);
+/* per-kernel device timing with CUDA events on the ctx stream (bench.py "roofline"):
+ * gnx_profile(ctx, 1) starts recording, gnx_profile_report writes one
+ * "kernel\tlaunches\ttotal_ms\n" line per kernel, gnx_profile(ctx, 0) stops. */
+int gnx_profile(gnx_ctx* ctx, int32_t enable);
+int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen);
 
 #ifdef __cplusplus
 }

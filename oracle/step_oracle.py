@@ -83,12 +83,29 @@ def age_step(age):
 # --------------------------------------------------------------------------------------
 # a2  movement
 # --------------------------------------------------------------------------------------
+def _cos_sin(direction):
+    """np.cos / np.sin as movement.py:75-76 evaluates them.  For a float64 direction this
+    is plain double precision.  For a float16 direction (conductance-surface lookup,
+    spatial.py:182-184, table dtype spatial.py:447) numpy returns float16, and *how* it
+    gets there depends on the host CPU: with AVX512 dispatch numpy 2.x uses a vector
+    half-precision routine that is off by up to 1.43 half-ulp on 13 % of inputs, without it
+    it converts half -> float, calls libm cosf/sinf and rounds back to half.  The oracle
+    (and the CUDA path) pin the portable semantics: the correctly rounded float32 result
+    rounded to half; golden vectors are recorded with NPY_DISABLE_CPU_FEATURES set so the
+    reference takes the same path (tests/golden/make_golden.py)."""
+    direction = np.asarray(direction)
+    if direction.dtype == np.float16:
+        d64 = direction.astype(np.float64)
+        return (np.cos(d64).astype(np.float32).astype(np.float16),
+                np.sin(d64).astype(np.float32).astype(np.float16))
+    return np.cos(direction), np.sin(direction)
+
+
 def move(x, y, direction, distance, land_dim, res_ratio=(1, 1)):
-    """movement.py:74-92.  `direction` may be float16 (conductance-surface lookup,
-    spatial.py:182-184, table dtype spatial.py:447) in which case numpy evaluates
-    cos/sin in half precision -- reproduced by handing numpy the same dtype."""
-    dist_x = np.cos(direction) * distance
-    dist_y = np.sin(direction) * distance
+    """movement.py:74-92."""
+    c, s = _cos_sin(direction)
+    dist_x = c * distance
+    dist_y = s * distance
     if res_ratio[0] != 1:
         dist_x = dist_x * res_ratio[0]
     if res_ratio[1] != 1:
@@ -364,9 +381,9 @@ def disperse(mid_x, mid_y, dir_draws, dist_draws, land_dim, res_ratio=(1, 1)):
     tries = np.zeros(B, dtype=np.int32)
     done = np.zeros(B, dtype=bool)
     for r in range(R):
-        d = dir_draws[:, r]
-        dx = np.cos(d) * dist_draws[:, r]
-        dy = np.sin(d) * dist_draws[:, r]
+        c, s = _cos_sin(dir_draws[:, r])
+        dx = c * dist_draws[:, r]
+        dy = s * dist_draws[:, r]
         if res_ratio[0] != 1:
             dx = dx * res_ratio[0]
         if res_ratio[1] != 1:

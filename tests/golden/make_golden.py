@@ -29,6 +29,13 @@ import warnings
 import contextlib
 import io
 
+# numpy's float16 cos/sin (conductance-surface directions, movement.py:75-76) are
+# CPU-dependent: with AVX512 dispatch they come from a low-precision vector routine.  Record
+# the vectors on the portable path (half -> float -> libm -> half), i.e. what the reference
+# computes on any CPU without AVX512.  Must be set before numpy is imported.
+os.environ.setdefault('NPY_DISABLE_CPU_FEATURES',
+                      'AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR')
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
