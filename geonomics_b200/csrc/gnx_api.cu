@@ -220,7 +220,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   pr.move_tab = pr.disp_tab = nullptr;
   pr.seed_lo = (uint32_t)cfg->seed;
   pr.seed_hi = (uint32_t)(cfg->seed >> 32);
-  pr.store_debug = 1;
+  pr.store_debug = 0;
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = std::max(1, cfg->disp_max_tries_injected);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -413,6 +413,29 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
   if ((r = up(dn->host_nbr_indptr, sizeof(int32_t) * (D.npts + 1), (const void**)&D.nbr_indptr))) return r;
   const int nnz = dn->host_nbr_indptr[D.npts];
   if ((r = up(dn->host_nbr_indices, sizeof(int32_t) * nnz, (const void**)&D.nbr_indices))) return r;
+  {
+    // data-independent parts of the gradient solve (interpnd.pyx: Q, L3 per edge)
+    std::vector<double> ex(nnz), ey(nnz), wx(nnz), wy(nnz), vinv((size_t)3 * D.npts);
+    const double* P = dn->host_points;
+    for (int i = 0; i < D.npts; ++i) {
+      double Q0 = 0, Q1 = 0, Q3 = 0;
+      for (int jj = dn->host_nbr_indptr[i]; jj < dn->host_nbr_indptr[i + 1]; ++jj) {
+        const int j = dn->host_nbr_indices[jj];
+        const double x = P[2 * j] - P[2 * i], y = P[2 * j + 1] - P[2 * i + 1];
+        const double L = sqrt(x * x + y * y), L3 = L * L * L;
+        ex[jj] = x; ey[jj] = y; wx[jj] = x / L3; wy[jj] = y / L3;
+        Q0 += 4 * x * x / L3; Q1 += 4 * x * y / L3; Q3 += 4 * y * y / L3;
+      }
+      const double det = Q0 * Q3 - Q1 * Q1;
+      vinv[3 * i] = Q3 / det; vinv[3 * i + 1] = -Q1 / det; vinv[3 * i + 2] = Q0 / det;
+    }
+    if ((r = up(ex.data(), sizeof(double) * nnz, (const void**)&D.e_ex))) return r;
+    if ((r = up(ey.data(), sizeof(double) * nnz, (const void**)&D.e_ey))) return r;
+    if ((r = up(wx.data(), sizeof(double) * nnz, (const void**)&D.e_wx))) return r;
+    if ((r = up(wy.data(), sizeof(double) * nnz, (const void**)&D.e_wy))) return r;
+    if ((r = up(vinv.data(), sizeof(double) * 3 * D.npts, (const void**)&D.v_inv))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));     // the host vectors go out of scope below
+  }
   if ((r = up(dn->host_square_tri, sizeof(int32_t) * 2 * (D.lat_ni - 1) * (D.lat_nj - 1),
               (const void**)&D.square_tri)))
     return r;
@@ -958,5 +981,13 @@ extern "C" int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen) {
   }
   if ((int64_t)out.size() + 1 > buflen) { g_last_error = "profile buffer too small"; return GNX_ERR_ARG; }
   memcpy(buf, out.c_str(), out.size() + 1);
+  return GNX_OK;
+}
+
+
+/* keep per-individual intermediates (n_nbrs, death_p, disp_tries, n_pairs raster) for parity tests */
+extern "C" int gnx_set_debug(gnx_ctx* ctx, int32_t on) {
+  ARG(ctx, "null ctx");
+  ctx->prm.store_debug = on ? 1 : 0;
   return GNX_OK;
 }

@@ -86,6 +86,11 @@ struct Dens {
   const int32_t* neighbors;
   const int32_t* nbr_indptr;
   const int32_t* nbr_indices;
+  const double* e_ex;      // per CSR entry: edge vector and ex/L^3, ey/L^3
+  const double* e_ey;
+  const double* e_wx;
+  const double* e_wy;
+  const double* v_inv;     // [npts][3] inverse of the per-vertex 2x2 system (i00, i01, i11)
   int32_t lat_ni, lat_nj;
   const int32_t* square_tri;
   int32_t colourable;

@@ -567,27 +567,24 @@ __global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const C
 // Gradient estimate (`_estimate_gradients_2d_global`): Gauss-Seidel sweeps in vertex order.
 // The 4 offset grids are independent sets of the lattice triangulation, so a sweep is 4
 // fully parallel phases with exactly the sequential algorithm's arithmetic.
+// Per-vertex update with the data-independent parts hoisted to setup (gnx_set_density):
+// the 2x2 matrix Q of `_estimate_gradients_2d_global` depends only on the triangulation,
+// so its inverse (v_inv) and the per-edge weights ex/L^3, ey/L^3 (e_wx, e_wy) are
+// precomputed; a sweep then costs 6 flops per edge and no division / sqrt.
 __device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, double* yv, int i) {
-  double Q0 = 0, Q1 = 0, Q3 = 0, s0 = 0, s1 = 0;
-  const double pi0 = d.points[2 * i], pi1 = d.points[2 * i + 1];
+  double s0 = 0, s1 = 0;
   const double f1 = f[i];
-  for (int jj = d.nbr_indptr[i]; jj < d.nbr_indptr[i + 1]; ++jj) {
-    const int j = d.nbr_indices[jj];
-    const double ex = d.points[2 * j] - pi0, ey = d.points[2 * j + 1] - pi1;
-    const double L = sqrt(ex * ex + ey * ey);
-    const double L3 = L * L * L;
-    const double f2 = f[j];
-    const double df2 = -ex * yv[2 * j] - ey * yv[2 * j + 1];
-    Q0 += 4 * ex * ex / L3;
-    Q1 += 4 * ex * ey / L3;
-    Q3 += 4 * ey * ey / L3;
-    s0 += (6 * (f1 - f2) - 2 * df2) * ex / L3;
-    s1 += (6 * (f1 - f2) - 2 * df2) * ey / L3;
+  const int je = d.nbr_indptr[i + 1];
+  for (int jj = d.nbr_indptr[i]; jj < je; ++jj) {
+    const int j = __ldg(&d.nbr_indices[jj]);
+    const double ex = __ldg(&d.e_ex[jj]), ey = __ldg(&d.e_ey[jj]);
+    // (6*(f1 - f2) - 2*df2) with df2 = -ex*y_j0 - ey*y_j1
+    const double tt = 6 * (f1 - f[j]) + 2 * (ex * yv[2 * j] + ey * yv[2 * j + 1]);
+    s0 += tt * __ldg(&d.e_wx[jj]);
+    s1 += tt * __ldg(&d.e_wy[jj]);
   }
-  const double Q2 = Q1;
-  const double det = Q0 * Q3 - Q1 * Q2;
-  const double r0 = (Q3 * s0 - Q1 * s1) / det;
-  const double r1 = (-Q2 * s0 + Q0 * s1) / det;
+  const double r0 = __ldg(&d.v_inv[3 * i]) * s0 + __ldg(&d.v_inv[3 * i + 1]) * s1;
+  const double r1 = __ldg(&d.v_inv[3 * i + 1]) * s0 + __ldg(&d.v_inv[3 * i + 2]) * s1;
   double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
   yv[2 * i] = -r0;
   yv[2 * i + 1] = -r1;
@@ -595,17 +592,25 @@ __device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, doub
   return change;
 }
 
-#define GS_BLOCK 512
+#define GS_BLOCK 256
+#define GS_SMEM_PTS 1536
 __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, int maxiter, double tol) {
   // blockIdx.x: 0 = species density N, 1 = pair-midpoint density
   const int which = blockIdx.x;
   const int* counts = d.counts + (size_t)which * d.npts;
-  double* f = d.vals + (size_t)which * d.npts;
-  double* yv = d.grad + (size_t)which * d.npts * 2;
+  double* gf = d.vals + (size_t)which * d.npts;
+  double* gy = d.grad + (size_t)which * d.npts * 2;
+  __shared__ double sf[GS_SMEM_PTS];
+  __shared__ double sy[2 * GS_SMEM_PTS];
   __shared__ double red[GS_BLOCK / 32];
   __shared__ double s_err;
+  const bool in_smem = d.npts <= GS_SMEM_PTS;
+  double* f = in_smem ? sf : gf;
+  double* yv = in_smem ? sy : gy;
   for (int k = threadIdx.x; k < d.npts; k += blockDim.x) {
-    f[k] = (double)counts[k] / d.areas[k];                 // spatial.py:95
+    const double v = (double)counts[k] / d.areas[k];       // spatial.py:95
+    f[k] = v;
+    gf[k] = v;
     yv[2 * k] = 0.0;
     yv[2 * k + 1] = 0.0;
   }
@@ -636,10 +641,9 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
     __syncthreads();
     if (s_err < tol) { iters = it + 1; break; }
   }
-  if (threadIdx.x == 0) {
-    c->gs_iters[which] = iters;
-    if (iters == 0) atomicOr((int*)&c->err, 0);   // scipy only warns; result still used
-  }
+  if (in_smem)
+    for (int k = threadIdx.x; k < 2 * d.npts; k += blockDim.x) gy[k] = sy[k];
+  if (threadIdx.x == 0) c->gs_iters[which] = iters;     // 0: maxiter reached (scipy only warns)
 }
 
 // Bezier ordinates of every triangle (`_clough_tocher_2d_single`, point-independent part)

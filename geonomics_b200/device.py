@@ -173,6 +173,10 @@ class DeviceSpecies:
         _lib.check(self._L.gnx_set_traits(self._ctx, len(traits), arr, _ptr(dom, _lib.c_int8_p)),
                    'gnx_set_traits')
 
+    def set_debug(self, on=True):
+        """Keep n_nbrs / death_p / disp_tries / n_pairs raster readable (parity tests)."""
+        _lib.check(self._L.gnx_set_debug(self._ctx, int(bool(on))), 'gnx_set_debug')
+
     def set_burn(self, burn):
         _lib.check(self._L.gnx_set_burn(self._ctx, int(bool(burn))), 'gnx_set_burn')
 

@@ -180,6 +180,9 @@ int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dens);
 int gnx_set_surface_tables(gnx_ctx* ctx, const uint16_t* host_move_f16, const uint16_t* host_disp_f16);
 int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* draws /* NULL: clear, back to Philox */);
 int gnx_set_burn(gnx_ctx* ctx, int32_t burn);   /* burn-in: no genomes, no selection (species.py:825) */
+/* keep per-individual intermediates (n_nbrs, death_p, disp_tries, n_pairs raster) readable
+ * through gnx_read_field; off by default (they cost extra HBM writes) */
+int gnx_set_debug(gnx_ctx* ctx, int32_t on);
 int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop);
 int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop /* buffers sized >= gnx_population_size */);
 int gnx_population_size(gnx_ctx* ctx, int64_t* n);          /* synchronises */

@@ -38,6 +38,7 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
     dev = make_device(arch, prm, capacity=capacity or (2 * n0 + 256),
                       disp_tries=draws['disp_dist'].shape[1])
     try:
+        dev.set_debug(True)
         dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'], g=state['g'],
                    z=state['z'], max_ind_idx=state['max_ind_idx'])
         d = dict(draws)
