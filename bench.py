@@ -45,7 +45,8 @@ def algorithmic_bytes(W, T, cells, YX):
         'k_find_mates': lambda s: s['n'] * (16 + 4 + 4 + 8 + 4),       # sorted x,y; perm; key; id; mate w
         'scan_pairs.reduce': lambda s: s['n'] * 8,
         'scan_pairs.apply': lambda s: s['n'] * 8 + s['P'] * (8 + 32 + 16 + 12),
-        'k_make_offspring': lambda s: s['B'] * (4 * W + 2 * W + 8 + 29 + 8 * T + 16 + 12),
+        'k_gametes': lambda s: s['B'] * (4 * W + 2 * W + 8 + 8 * T + 4 + 8 + 8),   # rows; keys; z w; pair; slots
+        'k_newborns': lambda s: s['B'] * (16 + 29 + 4),                          # midpoint r; record w; pair
         'k_density_counts': lambda s: s['npre'] * 16,
         'k_raster_N': lambda s: YX * 8,
         'k_raster_d': lambda s: YX * 24,
@@ -325,14 +326,14 @@ def main():
             row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
         table.append(row)
     top = next((r for r in table if 'achieved_GBs' in r), None)
-    gam = next((r for r in table if r['kernel'] == 'k_make_offspring'), None)
+    gam = next((r for r in table if r['kernel'] == 'k_gametes'), None)
     roofline = None
     if top is not None:
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_GBs'], 'peak': peak,
                     'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': None, 'peak_source': peak_src,
                     'share_of_step': top['share_of_step']}
         if gam is not None:
-            roofline['genotype_streaming_kernel'] = {'kernel': 'k_make_offspring',
+            roofline['genotype_streaming_kernel'] = {'kernel': 'k_gametes',
                                                      'achieved': gam.get('achieved_GBs'),
                                                      'frac': gam.get('frac_of_hbm_peak'),
                                                      'ms_per_launch': gam['ms_per_launch']}
@@ -405,7 +406,7 @@ def main():
                              '(> 126 MB L2)' % footprint_mb,
                        'rng': 'Philox4x32-10'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
-            'cpu_baseline': cpu, 'kernels': table[:12],
+            'cpu_baseline': cpu, 'kernels': table[:14], 'gs_iters': dev.counters()['gs_iters'],
         }
         print(json.dumps(line))
     dev.close()

@@ -188,8 +188,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &W.cellkey, cap);
   DM(ctx, &W.cellrank, cap);
   DM(ctx, &W.perm, cap);
-  DM(ctx, &W.sx, cap);
-  DM(ctx, &W.sy, cap);
+  DM(ctx, &W.sxy, cap);
   DM(ctx, &W.mate, cap);
   DM(ctx, &W.n_nbrs, cap);
   DM(ctx, &W.pairs, 2 * cap);
@@ -292,7 +291,8 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   const int Wq = ctx->Wq;
   std::vector<int32_t> te_locus;
   std::vector<double> te_alpha, te_dom;
-  std::vector<int32_t> chunk_ptr((size_t)std::max(1, n_traits) * (Wq + 1), 0);
+  const int NW = 4 * Wq;      // CSR over 32-bit words
+  std::vector<int32_t> chunk_ptr((size_t)std::max(1, n_traits) * (NW + 1), 0);
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   for (int t = 0; t < n_traits; ++t) {
     const gnx_trait_t& tr = traits[t];
@@ -302,17 +302,17 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
     for (int k = 0; k < tr.n_loci; ++k) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tr.host_loci[a] < tr.host_loci[b]; });
     int q = 0;
-    chunk_ptr[(size_t)t * (Wq + 1)] = (int32_t)te_locus.size();
+    chunk_ptr[(size_t)t * (NW + 1)] = (int32_t)te_locus.size();
     for (int kk = 0; kk < tr.n_loci; ++kk) {
       const int k = order[kk];
       const int locus = tr.host_loci[k];
       ARG(locus >= 0 && locus < ctx->cfg.L, "trait locus out of range");
-      while (q < locus / 128) chunk_ptr[(size_t)t * (Wq + 1) + (++q)] = (int32_t)te_locus.size();
+      while (q < locus / 32) chunk_ptr[(size_t)t * (NW + 1) + (++q)] = (int32_t)te_locus.size();
       te_locus.push_back(locus);
       te_alpha.push_back(tr.host_alpha[k]);
       te_dom.push_back(host_dom ? 1.0 + (double)host_dom[locus] : 1.0);
     }
-    while (q < Wq) chunk_ptr[(size_t)t * (Wq + 1) + (++q)] = (int32_t)te_locus.size();
+    while (q < NW) chunk_ptr[(size_t)t * (NW + 1) + (++q)] = (int32_t)te_locus.size();
     T.n_loci[t] = tr.n_loci;
     T.phi[t] = tr.phi;
     T.gamma[t] = tr.gamma;
@@ -690,8 +690,12 @@ extern "C" int gnx_find_mates(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   ARG(ctx->cfg.mating_radius > 0, "panmixia is not implemented in this build");
   PROF(ctx, "k_find_mates");
-  k_find_mates<<<grid_for(ctx, 16), 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
-                                                          ctx->d_c);
+  const int g = grid_for(ctx, 16);
+#define FM(MODE) k_find_mates<MODE><<<g, 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
+  if (ctx->cfg.choose_nearest) FM(1);
+  else if (ctx->cfg.inverse_dist) FM(2);
+  else FM(0);
+#undef FM
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -723,15 +727,20 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   const int Wq = ctx->Wq;
   const int g = grid_for(ctx, 8);
-#define MO(GW) k_make_offspring<GW><<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c)
-  PROF(ctx, "k_make_offspring");
-  if (Wq <= 1) MO(1);
-  else if (Wq <= 2) MO(2);
-  else if (Wq <= 4) MO(4);
-  else if (Wq <= 8) MO(8);
-  else if (Wq <= 16) MO(16);
-  else MO(32);
+  if (!ctx->burn) {
+#define MO(GW) k_gametes<GW><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c)
+    PROF(ctx, "k_gametes");
+    if (Wq <= 1) MO(1);
+    else if (Wq <= 2) MO(2);
+    else if (Wq <= 4) MO(4);
+    else if (Wq <= 8) MO(8);
+    else if (Wq <= 16) MO(16);
+    else MO(32);
 #undef MO
+    LAUNCHED(ctx);
+  }
+  PROF(ctx, "k_newborns");
+  k_newborns<<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   PROF(ctx, "k_after_births");
   k_after_births<<<1, 1, 0, s>>>(ctx->d_c);

@@ -107,8 +107,7 @@ struct Work {
   uint32_t* cellkey;
   uint32_t* cellrank;
   int32_t* perm;
-  double* sx;
-  double* sy;
+  double2* sxy;            // cell-sorted (x, y)
   int32_t* mate;
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]

@@ -14,7 +14,7 @@
 //   lookup); species.py:937-939 (cells).  Flags select which parts run so the stage-level
 //   C-ABI entry points and the fused step share one kernel.
 // ========================================================================================
-__device__ inline double surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
+__device__ __noinline__ double surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
                                                     int cx, int cy, int mixture, double kappa) {
   // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
   // dropped; queen directions in raster row-major order.
@@ -82,9 +82,13 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
             g, land.rasters + (size_t)prm.c.move_surf_layer * land.X * land.Y, land.X, land.Y, cx, cy,
             prm.c.move_surf_mixture, prm.c.move_surf_kappa);
         sincos_half(__float2half_rn((float)d), &sn, &cs);
+      } else if (dr.move_dir) {
+        sincos(dr.move_dir[i], &sn, &cs);
+      } else if (prm.c.dir_kappa < 1e-8) {
+        // numpy vonmises(mu, kappa < 1e-8) = pi*(2U - 1) (mu ignored): movement.py:55
+        sincospi(2.0 * g.uniform() - 1.0, &sn, &cs);
       } else {
-        double d = dr.move_dir ? dr.move_dir[i] : sample_vonmises(g, prm.c.dir_mu, prm.c.dir_kappa);
-        sincos(d, &sn, &cs);
+        sincos(sample_vonmises(g, prm.c.dir_mu, prm.c.dir_kappa), &sn, &cs);
       }
       double dist = dr.move_dist ? dr.move_dist[i]
                                  : sample_distance(g, prm.c.move_distr, prm.c.move_p1, prm.c.move_p2);
@@ -144,27 +148,33 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Co
   const int n = c->n, cur = c->cur;
   for (int p = GTID; p < n; p += GSTRIDE) {
     int i = w.perm[p];
-    w.sx[p] = pop.x[cur][i];
-    w.sy[p] = pop.y[cur][i];
+    w.sxy[p] = make_double2(pop.x[cur][i], pop.y[cur][i]);
   }
 }
 
 // ========================================================================================
 // a5: neighbour scan + mate choice.  species.py:2157-2215, spatial.py:191-245.
 //   One thread per focal, walking the three contiguous row-ranges of the cell-sorted
-//   coordinate arrays that cover its 3x3 cell block.  Closed ball on squared distances,
-//   products and sum rounded separately (as the reference's cKDTree does).
+//   (x, y) pairs that cover its 3x3 cell block with 128-bit loads.  Closed ball on squared
+//   distances, products and sum rounded separately (as the reference's cKDTree does).
+//   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are buffered
+//           in one pass and the k-th is picked, k = (R * count) >> 32
+//   MODE 1: nearest neighbour (spatial.py:194-203)
+//   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
+#define MATE_BUF 32
+template <int MODE>
 __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                      const Counters* c) {
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
   const double r2 = prm.r2, radius = prm.c.mating_radius;
+  const double2* __restrict__ sxy = w.sxy;
   for (int p = GTID; p < n; p += GSTRIDE) {
-    const int i = w.perm[p];
-    const double fx = w.sx[p], fy = w.sy[p];
-    const uint32_t key = w.cellkey[i];
-    const int cy = key / land.ncx, cx = key - cy * land.ncx;
+    const double2 f = sxy[p];
+    int cx = (int)floor(f.x / land.cell_size), cy = (int)floor(f.y / land.cell_size);
+    cx = min(cx, land.ncx - 1);
+    cy = min(cy, land.ncy - 1);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
     int lo[3], hi[3];
 #pragma unroll
@@ -174,69 +184,76 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       lo[r] = w.cell_start[row * land.ncx + x0];
       hi[r] = w.cell_start[row * land.ncx + x1 + 1];
     }
-    // pass 1: count (and nearest / weight sum)
     int cnt = 0;
+    int buf[MATE_BUF];
     double best = 1e300, wsum = 0.0;
     int best_q = -1, n_w = 0;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
       for (int q = lo[r]; q < hi[r]; ++q) {
-        if (q == p) continue;
-        double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
-        double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d2 <= r2) {
-          cnt += 1;
-          if (d2 < best) { best = d2; best_q = q; }
-          if (prm.c.inverse_dist) {
-            double d = sqrt(d2);
+        const double2 cxy = sxy[q];
+        const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d2 <= r2 && q != p) {
+          if (MODE == 0) { if (cnt < MATE_BUF) buf[cnt] = q; }
+          if (MODE == 1) { if (d2 < best) { best = d2; best_q = q; } }
+          if (MODE == 2) {
+            const double d = sqrt(d2);
             if (d != 0.0) { wsum += radius - d; n_w += 1; }
           }
+          cnt += 1;
         }
       }
+    const int i = w.perm[p];
     if (prm.store_debug) w.n_nbrs[i] = cnt;
     int mate = -1;
     if (cnt > 0) {
       RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MATE, t);
       int sel_q = -1;
-      if (prm.c.choose_nearest) {
+      if (MODE == 1) {
         sel_q = best_q;
-      } else if (prm.c.inverse_dist) {
+      } else if (MODE == 2) {
         if (n_w > 0) {
-          double u = dr.mate_inv_u ? dr.mate_inv_u[i] : g.uniform();
-          double target = u * wsum, acc = 0.0;
+          const double u = dr.mate_inv_u ? dr.mate_inv_u[i] : g.uniform();
+          const double target = u * wsum;
+          double acc = 0.0;
           int last = -1;
 #pragma unroll
-          for (int r = 0; r < 3 && sel_q < 0; ++r)
-            for (int q = lo[r]; q < hi[r]; ++q) {
-              if (q == p) continue;
-              double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
-              double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              if (d2 <= r2) {
-                double d = sqrt(d2);
+          for (int r = 0; r < 3; ++r)
+            for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
+              const double2 cxy = sxy[q];
+              const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              if (d2 <= r2 && q != p) {
+                const double d = sqrt(d2);
                 acc += (d != 0.0) ? radius - d : 0.0;
                 last = q;
-                if (target < acc) { sel_q = q; break; }
+                if (target < acc) sel_q = q;
               }
             }
           if (sel_q < 0) sel_q = last;
         }
       } else {
-        uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
+        const uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
         int k = (int)choose_k(R, (uint32_t)cnt);
+        if (k < MATE_BUF) {
+          sel_q = buf[k];
+        } else {                         // rare: more than MATE_BUF neighbours, walk again
 #pragma unroll
-        for (int r = 0; r < 3 && sel_q < 0; ++r)
-          for (int q = lo[r]; q < hi[r]; ++q) {
-            if (q == p) continue;
-            double dx = w.sx[q] - fx, dy = w.sy[q] - fy;
-            double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d2 <= r2) {
-              if (k == 0) { sel_q = q; break; }
-              k -= 1;
+          for (int r = 0; r < 3; ++r)
+            for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
+              const double2 cxy = sxy[q];
+              const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              if (d2 <= r2 && q != p) {
+                if (k == 0) sel_q = q;
+                k -= 1;
+              }
             }
-          }
+        }
       }
       if (sel_q >= 0) {
-        double u = dr.mate_u ? dr.mate_u[i] : g.uniform();
+        const double u = dr.mate_u ? dr.mate_u[i] : g.uniform();
         if (u < prm.c.b) mate = w.perm[sel_q];       // species.py:2212-2214
       }
     }
@@ -351,146 +368,169 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
-// phenotype contribution of one 128-bit unit pair (h0, h1) of trait t
-__device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, int Wq, const uint4& h0,
-                                                const uint4& h1) {
-  const int s = tr.chunk_ptr[t * (Wq + 1) + q], e = tr.chunk_ptr[t * (Wq + 1) + q + 1];
+// phenotype contribution of one 128-bit unit pair (h0, h1) of trait t.  The trait table is
+// a CSR over 32-bit words (4 per unit), so the word select is compile-time.
+__device__ __forceinline__ double trait_word(const Traits& tr, int s, int e, uint32_t w0, uint32_t w1,
+                                             bool polygenic) {
   double acc = 0.0;
   for (int k = s; k < e; ++k) {
-    const int bit = tr.te_locus[k] & 127;
-    double geno = 0.5 * (double)(unit_bit(h0, bit) + unit_bit(h1, bit));   // selection.py:30-33
-    if (tr.te_dom) geno = fmin(geno * tr.te_dom[k], 1.0);                    // selection.py:35-39
-    acc += (tr.n_loci[t] > 1) ? geno * tr.te_alpha[k] : geno;               // selection.py:43-47
+    const int sh = __ldg(&tr.te_locus[k]) & 31;
+    const int dosage = (int)((w0 >> sh) & 1u) + (int)((w1 >> sh) & 1u);
+    double geno = 0.5 * (double)dosage;                                     // selection.py:30-33
+    if (tr.te_dom) geno = fmin(geno * __ldg(&tr.te_dom[k]), 1.0);           // selection.py:35-39
+    acc += polygenic ? geno * __ldg(&tr.te_alpha[k]) : geno;                // selection.py:43-47
   }
   return acc;
 }
+__device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, int Wq, const uint4& h0,
+                                                const uint4& h1) {
+  const int* ptr = tr.chunk_ptr + t * (4 * Wq + 1) + 4 * q;
+  const int p0 = __ldg(ptr), p4 = __ldg(ptr + 4);
+  if (p0 == p4) return 0.0;
+  const int p1 = __ldg(ptr + 1), p2 = __ldg(ptr + 2), p3 = __ldg(ptr + 3);
+  const bool poly = tr.n_loci[t] > 1;
+  return trait_word(tr, p0, p1, h0.x, h1.x, poly) + trait_word(tr, p1, p2, h0.y, h1.y, poly) +
+         trait_word(tr, p2, p3, h0.z, h1.z, poly) + trait_word(tr, p3, p4, h0.w, h1.w, poly);
+}
 
+// ----- k_gametes: the genotype-streaming kernel -----------------------------------------
 template <int GW>
-__global__ void __launch_bounds__(256) k_make_offspring(Pop pop, Land land, Params prm, Traits tr, DevDraws dr,
-                                                         Work w, const Counters* c) {
+__global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
+                                                  const Counters* c) {
   const int n = c->n, B = c->B, cur = c->cur, n_free = c->n_free, n_slots = c->n_slots;
   const int64_t t = c->t, max_idx = c->max_idx;
   const int Wq = pop.Wq, T = pop.T;
   const int lane = threadIdx.x & (GW - 1);
   const int ngroups = GSTRIDE / GW;
   const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << ((threadIdx.x & 31) & ~(GW - 1)));
+  const int32_t* __restrict__ gslot = pop.gslot[cur];
   for (int o = GTID / GW; o < B; o += ngroups) {
     const int p = w.off_pair[o];
     const int i0 = w.pairs[2 * p], i1 = w.pairs[2 * p + 1];
     const int64_t oid = max_idx + 1 + o;                               // species.py:614-619
     const int dst = n + o;
-    int cslot = -1;
-    if (!prm.burn) {
-      cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
-      int k0, k1, h0, h1;
-      RngStream gg(prm.seed_lo, prm.seed_hi, oid, SITE_GAMETE, t);
-      if (dr.recomb_keys) {
-        // mating.py:176-181, 204-209: the pair's key slice is popped from its END
-        const int j = o - w.off_start[p];
-        const int e = 2 * (w.off_start[p] + w.nb[p]);
-        k0 = dr.recomb_keys[e - 1 - 2 * j];
-        k1 = dr.recomb_keys[e - 2 - 2 * j];
-      } else {
-        k0 = (int)choose_k(gg.u32(), prm.n_paths);      // species.py:625-627
-        k1 = (int)choose_k(gg.u32(), prm.n_paths);
-      }
-      if (dr.start_homs) {
-        h0 = dr.start_homs[2 * o];
-        h1 = dr.start_homs[2 * o + 1];
-      } else {
-        uint32_t bits = gg.u32();                        // mating.py:133
-        h0 = bits & 1;
-        h1 = (bits >> 1) & 1;
-      }
-      const uint4* P0 = pop.G + (size_t)pop.gslot[cur][i0] * 2 * Wq;
-      const uint4* P1 = pop.G + (size_t)pop.gslot[cur][i1] * 2 * Wq;
-      const uint4* M0 = prm.paths + (size_t)k0 * Wq;
-      const uint4* M1 = prm.paths + (size_t)k1 * Wq;
-      uint4* C = pop.G + (size_t)cslot * 2 * Wq;
-      const uint32_t f0 = h0 ? 0xffffffffu : 0u, f1 = h1 ? 0xffffffffu : 0u;
-      double zacc[GNX_MAX_TRAITS];
+    const int cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
+    int k0, k1, h0, h1;
+    RngStream gg(prm.seed_lo, prm.seed_hi, oid, SITE_GAMETE, t);
+    if (dr.recomb_keys) {
+      // mating.py:176-181, 204-209: the pair's key slice is popped from its END
+      const int j = o - w.off_start[p];
+      const int e = 2 * (w.off_start[p] + w.nb[p]);
+      k0 = dr.recomb_keys[e - 1 - 2 * j];
+      k1 = dr.recomb_keys[e - 2 - 2 * j];
+    } else {
+      k0 = (int)choose_k(gg.u32(), prm.n_paths);      // species.py:625-627
+      k1 = (int)choose_k(gg.u32(), prm.n_paths);
+    }
+    if (dr.start_homs) {
+      h0 = dr.start_homs[2 * o];
+      h1 = dr.start_homs[2 * o + 1];
+    } else {
+      const uint32_t bits = gg.u32();                  // mating.py:133
+      h0 = bits & 1;
+      h1 = (bits >> 1) & 1;
+    }
+    const uint4* P0 = pop.G + (size_t)gslot[i0] * 2 * Wq;
+    const uint4* P1 = pop.G + (size_t)gslot[i1] * 2 * Wq;
+    const uint4* M0 = prm.paths + (size_t)k0 * Wq;
+    const uint4* M1 = prm.paths + (size_t)k1 * Wq;
+    uint4* C = pop.G + (size_t)cslot * 2 * Wq;
+    const uint32_t f0 = h0 ? 0xffffffffu : 0u, f1 = h1 ? 0xffffffffu : 0u;
+    double zacc[GNX_MAX_TRAITS];
 #pragma unroll
-      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) zacc[tt] = 0.0;
-      for (int q = lane; q < Wq; q += GW) {
-        uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
-        uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
-        uint4 m0 = __ldg(M0 + q), m1 = __ldg(M1 + q);
-        m0 = make_uint4(m0.x ^ f0, m0.y ^ f0, m0.z ^ f0, m0.w ^ f0);
-        m1 = make_uint4(m1.x ^ f1, m1.y ^ f1, m1.z ^ f1, m1.w ^ f1);
-        // gamete_c[l] = g_parent_c[l, path[l] XOR start_c]  (mating.py:161-168)
-        uint4 g0 = bitsel(a0, a1, m0), g1 = bitsel(b0, b1, m1);
-        st_stream(C + q, g0);
-        st_stream(C + Wq + q, g1);
+    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) zacc[tt] = 0.0;
+    for (int q = lane; q < Wq; q += GW) {
+      const uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
+      const uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
+      uint4 m0 = __ldg(M0 + q), m1 = __ldg(M1 + q);
+      m0 = make_uint4(m0.x ^ f0, m0.y ^ f0, m0.z ^ f0, m0.w ^ f0);
+      m1 = make_uint4(m1.x ^ f1, m1.y ^ f1, m1.z ^ f1, m1.w ^ f1);
+      // gamete_c[l] = g_parent_c[l, path[l] XOR start_c]  (mating.py:161-168)
+      const uint4 g0 = bitsel(a0, a1, m0), g1 = bitsel(b0, b1, m1);
+      st_stream(C + q, g0);
+      st_stream(C + Wq + q, g1);
 #pragma unroll
-        for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
-          if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
-      }
+      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
+        if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
+    }
 #pragma unroll
-      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) {
-        if (tt < T) {
-          double v = zacc[tt];
+    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) {
+      if (tt < T) {
+        double v = zacc[tt];
 #pragma unroll
-          for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
-          if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + dst] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
-        }
+        for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
+        if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + dst] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
       }
     }
-    if (lane == 0) {
-      // ---- natal dispersal (movement.py:98-141)
-      const double mx = w.mid_x[p], my = w.mid_y[p];
-      RngStream g(prm.seed_lo, prm.seed_hi, oid, SITE_DISP, t);
-      double ox = 0.0, oy = 0.0;
-      int tries = 0;
-      const int max_tries = (dr.disp_dist || dr.disp_dir || dr.disp_choice) ? dr.disp_R : 1000;
-      bool ok = false;
-      while (!ok && tries < max_tries) {
-        double cs, sn;
-        if (prm.c.disp_surf_mode == GNX_SURF_TABLE) {
-          int col = dr.disp_choice ? dr.disp_choice[(size_t)o * dr.disp_R + tries]
-                                   : (int)choose_k(g.u32(), prm.c.surf_approx_len);
-          __half h = prm.disp_tab[((size_t)((int)my) * land.X + (int)mx) * prm.c.surf_approx_len + col];
-          sincos_half(h, &sn, &cs);
-        } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
-          double d = surface_direction_onthefly(
-              g, land.rasters + (size_t)prm.c.disp_surf_layer * land.X * land.Y, land.X, land.Y, (int)mx,
-              (int)my, prm.c.disp_surf_mixture, prm.c.disp_surf_kappa);
-          sincos_half(__float2half_rn((float)d), &sn, &cs);
-        } else {
-          // NB reference passes mu=0, kappa=0 whatever the species' params (species.py:650-653)
-          double d = dr.disp_dir ? dr.disp_dir[(size_t)o * dr.disp_R + tries] : sample_vonmises(g, 0.0, 0.0);
-          sincos(d, &sn, &cs);
-        }
-        double dist = dr.disp_dist ? dr.disp_dist[(size_t)o * dr.disp_R + tries]
-                                   : sample_distance(g, prm.c.disp_distr, prm.c.disp_p1, prm.c.disp_p2);
-        double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
-        if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
-        if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
-        ox = clampd(__dadd_rn(mx, dx), 0.0, land.max_x);
-        oy = clampd(__dadd_rn(my, dy), 0.0, land.max_y);
-        ok = (ox > 0.0 && ox < (double)land.X) && (oy > 0.0 && oy < (double)land.Y);
-        tries += 1;
+    if (lane == 0) pop.gslot[cur][dst] = cslot;
+  }
+}
+
+// ----- k_newborns: natal dispersal, sex, newborn record (one thread per offspring) -------
+__global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
+                                                   Counters* c) {
+  const int n = c->n, B = c->B, cur = c->cur;
+  const int64_t t = c->t, max_idx = c->max_idx;
+  for (int o = GTID; o < B; o += GSTRIDE) {
+    const int p = w.off_pair[o];
+    const int64_t oid = max_idx + 1 + o;
+    const int dst = n + o;
+    // ---- natal dispersal (movement.py:98-141)
+    const double mx = w.mid_x[p], my = w.mid_y[p];
+    RngStream g(prm.seed_lo, prm.seed_hi, oid, SITE_DISP, t);
+    double ox = 0.0, oy = 0.0;
+    int tries = 0;
+    const bool injected = dr.disp_dist || dr.disp_dir || dr.disp_choice;
+    const int max_tries = injected ? dr.disp_R : 1000;
+    bool ok = false;
+    while (!ok && tries < max_tries) {
+      double cs, sn;
+      if (prm.c.disp_surf_mode == GNX_SURF_TABLE) {
+        int col = dr.disp_choice ? dr.disp_choice[(size_t)o * dr.disp_R + tries]
+                                 : (int)choose_k(g.u32(), prm.c.surf_approx_len);
+        __half h = prm.disp_tab[((size_t)((int)my) * land.X + (int)mx) * prm.c.surf_approx_len + col];
+        sincos_half(h, &sn, &cs);
+      } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
+        double d = surface_direction_onthefly(
+            g, land.rasters + (size_t)prm.c.disp_surf_layer * land.X * land.Y, land.X, land.Y, (int)mx,
+            (int)my, prm.c.disp_surf_mixture, prm.c.disp_surf_kappa);
+        sincos_half(__float2half_rn((float)d), &sn, &cs);
+      } else if (dr.disp_dir) {
+        sincos(dr.disp_dir[(size_t)o * dr.disp_R + tries], &sn, &cs);
+      } else {
+        // NB reference passes mu=0, kappa=0 whatever the species' params (species.py:650-653):
+        // vonmises(0, 0) = pi*(2U - 1)
+        sincospi(2.0 * g.uniform() - 1.0, &sn, &cs);
       }
-      if (!ok) { tries = max_tries + 1; atomicOr((int*)&c->err, GNX_ERRBIT_DRAWS); }
-      if (prm.store_debug) w.disp_tries[o] = tries;
-      // ---- sex (species.py:657-662 + the re-draw quirk of individual.py:110-115)
-      RngStream gs(prm.seed_lo, prm.seed_hi, oid, SITE_SEX, t);
-      int first = 0;
-      if (prm.c.sex) {
-        double u = dr.sex_u ? dr.sex_u[o] : gs.uniform();
-        first = u < prm.c.sex_ratio_p;
-      }
-      int sex = 1;
-      if (!first) {
-        double u = dr.sex_redraw_u ? dr.sex_redraw_u[o] : gs.uniform();
-        sex = u < 0.5;
-      }
-      pop.x[cur][dst] = ox;
-      pop.y[cur][dst] = oy;
-      pop.age[cur][dst] = 0;
-      pop.sex[cur][dst] = (int8_t)sex;
-      pop.idx[cur][dst] = oid;
-      pop.gslot[cur][dst] = cslot;
+      double dist = dr.disp_dist ? dr.disp_dist[(size_t)o * dr.disp_R + tries]
+                                 : sample_distance(g, prm.c.disp_distr, prm.c.disp_p1, prm.c.disp_p2);
+      double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
+      if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
+      if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
+      ox = clampd(__dadd_rn(mx, dx), 0.0, land.max_x);
+      oy = clampd(__dadd_rn(my, dy), 0.0, land.max_y);
+      ok = (ox > 0.0 && ox < (double)land.X) && (oy > 0.0 && oy < (double)land.Y);
+      tries += 1;
     }
+    if (!ok) { tries = max_tries + 1; atomicOr((int*)&c->err, GNX_ERRBIT_DRAWS); }
+    if (prm.store_debug) w.disp_tries[o] = tries;
+    // ---- sex (species.py:657-662 + the re-draw quirk of individual.py:110-115)
+    int first = 0;
+    if (prm.c.sex) {
+      double u = dr.sex_u ? dr.sex_u[o] : g.uniform();
+      first = u < prm.c.sex_ratio_p;
+    }
+    int sex = 1;
+    if (!first) {
+      double u = dr.sex_redraw_u ? dr.sex_redraw_u[o] : g.uniform();
+      sex = u < 0.5;
+    }
+    pop.x[cur][dst] = ox;
+    pop.y[cur][dst] = oy;
+    pop.age[cur][dst] = 0;
+    pop.sex[cur][dst] = (int8_t)sex;
+    pop.idx[cur][dst] = oid;
+    if (prm.burn) pop.gslot[cur][dst] = -1;
   }
 }
 
@@ -511,7 +551,7 @@ __global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const
     for (int tt = 0; tt < T; ++tt) {
       double acc = 0.0;
       for (int q = 0; q < Wq; ++q) {
-        const int s = tr.chunk_ptr[tt * (Wq + 1) + q], e = tr.chunk_ptr[tt * (Wq + 1) + q + 1];
+        const int s = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q], e = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q + 4];
         if (s == e) continue;
         uint4 h0 = Gi[q], h1 = Gi[Wq + q];
         acc += trait_partial(tr, tt, q, Wq, h0, h1);
@@ -570,12 +610,15 @@ __global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const C
 // Per-vertex update with the data-independent parts hoisted to setup (gnx_set_density):
 // the 2x2 matrix Q of `_estimate_gradients_2d_global` depends only on the triangulation,
 // so its inverse (v_inv) and the per-edge weights ex/L^3, ey/L^3 (e_wx, e_wy) are
-// precomputed; a sweep then costs 6 flops per edge and no division / sqrt.
-__device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, double* yv, int i) {
+// precomputed; a sweep then costs 6 flops per edge and no division / sqrt.  EL lanes share
+// one vertex (one edge each, shuffle-reduced); EL = 1 is the plain sequential form.
+template <int EL>
+__device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, double* yv, int i, int lane,
+                                            unsigned mask) {
   double s0 = 0, s1 = 0;
   const double f1 = f[i];
   const int je = d.nbr_indptr[i + 1];
-  for (int jj = d.nbr_indptr[i]; jj < je; ++jj) {
+  for (int jj = d.nbr_indptr[i] + lane; jj < je; jj += EL) {
     const int j = __ldg(&d.nbr_indices[jj]);
     const double ex = __ldg(&d.e_ex[jj]), ey = __ldg(&d.e_ey[jj]);
     // (6*(f1 - f2) - 2*df2) with df2 = -ex*y_j0 - ey*y_j1
@@ -583,16 +626,25 @@ __device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, doub
     s0 += tt * __ldg(&d.e_wx[jj]);
     s1 += tt * __ldg(&d.e_wy[jj]);
   }
-  const double r0 = __ldg(&d.v_inv[3 * i]) * s0 + __ldg(&d.v_inv[3 * i + 1]) * s1;
-  const double r1 = __ldg(&d.v_inv[3 * i + 1]) * s0 + __ldg(&d.v_inv[3 * i + 2]) * s1;
-  double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
-  yv[2 * i] = -r0;
-  yv[2 * i + 1] = -r1;
-  change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
+#pragma unroll
+  for (int o = EL / 2; o >= 1; o >>= 1) {
+    s0 += __shfl_xor_sync(mask, s0, o);
+    s1 += __shfl_xor_sync(mask, s1, o);
+  }
+  double change = 0.0;
+  if (lane == 0) {
+    const double r0 = __ldg(&d.v_inv[3 * i]) * s0 + __ldg(&d.v_inv[3 * i + 1]) * s1;
+    const double r1 = __ldg(&d.v_inv[3 * i + 1]) * s0 + __ldg(&d.v_inv[3 * i + 2]) * s1;
+    change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
+    yv[2 * i] = -r0;
+    yv[2 * i + 1] = -r1;
+    change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
+  }
   return change;
 }
 
-#define GS_BLOCK 256
+#define GS_BLOCK 1024
+#define GS_EL 8
 #define GS_SMEM_PTS 1536
 __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, int maxiter, double tol) {
   // blockIdx.x: 0 = species density N, 1 = pair-midpoint density
@@ -615,28 +667,32 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
     yv[2 * k + 1] = 0.0;
   }
   __syncthreads();
+  const int lane = threadIdx.x & (GS_EL - 1), grp = threadIdx.x / GS_EL;
+  const unsigned gmask = ((1u << GS_EL) - 1u) << ((threadIdx.x & 31) & ~(GS_EL - 1));
   int iters = 0;
   for (int it = 0; it < maxiter; ++it) {
     double err = 0.0;
     if (d.colourable) {
       for (int g = 0; g < 4; ++g) {
         const int s = d.g_off[g], e = s + d.g_ni[g] * d.g_nj[g];
-        for (int v = s + threadIdx.x; v < e; v += blockDim.x) err = fmax(err, gs_vertex(d, f, yv, v));
+        for (int v = s + grp; v < e; v += GS_BLOCK / GS_EL)
+          err = fmax(err, gs_vertex<GS_EL>(d, f, yv, v, lane, gmask));
         __syncthreads();
       }
     } else {
       if (threadIdx.x == 0)
-        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex(d, f, yv, v));
+        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex<1>(d, f, yv, v, 0, 1u));
       __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double m = 0.0;
-      for (int k = 0; k < GS_BLOCK / 32; ++k) m = fmax(m, red[k]);
-      s_err = m;
+    if (threadIdx.x < 32) {
+      double m = red[threadIdx.x];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (threadIdx.x == 0) s_err = m;
     }
     __syncthreads();
     if (s_err < tol) { iters = it + 1; break; }

@@ -51,11 +51,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Coun
   const int n = f.size(c);
   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    // striped: consecutive threads touch consecutive elements (coalesced)
+    const int base = tile * SCAN_TILE + threadIdx.x;
     u64 s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k)
-      if (base + k < n) s += f.value(base + k);
+      if (base + k * SCAN_BLOCK < n) s += f.value(base + k * SCAN_BLOCK);
     u64 tot;
     block_excl_scan(s, &tot);
     if (threadIdx.x == 0) tile_sums[tile] = tot;
@@ -83,20 +84,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(F f, const Count
   const int n = f.size(c);
   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    // striped rows of SCAN_BLOCK consecutive elements; one block scan per row
+    const int base = tile * SCAN_TILE + threadIdx.x;
     u64 v[SCAN_ITEMS];
-    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k * SCAN_BLOCK < n) ? f.value(base + k * SCAN_BLOCK) : 0;
+    u64 carry = tile_sums[tile];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-      v[k] = (base + k < n) ? f.value(base + k) : 0;
-      s += v[k];
-    }
-    u64 tot;
-    u64 ex = block_excl_scan(s, &tot) + tile_sums[tile];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-      if (base + k < n) f.apply(base + k, v[k], ex);
-      ex += v[k];
+      u64 tot;
+      const u64 ex = block_excl_scan(v[k], &tot) + carry;
+      if (base + k * SCAN_BLOCK < n) f.apply(base + k * SCAN_BLOCK, v[k], ex);
+      carry += tot;
     }
   }
 }
