@@ -1,0 +1,967 @@
+"""Host-side mirror of the Geonomics API for the accelerated path.
+
+Same names, argument meaning and attributes as the reference (erthward/geonomics v1.4.9;
+`file:line` below are relative to /root/reference/geonomics/): the parameters file
+(`sim/params.py`), `read_parameters_file` (`main.py:308`), `make_model` (`main.py:442`),
+`Model.walk` / `Model.run` (`sim/model.py:966,866`), `Landscape`/`Layer`
+(`structs/landscape.py`), `Community` (`structs/community.py`), `Species`
+(`structs/species.py`), `Individual` (`structs/individual.py`), `GenomicArchitecture`,
+`Trait`, `Recombinations` (`structs/genome.py`).
+
+What changes is where the state lives and who advances it: individuals are
+structure-of-arrays device buffers owned by a `DeviceSpecies`, and one queue pass
+(`sim/model.py:603-667`) is one `gnx_step` of libgnxb200.so.  `Species` remains a mapping
+of ids to `Individual` objects, materialised lazily from the device when someone looks.
+
+Setup code here (layers, genomic architecture, starting genotypes, conductance tables,
+burn-in control) runs on the host with numpy, as it does in the reference; it is not on the
+per-timestep path ("setup").  There is no CPU implementation of the
+time step itself: stepping a Model without libgnxb200.so / a CUDA device raises.
+"""
+import copy
+import os
+import warnings
+from collections import OrderedDict
+
+import numpy as np
+
+from .device import DeviceSpecies
+
+
+# ---------------------------------------------------------------------------------------------
+# parameters (sim/params.py:713-760, 1127-1143)
+# ---------------------------------------------------------------------------------------------
+class ParametersDict(dict):
+    """Nested dict with attribute access (`params.model.T`), like params.py:730."""
+
+    def __init__(self, d=None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = ParametersDict(v) if isinstance(v, dict) and not isinstance(v, ParametersDict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __deepcopy__(self, memo):
+        return ParametersDict(copy.deepcopy(dict(self), memo))
+
+
+def read_parameters_file(filepath):
+    """main.py:308 / params.py:1127-1143: a parameters file is Python source defining `params`."""
+    ns = {'np': np}
+    with open(filepath) as f:
+        exec(compile(f.read(), filepath, 'exec'), ns)
+    p = ParametersDict(ns['params'])
+    name = os.path.splitext(os.path.basename(filepath))[0]
+    p.setdefault('model', ParametersDict())
+    p['model']['name'] = name
+    return p
+
+
+def make_params_dict(params, model_name='unnamed_model'):
+    """main.py:403."""
+    p = ParametersDict(params)
+    p.setdefault('model', ParametersDict())
+    p['model'].setdefault('name', model_name)
+    return p
+
+
+# ---------------------------------------------------------------------------------------------
+# landscape (structs/landscape.py)
+# ---------------------------------------------------------------------------------------------
+class Layer:
+    """landscape.py:34: a 2-D raster in [0, 1] plus georeferencing."""
+
+    def __init__(self, rast, lyr_type, name, dim, res=(1, 1), ulc=(0, 0), prj=None, idx=None):
+        self.idx = idx
+        self.type = lyr_type
+        self.name = str(name)
+        self.dim = tuple(dim)
+        self.res = res
+        self.ulc = ulc
+        self.prj = prj
+        self.rast = np.array(rast, dtype=np.float64)
+        assert self.rast.shape == (self.dim[1], self.dim[0]), (
+            'Layer raster must have shape (dim_y, dim_x) = %s, got %s' % ((self.dim[1], self.dim[0]),
+                                                                          self.rast.shape))
+        self._is_K = []
+
+
+def _make_random_lyr(dim, n_pts, interp_method='cubic', num_hab_types=2, dist='beta', alpha=0.05, beta=0.05):
+    """landscape.py:411-470."""
+    from scipy import interpolate
+    r = np.random
+    max_dim = max(dim)
+    if interp_method == 'nearest':
+        vals = (r.rand(n_pts) if dist == 'unif' else r.beta(alpha, beta, n_pts)) * (num_hab_types - 1)
+    else:
+        vals = r.rand(n_pts) if dist == 'unif' else r.beta(alpha, beta, n_pts)
+    pts = r.normal(max_dim / 2, max_dim * 2, [n_pts, 2])
+    grid_x, grid_y = np.mgrid[1:max_dim:complex('%ij' % max_dim), 1:max_dim:complex('%ij' % max_dim)]
+    I = interpolate.griddata(pts, vals, (grid_x, grid_y), method=interp_method)
+    if interp_method == 'nearest':
+        I = I.round().astype(float)
+    if interp_method == 'cubic':
+        I = I + abs(I.min()) + (0.01 * r.rand())
+        I = I / (I.max() + (0.01 * r.rand()))
+    if dim[0] != dim[1]:
+        I = I[:dim[1], :dim[0]]
+    return I
+
+
+def _make_defined_lyr(dim, rast, pts=None, vals=None, interp_method='cubic', num_hab_types=2):
+    """landscape.py:473-519."""
+    if rast is not None:
+        return np.array(rast, dtype=np.float64)
+    from scipy import interpolate
+    r = np.random
+    if interp_method == 'nearest':
+        vals = vals * (num_hab_types - 1)
+    max_dim = max(dim)
+    grid_x, grid_y = np.mgrid[1:max_dim:complex('%ij' % max_dim), 1:max_dim:complex('%ij' % max_dim)]
+    I = interpolate.griddata(pts, vals, (grid_x, grid_y), method=interp_method)
+    if interp_method == 'nearest':
+        I = I.round().astype(float)
+    if interp_method == 'cubic':
+        I = I + abs(I.min()) + (0.01 * r.rand())
+        I = I / (I.max() + (0.01 * r.rand()))
+    if dim[0] != dim[1]:
+        I = I[:dim[1], :dim[0]]
+    return I
+
+
+class _LandscapeChanger:
+    """ops/change.py:103-152, 302-357: scheduled, linearly interpolated raster series."""
+
+    def __init__(self, land, change_params):
+        changes = []
+        for lyr_num, events in change_params.items():
+            start_rast = land[lyr_num].rast
+            for _, ev in sorted(events.items()):
+                change_rast = np.array(ev['change_rast'], dtype=np.float64)
+                n_steps = int(ev['n_steps'])
+                timesteps = np.int64(np.round(np.linspace(ev['start_t'], ev['end_t'], n_steps)))
+                # linspace(start, end, n_steps + 1)[1:] per cell (change.py:349-354)
+                for k, t in enumerate(timesteps):
+                    rast = start_rast + (change_rast - start_rast) * ((k + 1) / float(n_steps))
+                    if k == n_steps - 1:
+                        rast = change_rast.copy()
+                    changes.append((int(t), lyr_num, rast))
+                start_rast = change_rast
+        self.changes = sorted(changes, key=lambda c: c[0])
+        self.change_info = {k: dict(v) for k, v in change_params.items()}
+        self._pos = 0
+
+    def _make_change(self, t, land):
+        made = False
+        while self._pos < len(self.changes) and self.changes[self._pos][0] == t:
+            _, lyr_num, rast = self.changes[self._pos]
+            land._set_raster(lyr_num, rast)
+            self._pos += 1
+            made = True
+        return made
+
+
+class Landscape(dict):
+    """landscape.py:199: dict of Layers keyed by layer number."""
+
+    def __init__(self, lyrs, res=(1, 1), ulc=(0, 0), prj=None):
+        super().__init__(lyrs)
+        first = next(iter(lyrs.values()))
+        self.dim = first.dim
+        self.res = res
+        self.ulc = ulc
+        self.prj = prj
+        self._res_ratio = (res[0] / res[1], 1) if res[0] != res[1] else (1, 1)
+        self._dim_om = len(str(max(self.dim)))
+        self._changer = None
+        self._listeners = []        # attached Species (device raster mirrors)
+        for n, lyr in self.items():
+            lyr.idx = n
+
+    def _set_raster(self, lyr_num, rast):
+        """landscape.py:353-354 (+ the device mirror; Species._set_K for the K layer)."""
+        self[lyr_num].rast = np.array(rast, dtype=np.float64)
+        for spp in self._listeners:
+            spp._on_raster_change(lyr_num, self[lyr_num].rast)
+
+    def _make_change(self, t, verbose=False):
+        if self._changer is not None:
+            self._changer._make_change(t, self)
+
+
+def _make_landscape(params, num_hab_types=2):
+    """landscape.py:522-674 ('random' and 'defined' layers; 'file'/'nlmpy' need rasterio /
+    nlmpy, which this image lacks -> they raise)."""
+    main = params.landscape.main
+    dim = tuple(main.dim)
+    res = tuple(main.res) if main.get('res') is not None else (1, 1)
+    ulc = tuple(main.ulc) if main.get('ulc') is not None else (0, 0)
+    prj = main.get('prj')
+    lyrs = {}
+    for n, (name, lp) in enumerate(params.landscape.layers.items()):
+        init = lp['init']
+        keys = list(init.keys())
+        if len(keys) != 1:
+            raise ValueError("Layer '%s' must have parameters for exactly one layer type" % name)
+        lyr_type = keys[0]
+        if lyr_type == 'random':
+            rast = _make_random_lyr(dim, num_hab_types=num_hab_types, **dict(init[lyr_type]))
+        elif lyr_type == 'defined':
+            rast = _make_defined_lyr(dim, num_hab_types=num_hab_types, **dict(init[lyr_type]))
+        else:
+            raise NotImplementedError("layer type '%s' needs rasterio/nlmpy, not available here" % lyr_type)
+        rast = np.clip(rast, 0, 1)                              # landscape.py:646-648
+        lyrs[n] = Layer(rast, lyr_type, name, dim, res, ulc, prj, idx=n)
+    land = Landscape(lyrs, res=res, ulc=ulc, prj=prj)
+    change_params = {}
+    for n, (name, lp) in enumerate(params.landscape.layers.items()):
+        if 'change' in lp:
+            change_params[n] = lp['change']
+    if change_params:
+        land._changer = _LandscapeChanger(land, change_params)
+    return land
+
+
+# ---------------------------------------------------------------------------------------------
+# genomic architecture (structs/genome.py)
+# ---------------------------------------------------------------------------------------------
+class Recombinations:
+    """genome.py:47-281: cache of `n` pre-simulated recombination events.  The reference
+    stores each as a bitarray 'subsetter' of '10'/'01' units per locus; here only the
+    homologue bit per locus is kept (`_paths`, uint8[n, L])."""
+
+    def __init__(self, L, positions, n, r_distr_alpha, r_distr_beta, recomb_rates, jitter_breakpoints=False):
+        self._L = L
+        self._positions = np.arange(L) if positions is None else np.sort(np.array(positions))
+        self._n = n
+        self._r_distr_alpha = r_distr_alpha
+        self._r_distr_beta = r_distr_beta
+        self._jitter_breakpoints = jitter_breakpoints
+        if recomb_rates is not None:
+            assert len(recomb_rates) == len(self._positions)
+            assert recomb_rates[0] == 0
+            self._rates = np.array(recomb_rates, dtype=np.float64)
+        else:
+            self._rates = self._draw_recombination_rates()
+        self._paths = None
+        self._breakpoints = None
+
+    def _draw_recombination_rates(self):
+        """genome.py:163-185."""
+        n = len(self._positions)
+        if self._r_distr_alpha is not None and self._r_distr_beta is not None:
+            rates = np.clip(np.random.beta(a=self._r_distr_alpha, b=self._r_distr_beta, size=n), 0, 0.5)
+        elif self._r_distr_alpha is not None:
+            rates = np.ones(n) * self._r_distr_alpha
+        else:
+            rates = np.ones(n) * (1 / self._L)
+        rates[0] = 0
+        return rates
+
+    def _set_events(self):
+        """genome.py:188-230: n x binomial(1, rates); path = cumsum % 2."""
+        ev = np.random.random((self._n, len(self._rates))) < self._rates[None, :]
+        self._breakpoints = {k: self._positions[np.where(e)] for k, e in enumerate(ev)}
+        self._paths = (np.cumsum(ev, axis=1) % 2).astype(np.uint8)
+
+    def _get_subsetter(self, event_key):
+        """The reference's '10'/'01' bit pattern for one event, as a bool array of length 2L."""
+        p = self._paths[event_key]
+        out = np.zeros(2 * len(p), dtype=bool)
+        out[0::2] = p == 0
+        out[1::2] = p == 1
+        return out
+
+
+class Trait:
+    """genome.py:284-437."""
+
+    def __init__(self, idx, name, phi, n_loci, mu, layer, alpha_distr_mu, alpha_distr_sigma, max_alpha_mag,
+                 gamma, univ_adv):
+        self.idx = idx
+        self.name = name
+        self.phi = phi
+        self.n_loci = n_loci
+        self.mu = 0 if mu is None else mu
+        self.lyr_num = layer
+        self.alpha_distr_mu = alpha_distr_mu
+        self.alpha_distr_sigma = alpha_distr_sigma
+        self.max_alpha_mag = max_alpha_mag
+        self.gamma = gamma
+        self.univ_adv = univ_adv
+        self.loci = np.int64([])
+        self.loci_idxs = None
+        self.alpha = np.array([])
+
+    def _get_phi(self, spp):
+        if type(self.phi) in (float, int):
+            return np.array([self.phi] * len(spp))
+        return self.phi[spp._cells[:, 1], spp._cells[:, 0]]
+
+
+class GenomicArchitecture:
+    """genome.py:440-810 (use_tskit=False path)."""
+
+    def __init__(self, dom, g_params, land, recomb_rates=None, recomb_positions=None):
+        self.x = 2
+        self.L = g_params.L
+        self.p = None
+        self.pleiotropy = g_params.get('pleiotropy', False)
+        self.dom = dom
+        self._use_dom = bool(np.any(self.dom))
+        self.sex = g_params.get('sex', False)
+        self.use_tskit = bool(g_params.get('use_tskit', False))
+        self.tskit_simp_interval = g_params.get('tskit_simp_interval', 100)
+        self.mu_neut = g_params.get('mu_neut', 0)
+        self.mu_delet = g_params.get('mu_delet', 0)
+        self.neut_loci = np.array(range(self.L))
+        self.nonneut_loci = np.array([])
+        self.delet_loci = np.int64([])
+        self.delet_loci_s = np.array([])
+        self.traits = None
+        if 'traits' in g_params and g_params['traits']:
+            self.traits = _make_traits(g_params.traits, land)
+        mus = [m for m in (self.mu_neut, self.mu_delet) if m is not None]
+        if self.traits is not None:
+            mus = mus + [t.mu for t in self.traits.values()]
+        self._mu_tot = sum(mus)
+        self._mu_nonneut = self._mu_tot - (self.mu_neut or 0)
+        self._mutables = None
+        self.recombinations = Recombinations(self.L, recomb_positions, g_params.get('n_recomb_sims', 10000),
+                                             g_params.get('r_distr_alpha'), g_params.get('r_distr_beta'),
+                                             recomb_rates, g_params.get('jitter_breakpoints', False))
+
+    def _draw_trait_alpha(self, trait_num, n=1):
+        """genome.py:666-687."""
+        trt = self.traits[trait_num]
+        if trt.alpha_distr_sigma == 0:
+            alpha = trt.alpha_distr_mu * np.array([1 - (i % 2) * 2 for i in range(n)])
+        else:
+            alpha = np.random.normal(trt.alpha_distr_mu, trt.alpha_distr_sigma, n)
+            if trt.max_alpha_mag is not None:
+                alpha = np.clip(alpha, -trt.max_alpha_mag, trt.max_alpha_mag)
+        if trt.n_loci == 1:
+            alpha = np.abs(alpha)
+        return alpha
+
+    def _set_trait_loci(self, trait_num, loci=None, alpha=None):
+        """genome.py:696-750 (initial assignment)."""
+        n = self.traits[trait_num].n_loci
+        assert n <= self.L
+        if loci is None:
+            pool = self.neut_loci if not self.pleiotropy else np.arange(self.L)
+            loci = set(np.random.choice(pool, size=n, replace=False))
+        trt = self.traits[trait_num]
+        trt.loci = np.sort(np.hstack((trt.loci, np.array([*loci])))).astype(np.int64)
+        trt.n_loci = trt.loci.size
+        self.nonneut_loci = np.array(sorted([*self.nonneut_loci] + [*loci]))
+        self.neut_loci = np.array(sorted(set(self.neut_loci).difference(set(self.nonneut_loci))))
+        effects = np.array([*np.atleast_1d(alpha)]) if alpha is not None else self._draw_trait_alpha(trait_num, n)
+        if n == 1:
+            effects = np.array([0.5])
+        assert len(loci) == len(effects)
+        trt.alpha = np.hstack((trt.alpha, effects))
+
+
+def _make_traits(traits_params, land):
+    """genome.py:826-867."""
+    traits = {}
+    for n, (name, v) in enumerate(traits_params.items()):
+        v = dict(v)
+        layer = v.pop('layer')
+        if isinstance(layer, str):
+            nums = [num for num, lyr in land.items() if lyr.name == layer]
+        else:
+            nums = [num for num, lyr in land.items() if lyr.idx == layer]
+        assert len(nums) == 1, 'Expected a single Layer named %s for Trait %s' % (layer, name)
+        traits[n] = Trait(n, name, layer=nums[0], **v)
+        if traits[n].n_loci == 1 and traits[n].mu != 0:
+            warnings.warn("Coercing Trait %i ('%s') to a 0 mutation rate because it is monogenic." % (n, name))
+            traits[n].mu = 0
+    return traits
+
+
+def _make_genomic_architecture(spp_params, land):
+    """genome.py:870-1062 (no custom CSV file in this build)."""
+    g_params = spp_params.gen_arch
+    if g_params.get('gen_arch_file') is not None:
+        import pandas as pd
+        gaf = pd.read_csv(g_params.gen_arch_file)
+        assert len(gaf) == g_params.L
+    else:
+        gaf = None
+    g_params['sex'] = spp_params.mating.sex
+    recomb_rates = recomb_positions = None
+    if gaf is not None:
+        recomb_rates = gaf['r'].values
+        recomb_positions = gaf['locus'].values
+        dom = gaf['dom'].values
+    else:
+        dom = np.array([int(g_params.dom)] * g_params.L)
+    ga = GenomicArchitecture(dom, g_params, land, recomb_rates, recomb_positions)
+    if ga.traits is not None:
+        if gaf is not None:
+            names = {t.name: n for n, t in ga.traits.items()}
+            tcol = [[names[v.strip()] for v in str(row).split(',') if v.strip() in names] for row in gaf['trait']]
+            acol = [[float(a) for a in str(row).split(',')] if str(row) != 'nan' else [] for row in gaf['alpha']]
+            for tn in ga.traits:
+                loci = np.array([l for l, ts in zip(gaf['locus'], tcol) if tn in ts])
+                alphas = np.array([a[ts.index(tn)] for ts, a in zip(tcol, acol) if tn in ts])
+                ga._set_trait_loci(tn, loci=loci, alpha=alphas)
+        else:
+            for tn in ga.traits:
+                ga._set_trait_loci(tn)
+    if gaf is None:
+        spf = g_params.get('start_p_fixed')
+        if spf is not None:
+            if isinstance(spf, bool):
+                ga.p = np.array([0.5] * g_params.L) if spf else np.random.beta(1, 1, g_params.L)
+            else:
+                assert 0 <= spf <= 1
+                ga.p = np.array([spf] * g_params.L, dtype=np.float64)
+        else:
+            ga.p = np.random.beta(1, 1, g_params.L)
+        if g_params.get('start_neut_zero') and len(ga.neut_loci) > 0:
+            ga.p[ga.neut_loci] = 0
+    else:
+        ga.p = gaf['p'].values
+    ga.recombinations._set_events()
+    return ga
+
+
+# ---------------------------------------------------------------------------------------------
+# conductance surfaces (utils/spatial.py:149-184, 365-461) -- table mode, built on the host
+# ---------------------------------------------------------------------------------------------
+class _ConductanceSurface:
+    def __init__(self, cond_lyr, mixture=True, approx_len=5000, vm_distr_kappa=12):
+        self.dim = cond_lyr.dim
+        self.mix = mixture
+        self.lyr_num = cond_lyr.idx
+        self.approx_len = 5000 if approx_len is None else approx_len
+        self.kappa = 12 if vm_distr_kappa is None else vm_distr_kappa
+        self.surf = _make_conductance_surface(cond_lyr.rast, self.mix, self.approx_len, self.kappa)
+
+
+def _make_conductance_surface(rast, mixture=True, approx_len=5000, vm_distr_kappa=12):
+    """spatial.py:432-461 (vectorised over cells; same distributions)."""
+    pi = np.pi
+    dirs = np.array([-3 * pi / 4, -pi / 2, -pi / 4, pi, 0, 3 * pi / 4, pi / 2, pi / 4])
+    Y, X = rast.shape
+    emb = np.zeros((Y + 2, X + 2))
+    emb[1:-1, 1:-1] = rast
+    offs = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]
+    neigh = np.stack([emb[1 + di:1 + di + Y, 1 + dj:1 + dj + X] for di, dj in offs], axis=-1)   # [Y, X, 8]
+    if mixture:
+        s = neigh.sum(axis=-1, keepdims=True)
+        probs = np.where(s > 0, neigh / np.where(s > 0, s, 1), 0.125)
+        cdf = np.cumsum(probs, axis=-1)
+        u = np.random.random((Y, X, approx_len))
+        pick = (u[..., None] >= cdf[:, :, None, :]).sum(axis=-1).clip(max=7)
+        loc = dirs[pick]
+    else:
+        mx = neigh.max(axis=-1, keepdims=True)
+        is_max = neigh == mx
+        loc = ((is_max * dirs).sum(axis=-1) / is_max.sum(axis=-1))[..., None] * np.ones((1, 1, approx_len))
+    surf = loc + np.random.vonmises(0, vm_distr_kappa, size=(Y, X, approx_len))
+    return np.float16(surf)
+
+
+# ---------------------------------------------------------------------------------------------
+# individuals and species (structs/individual.py, structs/species.py)
+# ---------------------------------------------------------------------------------------------
+class Individual:
+    """individual.py:26: a *view* of one individual's current state."""
+    __slots__ = ('idx', 'x', 'y', 'age', 'sex', 'e', 'z', 'fit', 'g', '_individuals_tab_id', '_nodes_tab_ids')
+
+    def __init__(self, idx, x, y, age=0, new_genome=None, sex=None, e=None, z=None, fit=None):
+        self.idx = idx
+        self.g = new_genome
+        self.x = float(x)
+        self.y = float(y)
+        self.sex = sex
+        self.age = age
+        self.e = e
+        self.z = [] if z is None else z
+        self.fit = fit
+        self._individuals_tab_id = None
+        self._nodes_tab_ids = {}
+
+
+class _ParamsVals:
+    def __init__(self, spp_name):
+        self.spp_name = spp_name
+
+
+class Species:
+    """species.py:77.  Mapping of individual id -> Individual (species order), backed by a
+    DeviceSpecies.  Parameter attributes (`spp.b`, `spp.mating_radius`, ...) resolve through
+    `_pv` like the reference (species.py:71-74, 405-425)."""
+
+    def __init__(self, name, idx, land, spp_params, genomic_architecture=None, N=0, seed=0):
+        self.idx = idx
+        self.name = str(name)
+        self._land = land
+        self._land_dim = land.dim
+        self._land_res = land.res
+        self._land_res_ratio = land._res_ratio
+        self.t = -1
+        self.burned = False
+        self.extinct = False
+        self.start_N = N
+        self.max_ind_idx = N - 1
+        self.N = None
+        self.K = None
+        self.K_layer = None
+        self.K_factor = None
+        self.Nt = []
+        self.n_births = []
+        self.n_deaths = []
+        self._move = False
+        self._move_surf = None
+        self._disp_surf = None
+        self._changer = None
+        self.sex_ratio = 0.5                      # species.py:399 (shadows the parameter, as there)
+        self._pv = _ParamsVals(self.name)
+        for section in ('mating', 'mortality', 'movement'):
+            if section in spp_params:
+                for att, val in spp_params[section].items():
+                    if not isinstance(val, dict):
+                        if att == 'sex_ratio':
+                            val = val / (val + 1)
+                        setattr(self._pv, att, val)
+                if section == 'movement' and spp_params[section].move:
+                    self._move = True
+        self.gen_arch = genomic_architecture
+        self.selection = (self.gen_arch is not None and
+                          ((self.gen_arch.mu_delet or 0) > 0 or self.gen_arch.traits is not None))
+        self.mutate = (self.gen_arch is not None and self.gen_arch._mu_tot is not None and
+                       self.gen_arch._mu_tot > 0)
+        self._seed = seed
+        self._dev = None
+        self._cache = None                     # host copy of the device state (lazy)
+        self._inds = None                      # OrderedDict of Individual views (lazy)
+        self._init_pop = None
+
+    def __getattr__(self, attr):
+        pv = self.__dict__.get('_pv')
+        if pv is not None and hasattr(pv, attr):
+            return getattr(pv, attr)
+        raise AttributeError("Species has no attribute '%s'" % attr)
+
+    # ---- device attachment --------------------------------------------------------------
+    def _device_params(self):
+        prm = dict(b=self.b, R=self.R, lam=self.n_births_distr_lambda, n_births_fixed=self.n_births_fixed,
+                   mating_radius=self.mating_radius, d_min=self.d_min, d_max=self.d_max, sex=self.sex,
+                   sex_ratio_p=self.sex_ratio, max_age=self.max_age, K_layer=self.K_layer,
+                   K_factor=self.K_factor, move=self._move,
+                   choose_nearest=self.choose_nearest_mate, inverse_dist=self.inverse_dist_mating,
+                   density_grid_window_width=self.density_grid_window_width)
+        if self._move:
+            prm['move_distr'] = (self.movement_distance_distr, self.movement_distance_distr_param1,
+                                 self.movement_distance_distr_param2)
+            prm['direction_mu'] = self.direction_distr_mu
+            prm['direction_kappa'] = self.direction_distr_kappa
+        prm['disp_distr'] = (self.dispersal_distance_distr, self.dispersal_distance_distr_param1,
+                             self.dispersal_distance_distr_param2)
+        for nm, surf in (('move_surf', self._move_surf), ('disp_surf', self._disp_surf)):
+            if surf is not None:
+                prm[nm] = dict(table=surf.surf, layer=surf.lyr_num, mixture=surf.mix, kappa=surf.kappa)
+        return prm
+
+    def _attach(self, capacity=None):
+        land = self._land
+        rasters = np.stack([land[l].rast for l in range(len(land))])
+        ga = None
+        if self.gen_arch is not None:
+            traits = []
+            for t in (self.gen_arch.traits or {}).values():
+                traits.append(dict(loci=t.loci, alpha=t.alpha, phi=t.phi, gamma=t.gamma, lyr_num=t.lyr_num,
+                                   univ_adv=t.univ_adv))
+            ga = dict(L=self.gen_arch.L, paths=self.gen_arch.recombinations._paths, traits=traits,
+                      dom=np.asarray(self.gen_arch.dom, dtype=np.int8))
+        if capacity is None:
+            capacity = int(max(4096, 3.0 * float(np.sum(self.K)), 2 * self.start_N))
+        self._dev = DeviceSpecies(land.dim, rasters, self._device_params(), ga, capacity=capacity,
+                                  seed=self._seed, res_ratio=self._land_res_ratio)
+        land._listeners.append(self)
+        p = self._init_pop
+        self._dev.set_burn(not self.burned)
+        self._dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], max_ind_idx=self.max_ind_idx)
+        self._init_pop = None
+        self._invalidate()
+
+    def _on_raster_change(self, lyr_num, rast):
+        if self._dev is not None:
+            self._dev.set_raster(lyr_num, rast)
+        if lyr_num == self.K_layer:
+            self._set_K(self._land)
+
+    # ---- the queue entries (sim/model.py:603-667) -------------------------------------
+    def _set_K(self, land):
+        """species.py:546-547."""
+        self.K = land[self.K_layer].rast * self.K_factor
+
+    def _set_t(self):
+        self.t += 1
+
+    def _step(self, n=1):
+        """_set_age_stage + _do_movement + _do_pop_dynamics + _set_Nt for n time steps
+        (species.py:567, 582, 822, 554) on the device."""
+        self._dev.step(n)
+        recs = self._dev.step_records()
+        for r in recs:
+            self.Nt.append(int(r['Nt']))
+            self.n_births.append(int(r['n_births']))
+            self.n_deaths.append(int(r['n_deaths']))
+        if recs:
+            self.max_ind_idx += int(sum(r['n_births'] for r in recs))
+            if recs[-1]['Nt'] == 0:
+                self.extinct = True                  # demography.py:329
+        self._invalidate()
+
+    def _invalidate(self):
+        self._cache = None
+        self._inds = None
+        self.N = None
+
+    # ---- lazy host views -----------------------------------------------------------------
+    def _state(self):
+        if self._cache is None:
+            if self._dev is None:
+                p = self._init_pop
+                self._cache = dict(x=p['x'], y=p['y'], age=p['age'], sex=p['sex'], idx=p['idx'],
+                                   z=np.zeros((len(p['x']), 0)), fit=np.full(len(p['x']), np.nan),
+                                   e=None, g=None)
+            else:
+                self._cache = self._dev.download(genomes=self.burned and self.gen_arch is not None, e=True)
+        return self._cache
+
+    def _individuals(self):
+        if self._inds is None:
+            s = self._state()
+            inds = OrderedDict()
+            g = s.get('g')
+            has_z = s['z'] is not None and s['z'].shape[1] > 0
+            for k in range(len(s['x'])):
+                inds[int(s['idx'][k])] = Individual(
+                    int(s['idx'][k]), s['x'][k], s['y'][k], int(s['age'][k]),
+                    None if g is None else g[k], int(s['sex'][k]),
+                    None if s.get('e') is None else list(s['e'][k]),
+                    list(s['z'][k]) if has_z else [], None if np.isnan(s['fit'][k]) else float(s['fit'][k]))
+            self._inds = inds
+        return self._inds
+
+    def __len__(self):
+        if self._cache is not None:
+            return len(self._cache['x'])
+        if self._dev is None:
+            return len(self._init_pop['x'])
+        return self._dev.population_size()
+
+    def __iter__(self):
+        return iter(self._individuals())
+
+    def __getitem__(self, idx):
+        return self._individuals()[idx]
+
+    def __contains__(self, idx):
+        return idx in self._individuals()
+
+    def keys(self):
+        return self._individuals().keys()
+
+    def values(self):
+        return self._individuals().values()
+
+    def items(self):
+        return self._individuals().items()
+
+    @property
+    def _coords(self):
+        s = self._state()
+        return np.stack([s['x'], s['y']], axis=1)
+
+    @property
+    def _cells(self):
+        return np.int32(np.floor(self._coords))
+
+    # getters (species.py:1364-1499)
+    def _get_x(self, individs=None):
+        return self._sel(self._state()['x'], individs)
+
+    def _get_y(self, individs=None):
+        return self._sel(self._state()['y'], individs)
+
+    def _get_coords(self, individs=None, as_float=True):
+        c = self._sel(self._coords, individs)
+        return c if as_float else np.int32(np.floor(c))
+
+    def _get_cells(self, individs=None):
+        return self._get_coords(individs, as_float=False)
+
+    def _get_age(self, individs=None):
+        return self._sel(self._state()['age'], individs)
+
+    def _get_sex(self, individs=None):
+        return self._sel(self._state()['sex'], individs)
+
+    def _get_z(self, trait_num=None, individs=None):
+        z = self._sel(self._state()['z'], individs)
+        return z if trait_num is None else z[:, trait_num]
+
+    def _get_e(self, lyr_num=None, individs=None):
+        e = self._sel(self._state()['e'], individs)
+        return e if lyr_num is None else e[:, lyr_num]
+
+    def _get_fit(self, individs=None):
+        return self._sel(self._state()['fit'], individs)
+
+    def _get_genotypes(self, loci=None, individs=None, biallelic=True, as_dict=False):
+        g = self._sel(self._state()['g'], individs)
+        if loci is not None:
+            g = g[:, loci, :]
+        if not biallelic:
+            g = g.mean(axis=2)
+        if as_dict:
+            ids = self._sel(self._state()['idx'], individs)
+            return {int(i): gi for i, gi in zip(ids, g)}
+        return g
+
+    def _sel(self, arr, individs):
+        if individs is None or arr is None:
+            return arr
+        ids = self._state()['idx']
+        pos = {int(v): k for k, v in enumerate(ids)}
+        return arr[[pos[int(i)] for i in individs]]
+
+    def _calc_density(self, normalize=False, as_layer=False, set_N=False):
+        """species.py:845-882: the N raster of the last completed step (device resident)."""
+        dens = self._dev.raster('N_RAST')
+        if normalize:
+            dens = (dens - dens.min()) / (dens.max() - dens.min())
+        if set_N:
+            self.N = dens
+            return None
+        return dens
+
+    # ---- post burn-in genome assignment (species.py:956-1094, genome.py:1108-1157) ----
+    def _set_genomes_and_tables(self, burn_T=None, T=None):
+        s = self._dev.download(genomes=False)
+        n = len(s['x'])
+        L = self.gen_arch.L
+        g = np.zeros((n, L, 2), dtype=np.int8)
+        flat = g.reshape(n, L, 2)
+        p = self.gen_arch.p
+        for site in range(L):
+            freq = p[site]
+            n_mut = int(round(2 * n * freq, 0))
+            if n_mut == n * 2 and freq < 1:
+                n_mut -= 1
+            if n_mut == 0 and freq > 0:
+                n_mut = 1
+            if n_mut > 0:
+                hom = np.random.permutation(2 * n)[:n_mut]
+                flat[hom // 2, site, hom % 2] = 1
+        self._dev.set_burn(False)
+        self._dev.upload(s['x'], s['y'], s['age'], s['sex'], s['idx'], g=g, max_ind_idx=s['max_ind_idx'])
+        self._invalidate()
+
+
+class Community(dict):
+    """community.py:25."""
+
+    def __init__(self, land, spps):
+        super().__init__(spps)
+        self.n_spps = len(spps)
+        self.t = -1
+        self.burned = False
+
+
+def _make_species(land, name, idx, spp_params, seed=0):
+    """species.py:3276-3397."""
+    init = dict(spp_params.init)
+    ga = _make_genomic_architecture(spp_params, land) if 'gen_arch' in spp_params else None
+    N = int(init.pop('N'))
+    spp = Species(name, idx, land, spp_params, ga, N=N, seed=seed)
+    # individual.py:188-229: uniform positions, Bernoulli(0.5) sex (with the re-draw quirk of
+    # Individual.__init__, individual.py:110-115: a drawn 0 is re-drawn)
+    xy = np.random.rand(N, 2) * np.array(land.dim)
+    x = np.clip(xy[:, 0], 0, land.dim[0] - 0.001)
+    y = np.clip(xy[:, 1], 0, land.dim[1] - 0.001)
+    sex = np.random.binomial(1, 0.5, N)
+    sex = np.where(sex == 1, 1, np.random.binomial(1, 0.5, N)).astype(np.int8)
+    spp._init_pop = dict(x=x, y=y, age=np.zeros(N, np.int32), sex=sex, idx=np.arange(N, dtype=np.int64))
+    K_layer = [lyr for lyr in land.values() if lyr.name == init['K_layer']]
+    assert len(K_layer) == 1, 'K_layer must name a single Layer'
+    spp.K_layer = K_layer[0].idx
+    spp.K_factor = init['K_factor']
+    K_layer[0]._is_K.append(idx)
+    spp._set_K(land)
+    mv = spp_params.get('movement', {})
+    if spp._move and 'move_surf' in mv:
+        ms = dict(mv['move_surf'])
+        lyr = [k for k, v in land.items() if v.name == ms.pop('layer')]
+        assert len(lyr) == 1
+        spp._move_surf = _ConductanceSurface(land[lyr[0]], **ms)
+    if 'disp_surf' in mv:
+        ds = dict(mv['disp_surf'])
+        lyr = [k for k, v in land.items() if v.name == ds.pop('layer')]
+        assert len(lyr) == 1
+        spp._disp_surf = _ConductanceSurface(land[lyr[0]], **ds)
+    return spp
+
+
+# ---------------------------------------------------------------------------------------------
+# model (sim/model.py)
+# ---------------------------------------------------------------------------------------------
+class Model:
+    """sim/model.py:47.  `walk` / `run` keep their reference signatures."""
+
+    def __init__(self, name, params, verbose=False):
+        self.params = copy.deepcopy(params)
+        m = self.params.model
+        self.name = name or 'unnamed_model'
+        self._verbose = verbose
+        self.seed = None
+        if 'seed' in m and m.seed is not None:
+            self.seed = m.seed.num if isinstance(m.seed, dict) else m.seed
+            if self.seed is not None:
+                np.random.seed(self.seed)                   # model.py:362-366
+        self.burn_T = m.burn_T
+        self.burn_t = -1
+        self.T = m.T
+        self.t = -1
+        its = m.get('its', {'n_its': 1})
+        self.n_its = its['n_its']
+        self.its = [*range(self.n_its)][::-1]
+        self.it = -1
+        self.land = _make_landscape(self.params)
+        spps = {}
+        for n, (sname, sp) in enumerate(self.params.comm.species.items()):
+            spps[n] = _make_species(self.land, sname, n, sp, seed=(self.seed or 0) * 1000003 + n)
+        self.comm = Community(self.land, spps)
+        for spp in self.comm.values():
+            spp._attach()
+        self.reassign_genomes = True
+        self._never_been_run = True
+
+    # ---- one queue pass (model.py:603-667, 699-787); each species is advanced itself (the
+    # reference's late-binding lambdas advance only the last species)
+    def _do_timestep(self, mode):
+        if mode == 'burn':
+            self.burn_t += 1
+            for spp in self.comm.values():
+                if not any(s.extinct for s in self.comm.values()):
+                    spp._step(1)
+            self._check_comm_burned()
+            if all(spp.burned for spp in self.comm.values()):
+                if self.reassign_genomes:
+                    for spp in self.comm.values():
+                        if spp.gen_arch is not None:
+                            spp._set_genomes_and_tables(self.burn_T, self.T)
+                    self.reassign_genomes = False
+                self.comm.burned = True
+        elif mode == 'main':
+            self.t += 1
+            self.comm.t += 1
+            for spp in self.comm.values():
+                if not any(s.extinct for s in self.comm.values()):
+                    spp._set_t()
+                    spp._step(1)
+            if self.land._changer is not None:
+                self.land._make_change(self.t)                 # model.py:646-652
+        return any(spp.extinct for spp in self.comm.values())
+
+    def _check_comm_burned(self):
+        """community.py:107-131 + burnin.py:94-103: minimum burn_T steps, then the paired
+        t-test on Nt.  The ADF test (statsmodels) and the per-cell spatial test are burn-in
+        control, out of scope here; they are skipped."""
+        from scipy.stats import ttest_ind
+        ok = all(len(spp.Nt) >= self.burn_T for spp in self.comm.values())
+        if ok:
+            for spp in self.comm.values():
+                nb = self.burn_T + self.burn_T % 2
+                a, b = spp.Nt[int(-nb):int(-nb / 2)], spp.Nt[int(-nb / 2):]
+                if len(a) > 1 and len(b) > 1 and np.std(a + b) > 0:
+                    ok = ok and bool(ttest_ind(a, b)[1] > 0.05)
+        for spp in self.comm.values():
+            spp.burned = ok
+        self.comm.burned = ok
+
+    def walk(self, T=1, mode='main', verbose=False):
+        """model.py:966: run T time steps in 'burn' or 'main' mode."""
+        assert mode in ('burn', 'main')
+        if mode == 'main' and not self.comm.burned:
+            raise ValueError("Model.walk(mode='main') called before the burn-in completed "
+                             "(walk(mode='burn') first), as in the reference (model.py:1112).")
+        if mode == 'burn' and self.comm.burned:
+            return
+        # fast path: whole walk on the device when nothing host-side has to happen per step
+        for t in range(T):
+            extinct = self._do_timestep(mode)
+            if verbose:
+                for spp in self.comm.values():
+                    print('%s:\tit=%i:\tt=%i\tspecies: %s N=%s (births=%s deaths=%s)' % (
+                        mode, self.it, self.burn_t if mode == 'burn' else self.t, spp.name,
+                        spp.Nt[-1] if spp.Nt else np.nan, spp.n_births[-1] if spp.n_births else np.nan,
+                        spp.n_deaths[-1] if spp.n_deaths else np.nan))
+            if extinct or (mode == 'burn' and self.comm.burned):
+                break
+
+    def run(self, verbose=False):
+        """model.py:866: burn in, then T main steps (one iteration; see bench.py for the
+        replicate-sharded multi-GPU form of n_its)."""
+        self.it += 1
+        self.walk(10 ** 9, 'burn', verbose)
+        self.walk(self.T, 'main', verbose)
+
+    # ---- getters (model.py:2787-3176) ---------------------------------------------------
+    def _spp(self, spp):
+        return self.comm[spp] if isinstance(spp, int) else [s for s in self.comm.values() if s.name == spp][0]
+
+    def get_x(self, spp=0, individs=None):
+        return self._spp(spp)._get_x(individs)
+
+    def get_y(self, spp=0, individs=None):
+        return self._spp(spp)._get_y(individs)
+
+    def get_coords(self, spp=0, individs=None, as_float=True):
+        return self._spp(spp)._get_coords(individs, as_float)
+
+    def get_cells(self, spp=0, individs=None):
+        return self._spp(spp)._get_cells(individs)
+
+    def get_age(self, spp=0, individs=None):
+        return self._spp(spp)._get_age(individs)
+
+    def get_z(self, spp=0, trait_num=None, individs=None):
+        return self._spp(spp)._get_z(trait_num, individs)
+
+    def get_e(self, spp=0, lyr_num=None, individs=None):
+        return self._spp(spp)._get_e(lyr_num, individs)
+
+    def get_fitness(self, spp=0, individs=None):
+        return self._spp(spp)._get_fit(individs)
+
+    def get_genotypes(self, spp=0, loci=None, individs=None, biallelic=True, as_dict=False):
+        return self._spp(spp)._get_genotypes(loci, individs, biallelic, as_dict)
+
+
+def make_model(parameters=None, verbose=False, name=None):
+    """main.py:442: a Model from a parameters-file path, a dict or a ParametersDict."""
+    if isinstance(parameters, str):
+        params = read_parameters_file(parameters)
+    elif isinstance(parameters, ParametersDict):
+        params = parameters
+    elif isinstance(parameters, dict):
+        params = make_params_dict(parameters, name or 'unnamed_model')
+    else:
+        raise ValueError('parameters must be a filepath, a dict or a ParametersDict')
+    return Model(name or params.get('model', {}).get('name', 'unnamed_model'), params, verbose=verbose)

@@ -434,6 +434,23 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
     if ((r = up(wx.data(), sizeof(double) * nnz, (const void**)&D.e_wx))) return r;
     if ((r = up(wy.data(), sizeof(double) * nnz, (const void**)&D.e_wy))) return r;
     if ((r = up(vinv.data(), sizeof(double) * 3 * D.npts, (const void**)&D.v_inv))) return r;
+    // padded fixed-degree copy for the unrolled per-vertex update
+    std::vector<int32_t> pj((size_t)8 * D.npts);
+    std::vector<double> pe((size_t)32 * D.npts, 0.0);
+    D.padded = 1;
+    for (int i = 0; i < D.npts; ++i) {
+      const int s0 = dn->host_nbr_indptr[i], deg = dn->host_nbr_indptr[i + 1] - s0;
+      if (deg > 8) D.padded = 0;
+      for (int k = 0; k < 8; ++k) {
+        pj[(size_t)8 * i + k] = k < deg ? dn->host_nbr_indices[s0 + k] : i;
+        if (k < deg) {
+          double* o = &pe[((size_t)8 * i + k) * 4];
+          o[0] = ex[s0 + k]; o[1] = ey[s0 + k]; o[2] = wx[s0 + k]; o[3] = wy[s0 + k];
+        }
+      }
+    }
+    if ((r = up(pj.data(), sizeof(int32_t) * pj.size(), (const void**)&D.p_j))) return r;
+    if ((r = up(pe.data(), sizeof(double) * pe.size(), (const void**)&D.p_e))) return r;
     CK(cudaStreamSynchronize(ctx->stream));     // the host vectors go out of scope below
   }
   if ((r = up(dn->host_square_tri, sizeof(int32_t) * 2 * (D.lat_ni - 1) * (D.lat_nj - 1),
@@ -629,7 +646,7 @@ static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   char nm[64];
   snprintf(nm, sizeof nm, "%s.reduce", name);
   PROF(ctx, nm);
-  scan_reduce_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  scan_reduce_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
   snprintf(nm, sizeof nm, "%s.spine", name);
   PROF(ctx, nm);
@@ -637,7 +654,7 @@ static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   LAUNCHED(ctx);
   snprintf(nm, sizeof nm, "%s.apply", name);
   PROF(ctx, nm);
-  scan_apply_kernel<F><<<grid_for(ctx, 4), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  scan_apply_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
   return GNX_OK;
 }

@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Co
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
-#define MATE_BUF 32
 template <int MODE>
 __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                      const Counters* c) {
@@ -185,25 +184,38 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       hi[r] = w.cell_start[row * land.ncx + x1 + 1];
     }
     int cnt = 0;
-    int buf[MATE_BUF];
+    // MODE 0 keeps the valid candidates of each row range as a 64-bit mask in registers
+    unsigned long long vm[3] = {0ull, 0ull, 0ull};
+    bool overflow = false;
     double best = 1e300, wsum = 0.0;
     int best_q = -1, n_w = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-      for (int q = lo[r]; q < hi[r]; ++q) {
-        const double2 cxy = sxy[q];
-        const double dx = cxy.x - f.x, dy = cxy.y - f.y;
-        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d2 <= r2 && q != p) {
-          if (MODE == 0) { if (cnt < MATE_BUF) buf[cnt] = q; }
-          if (MODE == 1) { if (d2 < best) { best = d2; best_q = q; } }
-          if (MODE == 2) {
-            const double d = sqrt(d2);
-            if (d != 0.0) { wsum += radius - d; n_w += 1; }
-          }
-          cnt += 1;
+    for (int r = 0; r < 3; ++r) {
+      const int len = hi[r] - lo[r];
+      if (MODE == 0 && len > 64) overflow = true;
+      // two candidates per iteration: both 128-bit loads are issued before either is used
+      for (int j = 0; j < len; j += 2) {
+        const int q0 = lo[r] + j, q1 = min(q0 + 1, hi[r] - 1);
+        const double2 c0 = sxy[q0], c1 = sxy[q1];
+        const double dx0 = c0.x - f.x, dy0 = c0.y - f.y, dx1 = c1.x - f.x, dy1 = c1.y - f.y;
+        const double d20 = __dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0));
+        const double d21 = __dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1));
+        const bool v0 = d20 <= r2 && q0 != p;
+        const bool v1 = d21 <= r2 && (q0 + 1) != p && (j + 1) < len;
+        if (MODE == 0) {
+          if (j < 64) vm[r] |= ((unsigned long long)v0 << j) | ((unsigned long long)v1 << ((j + 1) & 63));
         }
+        if (MODE == 1) {
+          if (v0 && d20 < best) { best = d20; best_q = q0; }
+          if (v1 && d21 < best) { best = d21; best_q = q0 + 1; }
+        }
+        if (MODE == 2) {
+          if (v0) { const double d = sqrt(d20); if (d != 0.0) { wsum += radius - d; n_w += 1; } }
+          if (v1) { const double d = sqrt(d21); if (d != 0.0) { wsum += radius - d; n_w += 1; } }
+        }
+        cnt += (int)v0 + (int)v1;
       }
+    }
     const int i = w.perm[p];
     if (prm.store_debug) w.n_nbrs[i] = cnt;
     int mate = -1;
@@ -236,9 +248,21 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       } else {
         const uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
         int k = (int)choose_k(R, (uint32_t)cnt);
-        if (k < MATE_BUF) {
-          sel_q = buf[k];
-        } else {                         // rare: more than MATE_BUF neighbours, walk again
+        if (!overflow) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int cr = __popcll(vm[r]);
+            if (sel_q < 0) {
+              if (k < cr) {
+                unsigned long long mm = vm[r];
+                for (int b = 0; b < k; ++b) mm &= mm - 1;          // drop the k lowest set bits
+                sel_q = lo[r] + __ffsll((long long)mm) - 1;
+              } else {
+                k -= cr;
+              }
+            }
+          }
+        } else {                         // rare: a row range longer than 64, walk again
 #pragma unroll
           for (int r = 0; r < 3; ++r)
             for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
@@ -373,6 +397,15 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
 __device__ __forceinline__ double trait_word(const Traits& tr, int s, int e, uint32_t w0, uint32_t w1,
                                              bool polygenic) {
   double acc = 0.0;
+  if (!tr.te_dom && polygenic) {
+    // common case: geno*alpha = dosage * (0.5*alpha) exactly (power-of-two scaling)
+    for (int k = s; k < e; ++k) {
+      const int sh = __ldg(&tr.te_locus[k]) & 31;
+      const int dosage = (int)((w0 >> sh) & 1u) + (int)((w1 >> sh) & 1u);
+      acc += (0.5 * (double)dosage) * __ldg(&tr.te_alpha[k]);              // selection.py:30-33, 43-44
+    }
+    return acc;
+  }
   for (int k = s; k < e; ++k) {
     const int sh = __ldg(&tr.te_locus[k]) & 31;
     const int dosage = (int)((w0 >> sh) & 1u) + (int)((w1 >> sh) & 1u);
@@ -609,42 +642,59 @@ __global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const C
 // fully parallel phases with exactly the sequential algorithm's arithmetic.
 // Per-vertex update with the data-independent parts hoisted to setup (gnx_set_density):
 // the 2x2 matrix Q of `_estimate_gradients_2d_global` depends only on the triangulation,
-// so its inverse (v_inv) and the per-edge weights ex/L^3, ey/L^3 (e_wx, e_wy) are
-// precomputed; a sweep then costs 6 flops per edge and no division / sqrt.  EL lanes share
-// one vertex (one edge each, shuffle-reduced); EL = 1 is the plain sequential form.
-template <int EL>
-__device__ __forceinline__ double gs_vertex(const Dens& d, const double* f, double* yv, int i, int lane,
-                                            unsigned mask) {
+// so its inverse (v_inv) and the per-edge weights ex/L^3, ey/L^3 are precomputed; a sweep
+// then costs 6 flops per edge and no sqrt.  Edges are stored padded to GS_DEG slots per
+// vertex (pad: neighbour = self, weights = 0), so the loop is fully unrolled and all loads
+// of a vertex are independent.
+#define GS_DEG 8
+__device__ __forceinline__ double gs_vertex_padded(const Dens& d, const double* f, double* yv, int i) {
   double s0 = 0, s1 = 0;
   const double f1 = f[i];
-  const int je = d.nbr_indptr[i + 1];
-  for (int jj = d.nbr_indptr[i] + lane; jj < je; jj += EL) {
-    const int j = __ldg(&d.nbr_indices[jj]);
-    const double ex = __ldg(&d.e_ex[jj]), ey = __ldg(&d.e_ey[jj]);
-    // (6*(f1 - f2) - 2*df2) with df2 = -ex*y_j0 - ey*y_j1
-    const double tt = 6 * (f1 - f[j]) + 2 * (ex * yv[2 * j] + ey * yv[2 * j + 1]);
-    s0 += tt * __ldg(&d.e_wx[jj]);
-    s1 += tt * __ldg(&d.e_wy[jj]);
-  }
+  const int4* jp = reinterpret_cast<const int4*>(d.p_j + (size_t)i * GS_DEG);
+  const int4 ja = __ldg(jp), jb = __ldg(jp + 1);
+  const int js[GS_DEG] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+  const double2* ep = reinterpret_cast<const double2*>(d.p_e + (size_t)i * GS_DEG * 4);
 #pragma unroll
-  for (int o = EL / 2; o >= 1; o >>= 1) {
-    s0 += __shfl_xor_sync(mask, s0, o);
-    s1 += __shfl_xor_sync(mask, s1, o);
+  for (int k = 0; k < GS_DEG; ++k) {
+    const double2 ev = __ldg(ep + 2 * k), ew = __ldg(ep + 2 * k + 1);   // (ex, ey), (ex/L^3, ey/L^3)
+    const int j = js[k];
+    // (6*(f1 - f2) - 2*df2) with df2 = -ex*y_j0 - ey*y_j1
+    const double tt = 6 * (f1 - f[j]) + 2 * (ev.x * yv[2 * j] + ev.y * yv[2 * j + 1]);
+    s0 += tt * ew.x;
+    s1 += tt * ew.y;
   }
-  double change = 0.0;
-  if (lane == 0) {
-    const double r0 = __ldg(&d.v_inv[3 * i]) * s0 + __ldg(&d.v_inv[3 * i + 1]) * s1;
-    const double r1 = __ldg(&d.v_inv[3 * i + 1]) * s0 + __ldg(&d.v_inv[3 * i + 2]) * s1;
-    change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
-    yv[2 * i] = -r0;
-    yv[2 * i + 1] = -r1;
-    change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
-  }
+  const double i00 = __ldg(&d.v_inv[3 * i]), i01 = __ldg(&d.v_inv[3 * i + 1]), i11 = __ldg(&d.v_inv[3 * i + 2]);
+  const double r0 = i00 * s0 + i01 * s1;
+  const double r1 = i01 * s0 + i11 * s1;
+  double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
+  yv[2 * i] = -r0;
+  yv[2 * i + 1] = -r1;
+  change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
   return change;
 }
 
-#define GS_BLOCK 1024
-#define GS_EL 8
+// general form (any degree, CSR), used when a vertex has more than GS_DEG neighbours or the
+// triangulation is not 4-colourable by grid
+__device__ __forceinline__ double gs_vertex_csr(const Dens& d, const double* f, double* yv, int i) {
+  double s0 = 0, s1 = 0;
+  const double f1 = f[i];
+  for (int jj = d.nbr_indptr[i]; jj < d.nbr_indptr[i + 1]; ++jj) {
+    const int j = d.nbr_indices[jj];
+    const double ex = d.e_ex[jj], ey = d.e_ey[jj];
+    const double tt = 6 * (f1 - f[j]) + 2 * (ex * yv[2 * j] + ey * yv[2 * j + 1]);
+    s0 += tt * d.e_wx[jj];
+    s1 += tt * d.e_wy[jj];
+  }
+  const double r0 = d.v_inv[3 * i] * s0 + d.v_inv[3 * i + 1] * s1;
+  const double r1 = d.v_inv[3 * i + 1] * s0 + d.v_inv[3 * i + 2] * s1;
+  double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
+  yv[2 * i] = -r0;
+  yv[2 * i + 1] = -r1;
+  change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
+  return change;
+}
+
+#define GS_BLOCK 256
 #define GS_SMEM_PTS 1536
 __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, int maxiter, double tol) {
   // blockIdx.x: 0 = species density N, 1 = pair-midpoint density
@@ -654,8 +704,6 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
   double* gy = d.grad + (size_t)which * d.npts * 2;
   __shared__ double sf[GS_SMEM_PTS];
   __shared__ double sy[2 * GS_SMEM_PTS];
-  __shared__ double red[GS_BLOCK / 32];
-  __shared__ double s_err;
   const bool in_smem = d.npts <= GS_SMEM_PTS;
   double* f = in_smem ? sf : gf;
   double* yv = in_smem ? sy : gy;
@@ -667,35 +715,28 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
     yv[2 * k + 1] = 0.0;
   }
   __syncthreads();
-  const int lane = threadIdx.x & (GS_EL - 1), grp = threadIdx.x / GS_EL;
-  const unsigned gmask = ((1u << GS_EL) - 1u) << ((threadIdx.x & 31) & ~(GS_EL - 1));
   int iters = 0;
   for (int it = 0; it < maxiter; ++it) {
     double err = 0.0;
+    int done;
     if (d.colourable) {
       for (int g = 0; g < 4; ++g) {
         const int s = d.g_off[g], e = s + d.g_ni[g] * d.g_nj[g];
-        for (int v = s + grp; v < e; v += GS_BLOCK / GS_EL)
-          err = fmax(err, gs_vertex<GS_EL>(d, f, yv, v, lane, gmask));
-        __syncthreads();
+        if (d.padded)
+          for (int v = s + threadIdx.x; v < e; v += GS_BLOCK) err = fmax(err, gs_vertex_padded(d, f, yv, v));
+        else
+          for (int v = s + threadIdx.x; v < e; v += GS_BLOCK) err = fmax(err, gs_vertex_csr(d, f, yv, v));
+        // the barrier that ends the last colour phase also carries the convergence vote:
+        // max over vertices of `change` < tol  <=>  every thread's local maximum < tol
+        if (g < 3) __syncthreads();
       }
+      done = __syncthreads_and(err < tol);
     } else {
       if (threadIdx.x == 0)
-        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex<1>(d, f, yv, v, 0, 1u));
-      __syncthreads();
+        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex_csr(d, f, yv, v));
+      done = __syncthreads_and(err < tol);
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      double m = red[threadIdx.x];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (threadIdx.x == 0) s_err = m;
-    }
-    __syncthreads();
-    if (s_err < tol) { iters = it + 1; break; }
+    if (done) { iters = it + 1; break; }
   }
   if (in_smem)
     for (int k = threadIdx.x; k < 2 * d.npts; k += blockDim.x) gy[k] = sy[k];

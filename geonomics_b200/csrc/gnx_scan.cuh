@@ -90,12 +90,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(F f, const Count
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k * SCAN_BLOCK < n) ? f.value(base + k * SCAN_BLOCK) : 0;
     u64 carry = tile_sums[tile];
+    u64 ex[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
       u64 tot;
-      const u64 ex = block_excl_scan(v[k], &tot) + carry;
-      if (base + k * SCAN_BLOCK < n) f.apply(base + k * SCAN_BLOCK, v[k], ex);
+      ex[k] = block_excl_scan(v[k], &tot) + carry;
       carry += tot;
     }
+    // all prefixes first, then all payload moves: the loads of the SCAN_ITEMS elements
+    // overlap instead of queueing behind the barriers of the next row's scan
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+      if (base + k * SCAN_BLOCK < n) f.apply(base + k * SCAN_BLOCK, v[k], ex[k]);
   }
 }

@@ -1,0 +1,81 @@
+"""GPU tests of the reference-shaped API (geonomics_b200.api) running on libgnxb200.so:
+make_model -> walk('burn') -> walk('main'), state views, environmental change, invariants,
+and per-individual phenotype / fitness checked against the oracle formulas."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PARAMS = os.path.join(HERE, 'data', 'params_small.py')
+
+
+@pytest.fixture(scope='module')
+def model():
+    from geonomics_b200 import api
+    mod = api.make_model(PARAMS)
+    mod.walk(10000, 'burn')
+    return mod
+
+
+def test_burn_in_then_main(model):
+    from oracle import step_oracle as so
+    mod = model
+    spp = mod.comm[0]
+    assert mod.comm.burned and spp.burned
+    assert len(spp.Nt) == mod.burn_t + 1 >= mod.burn_T
+    n_burn = len(spp.Nt)
+    # genomes were assigned after burn-in with the parameterised starting frequency
+    g = mod.get_genotypes()
+    assert g.shape == (len(spp), 60, 2)
+    assert abs(g.mean() - 0.5) < 0.01
+    rast1_before = mod.land[1].rast.copy()
+    mod.walk(12, 'main')
+    assert mod.t == 11 and len(spp.Nt) == n_burn + 12
+    assert len(spp.n_births) == len(spp.Nt) == len(spp.n_deaths)
+    N = np.array(spp.Nt)
+    assert np.all(N[1:] == N[:-1] + np.array(spp.n_births[1:]) - np.array(spp.n_deaths[1:]))
+    assert 0.3 * spp.K.sum() < N[-1] < 1.5 * spp.K.sum()
+    # the scheduled environmental change ran (t = 4, 6, 8) on host and device rasters
+    assert np.allclose(mod.land[1].rast, rast1_before[:, ::-1])
+    e = mod.get_e()
+    x, y = mod.get_x(), mod.get_y()
+    assert np.array_equal(e[:, 1], mod.land[1].rast[y.astype(int), x.astype(int)])
+    # views agree with each other and with the oracle formulas
+    assert len(spp) == N[-1] == len(x)
+    ids = np.array([i for i in spp])
+    assert len(np.unique(ids)) == len(ids) and ids.max() <= spp.max_ind_idx
+    assert np.all(np.diff(ids[ids >= 1200]) > 0)             # newborn ids ascend in species order
+    g = mod.get_genotypes()
+    t0 = spp.gen_arch.traits[0]
+    z_o = so.phenotype(g, [dict(loci=t0.loci, alpha=t0.alpha)])
+    np.testing.assert_allclose(mod.get_z(), z_o, rtol=1e-12)
+    ind = spp[int(ids[3])]
+    assert ind.x == x[3] and ind.age == mod.get_age()[3] and np.array_equal(ind.g, g[3])
+    assert x.min() >= 0 and x.max() <= 40 - 0.001 and y.min() >= 0 and y.max() <= 40 - 0.001
+    dens = spp._calc_density()
+    assert dens.shape == (40, 40) and dens.min() >= 0
+    # ages: everyone alive now aged by one per step since birth; newborns of the last step are 0
+    assert mod.get_age().min() == 0
+
+
+def test_walk_main_before_burn_raises():
+    from geonomics_b200 import api
+    mod = api.make_model(PARAMS)
+    with pytest.raises(ValueError):
+        mod.walk(1, 'main')
+
+
+def test_seeded_models_are_reproducible():
+    from geonomics_b200 import api
+    outs = []
+    for _ in range(2):
+        mod = api.make_model(PARAMS)
+        mod.walk(10000, 'burn')
+        mod.walk(5, 'main')
+        outs.append((list(mod.comm[0].Nt), mod.get_x().copy(), mod.get_genotypes().copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
