@@ -441,13 +441,31 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
     for (int i = 0; i < D.npts; ++i) {
       const int s0 = dn->host_nbr_indptr[i], deg = dn->host_nbr_indptr[i + 1] - s0;
       if (deg > 8) D.padded = 0;
+      const size_t np = (size_t)D.npts;
       for (int k = 0; k < 8; ++k) {
-        pj[(size_t)8 * i + k] = k < deg ? dn->host_nbr_indices[s0 + k] : i;
+        pj[k * np + i] = k < deg ? dn->host_nbr_indices[s0 + k] : i;
         if (k < deg) {
-          double* o = &pe[((size_t)8 * i + k) * 4];
-          o[0] = ex[s0 + k]; o[1] = ey[s0 + k]; o[2] = wx[s0 + k]; o[3] = wy[s0 + k];
+          pe[(4 * k + 0) * np + i] = ex[s0 + k];
+          pe[(4 * k + 1) * np + i] = ey[s0 + k];
+          pe[(4 * k + 2) * np + i] = wx[s0 + k];
+          pe[(4 * k + 3) * np + i] = wy[s0 + k];
         }
       }
+    }
+    std::vector<double> vinv_t((size_t)3 * D.npts);
+    for (int i = 0; i < D.npts; ++i)
+      for (int cc = 0; cc < 3; ++cc) vinv_t[(size_t)cc * D.npts + i] = vinv[3 * i + cc];
+    if ((r = up(vinv_t.data(), sizeof(double) * vinv_t.size(), (const void**)&D.v_inv_t))) return r;
+    {
+      // one blob in the kernel's shared-memory layout: [8][4][npts] f64 | [3][npts] f64 | [8][npts] i32
+      const size_t nb = ((size_t)D.npts * GS_TABLE_BYTES_PER_PT + 15) / 16 * 16;
+      std::vector<unsigned char> blob(nb, 0);
+      memcpy(blob.data(), pe.data(), pe.size() * 8);
+      memcpy(blob.data() + pe.size() * 8, vinv_t.data(), vinv_t.size() * 8);
+      memcpy(blob.data() + pe.size() * 8 + vinv_t.size() * 8, pj.data(), pj.size() * 4);
+      if ((r = up(blob.data(), nb, (const void**)&D.gs_table))) return r;
+      D.gs_table_bytes = (int32_t)nb;
+      CK(cudaStreamSynchronize(ctx->stream));
     }
     if ((r = up(pj.data(), sizeof(int32_t) * pj.size(), (const void**)&D.p_j))) return r;
     if ((r = up(pe.data(), sizeof(double) * pe.size(), (const void**)&D.p_e))) return r;
@@ -459,7 +477,7 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
   DM(ctx, &D.counts, (size_t)2 * D.npts, &ctx->dens_allocs);
   DM(ctx, &D.vals, (size_t)2 * D.npts, &ctx->dens_allocs);
   DM(ctx, &D.grad, (size_t)4 * D.npts, &ctx->dens_allocs);
-  DM(ctx, &D.coef, (size_t)2 * D.ntri * 19, &ctx->dens_allocs);
+  DM(ctx, &D.coef, (size_t)2 * D.ntri * 19 + 64, &ctx->dens_allocs);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_density = true;
   return GNX_OK;
@@ -795,7 +813,17 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   // scipy defaults reached through griddata: CloughTocher2DInterpolator(tol=1e-6, maxiter=400)
   PROF(ctx, "k_ct_gradients");
-  k_ct_gradients<<<2, GS_BLOCK, 0, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
+  const size_t gs_bytes = (size_t)ctx->dens.gs_table_bytes + (size_t)ctx->dens.npts * 24 + 16;
+  if (ctx->dens.colourable && ctx->dens.padded && gs_bytes <= 220 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(k_ct_gradients_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    k_ct_gradients_smem<<<2, GS_BLOCK, gs_bytes, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
+  } else {
+    k_ct_gradients<<<2, GS_BLOCK, 0, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
+  }
   LAUNCHED(ctx);
   PROF(ctx, "k_ct_coefficients");
   k_ct_coefficients<<<std::max(1, (2 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
@@ -940,6 +968,7 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
     case GNX_F_DISP_TRIES: p = W.disp_tries; b = (size_t)h.B * 4; break;
     case GNX_F_E: p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
     case GNX_F_COUNTERS: p = ctx->d_c; b = sizeof(Counters); break;
+    case 31: p = D.coef + (size_t)2 * D.ntri * 19; b = 64 * 8; break;   /* debug scratch */
     case GNX_F_GENOMES: p = ctx->d_stage_genomes; b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4); break;
     default: g_last_error = "unknown field"; return GNX_ERR_ARG;
   }

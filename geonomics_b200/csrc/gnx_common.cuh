@@ -91,8 +91,11 @@ struct Dens {
   const double* e_wx;
   const double* e_wy;
   const double* v_inv;     // [npts][3] inverse of the per-vertex 2x2 system (i00, i01, i11)
-  const int32_t* p_j;      // [npts][8] neighbours padded with self
-  const double* p_e;       // [npts][8][4] (ex, ey, ex/L^3, ey/L^3), padded with zeros
+  const int32_t* p_j;      // [8][npts] neighbours padded with self (transposed)
+  const double* p_e;       // [8][4][npts] (ex, ey, ex/L^3, ey/L^3), padded with zeros (transposed)
+  const double* v_inv_t;   // [3][npts]
+  const void* gs_table;    // contiguous blob [p_e | v_inv_t | p_j | pad16] staged into shared memory by TMA
+  int32_t gs_table_bytes;
   int32_t padded;          // every vertex has <= 8 neighbours
   int32_t lat_ni, lat_nj;
   const int32_t* square_tri;

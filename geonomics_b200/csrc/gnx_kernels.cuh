@@ -647,28 +647,30 @@ __global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const C
 // vertex (pad: neighbour = self, weights = 0), so the loop is fully unrolled and all loads
 // of a vertex are independent.
 #define GS_DEG 8
-__device__ __forceinline__ double gs_vertex_padded(const Dens& d, const double* f, double* yv, int i) {
+// Edge table layout is transposed: slot k, component c of vertex v is at [(4*k + c)*npts + v],
+// neighbour ids at [k*npts + v], inverse-matrix entries at [c*npts + v]; the threads of a
+// colour phase own consecutive vertices, so every shared-memory access is stride-1 across the
+// warp (the [vertex][slot] layout costs a 32-way bank conflict on every load).
+__device__ __forceinline__ double gs_vertex_padded(const int* __restrict__ pj, const double* __restrict__ pe,
+                                                   const double* __restrict__ vinv, const double* f, double* yv,
+                                                   int i, int npts) {
   double s0 = 0, s1 = 0;
   const double f1 = f[i];
-  const int4* jp = reinterpret_cast<const int4*>(d.p_j + (size_t)i * GS_DEG);
-  const int4 ja = __ldg(jp), jb = __ldg(jp + 1);
-  const int js[GS_DEG] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
-  const double2* ep = reinterpret_cast<const double2*>(d.p_e + (size_t)i * GS_DEG * 4);
 #pragma unroll
   for (int k = 0; k < GS_DEG; ++k) {
-    const double2 ev = __ldg(ep + 2 * k), ew = __ldg(ep + 2 * k + 1);   // (ex, ey), (ex/L^3, ey/L^3)
-    const int j = js[k];
+    const int j = pj[k * npts + i];
+    const double ex = pe[(4 * k + 0) * npts + i], ey = pe[(4 * k + 1) * npts + i];
     // (6*(f1 - f2) - 2*df2) with df2 = -ex*y_j0 - ey*y_j1
-    const double tt = 6 * (f1 - f[j]) + 2 * (ev.x * yv[2 * j] + ev.y * yv[2 * j + 1]);
-    s0 += tt * ew.x;
-    s1 += tt * ew.y;
+    const double tt = 6 * (f1 - f[j]) + 2 * (ex * yv[j] + ey * yv[npts + j]);
+    s0 += tt * pe[(4 * k + 2) * npts + i];
+    s1 += tt * pe[(4 * k + 3) * npts + i];
   }
-  const double i00 = __ldg(&d.v_inv[3 * i]), i01 = __ldg(&d.v_inv[3 * i + 1]), i11 = __ldg(&d.v_inv[3 * i + 2]);
+  const double i00 = vinv[i], i01 = vinv[npts + i], i11 = vinv[2 * npts + i];
   const double r0 = i00 * s0 + i01 * s1;
   const double r1 = i01 * s0 + i11 * s1;
-  double change = fmax(fabs(yv[2 * i] + r0), fabs(yv[2 * i + 1] + r1));
-  yv[2 * i] = -r0;
-  yv[2 * i + 1] = -r1;
+  double change = fmax(fabs(yv[i] + r0), fabs(yv[npts + i] + r1));
+  yv[i] = -r0;
+  yv[npts + i] = -r1;
   change /= fmax(1.0, fmax(fabs(r0), fabs(r1)));
   return change;
 }
@@ -696,21 +698,103 @@ __device__ __forceinline__ double gs_vertex_csr(const Dens& d, const double* f, 
 
 #define GS_BLOCK 256
 #define GS_SMEM_PTS 1536
+// bytes of dynamic shared memory per lattice point when the whole solve lives in shared
+// memory: edge table (8 slots x 4 doubles), inverse matrices (3), neighbour ids (8 ints),
+// gradients (2), values (1)
+#define GS_TABLE_BYTES_PER_PT (GS_DEG * 32 + 24 + GS_DEG * 4)
+extern __shared__ __align__(128) unsigned char gs_dyn_smem[];
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Fast path: the whole solve in shared memory (default lattices have <= 529 points = 178 KB).
+// The constant tables (one contiguous blob, already in the transposed shared-memory layout)
+// are staged by the TMA with one bulk copy per 32 KB chunk while the threads compute the
+// lattice values; everything after that touches shared memory only.
+__global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients_smem(Dens d, Counters* c, int maxiter, double tol) {
+  const int which = blockIdx.x;          // 0 = species density N, 1 = pair-midpoint density
+  const int npts = d.npts;
+  const int* counts = d.counts + (size_t)which * npts;
+  double* gf = d.vals + (size_t)which * npts;
+  double* gy = d.grad + (size_t)which * npts * 2;
+  __shared__ __align__(8) unsigned long long bar;
+  const uint32_t table_bytes = (uint32_t)d.gs_table_bytes;                // multiple of 16
+  double* spe = reinterpret_cast<double*>(gs_dyn_smem);                   // [8][4][npts]
+  double* svinv = spe + (size_t)npts * GS_DEG * 4;                        // [3][npts]
+  int* spj = reinterpret_cast<int*>(svinv + 3 * npts);                    // [8][npts]
+  double* sy = reinterpret_cast<double*>(gs_dyn_smem + table_bytes);      // [2][npts]
+  double* sf = sy + 2 * npts;                                             // [npts]
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, table_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(d.gs_table);
+    for (uint32_t off = 0; off < table_bytes; off += 32768) {
+      const uint32_t nb = min(32768u, table_bytes - off);
+      bulk_g2s(gs_dyn_smem + off, src + off, nb, &bar);
+    }
+  }
+  for (int k = threadIdx.x; k < npts; k += blockDim.x) {
+    const double v = (double)counts[k] / d.areas[k];       // spatial.py:95
+    sf[k] = v;
+    gf[k] = v;
+    sy[k] = 0.0;
+    sy[npts + k] = 0.0;
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  int iters = 0;
+  for (int it = 0; it < maxiter; ++it) {
+    double err = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int s = d.g_off[g], e = s + d.g_ni[g] * d.g_nj[g];
+      for (int v = s + threadIdx.x; v < e; v += GS_BLOCK)
+        err = fmax(err, gs_vertex_padded(spj, spe, svinv, sf, sy, v, npts));
+      // the barrier that ends the last colour phase also carries the convergence vote:
+      // max over vertices of `change` < tol  <=>  every thread's local maximum < tol
+      if (g < 3) __syncthreads();
+    }
+    if (__syncthreads_and(err < tol)) { iters = it + 1; break; }
+  }
+  for (int k = threadIdx.x; k < npts; k += blockDim.x) {
+    gy[2 * k] = sy[k];
+    gy[2 * k + 1] = sy[npts + k];
+  }
+  if (threadIdx.x == 0) c->gs_iters[which] = iters;     // 0: maxiter reached (scipy only warns)
+}
+
+// General path: larger lattices, vertices of degree > 8, or triangulations that are not
+// 4-colourable by grid (then one thread runs the sequential sweep).
 __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, int maxiter, double tol) {
-  // blockIdx.x: 0 = species density N, 1 = pair-midpoint density
   const int which = blockIdx.x;
   const int* counts = d.counts + (size_t)which * d.npts;
-  double* gf = d.vals + (size_t)which * d.npts;
-  double* gy = d.grad + (size_t)which * d.npts * 2;
-  __shared__ double sf[GS_SMEM_PTS];
-  __shared__ double sy[2 * GS_SMEM_PTS];
-  const bool in_smem = d.npts <= GS_SMEM_PTS;
-  double* f = in_smem ? sf : gf;
-  double* yv = in_smem ? sy : gy;
+  double* f = d.vals + (size_t)which * d.npts;
+  double* yv = d.grad + (size_t)which * d.npts * 2;
   for (int k = threadIdx.x; k < d.npts; k += blockDim.x) {
-    const double v = (double)counts[k] / d.areas[k];       // spatial.py:95
-    f[k] = v;
-    gf[k] = v;
+    f[k] = (double)counts[k] / d.areas[k];
     yv[2 * k] = 0.0;
     yv[2 * k + 1] = 0.0;
   }
@@ -718,29 +802,18 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
   int iters = 0;
   for (int it = 0; it < maxiter; ++it) {
     double err = 0.0;
-    int done;
     if (d.colourable) {
       for (int g = 0; g < 4; ++g) {
         const int s = d.g_off[g], e = s + d.g_ni[g] * d.g_nj[g];
-        if (d.padded)
-          for (int v = s + threadIdx.x; v < e; v += GS_BLOCK) err = fmax(err, gs_vertex_padded(d, f, yv, v));
-        else
-          for (int v = s + threadIdx.x; v < e; v += GS_BLOCK) err = fmax(err, gs_vertex_csr(d, f, yv, v));
-        // the barrier that ends the last colour phase also carries the convergence vote:
-        // max over vertices of `change` < tol  <=>  every thread's local maximum < tol
+        for (int v = s + threadIdx.x; v < e; v += GS_BLOCK) err = fmax(err, gs_vertex_csr(d, f, yv, v));
         if (g < 3) __syncthreads();
       }
-      done = __syncthreads_and(err < tol);
-    } else {
-      if (threadIdx.x == 0)
-        for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex_csr(d, f, yv, v));
-      done = __syncthreads_and(err < tol);
+    } else if (threadIdx.x == 0) {
+      for (int v = 0; v < d.npts; ++v) err = fmax(err, gs_vertex_csr(d, f, yv, v));
     }
-    if (done) { iters = it + 1; break; }
+    if (__syncthreads_and(err < tol)) { iters = it + 1; break; }
   }
-  if (in_smem)
-    for (int k = threadIdx.x; k < 2 * d.npts; k += blockDim.x) gy[k] = sy[k];
-  if (threadIdx.x == 0) c->gs_iters[which] = iters;     // 0: maxiter reached (scipy only warns)
+  if (threadIdx.x == 0) c->gs_iters[which] = iters;
 }
 
 // Bezier ordinates of every triangle (`_clough_tocher_2d_single`, point-independent part)
