@@ -281,15 +281,10 @@ def main():
         n_start.append(r['Nt'] - r['n_births'] + r['n_deaths'])
     ind_gens = float(sum(n_start))
     births = float(sum(r['n_births'] for r in recs))
-    t = torch.tensor([ms, ind_gens, births], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_all, ind_all, births_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
-    else:
-        ms_all, ind_all, births_all = ms, ind_gens, births
+    from geonomics_b200 import parallel
+    # job time = slowest rank's device time; job work = sum over ranks (no data-path collective)
+    ms_all, ind_all = parallel.reduce_throughput(ms, ind_gens, dist, 'cuda')
+    _, births_all = parallel.reduce_throughput(ms, births, dist, 'cuda')
     value = ind_all / (ms_all * 1e-3)
 
     # ---- per-kernel timing pass (CUDA events around every launch) for the roofline
@@ -370,13 +365,7 @@ def main():
             d2h += bufs['n'] * per_ind
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, float(e2e_ind)], dtype=torch.float64, device='cuda')
-        if dist is not None:
-            a = tt.clone()
-            dist.all_reduce(a, op=dist.ReduceOp.MAX)
-            b_ = tt.clone()
-            dist.all_reduce(b_, op=dist.ReduceOp.SUM)
-            dt, e2e_ind = float(a[0]), float(b_[1])
+        dt, e2e_ind = parallel.reduce_throughput(dt, float(e2e_ind), dist, 'cuda')
         e2e = {'value': e2e_ind / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d / args.e2e_steps,
                'd2h_bytes_per_step': d2h / args.e2e_steps, 'steps': args.e2e_steps,
                'api': 'gnx_walk_host (C-ABI, pinned host SoA buffers in and out every step)'}

@@ -763,7 +763,14 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   const int Wq = ctx->Wq;
   const int g = grid_for(ctx, 8);
   if (!ctx->burn) {
-#define MO(GW) k_gametes<GW><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c)
+#define MO(GW)                                                                                            \
+  do {                                                                                                    \
+    if (ctx->cfg.n_traits <= 2)                                                                           \
+      k_gametes<GW, 2><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c); \
+    else                                                                                                  \
+      k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,       \
+                                                      ctx->work, ctx->d_c);                               \
+  } while (0)
     PROF(ctx, "k_gametes");
     if (Wq <= 1) MO(1);
     else if (Wq <= 2) MO(2);

@@ -14,48 +14,80 @@
 //   lookup); species.py:937-939 (cells).  Flags select which parts run so the stage-level
 //   C-ABI entry points and the fused step share one kernel.
 // ========================================================================================
-__device__ __noinline__ double surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
-                                                    int cx, int cy, int mixture, double kappa) {
+// On-the-fly conductance-surface direction.  The reference pre-draws `approx_len` float16
+// samples per cell from this same distribution (spatial.py:365-461); at 4096^2 that table
+// would be 168 GB, so the sample is drawn here instead.  The result is quantised to float16
+// exactly as the table is, so the draw itself runs in float32.
+__device__ __forceinline__ float uniform_f32(RngStream& g) { return (g.u32() >> 8) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa) {
+  // numpy legacy_vonmises (Best & Fisher), single precision
+  const float PI_F = 3.14159265358979f;
+  if (kappa < 1e-8f) return PI_F * (2.0f * uniform_f32(g) - 1.0f);
+  const float r = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
+  const float rho = (r - sqrtf(2.0f * r)) / (2.0f * kappa);
+  const float s = (1.0f + rho * rho) / (2.0f * rho);
+  float W = 1.0f;
+  for (int it = 0; it < 64; ++it) {
+    const float Z = cospif(uniform_f32(g));
+    W = (1.0f + s * Z) / (s + Z);
+    const float Y = kappa * (s - W);
+    const float V = fmaxf(uniform_f32(g), 1e-30f);
+    if ((Y * (2.0f - Y) - V >= 0.0f) || (__logf(Y / V) + 1.0f - Y >= 0.0f)) break;
+  }
+  float res = acosf(fminf(fmaxf(W, -1.0f), 1.0f));
+  return (uniform_f32(g) < 0.5f) ? -res : res;
+}
+
+__device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
+                                                             int cx, int cy, int mixture, float kappa) {
   // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
   // dropped; queen directions in raster row-major order.
-  const double dirs[8] = {-3 * GNX_PI / 4, -GNX_PI / 2, -GNX_PI / 4, GNX_PI, 0.0,
-                          3 * GNX_PI / 4, GNX_PI / 2, GNX_PI / 4};
+  const float PI_F = 3.14159265358979f;
+  const float dirs[8] = {-3 * PI_F / 4, -PI_F / 2, -PI_F / 4, PI_F, 0.0f, 3 * PI_F / 4, PI_F / 2, PI_F / 4};
   const int di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
   const int dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-  double nv[8];
-  double sum = 0.0, mx = -1.0;
+  float nv[8];
+  float sum = 0.0f, mx = -1.0f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    int i = cy + di[k], j = cx + dj[k];
-    double v = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0;
+    const int i = cy + di[k], j = cx + dj[k];
+    const float v = (i >= 0 && i < Y && j >= 0 && j < X) ? (float)__ldg(&rast[(size_t)i * X + j]) : 0.0f;
     nv[k] = v;
     sum += v;
-    mx = v > mx ? v : mx;
+    mx = fmaxf(mx, v);
   }
-  double loc;
+  float loc;
   if (mixture) {
-    double u = g.uniform();
-    int pick = 7;
-    double acc = 0.0;
+    const float target = uniform_f32(g) * (sum > 0.0f ? sum : 8.0f);
+    float acc = 0.0f;
+    loc = dirs[7];
+    bool found = false;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      double p = sum > 0.0 ? nv[k] / sum : 0.125;
-      acc += p;
-      if (u < acc) { pick = k; break; }
+      acc += sum > 0.0f ? nv[k] : 1.0f;
+      if (!found && target < acc) { loc = dirs[k]; found = true; }
     }
-    loc = dirs[pick];
   } else {
-    double s = 0.0;
+    float sacc = 0.0f;
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      if (nv[k] == mx) { s += dirs[k]; cnt += 1; }
-    loc = s / cnt;
+      if (nv[k] == mx) { sacc += dirs[k]; cnt += 1; }
+    loc = sacc / cnt;
   }
-  // scipy vonmises.rvs(kappa, loc): loc + vonmises(0, kappa), not re-wrapped; stored as
-  // float16 in the reference table (spatial.py:447)
-  double d = loc + sample_vonmises(g, 0.0, kappa);
-  return (double)__half2float(__float2half_rn((float)d));
+  // scipy vonmises.rvs(kappa, loc): loc + vonmises(0, kappa), not re-wrapped; float16 like the
+  // reference table (spatial.py:447)
+  return __float2half_rn(loc + vonmises_f32(g, kappa));
+}
+
+// cos/sin of a float16 direction for the on-the-fly path: float32 libm, rounded to half
+// (numpy's portable float16 semantics up to the last float32 ulp)
+__device__ __forceinline__ void sincos_half_fast(__half h, double* s, double* c) {
+  float sf, cf;
+  sincosf(__half2float(h), &sf, &cf);
+  *c = (double)__half2float(__float2half_rn(cf));
+  *s = (double)__half2float(__float2half_rn(sf));
 }
 
 __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params prm, DevDraws dr,
@@ -78,10 +110,10 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
         sincos_half(h, &sn, &cs);
       } else if (prm.c.move_surf_mode == GNX_SURF_ONTHEFLY) {
         int cx = (int)x, cy = (int)y;
-        double d = surface_direction_onthefly(
+        const __half d = surface_direction_onthefly(
             g, land.rasters + (size_t)prm.c.move_surf_layer * land.X * land.Y, land.X, land.Y, cx, cy,
-            prm.c.move_surf_mixture, prm.c.move_surf_kappa);
-        sincos_half(__float2half_rn((float)d), &sn, &cs);
+            prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa);
+        sincos_half_fast(d, &sn, &cs);
       } else if (dr.move_dir) {
         sincos(dr.move_dir[i], &sn, &cs);
       } else if (prm.c.dir_kappa < 1e-8) {
@@ -427,7 +459,12 @@ __device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, 
 }
 
 // ----- k_gametes: the genotype-streaming kernel -----------------------------------------
-template <int GW>
+// GW lanes per offspring (power of two <= 32), NT = trait accumulators kept in registers
+// (instantiated for 2 and GNX_MAX_TRAITS).  Lane 0 of a group walks the index chain
+// (offspring -> pair -> parents' genome slots) and draws the two recombination keys and
+// start homologues once; the group gets them by shuffle.  Every lane then streams its
+// 128-bit units: 4 parental homologue loads + 2 path loads in flight, 2 stores.
+template <int GW, int NT>
 __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
                                                   const Counters* c) {
   const int n = c->n, B = c->B, cur = c->cur, n_free = c->n_free, n_slots = c->n_slots;
@@ -435,43 +472,57 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
   const int Wq = pop.Wq, T = pop.T;
   const int lane = threadIdx.x & (GW - 1);
   const int ngroups = GSTRIDE / GW;
-  const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << ((threadIdx.x & 31) & ~(GW - 1)));
+  const int lane0 = (threadIdx.x & 31) & ~(GW - 1);
+  const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << lane0);
   const int32_t* __restrict__ gslot = pop.gslot[cur];
   for (int o = GTID / GW; o < B; o += ngroups) {
-    const int p = w.off_pair[o];
-    const int i0 = w.pairs[2 * p], i1 = w.pairs[2 * p + 1];
-    const int64_t oid = max_idx + 1 + o;                               // species.py:614-619
-    const int dst = n + o;
-    const int cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
-    int k0, k1, h0, h1;
-    RngStream gg(prm.seed_lo, prm.seed_hi, oid, SITE_GAMETE, t);
-    if (dr.recomb_keys) {
-      // mating.py:176-181, 204-209: the pair's key slice is popped from its END
-      const int j = o - w.off_start[p];
-      const int e = 2 * (w.off_start[p] + w.nb[p]);
-      k0 = dr.recomb_keys[e - 1 - 2 * j];
-      k1 = dr.recomb_keys[e - 2 - 2 * j];
-    } else {
-      k0 = (int)choose_k(gg.u32(), prm.n_paths);      // species.py:625-627
-      k1 = (int)choose_k(gg.u32(), prm.n_paths);
+    int s0 = 0, s1 = 0, cslot = 0, kk0 = 0, kk1 = 0;     // kk = key | start << 30
+    if (lane == 0) {
+      const int p = w.off_pair[o];
+      const int2 pr = *reinterpret_cast<const int2*>(w.pairs + 2 * p);
+      s0 = gslot[pr.x];
+      s1 = gslot[pr.y];
+      cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
+      int k0, k1, h0, h1;
+      RngStream gg(prm.seed_lo, prm.seed_hi, max_idx + 1 + o, SITE_GAMETE, t);
+      if (dr.recomb_keys) {
+        // mating.py:176-181, 204-209: the pair's key slice is popped from its END
+        const int j = o - w.off_start[p];
+        const int e = 2 * (w.off_start[p] + w.nb[p]);
+        k0 = dr.recomb_keys[e - 1 - 2 * j];
+        k1 = dr.recomb_keys[e - 2 - 2 * j];
+      } else {
+        k0 = (int)choose_k(gg.u32(), prm.n_paths);      // species.py:625-627
+        k1 = (int)choose_k(gg.u32(), prm.n_paths);
+      }
+      if (dr.start_homs) {
+        h0 = dr.start_homs[2 * o];
+        h1 = dr.start_homs[2 * o + 1];
+      } else {
+        const uint32_t bits = gg.u32();                  // mating.py:133
+        h0 = bits & 1;
+        h1 = (bits >> 1) & 1;
+      }
+      kk0 = k0 | (h0 << 30);
+      kk1 = k1 | (h1 << 30);
+      pop.gslot[cur][n + o] = cslot;
     }
-    if (dr.start_homs) {
-      h0 = dr.start_homs[2 * o];
-      h1 = dr.start_homs[2 * o + 1];
-    } else {
-      const uint32_t bits = gg.u32();                  // mating.py:133
-      h0 = bits & 1;
-      h1 = (bits >> 1) & 1;
+    if (GW > 1) {
+      s0 = __shfl_sync(gmask, s0, lane0);
+      s1 = __shfl_sync(gmask, s1, lane0);
+      cslot = __shfl_sync(gmask, cslot, lane0);
+      kk0 = __shfl_sync(gmask, kk0, lane0);
+      kk1 = __shfl_sync(gmask, kk1, lane0);
     }
-    const uint4* P0 = pop.G + (size_t)gslot[i0] * 2 * Wq;
-    const uint4* P1 = pop.G + (size_t)gslot[i1] * 2 * Wq;
-    const uint4* M0 = prm.paths + (size_t)k0 * Wq;
-    const uint4* M1 = prm.paths + (size_t)k1 * Wq;
+    const uint4* P0 = pop.G + (size_t)s0 * 2 * Wq;
+    const uint4* P1 = pop.G + (size_t)s1 * 2 * Wq;
+    const uint4* M0 = prm.paths + (size_t)(kk0 & 0x3fffffff) * Wq;
+    const uint4* M1 = prm.paths + (size_t)(kk1 & 0x3fffffff) * Wq;
     uint4* C = pop.G + (size_t)cslot * 2 * Wq;
-    const uint32_t f0 = h0 ? 0xffffffffu : 0u, f1 = h1 ? 0xffffffffu : 0u;
-    double zacc[GNX_MAX_TRAITS];
+    const uint32_t f0 = (kk0 >> 30) ? 0xffffffffu : 0u, f1 = (kk1 >> 30) ? 0xffffffffu : 0u;
+    double zacc[NT];
 #pragma unroll
-    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) zacc[tt] = 0.0;
+    for (int tt = 0; tt < NT; ++tt) zacc[tt] = 0.0;
     for (int q = lane; q < Wq; q += GW) {
       const uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
       const uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
@@ -483,19 +534,18 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
       st_stream(C + q, g0);
       st_stream(C + Wq + q, g1);
 #pragma unroll
-      for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
+      for (int tt = 0; tt < NT; ++tt)
         if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
     }
 #pragma unroll
-    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt) {
+    for (int tt = 0; tt < NT; ++tt) {
       if (tt < T) {
         double v = zacc[tt];
 #pragma unroll
         for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
-        if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + dst] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
+        if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
       }
     }
-    if (lane == 0) pop.gslot[cur][dst] = cslot;
   }
 }
 
@@ -524,10 +574,10 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
         __half h = prm.disp_tab[((size_t)((int)my) * land.X + (int)mx) * prm.c.surf_approx_len + col];
         sincos_half(h, &sn, &cs);
       } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
-        double d = surface_direction_onthefly(
+        const __half d = surface_direction_onthefly(
             g, land.rasters + (size_t)prm.c.disp_surf_layer * land.X * land.Y, land.X, land.Y, (int)mx,
-            (int)my, prm.c.disp_surf_mixture, prm.c.disp_surf_kappa);
-        sincos_half(__float2half_rn((float)d), &sn, &cs);
+            (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa);
+        sincos_half_fast(d, &sn, &cs);
       } else if (dr.disp_dir) {
         sincos(dr.disp_dir[(size_t)o * dr.disp_R + tries], &sn, &cs);
       } else {
