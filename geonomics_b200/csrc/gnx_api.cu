@@ -192,6 +192,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &W.mate, cap);
   DM(ctx, &W.n_nbrs, cap);
   DM(ctx, &W.pairs, 2 * cap);
+  DM(ctx, &W.pair_slots, 2 * cap);
   DM(ctx, &W.nb, cap);
   DM(ctx, &W.off_start, cap);
   DM(ctx, &W.off_pair, cap);
@@ -766,11 +767,12 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
 #define MO(GW)                                                                                            \
   do {                                                                                                    \
     if (ctx->cfg.n_traits <= 2)                                                                           \
-      k_gametes<GW, 2><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c); \
+      k_gametes<GW, 2><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c, fnb); \
     else                                                                                                  \
       k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,       \
-                                                      ctx->work, ctx->d_c);                               \
+                                                      ctx->work, ctx->d_c, fnb);                          \
   } while (0)
+    const int fnb = ctx->cfg.n_births_fixed ? (int)ctx->cfg.n_births_lambda : 0;
     PROF(ctx, "k_gametes");
     if (Wq <= 1) MO(1);
     else if (Wq <= 2) MO(2);

@@ -117,6 +117,7 @@ struct Work {
   int32_t* mate;
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]
+  int32_t* pair_slots;     // [cap][2] genome slots of each pair's parents
   int32_t* nb;
   int32_t* off_start;
   int32_t* off_pair;

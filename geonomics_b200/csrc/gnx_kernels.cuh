@@ -216,37 +216,53 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       hi[r] = w.cell_start[row * land.ncx + x1 + 1];
     }
     int cnt = 0;
-    // MODE 0 keeps the valid candidates of each row range as a 64-bit mask in registers
-    unsigned long long vm[3] = {0ull, 0ull, 0ull};
+    // MODE 0 keeps the valid candidates of each row range as a 32-bit mask in registers
+    uint32_t vm[3] = {0u, 0u, 0u};
     bool overflow = false;
     double best = 1e300, wsum = 0.0;
     int best_q = -1, n_w = 0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int len = hi[r] - lo[r];
-      if (MODE == 0 && len > 64) overflow = true;
-      // two candidates per iteration: both 128-bit loads are issued before either is used
-      for (int j = 0; j < len; j += 2) {
-        const int q0 = lo[r] + j, q1 = min(q0 + 1, hi[r] - 1);
-        const double2 c0 = sxy[q0], c1 = sxy[q1];
-        const double dx0 = c0.x - f.x, dy0 = c0.y - f.y, dx1 = c1.x - f.x, dy1 = c1.y - f.y;
-        const double d20 = __dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0));
-        const double d21 = __dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1));
-        const bool v0 = d20 <= r2 && q0 != p;
-        const bool v1 = d21 <= r2 && (q0 + 1) != p && (j + 1) < len;
-        if (MODE == 0) {
-          if (j < 64) vm[r] |= ((unsigned long long)v0 << j) | ((unsigned long long)v1 << ((j + 1) & 63));
+      const double2* __restrict__ cand = sxy + lo[r];
+      const int self = p - lo[r];                   // position of the focal in this range, if any
+      if (MODE == 0) {
+        if (len > 32) overflow = true;
+        uint32_t m = 0u;
+#pragma unroll 4
+        for (int j = 0; j < len; ++j) {
+          const double2 cxy = cand[j];
+          const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          m |= (d2 <= r2 ? 1u : 0u) << (j & 31);
         }
-        if (MODE == 1) {
-          if (v0 && d20 < best) { best = d20; best_q = q0; }
-          if (v1 && d21 < best) { best = d21; best_q = q0 + 1; }
+        if (self >= 0 && self < 32 && self < len) m &= ~(1u << self);
+        vm[r] = m;
+        cnt += __popc(m);
+      } else {
+        for (int j = 0; j < len; ++j) {
+          const double2 cxy = cand[j];
+          const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (d2 <= r2 && j != self) {
+            if (MODE == 1) { if (d2 < best) { best = d2; best_q = lo[r] + j; } }
+            if (MODE == 2) { const double d = sqrt(d2); if (d != 0.0) { wsum += radius - d; n_w += 1; } }
+            cnt += 1;
+          }
         }
-        if (MODE == 2) {
-          if (v0) { const double d = sqrt(d20); if (d != 0.0) { wsum += radius - d; n_w += 1; } }
-          if (v1) { const double d = sqrt(d21); if (d != 0.0) { wsum += radius - d; n_w += 1; } }
-        }
-        cnt += (int)v0 + (int)v1;
       }
+    }
+    if (MODE == 0 && overflow) {
+      // rare: a row range longer than 32 candidates -- count exactly, select by a second walk
+      cnt = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        for (int q = lo[r]; q < hi[r]; ++q) {
+          const double2 cxy = sxy[q];
+          const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          cnt += (d2 <= r2 && q != p) ? 1 : 0;
+        }
     }
     const int i = w.perm[p];
     if (prm.store_debug) w.n_nbrs[i] = cnt;
@@ -283,18 +299,13 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
         if (!overflow) {
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
-            const int cr = __popcll(vm[r]);
+            const int cr = __popc(vm[r]);
             if (sel_q < 0) {
-              if (k < cr) {
-                unsigned long long mm = vm[r];
-                for (int b = 0; b < k; ++b) mm &= mm - 1;          // drop the k lowest set bits
-                sel_q = lo[r] + __ffsll((long long)mm) - 1;
-              } else {
-                k -= cr;
-              }
+              if (k < cr) sel_q = lo[r] + (int)__fns(vm[r], 0, k + 1);    // k-th set bit
+              else k -= cr;
             }
           }
-        } else {                         // rare: a row range longer than 64, walk again
+        } else {                         // rare: a row range longer than 32, walk again
 #pragma unroll
           for (int r = 0; r < 3; ++r)
             for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
@@ -348,6 +359,8 @@ struct PairScan {
     w.pairs[2 * p + 1] = m;
     w.mid_x[p] = (pop.x[cur][i] + pop.x[cur][m]) / 2;     // species.py:640-641
     w.mid_y[p] = (pop.y[cur][i] + pop.y[cur][m]) / 2;
+    // parents' genome slots, so the gamete kernel's index chain is one load shorter
+    reinterpret_cast<int2*>(w.pair_slots)[p] = make_int2(pop.gslot[cur][i], pop.gslot[cur][m]);
     if (fixed_nb > 0) {
       w.nb[p] = fixed_nb;
       w.off_start[p] = p * fixed_nb;
@@ -464,9 +477,13 @@ __device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, 
 // (offspring -> pair -> parents' genome slots) and draws the two recombination keys and
 // start homologues once; the group gets them by shuffle.  Every lane then streams its
 // 128-bit units: 4 parental homologue loads + 2 path loads in flight, 2 stores.
+struct BirthPlan {
+  int s0, s1, cslot, kk0, kk1;     // parents' slots, child slot, key | start << 30
+};
+
 template <int GW, int NT>
 __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
-                                                  const Counters* c) {
+                                                  const Counters* c, int fixed_nb) {
   const int n = c->n, B = c->B, cur = c->cur, n_free = c->n_free, n_slots = c->n_slots;
   const int64_t t = c->t, max_idx = c->max_idx;
   const int Wq = pop.Wq, T = pop.T;
@@ -474,15 +491,15 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
   const int ngroups = GSTRIDE / GW;
   const int lane0 = (threadIdx.x & 31) & ~(GW - 1);
   const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << lane0);
-  const int32_t* __restrict__ gslot = pop.gslot[cur];
-  for (int o = GTID / GW; o < B; o += ngroups) {
-    int s0 = 0, s1 = 0, cslot = 0, kk0 = 0, kk1 = 0;     // kk = key | start << 30
-    if (lane == 0) {
-      const int p = w.off_pair[o];
-      const int2 pr = *reinterpret_cast<const int2*>(w.pairs + 2 * p);
-      s0 = gslot[pr.x];
-      s1 = gslot[pr.y];
-      cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
+  // lane 0 of each group resolves offspring o -> (parents' slots, child slot, keys, starts)
+  auto load_plan = [&](int o) -> BirthPlan {
+    BirthPlan bp = {0, 0, 0, 0, 0};
+    if (lane == 0 && o < B) {
+      const int p = fixed_nb > 0 ? o / fixed_nb : w.off_pair[o];
+      const int2 sl = reinterpret_cast<const int2*>(w.pair_slots)[p];
+      bp.s0 = sl.x;
+      bp.s1 = sl.y;
+      bp.cslot = o < n_free ? pop.free_slots[n_free - 1 - o] : n_slots + (o - n_free);
       int k0, k1, h0, h1;
       RngStream gg(prm.seed_lo, prm.seed_hi, max_idx + 1 + o, SITE_GAMETE, t);
       if (dr.recomb_keys) {
@@ -503,23 +520,30 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
         h0 = bits & 1;
         h1 = (bits >> 1) & 1;
       }
-      kk0 = k0 | (h0 << 30);
-      kk1 = k1 | (h1 << 30);
-      pop.gslot[cur][n + o] = cslot;
+      bp.kk0 = k0 | (h0 << 30);
+      bp.kk1 = k1 | (h1 << 30);
     }
+    return bp;
+  };
+  int o = GTID / GW;
+  BirthPlan next = load_plan(o);
+  for (; o < B; o += ngroups) {
+    BirthPlan bp = next;
+    next = load_plan(o + ngroups);           // prefetch: overlaps the next index chain with this row stream
     if (GW > 1) {
-      s0 = __shfl_sync(gmask, s0, lane0);
-      s1 = __shfl_sync(gmask, s1, lane0);
-      cslot = __shfl_sync(gmask, cslot, lane0);
-      kk0 = __shfl_sync(gmask, kk0, lane0);
-      kk1 = __shfl_sync(gmask, kk1, lane0);
+      bp.s0 = __shfl_sync(gmask, bp.s0, lane0);
+      bp.s1 = __shfl_sync(gmask, bp.s1, lane0);
+      bp.cslot = __shfl_sync(gmask, bp.cslot, lane0);
+      bp.kk0 = __shfl_sync(gmask, bp.kk0, lane0);
+      bp.kk1 = __shfl_sync(gmask, bp.kk1, lane0);
     }
-    const uint4* P0 = pop.G + (size_t)s0 * 2 * Wq;
-    const uint4* P1 = pop.G + (size_t)s1 * 2 * Wq;
-    const uint4* M0 = prm.paths + (size_t)(kk0 & 0x3fffffff) * Wq;
-    const uint4* M1 = prm.paths + (size_t)(kk1 & 0x3fffffff) * Wq;
-    uint4* C = pop.G + (size_t)cslot * 2 * Wq;
-    const uint32_t f0 = (kk0 >> 30) ? 0xffffffffu : 0u, f1 = (kk1 >> 30) ? 0xffffffffu : 0u;
+    if (lane == 0) pop.gslot[cur][n + o] = bp.cslot;
+    const uint4* P0 = pop.G + (size_t)bp.s0 * 2 * Wq;
+    const uint4* P1 = pop.G + (size_t)bp.s1 * 2 * Wq;
+    const uint4* M0 = prm.paths + (size_t)(bp.kk0 & 0x3fffffff) * Wq;
+    const uint4* M1 = prm.paths + (size_t)(bp.kk1 & 0x3fffffff) * Wq;
+    uint4* C = pop.G + (size_t)bp.cslot * 2 * Wq;
+    const uint32_t f0 = (bp.kk0 >> 30) ? 0xffffffffu : 0u, f1 = (bp.kk1 >> 30) ? 0xffffffffu : 0u;
     double zacc[NT];
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt) zacc[tt] = 0.0;
