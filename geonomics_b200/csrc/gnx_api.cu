@@ -39,6 +39,7 @@ struct ProfSpan {
 struct gnx_ctx {
   gnx_config_t cfg;
   bool profiling = false;
+  bool no_tma = true;               // TMA-staged gamete kernel is opt-in: measured 2.3x slower (profiles/r01_notes.md)
   std::vector<ProfSpan> spans;
   cudaStream_t stream = nullptr;
   int device = 0;
@@ -773,6 +774,26 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
                                                       ctx->work, ctx->d_c, fnb);                          \
   } while (0)
     const int fnb = ctx->cfg.n_births_fixed ? (int)ctx->cfg.n_births_lambda : 0;
+    if (Wq >= 4 && Wq <= 32 && !ctx->no_tma) {
+      // rows >= 128 B: TMA-staged pipeline (k_gametes_tma)
+      const size_t Wb = 16 * (size_t)Wq, RB = 2 * Wb;
+      const size_t smem = GT_STAGES * (GT_NB * (2 * RB + 2 * Wb) + GT_NB * RB);
+      const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+#define MT(GW)                                                                                              \
+  do {                                                                                                      \
+    auto kern = ctx->cfg.n_traits <= 2 ? k_gametes_tma<GW, 2> : k_gametes_tma<GW, GNX_MAX_TRAITS>;           \
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    kern<<<grid_for(ctx, per_sm), GT_THREADS, smem, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,      \
+                                                         ctx->work, ctx->d_c, fnb);                         \
+  } while (0)
+      PROF(ctx, "k_gametes");
+      if (Wq <= 4) MT(4);
+      else if (Wq <= 8) MT(8);
+      else if (Wq <= 16) MT(16);
+      else MT(32);
+#undef MT
+      LAUNCHED(ctx);
+    } else {
     PROF(ctx, "k_gametes");
     if (Wq <= 1) MO(1);
     else if (Wq <= 2) MO(2);
@@ -782,6 +803,7 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
     else MO(32);
 #undef MO
     LAUNCHED(ctx);
+    }
   }
   PROF(ctx, "k_newborns");
   k_newborns<<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
@@ -1053,5 +1075,13 @@ extern "C" int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen) {
 extern "C" int gnx_set_debug(gnx_ctx* ctx, int32_t on) {
   ARG(ctx, "null ctx");
   ctx->prm.store_debug = on ? 1 : 0;
+  return GNX_OK;
+}
+
+
+/* A/B switch for the gamete kernel: 1 = TMA-staged pipeline when rows >= 128 B (default), 0 = register streaming */
+extern "C" int gnx_set_gamete_tma(gnx_ctx* ctx, int32_t on) {
+  ARG(ctx, "null ctx");
+  ctx->no_tma = !on;
   return GNX_OK;
 }

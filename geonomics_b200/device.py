@@ -177,6 +177,9 @@ class DeviceSpecies:
         """Keep n_nbrs / death_p / disp_tries / n_pairs raster readable (parity tests)."""
         _lib.check(self._L.gnx_set_debug(self._ctx, int(bool(on))), 'gnx_set_debug')
 
+    def set_gamete_tma(self, on=True):
+        _lib.check(self._L.gnx_set_gamete_tma(self._ctx, int(bool(on))), 'gnx_set_gamete_tma')
+
     def set_burn(self, burn):
         _lib.check(self._L.gnx_set_burn(self._ctx, int(bool(burn))), 'gnx_set_burn')
 
@@ -193,16 +196,20 @@ class DeviceSpecies:
             return
         d = _lib.Draws()
         keep = []
-        n = None
+
+        # the C struct carries one row count for every array: pad all of them (zeros) to the
+        # longest one so no site reads past its buffer
+        widths = dict(recomb_keys=2, start_homs=2, disp_dir=self.disp_R, disp_choice=self.disp_R,
+                      disp_dist=self.disp_R)
+        n = max([np.asarray(v).size // widths.get(k, 1) for k, v in draws.items() if v is not None] + [0])
 
         def put(name, key, dtype, typ, width=1):
-            nonlocal n
             a = draws.get(key)
             if a is None:
                 return
-            a = np.ascontiguousarray(a, dtype=dtype)
-            rows = a.size // width
-            n = rows if n is None else min(n, rows)
+            a = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+            if a.size < n * width:
+                a = np.concatenate([a, np.zeros(n * width - a.size, dtype=dtype)])
             keep.append(a)
             setattr(d, name, _ptr(a, typ))
         R = self.disp_R
@@ -225,7 +232,7 @@ class DeviceSpecies:
         put('sex_u', 'sex_u', np.float64, _lib.c_double_p)
         put('sex_redraw_u', 'sex_redraw_u', np.float64, _lib.c_double_p)
         put('death_u', 'death_u', np.float64, _lib.c_double_p)
-        d.n = int(n or 0)
+        d.n = int(n)
         _lib.check(self._L.gnx_set_draws(self._ctx, C.byref(d)), 'gnx_set_draws')
 
     # ---- population in / out ---------------------------------------------------------------

@@ -141,3 +141,30 @@ def compare_step(out, new_o, im_o, rtol=1e-6, exact_xy_tol=1e-9):
     assert rec['Nt'] == len(new_o['x'])
     assert rec['n_births'] == im_o['B']
     assert rec['n_deaths'] == im_o['n_deaths']
+
+
+def synthetic_case(L=1000, n=1500, n_traits=2, loci_per_trait=20, dim=(40, 40), seed=0, max_tries=8):
+    """A synthetic population in the golden-case format (arch, prm, state, draws), for parity
+    of the CUDA path against the (golden-pinned) oracle at genome sizes the reference-recorded
+    cases do not cover."""
+    from geonomics_b200 import workloads, genome_pack
+    from oracle import step_oracle as so
+    from oracle import draws as od
+    cfg = dict(dim=dim, N=n, L=L, n_traits=n_traits, loci_per_trait=loci_per_trait, mating_radius=2.0, b=0.5,
+               lam=1, R=0.5, phi=0.1, gamma=1.0, n_paths=500, recomb_rate=0.05, seed=seed, surfaces=False)
+    w = workloads.build(cfg, seed)
+    g = genome_pack.unpack_genomes(workloads.random_packed_genomes(n, L, seed + 1), L)
+    prm_w = w['prm']
+    arch = dict(land_dim=w['land_dim'], rasters=w['rasters'], K=w['rasters'][0] * prm_w['K_factor'], ww=None,
+                traits=w['gen_arch']['traits'], dom=np.zeros(L, np.int8), paths=w['gen_arch']['paths'],
+                move_surf=None, disp_surf=None)
+    arch['ww'] = round(0.1 * max(dim))
+    prm = dict(b=prm_w['b'], R=prm_w['R'], lam=1, n_births_fixed=True, mating_radius=2.0, d_min=0.0, d_max=1.0,
+               sex=False, sex_ratio_p=0.5, max_age=None, direction_mu=0.0, direction_kappa=0.0)
+    z = so.phenotype(g, arch['traits'])
+    state = dict(x=w['pop']['x'], y=w['pop']['y'], age=w['pop']['age'], sex=w['pop']['sex'],
+                 idx=w['pop']['idx'], g=g, z=z, max_ind_idx=n - 1)
+    rng = np.random.default_rng(seed + 5)
+    draws = od.make_draws(rng, dict(prm, move_distr=('wald', 1.0, 1.0), disp_distr=('wald', 1.0, 1.0)), n, n,
+                          len(arch['paths']), max_tries=max_tries)
+    return arch, prm, state, draws
