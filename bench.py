@@ -47,7 +47,7 @@ def algorithmic_bytes(W, T, cells, YX):
         'scan_pairs.apply': lambda s: s['n'] * 8 + s['P'] * (8 + 32 + 16 + 12),
         'k_gametes': lambda s: s['B'] * (4 * W + 2 * W + 8 + 8 * T + 4 + 8 + 8),   # rows; keys; z w; pair; slots
         'k_newborns': lambda s: s['B'] * (16 + 29 + 4),                          # midpoint r; record w; pair
-        'k_density_counts': lambda s: s['npre'] * 16,
+        'k_density_counts': lambda s: (s['npre'] + s['P']) * 16,
         'k_raster_N': lambda s: YX * 8,
         'k_raster_d': lambda s: YX * 24,
         'k_death': lambda s: s['npre'] * (16 + 8 * T + 8 + 8 * T + 8 + 4 + 8 + 1),

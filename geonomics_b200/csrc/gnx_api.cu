@@ -61,7 +61,7 @@ struct gnx_ctx {
   double* d_rasters = nullptr;
   double* d_K = nullptr;
   uint4* d_stage_genomes = nullptr;   // species-order staging for upload/download
-  bool have_density = false, have_paths = false, have_traits = false;
+  bool have_density = false, have_paths = false, have_traits = false, have_rasters = false;
   int64_t launches = 0;
   int burn = 0;
   int host_n_hint = 0;
@@ -206,7 +206,11 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &W.N_rast, plane);
   DM(ctx, &W.NP_rast, plane);
   DM(ctx, &W.d_rast, plane);
+  W.envd_stride = 1 + cfg->n_traits;
+  DM(ctx, &W.envd, plane * (size_t)W.envd_stride);
   DM(ctx, &W.e_out, (size_t)cap * cfg->n_layers);
+  DM(ctx, &W.fix_list, plane);
+  DM(ctx, &W.fix_count, 1);
   W.max_records = 1 << 16;
   DM(ctx, &W.records, (size_t)W.max_records);
   DM(ctx, &ctx->d_c, 1);
@@ -246,6 +250,14 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+static int pack_env(gnx_ctx* ctx) {
+  if (!ctx->have_traits || ctx->cfg.n_traits == 0 || !ctx->have_rasters) return GNX_OK;
+  PROF(ctx, "k_pack_env");
+  k_pack_env<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->land, ctx->traits, ctx->work, ctx->cfg.n_traits);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
 static int set_K(gnx_ctx* ctx) {
   const int ncell = ctx->cfg.dim_x * ctx->cfg.dim_y;
   PROF(ctx, "k_K_from_layer");
@@ -260,6 +272,9 @@ extern "C" int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters) {
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   CK(cudaMemcpyAsync(ctx->d_rasters, host_rasters, plane * ctx->cfg.n_layers * sizeof(double),
                      cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_rasters = true;
+  int r = pack_env(ctx);
+  if (r != GNX_OK) return r;
   return set_K(ctx);
 }
 
@@ -268,6 +283,8 @@ extern "C" int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_ra
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   CK(cudaMemcpyAsync(ctx->d_rasters + plane * layer, host_raster, plane * sizeof(double), cudaMemcpyHostToDevice,
                      ctx->stream));
+  int r = pack_env(ctx);
+  if (r != GNX_OK) return r;
   if (layer == ctx->cfg.K_layer) return set_K(ctx);      // model.py:651-652 (Species._set_K)
   return GNX_OK;
 }
@@ -338,7 +355,7 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   }
   if ((r = upload_vec(ctx, chunk_ptr, &T.chunk_ptr, ctx->trait_allocs)) != GNX_OK) return r;
   ctx->have_traits = true;
-  return GNX_OK;
+  return pack_env(ctx);
 }
 
 extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_paths) {
@@ -371,6 +388,63 @@ extern "C" int gnx_set_surface_tables(gnx_ctx* ctx, const uint16_t* host_move_f1
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
+}
+
+// ---- Clough-Tocher: Bezier ordinates -> monomial coefficients (setup) -----------------
+// w on micro-triangle k (b_k = smallest barycentric coordinate), written exactly as
+// scipy/interpolate/interpnd.pyx `_clough_tocher_2d_single` evaluates it.
+static double ct_w_forced(const double* c, int k, double b0, double b1) {
+  const double b[3] = {b0, b1, 1.0 - b0 - b1};
+  const double minval = b[k];
+  const double b1_ = b[0] - minval, b2 = b[1] - minval, b3 = b[2] - minval, b4 = 3 * minval;
+  const double c3000 = c[0], c0300 = c[1], c0030 = c[2], c0003 = c[3], c2100 = c[4], c2010 = c[5], c2001 = c[6],
+               c0210 = c[7], c0201 = c[8], c0021 = c[9], c1200 = c[10], c1020 = c[11], c1002 = c[12],
+               c0120 = c[13], c0102 = c[14], c0012 = c[15], c1101 = c[16], c1011 = c[17], c0111 = c[18];
+  const double B1 = b1_;
+  return B1 * B1 * B1 * c3000 + 3 * B1 * B1 * b2 * c2100 + 3 * B1 * B1 * b3 * c2010 + 3 * B1 * B1 * b4 * c2001 +
+         3 * B1 * b2 * b2 * c1200 + 6 * B1 * b2 * b4 * c1101 + 3 * B1 * b3 * b3 * c1020 + 6 * B1 * b3 * b4 * c1011 +
+         3 * B1 * b4 * b4 * c1002 + b2 * b2 * b2 * c0300 + 3 * b2 * b2 * b3 * c0210 + 3 * b2 * b2 * b4 * c0201 +
+         3 * b2 * b3 * b3 * c0120 + 6 * b2 * b3 * b4 * c0111 + 3 * b2 * b4 * b4 * c0102 + b3 * b3 * b3 * c0030 +
+         3 * b3 * b3 * b4 * c0021 + 3 * b3 * b4 * b4 * c0012 + b4 * b4 * b4 * c0003;
+}
+
+// M_k (10 x 19): w = sum_r (M_k c)_r * mono_r(b0, b1), mono order 1, b1, b1^2, b1^3, b0, b0 b1,
+// b0 b1^2, b0^2, b0^2 b1, b0^3.  Obtained by interpolation on the 10 nodes (i/3, j/3).
+static void ct_build_mono(double* M /* [3][10][19] */) {
+  double pts[10][2];
+  int np = 0;
+  for (int i = 0; i <= 3; ++i)
+    for (int j = 0; i + j <= 3; ++j) { pts[np][0] = i / 3.0; pts[np][1] = j / 3.0; ++np; }
+  auto mono = [](double b0, double b1, double* out) {
+    out[0] = 1; out[1] = b1; out[2] = b1 * b1; out[3] = b1 * b1 * b1; out[4] = b0; out[5] = b0 * b1;
+    out[6] = b0 * b1 * b1; out[7] = b0 * b0; out[8] = b0 * b0 * b1; out[9] = b0 * b0 * b0;
+  };
+  for (int k = 0; k < 3; ++k) {
+    // augmented system V x = W for the 19 unit coefficient vectors at once
+    double A[10][10 + 19];
+    for (int p = 0; p < 10; ++p) {
+      mono(pts[p][0], pts[p][1], A[p]);
+      for (int m = 0; m < 19; ++m) {
+        double e[19] = {0};
+        e[m] = 1.0;
+        A[p][10 + m] = ct_w_forced(e, k, pts[p][0], pts[p][1]);
+      }
+    }
+    for (int col = 0; col < 10; ++col) {           // Gauss-Jordan with partial pivoting
+      int piv = col;
+      for (int r = col + 1; r < 10; ++r) if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
+      if (piv != col) for (int q = 0; q < 29; ++q) std::swap(A[col][q], A[piv][q]);
+      const double inv = 1.0 / A[col][col];
+      for (int q = 0; q < 29; ++q) A[col][q] *= inv;
+      for (int r = 0; r < 10; ++r) {
+        if (r == col) continue;
+        const double f = A[r][col];
+        if (f != 0.0) for (int q = 0; q < 29; ++q) A[r][q] -= f * A[col][q];
+      }
+    }
+    for (int r = 0; r < 10; ++r)
+      for (int m = 0; m < 19; ++m) M[(k * 10 + r) * 19 + m] = A[r][10 + m];
+  }
 }
 
 extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
@@ -473,13 +547,33 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
     if ((r = up(pe.data(), sizeof(double) * pe.size(), (const void**)&D.p_e))) return r;
     CK(cudaStreamSynchronize(ctx->stream));     // the host vectors go out of scope below
   }
+  {
+    // per-triangle affine map (qi, qj) -> (b0, b1) and the Bezier -> monomial matrices
+    std::vector<double> aff((size_t)6 * D.ntri);
+    const double* P = dn->host_points;
+    for (int t = 0; t < D.ntri; ++t) {
+      const int v0 = dn->host_simplices[3 * t], v1 = dn->host_simplices[3 * t + 1], v2 = dn->host_simplices[3 * t + 2];
+      const double a00 = P[2 * v0] - P[2 * v2], a01 = P[2 * v1] - P[2 * v2];
+      const double a10 = P[2 * v0 + 1] - P[2 * v2 + 1], a11 = P[2 * v1 + 1] - P[2 * v2 + 1];
+      const double det = a00 * a11 - a01 * a10;
+      const double i00 = a11 / det, i01 = -a01 / det, i10 = -a10 / det, i11 = a00 / det;
+      double* o = &aff[(size_t)6 * t];
+      o[1] = i00; o[2] = i01; o[0] = -(i00 * P[2 * v2] + i01 * P[2 * v2 + 1]);
+      o[4] = i10; o[5] = i11; o[3] = -(i10 * P[2 * v2] + i11 * P[2 * v2 + 1]);
+    }
+    if ((r = up(aff.data(), sizeof(double) * aff.size(), (const void**)&D.tri_aff))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    static double mono[3 * 10 * 19];
+    ct_build_mono(mono);
+    CK(cudaMemcpyToSymbol(CT_MONO, mono, sizeof mono));
+  }
   if ((r = up(dn->host_square_tri, sizeof(int32_t) * 2 * (D.lat_ni - 1) * (D.lat_nj - 1),
               (const void**)&D.square_tri)))
     return r;
   DM(ctx, &D.counts, (size_t)2 * D.npts, &ctx->dens_allocs);
   DM(ctx, &D.vals, (size_t)2 * D.npts, &ctx->dens_allocs);
   DM(ctx, &D.grad, (size_t)4 * D.npts, &ctx->dens_allocs);
-  DM(ctx, &D.coef, (size_t)2 * D.ntri * 19 + 64, &ctx->dens_allocs);
+  DM(ctx, &D.coef, (size_t)2 * D.ntri * CT_STRIDE + 64, &ctx->dens_allocs);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_density = true;
   return GNX_OK;
@@ -830,10 +924,8 @@ extern "C" int gnx_density_counts(gnx_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(ctx->dens.counts, 0, (size_t)2 * ctx->dens.npts * 4, s));
   PROF(ctx, "k_density_counts");
-  k_density_counts<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 0);
-  LAUNCHED(ctx);
-  PROF(ctx, "k_density_counts");
-  k_density_counts<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, 1);
+  // one launch: blockIdx.y = 0 counts all individuals, 1 counts pair midpoints
+  k_density_counts<<<dim3(2 * ctx->num_sms, 2), 512, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -857,13 +949,20 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   }
   LAUNCHED(ctx);
   PROF(ctx, "k_ct_coefficients");
-  k_ct_coefficients<<<std::max(1, (2 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
+  k_ct_coefficients<<<std::max(1, (6 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
   LAUNCHED(ctx);
+  CK(cudaMemsetAsync(ctx->work.fix_count, 0, sizeof(int32_t), s));
   PROF(ctx, "k_raster_N");
   k_raster_N<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
+  PROF(ctx, "k_raster_N_fix");
+  k_raster_N_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
   PROF(ctx, "k_raster_d");
   k_raster_d<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
+  LAUNCHED(ctx);
+  PROF(ctx, "k_raster_d_fix");
+  k_raster_d_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -999,7 +1098,7 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
     case GNX_F_DISP_TRIES: p = W.disp_tries; b = (size_t)h.B * 4; break;
     case GNX_F_E: p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
     case GNX_F_COUNTERS: p = ctx->d_c; b = sizeof(Counters); break;
-    case 31: p = D.coef + (size_t)2 * D.ntri * 19; b = 64 * 8; break;   /* debug scratch */
+    case 31: p = D.coef + (size_t)2 * D.ntri * CT_STRIDE; b = 64 * 8; break;   /* debug scratch */
     case GNX_F_GENOMES: p = ctx->d_stage_genomes; b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4); break;
     default: g_last_error = "unknown field"; return GNX_ERR_ARG;
   }

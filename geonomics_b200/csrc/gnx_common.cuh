@@ -99,12 +99,13 @@ struct Dens {
   int32_t padded;          // every vertex has <= 8 neighbours
   int32_t lat_ni, lat_nj;
   const int32_t* square_tri;
+  const double* tri_aff;   // [ntri][6]: b0 = a0 + a1*qi + a2*qj, b1 = a3 + a4*qi + a5*qj
   int32_t colourable;
   // work
   int32_t* counts;   // [2][npts]
   double* vals;      // [2][npts]
   double* grad;      // [2][npts][2]
-  double* coef;      // [2][ntri][19]
+  double* coef;      // [2][ntri][3][10] monomial coefficients per micro-triangle
 };
 
 struct Work {
@@ -130,7 +131,11 @@ struct Work {
   double* N_rast;
   double* NP_rast;
   double* d_rast;
+  double* envd;            // [Y*X][1 + T]: d raster slot + each trait's environment value
+  int32_t envd_stride;
   double* e_out;
+  int32_t* fix_list;       // landscape cells whose N needs the exact-order re-evaluation
+  int32_t* fix_count;
   gnx_step_record_t* records;
   int32_t max_records;
 };

@@ -832,8 +832,9 @@ __global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const
 // global atomics.
 // ========================================================================================
 #define DENS_SMEM_BINS 4096
-__global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const Counters* c, Dens d, int which) {
-  // which = 0: all individuals alive before mortality; 1: pair midpoints
+__global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const Counters* c, Dens d) {
+  // blockIdx.y = 0: all individuals alive before mortality; 1: pair midpoints
+  const int which = blockIdx.y;
   const double* __restrict__ xs = which == 0 ? pop.x[c->cur] : w.mid_x;
   const double* __restrict__ ys = which == 0 ? pop.y[c->cur] : w.mid_y;
   __shared__ int hist[DENS_SMEM_BINS];
@@ -843,7 +844,7 @@ __global__ void __launch_bounds__(256) k_density_counts(Pop pop, Work w, const C
   __syncthreads();
   const int n = which == 0 ? c->n_pre : c->P;
   int* gcounts = d.counts + (size_t)which * d.npts;
-  for (int i = GTID; i < n; i += GSTRIDE) {
+  for (int i = GTID; i < n; i += GSTRIDE) {       // GTID / GSTRIDE use the x dimension only
     const double x = xs[i], y = ys[i];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -1023,10 +1024,15 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
   if (threadIdx.x == 0) c->gs_iters[which] = iters;
 }
 
+__constant__ double CT_MONO[3 * 10 * 19];      // set by gnx_set_density
+#define CT_STRIDE 49                           // per triangle: 3 x 10 monomial coefficients + 19 Bezier ordinates
+
 // Bezier ordinates of every triangle (`_clough_tocher_2d_single`, point-independent part)
 __global__ void __launch_bounds__(128) k_ct_coefficients(Dens d) {
-  const int total = 2 * d.ntri;
-  for (int id = GTID; id < total; id += GSTRIDE) {
+  // 3 threads per (density, triangle): each converts the ordinates to one micro-triangle's monomials
+  const int total = 6 * d.ntri;
+  for (int id3 = GTID; id3 < total; id3 += GSTRIDE) {
+    const int id = id3 / 3, kpart = id3 - 3 * id;
     const int which = id / d.ntri, t = id - which * d.ntri;
     const double* f = d.vals + (size_t)which * d.npts;
     const double* gr = d.grad + (size_t)which * d.npts * 2;
@@ -1082,15 +1088,30 @@ __global__ void __launch_bounds__(128) k_ct_coefficients(Dens d) {
     const double c0102 = (c1101 + c0111 + c0201) / 3;
     const double c0012 = (c1011 + c0111 + c0021) / 3;
     const double c0003 = (c1002 + c0102 + c0012) / 3;
-    double* o = d.coef + ((size_t)which * d.ntri + t) * 19;
-    o[0] = c3000; o[1] = c0300; o[2] = c0030; o[3] = c0003; o[4] = c2100; o[5] = c2010; o[6] = c2001;
-    o[7] = c0210; o[8] = c0201; o[9] = c0021; o[10] = c1200; o[11] = c1020; o[12] = c1002; o[13] = c0120;
-    o[14] = c0102; o[15] = c0012; o[16] = c1101; o[17] = c1011; o[18] = c0111;
+    const double o[19] = {c3000, c0300, c0030, c0003, c2100, c2010, c2001, c0210, c0201, c0021,
+                          c1200, c1020, c1002, c0120, c0102, c0012, c1101, c1011, c0111};
+    // Bezier ordinates -> monomial coefficients in (b0, b1) for each micro-triangle
+    double* mo = d.coef + ((size_t)which * d.ntri + t) * CT_STRIDE;
+    if (kpart == 0) {
+#pragma unroll
+      for (int cidx = 0; cidx < 19; ++cidx) mo[30 + cidx] = o[cidx];
+    }
+    {
+      const int k = kpart;
+      for (int r = 0; r < 10; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int cidx = 0; cidx < 19; ++cidx) acc = fma(CT_MONO[(k * 10 + r) * 19 + cidx], o[cidx], acc);
+        mo[k * 10 + r] = acc;
+      }
+    }
   }
 }
 
-// point-dependent part of `_clough_tocher_2d_single` at (qi, qj)
-__device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double qi, double qj) {
+// Exact-order evaluation (scipy's own formula and operation order) from the Bezier ordinates.
+// Used where the interpolant is at rounding-noise level (|w| < 1e-7), so that the sign / exact
+// zero-ness of empty regions -- which d = N_d / N amplifies -- matches scipy's.
+__device__ __noinline__ double ct_eval_exact(const Dens& d, int which, double qi, double qj) {
   int si = (int)floor(qi / d.hww), sj = (int)floor(qj / d.hww);
   si = min(max(si, 0), d.lat_ni - 2);
   sj = min(max(sj, 0), d.lat_nj - 2);
@@ -1110,7 +1131,7 @@ __device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double
     b2 = 1 - b0 - b1;
     if (fmin(b0, fmin(b1, b2)) >= -1e-12 || k == 1) break;
   }
-  const double* cf = d.coef + ((size_t)which * d.ntri + t) * 19;
+  const double* cf = d.coef + ((size_t)which * d.ntri + t) * CT_STRIDE + 30;
   const double minval = fmin(b0, fmin(b1, b2));
   const double B1 = b0 - minval, B2 = b1 - minval, B3 = b2 - minval, B4 = 3 * minval;
   const double c3000 = cf[0], c0300 = cf[1], c0030 = cf[2], c0003 = cf[3], c2100 = cf[4], c2010 = cf[5],
@@ -1124,6 +1145,38 @@ __device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double
           3 * B3 * B3 * B4 * c0021 + 3 * B3 * B4 * B4 * c0012 + B4 * B4 * B4 * c0003);
 }
 
+// point-dependent part of `_clough_tocher_2d_single` at (qi, qj).  Inside a triangle the
+// interpolant is, on each of its three micro-triangles (k = index of the smallest
+// barycentric coordinate), a bivariate cubic in (b0, b1); k_ct_coefficients converts the 19
+// Bezier ordinates to those 3 x 10 monomial coefficients (CT_MONO, fixed 10x19 matrices built
+// at setup), and the barycentric coordinates are an affine map of (qi, qj) precomputed per
+// triangle (tri_aff), so one evaluation is ~12 FMAs with no division.
+__device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double qi, double qj) {
+  int si = (int)floor(qi / d.hww), sj = (int)floor(qj / d.hww);
+  si = min(max(si, 0), d.lat_ni - 2);
+  sj = min(max(sj, 0), d.lat_nj - 2);
+  const int2 st = __ldg(reinterpret_cast<const int2*>(d.square_tri) + (si * (d.lat_nj - 1) + sj));
+  int t = st.x;
+  const double* a = d.tri_aff + 6 * t;
+  double b0 = fma(a[2], qj, fma(a[1], qi, a[0]));
+  double b1 = fma(a[5], qj, fma(a[4], qi, a[3]));
+  double b2 = 1.0 - b0 - b1;
+  if (fmin(b0, fmin(b1, b2)) < -1e-12) {
+    t = st.y;
+    a = d.tri_aff + 6 * t;
+    b0 = fma(a[2], qj, fma(a[1], qi, a[0]));
+    b1 = fma(a[5], qj, fma(a[4], qi, a[3]));
+    b2 = 1.0 - b0 - b1;
+  }
+  const int k = (b0 <= b1 && b0 <= b2) ? 0 : ((b1 <= b2) ? 1 : 2);
+  const double* m = d.coef + ((size_t)which * d.ntri + t) * CT_STRIDE + k * 10;
+  // order: 1, b1, b1^2, b1^3, b0, b0 b1, b0 b1^2, b0^2, b0^2 b1, b0^3
+  const double r0 = fma(b1, fma(b1, fma(b1, m[3], m[2]), m[1]), m[0]);
+  const double r1 = fma(b1, fma(b1, m[6], m[5]), m[4]);
+  const double r2 = fma(b1, m[8], m[7]);
+  return fma(b0, fma(b0, fma(b0, m[9], r2), r1), r0);
+}
+
 // N raster (Species._calc_density species.py:845-882, clip >= 0) + its maximum
 __global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Counters* c) {
   const int ncell = land.X * land.Y;
@@ -1131,7 +1184,27 @@ __global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Cou
   for (int id = GTID; id < ncell; id += GSTRIDE) {
     const int i = id / land.X, j = id - i * land.X;
     double v = ct_eval_point(d, 0, i + 0.5, j + 0.5);
+    // where the interpolant is at rounding-noise level its sign / exact zero-ness is what
+    // d = N_d / N amplifies: those cells are re-evaluated in scipy's exact operation order
+    // by k_raster_N_fix (none in a populated landscape)
+    if (fabs(v) < 1e-7) w.fix_list[atomicAdd(w.fix_count, 1)] = id;
     v = v < 0.0 ? 0.0 : v;                    // np.clip(dens, a_min=0)
+    w.N_rast[id] = v;
+    mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&c->nmax_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+__global__ void __launch_bounds__(256) k_raster_N_fix(Dens d, Land land, Work w, Counters* c) {
+  const int nfix = *w.fix_count;
+  double mx = 0.0;
+  for (int k = GTID; k < nfix; k += GSTRIDE) {
+    const int id = w.fix_list[k];
+    const int i = id / land.X, j = id - i * land.X;
+    double v = ct_eval_exact(d, 0, i + 0.5, j + 0.5);
+    v = v < 0.0 ? 0.0 : v;
     w.N_rast[id] = v;
     mx = fmax(mx, v);
   }
@@ -1142,26 +1215,43 @@ __global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Cou
 
 // a7 + a14: n_pairs raster (demography.py:60-91) and the logistic d raster
 // (demography.py:104-172), never materialising dNdt / N_b / N_d.
+__device__ __forceinline__ void raster_d_cell(const Land& land, const Params& prm, const Work& w, int id,
+                                              double np, double Nmax) {
+  np = np < 0.0 ? 0.0 : np;
+  if (isnan(np)) np = 0.0;
+  if (prm.store_debug) w.NP_rast[id] = np;
+  const double N = w.N_rast[id], K = land.K[id];
+  double dNdt = prm.c.R * (1 - (N / K)) * N;        // demography.py:95-97
+  if (dNdt < -Nmax) dNdt = -Nmax;                   // np.clip(a_min=-N.max())
+  if (isnan(dNdt) || isinf(dNdt)) dNdt = -Nmax;
+  const double N_b = prm.c.b * prm.c.n_births_lambda * np;     // demography.py:142
+  const double N_d = N_b - dNdt;                    // demography.py:149
+  double dv = N_d / N;                              // demography.py:159-160
+  if (isnan(dv)) dv = 0.0;
+  dv = dv < prm.c.d_min ? prm.c.d_min : (dv > prm.c.d_max ? prm.c.d_max : dv);
+  w.envd[(size_t)id * w.envd_stride] = dv;          // packed [cell][d | e_trait0 | e_trait1 ...]
+  if (prm.store_debug) w.d_rast[id] = dv;
+}
+
 __global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c) {
   const int ncell = land.X * land.Y;
   const double Nmax = __longlong_as_double((long long)c->nmax_bits);
-  const double R = prm.c.R, b = prm.c.b, lam = prm.c.n_births_lambda;
   for (int id = GTID; id < ncell; id += GSTRIDE) {
     const int i = id / land.X, j = id - i * land.X;
-    double np = ct_eval_point(d, 1, i + 0.5, j + 0.5);
-    np = np < 0.0 ? 0.0 : np;
-    if (isnan(np)) np = 0.0;
-    if (prm.store_debug) w.NP_rast[id] = np;
-    const double N = w.N_rast[id], K = land.K[id];
-    double dNdt = R * (1 - (N / K)) * N;              // demography.py:95-97
-    if (dNdt < -Nmax) dNdt = -Nmax;                   // np.clip(a_min=-N.max())
-    if (isnan(dNdt) || isinf(dNdt)) dNdt = -Nmax;
-    const double N_b = b * lam * np;                  // demography.py:142
-    const double N_d = N_b - dNdt;                    // demography.py:149
-    double dv = N_d / N;                              // demography.py:159-160
-    if (isnan(dv)) dv = 0.0;
-    dv = dv < prm.c.d_min ? prm.c.d_min : (dv > prm.c.d_max ? prm.c.d_max : dv);
-    w.d_rast[id] = dv;
+    raster_d_cell(land, prm, w, id, ct_eval_point(d, 1, i + 0.5, j + 0.5), Nmax);
+  }
+}
+
+// cells whose density is at rounding-noise level (fix_list, built by k_raster_N): there
+// d = N_d / N turns the noise of the pair-density interpolant into 0 or 1, so it too is
+// evaluated in scipy's exact operation order
+__global__ void __launch_bounds__(256) k_raster_d_fix(Dens d, Land land, Params prm, Work w, const Counters* c) {
+  const int nfix = *w.fix_count;
+  const double Nmax = __longlong_as_double((long long)c->nmax_bits);
+  for (int k = GTID; k < nfix; k += GSTRIDE) {
+    const int id = w.fix_list[k];
+    const int i = id / land.X, j = id - i * land.X;
+    raster_d_cell(land, prm, w, id, ct_eval_exact(d, 1, i + 0.5, j + 0.5), Nmax);
   }
 }
 
@@ -1179,11 +1269,12 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
     const double x = pop.x[cur][i], y = pop.y[cur][i];
     const int cx = (int)x, cy = (int)y;
     const size_t cell = (size_t)cy * land.X + cx;
-    double p = w.d_rast[cell];                                   // demography.py:306
+    const double* __restrict__ ed = w.envd + cell * w.envd_stride;   // one sector: d and the traits' e
+    double p = ed[0];                                              // demography.py:306
     if (prm.selection) {
       double wfit = 1.0;
       for (int tt = 0; tt < T; ++tt) {
-        const double e = tr.univ_adv[tt] ? 1.0 : __ldg(&land.rasters[(size_t)tr.layer[tt] * plane + cell]);
+        const double e = tr.univ_adv[tt] ? 1.0 : ed[1 + tt];     // species.py:913-922 gather
         const double z = pop.z[cur][(size_t)tt * pop.cap + i];
         const double phi = tr.phi_rast[tt] ? __ldg(&tr.phi_rast[tt][cell]) : tr.phi[tt];
         const double diff = fabs(e - z);
@@ -1281,6 +1372,14 @@ __global__ void __launch_bounds__(256) k_gather_genomes(Pop pop, uint4* out, con
     const int i = (int)(k / row), q = (int)(k - (long long)i * row);
     out[k] = pop.G[(size_t)pop.gslot[cur][i] * row + q];
   }
+}
+
+// environment values of each trait's layer packed next to the d slot (setup / env change)
+__global__ void __launch_bounds__(256) k_pack_env(Land land, Traits tr, Work w, int T) {
+  const size_t plane = (size_t)land.X * land.Y;
+  for (size_t id = GTID; id < plane; id += GSTRIDE)
+    for (int tt = 0; tt < T; ++tt)
+      w.envd[id * w.envd_stride + 1 + tt] = land.rasters[(size_t)tr.layer[tt] * plane + id];
 }
 
 __global__ void k_K_from_layer(const double* rast, double* K, double factor, int ncell) {
