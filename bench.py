@@ -215,8 +215,8 @@ def main():
     ap.add_argument('--workload', default='c2')
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (debug only)')
-    ap.add_argument('--cpu-sample', type=int, default=20000)
-    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--cpu-sample', type=int, default=100000)
+    ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
     args = ap.parse_args()
@@ -235,6 +235,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION/INFO; the contract is
+        # ONE JSON line on stdout, so keep NCCL quiet unless explicitly asked otherwise
+        if not os.environ.get('GNX_KEEP_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 

@@ -61,6 +61,7 @@ struct gnx_ctx {
   double* d_rasters = nullptr;
   double* d_K = nullptr;
   uint4* d_stage_genomes = nullptr;   // species-order staging for upload/download
+  double* d_stage_z = nullptr;        // [n][T] row-major staging of phenotypes
   bool have_density = false, have_paths = false, have_traits = false, have_rasters = false;
   int64_t launches = 0;
   int burn = 0;
@@ -168,6 +169,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &P.G, (size_t)cap * 2 * ctx->Wq);
   DM(ctx, &P.free_slots, cap);
   DM(ctx, &ctx->d_stage_genomes, (size_t)cap * 2 * ctx->Wq);
+  DM(ctx, &ctx->d_stage_z, (size_t)cap * std::max(1, cfg->n_traits));
   // landscape
   Land& Ld = ctx->land;
   Ld.X = cfg->dim_x;
@@ -649,51 +651,28 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
   const size_t n = (size_t)pop->n;
   cudaStream_t s = ctx->stream;
   Pop& P = ctx->pop;
-  Counters h;
-  memset(&h, 0, sizeof h);
-  h.n = h.n_pre = (int)n;
-  h.cur = 0;
-  h.n_free = 0;
-  h.n_slots = (int)n;
-  h.max_idx = pop->max_ind_idx;
-  // keep the running time-step counter across uploads (Philox counter)
-  Counters old;
-  int r = read_counters(ctx, &old);
-  if (r != GNX_OK) return r;
-  h.t = old.t;
-  h.n_rec = old.n_rec;
+  // everything below is asynchronous on the ctx stream: no host-side staging loops
   CK(cudaMemcpyAsync(P.x[0], pop->x, n * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(P.y[0], pop->y, n * 8, cudaMemcpyHostToDevice, s));
   if (pop->age) CK(cudaMemcpyAsync(P.age[0], pop->age, n * 4, cudaMemcpyHostToDevice, s));
   else CK(cudaMemsetAsync(P.age[0], 0, n * 4, s));
   if (pop->sex) CK(cudaMemcpyAsync(P.sex[0], pop->sex, n, cudaMemcpyHostToDevice, s));
   else CK(cudaMemsetAsync(P.sex[0], 0, n, s));
-  std::vector<int64_t> ids;
-  std::vector<int32_t> slots(n);
-  for (size_t i = 0; i < n; ++i) slots[i] = (int32_t)i;
   if (pop->idx) CK(cudaMemcpyAsync(P.idx[0], pop->idx, n * 8, cudaMemcpyHostToDevice, s));
-  else {
-    ids.resize(n);
-    for (size_t i = 0; i < n; ++i) ids[i] = (int64_t)i;
-    CK(cudaMemcpyAsync(P.idx[0], ids.data(), n * 8, cudaMemcpyHostToDevice, s));
-    if (h.max_idx < (int64_t)n - 1) h.max_idx = (int64_t)n - 1;
-  }
-  CK(cudaMemcpyAsync(P.gslot[0], slots.data(), n * 4, cudaMemcpyHostToDevice, s));
-  if (pop->genomes) {
-    CK(cudaMemcpyAsync(P.G, pop->genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyHostToDevice, s));
-  }
+  if (pop->genomes) CK(cudaMemcpyAsync(P.G, pop->genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyHostToDevice, s));
   if (pop->fit) CK(cudaMemcpyAsync(P.fit[0], pop->fit, n * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->d_c, &h, sizeof h, cudaMemcpyHostToDevice, s));
-  if (pop->z && ctx->cfg.n_traits > 0) {
-    // host z is [n][T]; device z is [T][cap]
-    std::vector<double> zt(n);
-    for (int t = 0; t < ctx->cfg.n_traits; ++t) {
-      for (size_t i = 0; i < n; ++i) zt[i] = pop->z[i * ctx->cfg.n_traits + t];
-      CK(cudaMemcpyAsync(P.z[0] + (size_t)t * P.cap, zt.data(), n * 8, cudaMemcpyHostToDevice, s));
-      CK(cudaStreamSynchronize(s));
-    }
-  } else if (pop->genomes && ctx->cfg.n_traits > 0 && ctx->have_traits) {
-    r = gnx_phenotype(ctx);
+  const bool have_z = pop->z && ctx->cfg.n_traits > 0;
+  if (have_z) CK(cudaMemcpyAsync(ctx->d_stage_z, pop->z, n * ctx->cfg.n_traits * 8, cudaMemcpyHostToDevice, s));
+  // slots = identity, ids = 0..n-1 when absent, z transposed to [T][cap], counters reset
+  // (the Philox time-step counter and the record cursor carry over)
+  int64_t max_idx = pop->max_ind_idx;
+  if (!pop->idx && max_idx < (int64_t)n - 1) max_idx = (int64_t)n - 1;
+  PROF(ctx, "k_upload_finish");
+  k_upload_finish<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c, (int)n, max_idx, pop->idx ? 0 : 1,
+                                                  have_z ? ctx->d_stage_z : nullptr);
+  LAUNCHED(ctx);
+  if (!have_z && pop->genomes && ctx->cfg.n_traits > 0 && ctx->have_traits) {
+    int r = gnx_phenotype(ctx);
     if (r != GNX_OK) return r;
   }
   CK(cudaStreamSynchronize(s));
@@ -736,12 +715,10 @@ extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
     CK(cudaMemcpyAsync(pop->genomes, ctx->d_stage_genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyDeviceToHost, s));
   }
   if (pop->z && ctx->cfg.n_traits > 0) {
-    std::vector<double> zt(n);
-    for (int t = 0; t < ctx->cfg.n_traits; ++t) {
-      CK(cudaMemcpyAsync(zt.data(), P.z[cur] + (size_t)t * P.cap, n * 8, cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      for (size_t i = 0; i < n; ++i) pop->z[i * ctx->cfg.n_traits + t] = zt[i];
-    }
+    PROF(ctx, "k_z_to_rows");
+    k_z_to_rows<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c, ctx->d_stage_z);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(pop->z, ctx->d_stage_z, n * ctx->cfg.n_traits * 8, cudaMemcpyDeviceToHost, s));
   }
   if (pop->e) {
     r = gnx_sample_env(ctx);

@@ -1382,6 +1382,28 @@ __global__ void __launch_bounds__(256) k_pack_env(Land land, Traits tr, Work w, 
       w.envd[id * w.envd_stride + 1 + tt] = land.rasters[(size_t)tr.layer[tt] * plane + id];
 }
 
+// upload epilogue: identity genome slots, default ids, z [n][T] -> [T][cap], counters reset
+// (time-step counter and record cursor carry over)
+__global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int n, long long max_idx, int make_ids,
+                                                        const double* z_rows) {
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    pop.gslot[0][i] = i;
+    if (make_ids) pop.idx[0][i] = i;
+    if (z_rows)
+      for (int tt = 0; tt < pop.T; ++tt) pop.z[0][(size_t)tt * pop.cap + i] = z_rows[(size_t)i * pop.T + tt];
+  }
+  if (GTID == 0) {
+    c->n = n; c->n_pre = n; c->P = 0; c->B = 0; c->deaths = 0; c->n_free = 0; c->n_slots = n; c->cur = 0;
+    c->max_idx = max_idx; c->err = 0; c->nmax_bits = 0ull;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_z_to_rows(Pop pop, const Counters* c, double* z_rows) {
+  const int n = c->n, cur = c->cur;
+  for (int i = GTID; i < n; i += GSTRIDE)
+    for (int tt = 0; tt < pop.T; ++tt) z_rows[(size_t)i * pop.T + tt] = pop.z[cur][(size_t)tt * pop.cap + i];
+}
+
 __global__ void k_K_from_layer(const double* rast, double* K, double factor, int ncell) {
   for (int id = GTID; id < ncell; id += GSTRIDE) K[id] = rast[id] * factor;   // species.py:546-547
 }
