@@ -93,6 +93,7 @@ class Draws(C.Structure):
         ('poisson', c_int32_p), ('recomb_keys', c_int32_p), ('start_homs', c_int32_p),
         ('disp_dir', c_double_p), ('disp_choice', c_int32_p), ('disp_dist', c_double_p),
         ('sex_u', c_double_p), ('sex_redraw_u', c_double_p), ('death_u', c_double_p),
+        ('pan_u', c_double_p), ('pan_R', c_uint32_p),
     ]
 
 

@@ -617,6 +617,8 @@ extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
   if ((r = up(dr->sex_u, n * 8, (const void**)&D.sex_u))) return r;
   if ((r = up(dr->sex_redraw_u, n * 8, (const void**)&D.sex_redraw_u))) return r;
   if ((r = up(dr->death_u, n * 8, (const void**)&D.death_u))) return r;
+  if ((r = up(dr->pan_u, n * 8, (const void**)&D.pan_u))) return r;
+  if ((r = up(dr->pan_R, 2 * n * 4, (const void**)&D.pan_R))) return r;
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
 }
@@ -789,6 +791,7 @@ static int finish_binning(gnx_ctx* ctx) {
 
 extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  if (ctx->cfg.mating_radius <= 0) return GNX_OK;      // panmixia needs no spatial binning
   int r = age_move_bin(ctx, 0, 0, 1);
   if (r != GNX_OK) return r;
   return finish_binning(ctx);
@@ -796,7 +799,12 @@ extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
 
 extern "C" int gnx_find_mates(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
-  ARG(ctx->cfg.mating_radius > 0, "panmixia is not implemented in this build");
+  if (ctx->cfg.mating_radius <= 0) {          // mating_radius = None: Wright-Fisher style panmixia
+    PROF(ctx, "k_panmixia");
+    k_panmixia<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
+    LAUNCHED(ctx);
+    return GNX_OK;
+  }
   PROF(ctx, "k_find_mates");
   const int g = grid_for(ctx, 16);
 #define FM(MODE) k_find_mates<MODE><<<g, 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
@@ -811,7 +819,8 @@ extern "C" int gnx_find_mates(gnx_ctx* ctx) {
 extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   const bool fixed = ctx->cfg.n_births_fixed != 0;
-  PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0};
+  PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0,
+              ctx->cfg.mating_radius <= 0 ? 1 : 0};
   if (fixed) ARG(ps.fixed_nb >= 1, "n_births_fixed needs n_births_distr_lambda >= 1");
   int r = run_scan(ctx, ps, "scan_pairs");
   if (r != GNX_OK) return r;
@@ -977,8 +986,9 @@ extern "C" int gnx_sample_env(gnx_ctx* ctx) {
 static int one_step(gnx_ctx* ctx) {
   int r;
   // a1 + a2 + a4 fused: age, movement, cell keys + histogram
-  if ((r = age_move_bin(ctx, 1, ctx->cfg.move ? 1 : 0, 1))) return r;
-  if ((r = finish_binning(ctx))) return r;
+  const bool panmixia = ctx->cfg.mating_radius <= 0;
+  if ((r = age_move_bin(ctx, 1, ctx->cfg.move ? 1 : 0, panmixia ? 0 : 1))) return r;
+  if (!panmixia && (r = finish_binning(ctx))) return r;
   if ((r = gnx_find_mates(ctx))) return r;
   if ((r = gnx_dedup_pairs(ctx))) return r;
   if ((r = gnx_make_offspring(ctx))) return r;

@@ -157,6 +157,8 @@ struct DevDraws {
   const double* sex_u;
   const double* sex_redraw_u;
   const double* death_u;
+  const double* pan_u;
+  const uint32_t* pan_R;
   int32_t disp_R;
 };
 

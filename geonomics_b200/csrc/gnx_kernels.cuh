@@ -328,6 +328,28 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
   }
 }
 
+// Panmixia (mating_radius = None), species.py:2178-2194: n_mates ~ Binomial(N, b) mating slots
+// (one Bernoulli(b) per individual has exactly that sum), each drawing two individuals with
+// replacement; selfing pairs are dropped; with sexes, column 0 must be female and column 1
+// male (mating.py:41-55).  No de-duplication (mating.py:64-65).
+__global__ void __launch_bounds__(256) k_panmixia(Pop pop, Params prm, DevDraws dr, Work w, const Counters* c) {
+  const int n = c->n, cur = c->cur;
+  const int64_t t = c->t;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_PANMIXIA, t);
+    const double u = dr.pan_u ? dr.pan_u[i] : g.uniform();
+    const uint32_t R0 = dr.pan_R ? dr.pan_R[2 * i] : g.u32();
+    const uint32_t R1 = dr.pan_R ? dr.pan_R[2 * i + 1] : g.u32();
+    const bool active = prm.c.b >= 1.0 || u < prm.c.b;
+    const int a = (int)choose_k(R0, (uint32_t)n), b2 = (int)choose_k(R1, (uint32_t)n);
+    bool ok = active && a != b2;
+    if (ok && prm.c.sex) ok = pop.sex[cur][a] == 0 && pop.sex[cur][b2] == 1;
+    w.mate[i] = ok ? a : -1;
+    w.perm[i] = b2;
+    if (prm.store_debug) w.n_nbrs[i] = n - 1;
+  }
+}
+
 // ========================================================================================
 // a6 + a8: sex filter / reciprocal de-dup (mating.py:41-63), stream compaction into the
 // canonical pair list, births per pair (species.py:604-609, mating.py:120-126), offspring
@@ -339,10 +361,12 @@ struct PairScan {
   const Counters* cc;
   int32_t sexed;
   int32_t fixed_nb;      // > 0: n_births_fixed
+  int32_t panmixia;      // pairs are (mate[i], perm[i]) drawn by k_panmixia, already filtered
   __device__ int size(const Counters* c) const { return c->n; }
   __device__ bool keep(int i) const {
     int m = w.mate[i];
     if (m < 0) return false;
+    if (panmixia) return true;
     if (sexed) {
       const int8_t* sx = pop.sex[cc->cur];
       return sx[i] == 0 && sx[m] == 1;                 // mating.py:41-55
@@ -353,8 +377,10 @@ struct PairScan {
   __device__ void apply(int i, u64 v, u64 ex) const {
     if (!v) return;
     const int p = (int)(ex >> 32);
-    const int m = w.mate[i];
     const int cur = cc->cur;
+    const int slot = i;
+    const int m = panmixia ? w.perm[slot] : w.mate[slot];
+    i = panmixia ? w.mate[slot] : slot;
     w.pairs[2 * p] = i;
     w.pairs[2 * p + 1] = m;
     w.mid_x[p] = (pop.x[cur][i] + pop.x[cur][m]) / 2;     // species.py:640-641
@@ -386,7 +412,9 @@ __global__ void __launch_bounds__(256) k_draw_births(Pop pop, Params prm, DevDra
     int nbv;
     if (dr.poisson) nbv = dr.poisson[p];
     else {
-      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][w.pairs[2 * p]], SITE_BIRTHS, c->t);
+      // keyed by the pair's position in the canonical pair list (an individual can belong to
+      // several pairs under panmixia)
+      RngStream g(prm.seed_lo, prm.seed_hi, (int64_t)p, SITE_BIRTHS, c->t);
       nbv = sample_poisson(g, prm.c.n_births_lambda);
     }
     w.nb[p] = max(nbv, 1);                   // mating.py:125

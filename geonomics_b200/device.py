@@ -199,7 +199,7 @@ class DeviceSpecies:
 
         # the C struct carries one row count for every array: pad all of them (zeros) to the
         # longest one so no site reads past its buffer
-        widths = dict(recomb_keys=2, start_homs=2, disp_dir=self.disp_R, disp_choice=self.disp_R,
+        widths = dict(recomb_keys=2, start_homs=2, pan_R=2, disp_dir=self.disp_R, disp_choice=self.disp_R,
                       disp_dist=self.disp_R)
         n = max([np.asarray(v).size // widths.get(k, 1) for k, v in draws.items() if v is not None] + [0])
 
@@ -232,6 +232,8 @@ class DeviceSpecies:
         put('sex_u', 'sex_u', np.float64, _lib.c_double_p)
         put('sex_redraw_u', 'sex_redraw_u', np.float64, _lib.c_double_p)
         put('death_u', 'death_u', np.float64, _lib.c_double_p)
+        put('pan_u', 'pan_u', np.float64, _lib.c_double_p)
+        put('pan_R', 'pan_R', np.uint32, _lib.c_uint32_p, 2)
         d.n = int(n)
         _lib.check(self._L.gnx_set_draws(self._ctx, C.byref(d)), 'gnx_set_draws')
 

@@ -145,6 +145,8 @@ typedef struct {
   const double* sex_u;              /* A11 [n] */
   const double* sex_redraw_u;       /* A12 [n] */
   const double* death_u;            /* A16 [n] */
+  const double* pan_u;              /* A3 panmixia [n]: individual i opens a mating slot iff u < b */
+  const uint32_t* pan_R;            /* A3 panmixia [n][2]: the slot's two parents, (R * N) >> 32 */
 } gnx_draws_t;
 
 /* Host-side SoA view of a population (upload / download). Any pointer may be NULL. */

@@ -24,6 +24,8 @@ def make_draws(rng, prm, n, cap, n_paths, max_tries=8):
     d['sex_u'] = rng.random(cap)
     d['sex_redraw_u'] = rng.random(cap)
     d['death_u'] = rng.random(n + cap)
+    d['pan_u'] = rng.random(n)
+    d['pan_R'] = rng.integers(0, 1 << 32, (n, 2), dtype=np.uint64).astype(np.uint32)
     return d
 
 

@@ -272,6 +272,23 @@ def find_mates_radius(x, y, land_dim, radius, b, mate_R, mate_u, sex=None,
     return pairs, n_nbrs, mate
 
 
+def find_mates_panmixia_draws(n, b, pan_u, pan_R, sex=None):
+    """species.py:2178-2194 with the draw convention shared with the CUDA path: individual i
+    opens a mating slot iff pan_u[i] < b (the number of slots is then Binomial(N, b), as
+    np.random.binomial(n=len(self), p=self.b) draws it); the slot's parents are
+    a = (pan_R[i,0]*N) >> 32, b = (pan_R[i,1]*N) >> 32 (np.random.choice with replacement);
+    selfing pairs are dropped (species.py:2192-2193); with sexes column 0 must be female and
+    column 1 male (mating.py:41-55).  Pairs are listed in slot order."""
+    pan_R = np.asarray(pan_R, dtype=np.uint64).reshape(-1, 2)[:n]
+    a = ((pan_R[:, 0] * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+    c = ((pan_R[:, 1] * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+    active = np.ones(n, bool) if b >= 1 else (np.asarray(pan_u)[:n] < b)
+    ok = active & (a != c)
+    if sex is not None:
+        ok &= (sex[a] == 0) & (sex[c] == 1)
+    return np.stack([a[ok], c[ok]], axis=1)
+
+
 def find_mates_panmixia(n_mates_draw_idx):
     """species.py:2178-2194 (mating_radius=None): 2*n_mates ordinals drawn with
     replacement, folded to (n_mates, 2), selfing pairs dropped; no de-dup
@@ -770,11 +787,17 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
     im['mv_e'] = sample_env(rasters, x, y)
     # a5/a6
     sexed = bool(prm['sex'])
-    pairs, n_nbrs, mate = find_mates_radius(
-        x, y, land_dim, prm['mating_radius'], prm['b'], draws['mate_R'], draws['mate_u'],
-        sex=state['sex'] if sexed else None,
-        choose_nearest=prm.get('choose_nearest', False),
-        inverse_dist=prm.get('inverse_dist', False), inv_u=draws.get('mate_inv_u'))
+    if prm['mating_radius'] is None:
+        pairs = find_mates_panmixia_draws(n0, prm['b'], draws['pan_u'], draws['pan_R'],
+                                          state['sex'] if sexed else None)
+        n_nbrs = np.full(n0, n0 - 1, dtype=np.int32)
+        mate = None
+    else:
+        pairs, n_nbrs, mate = find_mates_radius(
+            x, y, land_dim, prm['mating_radius'], prm['b'], draws['mate_R'], draws['mate_u'],
+            sex=state['sex'] if sexed else None,
+            choose_nearest=prm.get('choose_nearest', False),
+            inverse_dist=prm.get('inverse_dist', False), inv_u=draws.get('mate_inv_u'))
     im['pairs'], im['n_nbrs'], im['mate'] = pairs, n_nbrs, mate
     # a7
     im['n_pairs_rast'] = n_pairs_raster(dgs, x, y, pairs, land_dim)

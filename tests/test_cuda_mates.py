@@ -94,3 +94,20 @@ def test_empty_and_single():
             assert dev.population_size() <= n
         finally:
             dev.close()
+
+
+@pytest.mark.parametrize('sexed,b', [(False, 0.3), (True, 0.8), (False, 1.0)])
+def test_panmixia_full_step(sexed, b):
+    """mating_radius = None (species.py:2178-2194): Wright-Fisher style random pairing."""
+    from oracle import step_oracle as so
+    from parity_util import synthetic_case, run_device_step, compare_step
+    arch, prm, state, draws = synthetic_case(L=64, n=1500, loci_per_trait=8, seed=31, max_tries=24)
+    prm = dict(prm, mating_radius=None, b=b, sex=sexed)
+    new_o, im_o = so.step(state, arch, prm, draws)
+    expected = 1500 * b * (0.25 if sexed else 1.0)
+    assert abs(len(im_o['pairs']) - expected) < 5 * np.sqrt(expected)
+    assert np.all(im_o['pairs'][:, 0] != im_o['pairs'][:, 1])
+    if sexed:
+        assert np.all(state['sex'][im_o['pairs'][:, 0]] == 0) and np.all(state['sex'][im_o['pairs'][:, 1]] == 1)
+    out = run_device_step(arch, prm, state, draws, staged=True)
+    compare_step(out, new_o, im_o)
