@@ -155,6 +155,7 @@ SIGNATURES = {
     'gnx_sync': (C.c_int, [_ctx]),
     'gnx_walk_host': (C.c_int, [_ctx, C.POINTER(Population), C.c_int32]),
     'gnx_read_step_records': (C.c_int, [_ctx, C.POINTER(StepRecord), C.c_int32, c_int32_p]),
+    'gnx_stats_genotypes': (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
     'gnx_read_field': (C.c_int, [_ctx, C.c_int32, C.c_void_p, C.c_int64]),
     'gnx_device_ptr': (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     'gnx_stream': (C.c_void_p, [_ctx]),

@@ -751,6 +751,23 @@ class Species:
             return None
         return dens
 
+    # ---- statistics on the device (sim/stats.py:399-435) ---------------------------------
+    def _calc_het(self, mean=False):
+        """stats.py:399-410: locus-wise (or mean) frequency of heterozygotes."""
+        het = self._dev.stats()['het']
+        return float(np.mean(het)) if mean else het
+
+    def _calc_maf(self):
+        """stats.py:412-425."""
+        return self._dev.stats()['maf']
+
+    def _calc_allele_freqs(self):
+        return self._dev.stats()['freq']
+
+    def _calc_mean_fitness(self):
+        """stats.py:428-435: mean of the fitness values of the last completed step."""
+        return self._dev.stats()['mean_fit'] if self.gen_arch.traits is not None else np.nan
+
     # ---- post burn-in genome assignment (species.py:956-1094, genome.py:1108-1157) ----
     def _set_genomes_and_tables(self, burn_T=None, T=None):
         s = self._dev.download(genomes=False)

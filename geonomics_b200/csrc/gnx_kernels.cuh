@@ -1432,6 +1432,53 @@ __global__ void __launch_bounds__(256) k_z_to_rows(Pop pop, const Counters* c, d
     for (int tt = 0; tt < pop.T; ++tt) z_rows[(size_t)i * pop.T + tt] = pop.z[cur][(size_t)tt * pop.cap + i];
 }
 
+// ========================================================================================
+// f2 on-device stats (sim/stats.py:399-435): per-locus 1-allele counts and heterozygote
+// counts straight from the bit-packed genotypes, and the fitness sum.  A warp takes 32
+// individuals; for every 32-bit word column, one ballot per bit turns the 32 lanes' words
+// into a per-locus count (vertical popcount), accumulated in shared memory per CTA.
+// ========================================================================================
+__global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters* c, unsigned long long* c1,
+                                                          unsigned long long* chet, double* fit_sum) {
+  extern __shared__ unsigned int st_smem[];       // [2][Wwords * 32]
+  const int n = c->n, cur = c->cur, Ww = 4 * pop.Wq, nbits = Ww * 32;
+  for (int k = threadIdx.x; k < 2 * nbits; k += blockDim.x) st_smem[k] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nwarps = GSTRIDE / 32;
+  double fsum = 0.0;
+  for (int base = (GTID / 32) * 32; base < n; base += nwarps * 32) {
+    const int i = base + lane;
+    const bool live = i < n;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(pop.G + (size_t)(live ? pop.gslot[cur][i] : 0) * 2 * pop.Wq);
+    if (live) fsum += pop.fit[cur][i];
+    for (int wd = 0; wd < Ww; ++wd) {
+      const uint32_t h0 = live ? row[wd] : 0u, h1 = live ? row[Ww + wd] : 0u;
+      const uint32_t both = h0 & h1, x = h0 ^ h1;
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b) {
+        const unsigned mx = __ballot_sync(0xffffffffu, (x >> b) & 1u);
+        const unsigned mb = __ballot_sync(0xffffffffu, (both >> b) & 1u);
+        if (lane == b) {          // lane b owns bit b of this word column
+          const int nhet = __popc(mx), nhom = __popc(mb);
+          if (nhet | nhom) {
+            atomicAdd(&st_smem[wd * 32 + b], (unsigned)(nhet + 2 * nhom));
+            atomicAdd(&st_smem[nbits + wd * 32 + b], (unsigned)nhet);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+  if (lane == 0 && fsum != 0.0) atomicAdd(fit_sum, fsum);
+  __syncthreads();
+  for (int k = threadIdx.x; k < nbits; k += blockDim.x) {
+    if (st_smem[k]) atomicAdd(&c1[k], (unsigned long long)st_smem[k]);
+    if (st_smem[nbits + k]) atomicAdd(&chet[k], (unsigned long long)st_smem[nbits + k]);
+  }
+}
+
 __global__ void k_K_from_layer(const double* rast, double* K, double factor, int ncell) {
   for (int id = GTID; id < ncell; id += GSTRIDE) K[id] = rast[id] * factor;   // species.py:546-547
 }

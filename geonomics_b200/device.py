@@ -330,6 +330,21 @@ class DeviceSpecies:
         return [dict(t=r.t, Nt=r.Nt, n_births=r.n_births, n_deaths=r.n_deaths, n_pairs=r.n_pairs)
                 for r in arr[:n.value]]
 
+    def stats(self):
+        """Per-locus statistics computed on the device from the packed genotypes
+        (sim/stats.py:399-435): dict(N, freq, het, maf, mean_fit)."""
+        c1 = np.zeros(max(1, self.Lg), dtype=np.uint64)
+        het = np.zeros(max(1, self.Lg), dtype=np.uint64)
+        fs = C.c_double()
+        n = C.c_int64()
+        _lib.check(self._L.gnx_stats_genotypes(self._ctx, c1.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               het.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(fs),
+                                               C.byref(n)), 'gnx_stats_genotypes')
+        N = int(n.value)
+        freq = c1[:self.Lg] / float(2 * N) if N else np.zeros(self.Lg)
+        return dict(N=N, freq=freq, het=het[:self.Lg] / float(N) if N else np.zeros(self.Lg),
+                    maf=np.minimum(freq, 1 - freq), mean_fit=float(fs.value) / N if N else float('nan'))
+
     def counters(self):
         c = self.read('COUNTERS', 24)
         names = ['n', 'n_pre', 'P', 'B', 'deaths', 'n_free', 'n_slots', 'cur']

@@ -232,6 +232,12 @@ int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps);
 /* Drain the per-step records accumulated since the last call (synchronises). */
 int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out);
 
+/* ---- on-device statistics (sim/stats.py:399-435 _calc_het / _calc_maf / _calc_mean_fitness;
+ *      SURVEY.md section 8f rank 2): per-locus 1-allele counts and heterozygote counts by
+ *      vertical popcount over the packed genotypes, and the sum of fitness.  Synchronises. */
+int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1 /* [L] */, uint64_t* host_het /* [L] */,
+                        double* fit_sum, int64_t* n);
+
 /* ---- introspection (parity tests, lazy API views) -------------------------------------- */
 enum {
   GNX_F_X = 1, GNX_F_Y, GNX_F_AGE, GNX_F_SEX, GNX_F_IDX, GNX_F_Z, GNX_F_FIT, GNX_F_GSLOT,

@@ -91,6 +91,12 @@ CASES = {
                  move=('wald', 0.6, 1.0), disp=('wald', 0.6, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=[0.1], gamma=[1], seed=13,
                  surfaces=True, main_steps=3),
+    # a burn-in step: no genomes, no selection (species.py:825-830, 624, 666-672)
+    'burn': dict(dim=(30, 30), N=700, K_factor=1.0, L=20, n_traits=1, trait_loci=[4],
+                 mating_radius=2, b=0.5, sex=False, n_births_fixed=True, lam=1,
+                 move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                 dom=False, max_age=None, phi=[0.1], gamma=[1], seed=14,
+                 surfaces=False, main_steps=0, burn_case=6),
 }
 
 
@@ -171,10 +177,14 @@ def capture_state(spp):
         y=np.array([i.y for i in inds], dtype=np.float64),
         age=np.array([i.age for i in inds], dtype=np.int32),
         sex=np.array([i.sex for i in inds], dtype=np.int8),
-        g=np.stack([np.int8(i.g) for i in inds]) if len(inds) else np.zeros((0, 0, 2), np.int8),
     )
-    if spp.gen_arch.traits is not None:
+    nt = len(spp.gen_arch.traits) if spp.gen_arch.traits is not None else 0
+    if len(inds) and all(i.g is not None for i in inds):
+        st['g'] = np.stack([np.int8(i.g) for i in inds])
         st['z'] = np.array([i.z for i in inds], dtype=np.float64).reshape(len(inds), -1)
+    else:       # burn-in: individuals carry no genomes yet (species.py:666-672)
+        st['g'] = np.zeros((len(inds), spp.gen_arch.L, 2), np.int8)
+        st['z'] = np.zeros((len(inds), nt))
     st['fit'] = np.array([np.nan if i.fit is None else i.fit for i in inds], dtype=np.float64)
     return st
 
@@ -423,8 +433,11 @@ def record_case(gnx, case, out_dir=HERE):
         _b.SpatialTester.run_test = lambda self, n, alpha=0.05: True
     with contextlib.redirect_stdout(io.StringIO()):
         mod = gnx.make_model(p, name='golden_' + case)
-        mod.walk(10000, 'burn', verbose=False)
-        mod.walk(c['main_steps'], 'main', verbose=False)
+        if c.get('burn_case'):
+            mod.walk(c['burn_case'], 'burn', verbose=False)      # stop inside the burn-in
+        else:
+            mod.walk(10000, 'burn', verbose=False)
+            mod.walk(c['main_steps'], 'main', verbose=False)
     spp = mod.comm[0]
     land = mod.land
     print(case, 'N =', len(spp), 'L =', spp.gen_arch.L, 'burn_t =', mod.burn_t)
@@ -504,7 +517,8 @@ def record_case(gnx, case, out_dir=HERE):
             rec[k] = rp.rec[k]
     rec['ref_pairs_ids'] = holder['ref_pairs_ids']
     rec['pairs'] = holder['pairs']
-    rec['nb'] = rp.rec.get('nb', np.zeros(0, np.int64))
+    rec['nb'] = rp.rec.get('nb', np.full(len(holder['pairs']), int(c['lam']), dtype=np.int64))
+    rec['prm_burn'] = np.float64(1.0 if c.get('burn_case') else 0.0)
     B = int(rec['nb'].sum())
     rec['B'] = np.int64(B)
     rec['mid_x'] = np.array(rp.rec.get('mid_x', []), dtype=np.float64)
@@ -516,8 +530,9 @@ def record_case(gnx, case, out_dir=HERE):
     rec['dNdt_rast'] = rp.rec['_calc_dNdt']
     rec['d_rast'] = rp.rec['_calc_d']
     rec['death_p'] = rp.rec['death_p']
-    rec['fit_all'] = rp.rec['fit']           # fitness of the N0+B individuals alive before mortality
-    rec['d_ind'] = rp.rec['d_ind']
+    if 'fit' in rp.rec:                      # absent in a burn-in step (no selection)
+        rec['fit_all'] = rp.rec['fit']       # fitness of the N0+B individuals alive before mortality
+        rec['d_ind'] = rp.rec['d_ind']
     st2 = capture_state(spp)
     for k, v in st2.items():
         rec['out_' + k] = v

@@ -32,7 +32,8 @@ def load_case(name):
                sex_ratio_p=float(z['prm_sex_ratio_p']),
                max_age=None if z['prm_max_age'] < 0 else int(z['prm_max_age']),
                direction_mu=float(z['prm_direction_distr_mu']),
-               direction_kappa=float(z['prm_direction_distr_kappa']))
+               direction_kappa=float(z['prm_direction_distr_kappa']),
+               burn=bool(z['prm_burn']) if 'prm_burn' in z.files else False)
     if prm['lam'] == int(prm['lam']):
         prm['lam'] = int(prm['lam'])
     state = dict(x=z['in_x'], y=z['in_y'], age=z['in_age'], sex=z['in_sex'], idx=z['in_idx'],

@@ -39,8 +39,15 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
                       disp_tries=draws['disp_dist'].shape[1])
     try:
         dev.set_debug(True)
-        dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'], g=state['g'],
-                   z=state['z'], max_ind_idx=state['max_ind_idx'])
+        burn = bool(prm.get('burn', False))
+        if burn:
+            dev.set_burn(True)
+            dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'],
+                       max_ind_idx=state['max_ind_idx'])
+        else:
+            dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'], g=state['g'],
+                       z=state['z'], max_ind_idx=state['max_ind_idx'])
+        out_burn = burn
         d = dict(draws)
         if arch.get('move_surf') is None:
             d.pop('move_choice', None)
@@ -90,8 +97,9 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
         else:
             dev.step(1)
         dev.sync()
-        out['new'] = dev.download(e=True)
+        out['new'] = dev.download(e=True, genomes=not out_burn)
         out['new']['e'] = out['new']['e'][:, :-1]
+        out['burn'] = out_burn
         out['records'] = dev.step_records()
         out['counters'] = dev.counters()
         out['launches'] = dev.launch_count
@@ -121,21 +129,24 @@ def compare_step(out, new_o, im_o, rtol=1e-6, exact_xy_tol=1e-9):
         assert np.array_equal(out['pre']['age'], pre_o['age'])
         np.testing.assert_allclose(out['pre']['x'], pre_o['x'], rtol=0, atol=exact_xy_tol)
         np.testing.assert_allclose(out['pre']['y'], pre_o['y'], rtol=0, atol=exact_xy_tol)
-        np.testing.assert_allclose(out['pre']['z'], pre_o['z'], rtol=1e-12, atol=1e-15)
+        if not out.get('burn'):
+            np.testing.assert_allclose(out['pre']['z'], pre_o['z'], rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(out['N_rast'], im_o['N_rast'], rtol=rtol, atol=1e-9)
         np.testing.assert_allclose(out['n_pairs_rast'], im_o['n_pairs_rast'], rtol=rtol, atol=1e-9)
         np.testing.assert_allclose(out['d_rast'], im_o['d_rast'], rtol=rtol, atol=1e-9)
-        np.testing.assert_allclose(out['fit_all'], im_o['fit_all'], rtol=rtol)
+        if not out.get('burn'):
+            np.testing.assert_allclose(out['fit_all'], im_o['fit_all'], rtol=rtol)
         np.testing.assert_allclose(out['death_p'], im_o['death_p'], rtol=rtol, atol=1e-9)
     new = out['new']
     assert np.array_equal(new['idx'], new_o['idx'])
     assert np.array_equal(new['age'], new_o['age'])
     assert np.array_equal(new['sex'], new_o['sex'])
-    assert np.array_equal(new['g'], new_o['g'])
     np.testing.assert_allclose(new['x'], new_o['x'], rtol=0, atol=exact_xy_tol)
     np.testing.assert_allclose(new['y'], new_o['y'], rtol=0, atol=exact_xy_tol)
-    np.testing.assert_allclose(new['z'], new_o['z'], rtol=1e-12, atol=1e-15)
-    np.testing.assert_allclose(new['fit'], new_o['fit'], rtol=rtol)
+    if not out.get('burn'):
+        assert np.array_equal(new['g'], new_o['g'])
+        np.testing.assert_allclose(new['z'], new_o['z'], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(new['fit'], new_o['fit'], rtol=rtol)
     assert np.array_equal(new['e'], new_o['e'])
     assert new['max_ind_idx'] == new_o['max_ind_idx']
     rec = out['records'][-1]

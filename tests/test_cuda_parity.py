@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def stepped(request):
     from oracle import step_oracle as so
     z, arch, prm, state, draws = load_case(request.param)
-    new_o, im_o = so.step(state, arch, prm, draws)
+    new_o, im_o = so.step(state, arch, prm, draws, burn=prm.get('burn', False))
     out = run_device_step(arch, prm, state, draws, staged=True)
     return request.param, z, out, new_o, im_o
 
@@ -34,6 +34,13 @@ def test_staged_step_matches_reference_vectors(stepped):
     assert np.array_equal(out['pre']['sex'], z['pre_sex'])
     new = out['new']
     assert np.array_equal(new['idx'], z['out_idx'])
+    if out.get('burn'):
+        assert np.array_equal(new['sex'], z['out_sex']) and np.array_equal(new['age'], z['out_age'])
+        np.testing.assert_allclose(new['x'], z['out_x'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(out['d_rast'], z['d_rast'], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(out['death_p'], z['death_p'], rtol=1e-6, atol=1e-9)
+        assert out['records'][-1]['n_deaths'] == int(z['out_n_deaths'])
+        return
     assert np.array_equal(new['g'], z['out_g'])
     assert np.array_equal(new['sex'], z['out_sex'])
     assert np.array_equal(new['age'], z['out_age'])
@@ -68,6 +75,6 @@ def test_density_counts_exact(stepped):
 def test_fused_step_equals_staged(name):
     from oracle import step_oracle as so
     z, arch, prm, state, draws = load_case(name)
-    new_o, im_o = so.step(state, arch, prm, draws)
+    new_o, im_o = so.step(state, arch, prm, draws, burn=prm.get('burn', False))
     out = run_device_step(arch, prm, state, draws, staged=False)
     compare_step(out, new_o, im_o)

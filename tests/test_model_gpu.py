@@ -79,3 +79,20 @@ def test_seeded_models_are_reproducible():
     assert outs[0][0] == outs[1][0]
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_on_device_stats_match_numpy(model):
+    """sim/stats.py:399-435 formulas on the downloaded genotypes vs the device reductions."""
+    mod = model
+    spp = mod.comm[0]
+    g = mod.get_genotypes()                       # [N, L, 2]
+    N = g.shape[0]
+    het_ref = np.sum(np.mean(g, axis=2) == 0.5, axis=0) / N
+    f1 = np.sum(np.sum(g, axis=2), axis=0) / (2 * N)
+    maf_ref = np.where(f1 > 0.5, 1 - f1, f1)
+    np.testing.assert_allclose(spp._calc_het(), het_ref, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(spp._calc_maf(), maf_ref, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(spp._calc_allele_freqs(), f1, rtol=0, atol=1e-15)
+    assert abs(spp._calc_het(mean=True) - het_ref.mean()) < 1e-15
+    fit = mod.get_fitness()
+    assert abs(spp._calc_mean_fitness() - fit.mean()) < 1e-12
