@@ -113,6 +113,19 @@ class StepRecord(C.Structure):
                 ('n_deaths', C.c_int64), ('n_pairs', C.c_int64)]
 
 
+class TskitRows(C.Structure):
+    _fields_ = [
+        ('n_edges', C.c_int64), ('n_births', C.c_int64),
+        ('edge_left', c_double_p), ('edge_right', c_double_p), ('edge_parent', c_int32_p), ('edge_child', c_int32_p),
+        ('birth_idx', c_int64_p),
+        ('birth_x', c_double_p), ('birth_y', c_double_p),
+        ('birth_z', c_double_p),
+        ('birth_time', c_double_p),
+        ('first_node_id', C.c_int32),
+        ('first_individual_row', C.c_int32),
+    ]
+
+
 FIELDS = dict(
     X=1, Y=2, AGE=3, SEX=4, IDX=5, Z=6, FIT=7, GSLOT=8, N_NBRS=9, MATE=10, PAIRS=11, NB=12,
     PERM=13, CELL_START=14, COUNTS_N=15, COUNTS_P=16, VALS_N=17, VALS_P=18, GRAD_N=19, GRAD_P=20,
@@ -155,6 +168,10 @@ SIGNATURES = {
     'gnx_sync': (C.c_int, [_ctx]),
     'gnx_walk_host': (C.c_int, [_ctx, C.POINTER(Population), C.c_int32]),
     'gnx_read_step_records': (C.c_int, [_ctx, C.POINTER(StepRecord), C.c_int32, c_int32_p]),
+    'gnx_tskit_enable': (C.c_int, [_ctx, C.c_int64, C.c_int64]),
+    'gnx_tskit_set_nodes': (C.c_int, [_ctx, c_int32_p, c_int32_p, C.c_int64, C.c_int32, C.c_int32]),
+    'gnx_tskit_drain': (C.c_int, [_ctx, C.POINTER(TskitRows)]),
+    'gnx_tskit_renumber': (C.c_int, [_ctx]),
     'gnx_stats_genotypes': (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
     'gnx_read_field': (C.c_int, [_ctx, C.c_int32, C.c_void_p, C.c_int64]),
     'gnx_device_ptr': (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),

@@ -53,6 +53,9 @@ struct gnx_ctx {
   Work work{};
   Params prm{};
   DevDraws draws{};
+  Tsk tsk{};
+  std::vector<uint32_t> host_paths;   // packed recombination paths (breakpoint CSR for tskit records)
+  std::vector<void*> tsk_allocs;
   Counters* d_c = nullptr;
   std::vector<void*> allocs;        // everything cudaMalloc'ed for the ctx lifetime
   std::vector<void*> draw_allocs;   // injected-draw buffers
@@ -247,6 +250,7 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   free_bucket(ctx->draw_allocs);
   free_bucket(ctx->trait_allocs);
   free_bucket(ctx->dens_allocs);
+  free_bucket(ctx->tsk_allocs);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GNX_OK;
@@ -370,6 +374,7 @@ extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_pa
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prm.paths = d;
   ctx->have_paths = true;
+  ctx->host_paths.assign(host_packed_paths, host_packed_paths + n * 4);
   return GNX_OK;
 }
 
@@ -886,10 +891,16 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
     }
   }
   PROF(ctx, "k_newborns");
-  k_newborns<<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
+  k_newborns<<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c, ctx->tsk);
   LAUNCHED(ctx);
+  if (ctx->tsk.enabled && !ctx->burn) {
+    TskitScan ts{ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->tsk, ctx->d_c,
+                 ctx->cfg.n_births_fixed ? (int)ctx->cfg.n_births_lambda : 0};
+    int r = run_scan(ctx, ts, "scan_tskit_edges");
+    if (r != GNX_OK) return r;
+  }
   PROF(ctx, "k_after_births");
-  k_after_births<<<1, 1, 0, s>>>(ctx->d_c);
+  k_after_births<<<1, 1, 0, s>>>(ctx->d_c, (ctx->tsk.enabled && !ctx->burn) ? 1 : 0);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -1201,4 +1212,123 @@ extern "C" int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1, uint64_t* ho
   memcpy(fit_sum, &h[2 * nbits], 8);
   *n = hc.n;
   return check_device_err(hc);
+}
+
+
+// ---- tskit record buffering (species.py:692-736, genome.py:234-281) --
+// Node / edge / individual rows of every birth are written to device buffers by the step
+// kernels and handed to the host (tskit's TableCollection.append_columns) at the simplify
+// interval (model.py:756-768).
+extern "C" int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t birth_capacity) {
+  ARG(ctx && edge_capacity > 0 && birth_capacity > 0, "capacities");
+  ARG(edge_capacity < (1ll << 31) && birth_capacity < (1ll << 31), "capacities");
+  if (!ctx->have_paths) { g_last_error = "recombination paths not set"; return GNX_ERR_STATE; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_bucket(ctx->tsk_allocs);
+  Tsk& T = ctx->tsk;
+  memset(&T, 0, sizeof T);
+  // breakpoints of every cached path: loci where the path switches homologue (genome.py:194-199)
+  const int L = ctx->cfg.L, W = ctx->Wwords, np = ctx->cfg.n_recomb_paths;
+  std::vector<int32_t> ptr(np + 1, 0), pos;
+  for (int k = 0; k < np; ++k) {
+    const uint32_t* row = &ctx->host_paths[(size_t)k * W];
+    int prev = 0;                                   // rate[0] == 0: every path starts on homologue 0
+    for (int l = 0; l < L; ++l) {
+      const int b = (row[l >> 5] >> (l & 31)) & 1;
+      if (b != prev) pos.push_back(l);
+      prev = b;
+    }
+    ptr[k + 1] = (int32_t)pos.size();
+  }
+  int r;
+  if ((r = upload_vec(ctx, ptr, &T.bp_ptr, ctx->tsk_allocs)) != GNX_OK) return r;
+  if ((r = upload_vec(ctx, pos, &T.bp_pos, ctx->tsk_allocs)) != GNX_OK) return r;
+  T.L = (double)L;
+  T.edge_cap = (int32_t)edge_capacity;
+  T.born_cap = (int32_t)birth_capacity;
+  DM(ctx, &T.e_left, edge_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.e_right, edge_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.e_parent, edge_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.e_child, edge_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.b_idx, birth_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.b_x, birth_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.b_y, birth_capacity, &ctx->tsk_allocs);
+  DM(ctx, &T.b_z, birth_capacity * std::max(1, ctx->cfg.n_traits), &ctx->tsk_allocs);
+  DM(ctx, &T.b_time, birth_capacity, &ctx->tsk_allocs);
+  const int64_t cap = ctx->cfg.capacity;
+  for (int h = 0; h < 2; ++h)
+    for (int b = 0; b < 2; ++b) DM(ctx, &ctx->pop.node[h][b], cap, &ctx->tsk_allocs);
+  T.enabled = 1;
+  // node ids 2k, 2k+1 in species order (species.py:1148-1152); time origin = now
+  PROF(ctx, "k_tskit_renumber");
+  k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, 1);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+// after TableCollection.simplify(): nodes become 2k, 2k+1 in species order and the
+// individuals table holds exactly the live individuals (species.py:1140-1164)
+extern "C" int gnx_tskit_renumber(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
+  PROF(ctx, "k_tskit_renumber");
+  k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, 0);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+// explicit node ids (e.g. the msprime-seeded start, species.py:1060-1063), species order
+extern "C" int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, const int32_t* host_node1, int64_t n,
+                                   int32_t next_node_id, int32_t next_individual_row) {
+  ARG(ctx && host_node0 && host_node1, "null");
+  if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  ARG(n == h.n, "n differs from the population size");
+  CK(cudaMemcpyAsync(ctx->pop.node[0][h.cur], host_node0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pop.node[1][h.cur], host_node1, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  h.n_nodes = next_node_id;
+  h.n_ind_rows = next_individual_row;
+  CK(cudaMemcpyAsync(ctx->d_c, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+// Copies the rows buffered since the last drain into host column arrays and empties the
+// buffers.  Pass NULL arrays (with rows->n_* = 0) to query the counts first.
+extern "C" int gnx_tskit_drain(gnx_ctx* ctx, gnx_tskit_rows_t* rows) {
+  ARG(ctx && rows, "null");
+  if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  if ((r = check_device_err(h)) != GNX_OK) return r;
+  const bool query = rows->edge_left == nullptr && rows->birth_idx == nullptr;
+  if (!query) {
+    ARG(rows->n_edges >= h.n_edges && rows->n_births >= h.n_born, "host buffers too small");
+    Tsk& T = ctx->tsk;
+    cudaStream_t s = ctx->stream;
+    const size_t ne = (size_t)h.n_edges, nb = (size_t)h.n_born;
+    CK(cudaMemcpyAsync(rows->edge_left, T.e_left, ne * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->edge_right, T.e_right, ne * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->edge_parent, T.e_parent, ne * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->edge_child, T.e_child, ne * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->birth_idx, T.b_idx, nb * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->birth_x, T.b_x, nb * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->birth_y, T.b_y, nb * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rows->birth_time, T.b_time, nb * 8, cudaMemcpyDeviceToHost, s));
+    for (int t = 0; t < ctx->cfg.n_traits; ++t)
+      CK(cudaMemcpyAsync(rows->birth_z + (size_t)t * nb, T.b_z + (size_t)t * T.born_cap, nb * 8,
+                         cudaMemcpyDeviceToHost, s));
+    rows->first_node_id = h.n_nodes - 2 * h.n_born;
+    rows->first_individual_row = h.n_ind_rows - h.n_born;
+    const int32_t zero2[2] = {0, 0};
+    CK(cudaMemcpyAsync(&ctx->d_c->n_edges, zero2, 8, cudaMemcpyHostToDevice, s));   // n_edges, n_born
+    CK(cudaStreamSynchronize(s));
+  }
+  rows->n_edges = h.n_edges;
+  rows->n_births = h.n_born;
+  return GNX_OK;
 }

@@ -29,6 +29,12 @@ struct Counters {
   int32_t gs_iters[2];
   unsigned long long nmax_bits;   // bits of max(N raster) (N >= 0 so unsigned order works)
   int32_t pad[2];
+  // tskit record buffering (a18)
+  int32_t n_nodes;      // next row id of the tskit nodes table
+  int32_t n_ind_rows;   // next row id of the tskit individuals table
+  int32_t n_edges;      // edge rows buffered since the last drain
+  int32_t n_born;       // newborn (individual + 2 node) rows buffered since the last drain
+  int64_t tsk_t0;       // Counters.t when recording was enabled (node time = -(t - tsk_t0))
 };
 #define GNX_ERRBIT_CAPACITY 1
 #define GNX_ERRBIT_DRAWS 2
@@ -44,6 +50,7 @@ struct Pop {
   int32_t* gslot[2];
   double* z[2];        // [T][cap]
   double* fit[2];
+  int32_t* node[2][2]; // [homologue][buffer][cap] tskit node ids (NULL unless recording)
   uint4* G;            // [cap][2][Wq]
   int32_t* free_slots; // [cap]
   int32_t cap;
@@ -138,6 +145,24 @@ struct Work {
   int32_t* fix_count;
   gnx_step_record_t* records;
   int32_t max_records;
+};
+
+// tskit record buffers (species.py:692-736): rows accumulated on the device between drains
+struct Tsk {
+  int32_t enabled;
+  const int32_t* bp_ptr;   // [n_paths + 1] CSR of recombination breakpoints per cached path
+  const int32_t* bp_pos;   // locus index of each breakpoint (segment edge = pos - 0.5, genome.py:248-249)
+  double L;                // sequence length
+  int32_t edge_cap, born_cap;
+  double* e_left;
+  double* e_right;
+  int32_t* e_parent;
+  int32_t* e_child;
+  int64_t* b_idx;          // individuals-table metadata (gnx individual idx)
+  double* b_x;
+  double* b_y;
+  double* b_z;             // [T][born_cap]
+  double* b_time;          // nodes-table time = -t
 };
 
 struct DevDraws {

@@ -761,8 +761,9 @@ __global__ void __launch_bounds__(GT_THREADS) k_gametes_tma(Pop pop, Params prm,
 
 // ----- k_newborns: natal dispersal, sex, newborn record (one thread per offspring) -------
 __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
-                                                   Counters* c) {
+                                                   Counters* c, Tsk tsk) {
   const int n = c->n, B = c->B, cur = c->cur;
+  const int n_nodes = c->n_nodes, n_born = c->n_born;
   const int64_t t = c->t, max_idx = c->max_idx;
   for (int o = GTID; o < B; o += GSTRIDE) {
     const int p = w.off_pair[o];
@@ -824,11 +825,101 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
     pop.sex[cur][dst] = (int8_t)sex;
     pop.idx[cur][dst] = oid;
     if (prm.burn) pop.gslot[cur][dst] = -1;
+    if (tsk.enabled) {
+      // species.py:692-736: one individuals row (location = [x, y, z...], metadata = idx) and
+      // two nodes rows (flags=1, time=-t, population=0) per offspring, in offspring order
+      pop.node[0][cur][dst] = n_nodes + 2 * o;
+      pop.node[1][cur][dst] = n_nodes + 2 * o + 1;
+      const int k = n_born + o;
+      if (k < tsk.born_cap) {
+        tsk.b_idx[k] = oid;
+        tsk.b_x[k] = ox;
+        tsk.b_y[k] = oy;
+        tsk.b_time[k] = -(double)(t - c->tsk_t0);
+        for (int tt = 0; tt < pop.T; ++tt)
+          tsk.b_z[(size_t)tt * tsk.born_cap + k] = pop.z[cur][(size_t)tt * pop.cap + dst];
+      } else {
+        atomicOr((int*)&c->err, GNX_ERRBIT_CAPACITY);
+      }
+    }
   }
 }
 
-__global__ void k_after_births(Counters* c) {
+// edges of every offspring (species.py:723-729 + Recombinations._get_seg_info
+// genome.py:257-281): for homologue h inherited from parent pair[h] through cached path k_h
+// started on homologue s_h, segment i spans [bp[i-1]-0.5, bp[i]-0.5) (0 and L at the ends)
+// and descends from the parent's node (i + s_h) % 2.
+struct TskitScan {
+  Pop pop;
+  Params prm;
+  DevDraws dr;
+  Work w;
+  Tsk tsk;
+  const Counters* cc;
+  int32_t fixed_nb;
+  __device__ int size(const Counters* c) const { return c->B; }
+  __device__ void keys(int o, int* p, int* k0, int* k1, int* h0, int* h1) const {
+    // must mirror k_gametes' plan exactly (same keys and start homologues)
+    *p = fixed_nb > 0 ? o / fixed_nb : w.off_pair[o];
+    RngStream gg(prm.seed_lo, prm.seed_hi, cc->max_idx + 1 + o, SITE_GAMETE, cc->t);
+    if (dr.recomb_keys) {
+      const int j = o - w.off_start[*p];
+      const int e = 2 * (w.off_start[*p] + w.nb[*p]);
+      *k0 = dr.recomb_keys[e - 1 - 2 * j];
+      *k1 = dr.recomb_keys[e - 2 - 2 * j];
+    } else {
+      *k0 = (int)choose_k(gg.u32(), prm.n_paths);
+      *k1 = (int)choose_k(gg.u32(), prm.n_paths);
+    }
+    if (dr.start_homs) {
+      *h0 = dr.start_homs[2 * o];
+      *h1 = dr.start_homs[2 * o + 1];
+    } else {
+      const uint32_t bits = gg.u32();
+      *h0 = bits & 1;
+      *h1 = (bits >> 1) & 1;
+    }
+  }
+  __device__ u64 value(int o) const {
+    int p, k0, k1, h0, h1;
+    keys(o, &p, &k0, &k1, &h0, &h1);
+    return (u64)((tsk.bp_ptr[k0 + 1] - tsk.bp_ptr[k0] + 1) + (tsk.bp_ptr[k1 + 1] - tsk.bp_ptr[k1] + 1));
+  }
+  __device__ void apply(int o, u64, u64 ex) const {
+    int p, k[2], h[2];
+    keys(o, &p, &k[0], &k[1], &h[0], &h[1]);
+    const int cur = cc->cur;
+    long long e = (long long)cc->n_edges + (long long)ex;
+    for (int hom = 0; hom < 2; ++hom) {
+      const int par = w.pairs[2 * p + hom];
+      const int pn[2] = {pop.node[0][cur][par], pop.node[1][cur][par]};
+      const int child = cc->n_nodes + 2 * o + hom;
+      const int s = tsk.bp_ptr[k[hom]], nbp = tsk.bp_ptr[k[hom] + 1] - s;
+      for (int i = 0; i <= nbp; ++i, ++e) {
+        if (e >= tsk.edge_cap) continue;
+        tsk.e_left[e] = i == 0 ? 0.0 : (double)tsk.bp_pos[s + i - 1] - 0.5;
+        tsk.e_right[e] = i == nbp ? tsk.L : (double)tsk.bp_pos[s + i] - 0.5;
+        tsk.e_parent[e] = pn[(i + h[hom]) & 1];
+        tsk.e_child[e] = child;
+      }
+    }
+  }
+  __device__ void total(Counters* c, u64 tot) const {
+    // stash the step's edge count; k_after_births folds it into n_edges once apply has run
+    c->pad[1] = (int)tot;
+    if ((long long)c->n_edges + (long long)tot > tsk.edge_cap) c->err |= GNX_ERRBIT_CAPACITY;
+  }
+};
+
+__global__ void k_after_births(Counters* c, int tsk_enabled) {
   const int B = c->B;
+  if (tsk_enabled) {
+    c->n_nodes += 2 * B;
+    c->n_ind_rows += B;
+    c->n_born += B;
+    c->n_edges += c->pad[1];
+    c->pad[1] = 0;
+  }
   c->n_pre = c->n + B;
   const int nf = c->n_free;
   if (B <= nf) c->n_free = nf - B;
@@ -1348,6 +1439,10 @@ struct MortalityScan {
       pop.fit[d][dst] = pop.fit[s][i];
       for (int tt = 0; tt < pop.T; ++tt)
         pop.z[d][(size_t)tt * pop.cap + dst] = pop.z[s][(size_t)tt * pop.cap + i];
+      if (pop.node[0][0]) {
+        pop.node[0][d][dst] = pop.node[0][s][i];
+        pop.node[1][d][dst] = pop.node[1][s][i];
+      }
     } else if (!burn) {
       // n_free was already lowered by this step's births (k_after_births)
       pop.free_slots[cc->n_free + (int)(ex & 0xffffffffu)] = pop.gslot[s][i];
@@ -1417,12 +1512,17 @@ __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int
   for (int i = GTID; i < n; i += GSTRIDE) {
     pop.gslot[0][i] = i;
     if (make_ids) pop.idx[0][i] = i;
+    if (pop.node[0][0]) {             // post-simplify convention, species.py:1148-1152
+      pop.node[0][0][i] = 2 * i;
+      pop.node[1][0][i] = 2 * i + 1;
+    }
     if (z_rows)
       for (int tt = 0; tt < pop.T; ++tt) pop.z[0][(size_t)tt * pop.cap + i] = z_rows[(size_t)i * pop.T + tt];
   }
   if (GTID == 0) {
     c->n = n; c->n_pre = n; c->P = 0; c->B = 0; c->deaths = 0; c->n_free = 0; c->n_slots = n; c->cur = 0;
     c->max_idx = max_idx; c->err = 0; c->nmax_bits = 0ull;
+    c->n_nodes = 2 * n; c->n_ind_rows = n; c->n_edges = 0; c->n_born = 0;
   }
 }
 
@@ -1476,6 +1576,21 @@ __global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters
   for (int k = threadIdx.x; k < nbits; k += blockDim.x) {
     if (st_smem[k]) atomicAdd(&c1[k], (unsigned long long)st_smem[k]);
     if (st_smem[nbits + k]) atomicAdd(&chet[k], (unsigned long long)st_smem[nbits + k]);
+  }
+}
+
+// node ids 2k, 2k+1 in species order (after simplify, species.py:1148-1152); reset_t0 marks
+// the current step as tskit time 0
+__global__ void __launch_bounds__(256) k_tskit_renumber(Pop pop, Counters* c, int reset_t0) {
+  const int n = c->n, cur = c->cur;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    pop.node[0][cur][i] = 2 * i;
+    pop.node[1][cur][i] = 2 * i + 1;
+  }
+  if (GTID == 0) {
+    c->n_nodes = 2 * n;
+    c->n_ind_rows = n;
+    if (reset_t0) { c->tsk_t0 = c->t; c->n_edges = 0; c->n_born = 0; }
   }
 }
 

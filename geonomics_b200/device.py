@@ -330,6 +330,44 @@ class DeviceSpecies:
         return [dict(t=r.t, Nt=r.Nt, n_births=r.n_births, n_deaths=r.n_deaths, n_pairs=r.n_pairs)
                 for r in arr[:n.value]]
 
+    # ---- tskit record buffering (species.py:692-736) ---------------------------------------
+    def tskit_enable(self, edge_capacity, birth_capacity):
+        _lib.check(self._L.gnx_tskit_enable(self._ctx, int(edge_capacity), int(birth_capacity)), 'gnx_tskit_enable')
+
+    def tskit_set_nodes(self, node0, node1, next_node_id, next_individual_row):
+        a = np.ascontiguousarray(node0, dtype=np.int32)
+        b = np.ascontiguousarray(node1, dtype=np.int32)
+        _lib.check(self._L.gnx_tskit_set_nodes(self._ctx, _ptr(a, _lib.c_int32_p), _ptr(b, _lib.c_int32_p), len(a),
+                                               int(next_node_id), int(next_individual_row)), 'gnx_tskit_set_nodes')
+
+    def tskit_renumber(self):
+        _lib.check(self._L.gnx_tskit_renumber(self._ctx), 'gnx_tskit_renumber')
+
+    def tskit_drain(self):
+        """Rows buffered since the last drain, as numpy columns ready for
+        tskit.TableCollection.{edges,nodes,individuals}.append_columns."""
+        q = _lib.TskitRows()
+        _lib.check(self._L.gnx_tskit_drain(self._ctx, C.byref(q)), 'gnx_tskit_drain')
+        ne, nb, T = int(q.n_edges), int(q.n_births), self.n_traits
+        out = dict(left=np.empty(ne), right=np.empty(ne), parent=np.empty(ne, np.int32), child=np.empty(ne, np.int32),
+                   idx=np.empty(nb, np.int64), x=np.empty(nb), y=np.empty(nb), z=np.empty((max(1, T), nb)),
+                   time=np.empty(nb))
+        r = _lib.TskitRows()
+        r.n_edges, r.n_births = ne, nb
+        r.edge_left, r.edge_right = _ptr(out['left'], _lib.c_double_p), _ptr(out['right'], _lib.c_double_p)
+        r.edge_parent, r.edge_child = _ptr(out['parent'], _lib.c_int32_p), _ptr(out['child'], _lib.c_int32_p)
+        r.birth_idx = _ptr(out['idx'], _lib.c_int64_p)
+        r.birth_x, r.birth_y = _ptr(out['x'], _lib.c_double_p), _ptr(out['y'], _lib.c_double_p)
+        r.birth_z, r.birth_time = _ptr(out['z'], _lib.c_double_p), _ptr(out['time'], _lib.c_double_p)
+        _lib.check(self._L.gnx_tskit_drain(self._ctx, C.byref(r)), 'gnx_tskit_drain')
+        out['z'] = out['z'][:T].T.copy()
+        out['first_node_id'] = int(r.first_node_id)
+        out['first_individual_row'] = int(r.first_individual_row)
+        # nodes table columns of birth k: ids first_node_id + 2k (+1), flags 1, population 0
+        out['node_time'] = np.repeat(out['time'], 2)
+        out['node_individual'] = np.repeat(out['first_individual_row'] + np.arange(nb), 2)
+        return out
+
     def stats(self):
         """Per-locus statistics computed on the device from the packed genotypes
         (sim/stats.py:399-435): dict(N, freq, het, maf, mean_fit)."""

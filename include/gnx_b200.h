@@ -232,6 +232,30 @@ int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps);
 /* Drain the per-step records accumulated since the last call (synchronises). */
 int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out);
 
+/* ---- tskit record buffering -----------------------------------
+ * Replaces the per-offspring TableCollection.add_row calls of Species._do_mating
+ * (species.py:692-736) and Recombinations._get_seg_info (genome.py:257-281): for every birth
+ * the step kernels append, to device buffers, one individuals row (location = [x, y, z...],
+ * metadata = idx), two nodes rows (flags = 1, time = -t, population = 0) and one edges row
+ * per recombination segment and homologue.  The host drains them into tskit with
+ * TableCollection.{individuals,nodes,edges}.append_columns at its existing simplify
+ * interval (model.py:756-768), then calls gnx_tskit_renumber (species.py:1148-1152). */
+typedef struct {
+  int64_t n_edges, n_births;        /* in: capacity of the arrays below; out: rows written */
+  double* edge_left; double* edge_right; int32_t* edge_parent; int32_t* edge_child;
+  int64_t* birth_idx;               /* individuals.metadata (4 LE bytes of idx in the reference) */
+  double* birth_x; double* birth_y; /* individuals.location[0:2] */
+  double* birth_z;                  /* [n_traits][n_births] individuals.location[2:] */
+  double* birth_time;               /* nodes.time of the two nodes of birth k */
+  int32_t first_node_id;            /* nodes rows of birth k: first_node_id + 2k, + 2k + 1 */
+  int32_t first_individual_row;     /* individuals row of birth k: first_individual_row + k */
+} gnx_tskit_rows_t;
+int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t birth_capacity);
+int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, const int32_t* host_node1, int64_t n,
+                        int32_t next_node_id, int32_t next_individual_row);
+int gnx_tskit_drain(gnx_ctx* ctx, gnx_tskit_rows_t* rows);   /* NULL arrays: query the counts only */
+int gnx_tskit_renumber(gnx_ctx* ctx);
+
 /* ---- on-device statistics (sim/stats.py:399-435 _calc_het / _calc_maf / _calc_mean_fitness;
  *      SURVEY.md section 8f rank 2): per-locus 1-allele counts and heterozygote counts by
  *      vertical popcount over the packed genotypes, and the sum of fitness.  Synchronises. */

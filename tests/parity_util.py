@@ -155,7 +155,7 @@ def compare_step(out, new_o, im_o, rtol=1e-6, exact_xy_tol=1e-9):
     assert rec['n_deaths'] == im_o['n_deaths']
 
 
-def synthetic_case(L=1000, n=1500, n_traits=2, loci_per_trait=20, dim=(40, 40), seed=0, max_tries=8):
+def synthetic_case(L=1000, n=1500, n_traits=2, loci_per_trait=20, dim=(40, 40), seed=0, max_tries=8, cap=None):
     """A synthetic population in the golden-case format (arch, prm, state, draws), for parity
     of the CUDA path against the (golden-pinned) oracle at genome sizes the reference-recorded
     cases do not cover."""
@@ -177,6 +177,6 @@ def synthetic_case(L=1000, n=1500, n_traits=2, loci_per_trait=20, dim=(40, 40), 
     state = dict(x=w['pop']['x'], y=w['pop']['y'], age=w['pop']['age'], sex=w['pop']['sex'],
                  idx=w['pop']['idx'], g=g, z=z, max_ind_idx=n - 1)
     rng = np.random.default_rng(seed + 5)
-    draws = od.make_draws(rng, dict(prm, move_distr=('wald', 1.0, 1.0), disp_distr=('wald', 1.0, 1.0)), n, n,
-                          len(arch['paths']), max_tries=max_tries)
+    draws = od.make_draws(rng, dict(prm, move_distr=('wald', 1.0, 1.0), disp_distr=('wald', 1.0, 1.0)), n,
+                          cap or n, len(arch['paths']), max_tries=max_tries)
     return arch, prm, state, draws
