@@ -316,6 +316,9 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   const int Wq = ctx->Wq;
   std::vector<int32_t> te_locus;
   std::vector<double> te_alpha, te_dom;
+  struct TraitEntry { int32_t off, sh; double half_alpha; };      // Traits::te_pack
+  static_assert(sizeof(TraitEntry) == 16, "TraitEntry is one 128-bit load");
+  std::vector<TraitEntry> te_pack;
   const int NW = 4 * Wq;      // CSR over 32-bit words
   std::vector<int32_t> chunk_ptr((size_t)std::max(1, n_traits) * (NW + 1), 0);
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
@@ -336,6 +339,7 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
       te_locus.push_back(locus);
       te_alpha.push_back(tr.host_alpha[k]);
       te_dom.push_back(host_dom ? 1.0 + (double)host_dom[locus] : 1.0);
+      te_pack.push_back(TraitEntry{(locus >> 5) * 8, locus & 31, 0.5 * tr.host_alpha[k]});
     }
     while (q < NW) chunk_ptr[(size_t)t * (NW + 1) + (++q)] = (int32_t)te_locus.size();
     T.n_loci[t] = tr.n_loci;
@@ -360,6 +364,9 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
     T.te_dom = nullptr;
   }
   if ((r = upload_vec(ctx, chunk_ptr, &T.chunk_ptr, ctx->trait_allocs)) != GNX_OK) return r;
+  const TraitEntry* d_pack = nullptr;
+  if ((r = upload_vec(ctx, te_pack, &d_pack, ctx->trait_allocs)) != GNX_OK) return r;
+  T.te_pack = d_pack;
   ctx->have_traits = true;
   return pack_env(ctx);
 }
@@ -852,11 +859,16 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   if (!ctx->burn) {
 #define MO(GW)                                                                                            \
   do {                                                                                                    \
+    /* child rows staged in shared memory for the phenotype when they fit (32 KB per block) */           \
+    const size_t rows_b = (size_t)(256 / GW) * 2 * Wq * 16;                                               \
+    const int stage = (GW > 1 && ctx->cfg.n_traits > 0 && rows_b <= 32 * 1024) ? 1 : 0;                             \
     if (ctx->cfg.n_traits <= 2)                                                                           \
-      k_gametes<GW, 2><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c, fnb); \
+      k_gametes<GW, 2><<<g, 256, stage ? rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,   \
+                                                          ctx->work, ctx->d_c, fnb, stage);               \
     else                                                                                                  \
-      k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,       \
-                                                      ctx->work, ctx->d_c, fnb);                          \
+      k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, stage ? rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits,  \
+                                                                       ctx->draws, ctx->work, ctx->d_c,   \
+                                                                       fnb, stage);                       \
   } while (0)
     const int fnb = ctx->cfg.n_births_fixed ? (int)ctx->cfg.n_births_lambda : 0;
     if (Wq >= 4 && Wq <= 32 && !ctx->no_tma) {

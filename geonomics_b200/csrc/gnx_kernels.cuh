@@ -511,18 +511,31 @@ struct BirthPlan {
 
 template <int GW, int NT>
 __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
-                                                  const Counters* c, int fixed_nb) {
+                                                  const Counters* c, int fixed_nb, int stage_rows) {
+  // stage_rows: the child's row is also kept in shared memory (2*Wq uint4 per group) and the
+  // phenotype is accumulated over the trait table with the entries dealt round-robin to the
+  // group's lanes -- balanced, where the per-unit walk leaves most lanes idle.
+  extern __shared__ uint4 g_rows[];
   const int n = c->n, B = c->B, cur = c->cur, n_free = c->n_free, n_slots = c->n_slots;
   const int64_t t = c->t, max_idx = c->max_idx;
   const int Wq = pop.Wq, T = pop.T;
   const int lane = threadIdx.x & (GW - 1);
-  const int ngroups = GSTRIDE / GW;
-  const int lane0 = (threadIdx.x & 31) & ~(GW - 1);
+  // the staged row interleaves the homologues word by word ([h0 word w, h1 word w] adjacent),
+  // so one 64-bit shared load serves both alleles of a locus
+  uint32_t* const row32 = reinterpret_cast<uint32_t*>(g_rows + (size_t)(threadIdx.x / GW) * 2 * Wq);
+  const bool fast_trait = !tr.te_dom;
+  const int wl = threadIdx.x & 31;
+  const int lane0 = wl & ~(GW - 1);
+  constexpr int G = 32 / GW;              // offspring groups per warp
+  const int grp = wl / GW;
   const unsigned gmask = GW == 32 ? 0xffffffffu : (((1u << GW) - 1u) << lane0);
-  // lane 0 of each group resolves offspring o -> (parents' slots, child slot, keys, starts)
+  // A warp takes chunks of 32 consecutive offspring.  Every lane first resolves ONE offspring
+  // of the chunk: offspring -> (parents' genome slots, child slot, recombination keys, start
+  // homologues), coalesced and with no idle lanes; the GW iterations that stream the rows then
+  // fetch their plan by shuffle.  The next chunk's plans are prefetched under the row stream.
   auto load_plan = [&](int o) -> BirthPlan {
     BirthPlan bp = {0, 0, 0, 0, 0};
-    if (lane == 0 && o < B) {
+    if (o < B) {
       const int p = fixed_nb > 0 ? o / fixed_nb : w.off_pair[o];
       const int2 sl = reinterpret_cast<const int2*>(w.pair_slots)[p];
       bp.s0 = sl.x;
@@ -553,19 +566,24 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
     }
     return bp;
   };
-  int o = GTID / GW;
-  BirthPlan next = load_plan(o);
-  for (; o < B; o += ngroups) {
-    BirthPlan bp = next;
-    next = load_plan(o + ngroups);           // prefetch: overlaps the next index chain with this row stream
-    if (GW > 1) {
-      bp.s0 = __shfl_sync(gmask, bp.s0, lane0);
-      bp.s1 = __shfl_sync(gmask, bp.s1, lane0);
-      bp.cslot = __shfl_sync(gmask, bp.cslot, lane0);
-      bp.kk0 = __shfl_sync(gmask, bp.kk0, lane0);
-      bp.kk1 = __shfl_sync(gmask, bp.kk1, lane0);
-    }
-    if (lane == 0) pop.gslot[cur][n + o] = bp.cslot;
+  const int nwarps = GSTRIDE >> 5, nchunks = (B + 31) >> 5;
+  int ch = GTID >> 5;
+  BirthPlan next = load_plan(ch * 32 + wl);
+  for (; ch < nchunks; ch += nwarps) {
+    const BirthPlan mine = next;
+    next = load_plan((ch + nwarps) * 32 + wl);
+    if (ch * 32 + wl < B) pop.gslot[cur][n + ch * 32 + wl] = mine.cslot;
+#pragma unroll 1
+  for (int j = 0; j < GW; ++j) {
+    const int src = j * G + grp;
+    const int o = ch * 32 + src;
+    BirthPlan bp;
+    bp.s0 = __shfl_sync(0xffffffffu, mine.s0, src);
+    bp.s1 = __shfl_sync(0xffffffffu, mine.s1, src);
+    bp.cslot = __shfl_sync(0xffffffffu, mine.cslot, src);
+    bp.kk0 = __shfl_sync(0xffffffffu, mine.kk0, src);
+    bp.kk1 = __shfl_sync(0xffffffffu, mine.kk1, src);
+    if (o >= B) continue;                    // uniform over the group
     const uint4* P0 = pop.G + (size_t)bp.s0 * 2 * Wq;
     const uint4* P1 = pop.G + (size_t)bp.s1 * 2 * Wq;
     const uint4* M0 = prm.paths + (size_t)(bp.kk0 & 0x3fffffff) * Wq;
@@ -585,9 +603,50 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
       const uint4 g0 = bitsel(a0, a1, m0), g1 = bitsel(b0, b1, m1);
       st_stream(C + q, g0);
       st_stream(C + Wq + q, g1);
+      if (stage_rows) {
+        reinterpret_cast<uint4*>(row32)[2 * q] = make_uint4(g0.x, g1.x, g0.y, g1.y);
+        reinterpret_cast<uint4*>(row32)[2 * q + 1] = make_uint4(g0.z, g1.z, g0.w, g1.w);
+      } else {
 #pragma unroll
-      for (int tt = 0; tt < NT; ++tt)
-        if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
+        for (int tt = 0; tt < NT; ++tt)
+          if (tt < T) zacc[tt] += trait_partial(tr, tt, q, Wq, g0, g1);
+      }
+    }
+    if (stage_rows) {
+      __syncwarp(gmask);
+      const int NW = 4 * Wq;
+#pragma unroll
+      for (int tt = 0; tt < NT; ++tt) {
+        if (tt < T) {
+          const int ks = __ldg(&tr.chunk_ptr[tt * (NW + 1)]), ke = __ldg(&tr.chunk_ptr[tt * (NW + 1) + NW]);
+          const bool poly = tr.n_loci[tt] > 1;
+          double acc = 0.0;
+          if (fast_trait && poly) {
+            // geno * alpha = (b0 + b1) * (alpha / 2), exact (selection.py:30-33, 43-44)
+            const int4* __restrict__ tp = reinterpret_cast<const int4*>(tr.te_pack);
+            for (int k = ks + lane; k < ke; k += GW) {
+              const int4 e = __ldg(tp + k);                 // {byte offset of the word pair, shift, alpha/2}
+              const uint2 ww = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(row32) + e.x);
+              const double ha = __hiloint2double(e.w, e.z);
+              double v = 0.0;
+              if ((ww.x >> e.y) & 1u) v = ha;
+              if ((ww.y >> e.y) & 1u) v += ha;
+              acc += v;
+            }
+          } else {
+            for (int k = ks + lane; k < ke; k += GW) {
+              const int loc = __ldg(&tr.te_locus[k]);
+              const int wi = 2 * (loc >> 5), sh = loc & 31;
+              const int dosage = (int)((row32[wi] >> sh) & 1u) + (int)((row32[wi + 1] >> sh) & 1u);
+              double geno = 0.5 * (double)dosage;                                 // selection.py:30-33
+              if (!fast_trait) geno = fmin(geno * __ldg(&tr.te_dom[k]), 1.0);     // selection.py:35-39
+              acc += poly ? geno * __ldg(&tr.te_alpha[k]) : geno;                 // selection.py:43-47
+            }
+          }
+          zacc[tt] = acc;
+        }
+      }
+      __syncwarp(gmask);      // the row is rewritten by the next offspring
     }
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt) {
@@ -598,6 +657,7 @@ __global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr,
         if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
       }
     }
+  }
   }
 }
 

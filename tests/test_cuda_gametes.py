@@ -43,4 +43,4 @@ def test_tma_and_register_kernels_agree(L):
     assert len(a['x']) == len(b['x']) > 1000
     assert np.array_equal(a['idx'], b['idx'])
     assert np.array_equal(a['genomes'], b['genomes'])
-    assert np.array_equal(a['z'], b['z'])
+    assert np.allclose(a['z'], b['z'], rtol=1e-12, atol=1e-14)      # summation order differs
