@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libgnxb200.so')
+# GNX_B200_LIB selects another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get('GNX_B200_LIB') or os.path.join(HERE, 'libgnxb200.so')
 HEADER_PATH = os.path.join(os.path.dirname(HERE), 'include', 'gnx_b200.h')
 
 GNX_ABI_VERSION = 1

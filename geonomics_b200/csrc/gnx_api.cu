@@ -62,6 +62,7 @@ struct gnx_ctx {
   std::vector<void*> trait_allocs;
   std::vector<void*> dens_allocs;
   double* d_rasters = nullptr;
+  float* d_surf_f32[2] = {nullptr, nullptr};
   double* d_K = nullptr;
   uint4* d_stage_genomes = nullptr;   // species-order staging for upload/download
   double* d_stage_z = nullptr;        // [n][T] row-major staging of phenotypes
@@ -186,6 +187,19 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &ctx->d_rasters, plane * cfg->n_layers);
   DM(ctx, &ctx->d_K, plane);
   Ld.rasters = ctx->d_rasters;
+  {
+    const int mode[2] = {cfg->move ? cfg->move_surf_mode : GNX_SURF_NONE, cfg->disp_surf_mode};
+    const int lyr[2] = {cfg->move_surf_layer, cfg->disp_surf_layer};
+    for (int k = 0; k < 2; ++k) {
+      if (mode[k] != GNX_SURF_ONTHEFLY) continue;
+      if (k == 1 && mode[0] == GNX_SURF_ONTHEFLY && lyr[0] == lyr[1]) {
+        ctx->d_surf_f32[1] = ctx->d_surf_f32[0];
+      } else {
+        DM(ctx, &ctx->d_surf_f32[k], plane);
+      }
+      Ld.surf_f32[k] = ctx->d_surf_f32[k];
+    }
+  }
   Ld.K = ctx->d_K;
   // work
   Work& W = ctx->work;
@@ -264,6 +278,20 @@ static int pack_env(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+// refresh the float32 conductance copies after `layer` (or every layer, -1) changed
+static int refresh_surf_f32(gnx_ctx* ctx, int layer) {
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  const int lyr[2] = {ctx->cfg.move_surf_layer, ctx->cfg.disp_surf_layer};
+  for (int k = 0; k < 2; ++k) {
+    if (!ctx->d_surf_f32[k] || (layer >= 0 && layer != lyr[k])) continue;
+    if (k == 1 && ctx->d_surf_f32[1] == ctx->d_surf_f32[0]) continue;
+    PROF(ctx, "k_raster_to_f32");
+    k_raster_to_f32<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->d_rasters + plane * lyr[k], ctx->d_surf_f32[k], plane);
+    LAUNCHED(ctx);
+  }
+  return GNX_OK;
+}
+
 static int set_K(gnx_ctx* ctx) {
   const int ncell = ctx->cfg.dim_x * ctx->cfg.dim_y;
   PROF(ctx, "k_K_from_layer");
@@ -281,6 +309,7 @@ extern "C" int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters) {
   ctx->have_rasters = true;
   int r = pack_env(ctx);
   if (r != GNX_OK) return r;
+  if ((r = refresh_surf_f32(ctx, -1)) != GNX_OK) return r;
   return set_K(ctx);
 }
 
@@ -291,6 +320,7 @@ extern "C" int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_ra
                      ctx->stream));
   int r = pack_env(ctx);
   if (r != GNX_OK) return r;
+  if ((r = refresh_surf_f32(ctx, layer)) != GNX_OK) return r;
   if (layer == ctx->cfg.K_layer) return set_K(ctx);      // model.py:651-652 (Species._set_K)
   return GNX_OK;
 }

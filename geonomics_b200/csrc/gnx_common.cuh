@@ -77,6 +77,8 @@ struct Traits {
 struct Land {
   const double* rasters;   // [n_layers][Y][X]
   const double* K;         // [Y][X]
+  const float* surf_f32[2]; // float32 copies of the movement / dispersal conductance layers
+                            // (on-the-fly surface mode only; half the footprint, L2-resident)
   int32_t X, Y, n_layers;
   double max_x, max_y;     // dim - 0.001 (movement.py:89-92)
   // mating grid

@@ -39,7 +39,7 @@ __device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa) {
   return (uniform_f32(g) < 0.5f) ? -res : res;
 }
 
-__device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const double* rast, int X, int Y,
+__device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const float* rast, int X, int Y,
                                                              int cx, int cy, int mixture, float kappa) {
   // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
   // dropped; queen directions in raster row-major order.
@@ -52,7 +52,7 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int i = cy + di[k], j = cx + dj[k];
-    const float v = (i >= 0 && i < Y && j >= 0 && j < X) ? (float)__ldg(&rast[(size_t)i * X + j]) : 0.0f;
+    const float v = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0f;
     nv[k] = v;
     sum += v;
     mx = fmaxf(mx, v);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
       } else if (prm.c.move_surf_mode == GNX_SURF_ONTHEFLY) {
         int cx = (int)x, cy = (int)y;
         const __half d = surface_direction_onthefly(
-            g, land.rasters + (size_t)prm.c.move_surf_layer * land.X * land.Y, land.X, land.Y, cx, cy,
+            g, land.surf_f32[0], land.X, land.Y, cx, cy,
             prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa);
         sincos_half_fast(d, &sn, &cs);
       } else if (dr.move_dir) {
@@ -373,27 +373,55 @@ struct PairScan {
     }
     return !(w.mate[m] == i && m < i);                 // mating.py:62-63 (canonical)
   }
-  __device__ u64 value(int i) const { return keep(i) ? ((u64)1 << 32) : 0; }
-  __device__ void apply(int i, u64 v, u64 ex) const {
-    if (!v) return;
-    const int p = (int)(ex >> 32);
+  // the reduce pass evaluates the predicate (a dependent random gather) once and leaves it in
+  // w.alive, which the mortality stage only rewrites later in the step
+  __device__ u64 value_first(int i) const {
+    const bool k = keep(i);
+    w.alive[i] = k ? 1 : 0;
+    return k ? ((u64)1 << 32) : 0;
+  }
+  __device__ u64 value(int i) const { return w.alive[i] ? ((u64)1 << 32) : 0; }
+  static constexpr bool BATCHED = true;
+  __device__ void apply_batch(const int* idx, const u64* v, const u64* ex, int n) const {
     const int cur = cc->cur;
-    const int slot = i;
-    const int m = panmixia ? w.perm[slot] : w.mate[slot];
-    i = panmixia ? w.mate[slot] : slot;
-    w.pairs[2 * p] = i;
-    w.pairs[2 * p + 1] = m;
-    w.mid_x[p] = (pop.x[cur][i] + pop.x[cur][m]) / 2;     // species.py:640-641
-    w.mid_y[p] = (pop.y[cur][i] + pop.y[cur][m]) / 2;
-    // parents' genome slots, so the gamete kernel's index chain is one load shorter
-    reinterpret_cast<int2*>(w.pair_slots)[p] = make_int2(pop.gslot[cur][i], pop.gslot[cur][m]);
-    if (fixed_nb > 0) {
-      w.nb[p] = fixed_nb;
-      w.off_start[p] = p * fixed_nb;
-      for (int j = 0; j < fixed_nb; ++j)
-        if ((long long)p * fixed_nb + j < pop.cap) w.off_pair[p * fixed_nb + j] = p;
+    bool on[SCAN_ITEMS];
+    int a[SCAN_ITEMS], m[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      on[k] = idx[k] < n && v[k] != 0;
+      if (on[k]) {
+        m[k] = panmixia ? w.perm[idx[k]] : w.mate[idx[k]];
+        a[k] = panmixia ? w.mate[idx[k]] : idx[k];
+      }
+    }
+    double xa[SCAN_ITEMS], xm[SCAN_ITEMS], ya[SCAN_ITEMS], ym[SCAN_ITEMS];
+    int sa[SCAN_ITEMS], sm[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      if (on[k]) {
+        xa[k] = pop.x[cur][a[k]]; xm[k] = pop.x[cur][m[k]];
+        ya[k] = pop.y[cur][a[k]]; ym[k] = pop.y[cur][m[k]];
+        sa[k] = pop.gslot[cur][a[k]]; sm[k] = pop.gslot[cur][m[k]];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      if (!on[k]) continue;
+      const int p = (int)(ex[k] >> 32);
+      reinterpret_cast<int2*>(w.pairs)[p] = make_int2(a[k], m[k]);
+      w.mid_x[p] = (xa[k] + xm[k]) / 2;     // species.py:640-641
+      w.mid_y[p] = (ya[k] + ym[k]) / 2;
+      // parents' genome slots, so the gamete kernel's index chain is one load shorter
+      reinterpret_cast<int2*>(w.pair_slots)[p] = make_int2(sa[k], sm[k]);
+      if (fixed_nb > 0) {
+        w.nb[p] = fixed_nb;
+        w.off_start[p] = p * fixed_nb;
+        for (int j = 0; j < fixed_nb; ++j)
+          if ((long long)p * fixed_nb + j < pop.cap) w.off_pair[p * fixed_nb + j] = p;
+      }
     }
   }
+  __device__ void apply(int, u64, u64) const {}
   __device__ void total(Counters* c, u64 tot) const {
     int P = (int)(tot >> 32);
     c->P = P;
@@ -509,8 +537,11 @@ struct BirthPlan {
   int s0, s1, cslot, kk0, kk1;     // parents' slots, child slot, key | start << 30
 };
 
+#ifndef GNX_GAM_MINB
+#define GNX_GAM_MINB 4          // 64 registers: 4 CTAs per SM measured fastest (3, 5, 6 are slower)
+#endif
 template <int GW, int NT>
-__global__ void __launch_bounds__(256) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
+__global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params prm, Traits tr, DevDraws dr, Work w,
                                                   const Counters* c, int fixed_nb, int stage_rows) {
   // stage_rows: the child's row is also kept in shared memory (2*Wq uint4 per group) and the
   // phenotype is accumulated over the trait table with the entries dealt round-robin to the
@@ -846,7 +877,7 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
         sincos_half(h, &sn, &cs);
       } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
         const __half d = surface_direction_onthefly(
-            g, land.rasters + (size_t)prm.c.disp_surf_layer * land.X * land.Y, land.X, land.Y, (int)mx,
+            g, land.surf_f32[1], land.X, land.Y, (int)mx,
             (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa);
         sincos_half_fast(d, &sn, &cs);
       } else if (dr.disp_dir) {
@@ -1486,28 +1517,75 @@ struct MortalityScan {
   int32_t burn;
   __device__ int size(const Counters* c) const { return c->n_pre; }
   __device__ u64 value(int i) const { return w.alive[i] ? ((u64)1 << 32) : (u64)1; }
-  __device__ void apply(int i, u64 v, u64 ex) const {
+  // all loads of the SCAN_ITEMS elements are issued before the first store: source and
+  // destination halves cannot be proven disjoint by the compiler, so interleaved copies
+  // would serialise on memory latency
+  static constexpr bool BATCHED = true;
+  __device__ void apply_batch(const int* i, const u64* v, const u64* ex, int n) const {
     const int s = cc->cur, d = s ^ 1;
-    if (v >> 32) {
-      const int dst = (int)(ex >> 32);
-      pop.x[d][dst] = pop.x[s][i];
-      pop.y[d][dst] = pop.y[s][i];
-      pop.age[d][dst] = pop.age[s][i];
-      pop.sex[d][dst] = pop.sex[s][i];
-      pop.idx[d][dst] = pop.idx[s][i];
-      pop.gslot[d][dst] = pop.gslot[s][i];
-      pop.fit[d][dst] = pop.fit[s][i];
-      for (int tt = 0; tt < pop.T; ++tt)
-        pop.z[d][(size_t)tt * pop.cap + dst] = pop.z[s][(size_t)tt * pop.cap + i];
-      if (pop.node[0][0]) {
-        pop.node[0][d][dst] = pop.node[0][s][i];
-        pop.node[1][d][dst] = pop.node[1][s][i];
+    bool live[SCAN_ITEMS], dead[SCAN_ITEMS];
+    int dst[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      live[k] = i[k] < n && (v[k] >> 32);
+      dead[k] = i[k] < n && !(v[k] >> 32);
+      dst[k] = (int)(ex[k] >> 32);
+    }
+    {
+      double x[SCAN_ITEMS], y[SCAN_ITEMS], fit[SCAN_ITEMS];
+      int64_t id[SCAN_ITEMS];
+      int32_t age[SCAN_ITEMS], gs[SCAN_ITEMS];
+      int8_t sx[SCAN_ITEMS];
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (live[k]) {
+          x[k] = pop.x[s][i[k]];
+          y[k] = pop.y[s][i[k]];
+          fit[k] = pop.fit[s][i[k]];
+          id[k] = pop.idx[s][i[k]];
+          age[k] = pop.age[s][i[k]];
+          sx[k] = pop.sex[s][i[k]];
+        }
+        if (live[k] || dead[k]) gs[k] = pop.gslot[s][i[k]];
       }
-    } else if (!burn) {
-      // n_free was already lowered by this step's births (k_after_births)
-      pop.free_slots[cc->n_free + (int)(ex & 0xffffffffu)] = pop.gslot[s][i];
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (live[k]) {
+          pop.x[d][dst[k]] = x[k];
+          pop.y[d][dst[k]] = y[k];
+          pop.fit[d][dst[k]] = fit[k];
+          pop.idx[d][dst[k]] = id[k];
+          pop.age[d][dst[k]] = age[k];
+          pop.sex[d][dst[k]] = sx[k];
+          pop.gslot[d][dst[k]] = gs[k];
+        } else if (dead[k] && !burn) {
+          // n_free was already lowered by this step's births (k_after_births)
+          pop.free_slots[cc->n_free + (int)(ex[k] & 0xffffffffu)] = gs[k];
+        }
+      }
+    }
+    for (int tt = 0; tt < pop.T; ++tt) {
+      const double* zs = pop.z[s] + (size_t)tt * pop.cap;
+      double* zd = pop.z[d] + (size_t)tt * pop.cap;
+      double z[SCAN_ITEMS];
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (live[k]) z[k] = zs[i[k]];
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (live[k]) zd[dst[k]] = z[k];
+    }
+    if (pop.node[0][0]) {
+      int32_t a[SCAN_ITEMS], b[SCAN_ITEMS];
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (live[k]) { a[k] = pop.node[0][s][i[k]]; b[k] = pop.node[1][s][i[k]]; }
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (live[k]) { pop.node[0][d][dst[k]] = a[k]; pop.node[1][d][dst[k]] = b[k]; }
     }
   }
+  __device__ void apply(int, u64, u64) const {}
   __device__ void total(Counters* c, u64 tot) const {
     // spine runs before apply: stash totals where apply does not read them
     c->deaths = (int)(tot & 0xffffffffu);
@@ -1558,6 +1636,10 @@ __global__ void __launch_bounds__(256) k_gather_genomes(Pop pop, uint4* out, con
 }
 
 // environment values of each trait's layer packed next to the d slot (setup / env change)
+__global__ void __launch_bounds__(256) k_raster_to_f32(const double* src, float* dst, size_t n) {
+  for (size_t id = GTID; id < n; id += GSTRIDE) dst[id] = (float)src[id];
+}
+
 __global__ void __launch_bounds__(256) k_pack_env(Land land, Traits tr, Work w, int T) {
   const size_t plane = (size_t)land.X * land.Y;
   for (size_t id = GTID; id < plane; id += GSTRIDE)

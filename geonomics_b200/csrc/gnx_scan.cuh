@@ -5,7 +5,14 @@
 //   u64  value(int i)                              packed (hi << 32 | lo) contribution
 //   void apply(int i, u64 value, u64 exclusive)    consume the exclusive prefix
 //   void total(Counters*, u64 total)               called once by the spine
+// Optional:
+//   u64  value_first(int i)                        used by the reduce pass instead of value()
+//                                                  (e.g. to cache an expensive predicate)
+//   static constexpr bool BATCHED = true; void apply_batch(const int* i, const u64* v,
+//        const u64* ex, int n)                     consume SCAN_ITEMS elements at once, so the
+//                                                  functor can issue all loads before any store
 #pragma once
+#include <type_traits>
 #include "gnx_common.cuh"
 
 #define SCAN_BLOCK 256
@@ -46,6 +53,21 @@ __device__ __forceinline__ u64 block_excl_scan(u64 v, u64* total) {
   return excl;
 }
 
+template <class F, class = void>
+struct scan_has_value_first : std::false_type {};
+template <class F>
+struct scan_has_value_first<F, std::void_t<decltype(std::declval<const F&>().value_first(0))>> : std::true_type {};
+template <class F, class = void>
+struct scan_is_batched : std::false_type {};
+template <class F>
+struct scan_is_batched<F, std::void_t<decltype(F::BATCHED)>> : std::true_type {};
+
+template <class F>
+__device__ __forceinline__ u64 scan_value_first(const F& f, int i) {
+  if constexpr (scan_has_value_first<F>::value) return f.value_first(i);
+  else return f.value(i);
+}
+
 template <class F>
 __global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Counters* c, u64* tile_sums) {
   const int n = f.size(c);
@@ -56,7 +78,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Coun
     u64 s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k)
-      if (base + k * SCAN_BLOCK < n) s += f.value(base + k * SCAN_BLOCK);
+      if (base + k * SCAN_BLOCK < n) s += scan_value_first(f, base + k * SCAN_BLOCK);
     u64 tot;
     block_excl_scan(s, &tot);
     if (threadIdx.x == 0) tile_sums[tile] = tot;
@@ -99,8 +121,15 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_apply_kernel(F f, const Count
     }
     // all prefixes first, then all payload moves: the loads of the SCAN_ITEMS elements
     // overlap instead of queueing behind the barriers of the next row's scan
+    if constexpr (scan_is_batched<F>::value) {
+      int idx[SCAN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-      if (base + k * SCAN_BLOCK < n) f.apply(base + k * SCAN_BLOCK, v[k], ex[k]);
+      for (int k = 0; k < SCAN_ITEMS; ++k) idx[k] = base + k * SCAN_BLOCK;
+      f.apply_batch(idx, v, ex, n);
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k * SCAN_BLOCK < n) f.apply(base + k * SCAN_BLOCK, v[k], ex[k]);
+    }
   }
 }
