@@ -161,8 +161,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   P.Wq = ctx->Wq;
   P.T = cfg->n_traits;
   for (int h = 0; h < 2; ++h) {
-    DM(ctx, &P.x[h], cap);
-    DM(ctx, &P.y[h], cap);
+    DM(ctx, &P.xy[h], cap);
     DM(ctx, &P.age[h], cap);
     DM(ctx, &P.sex[h], cap);
     DM(ctx, &P.idx[h], cap);
@@ -216,8 +215,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &W.nb, cap);
   DM(ctx, &W.off_start, cap);
   DM(ctx, &W.off_pair, cap);
-  DM(ctx, &W.mid_x, cap);
-  DM(ctx, &W.mid_y, cap);
+  DM(ctx, &W.mid, cap);
   DM(ctx, &W.alive, cap);
   DM(ctx, &W.death_p, cap);
   DM(ctx, &W.disp_tries, cap);
@@ -696,8 +694,9 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
   cudaStream_t s = ctx->stream;
   Pop& P = ctx->pop;
   // everything below is asynchronous on the ctx stream: no host-side staging loops
-  CK(cudaMemcpyAsync(P.x[0], pop->x, n * 8, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(P.y[0], pop->y, n * 8, cudaMemcpyHostToDevice, s));
+  // x | y staged as plain arrays in the idle half; k_upload_finish interleaves them
+  CK(cudaMemcpyAsync(reinterpret_cast<double*>(P.xy[1]), pop->x, n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(reinterpret_cast<double*>(P.xy[1]) + P.cap, pop->y, n * 8, cudaMemcpyHostToDevice, s));
   if (pop->age) CK(cudaMemcpyAsync(P.age[0], pop->age, n * 4, cudaMemcpyHostToDevice, s));
   else CK(cudaMemsetAsync(P.age[0], 0, n * 4, s));
   if (pop->sex) CK(cudaMemcpyAsync(P.sex[0], pop->sex, n, cudaMemcpyHostToDevice, s));
@@ -746,8 +745,14 @@ extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
   Pop& P = ctx->pop;
   pop->n = h.n;
   pop->max_ind_idx = h.max_idx;
-  if (pop->x) CK(cudaMemcpyAsync(pop->x, P.x[cur], n * 8, cudaMemcpyDeviceToHost, s));
-  if (pop->y) CK(cudaMemcpyAsync(pop->y, P.y[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->x || pop->y) {
+    PROF(ctx, "k_xy_split");
+    k_xy_split<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c);
+    LAUNCHED(ctx);
+    const double* sx = reinterpret_cast<const double*>(P.xy[cur ^ 1]);
+    if (pop->x) CK(cudaMemcpyAsync(pop->x, sx, n * 8, cudaMemcpyDeviceToHost, s));
+    if (pop->y) CK(cudaMemcpyAsync(pop->y, sx + P.cap, n * 8, cudaMemcpyDeviceToHost, s));
+  }
   if (pop->age) CK(cudaMemcpyAsync(pop->age, P.age[cur], n * 4, cudaMemcpyDeviceToHost, s));
   if (pop->sex) CK(cudaMemcpyAsync(pop->sex, P.sex[cur], n, cudaMemcpyDeviceToHost, s));
   if (pop->idx) CK(cudaMemcpyAsync(pop->idx, P.idx[cur], n * 8, cudaMemcpyDeviceToHost, s));
@@ -1109,8 +1114,14 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
   void* p = nullptr;
   size_t b = 0;
   switch (field) {
-    case GNX_F_X: p = P.x[cur]; b = n * 8; break;
-    case GNX_F_Y: p = P.y[cur]; b = n * 8; break;
+    case GNX_F_X:
+    case GNX_F_Y:
+      // plain arrays staged in the idle half (valid until the next step or upload)
+      k_xy_split<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(P, ctx->d_c);
+      CK(cudaGetLastError());
+      p = reinterpret_cast<double*>(P.xy[cur ^ 1]) + (field == GNX_F_Y ? cap : 0);
+      b = n * 8;
+      break;
     case GNX_F_AGE: p = P.age[cur]; b = n * 4; break;
     case GNX_F_SEX: p = P.sex[cur]; b = n; break;
     case GNX_F_IDX: p = P.idx[cur]; b = n * 8; break;

@@ -42,8 +42,8 @@ struct Counters {
 
 // Double-buffered scalar SoA in species order + slot-indexed genome rows.
 struct Pop {
-  double* x[2];
-  double* y[2];
+  double2* xy[2];      // (x, y) interleaved: always used together, and one 16-byte gather
+                       // costs one DRAM burst where two 8-byte gathers cost two
   int32_t* age[2];
   int8_t* sex[2];
   int64_t* idx[2];
@@ -132,8 +132,7 @@ struct Work {
   int32_t* nb;
   int32_t* off_start;
   int32_t* off_pair;
-  double* mid_x;
-  double* mid_y;
+  double2* mid;            // pair midpoints (x, y)
   uint8_t* alive;
   double* death_p;
   int32_t* disp_tries;

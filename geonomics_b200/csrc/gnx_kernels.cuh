@@ -95,11 +95,11 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
                                                        int do_bin) {
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
-  double* __restrict__ X = pop.x[cur];
-  double* __restrict__ Yc = pop.y[cur];
+  double2* __restrict__ XY = pop.xy[cur];
   for (int i = GTID; i < n; i += GSTRIDE) {
     if (do_age) pop.age[cur][i] += 1;
-    double x = X[i], y = Yc[i];
+    const double2 xy0 = XY[i];
+    double x = xy0.x, y = xy0.y;
     if (do_move) {
       RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MOVE, t);
       double cs, sn;
@@ -129,8 +129,7 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
       if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
       x = clampd(__dadd_rn(x, dx), 0.0, land.max_x);
       y = clampd(__dadd_rn(y, dy), 0.0, land.max_y);
-      X[i] = x;
-      Yc[i] = y;
+      XY[i] = make_double2(x, y);
     }
     if (do_bin) {
       int cx = (int)floor(x / land.cell_size), cy = (int)floor(y / land.cell_size);
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Co
   const int n = c->n, cur = c->cur;
   for (int p = GTID; p < n; p += GSTRIDE) {
     int i = w.perm[p];
-    w.sxy[p] = make_double2(pop.x[cur][i], pop.y[cur][i]);
+    w.sxy[p] = pop.xy[cur][i];
   }
 }
 
@@ -394,13 +393,13 @@ struct PairScan {
         a[k] = panmixia ? w.mate[idx[k]] : idx[k];
       }
     }
-    double xa[SCAN_ITEMS], xm[SCAN_ITEMS], ya[SCAN_ITEMS], ym[SCAN_ITEMS];
+    double2 pa[SCAN_ITEMS], pm[SCAN_ITEMS];
     int sa[SCAN_ITEMS], sm[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
       if (on[k]) {
-        xa[k] = pop.x[cur][a[k]]; xm[k] = pop.x[cur][m[k]];
-        ya[k] = pop.y[cur][a[k]]; ym[k] = pop.y[cur][m[k]];
+        pa[k] = pop.xy[cur][a[k]];
+        pm[k] = pop.xy[cur][m[k]];
         sa[k] = pop.gslot[cur][a[k]]; sm[k] = pop.gslot[cur][m[k]];
       }
     }
@@ -409,8 +408,7 @@ struct PairScan {
       if (!on[k]) continue;
       const int p = (int)(ex[k] >> 32);
       reinterpret_cast<int2*>(w.pairs)[p] = make_int2(a[k], m[k]);
-      w.mid_x[p] = (xa[k] + xm[k]) / 2;     // species.py:640-641
-      w.mid_y[p] = (ya[k] + ym[k]) / 2;
+      w.mid[p] = make_double2((pa[k].x + pm[k].x) / 2, (pa[k].y + pm[k].y) / 2);     // species.py:640-641
       // parents' genome slots, so the gamete kernel's index chain is one load shorter
       reinterpret_cast<int2*>(w.pair_slots)[p] = make_int2(sa[k], sm[k]);
       if (fixed_nb > 0) {
@@ -861,7 +859,8 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
     const int64_t oid = max_idx + 1 + o;
     const int dst = n + o;
     // ---- natal dispersal (movement.py:98-141)
-    const double mx = w.mid_x[p], my = w.mid_y[p];
+    const double2 mid = w.mid[p];
+    const double mx = mid.x, my = mid.y;
     RngStream g(prm.seed_lo, prm.seed_hi, oid, SITE_DISP, t);
     double ox = 0.0, oy = 0.0;
     int tries = 0;
@@ -910,8 +909,7 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
       double u = dr.sex_redraw_u ? dr.sex_redraw_u[o] : g.uniform();
       sex = u < 0.5;
     }
-    pop.x[cur][dst] = ox;
-    pop.y[cur][dst] = oy;
+    pop.xy[cur][dst] = make_double2(ox, oy);
     pop.age[cur][dst] = 0;
     pop.sex[cur][dst] = (int8_t)sex;
     pop.idx[cur][dst] = oid;
@@ -1045,8 +1043,7 @@ __global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const
 __global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const Counters* c, Dens d) {
   // blockIdx.y = 0: all individuals alive before mortality; 1: pair midpoints
   const int which = blockIdx.y;
-  const double* __restrict__ xs = which == 0 ? pop.x[c->cur] : w.mid_x;
-  const double* __restrict__ ys = which == 0 ? pop.y[c->cur] : w.mid_y;
+  const double2* __restrict__ pts = which == 0 ? pop.xy[c->cur] : w.mid;
   __shared__ int hist[DENS_SMEM_BINS];
   const bool use_smem = d.npts <= DENS_SMEM_BINS;
   if (use_smem)
@@ -1055,7 +1052,8 @@ __global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const C
   const int n = which == 0 ? c->n_pre : c->P;
   int* gcounts = d.counts + (size_t)which * d.npts;
   for (int i = GTID; i < n; i += GSTRIDE) {       // GTID / GSTRIDE use the x dimension only
-    const double x = xs[i], y = ys[i];
+    const double2 pt = pts[i];
+    const double x = pt.x, y = pt.y;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       double xc = floordiv_exact(x - d.g_xe[g] * d.ww / 2., d.ww) + d.g_xe[g];
@@ -1476,7 +1474,8 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
   const int64_t t = c->t;
   const size_t plane = (size_t)land.X * land.Y;
   for (int i = GTID; i < n; i += GSTRIDE) {
-    const double x = pop.x[cur][i], y = pop.y[cur][i];
+    const double2 xy = pop.xy[cur][i];
+    const double x = xy.x, y = xy.y;
     const int cx = (int)x, cy = (int)y;
     const size_t cell = (size_t)cy * land.X + cx;
     const double* __restrict__ ed = w.envd + cell * w.envd_stride;   // one sector: d and the traits' e
@@ -1532,15 +1531,15 @@ struct MortalityScan {
       dst[k] = (int)(ex[k] >> 32);
     }
     {
-      double x[SCAN_ITEMS], y[SCAN_ITEMS], fit[SCAN_ITEMS];
+      double2 xy[SCAN_ITEMS];
+      double fit[SCAN_ITEMS];
       int64_t id[SCAN_ITEMS];
       int32_t age[SCAN_ITEMS], gs[SCAN_ITEMS];
       int8_t sx[SCAN_ITEMS];
 #pragma unroll
       for (int k = 0; k < SCAN_ITEMS; ++k) {
         if (live[k]) {
-          x[k] = pop.x[s][i[k]];
-          y[k] = pop.y[s][i[k]];
+          xy[k] = pop.xy[s][i[k]];
           fit[k] = pop.fit[s][i[k]];
           id[k] = pop.idx[s][i[k]];
           age[k] = pop.age[s][i[k]];
@@ -1551,8 +1550,7 @@ struct MortalityScan {
 #pragma unroll
       for (int k = 0; k < SCAN_ITEMS; ++k) {
         if (live[k]) {
-          pop.x[d][dst[k]] = x[k];
-          pop.y[d][dst[k]] = y[k];
+          pop.xy[d][dst[k]] = xy[k];
           pop.fit[d][dst[k]] = fit[k];
           pop.idx[d][dst[k]] = id[k];
           pop.age[d][dst[k]] = age[k];
@@ -1620,7 +1618,8 @@ __global__ void __launch_bounds__(256) k_sample_env(Pop pop, Land land, Work w, 
   const int n = c->n, cur = c->cur;
   const size_t plane = (size_t)land.X * land.Y;
   for (int i = GTID; i < n; i += GSTRIDE) {
-    const size_t cell = (size_t)((int)pop.y[cur][i]) * land.X + (int)pop.x[cur][i];
+    const double2 xy = pop.xy[cur][i];
+    const size_t cell = (size_t)((int)xy.y) * land.X + (int)xy.x;
     for (int l = 0; l < land.n_layers; ++l) w.e_out[(size_t)i * land.n_layers + l] = land.rasters[l * plane + cell];
   }
 }
@@ -1651,7 +1650,11 @@ __global__ void __launch_bounds__(256) k_pack_env(Land land, Traits tr, Work w, 
 // (time-step counter and record cursor carry over)
 __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int n, long long max_idx, int make_ids,
                                                         const double* z_rows) {
+  // x and y arrive as two plain arrays staged in the other half: [0, n) and [cap, cap + n)
+  const double* sx = reinterpret_cast<const double*>(pop.xy[1]);
+  const double* sy = sx + pop.cap;
   for (int i = GTID; i < n; i += GSTRIDE) {
+    pop.xy[0][i] = make_double2(sx[i], sy[i]);
     pop.gslot[0][i] = i;
     if (make_ids) pop.idx[0][i] = i;
     if (pop.node[0][0]) {             // post-simplify convention, species.py:1148-1152
@@ -1665,6 +1668,19 @@ __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int
     c->n = n; c->n_pre = n; c->P = 0; c->B = 0; c->deaths = 0; c->n_free = 0; c->n_slots = n; c->cur = 0;
     c->max_idx = max_idx; c->err = 0; c->nmax_bits = 0ull;
     c->n_nodes = 2 * n; c->n_ind_rows = n; c->n_edges = 0; c->n_born = 0;
+  }
+}
+
+// de-interleave (x, y) of the current half into two plain arrays staged in the other half
+// ([0, n) and [cap, cap + n)), for the host-facing views
+__global__ void __launch_bounds__(256) k_xy_split(Pop pop, const Counters* c) {
+  const int n = max(c->n, c->n_pre), cur = c->cur;
+  double* sx = reinterpret_cast<double*>(pop.xy[cur ^ 1]);
+  double* sy = sx + pop.cap;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const double2 v = pop.xy[cur][i];
+    sx[i] = v.x;
+    sy[i] = v.y;
   }
 }
 
