@@ -95,6 +95,9 @@ class Draws(C.Structure):
         ('disp_dir', c_double_p), ('disp_choice', c_int32_p), ('disp_dist', c_double_p),
         ('sex_u', c_double_p), ('sex_redraw_u', c_double_p), ('death_u', c_double_p),
         ('pan_u', c_double_p), ('pan_R', c_uint32_p),
+        ('n_mut', C.c_int64),
+        ('mut_n', c_int32_p), ('mut_type_u', c_double_p), ('mut_ind_R', c_uint32_p),
+        ('mut_homol_u', c_double_p), ('mut_s', c_double_p),
     ]
 
 
@@ -107,6 +110,22 @@ class Population(C.Structure):
         ('z', c_double_p), ('fit', c_double_p), ('e', c_double_p),
         ('max_ind_idx', C.c_int64),
     ]
+
+
+class Mutation(C.Structure):
+    _fields_ = [
+        ('mu_neut', C.c_double), ('mu_delet', C.c_double),
+        ('delet_s_shape', C.c_double), ('delet_s_scale', C.c_double),
+        ('n_mutables', C.c_int32), ('host_mutables', c_int32_p),
+        ('n_nonneut', C.c_int32), ('host_nonneut_loci', c_int32_p),
+        ('n_delet', C.c_int32), ('host_delet_loci', c_int32_p), ('host_delet_s', c_double_p),
+        ('log_capacity', C.c_int32),
+    ]
+
+
+class MutationRow(C.Structure):
+    _fields_ = [('t', C.c_int64), ('individual', C.c_int64), ('locus', C.c_int32), ('row', C.c_int32),
+                ('homologue', C.c_int32), ('type', C.c_int32), ('s', C.c_double)]
 
 
 class StepRecord(C.Structure):
@@ -173,6 +192,10 @@ SIGNATURES = {
     'gnx_tskit_set_nodes': (C.c_int, [_ctx, c_int32_p, c_int32_p, C.c_int64, C.c_int32, C.c_int32]),
     'gnx_tskit_drain': (C.c_int, [_ctx, C.POINTER(TskitRows)]),
     'gnx_tskit_renumber': (C.c_int, [_ctx]),
+    'gnx_set_mutation': (C.c_int, [_ctx, C.POINTER(Mutation)]),
+    'gnx_mutate': (C.c_int, [_ctx]),
+    'gnx_read_mutations': (C.c_int, [_ctx, C.POINTER(MutationRow), C.c_int32, c_int32_p, c_int32_p, c_int32_p,
+                                     c_int32_p, c_int32_p, c_double_p, c_int32_p]),
     'gnx_stats_genotypes': (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
     'gnx_read_field': (C.c_int, [_ctx, C.c_int32, C.c_void_p, C.c_int64]),
     'gnx_device_ptr': (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),

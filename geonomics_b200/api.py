@@ -306,6 +306,10 @@ class Trait:
         return self.phi[spp._cells[:, 1], spp._cells[:, 0]]
 
 
+class MutationRateError(Exception):
+    """genome.py:36-37."""
+
+
 class GenomicArchitecture:
     """genome.py:440-810 (use_tskit=False path)."""
 
@@ -321,6 +325,8 @@ class GenomicArchitecture:
         self.tskit_simp_interval = g_params.get('tskit_simp_interval', 100)
         self.mu_neut = g_params.get('mu_neut', 0)
         self.mu_delet = g_params.get('mu_delet', 0)
+        self.delet_alpha_distr_shape = g_params.get('delet_alpha_distr_shape', 0.2)
+        self.delet_alpha_distr_scale = g_params.get('delet_alpha_distr_scale', 0.2)
         self.neut_loci = np.array(range(self.L))
         self.nonneut_loci = np.array([])
         self.delet_loci = np.int64([])
@@ -543,6 +549,12 @@ class Species:
                           ((self.gen_arch.mu_delet or 0) > 0 or self.gen_arch.traits is not None))
         self.mutate = (self.gen_arch is not None and self.gen_arch._mu_tot is not None and
                        self.gen_arch._mu_tot > 0)
+        self.mut_log = None
+        if 'gen_arch' in spp_params and spp_params['gen_arch'].get('mut_log'):
+            self.mut_log = spp_params['gen_arch']['mut_log']
+            if self.mut_log is True:
+                self.mut_log = '%s_mutations.log' % name
+        self.mutations = []                    # drained device mutation log (dict rows)
         self._seed = seed
         self._dev = None
         self._cache = None                     # host copy of the device state (lazy)
@@ -620,6 +632,8 @@ class Species:
             self.Nt.append(int(r['Nt']))
             self.n_births.append(int(r['n_births']))
             self.n_deaths.append(int(r['n_deaths']))
+        if self.mutate and self.burned:
+            self._sync_mutations()
         if recs:
             self.max_ind_idx += int(sum(r['n_births'] for r in recs))
             if recs[-1]['Nt'] == 0:
@@ -788,7 +802,61 @@ class Species:
                 flat[hom // 2, site, hom % 2] = 1
         self._dev.set_burn(False)
         self._dev.upload(s['x'], s['y'], s['age'], s['sex'], s['idx'], g=g, max_ind_idx=s['max_ind_idx'])
+        self._set_mutation(burn_T, T)
         self._invalidate()
+
+    def _set_mutation(self, burn_T, T):
+        """species.py:960-967 + genome.py:1060-1104: check the rates against the infinite-sites
+        budget, shuffle the mutable loci, hand the bookkeeping to the device (a13)."""
+        ga = self.gen_arch
+        if not self.mutate:
+            return
+        if ga.use_tskit:
+            raise NotImplementedError('mutation with use_tskit=True needs msprime/tskit tables')
+        if ga.traits is not None and any(t.mu > 0 for t in ga.traits.values()):
+            # genome.py:430: Trait._add_locus indexes loci_idxs, which is None when use_tskit=False
+            raise NotImplementedError('trait mutation (Trait.mu > 0) raises in the reference when '
+                                      'use_tskit=False (genome.py:416-437); only mu_neut / mu_delet are supported')
+        # mutation.py:24-41 _calc_estimated_total_mutations
+        mean_births = float(np.sum(self.K)) * self.b * self.n_births_distr_lambda
+        est = int(2.5 * mean_births * ga.L * (T or 0) * ga._mu_tot)
+        nonneut = set(int(v) for v in ga.nonneut_loci)
+        if est > 0.75 * (ga.L - len(nonneut)):
+            raise MutationRateError('This species has been parameterized with too few neutral loci to '
+                                    'accommodate the expected number of mutations. (Geonomics only uses an '
+                                    'infinite sites model.)')
+        if len(ga.neut_loci) == 0 and ga._mu_tot > 0:        # genome.py:1082-1094
+            warnings.warn('non-zero mutation rates but no neutral loci: mutation switched off')
+            ga.mu_neut = ga.mu_delet = 0
+            self.mutate = False
+            return
+        mutables = [*set(range(ga.L)).difference(nonneut)]    # genome.py:1101-1104
+        np.random.shuffle(mutables)
+        ga._mutables = [*mutables]
+        self._dev.set_mutation(ga.mu_neut or 0, ga.mu_delet or 0, ga._mutables,
+                               np.sort(np.array(sorted(nonneut), dtype=np.int64)), ga.delet_loci, ga.delet_loci_s,
+                               ga.delet_alpha_distr_shape, ga.delet_alpha_distr_scale,
+                               log_capacity=max(ga.L, 16))
+
+    def _sync_mutations(self):
+        """Pull the device's mutation log and bookkeeping into gen_arch (what mutation.py:199-205
+        logs, and genome.py:753-788 maintains, in the reference)."""
+        if not self.mutate or self._dev is None or not self.burned:
+            return []
+        rows, st = self._dev.read_mutations(max_rows=max(self.gen_arch.L, 16))
+        ga = self.gen_arch
+        ga._mutables = ga._mutables[:st['n_mutables']]
+        ga.nonneut_loci = st['nonneut_loci'].astype(np.int64)
+        ga.neut_loci = np.array(sorted(set(range(ga.L)).difference(set(int(v) for v in ga.nonneut_loci))))
+        ga.delet_loci = st['delet_loci'].astype(np.int64)
+        ga.delet_loci_s = st['delet_s']
+        self.mutations.extend(rows)
+        if self.mut_log:
+            with open(self.mut_log, 'a') as f:
+                for r in rows:
+                    f.write('MUTATION: %s\n\t INDIVIDUAL %i,  LOCUS %i\n\t timestep %i\n\n'
+                            % (r['type'], r['individual'], r['locus'], r['t']))
+        return rows
 
 
 class Community(dict):

@@ -54,6 +54,9 @@ struct gnx_ctx {
   Params prm{};
   DevDraws draws{};
   Tsk tsk{};
+  Mut mut{};
+  bool mut_delet = false;
+  std::vector<void*> mut_allocs;
   std::vector<uint32_t> host_paths;   // packed recombination paths (breakpoint CSR for tskit records)
   std::vector<void*> tsk_allocs;
   Counters* d_c = nullptr;
@@ -121,6 +124,7 @@ extern "C" const char* gnx_strerror(int code) {
     case GNX_ERR_CAPACITY: return "population outgrew ctx capacity";
     case GNX_ERR_DRAWS: return "injected draw buffer exhausted";
     case GNX_ERR_STATE: return "call made in the wrong state";
+    case GNX_ERR_MUTABLES: return "no mutable locus left";
     default: return "unknown error";
   }
 }
@@ -263,6 +267,7 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   free_bucket(ctx->trait_allocs);
   free_bucket(ctx->dens_allocs);
   free_bucket(ctx->tsk_allocs);
+  free_bucket(ctx->mut_allocs);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GNX_OK;
@@ -659,6 +664,13 @@ extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
   if ((r = up(dr->death_u, n * 8, (const void**)&D.death_u))) return r;
   if ((r = up(dr->pan_u, n * 8, (const void**)&D.pan_u))) return r;
   if ((r = up(dr->pan_R, 2 * n * 4, (const void**)&D.pan_R))) return r;
+  const size_t nm = (size_t)std::max<int64_t>(dr->n_mut, 0);
+  D.n_mut = (int64_t)nm;
+  if ((r = up(dr->mut_n, 4, (const void**)&D.mut_n))) return r;
+  if ((r = up(dr->mut_type_u, nm * 8, (const void**)&D.mut_type_u))) return r;
+  if ((r = up(dr->mut_ind_R, nm * 4, (const void**)&D.mut_ind_R))) return r;
+  if ((r = up(dr->mut_homol_u, nm * 8, (const void**)&D.mut_homol_u))) return r;
+  if ((r = up(dr->mut_s, nm * 8, (const void**)&D.mut_s))) return r;
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
 }
@@ -667,7 +679,8 @@ extern "C" int gnx_set_burn(gnx_ctx* ctx, int32_t burn) {
   ARG(ctx, "null ctx");
   ctx->burn = burn ? 1 : 0;
   ctx->prm.burn = ctx->burn;
-  ctx->prm.selection = (!ctx->burn && ctx->cfg.n_traits > 0) ? 1 : 0;
+  // species.py:449-451: selection if there are traits or deleterious mutation
+  ctx->prm.selection = (!ctx->burn && (ctx->cfg.n_traits > 0 || (ctx->mut.enabled && ctx->mut_delet))) ? 1 : 0;
   return GNX_OK;
 }
 
@@ -679,7 +692,8 @@ static int read_counters(gnx_ctx* ctx, Counters* h) {
 
 static int check_device_err(const Counters& h) {
   if (h.err & GNX_ERRBIT_CAPACITY) { g_last_error = "population outgrew ctx capacity"; return GNX_ERR_CAPACITY; }
-  if (h.err & GNX_ERRBIT_DRAWS) { g_last_error = "injected dispersal draws exhausted"; return GNX_ERR_DRAWS; }
+  if (h.err & GNX_ERRBIT_DRAWS) { g_last_error = "injected draws exhausted (dispersal tries or mutation rows)"; return GNX_ERR_DRAWS; }
+  if (h.err & GNX_ERRBIT_MUTABLES) { g_last_error = "mutation: no mutable locus left (the reference raises IndexError on _mutables.pop())"; return GNX_ERR_MUTABLES; }
   return GNX_OK;
 }
 
@@ -882,6 +896,8 @@ extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+extern "C" int gnx_mutate(gnx_ctx* ctx);
+
 extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   if (!ctx->burn) {
@@ -946,10 +962,112 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
     int r = run_scan(ctx, ts, "scan_tskit_edges");
     if (r != GNX_OK) return r;
   }
+  if (ctx->mut.enabled && !ctx->burn) {
+    int r = gnx_mutate(ctx);                       // species.py:808-809
+    if (r != GNX_OK) return r;
+  }
   PROF(ctx, "k_after_births");
   k_after_births<<<1, 1, 0, s>>>(ctx->d_c, (ctx->tsk.enabled && !ctx->burn) ? 1 : 0);
   LAUNCHED(ctx);
   return GNX_OK;
+}
+
+// ---- a13 mutation -------------------------------------------------------------------------
+extern "C" int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m) {
+  ARG(ctx, "null ctx");
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_bucket(ctx->mut_allocs);
+  memset(&ctx->mut, 0, sizeof ctx->mut);
+  ctx->mut_delet = false;
+  if (!m || (m->mu_neut <= 0 && m->mu_delet <= 0)) return gnx_set_burn(ctx, ctx->burn);
+  ARG(m->mu_neut >= 0 && m->mu_delet >= 0, "negative mutation rate");
+  ARG(m->n_mutables >= 0 && (m->n_mutables == 0 || m->host_mutables), "mutables");
+  ARG(m->n_nonneut >= 0 && m->n_nonneut <= ctx->cfg.L && (m->n_nonneut == 0 || m->host_nonneut_loci), "nonneut_loci");
+  ARG(m->n_delet >= 0 && m->n_delet <= ctx->cfg.L && (m->n_delet == 0 || (m->host_delet_loci && m->host_delet_s)),
+      "delet_loci");
+  const int L = ctx->cfg.L;
+  Mut& M = ctx->mut;
+  M.enabled = 1;
+  M.n_types = 2;
+  M.mu_tot = m->mu_neut + m->mu_delet;                 // genome.py:599-603 (trait rates are 0 here)
+  // genome.py:657-662: probs = mu / sum(mu); numpy choice: cdf = cumsum(p); cdf /= cdf[-1]
+  {
+    const double tot = m->mu_neut + m->mu_delet;
+    const double p0 = m->mu_neut / tot, p1 = m->mu_delet / tot;
+    const double c0 = p0, c1 = p0 + p1;
+    M.cdf[0] = c0 / c1;
+    M.cdf[1] = c1 / c1;
+  }
+  M.s_shape = m->delet_s_shape;
+  M.s_scale = m->delet_s_scale;
+  M.L = L;
+  M.log_cap = std::max(m->log_capacity, 1);
+  DM(ctx, &M.mutables, (size_t)std::max(L, m->n_mutables), &ctx->mut_allocs);
+  DM(ctx, &M.nonneut, (size_t)L + 1, &ctx->mut_allocs);
+  DM(ctx, &M.delet_loci, (size_t)L + 1, &ctx->mut_allocs);
+  DM(ctx, &M.delet_s, (size_t)L + 1, &ctx->mut_allocs);
+  DM(ctx, &M.counts, 4, &ctx->mut_allocs);
+  DM(ctx, &M.log, (size_t)M.log_cap, &ctx->mut_allocs);
+  cudaStream_t s = ctx->stream;
+  if (m->n_mutables) CK(cudaMemcpyAsync(M.mutables, m->host_mutables, (size_t)m->n_mutables * 4, cudaMemcpyHostToDevice, s));
+  if (m->n_nonneut) CK(cudaMemcpyAsync(M.nonneut, m->host_nonneut_loci, (size_t)m->n_nonneut * 4, cudaMemcpyHostToDevice, s));
+  if (m->n_delet) {
+    CK(cudaMemcpyAsync(M.delet_loci, m->host_delet_loci, (size_t)m->n_delet * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(M.delet_s, m->host_delet_s, (size_t)m->n_delet * 8, cudaMemcpyHostToDevice, s));
+  }
+  const int32_t counts[4] = {m->n_mutables, m->n_nonneut, m->n_delet, 0};
+  CK(cudaMemcpyAsync(M.counts, counts, sizeof counts, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->mut_delet = m->mu_delet > 0 || m->n_delet > 0;
+  return gnx_set_burn(ctx, ctx->burn);                 // refresh prm.selection
+}
+
+extern "C" int gnx_mutate(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  if (!ctx->mut.enabled || ctx->burn) return GNX_OK;
+  PROF(ctx, "k_mutate");
+  k_mutate<<<1, 32, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->mut, ctx->d_c);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_read_mutations(gnx_ctx* ctx, gnx_mutation_row_t* rows, int32_t max_rows, int32_t* n_rows,
+                                  int32_t* n_mutables_left, int32_t* host_nonneut_loci, int32_t* n_nonneut,
+                                  int32_t* host_delet_loci, double* host_delet_s, int32_t* n_delet) {
+  ARG(ctx, "null ctx");
+  if (!ctx->mut.enabled) {
+    if (n_rows) *n_rows = 0;
+    if (n_mutables_left) *n_mutables_left = 0;
+    if (n_nonneut) *n_nonneut = 0;
+    if (n_delet) *n_delet = 0;
+    return GNX_OK;
+  }
+  Mut& M = ctx->mut;
+  cudaStream_t s = ctx->stream;
+  int32_t counts[4];
+  CK(cudaMemcpyAsync(counts, M.counts, sizeof counts, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int nr = std::min(counts[3], std::max(max_rows, 0));
+  if (rows && nr > 0) CK(cudaMemcpyAsync(rows, M.log, (size_t)nr * sizeof(gnx_mutation_row_t), cudaMemcpyDeviceToHost, s));
+  if (host_nonneut_loci && counts[1] > 0)
+    CK(cudaMemcpyAsync(host_nonneut_loci, M.nonneut, (size_t)counts[1] * 4, cudaMemcpyDeviceToHost, s));
+  if (host_delet_loci && counts[2] > 0)
+    CK(cudaMemcpyAsync(host_delet_loci, M.delet_loci, (size_t)counts[2] * 4, cudaMemcpyDeviceToHost, s));
+  if (host_delet_s && counts[2] > 0)
+    CK(cudaMemcpyAsync(host_delet_s, M.delet_s, (size_t)counts[2] * 8, cudaMemcpyDeviceToHost, s));
+  if (rows) {                       // drained: reset the log cursor
+    const int32_t zero = 0;
+    CK(cudaMemcpyAsync(M.counts + 3, &zero, 4, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (n_rows) *n_rows = rows ? nr : counts[3];
+  if (n_mutables_left) *n_mutables_left = counts[0];
+  if (n_nonneut) *n_nonneut = counts[1];
+  if (n_delet) *n_delet = counts[2];
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  return check_device_err(h);
 }
 
 extern "C" int gnx_phenotype(gnx_ctx* ctx) {
@@ -1015,7 +1133,7 @@ extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   PROF(ctx, "k_death");
   k_death<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
-                                                    ctx->work, ctx->d_c);
+                                                    ctx->work, ctx->d_c, ctx->mut);
   LAUNCHED(ctx);
   return GNX_OK;
 }

@@ -39,6 +39,8 @@ struct Counters {
 #define GNX_ERRBIT_CAPACITY 1
 #define GNX_ERRBIT_DRAWS 2
 #define GNX_ERRBIT_GS 4
+#define GNX_ERRBIT_MUTABLES 8     // _mutables.pop() on an empty list
+#define GNX_ERRBIT_MUTLOG 16      // mutation log full (rows dropped, bookkeeping still exact)
 
 // Double-buffered scalar SoA in species order + slot-indexed genome rows.
 struct Pop {
@@ -187,6 +189,30 @@ struct DevDraws {
   const double* pan_u;
   const uint32_t* pan_R;
   int32_t disp_R;
+  int64_t n_mut;
+  const int32_t* mut_n;
+  const double* mut_type_u;
+  const uint32_t* mut_ind_R;
+  const double* mut_homol_u;
+  const double* mut_s;
+};
+
+// a13 mutation bookkeeping (ops/mutation.py; genome.py:753-788).  All arrays are device
+// resident and edited by the single thread of k_mutate.
+struct Mut {
+  int32_t enabled;
+  int32_t n_types;                 // neutral, deleterious (trait mutation is rejected at setup)
+  double mu_tot;                   // genome.py:599-603
+  double cdf[2];                   // cumulative type probabilities (genome.py:650-663)
+  double s_shape, s_scale;         // genome.py:690-693
+  int32_t* mutables;               // popped from the end
+  int32_t* nonneut;                // ascending, capacity L
+  int32_t* delet_loci;             // ascending, capacity L
+  double* delet_s;
+  int32_t* counts;                 // [0] n_mutables [1] n_nonneut [2] n_delet [3] n_log
+  gnx_mutation_row_t* log;
+  int32_t log_cap;
+  int32_t L;
 };
 
 struct Params {
@@ -220,7 +246,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 enum {
   SITE_MOVE = 1, SITE_MATE = 2, SITE_BIRTHS = 3, SITE_GAMETE = 4, SITE_DISP = 5, SITE_SEX = 6,
-  SITE_DEATH = 7, SITE_PANMIXIA = 8
+  SITE_DEATH = 7, SITE_PANMIXIA = 8, SITE_MUTATE = 9
 };
 
 // A stream of random words addressed by (seed; entity id, call site, time step).
@@ -313,6 +339,49 @@ __device__ inline double sample_distance(RngStream& g, int distr, double p1, dou
 }
 
 // numpy legacy poisson: multiplication method below lam = 10, PTRS above
+// Gamma(shape, scale): Marsaglia & Tsang (2000), with the U^(1/shape) boost below shape 1
+// (numpy's legacy generator uses the same method for shape > 1).
+__device__ inline double sample_gamma(RngStream& g, double shape, double scale) {
+  if (shape <= 0.0) return 0.0;
+  double boost = 1.0;
+  if (shape < 1.0) {
+    boost = pow(1.0 - g.uniform(), 1.0 / shape);
+    shape += 1.0;
+  }
+  const double d = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+  for (int it = 0; it < 1000; ++it) {
+    double x, v;
+    do {
+      x = g.normal();
+      v = 1.0 + cc * x;
+    } while (v <= 0.0);
+    v = v * v * v;
+    const double u = 1.0 - g.uniform();
+    if (u < 1.0 - 0.0331 * (x * x) * (x * x)) return d * v * boost * scale;
+    if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return d * v * boost * scale;
+  }
+  return d * boost * scale;
+}
+
+// Binomial(n, p) by geometric waiting times between successes: exact, O(n p) -- the count is
+// bounded by the number of mutable loci (infinite sites), so it is always small here.
+__device__ inline long long sample_binomial_wait(RngStream& g, long long n, double p) {
+  if (p <= 0.0 || n <= 0) return 0;
+  if (p >= 1.0) return n;
+  const double lq = log1p(-p);
+  long long pos = 0, k = 0;
+  while (true) {
+    const double u = 1.0 - g.uniform();                 // (0, 1]
+    const double gap = floor(log(u) / lq);              // failures before the next success
+    if (gap >= (double)(n - pos)) break;
+    pos += (long long)gap + 1;
+    if (pos > n) break;
+    k += 1;
+    if (k > (1 << 24)) break;
+  }
+  return k;
+}
+
 __device__ inline int sample_poisson(RngStream& g, double lam) {
   if (lam <= 0.0) return 0;
   if (lam < 10.0) {

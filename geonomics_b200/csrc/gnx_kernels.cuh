@@ -1035,6 +1035,95 @@ __global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const
 }
 
 // ========================================================================================
+// a13: mutation of this step's offspring (ops/mutation.py:169-206), use_tskit = False.
+//   One thread: the number of mutations in a run is bounded by the mutable loci (infinite
+//   sites, genome.py:1101-1104), and every event edits small sorted tables in order.
+//   neutral (mutation.py:62-86): consumes a locus, genotypes untouched.
+//   deleterious (mutation.py:90-131, 156-166; genome.py:753-788): locus joins nonneut_loci at
+//   idx and (delet_loci, delet_s); the offspring's genotype ROW idx of the drawn homologue is
+//   set to 1 (mutation.py:117 as written) and its phenotype recomputed (species.py:929).
+// ========================================================================================
+__device__ inline int lower_bound_i32(const int32_t* a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_mutate(Pop pop, Params prm, Traits tr, DevDraws dr, Mut mu, Counters* c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int B = c->B, n = c->n, cur = c->cur, Wq = pop.Wq;
+  if (B == 0) return;
+  RngStream g(prm.seed_lo, prm.seed_hi, c->max_idx + 1, SITE_MUTATE, c->t);
+  const long long n_muts = dr.mut_n ? (long long)dr.mut_n[0]
+                                    : sample_binomial_wait(g, (long long)B * mu.L, mu.mu_tot);   // mutation.py:172-173
+  for (long long m = 0; m < n_muts; ++m) {
+    if (dr.mut_n && m >= dr.n_mut) { c->err |= GNX_ERRBIT_DRAWS; break; }
+    // genome.py:650-663: choice(types, p) = searchsorted(cdf, u, side='right')
+    const double ut = dr.mut_type_u ? dr.mut_type_u[m] : g.uniform();
+    const int type = ut < mu.cdf[0] ? 0 : 1;
+    if (mu.counts[0] == 0) { c->err |= GNX_ERRBIT_MUTABLES; break; }    // list.pop() on an empty list
+    const double s_raw = type == 1 ? (dr.mut_s ? dr.mut_s[m] : sample_gamma(g, mu.s_shape, mu.s_scale)) : 0.0;
+    const double sel = fmin(s_raw, 1.0);                                  // genome.py:692
+    const int locus = mu.mutables[--mu.counts[0]];                        // mutation.py:73 / :95
+    const uint32_t R = dr.mut_ind_R ? dr.mut_ind_R[m] : g.u32();
+    // r.choice(offspring): the list holds the new ids in DESCENDING order (species.py:615-622)
+    const int o = B - 1 - (int)choose_k(R, (uint32_t)B);
+    const double uh = dr.mut_homol_u ? dr.mut_homol_u[m] : g.uniform();
+    const int homol = uh < 0.5 ? 1 : 0;                                   // r.binomial(1, 0.5)
+    int row = -1;
+    if (type == 1) {
+      // genome.py:753-788 _add_nonneut_locus
+      int nn = mu.counts[1];
+      const int idx = lower_bound_i32(mu.nonneut, nn, locus);
+      for (int k = nn; k > idx; --k) mu.nonneut[k] = mu.nonneut[k - 1];
+      mu.nonneut[idx] = locus;
+      mu.counts[1] = nn + 1;
+      int nd = mu.counts[2];
+      const int di = lower_bound_i32(mu.delet_loci, nd, locus);
+      for (int k = nd; k > di; --k) { mu.delet_loci[k] = mu.delet_loci[k - 1]; mu.delet_s[k] = mu.delet_s[k - 1]; }
+      mu.delet_loci[di] = locus;
+      mu.delet_s[di] = sel;
+      mu.counts[2] = nd + 1;
+      // mutation.py:117: spp[individ].g[idx, homol] = 1
+      row = idx;
+      const int i = n + o;
+      uint32_t* hw = reinterpret_cast<uint32_t*>(pop.G + ((size_t)pop.gslot[cur][i] * 2 + homol) * Wq);
+      hw[row >> 5] |= 1u << (row & 31);
+      // species.py:929 _set_z_individ
+      const uint4* Gi = pop.G + (size_t)pop.gslot[cur][i] * 2 * Wq;
+      for (int tt = 0; tt < pop.T; ++tt) {
+        double acc = 0.0;
+        for (int q = 0; q < Wq; ++q) {
+          const int ks = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q], ke = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q + 4];
+          if (ks == ke) continue;
+          const uint4 h0 = Gi[q], h1 = Gi[Wq + q];
+          acc += trait_partial(tr, tt, q, Wq, h0, h1);
+        }
+        pop.z[cur][(size_t)tt * pop.cap + i] = (tr.n_loci[tt] > 1) ? 0.5 + acc : acc;
+      }
+    }
+    const int nl = mu.counts[3];
+    if (nl < mu.log_cap) {
+      gnx_mutation_row_t r;
+      r.t = c->t;
+      r.individual = c->max_idx + 1 + o;
+      r.locus = locus;
+      r.row = row;
+      r.homologue = homol;
+      r.type = type;
+      r.s = sel;
+      mu.log[nl] = r;
+      mu.counts[3] = nl + 1;
+    } else {
+      c->err |= GNX_ERRBIT_MUTLOG;
+    }
+  }
+}
+
+// ========================================================================================
 // a10 (counts): _DensityGrid._calc_density spatial.py:73-97.  Four offset coarse grids;
 // cell = (x - edge*ww/2) // ww + edge.  Per-CTA shared-memory histograms, merged with
 // global atomics.
@@ -1469,7 +1558,7 @@ __global__ void __launch_bounds__(256) k_raster_d_fix(Dens d, Land land, Params 
 // Bernoulli mortality draw (demography.py:175-176).
 // ========================================================================================
 __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
-                                                const Counters* c) {
+                                                const Counters* c, Mut mu) {
   const int n = c->n_pre, cur = c->cur, T = pop.T;
   const int64_t t = c->t;
   const size_t plane = (size_t)land.X * land.Y;
@@ -1492,6 +1581,22 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
         wfit *= 1 - phi * pw;                                     // selection.py:51-54
       }
       if (T > 0) wfit = wfit < 0.001 ? 0.001 : wfit;             // selection.py:74
+      if (mu.enabled) {
+        // selection.py:78-94: prod_k (1 - s_k * dosage(delet_locus_k)); a row gather per
+        // individual, only once a deleterious mutation exists
+        const int nd = mu.counts[2];
+        if (nd > 0) {
+          const uint32_t* g0 = reinterpret_cast<const uint32_t*>(pop.G + (size_t)pop.gslot[cur][i] * 2 * pop.Wq);
+          const uint32_t* g1 = g0 + 4 * pop.Wq;
+          double wd = 1.0;
+          for (int k = 0; k < nd; ++k) {
+            const int loc = mu.delet_loci[k];
+            const int dosage = (int)((g0[loc >> 5] >> (loc & 31)) & 1u) + (int)((g1[loc >> 5] >> (loc & 31)) & 1u);
+            wd *= 1.0 - (double)dosage * mu.delet_s[k];
+          }
+          wfit *= wd;                                              // selection.py:110-111
+        }
+      }
       pop.fit[cur][i] = wfit;
       p = 1 - (1 - p) * wfit;                                     // selection.py:122
     }

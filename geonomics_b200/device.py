@@ -201,7 +201,8 @@ class DeviceSpecies:
         # longest one so no site reads past its buffer
         widths = dict(recomb_keys=2, start_homs=2, pan_R=2, disp_dir=self.disp_R, disp_choice=self.disp_R,
                       disp_dist=self.disp_R)
-        n = max([np.asarray(v).size // widths.get(k, 1) for k, v in draws.items() if v is not None] + [0])
+        n = max([np.asarray(v).size // widths.get(k, 1) for k, v in draws.items()
+                 if v is not None and not k.startswith('mut_')] + [0])
 
         def put(name, key, dtype, typ, width=1):
             a = draws.get(key)
@@ -235,7 +236,55 @@ class DeviceSpecies:
         put('pan_u', 'pan_u', np.float64, _lib.c_double_p)
         put('pan_R', 'pan_R', np.uint32, _lib.c_uint32_p, 2)
         d.n = int(n)
+        # mutation draws (their own row count: one row per mutation)
+        if draws.get('mut_n') is not None:
+            nm = max([np.asarray(draws[k]).size for k in ('mut_type_u', 'mut_ind_R', 'mut_homol_u', 'mut_s')
+                      if draws.get(k) is not None] + [0])
+            n, n_rows = nm, n
+            keep.append(np.ascontiguousarray(np.asarray(draws['mut_n']).reshape(-1)[:1], dtype=np.int32))
+            d.mut_n = _ptr(keep[-1], _lib.c_int32_p)
+            put('mut_type_u', 'mut_type_u', np.float64, _lib.c_double_p)
+            put('mut_ind_R', 'mut_ind_R', np.uint32, _lib.c_uint32_p)
+            put('mut_homol_u', 'mut_homol_u', np.float64, _lib.c_double_p)
+            put('mut_s', 'mut_s', np.float64, _lib.c_double_p)
+            d.n_mut = int(nm)
+            n = n_rows
         _lib.check(self._L.gnx_set_draws(self._ctx, C.byref(d)), 'gnx_set_draws')
+
+    # ---- a13 mutation ------------------------------------------------------------------------
+    def set_mutation(self, mu_neut, mu_delet, mutables, nonneut_loci, delet_loci=(), delet_s=(),
+                     delet_s_shape=0.2, delet_s_scale=0.2, log_capacity=4096):
+        """Enable mutation of each step's offspring (ops/mutation.py:169-206, use_tskit=False).
+        mutables: the shuffled list of mutable loci (genome.py:1101-1104), popped from its end."""
+        m = _lib.Mutation()
+        m.mu_neut, m.mu_delet = float(mu_neut), float(mu_delet)
+        m.delet_s_shape, m.delet_s_scale = float(delet_s_shape), float(delet_s_scale)
+        mt = np.ascontiguousarray(mutables, dtype=np.int32)
+        nn = np.ascontiguousarray(nonneut_loci, dtype=np.int32)
+        dl = np.ascontiguousarray(delet_loci, dtype=np.int32)
+        ds = np.ascontiguousarray(delet_s, dtype=np.float64)
+        m.n_mutables, m.host_mutables = len(mt), _ptr(mt, _lib.c_int32_p)
+        m.n_nonneut, m.host_nonneut_loci = len(nn), _ptr(nn, _lib.c_int32_p)
+        m.n_delet, m.host_delet_loci, m.host_delet_s = len(dl), _ptr(dl, _lib.c_int32_p), _ptr(ds, _lib.c_double_p)
+        m.log_capacity = int(log_capacity)
+        _lib.check(self._L.gnx_set_mutation(self._ctx, C.byref(m)), 'gnx_set_mutation')
+
+    def read_mutations(self, max_rows=4096):
+        """Drain the mutation log; returns (rows, state) with rows a list of dicts (t, individual,
+        locus, row, homologue, type, s) and state the current bookkeeping arrays."""
+        rows = (_lib.MutationRow * max_rows)()
+        n_rows, n_left, n_nn, n_dl = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        nn = np.zeros(self.Lg + 1, np.int32)
+        dl = np.zeros(self.Lg + 1, np.int32)
+        ds = np.zeros(self.Lg + 1, np.float64)
+        _lib.check(self._L.gnx_read_mutations(
+            self._ctx, rows, max_rows, C.byref(n_rows), C.byref(n_left), _ptr(nn, _lib.c_int32_p), C.byref(n_nn),
+            _ptr(dl, _lib.c_int32_p), _ptr(ds, _lib.c_double_p), C.byref(n_dl)), 'gnx_read_mutations')
+        out = [dict(t=r.t, individual=r.individual, locus=r.locus, row=r.row, homologue=r.homologue,
+                    type=('neut', 'delet')[r.type], s=r.s) for r in rows[:n_rows.value]]
+        state = dict(n_mutables=n_left.value, nonneut_loci=nn[:n_nn.value].copy(),
+                     delet_loci=dl[:n_dl.value].copy(), delet_s=ds[:n_dl.value].copy())
+        return out, state
 
     # ---- population in / out ---------------------------------------------------------------
     def _pop_struct(self, bufs):

@@ -47,7 +47,8 @@ enum {
   GNX_ERR_ARG = -2,         /* invalid argument */
   GNX_ERR_CAPACITY = -3,    /* population outgrew ctx capacity */
   GNX_ERR_DRAWS = -4,       /* an injected draw buffer was exhausted */
-  GNX_ERR_STATE = -5        /* call made in the wrong state (e.g. genomes not set) */
+  GNX_ERR_STATE = -5,       /* call made in the wrong state (e.g. genomes not set) */
+  GNX_ERR_MUTABLES = -6     /* no mutable locus left (the reference raises on _mutables.pop()) */
 };
 
 /* Species + landscape parameters the hot path reads.  Mirrors the attributes the reference
@@ -147,6 +148,14 @@ typedef struct {
   const double* death_u;            /* A16 [n] */
   const double* pan_u;              /* A3 panmixia [n]: individual i opens a mating slot iff u < b */
   const uint32_t* pan_R;            /* A3 panmixia [n][2]: the slot's two parents, (R * N) >> 32 */
+  /* mutation (ops/mutation.py:169-206); n_mut = length of the per-mutation arrays */
+  int64_t n_mut;
+  const int32_t* mut_n;             /* [1] number of mutations this step (binomial(B*L, mu_tot) output) */
+  const double* mut_type_u;         /* [n_mut] type = searchsorted(cdf(mu_neut, mu_delet, ...), u, 'right') */
+  const uint32_t* mut_ind_R;        /* [n_mut] mutated offspring = B - 1 - ((R * B) >> 32): r.choice over the
+                                     * descending id list of species.py:615-622 */
+  const double* mut_homol_u;        /* [n_mut] homologue = (u < 0.5) */
+  const double* mut_s;              /* [n_mut] gamma(shape, scale) output for deleterious s (before min(s, 1)) */
 } gnx_draws_t;
 
 /* Host-side SoA view of a population (upload / download). Any pointer may be NULL. */
@@ -255,6 +264,51 @@ int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, const int32_t* 
                         int32_t next_node_id, int32_t next_individual_row);
 int gnx_tskit_drain(gnx_ctx* ctx, gnx_tskit_rows_t* rows);   /* NULL arrays: query the counts only */
 int gnx_tskit_renumber(gnx_ctx* ctx);
+
+/* ---- a13 mutation (ops/mutation.py:169-206 _do_mutation; :62-86 neutral; :90-131 + :156-166
+ *      deleterious; genome.py:650-663 _draw_mut_types, :690-693 _draw_delet_s, :753-788
+ *      _add_nonneut_locus), for use_tskit = False genomes.  Runs inside gnx_make_offspring /
+ *      gnx_step right after the newborn records are written (species.py:808-809).
+ *      Infinite sites: every mutation pops one locus from the END of the shuffled `mutables`
+ *      list (genome.py:1101-1104), so a run has at most n_mutables mutations and the
+ *      bookkeeping is one device thread.
+ *      - neutral: consumes a locus and the draws; the genotype array is NOT changed
+ *        (mutation.py:81-82).
+ *      - deleterious: s = min(gamma(shape, scale), 1); the locus joins nonneut_loci at
+ *        idx = bisect_left(nonneut_loci, locus) and (delet_loci, delet_s); the offspring's
+ *        genotype is set to 1 at ROW idx of the chosen homologue (mutation.py:117 indexes the
+ *        L-row genotype array with the nonneut_loci position, not with the locus -- reproduced
+ *        as is) and its phenotype is recomputed; fitness is then multiplied by
+ *        prod_k (1 - s_k * dosage(delet_locus_k)) (selection.py:78-94).
+ *      - trait mutations (Trait.mu > 0) raise in the reference when use_tskit = False
+ *        (genome.py:430, loci_idxs is None): rejected here with GNX_ERR_ARG. */
+typedef struct {
+  double mu_neut, mu_delet;           /* per-site, per-generation rates (genome.py:596-603) */
+  double delet_s_shape, delet_s_scale;
+  int32_t n_mutables;
+  const int32_t* host_mutables;       /* shuffled list; popped from the end */
+  int32_t n_nonneut;
+  const int32_t* host_nonneut_loci;   /* ascending (trait loci + earlier deleterious loci) */
+  int32_t n_delet;
+  const int32_t* host_delet_loci;     /* ascending */
+  const double* host_delet_s;
+  int32_t log_capacity;               /* rows kept for gnx_read_mutations */
+} gnx_mutation_t;
+typedef struct {
+  int64_t t;                          /* time step */
+  int64_t individual;                 /* idx of the mutated offspring */
+  int32_t locus;
+  int32_t row;                        /* genotype row written (= idx), -1 for neutral */
+  int32_t homologue;
+  int32_t type;                       /* 0 neutral, 1 deleterious */
+  double s;                           /* selection coefficient (deleterious) */
+} gnx_mutation_row_t;
+int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m);
+int gnx_mutate(gnx_ctx* ctx);         /* stage entry; already part of gnx_make_offspring / gnx_step */
+/* drains the mutation log and returns the current bookkeeping arrays (any pointer may be NULL) */
+int gnx_read_mutations(gnx_ctx* ctx, gnx_mutation_row_t* rows, int32_t max_rows, int32_t* n_rows,
+                       int32_t* n_mutables_left, int32_t* host_nonneut_loci, int32_t* n_nonneut,
+                       int32_t* host_delet_loci, double* host_delet_s, int32_t* n_delet);
 
 /* ---- on-device statistics (sim/stats.py:399-435 _calc_het / _calc_maf / _calc_mean_fitness;
  *      SURVEY.md section 8f rank 2): per-locus 1-allele counts and heterozygote counts by

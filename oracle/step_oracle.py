@@ -754,6 +754,78 @@ def mortality(p, u):
 
 
 # --------------------------------------------------------------------------------------
+# a13 mutation (use_tskit = False)
+# --------------------------------------------------------------------------------------
+def mutation_type_cdf(mu_neut, mu_delet, trait_mus=()):
+    """genome.py:650-663 _draw_mut_types: probs = mu / sum(mu) over ('neut', 'delet', 't0', ...);
+    numpy RandomState.choice(p=...) draws searchsorted(cumsum(p) / cumsum(p)[-1], u, 'right')."""
+    mus = [mu_neut, mu_delet] + list(trait_mus)
+    tot = sum(mus)
+    p = np.array([m / tot for m in mus], dtype=np.float64)
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    return cdf
+
+
+def mutate(og, oz, mut, draws, traits, dom, first_id):
+    """ops/mutation.py:169-206 _do_mutation on this step's B offspring (rows of og int8[B, L, 2]).
+
+    mut: dict(mu_neut, mu_delet, mutables (list, popped from the end: mutation.py:73, :95),
+              nonneut_loci, delet_loci, delet_s (ascending arrays)) -- updated copies are returned.
+    draws: mut_n (binomial(B*L, mu_tot) output, :172-173), and per mutation mut_type_u,
+           mut_ind_R (r.choice(offspring) := offspring[(R*B) >> 32], offspring ids descending), mut_homol_u
+           (r.binomial(1, .5) := u < .5), mut_s (r.gamma output, genome.py:691).
+    neutral (:62-86): pops a locus, genotypes untouched (:81-82).
+    deleterious (:156-166 -> :90-131): s = min(gamma, 1); idx = _add_nonneut_locus
+      (genome.py:753-788: bisect into nonneut_loci; delet_loci / delet_loci_s likewise);
+      g[idx, homol] = 1 -- row idx, as written at mutation.py:117; z recomputed (:119).
+    Returns (og, oz, new_mut, log rows)."""
+    B, L = og.shape[0], og.shape[1]
+    new = dict(mut)
+    mutables = list(mut['mutables'])
+    nonneut = [int(v) for v in mut['nonneut_loci']]
+    dl = [int(v) for v in mut['delet_loci']]
+    ds = [float(v) for v in mut['delet_s']]
+    log = []
+    n_muts = int(np.asarray(draws['mut_n']).reshape(-1)[0]) if B else 0
+    if n_muts > 0:
+        cdf = mutation_type_cdf(mut['mu_neut'], mut['mu_delet'], mut.get('trait_mus', ()))
+        og = og.copy()
+        oz = oz.copy()
+        for m in range(n_muts):
+            ti = int(np.searchsorted(cdf, draws['mut_type_u'][m], side='right'))
+            assert ti in (0, 1), 'trait mutation raises in the reference when use_tskit=False (genome.py:430)'
+            locus = int(mutables.pop())
+            # keys_list is the DESCENDING id list (species.py:615-622), so choice index k is offspring B-1-k
+            o = B - 1 - int(choose_k(np.uint32(draws['mut_ind_R'][m]), B))
+            homol = int(draws['mut_homol_u'][m] < 0.5)
+            row, sel = -1, 0.0
+            if ti == 1:
+                sel = min(float(draws['mut_s'][m]), 1.0)                     # genome.py:690-693
+                import bisect
+                row = bisect.bisect_left(nonneut, locus)
+                nonneut.insert(row, locus)
+                di = bisect.bisect_left(dl, locus)
+                dl.insert(di, locus)
+                ds.insert(di, sel)
+                og[o, row, homol] = 1                                        # mutation.py:117
+                if traits:
+                    oz[o] = phenotype(og[o:o + 1], traits, dom)[0]           # species.py:929
+            log.append(dict(individual=first_id + o, locus=locus, row=row, homologue=homol,
+                            type=('neut', 'delet')[ti], s=sel))
+    new['mutables'] = mutables
+    new['nonneut_loci'] = np.array(nonneut, dtype=np.int64)
+    new['delet_loci'] = np.array(dl, dtype=np.int64)
+    new['delet_s'] = np.array(ds, dtype=np.float64)
+    return og, oz, new, log
+
+
+def delet_dosage(g, delet_loci):
+    """selection.py:78-94: diploid dosage at the deleterious loci (use_tskit=False: g rows are loci)."""
+    return np.sum(g[:, np.asarray(delet_loci, dtype=np.int64), :], axis=2)
+
+
+# --------------------------------------------------------------------------------------
 # one whole main time step (model.py:603-667 queue order for one species):
 #   _set_age_stage -> _do_movement (+_set_e) -> _do_pop_dynamics -> _set_Nt
 # --------------------------------------------------------------------------------------
@@ -829,6 +901,9 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
                           draws['start_homs'][:B], arch['paths']) if B else \
             np.zeros((0,) + state['g'].shape[1:], np.int8)
         oz = phenotype(og, traits, arch.get('dom')) if traits else np.zeros((B, 0))
+        if arch.get('mutation') is not None:                                 # species.py:808-809
+            og, oz, im['mutation'], im['mut_log'] = mutate(
+                og, oz, arch['mutation'], draws, traits, arch.get('dom'), int(state['max_ind_idx']) + 1)
         g_all = np.concatenate([state['g'], og])
         z_all = np.concatenate([state['z'], oz]) if traits else None
     else:
@@ -847,9 +922,14 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
     im['d_rast'] = d
     # a15
     e_all = sample_env(rasters, x_all, y_all)
-    if traits and not burn:
+    mut_now = im.get('mutation', arch.get('mutation'))
+    has_delet = (not burn) and mut_now is not None and len(mut_now['delet_loci']) > 0
+    # species.py:449-451: selection if there are traits or mu_delet > 0
+    selection = (not burn) and (bool(traits) or (mut_now is not None and mut_now['mu_delet'] > 0))
+    if selection:
         cxa, cya = cells(x_all, y_all)
-        w = fitness(e_all, z_all, traits, cxa, cya)
+        delet = (delet_dosage(g_all, mut_now['delet_loci']), mut_now['delet_s']) if has_delet else None
+        w = fitness(e_all, z_all, traits, cxa, cya, delet=delet)
     else:
         w = None
     im['fit_all'] = w

@@ -97,6 +97,13 @@ CASES = {
                  move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=[0.1], gamma=[1], seed=14,
                  surfaces=False, main_steps=0, burn_case=6),
+    # neutral + deleterious mutation (ops/mutation.py), use_tskit=False; recorded after a few
+    # main steps so that earlier deleterious loci already enter the fitness
+    'mut': dict(dim=(40, 40), N=900, K_factor=0.8, L=400, n_traits=2, trait_loci=[5, 4],
+                mating_radius=2, b=0.4, sex=False, n_births_fixed=True, lam=1,
+                move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                dom=False, max_age=None, phi=[0.1, 0.05], gamma=[1, 2], seed=15,
+                surfaces=False, main_steps=5, mu_neut=1e-5, mu_delet=1e-5, model_T=10, mut_n=7),
 }
 
 
@@ -160,7 +167,12 @@ def build_params(gnx, case, tmpdir='/tmp'):
         tr['alpha_distr_sigma'] = 0.15 if c['trait_loci'][t] > 1 else 0
         tr['max_alpha_mag'] = 0.3
         tr['univ_adv'] = c.get('univ_adv', [False] * 4)[t]
-    p['model']['T'] = 100
+    p['model']['T'] = c.get('model_T', 100)
+    if c.get('mu_neut') is not None:
+        g['mu_neut'] = c['mu_neut']
+        g['mu_delet'] = c['mu_delet']
+        g['delet_alpha_distr_shape'] = 0.2
+        g['delet_alpha_distr_scale'] = 0.2
     p['model']['burn_T'] = c.get('force_burn', 20)
     p['model']['seed'] = {'num': c['seed']}
     return p
@@ -215,6 +227,16 @@ def capture_arch(spp, land):
     if spp._move_surf is not None:
         out['move_surf'] = np.asarray(spp._move_surf.surf)          # float16 [Y, X, A]
         out['disp_surf'] = np.asarray(spp._disp_surf.surf)
+    if getattr(spp, 'mutate', False):
+        out['mut_mu_neut'] = np.float64(ga.mu_neut)
+        out['mut_mu_delet'] = np.float64(ga.mu_delet)
+        out['mut_trait_mus'] = np.array([tr.mu for tr in ga.traits.values()], dtype=np.float64)
+        out['mut_mutables'] = np.array(ga._mutables, dtype=np.int64)
+        out['mut_nonneut_loci'] = np.array(ga.nonneut_loci, dtype=np.int64)
+        out['mut_delet_loci'] = np.array(ga.delet_loci, dtype=np.int64)
+        out['mut_delet_s'] = np.array(ga.delet_loci_s, dtype=np.float64)
+        out['mut_s_shape'] = np.float64(ga.delet_alpha_distr_shape)
+        out['mut_s_scale'] = np.float64(ga.delet_alpha_distr_scale)
     prm = {}
     for k in ('b', 'R', 'n_births_distr_lambda', 'mating_radius', 'd_min', 'd_max',
               'direction_distr_mu', 'direction_distr_kappa'):
@@ -243,6 +265,8 @@ class Replay:
         self.sex_phase = 0
         self.n_start = 0
         self.focals = None
+        self.in_mutation = False
+        self.n_mut_done = 0
 
     # -- movement / dispersal samplers (movement.py:55-72, 111-120)
     def vonmises(self, mu, kappa, size=None):
@@ -267,7 +291,18 @@ class Replay:
             return np.array([self.d['disp_choice'][self.off, self.tries]])
         return self.d['move_choice'][:size].copy()
 
+    def gamma(self, shape, scale=1.0, size=None):          # genome.py:691
+        return float(self.d['mut_s'][self.n_mut_done])
+
     def choice(self, opts, *a, **k):
+        if self.in_mutation:
+            if 'p' in k:                                   # genome.py:662 _draw_mut_types
+                cdf = np.cumsum(np.asarray(k['p'], dtype=np.float64))
+                cdf /= cdf[-1]
+                u = self.d['mut_type_u'][:k['size']]
+                return np.asarray(opts)[np.searchsorted(cdf, u, side='right')]
+            # mutation.py:66 / :101 r.choice(offspring)
+            return opts[int(so.choose_k(self.d['mut_ind_R'][self.n_mut_done], len(opts)))]
         # mate choice (spatial.py:241): canonical k-th neighbour
         i = self.focals[self.n_choice]
         self.n_choice += 1
@@ -279,6 +314,12 @@ class Replay:
         return order[kk]
 
     def binomial(self, n=None, p=None, size=None):
+        if self.in_mutation:
+            if n == 1:                                       # mutation.py:76 / :107 homologue
+                r = int(self.d['mut_homol_u'][self.n_mut_done] < 0.5)
+                self.n_mut_done += 1
+                return r
+            return int(self.d['mut_n'][0])                   # mutation.py:172 n_muts
         if np.ndim(p) == 1:                                  # demography.py:176
             u = self.d['death_u'][:len(p)]
             self.rec['death_p'] = np.array(p, dtype=np.float64)
@@ -328,6 +369,22 @@ def patched(rp):
     setp(npr, 'choice', rp.choice)
     setp(npr, 'binomial', rp.binomial)
     setp(npr, 'poisson', rp.poisson)
+    setp(npr, 'gamma', rp.gamma)
+
+    # mutation stage marker (species.py:808-809)
+    orig_mut = sp._do_mutation
+
+    def do_mutation(offspring, spp, log=None):
+        rp.in_mutation = True
+        rp.n_mut_done = 0
+        ga = spp.gen_arch
+        before = len(ga._mutables)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = orig_mut(offspring, spp, log=log)
+        rp.in_mutation = False
+        rp.rec['mut_count'] = before - len(ga._mutables)
+        return out
+    setp(sp, '_do_mutation', do_mutation)
 
     # dispersal wrapper: offspring counter (species.py:645-648)
     orig_disp = sp._do_dispersal
@@ -403,6 +460,13 @@ def make_draws(rng, cap, spp, case):
     d['sex_u'] = rng.random(cap)
     d['sex_redraw_u'] = rng.random(cap)
     d['death_u'] = rng.random(cap)
+    if c.get('mut_n'):
+        nm = c['mut_n']
+        d['mut_n'] = np.array([nm], dtype=np.int32)
+        d['mut_type_u'] = rng.random(nm)
+        d['mut_ind_R'] = rng.integers(0, 2**32, nm, dtype=np.uint64).astype(np.uint32)
+        d['mut_homol_u'] = rng.random(nm)
+        d['mut_s'] = rng.gamma(0.2, 0.2, nm)
     return d
 
 
@@ -541,6 +605,13 @@ def record_case(gnx, case, out_dir=HERE):
     rec['out_n_births'] = np.int64(spp.n_births[-1])
     rec['out_n_deaths'] = np.int64(spp.n_deaths[-1])
     rec['out_e'] = np.array([i.e for i in spp.values()], dtype=np.float64)
+    if getattr(spp, 'mutate', False):
+        ga = spp.gen_arch
+        assert rp.rec['mut_count'] == c['mut_n']
+        rec['out_mut_mutables'] = np.array(ga._mutables, dtype=np.int64)
+        rec['out_mut_nonneut_loci'] = np.array(ga.nonneut_loci, dtype=np.int64)
+        rec['out_mut_delet_loci'] = np.array(ga.delet_loci, dtype=np.int64)
+        rec['out_mut_delet_s'] = np.array(ga.delet_loci_s, dtype=np.float64)
     # trim draw arrays to what can be consumed (keeps fixtures small)
     nmax = N0 + B + 8
     for k in list(rec):

@@ -23,6 +23,13 @@ def load_case(name):
                 ww=float(z['ww']), traits=traits, dom=z['dom'], paths=z['paths'],
                 move_surf=z['move_surf'] if 'move_surf' in z.files else None,
                 disp_surf=z['disp_surf'] if 'disp_surf' in z.files else None)
+    if 'mut_mu_neut' in z.files:
+        arch['mutation'] = dict(mu_neut=float(z['mut_mu_neut']), mu_delet=float(z['mut_mu_delet']),
+                                trait_mus=[float(v) for v in z['mut_trait_mus']],
+                                mutables=[int(v) for v in z['mut_mutables']],
+                                nonneut_loci=z['mut_nonneut_loci'], delet_loci=z['mut_delet_loci'],
+                                delet_s=z['mut_delet_s'], s_shape=float(z['mut_s_shape']),
+                                s_scale=float(z['mut_s_scale']))
     if arch['ww'] == int(arch['ww']):
         arch['ww'] = int(arch['ww'])
     prm = dict(b=float(z['prm_b']), R=float(z['prm_R']), lam=float(z['prm_n_births_distr_lambda']),

@@ -48,6 +48,10 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
             dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'], g=state['g'],
                        z=state['z'], max_ind_idx=state['max_ind_idx'])
         out_burn = burn
+        mut = arch.get('mutation')
+        if mut is not None and not burn:
+            dev.set_mutation(mut['mu_neut'], mut['mu_delet'], mut['mutables'], mut['nonneut_loci'],
+                             mut['delet_loci'], mut['delet_s'], mut.get('s_shape', 0.2), mut.get('s_scale', 0.2))
         d = dict(draws)
         if arch.get('move_surf') is None:
             d.pop('move_choice', None)
@@ -97,6 +101,8 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
         else:
             dev.step(1)
         dev.sync()
+        if mut is not None and not burn:
+            out['mut_log'], out['mutation'] = dev.read_mutations()
         out['new'] = dev.download(e=True, genomes=not out_burn)
         out['new']['e'] = out['new']['e'][:, :-1]
         out['burn'] = out_burn

@@ -96,3 +96,40 @@ def test_on_device_stats_match_numpy(model):
     assert abs(spp._calc_het(mean=True) - het_ref.mean()) < 1e-15
     fit = mod.get_fitness()
     assert abs(spp._calc_mean_fitness() - fit.mean()) < 1e-12
+
+
+def test_model_with_mutation():
+    """make_model -> burn -> main with mu_neut, mu_delet > 0 (a13): the device's mutation log
+    is pulled into Species.mutations / GenomicArchitecture like the reference maintains them."""
+    from geonomics_b200 import api
+    p = api.read_parameters_file(PARAMS)
+    g = p['comm']['species']['spp_0']['gen_arch']
+    g['L'] = 600
+    g['mu_neut'] = 1e-5
+    g['mu_delet'] = 1e-5
+    p['model']['T'] = 12
+    mod = api.make_model(p)
+    mod.walk(10000, 'burn')
+    spp = mod.comm[0]
+    ga = spp.gen_arch
+    assert spp.mutate and len(ga._mutables) == 600 - len(ga.nonneut_loci)
+    n_nonneut0 = len(ga.nonneut_loci)
+    mutables0 = list(ga._mutables)
+    mod.walk(12, 'main')
+    births = sum(spp.n_births[-12:])
+    expect = births * 600 * 2e-5
+    assert expect > 10
+    assert 0 < len(spp.mutations) and abs(len(spp.mutations) - expect) < 6 * np.sqrt(expect)
+    assert [r['locus'] for r in spp.mutations] == mutables0[::-1][:len(spp.mutations)]
+    n_del = sum(r['type'] == 'delet' for r in spp.mutations)
+    assert len(ga.delet_loci) == n_del == len(ga.delet_loci_s)
+    assert len(ga.nonneut_loci) == n_nonneut0 + n_del
+    assert len(ga._mutables) == len(mutables0) - len(spp.mutations)
+    # every logged individual was born in the step it was logged for
+    assert all(r['individual'] <= spp.max_ind_idx for r in spp.mutations)
+    # too many expected mutations for the genome: the reference's MutationRateError
+    p2 = api.read_parameters_file(PARAMS)
+    p2['comm']['species']['spp_0']['gen_arch']['mu_neut'] = 1e-3
+    mod2 = api.make_model(p2)
+    with pytest.raises(api.MutationRateError):
+        mod2.walk(10000, 'burn')

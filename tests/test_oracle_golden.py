@@ -17,7 +17,7 @@ def case(request):
 
 
 def test_cases_present():
-    assert {'base', 'sexed', 'surf', 'burn'} <= set(CASES)
+    assert {'base', 'sexed', 'surf', 'burn', 'mut'} <= set(CASES)
 
 
 def test_age_and_movement_bit_exact(case):
@@ -111,6 +111,19 @@ def test_mortality_and_final_state(case):
         np.testing.assert_allclose(new['z'], z['out_z'], rtol=1e-12)
         np.testing.assert_allclose(new['fit'], z['out_fit'], rtol=1e-12)
     assert new['max_ind_idx'] == int(z['out_max_ind_idx'])
+
+
+def test_mutation_bookkeeping(case):
+    name, z, arch, prm, state, draws, new, im = case
+    if arch.get('mutation') is None:
+        pytest.skip('no mutation in this case')
+    m = im['mutation']
+    assert np.array_equal(m['mutables'], z['out_mut_mutables'])
+    assert np.array_equal(m['nonneut_loci'], z['out_mut_nonneut_loci'])
+    assert np.array_equal(m['delet_loci'], z['out_mut_delet_loci'])
+    assert np.array_equal(m['delet_s'], z['out_mut_delet_s'])
+    assert len(im['mut_log']) == int(draws['mut_n'][0])
+    assert {r['type'] for r in im['mut_log']} == {'neut', 'delet'}      # the case exercises both
 
 
 def test_pack_roundtrip(case):
