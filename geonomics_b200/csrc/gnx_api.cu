@@ -42,6 +42,8 @@ struct gnx_ctx {
   bool no_tma = true;               // TMA-staged gamete kernel is opt-in: measured 2.3x slower (profiles/r01_notes.md)
   std::vector<ProfSpan> spans;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // density chain of the fused step (one_step)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int device = 0;
   int num_sms = 148;
   int Wq = 0, Wwords = 0;
@@ -157,6 +159,9 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   ctx->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   const int64_t cap = cfg->capacity;
   ctx->Wq = std::max(1, (cfg->L + 127) / 128);
   ctx->Wwords = 4 * ctx->Wq;
@@ -269,6 +274,9 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   free_bucket(ctx->tsk_allocs);
   free_bucket(ctx->mut_allocs);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return GNX_OK;
 }
@@ -898,12 +906,17 @@ extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
 
 extern "C" int gnx_mutate(gnx_ctx* ctx);
 
-extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
-  ARG(ctx, "null ctx");
+// gnx_make_offspring in three parts, so the fused step can overlap the density chain (which
+// needs only the newborns' positions) with the genotype streaming
+static int offspring_check(gnx_ctx* ctx) {
   if (!ctx->burn) {
     if (!ctx->have_paths) { g_last_error = "recombination paths not set"; return GNX_ERR_STATE; }
     if (ctx->cfg.n_traits > 0 && !ctx->have_traits) { g_last_error = "traits not set"; return GNX_ERR_STATE; }
   }
+  return GNX_OK;
+}
+
+static int offspring_gametes(gnx_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   const int Wq = ctx->Wq;
   const int g = grid_for(ctx, 8);
@@ -953,9 +966,19 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
     LAUNCHED(ctx);
     }
   }
+  return GNX_OK;
+}
+
+static int offspring_newborns(gnx_ctx* ctx) {
   PROF(ctx, "k_newborns");
-  k_newborns<<<g, 256, 0, s>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c, ctx->tsk);
+  k_newborns<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+                                                        ctx->d_c, ctx->tsk);
   LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+static int offspring_finish(gnx_ctx* ctx) {
+  cudaStream_t s = ctx->stream;
   if (ctx->tsk.enabled && !ctx->burn) {
     TskitScan ts{ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->tsk, ctx->d_c,
                  ctx->cfg.n_births_fixed ? (int)ctx->cfg.n_births_lambda : 0};
@@ -970,6 +993,15 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   k_after_births<<<1, 1, 0, s>>>(ctx->d_c, (ctx->tsk.enabled && !ctx->burn) ? 1 : 0);
   LAUNCHED(ctx);
   return GNX_OK;
+}
+
+extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  int r;
+  if ((r = offspring_check(ctx))) return r;
+  if ((r = offspring_gametes(ctx))) return r;
+  if ((r = offspring_newborns(ctx))) return r;
+  return offspring_finish(ctx);
 }
 
 // ---- a13 mutation -------------------------------------------------------------------------
@@ -1167,9 +1199,31 @@ static int one_step(gnx_ctx* ctx) {
   if (!panmixia && (r = finish_binning(ctx))) return r;
   if ((r = gnx_find_mates(ctx))) return r;
   if ((r = gnx_dedup_pairs(ctx))) return r;
-  if ((r = gnx_make_offspring(ctx))) return r;
-  if ((r = gnx_density_counts(ctx))) return r;
-  if ((r = gnx_density_eval(ctx))) return r;
+  if (ctx->stream2 && !ctx->profiling && !(ctx->tsk.enabled && !ctx->burn)) {
+    // Newborn records first (positions do not depend on genotypes), then two branches:
+    //   stream  : gametes -> mutation -> birth bookkeeping
+    //   stream2 : density counts -> gradients -> Clough-Tocher coefficients -> N, d rasters
+    // The density chain is a string of small latency-bound kernels; it hides under the
+    // genotype streaming.  They join before the death probabilities.
+    if ((r = offspring_check(ctx))) return r;
+    if ((r = offspring_newborns(ctx))) return r;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->stream2;
+    r = gnx_density_counts(ctx);
+    if (r == GNX_OK) r = gnx_density_eval(ctx);
+    ctx->stream = main_stream;
+    if (r != GNX_OK) return r;
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    if ((r = offspring_gametes(ctx))) return r;
+    if ((r = offspring_finish(ctx))) return r;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  } else {
+    if ((r = gnx_make_offspring(ctx))) return r;
+    if ((r = gnx_density_counts(ctx))) return r;
+    if ((r = gnx_density_eval(ctx))) return r;
+  }
   if ((r = gnx_death_prob(ctx))) return r;
   if ((r = gnx_mortality(ctx))) return r;
   return GNX_OK;

@@ -1138,7 +1138,7 @@ __global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const C
   if (use_smem)
     for (int k = threadIdx.x; k < d.npts; k += blockDim.x) hist[k] = 0;
   __syncthreads();
-  const int n = which == 0 ? c->n_pre : c->P;
+  const int n = which == 0 ? c->n + c->B : c->P;      // = n_pre once the birth bookkeeping has run
   int* gcounts = d.counts + (size_t)which * d.npts;
   for (int i = GTID; i < n; i += GSTRIDE) {       // GTID / GSTRIDE use the x dimension only
     const double2 pt = pts[i];

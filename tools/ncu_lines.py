@@ -82,14 +82,19 @@ def main():
     dis = disasm_lines(a.lib, a.kernel)
     ks = ncu_source(a.report, a.kernel)
     name, hdr, body = ks[a.launch]
-    fn = None
-    for dem, table in dis.items():
-        if dem.split('(')[0].replace('void ', '').replace('(int)', '') in name.replace('(int)', ''):
-            fn = table
-    if fn is None:
-        fn = list(dis.values())[0]
     ia, ie, isamp = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
+    isrc = hdr.index('Source')
     base = int(body[0][ia], 16) if body[0][ia].startswith('0x') else int(body[0][ia])
+
+    def mismatches(table):
+        bad = 0
+        for r in body:
+            addr = (int(r[ia], 16) if r[ia].startswith('0x') else int(r[ia])) - base
+            if table.get(addr, (None, ''))[1].split()[:1] != r[isrc].split()[:1]:
+                bad += 1
+        return bad
+    # several template instantiations can match the regex: take the one whose SASS agrees
+    fn = min(dis.values(), key=mismatches)
     per = {}
     tot_e = tot_s = 0
     mism = 0
