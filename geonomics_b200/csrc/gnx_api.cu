@@ -229,6 +229,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   DM(ctx, &W.death_p, cap);
   DM(ctx, &W.disp_tries, cap);
   DM(ctx, &W.tile_sums, (size_t)std::max<int64_t>(cap, ctx->ncell) / SCAN_TILE + 2);
+  DM(ctx, &W.scan_ticket, 4);
   DM(ctx, &W.N_rast, plane);
   DM(ctx, &W.NP_rast, plane);
   DM(ctx, &W.d_rast, plane);
@@ -808,11 +809,8 @@ static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   char nm[64];
   snprintf(nm, sizeof nm, "%s.reduce", name);
   PROF(ctx, nm);
-  scan_reduce_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
-  LAUNCHED(ctx);
-  snprintf(nm, sizeof nm, "%s.spine", name);
-  PROF(ctx, nm);
-  scan_spine_kernel<F><<<1, SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  scan_reduce_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums,
+                                                                ctx->work.scan_ticket);
   LAUNCHED(ctx);
   snprintf(nm, sizeof nm, "%s.apply", name);
   PROF(ctx, nm);

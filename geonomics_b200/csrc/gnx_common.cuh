@@ -139,6 +139,7 @@ struct Work {
   double* death_p;
   int32_t* disp_tries;
   unsigned long long* tile_sums;
+  unsigned int* scan_ticket;   // last-block election of scan_reduce_kernel (self-resetting)
   double* N_rast;
   double* NP_rast;
   double* d_rast;

@@ -1,6 +1,6 @@
 // gnx_scan.cuh -- device-wide exclusive scan of packed (hi, lo) u32 pairs, sized from
-// device-resident counters (no host round trip).  Three launches: per-tile reduce,
-// single-CTA spine, per-tile apply.  The functor supplies:
+// device-resident counters (no host round trip).  Two launches: per-tile reduce (whose last
+// block also scans the tile sums), per-tile apply.  The functor supplies:
 //   int  size(const Counters*)                     number of elements
 //   u64  value(int i)                              packed (hi << 32 | lo) contribution
 //   void apply(int i, u64 value, u64 exclusive)    consume the exclusive prefix
@@ -68,8 +68,12 @@ __device__ __forceinline__ u64 scan_value_first(const F& f, int i) {
   else return f.value(i);
 }
 
+// Pass 1: per-tile sums; the LAST block to finish (atomic ticket, no spinning) also runs the
+// spine -- an exclusive scan of the tile sums by one CTA -- and hands the grand total to the
+// functor.  That saves the separate single-CTA launch between reduce and apply.
 template <class F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Counters* c, u64* tile_sums) {
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, Counters* c, u64* tile_sums,
+                                                                 unsigned int* ticket) {
   const int n = f.size(c);
   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -83,22 +87,25 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(F f, const Coun
     block_excl_scan(s, &tot);
     if (threadIdx.x == 0) tile_sums[tile] = tot;
   }
-}
-
-template <class F>
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_spine_kernel(F f, Counters* c, u64* tile_sums) {
-  const int n = f.size(c);
-  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  __shared__ bool is_last;
+  __threadfence();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   u64 carry = 0;
   for (int base = 0; base < ntiles; base += SCAN_BLOCK) {
     const int i = base + threadIdx.x;
-    u64 v = i < ntiles ? tile_sums[i] : 0;
+    u64 v = i < ntiles ? __ldcg(&tile_sums[i]) : 0;
     u64 tot;
     u64 ex = block_excl_scan(v, &tot);
     if (i < ntiles) tile_sums[i] = carry + ex;
     carry += tot;
   }
-  if (threadIdx.x == 0) f.total(c, carry);
+  if (threadIdx.x == 0) {
+    f.total(c, carry);
+    *ticket = 0u;              // ready for the next scan on this stream
+  }
 }
 
 template <class F>
