@@ -149,7 +149,8 @@ class _LandscapeChanger:
                 timesteps = np.int64(np.round(np.linspace(ev['start_t'], ev['end_t'], n_steps)))
                 # linspace(start, end, n_steps + 1)[1:] per cell (change.py:349-354)
                 for k, t in enumerate(timesteps):
-                    rast = start_rast + (change_rast - start_rast) * ((k + 1) / float(n_steps))
+                    # numpy.linspace arithmetic, per cell: y_k = k * ((b - a) / n) + a, last = b
+                    rast = (k + 1) * ((change_rast - start_rast) / float(n_steps)) + start_rast
                     if k == n_steps - 1:
                         rast = change_rast.copy()
                     changes.append((int(t), lyr_num, rast))

@@ -125,3 +125,25 @@ def test_conductance_surface_table_statistics():
     ang = surf[2, 2].astype(np.float64)
     assert abs(np.mean(np.cos(ang)) - 0.957) < 0.03      # E[cos] = I1(12)/I0(12) around direction 0
     assert abs(np.mean(np.sin(ang))) < 0.05
+
+
+def test_landscape_change_series_is_numpy_linspace():
+    """ops/change.py:349-354: every cell follows np.linspace(start, end, n_steps + 1)[1:], at the
+    time steps round(linspace(start_t, end_t, n_steps)) (change.py:310) -- bit for bit."""
+    from geonomics_b200 import api
+    rng = np.random.default_rng(3)
+    start = rng.random((5, 7))
+    end = rng.random((5, 7))
+    end[0, 0] = start[0, 0]                      # a cell that does not change (step == 0)
+
+    class _Lyr:
+        rast = start
+    land = {0: _Lyr()}
+    ch = api._LandscapeChanger(land, {0: {0: dict(change_rast=end, start_t=3, end_t=17, n_steps=6)}})
+    ts = np.int64(np.round(np.linspace(3, 17, 6)))
+    assert [c[0] for c in ch.changes] == list(ts)
+    ref = np.stack([np.linspace(start.flat[i], end.flat[i], 7)[1:] for i in range(start.size)])
+    for k, (_, lyr, rast) in enumerate(ch.changes):
+        assert lyr == 0
+        assert np.array_equal(rast.ravel(), ref[:, k])
+    assert np.array_equal(ch.changes[-1][2], end)

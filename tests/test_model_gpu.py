@@ -133,3 +133,31 @@ def test_model_with_mutation():
     mod2 = api.make_model(p2)
     with pytest.raises(api.MutationRateError):
         mod2.walk(10000, 'burn')
+
+
+def test_two_species_advance_independently():
+    """species do not interact (community.py:37-43); each one
+    owns a device context and its own stream.  (The reference's queue lambdas advance only the
+    last species, model.py:613-656 -- consciously corrected here.)"""
+    import copy
+    from geonomics_b200 import api
+    p = api.read_parameters_file(PARAMS)
+    spp = p['comm']['species']
+    spp['spp_1'] = copy.deepcopy(spp['spp_0'])
+    spp['spp_1']['init']['N'] = int(spp['spp_0']['init']['N'] * 0.6)
+    spp['spp_1']['mating']['b'] = 0.35
+    mod = api.make_model(p)
+    mod.walk(10000, 'burn')
+    assert all(s.burned for s in mod.comm.values()) and mod.comm.burned
+    a, b = mod.comm[0], mod.comm[1]
+    na, nb = len(a.Nt), len(b.Nt)
+    assert na == nb > 0
+    mod.walk(6, 'main')
+    for s in (a, b):
+        assert len(s.Nt) == na + 6
+        N = np.array(s.Nt)
+        assert np.all(N[1:] == N[:-1] + np.array(s.n_births[1:]) - np.array(s.n_deaths[1:]))
+        assert len(s) == s.Nt[-1] > 0
+    # different parameters and RNG streams: the trajectories are not copies of each other
+    assert list(a.Nt[-6:]) != list(b.Nt[-6:])
+    assert mod.get_genotypes(0).shape[0] == len(a) and mod.get_genotypes(1).shape[0] == len(b)
