@@ -270,7 +270,11 @@ struct RngStream {
       ctr.w += 1;
       pos = 0;
     }
-    uint32_t v = pos == 0 ? out.x : pos == 1 ? out.y : pos == 2 ? out.z : out.w;
+    // the block is consumed as a shift register: no select chain on a dynamic position
+    const uint32_t v = out.x;
+    out.x = out.y;
+    out.y = out.z;
+    out.z = out.w;
     pos += 1;
     return v;
   }
@@ -282,9 +286,7 @@ struct RngStream {
   __device__ __forceinline__ double normal() {
     double u1 = 1.0 - uniform();           // (0, 1]
     double u2 = uniform();
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    return sqrt(-2.0 * log(u1)) * c;
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
   }
 };
 

@@ -20,13 +20,19 @@
 // exactly as the table is, so the draw itself runs in float32.
 __device__ __forceinline__ float uniform_f32(RngStream& g) { return (g.u32() >> 8) * (1.0f / 16777216.0f); }
 
-__device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa) {
+// s of numpy's legacy_vonmises (Best & Fisher): depends on kappa only, computed once per thread
+// outside the per-individual loop
+__device__ __forceinline__ float vonmises_s_f32(float kappa) {
+  if (kappa < 1e-8f) return 0.0f;
+  const float r = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
+  const float rho = (r - sqrtf(2.0f * r)) / (2.0f * kappa);
+  return (1.0f + rho * rho) / (2.0f * rho);
+}
+
+__device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa, float s) {
   // numpy legacy_vonmises (Best & Fisher), single precision
   const float PI_F = 3.14159265358979f;
   if (kappa < 1e-8f) return PI_F * (2.0f * uniform_f32(g) - 1.0f);
-  const float r = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
-  const float rho = (r - sqrtf(2.0f * r)) / (2.0f * kappa);
-  const float s = (1.0f + rho * rho) / (2.0f * rho);
   float W = 1.0f;
   for (int it = 0; it < 64; ++it) {
     const float Z = cospif(uniform_f32(g));
@@ -40,7 +46,8 @@ __device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa) {
 }
 
 __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const float* rast, int X, int Y,
-                                                             int cx, int cy, int mixture, float kappa) {
+                                                             int cx, int cy, int mixture, float kappa,
+                                                             float vm_s) {
   // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
   // dropped; queen directions in raster row-major order.
   const float PI_F = 3.14159265358979f;
@@ -78,7 +85,7 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
   }
   // scipy vonmises.rvs(kappa, loc): loc + vonmises(0, kappa), not re-wrapped; float16 like the
   // reference table (spatial.py:447)
-  return __float2half_rn(loc + vonmises_f32(g, kappa));
+  return __float2half_rn(loc + vonmises_f32(g, kappa, vm_s));
 }
 
 // cos/sin of a float16 direction for the on-the-fly path: float32 libm, rounded to half
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
   double2* __restrict__ XY = pop.xy[cur];
+  const float vm_s = vonmises_s_f32((float)prm.c.move_surf_kappa);
   for (int i = GTID; i < n; i += GSTRIDE) {
     if (do_age) pop.age[cur][i] += 1;
     const double2 xy0 = XY[i];
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params
         int cx = (int)x, cy = (int)y;
         const __half d = surface_direction_onthefly(
             g, land.surf_f32[0], land.X, land.Y, cx, cy,
-            prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa);
+            prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa, vm_s);
         sincos_half_fast(d, &sn, &cs);
       } else if (dr.move_dir) {
         sincos(dr.move_dir[i], &sn, &cs);
@@ -296,14 +304,26 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
         const uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
         int k = (int)choose_k(R, (uint32_t)cnt);
         if (!overflow) {
+          uint32_t msel = 0u;
+          int base_q = 0;
+          bool found = false;
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const int cr = __popc(vm[r]);
-            if (sel_q < 0) {
-              if (k < cr) sel_q = lo[r] + (int)__fns(vm[r], 0, k + 1);    // k-th set bit
+            if (!found) {
+              if (k < cr) { msel = vm[r]; base_q = lo[r]; found = true; }
               else k -= cr;
             }
           }
+          // position of the (k+1)-th set bit of msel: popcount bisection (branch-free; __fns is
+          // a software loop)
+          int bit = 0;
+#pragma unroll
+          for (int wdt = 16; wdt >= 1; wdt >>= 1) {
+            const int cl = __popc(msel & ((1u << wdt) - 1u));
+            if (k >= cl) { k -= cl; msel >>= wdt; bit += wdt; }
+          }
+          sel_q = base_q + bit;
         } else {                         // rare: a row range longer than 32, walk again
 #pragma unroll
           for (int r = 0; r < 3; ++r)
@@ -852,6 +872,7 @@ __global__ void __launch_bounds__(GT_THREADS) k_gametes_tma(Pop pop, Params prm,
 __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                    Counters* c, Tsk tsk) {
   const int n = c->n, B = c->B, cur = c->cur;
+  const float vm_s = vonmises_s_f32((float)prm.c.disp_surf_kappa);
   const int n_nodes = c->n_nodes, n_born = c->n_born;
   const int64_t t = c->t, max_idx = c->max_idx;
   for (int o = GTID; o < B; o += GSTRIDE) {
@@ -877,7 +898,7 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
       } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
         const __half d = surface_direction_onthefly(
             g, land.surf_f32[1], land.X, land.Y, (int)mx,
-            (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa);
+            (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa, vm_s);
         sincos_half_fast(d, &sn, &cs);
       } else if (dr.disp_dir) {
         sincos(dr.disp_dir[(size_t)o * dr.disp_R + tries], &sn, &cs);
