@@ -109,6 +109,18 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def load_traffic(workload, scale):
+    """Measured DRAM bytes per launch from the committed `ncu --set full` capture of this workload
+    (profiles/r01_traffic.json, written by tools/make_traffic.py); {} if there is none."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if scale != 1.0 or not os.path.exists(path):
+        return {}
+    try:
+        return json.load(open(path)).get(workload, {}).get('kernels', {})
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -313,6 +325,7 @@ def main():
     s['npre'] = s['n'] + s['B']
     peak, peak_src = load_peaks()
     table = []
+    traffic = load_traffic(args.workload, args.scale)
     step_ms = sum(v[1] for v in prof.values()) / args.steps
     for name, (cnt, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         per_launch_ms = tot_ms / cnt
@@ -323,13 +336,16 @@ def main():
             row['algorithmic_bytes'] = b
             row['achieved_GBs'] = b / (per_launch_ms * 1e-3) / 1e9
             row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
+        if name in traffic:
+            row['dram_bytes_ncu'] = traffic[name]['dram_bytes_per_launch']
         table.append(row)
     top = next((r for r in table if 'achieved_GBs' in r), None)
     gam = next((r for r in table if r['kernel'] == 'k_gametes'), None)
     roofline = None
     if top is not None:
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_GBs'], 'peak': peak,
-                    'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': None, 'peak_source': peak_src,
+                    'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': top.get('dram_bytes_ncu'),
+                    'algorithmic_bytes': top['algorithmic_bytes'], 'peak_source': peak_src,
                     'share_of_step': top['share_of_step']}
         if gam is not None:
             roofline['genotype_streaming_kernel'] = {'kernel': 'k_gametes',

@@ -47,7 +47,7 @@ def main():
                     d['us'] = round(t, 1)
                 else:
                     d[short] = round(float(v.replace(',', '')), 1)
-        d['dram_GBs'] = round((d.get('rd_MB', 0) + d.get('wr_MB', 0)) / max(d['us'], 1e-9) * 1e-3 * 1e3, 0)
+        d["dram_GBs"] = round((d.get("rd_MB", 0) + d.get("wr_MB", 0)) / max(d["us"], 1e-9) * 1e3, 0)
         st = []
         for s in STALLS:
             c = 'smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % s
