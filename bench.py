@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -222,7 +222,8 @@ def workload_desc(cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=None,
+                    help='timed steps (default 1000 for the GPU arm: ~0.45 s, enough clock samples; 20 for --impl reference)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--workload', default='c2')
     ap.add_argument('--impl', default='b200')
@@ -232,6 +233,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == 'reference' else 1000
     from geonomics_b200 import workloads
     cfg = dict(workloads.CONFIGS[args.workload])
     if args.scale != 1.0:
