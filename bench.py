@@ -232,6 +232,9 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--replicates', type=int, default=None,
+                    help='replicate populations per GPU, stepped concurrently on their own streams '
+                         '(default 8 for c3 = BASELINE configs[2]: 64 replicates on 8 GPUs; 1 otherwise)')
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == 'reference' else 1000
@@ -267,6 +270,26 @@ def main():
     dev.upload(w['pop']['x'], w['pop']['y'], w['pop']['age'], w['pop']['sex'], w['pop']['idx'],
                genomes_packed=genomes)
     stream = torch.cuda.ExternalStream(dev.stream_ptr)
+    # further replicate populations on this GPU (independent iterations, model.py:115-117): each has
+    # its own context and stream; the steps are enqueued round-robin and overlap on the device
+    R = args.replicates if args.replicates is not None else (8 if args.workload == 'c3' else 1)
+    devs, streams = [dev], [stream]
+    for k in range(1, R):
+        wk = workloads.build(cfg, cfg['seed'] + rank + 1000 * k)
+        dk = DeviceSpecies(wk['land_dim'], wk['rasters'], wk['prm'], wk['gen_arch'], capacity=cap,
+                           seed=cfg['seed'] + 7919 * rank + 104729 * k)
+        dk.upload(wk['pop']['x'], wk['pop']['y'], wk['pop']['age'], wk['pop']['sex'], wk['pop']['idx'],
+                  genomes_packed=workloads.random_packed_genomes(N0, L, cfg['seed'] + 1 + rank + 1000 * k))
+        devs.append(dk)
+        streams.append(torch.cuda.ExternalStream(dk.stream_ptr))
+
+    def step_all(n):
+        done = 0
+        while done < n:                      # chunks keep every stream's launch queue fed
+            c = min(16, n - done)
+            for d in devs:
+                d.step(c)
+            done += c
 
     def barrier():
         if dist is not None:
@@ -274,32 +297,34 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up
-    dev.step(args.warmup)
-    dev.sync()
-    dev.step_records()
-    launches0 = dev.launch_count
+    step_all(args.warmup)
+    for d in devs:
+        d.sync()
+        d.step_records()
+    launches0 = sum(d.launch_count for d in devs)
     # ---- timed region: K steps, state resident in HBM, CUDA events on the launching stream
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    dev.step(args.steps)
-    e1.record(stream)
-    dev.sync()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1s = [torch.cuda.Event(enable_timing=True) for _ in devs]
+    e0.record(stream)                        # every stream is idle here (barrier above)
+    step_all(args.steps)
+    for e1, st in zip(e1s, streams):
+        e1.record(st)
+    for d in devs:
+        d.sync()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max(e0.elapsed_time(e1) for e1 in e1s)
     clocks = sampler.stop()
-    launches = dev.launch_count - launches0
-    recs = dev.step_records()
-    assert len(recs) == args.steps, (len(recs), args.steps)
+    launches = sum(d.launch_count for d in devs) - launches0
     # individuals processed per step = population at step start
-    n_start = []
-    prev = None
-    for r in recs:
-        n_start.append(r['Nt'] - r['n_births'] + r['n_deaths'])
-    ind_gens = float(sum(n_start))
-    births = float(sum(r['n_births'] for r in recs))
+    ind_gens = births = 0.0
+    for d in devs:
+        recs = d.step_records()
+        assert len(recs) == args.steps, (len(recs), args.steps)
+        ind_gens += float(sum(r['Nt'] - r['n_births'] + r['n_deaths'] for r in recs))
+        births += float(sum(r['n_births'] for r in recs))
     from geonomics_b200 import parallel
     # job time = slowest rank's device time; job work = sum over ranks (no data-path collective)
     ms_all, ind_all = parallel.reduce_throughput(ms, ind_gens, dist, 'cuda')
@@ -412,7 +437,9 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 coordinates/phenotypes + u32 bit-packed genotypes',
             'data': 'synthetic',
             'config': {'workload': args.workload + ': ' + workload_desc(cfg),
-                       'replicates': world, 'parallelism': 'one replicate population per GPU, no collective',
+                       'replicates': world * R,
+                       'parallelism': '%d replicate population%s per GPU (own context and stream each), no '
+                                      'collective' % (R, '' if R == 1 else 's'),
                        'births_per_individual': births_all / ind_all,
                        'l2': 'not flushed between steps: a step streams ~%.0f MB of state and work arrays '
                              '(> 126 MB L2)' % footprint_mb,
@@ -421,7 +448,8 @@ def main():
             'cpu_baseline': cpu, 'kernels': table[:14], 'gs_iters': dev.counters()['gs_iters'],
         }
         print(json.dumps(line))
-    dev.close()
+    for d in devs:
+        d.close()
     if dist is not None:
         dist.destroy_process_group()
 

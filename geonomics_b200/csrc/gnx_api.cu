@@ -44,6 +44,13 @@ struct gnx_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;          // density chain of the fused step (one_step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // one fused step captured as a CUDA graph (every kernel reads its sizes from the device
+  // counters, so the same graph serves every step); re-captured when any kernel argument changes
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_kernels = 0;
+  int64_t steps_done = 0;
+  std::vector<unsigned char> graph_key;
   int device = 0;
   int num_sms = 148;
   int Wq = 0, Wwords = 0;
@@ -162,6 +169,7 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  if (const char* ng = getenv("GNX_NO_GRAPH")) ctx->use_graph = !(ng[0] && ng[0] != '0');
   const int64_t cap = cfg->capacity;
   ctx->Wq = std::max(1, (cfg->L + 127) / 128);
   ctx->Wwords = 4 * ctx->Wq;
@@ -278,6 +286,7 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   delete ctx;
   return GNX_OK;
 }
@@ -1227,11 +1236,69 @@ static int one_step(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+// everything the step's kernels take by value: if it changes, the captured graph is stale
+static void step_key(const gnx_ctx* ctx, std::vector<unsigned char>* key) {
+  key->clear();
+  auto put = [&](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    key->insert(key->end(), b, b + n);
+  };
+  put(&ctx->pop, sizeof ctx->pop);
+  put(&ctx->land, sizeof ctx->land);
+  put(&ctx->prm, sizeof ctx->prm);
+  put(&ctx->traits, sizeof ctx->traits);
+  put(&ctx->draws, sizeof ctx->draws);
+  put(&ctx->work, sizeof ctx->work);
+  put(&ctx->dens, sizeof ctx->dens);
+  put(&ctx->tsk, sizeof ctx->tsk);
+  put(&ctx->mut, sizeof ctx->mut);
+  const int flags[4] = {ctx->burn, ctx->no_tma ? 1 : 0, ctx->have_density ? 1 : 0, ctx->mut_delet ? 1 : 0};
+  put(flags, sizeof flags);
+}
+
+static void drop_graph(gnx_ctx* ctx) {
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  ctx->graph_exec = nullptr;
+}
+
+static int capture_step(gnx_ctx* ctx) {
+  drop_graph(ctx);
+  const int64_t launches0 = ctx->launches;
+  CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  int r = one_step(ctx);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  ctx->graph_kernels = (int)(ctx->launches - launches0);
+  ctx->launches = launches0;                 // nothing ran yet
+  if (r != GNX_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return GNX_ERR_CUDA; }
+  e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { ctx->graph_exec = nullptr; g_last_error = cudaGetErrorString(e); return GNX_ERR_CUDA; }
+  step_key(ctx, &ctx->graph_key);
+  return GNX_OK;
+}
+
 extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
   ARG(ctx && n_steps >= 0, "n_steps");
+  std::vector<unsigned char> key;
   for (int k = 0; k < n_steps; ++k) {
-    int r = one_step(ctx);
-    if (r != GNX_OK) return r;
+    // the first step of a context runs un-captured (validates state, sets kernel attributes)
+    if (ctx->use_graph && !ctx->profiling && ctx->steps_done >= 1) {
+      if (k == 0 || !ctx->graph_exec) {
+        step_key(ctx, &key);
+        if (!ctx->graph_exec || key != ctx->graph_key) {
+          int r = capture_step(ctx);
+          if (r != GNX_OK) return r;
+        }
+      }
+      CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+      ctx->launches += ctx->graph_kernels;
+    } else {
+      int r = one_step(ctx);
+      if (r != GNX_OK) return r;
+    }
+    ctx->steps_done += 1;
   }
   return GNX_OK;
 }
