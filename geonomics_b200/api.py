@@ -629,10 +629,13 @@ class Species:
         (species.py:567, 582, 822, 554) on the device."""
         self._dev.step(n)
         recs = self._dev.step_records()
-        for r in recs:
+        for k, r in enumerate(recs):
             self.Nt.append(int(r['Nt']))
             self.n_births.append(int(r['n_births']))
             self.n_deaths.append(int(r['n_deaths']))
+            if r['Nt'] == 0:                         # extinct: the reference stops here (model.py:704-706);
+                recs = recs[:k + 1]                  # later steps of a bulk call were no-ops on an empty population
+                break
         if self.mutate and self.burned:
             self._sync_mutations()
         if recs:
@@ -989,7 +992,29 @@ class Model:
                              "(walk(mode='burn') first), as in the reference (model.py:1112).")
         if mode == 'burn' and self.comm.burned:
             return
-        # fast path: whole walk on the device when nothing host-side has to happen per step
+        # fast path: between two host-side events (a scheduled landscape change, the end of the
+        # walk) the steps are enqueued in one call -- no host round trip per time step
+        if mode == 'main' and not verbose and len(self.comm) == 1:
+            spp = next(iter(self.comm.values()))
+            done = 0
+            while done < T and not spp.extinct:
+                n = T - done
+                changer = self.land._changer
+                if changer is not None and changer._pos < len(changer.changes):
+                    t_change = changer.changes[changer._pos][0]       # applied after the step at t_change
+                    n = max(1, min(n, t_change - self.t))
+                n_rec0 = len(spp.Nt)
+                spp._step(n)
+                ran = len(spp.Nt) - n_rec0                           # < n if the species went extinct
+                spp.t += ran
+                self.t += ran
+                self.comm.t += ran
+                done += ran
+                if changer is not None:
+                    self.land._make_change(self.t)                    # model.py:646-652
+                if ran < n:
+                    break
+            return
         for t in range(T):
             extinct = self._do_timestep(mode)
             if verbose:
