@@ -197,6 +197,8 @@ SIGNATURES = {
     'gnx_read_mutations': (C.c_int, [_ctx, C.POINTER(MutationRow), C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                      c_int32_p, c_int32_p, c_double_p, c_int32_p]),
     'gnx_stats_genotypes': (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
+    'gnx_stats_genotypes_region': (C.c_int, [_ctx, C.c_double, C.c_double, C.c_double, C.c_double,
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
     'gnx_read_field': (C.c_int, [_ctx, C.c_int32, C.c_void_p, C.c_int64]),
     'gnx_device_ptr': (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     'gnx_stream': (C.c_void_p, [_ctx]),

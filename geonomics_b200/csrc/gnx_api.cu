@@ -1479,20 +1479,26 @@ extern "C" int gnx_set_gamete_tma(gnx_ctx* ctx, int32_t on) {
 // per locus; *fit_sum: sum of the fitness values of the last completed step; *n: population
 // size.  (het = host_het / n, freq_1 = host_c1 / 2n, maf = min(freq_1, 1 - freq_1).)
 extern "C" int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1, uint64_t* host_het, double* fit_sum, int64_t* n) {
+  return gnx_stats_genotypes_region(ctx, -1e300, 1e300, -1e300, 1e300, host_c1, host_het, fit_sum, n);
+}
+
+extern "C" int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_max, double y_min, double y_max,
+                                          uint64_t* host_c1, uint64_t* host_het, double* fit_sum, int64_t* n) {
   ARG(ctx && host_c1 && host_het && fit_sum && n, "null");
   if (ctx->burn || ctx->cfg.L == 0) { g_last_error = "no genomes on the device"; return GNX_ERR_STATE; }
   const int nbits = ctx->Wwords * 32;
   unsigned long long* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)(2 * nbits + 1) * 8));
-  CK(cudaMemsetAsync(d, 0, (size_t)(2 * nbits + 1) * 8, ctx->stream));
+  CK(cudaMalloc(&d, (size_t)(2 * nbits + 2) * 8));
+  CK(cudaMemsetAsync(d, 0, (size_t)(2 * nbits + 2) * 8, ctx->stream));
   const size_t smem = (size_t)2 * nbits * 4;
   if (smem > 48 * 1024)
     CK(cudaFuncSetAttribute(k_stats_genotypes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PROF(ctx, "k_stats_genotypes");
   k_stats_genotypes<<<grid_for(ctx, 2), 256, smem, ctx->stream>>>(ctx->pop, ctx->d_c, d, d + nbits,
-                                                                  reinterpret_cast<double*>(d + 2 * nbits));
+                                                                  reinterpret_cast<double*>(d + 2 * nbits),
+                                                                  x_min, x_max, y_min, y_max, d + 2 * nbits + 1);
   LAUNCHED(ctx);
-  std::vector<unsigned long long> h((size_t)2 * nbits + 1);
+  std::vector<unsigned long long> h((size_t)2 * nbits + 2);
   CK(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   Counters hc;
   int r = read_counters(ctx, &hc);
@@ -1500,7 +1506,7 @@ extern "C" int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1, uint64_t* ho
   if (r != GNX_OK) return r;
   for (int l = 0; l < ctx->cfg.L; ++l) { host_c1[l] = h[l]; host_het[l] = h[nbits + l]; }
   memcpy(fit_sum, &h[2 * nbits], 8);
-  *n = hc.n;
+  *n = (int64_t)h[2 * nbits + 1];
   return check_device_err(hc);
 }
 

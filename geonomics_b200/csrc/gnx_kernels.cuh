@@ -1823,7 +1823,9 @@ __global__ void __launch_bounds__(256) k_z_to_rows(Pop pop, const Counters* c, d
 // into a per-locus count (vertical popcount), accumulated in shared memory per CTA.
 // ========================================================================================
 __global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters* c, unsigned long long* c1,
-                                                          unsigned long long* chet, double* fit_sum) {
+                                                          unsigned long long* chet, double* fit_sum,
+                                                          double x0, double x1, double y0, double y1,
+                                                          unsigned long long* n_in) {
   extern __shared__ unsigned int st_smem[];       // [2][Wwords * 32]
   const int n = c->n, cur = c->cur, Ww = 4 * pop.Wq, nbits = Ww * 32;
   for (int k = threadIdx.x; k < 2 * nbits; k += blockDim.x) st_smem[k] = 0u;
@@ -1833,7 +1835,13 @@ __global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters
   double fsum = 0.0;
   for (int base = (GTID / 32) * 32; base < n; base += nwarps * 32) {
     const int i = base + lane;
-    const bool live = i < n;
+    bool live = i < n;
+    if (live) {                      // restrict to the rectangle [x0, x1) x [y0, y1) (sub-population statistics)
+      const double2 xy = pop.xy[cur][i];
+      live = xy.x >= x0 && xy.x < x1 && xy.y >= y0 && xy.y < y1;
+    }
+    const unsigned inside = __ballot_sync(0xffffffffu, live);
+    if (lane == 0 && inside) atomicAdd(n_in, (unsigned long long)__popc(inside));
     const uint32_t* row = reinterpret_cast<const uint32_t*>(pop.G + (size_t)(live ? pop.gslot[cur][i] : 0) * 2 * pop.Wq);
     if (live) fsum += pop.fit[cur][i];
     for (int wd = 0; wd < Ww; ++wd) {

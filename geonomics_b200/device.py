@@ -417,20 +417,37 @@ class DeviceSpecies:
         out['node_individual'] = np.repeat(out['first_individual_row'] + np.arange(nb), 2)
         return out
 
-    def stats(self):
+    def stats(self, region=None):
         """Per-locus statistics computed on the device from the packed genotypes
-        (sim/stats.py:399-435): dict(N, freq, het, maf, mean_fit)."""
+        (sim/stats.py:399-435): dict(N, freq, het, maf, mean_fit).  region = (x_min, x_max,
+        y_min, y_max) restricts them to the individuals in that half-open rectangle."""
         c1 = np.zeros(max(1, self.Lg), dtype=np.uint64)
         het = np.zeros(max(1, self.Lg), dtype=np.uint64)
         fs = C.c_double()
         n = C.c_int64()
-        _lib.check(self._L.gnx_stats_genotypes(self._ctx, c1.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                               het.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(fs),
-                                               C.byref(n)), 'gnx_stats_genotypes')
+        x0, x1, y0, y1 = region if region is not None else (-1e300, 1e300, -1e300, 1e300)
+        _lib.check(self._L.gnx_stats_genotypes_region(
+            self._ctx, float(x0), float(x1), float(y0), float(y1), c1.ctypes.data_as(C.POINTER(C.c_uint64)),
+            het.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(fs), C.byref(n)), 'gnx_stats_genotypes_region')
         N = int(n.value)
         freq = c1[:self.Lg] / float(2 * N) if N else np.zeros(self.Lg)
         return dict(N=N, freq=freq, het=het[:self.Lg] / float(N) if N else np.zeros(self.Lg),
                     maf=np.minimum(freq, 1 - freq), mean_fit=float(fs.value) / N if N else float('nan'))
+
+    def fst(self, region_a, region_b, est_Hs=False):
+        """Per-locus pairwise Fst = (Ht - Hs) / Ht between two rectangular sub-populations, as in the
+        reference's validation suite (tests/validation/island/island_test.py:54-68 calc_Fst_HsHt):
+        Ht = 2 pbar (1 - pbar), Hs = mean observed heterozygosity of the two (or p(1-p) summed
+        with est_Hs); NaN where the two frequencies are equal.  Allele counts come from the device."""
+        a, b = self.stats(region_a), self.stats(region_b)
+        f0, f1 = a['freq'], b['freq']
+        pbar = (f0 + f1) / 2
+        Ht = 2 * pbar * (1 - pbar)
+        Hs = (f0 * (1 - f0) + f1 * (1 - f1)) if est_Hs else (a['het'] + b['het']) / 2
+        with np.errstate(divide='ignore', invalid='ignore'):
+            out = (Ht - Hs) / Ht
+        out[f0 == f1] = np.nan
+        return out
 
     def counters(self):
         c = self.read('COUNTERS', 24)

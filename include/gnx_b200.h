@@ -315,6 +315,10 @@ int gnx_read_mutations(gnx_ctx* ctx, gnx_mutation_row_t* rows, int32_t max_rows,
  *      vertical popcount over the packed genotypes, and the sum of fitness.  Synchronises. */
 int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1 /* [L] */, uint64_t* host_het /* [L] */,
                         double* fit_sum, int64_t* n);
+/* the same restricted to the individuals in [x_min, x_max) x [y_min, y_max): sub-population allele
+ * counts for pairwise Fst = (Ht - Hs) / Ht (tests/validation/island/island_test.py:54-68) */
+int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_max, double y_min, double y_max,
+                               uint64_t* host_c1, uint64_t* host_het, double* fit_sum, int64_t* n);
 
 /* ---- introspection (parity tests, lazy API views) -------------------------------------- */
 enum {

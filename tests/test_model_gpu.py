@@ -161,3 +161,35 @@ def test_two_species_advance_independently():
     # different parameters and RNG streams: the trajectories are not copies of each other
     assert list(a.Nt[-6:]) != list(b.Nt[-6:])
     assert mod.get_genotypes(0).shape[0] == len(a) and mod.get_genotypes(1).shape[0] == len(b)
+
+
+def test_region_stats_and_fst_match_numpy(model):
+    """Sub-population allele counts on the device and the pairwise Fst of the reference's
+    validation suite (tests/validation/island/island_test.py:54-68) against numpy on the
+    downloaded genotypes."""
+    mod = model
+    spp = mod.comm[0]
+    g = mod.get_genotypes().astype(np.int64)      # [N, L, 2]
+    x, y = mod.get_x(), mod.get_y()
+    X, Y = mod.land.dim
+    west, east = (0, X / 2, 0, Y), (X / 2, X, 0, Y)
+    dev = spp._dev
+    out = {}
+    for name, (x0, x1, y0, y1) in (('w', west), ('e', east)):
+        m = (x >= x0) & (x < x1) & (y >= y0) & (y < y1)
+        st = dev.stats(region=(x0, x1, y0, y1))
+        assert st['N'] == int(m.sum()) > 0
+        f = g[m].sum(axis=(0, 2)) / (2.0 * m.sum())
+        het = (g[m].sum(axis=2) == 1).sum(axis=0) / float(m.sum())
+        np.testing.assert_allclose(st['freq'], f, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(st['het'], het, rtol=0, atol=1e-15)
+        out[name] = (f, het)
+    (f0, h0), (f1, h1) = out['w'], out['e']
+    pbar = (f0 + f1) / 2
+    Ht = 2 * pbar * (1 - pbar)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        fst_ref = (Ht - (h0 + h1) / 2) / Ht
+    fst_ref[f0 == f1] = np.nan
+    np.testing.assert_allclose(dev.fst(west, east), fst_ref, rtol=1e-12, atol=1e-15, equal_nan=True)
+    whole = dev.stats()
+    assert whole['N'] == len(spp)
