@@ -253,12 +253,22 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION/INFO; the contract is
-        # ONE JSON line on stdout, so keep NCCL quiet unless explicitly asked otherwise
-        if not os.environ.get('GNX_KEEP_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION/WARN/INFO; the contract
+        # is ONE JSON line on stdout, so file descriptor 1 points at stderr while the communicator
+        # is created (init + a first collective), then is restored
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            t = torch.zeros(1, device='cuda')
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from geonomics_b200.device import DeviceSpecies
     w = workloads.build(cfg, cfg['seed'] + rank)            # one replicate population per rank
