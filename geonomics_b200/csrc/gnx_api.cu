@@ -521,6 +521,11 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
   memset(&D, 0, sizeof D);
   D.ww = dn->window_width;
   D.hww = dn->window_width / 2.;
+  {
+    const double scaled = D.hww * 1048576.0;     // 2^20
+    D.half_index_ok = (D.hww > 0 && scaled == std::floor(scaled) && ctx->cfg.dim_x < (1 << 30) &&
+                       ctx->cfg.dim_y < (1 << 30)) ? 1 : 0;
+  }
   D.npts = dn->n_points;
   D.ntri = dn->n_tri;
   int off = 0;

@@ -90,6 +90,7 @@ struct Land {
 
 struct Dens {
   double ww, hww;
+  int32_t half_index_ok;   // hww is a multiple of 2^-20: grid cells from one half-window index per axis
   int32_t npts, ntri;
   const double* points;    // [npts][2] (i, j)
   const double* areas;

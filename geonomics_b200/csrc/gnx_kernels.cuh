@@ -1164,11 +1164,26 @@ __global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const C
   for (int i = GTID; i < n; i += GSTRIDE) {       // GTID / GSTRIDE use the x dimension only
     const double2 pt = pts[i];
     const double x = pt.x, y = pt.y;
+    // Half-window index once per axis: with h = x // (ww/2), x // ww = h >> 1 and
+    // (x - ww/2) // ww + 1 = (h + 1) >> 1.  Exact whenever x - ww/2 is exact in binary64, which
+    // holds for half-windows that are multiples of 2^-20 (the default window width is an
+    // integer: spatial.py:286-289); otherwise the four floor divisions are done as written.
+    int hx = 0, hy = 0;
+    if (d.half_index_ok) {
+      hx = (int)floordiv_exact(x, d.hww);
+      hy = (int)floordiv_exact(y, d.hww);
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      double xc = floordiv_exact(x - d.g_xe[g] * d.ww / 2., d.ww) + d.g_xe[g];
-      double yc = floordiv_exact(y - d.g_ye[g] * d.ww / 2., d.ww) + d.g_ye[g];
-      int a = (int)yc - d.g_i0[g], b = (int)xc - d.g_j0[g];
+      int xi, yi;
+      if (d.half_index_ok) {
+        xi = (hx + d.g_xe[g]) >> 1;
+        yi = (hy + d.g_ye[g]) >> 1;
+      } else {
+        xi = (int)(floordiv_exact(x - d.g_xe[g] * d.ww / 2., d.ww) + d.g_xe[g]);
+        yi = (int)(floordiv_exact(y - d.g_ye[g] * d.ww / 2., d.ww) + d.g_ye[g]);
+      }
+      int a = yi - d.g_i0[g], b = xi - d.g_j0[g];
       if (a >= 0 && a < d.g_ni[g] && b >= 0 && b < d.g_nj[g]) {
         int bin = d.g_off[g] + a * d.g_nj[g] + b;
         if (use_smem) atomicAdd(&hist[bin], 1);

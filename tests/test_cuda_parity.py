@@ -78,3 +78,32 @@ def test_fused_step_equals_staged(name):
     new_o, im_o = so.step(state, arch, prm, draws, burn=prm.get('burn', False))
     out = run_device_step(arch, prm, state, draws, staged=False)
     compare_step(out, new_o, im_o)
+
+
+@pytest.mark.parametrize('ww', [3, 2.5, 3.7, 7.25])
+def test_density_counts_window_widths(ww):
+    """Grid-cell assignment (spatial.py:73-97) for integer, dyadic and non-dyadic window widths:
+    the one-index-per-axis shortcut (dyadic half-windows) and the four floor divisions as
+    written (everything else) both match the oracle bin for bin, including points on cell edges."""
+    from oracle import step_oracle as so
+    from parity_util import synthetic_case, make_device
+    arch, prm, state, draws = synthetic_case(L=32, n=30000, n_traits=0, loci_per_trait=0, dim=(60, 45), seed=77)
+    arch['ww'] = ww
+    x, y = state['x'].copy(), state['y'].copy()
+    # a third of the points exactly on multiples of the half-window
+    k = len(x) // 3
+    x[:k] = np.minimum(np.round(x[:k] / (ww / 2)) * (ww / 2), 60 - 0.001)
+    y[:k] = np.minimum(np.round(y[:k] / (ww / 2)) * (ww / 2), 45 - 0.001)
+    dev = make_device(arch, prm, capacity=40000)
+    try:
+        dev.set_burn(True)
+        dev.upload(x, y, state['age'], state['sex'], state['idx'], max_ind_idx=state['max_ind_idx'])
+        dev.stage('density_counts')
+        dev.sync()
+        got = dev.read('COUNTS_N', len(dev.density.points))
+    finally:
+        dev.close()
+    dgs = so.DensityGridStack(arch['land_dim'], ww)
+    want = np.concatenate([c.ravel() for c in dgs.counts(x, y)])
+    assert np.array_equal(got, want)
+    assert got.sum() > 0
