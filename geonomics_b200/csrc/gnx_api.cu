@@ -1159,13 +1159,17 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   LAUNCHED(ctx);
   CK(cudaMemsetAsync(ctx->work.fix_count, 0, sizeof(int32_t), s));
   PROF(ctx, "k_raster_N");
-  k_raster_N<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
+  // rows per CTA: the smallest whole number that fits the resident grid (no ragged last pass)
+  const int rg_max = grid_for(ctx, 8);
+  const int rows_per_cta = (ctx->cfg.dim_y + rg_max - 1) / rg_max;
+  const int rgrid = (ctx->cfg.dim_y + rows_per_cta - 1) / rows_per_cta;
+  k_raster_N<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   PROF(ctx, "k_raster_N_fix");
   k_raster_N_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   PROF(ctx, "k_raster_d");
-  k_raster_d<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
+  k_raster_d<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   PROF(ctx, "k_raster_d_fix");
   k_raster_d_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);

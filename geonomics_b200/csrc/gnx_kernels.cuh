@@ -1484,10 +1484,17 @@ __device__ __noinline__ double ct_eval_exact(const Dens& d, int which, double qi
 // Bezier ordinates to those 3 x 10 monomial coefficients (CT_MONO, fixed 10x19 matrices built
 // at setup), and the barycentric coordinates are an affine map of (qi, qj) precomputed per
 // triangle (tri_aff), so one evaluation is ~12 FMAs with no division.
-__device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double qi, double qj) {
-  int si = (int)floor(qi / d.hww), sj = (int)floor(qj / d.hww);
-  si = min(max(si, 0), d.lat_ni - 2);
-  sj = min(max(sj, 0), d.lat_nj - 2);
+// lattice square index floor(q / hww), clamped: multiplicative estimate corrected to the exact
+// floor (the products are exact for the half-windows in use), no division
+__device__ __forceinline__ int lattice_index(double q, double hww, double inv_hww, int smax) {
+  int s = (int)floor(q * inv_hww);
+  if ((double)(s + 1) * hww <= q) s += 1;
+  else if ((double)s * hww > q) s -= 1;
+  return min(max(s, 0), smax);
+}
+
+__device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double qi, double qj, int si, double inv_hww) {
+  const int sj = lattice_index(qj, d.hww, inv_hww, d.lat_nj - 2);
   const int2 st = __ldg(reinterpret_cast<const int2*>(d.square_tri) + (si * (d.lat_nj - 1) + sj));
   int t = st.x;
   const double* a = d.tri_aff + 6 * t;
@@ -1511,12 +1518,16 @@ __device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double
 }
 
 // N raster (Species._calc_density species.py:845-882, clip >= 0) + its maximum
+// (rows are dealt to CTAs, columns to threads: no integer division per cell, the lattice row
+// index is computed once per row)
 __global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Counters* c) {
-  const int ncell = land.X * land.Y;
   double mx = 0.0;
-  for (int id = GTID; id < ncell; id += GSTRIDE) {
-    const int i = id / land.X, j = id - i * land.X;
-    double v = ct_eval_point(d, 0, i + 0.5, j + 0.5);
+  const double inv_hww = 1.0 / d.hww;
+  for (int i = blockIdx.x; i < land.Y; i += gridDim.x) {
+   const int si = lattice_index(i + 0.5, d.hww, inv_hww, d.lat_ni - 2);
+   for (int j = threadIdx.x; j < land.X; j += blockDim.x) {
+    const int id = i * land.X + j;
+    double v = ct_eval_point(d, 0, i + 0.5, j + 0.5, si, inv_hww);
     // where the interpolant is at rounding-noise level its sign / exact zero-ness is what
     // d = N_d / N amplifies: those cells are re-evaluated in scipy's exact operation order
     // by k_raster_N_fix (none in a populated landscape)
@@ -1524,6 +1535,7 @@ __global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Cou
     v = v < 0.0 ? 0.0 : v;                    // np.clip(dens, a_min=0)
     w.N_rast[id] = v;
     mx = fmax(mx, v);
+   }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1567,11 +1579,12 @@ __device__ __forceinline__ void raster_d_cell(const Land& land, const Params& pr
 }
 
 __global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c) {
-  const int ncell = land.X * land.Y;
   const double Nmax = __longlong_as_double((long long)c->nmax_bits);
-  for (int id = GTID; id < ncell; id += GSTRIDE) {
-    const int i = id / land.X, j = id - i * land.X;
-    raster_d_cell(land, prm, w, id, ct_eval_point(d, 1, i + 0.5, j + 0.5), Nmax);
+  const double inv_hww = 1.0 / d.hww;
+  for (int i = blockIdx.x; i < land.Y; i += gridDim.x) {
+    const int si = lattice_index(i + 0.5, d.hww, inv_hww, d.lat_ni - 2);
+    for (int j = threadIdx.x; j < land.X; j += blockDim.x)
+      raster_d_cell(land, prm, w, i * land.X + j, ct_eval_point(d, 1, i + 0.5, j + 0.5, si, inv_hww), Nmax);
   }
 }
 
