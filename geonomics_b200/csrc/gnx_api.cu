@@ -968,7 +968,10 @@ static int offspring_gametes(gnx_ctx* ctx) {
       LAUNCHED(ctx);
     } else {
     PROF(ctx, "k_gametes");
-    if (Wq <= 1) MO(1);
+#ifndef GNX_GAM_W1
+#define GNX_GAM_W1 1
+#endif
+    if (Wq <= 1) MO(GNX_GAM_W1);
     else if (Wq <= 2) MO(2);
     else if (Wq <= 4) MO(4);
     else if (Wq <= 8) MO(8);

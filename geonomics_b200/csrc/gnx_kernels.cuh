@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       hi[r] = w.cell_start[row * land.ncx + x1 + 1];
     }
     int cnt = 0;
-    // MODE 0 keeps the valid candidates of each row range as a 32-bit mask in registers
-    uint32_t vm[3] = {0u, 0u, 0u};
+    // MODE 0 keeps the valid candidates of each row range as two 32-bit masks in registers
+    // (candidates 0-31 and 32-63 of the range: evolved populations clump, and a range longer
+    // than 32 would otherwise send the whole warp down the recount path)
+    uint32_t vm[3] = {0u, 0u, 0u}, vh[3] = {0u, 0u, 0u};
     bool overflow = false;
     double best = 1e300, wsum = 0.0;
     int best_q = -1, n_w = 0;
@@ -234,18 +236,32 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
       const double2* __restrict__ cand = sxy + lo[r];
       const int self = p - lo[r];                   // position of the focal in this range, if any
       if (MODE == 0) {
-        if (len > 32) overflow = true;
-        uint32_t m = 0u;
+        if (len > 64) overflow = true;
+        uint32_t m = 0u, mh = 0u;
+        const int len0 = min(len, 32);
 #pragma unroll 4
-        for (int j = 0; j < len; ++j) {
+        for (int j = 0; j < len0; ++j) {
           const double2 cxy = cand[j];
           const double dx = cxy.x - f.x, dy = cxy.y - f.y;
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-          m |= (d2 <= r2 ? 1u : 0u) << (j & 31);
+          m |= (d2 <= r2 ? 1u : 0u) << j;
         }
-        if (self >= 0 && self < 32 && self < len) m &= ~(1u << self);
+        if (len > 32) {
+          const int len1 = min(len, 64) - 32;
+          for (int j = 0; j < len1; ++j) {
+            const double2 cxy = cand[32 + j];
+            const double dx = cxy.x - f.x, dy = cxy.y - f.y;
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            mh |= (d2 <= r2 ? 1u : 0u) << j;
+          }
+        }
+        if (self >= 0 && self < len) {
+          if (self < 32) m &= ~(1u << self);
+          else if (self < 64) mh &= ~(1u << (self - 32));
+        }
         vm[r] = m;
-        cnt += __popc(m);
+        vh[r] = mh;
+        cnt += __popc(m) + __popc(mh);
       } else {
         for (int j = 0; j < len; ++j) {
           const double2 cxy = cand[j];
@@ -313,6 +329,11 @@ __global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params p
             if (!found) {
               if (k < cr) { msel = vm[r]; base_q = lo[r]; found = true; }
               else k -= cr;
+            }
+            const int ch = __popc(vh[r]);
+            if (!found) {
+              if (k < ch) { msel = vh[r]; base_q = lo[r] + 32; found = true; }
+              else k -= ch;
             }
           }
           // position of the (k+1)-th set bit of msel: popcount bisection (branch-free; __fns is

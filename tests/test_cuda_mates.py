@@ -68,6 +68,18 @@ def test_dense_population_overflow_path(mode):
     assert nn.max() > 100                                      # row ranges far beyond 32 candidates
 
 
+@pytest.mark.parametrize('mode', ['random', 'nearest', 'inverse'])
+def test_medium_density_second_mask_path(mode):
+    """Row ranges of 33-64 candidates (clumped, evolved populations): the second 32-bit mask."""
+    rng = np.random.default_rng(8)
+    dim = (20, 20)
+    n = 1400                                                   # ~14 per mating-grid cell, ~42 per 3-cell run
+    x = rng.uniform(0, dim[0] - 0.001, n)
+    y = rng.uniform(0, dim[1] - 0.001, n)
+    nn = _run(x, y, dim, 2.0, 0.6, mode, 9)
+    assert 33 < nn.max() < 110 and np.median(nn) > 25
+
+
 def test_edge_cases():
     dim = (10, 10)
     # corners, an exactly coincident couple, a neighbour at exactly distance r, an isolate
