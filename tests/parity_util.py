@@ -32,13 +32,13 @@ def make_device(arch, prm, capacity=None, seed=0, disp_tries=6, extra=None):
                          disp_tries_injected=disp_tries)
 
 
-def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
+def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=True):
     """One main time step on the device with injected draws; returns intermediates."""
     n0 = len(state['x'])
     dev = make_device(arch, prm, capacity=capacity or (2 * n0 + 256),
                       disp_tries=draws['disp_dist'].shape[1])
     try:
-        dev.set_debug(True)
+        dev.set_debug(debug)
         burn = bool(prm.get('burn', False))
         if burn:
             dev.set_burn(True)
@@ -100,6 +100,8 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True):
             dev.stage('mortality')
         else:
             dev.step(1)
+            if not debug:
+                out['N_rast_on_demand'] = dev.raster('N_RAST')
         dev.sync()
         if mut is not None and not burn:
             out['mut_log'], out['mutation'] = dev.read_mutations()

@@ -107,3 +107,17 @@ def test_density_counts_window_widths(ww):
     want = np.concatenate([c.ravel() for c in dgs.counts(x, y)])
     assert np.array_equal(got, want)
     assert got.sum() > 0
+
+
+@pytest.mark.parametrize('name', case_names())
+def test_production_step_matches_oracle(name):
+    """The step as it runs in production (fused gnx_step, no debug arrays): the survivors, their
+    genotypes, phenotypes and fitness must equal the oracle's, and so must the N raster read
+    afterwards (`spp.N`)."""
+    from oracle import step_oracle as so
+    z, arch, prm, state, draws = load_case(name)
+    new_o, im_o = so.step(state, arch, prm, draws, burn=prm.get('burn', False))
+    out = run_device_step(arch, prm, state, draws, staged=False, debug=False)
+    compare_step(out, new_o, im_o)
+    assert np.array_equal(out['new']['idx'], z['out_idx'])
+    np.testing.assert_allclose(out['N_rast_on_demand'], im_o['N_rast'], rtol=1e-6, atol=1e-9)
