@@ -97,6 +97,12 @@ CASES = {
                  move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=[0.1], gamma=[1], seed=14,
                  surfaces=False, main_steps=0, burn_case=6),
+    # Wright-Fisher style panmixia (mating_radius = None, species.py:2178-2194)
+    'pan': dict(dim=(30, 30), N=600, K_factor=0.7, L=50, n_traits=1, trait_loci=[6],
+                mating_radius=None, b=0.3, sex=False, n_births_fixed=True, lam=1,
+                move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                dom=False, max_age=None, phi=[0.1], gamma=[1], seed=16,
+                surfaces=False, main_steps=3),
     # neutral + deleterious mutation (ops/mutation.py), use_tskit=False; recorded after a few
     # main steps so that earlier deleterious loci already enter the fitness
     'mut': dict(dim=(40, 40), N=900, K_factor=0.8, L=400, n_traits=2, trait_loci=[5, 4],
@@ -240,7 +246,8 @@ def capture_arch(spp, land):
     prm = {}
     for k in ('b', 'R', 'n_births_distr_lambda', 'mating_radius', 'd_min', 'd_max',
               'direction_distr_mu', 'direction_distr_kappa'):
-        prm[k] = float(getattr(spp, k))
+        v = getattr(spp, k)
+        prm[k] = -1.0 if v is None else float(v)          # mating_radius None (panmixia) -> -1
     prm['sex'] = int(bool(spp.sex))
     prm['sex_ratio_p'] = float(spp.sex_ratio)
     prm['n_births_fixed'] = int(bool(spp.n_births_fixed))
@@ -267,6 +274,7 @@ class Replay:
         self.focals = None
         self.in_mutation = False
         self.n_mut_done = 0
+        self.pan_phase = False
 
     # -- movement / dispersal samplers (movement.py:55-72, 111-120)
     def vonmises(self, mu, kappa, size=None):
@@ -295,6 +303,15 @@ class Replay:
         return float(self.d['mut_s'][self.n_mut_done])
 
     def choice(self, opts, *a, **k):
+        if self.pan_phase:
+            # species.py:2189: 2 * n_mates individuals with replacement; slot i (pan_u[i] < b) draws
+            # the ordinals (pan_R[i, 0] * N) >> 32 and (pan_R[i, 1] * N) >> 32
+            n = len(opts)
+            act = np.nonzero(self.d['pan_u'][:n] < self.spp.b)[0]
+            R = self.d['pan_R'][act].astype(np.uint64)
+            ac = ((R * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+            assert k.get('size') == 2 * len(act)
+            return ac.reshape(-1)
         if self.in_mutation:
             if 'p' in k:                                   # genome.py:662 _draw_mut_types
                 cdf = np.cumsum(np.asarray(k['p'], dtype=np.float64))
@@ -314,6 +331,8 @@ class Replay:
         return order[kk]
 
     def binomial(self, n=None, p=None, size=None):
+        if self.pan_phase:                                   # species.py:2183 n_mates
+            return int((self.d['pan_u'][:n] < p).sum())
         if self.in_mutation:
             if n == 1:                                       # mutation.py:76 / :107 homologue
                 r = int(self.d['mut_homol_u'][self.n_mut_done] < 0.5)
@@ -460,6 +479,9 @@ def make_draws(rng, cap, spp, case):
     d['sex_u'] = rng.random(cap)
     d['sex_redraw_u'] = rng.random(cap)
     d['death_u'] = rng.random(cap)
+    if c['mating_radius'] is None:
+        d['pan_u'] = rng.random(cap)
+        d['pan_R'] = rng.integers(0, 2**32, (cap, 2), dtype=np.uint64).astype(np.uint32)
     if c.get('mut_n'):
         nm = c['mut_n']
         d['mut_n'] = np.array([nm], dtype=np.int32)
@@ -534,24 +556,38 @@ def record_case(gnx, case, out_dir=HERE):
 
         # ---- a5/a6 mate search with canonical ordering wrapper
         x, y = st1['x'], st1['y']
-        rank, _, _ = so.canonical_rank(x, y, land.dim, spp.mating_radius)
-        rp.rank = rank
-        nb_lists = so.neighbor_lists(x, y, land.dim, spp.mating_radius)
-        rp.focals = [i for i, l in enumerate(nb_lists) if len(l) > 0]
-        rp.n_choice = 0
-        rec['n_nbrs'] = np.array([len(l) for l in nb_lists], dtype=np.int32)
+        panmixia = spp.mating_radius is None
+        if panmixia:
+            nb_lists, mate_ord = None, None
+            rec['n_nbrs'] = np.full(N0, N0 - 1, dtype=np.int32)
+        else:
+            rank, _, _ = so.canonical_rank(x, y, land.dim, spp.mating_radius)
+            rp.rank = rank
+            nb_lists = so.neighbor_lists(x, y, land.dim, spp.mating_radius)
+            rp.focals = [i for i, l in enumerate(nb_lists) if len(l) > 0]
+            rp.n_choice = 0
+            rec['n_nbrs'] = np.array([len(l) for l in nb_lists], dtype=np.int32)
 
-        # oracle's own prediction of the mate of every focal (needed to orient pairs)
-        _, _, mate_ord = so.find_mates_radius(
-            x, y, land.dim, spp.mating_radius, spp.b, draws['mate_R'], draws['mate_u'],
-            sex=None, nbrs=nb_lists)
+            # oracle's own prediction of the mate of every focal (needed to orient pairs)
+            _, _, mate_ord = so.find_mates_radius(
+                x, y, land.dim, spp.mating_radius, spp.b, draws['mate_R'], draws['mate_u'],
+                sex=None, nbrs=nb_lists)
         orig_find = spp._find_mating_pairs
         holder = {}
 
         def find_canonical():
+            rp.pan_phase = panmixia
             ref_pairs = orig_find()
+            rp.pan_phase = False
             holder['ref_pairs_ids'] = np.array(ref_pairs, dtype=np.int64).reshape(-1, 2)
-            if spp.sex:
+            if panmixia:
+                # the reference folds each drawn couple through a Python set (species.py:2192), which
+                # may swap the two parents; canonical = draw order (oracle), matched as a multiset
+                can = so.find_mates_panmixia_draws(N0, spp.b, draws['pan_u'], draws['pan_R'], None)
+                ref_unordered = sorted(tuple(sorted(p)) for p in holder['ref_pairs_ids'].tolist())
+                ours = sorted(tuple(sorted(p)) for p in ids0[can].tolist())
+                assert ref_unordered == ours, 'panmixia pairs differ from the reference'
+            elif spp.sex:
                 # sexed: reference keeps (female focal, male mate) rows in focal order
                 pos = {int(v): k for k, v in enumerate(ids0)}
                 can = np.array([(pos[int(a)], pos[int(b)]) for a, b in
@@ -572,7 +608,7 @@ def record_case(gnx, case, out_dir=HERE):
     for f, o in zip(rp.rec.get('ref_opts_focal', []), rp.rec.get('ref_opts', [])):
         counts[f] = len(o)
         assert np.array_equal(o, np.sort(nb_lists[f])), 'oracle neighbour set != reference'
-    assert np.array_equal(counts, rec['n_nbrs']), 'oracle neighbour counts != reference'
+    assert panmixia or np.array_equal(counts, rec['n_nbrs']), 'oracle neighbour counts != reference'
     rec['ref_nbr_indptr'] = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     rec['ref_nbr_indices'] = (np.concatenate(rp.rec['ref_opts']).astype(np.int32)
                               if rp.rec.get('ref_opts') else np.zeros(0, np.int32))

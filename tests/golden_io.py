@@ -34,7 +34,8 @@ def load_case(name):
         arch['ww'] = int(arch['ww'])
     prm = dict(b=float(z['prm_b']), R=float(z['prm_R']), lam=float(z['prm_n_births_distr_lambda']),
                n_births_fixed=bool(z['prm_n_births_fixed']),
-               mating_radius=float(z['prm_mating_radius']), d_min=float(z['prm_d_min']),
+               mating_radius=None if float(z['prm_mating_radius']) < 0 else float(z['prm_mating_radius']),
+               d_min=float(z['prm_d_min']),
                d_max=float(z['prm_d_max']), sex=bool(z['prm_sex']),
                sex_ratio_p=float(z['prm_sex_ratio_p']),
                max_age=None if z['prm_max_age'] < 0 else int(z['prm_max_age']),
