@@ -97,6 +97,18 @@ CASES = {
                  move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=[0.1], gamma=[1], seed=14,
                  surfaces=False, main_steps=0, burn_case=6),
+    # nearest-neighbour mating (spatial.py:194-203) and inverse-distance-weighted mate choice
+    # (spatial.py:209-229)
+    'nearest': dict(dim=(30, 30), N=700, K_factor=0.8, L=40, n_traits=1, trait_loci=[5],
+                    mating_radius=2.5, b=0.5, sex=False, n_births_fixed=True, lam=1,
+                    move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                    dom=False, max_age=None, phi=[0.1], gamma=[1], seed=17,
+                    surfaces=False, main_steps=3, choose_nearest=True),
+    'invdist': dict(dim=(30, 30), N=700, K_factor=0.8, L=40, n_traits=1, trait_loci=[5],
+                    mating_radius=2.5, b=0.5, sex=False, n_births_fixed=True, lam=1,
+                    move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                    dom=False, max_age=None, phi=[0.1], gamma=[1], seed=18,
+                    surfaces=False, main_steps=3, inverse_dist=True),
     # Wright-Fisher style panmixia (mating_radius = None, species.py:2178-2194)
     'pan': dict(dim=(30, 30), N=600, K_factor=0.7, L=50, n_traits=1, trait_loci=[6],
                 mating_radius=None, b=0.3, sex=False, n_births_fixed=True, lam=1,
@@ -141,6 +153,8 @@ def build_params(gnx, case, tmpdir='/tmp'):
     m['n_births_distr_lambda'] = c['lam']
     m['n_births_fixed'] = c['n_births_fixed']
     m['mating_radius'] = c['mating_radius']
+    m['choose_nearest_mate'] = bool(c.get('choose_nearest', False))
+    m['inverse_dist_mating'] = bool(c.get('inverse_dist', False))
     s['mortality']['max_age'] = c['max_age']
     mv = s['movement']
     mv['direction_distr_mu'] = c['mu']
@@ -248,6 +262,8 @@ def capture_arch(spp, land):
               'direction_distr_mu', 'direction_distr_kappa'):
         v = getattr(spp, k)
         prm[k] = -1.0 if v is None else float(v)          # mating_radius None (panmixia) -> -1
+    prm['choose_nearest'] = int(bool(spp.choose_nearest_mate))
+    prm['inverse_dist'] = int(bool(spp.inverse_dist_mating))
     prm['sex'] = int(bool(spp.sex))
     prm['sex_ratio_p'] = float(spp.sex_ratio)
     prm['n_births_fixed'] = int(bool(spp.n_births_fixed))
@@ -312,6 +328,22 @@ class Replay:
             ac = ((R * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
             assert k.get('size') == 2 * len(act)
             return ac.reshape(-1)
+        if 'p' in k and not self.in_mutation:
+            # inverse-distance mate choice (spatial.py:222-227): the reference lists the options by
+            # ascending distance; the shared convention walks them in canonical order.  Check the
+            # option set and the weights, return the oracle's pick for this focal.
+            i = self.focals[self.n_choice]
+            self.n_choice += 1
+            opts = np.asarray(opts, dtype=np.int64)
+            x, y = self.xy
+            d = np.sqrt((x[opts] - x[i]) ** 2 + (y[opts] - y[i]) ** 2)
+            w = self.spp.mating_radius - d
+            np.testing.assert_allclose(np.asarray(k['p']), w / w.sum(), rtol=1e-9, atol=1e-12)
+            self.rec.setdefault('ref_opts_focal', []).append(i)
+            self.rec.setdefault('ref_opts', []).append(np.sort(opts))
+            m = int(self.mate_full[i])
+            assert m in opts
+            return m
         if self.in_mutation:
             if 'p' in k:                                   # genome.py:662 _draw_mut_types
                 cdf = np.cumsum(np.asarray(k['p'], dtype=np.float64))
@@ -479,6 +511,8 @@ def make_draws(rng, cap, spp, case):
     d['sex_u'] = rng.random(cap)
     d['sex_redraw_u'] = rng.random(cap)
     d['death_u'] = rng.random(cap)
+    if c.get('inverse_dist'):
+        d['mate_inv_u'] = rng.random(cap)
     if c['mating_radius'] is None:
         d['pan_u'] = rng.random(cap)
         d['pan_R'] = rng.integers(0, 2**32, (cap, 2), dtype=np.uint64).astype(np.uint32)
@@ -569,9 +603,16 @@ def record_case(gnx, case, out_dir=HERE):
             rec['n_nbrs'] = np.array([len(l) for l in nb_lists], dtype=np.int32)
 
             # oracle's own prediction of the mate of every focal (needed to orient pairs)
+            modes = dict(choose_nearest=bool(spp.choose_nearest_mate), inverse_dist=bool(spp.inverse_dist_mating),
+                         inv_u=draws.get('mate_inv_u'))
             _, _, mate_ord = so.find_mates_radius(
                 x, y, land.dim, spp.mating_radius, spp.b, draws['mate_R'], draws['mate_u'],
-                sex=None, nbrs=nb_lists)
+                sex=None, nbrs=nb_lists, **modes)
+            # ... and the choice itself, whatever the Bernoulli(b) draw says (inverse-distance replay)
+            _, _, rp.mate_full = so.find_mates_radius(
+                x, y, land.dim, spp.mating_radius, 2.0, draws['mate_R'], draws['mate_u'],
+                sex=None, nbrs=nb_lists, **modes)
+            rp.xy = (x, y)
         orig_find = spp._find_mating_pairs
         holder = {}
 
@@ -608,7 +649,9 @@ def record_case(gnx, case, out_dir=HERE):
     for f, o in zip(rp.rec.get('ref_opts_focal', []), rp.rec.get('ref_opts', [])):
         counts[f] = len(o)
         assert np.array_equal(o, np.sort(nb_lists[f])), 'oracle neighbour set != reference'
-    assert panmixia or np.array_equal(counts, rec['n_nbrs']), 'oracle neighbour counts != reference'
+    # (nearest-neighbour mode goes through cKDTree.query and never lists the neighbour sets)
+    assert panmixia or c.get('choose_nearest') or np.array_equal(counts, rec['n_nbrs']), \
+        'oracle neighbour counts != reference'
     rec['ref_nbr_indptr'] = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     rec['ref_nbr_indices'] = (np.concatenate(rp.rec['ref_opts']).astype(np.int32)
                               if rp.rec.get('ref_opts') else np.zeros(0, np.int32))

@@ -41,7 +41,9 @@ def load_case(name):
                max_age=None if z['prm_max_age'] < 0 else int(z['prm_max_age']),
                direction_mu=float(z['prm_direction_distr_mu']),
                direction_kappa=float(z['prm_direction_distr_kappa']),
-               burn=bool(z['prm_burn']) if 'prm_burn' in z.files else False)
+               burn=bool(z['prm_burn']) if 'prm_burn' in z.files else False,
+               choose_nearest=bool(z['prm_choose_nearest']) if 'prm_choose_nearest' in z.files else False,
+               inverse_dist=bool(z['prm_inverse_dist']) if 'prm_inverse_dist' in z.files else False)
     if prm['lam'] == int(prm['lam']):
         prm['lam'] = int(prm['lam'])
     state = dict(x=z['in_x'], y=z['in_y'], age=z['in_age'], sex=z['in_sex'], idx=z['in_idx'],

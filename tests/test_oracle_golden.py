@@ -17,7 +17,7 @@ def case(request):
 
 
 def test_cases_present():
-    assert {'base', 'sexed', 'surf', 'burn', 'mut', 'pan'} <= set(CASES)
+    assert {'base', 'sexed', 'surf', 'burn', 'mut', 'pan', 'nearest', 'invdist'} <= set(CASES)
 
 
 def test_age_and_movement_bit_exact(case):
@@ -35,6 +35,8 @@ def test_neighbour_sets_match_reference(case):
     assert np.array_equal(im['n_nbrs'], z['n_nbrs'])
     if prm['mating_radius'] is None:
         pytest.skip('panmixia: no neighbour search')
+    if prm.get('choose_nearest'):
+        pytest.skip('nearest-neighbour mode: the reference never lists neighbour sets (cKDTree.query)')
     nb = so.neighbor_lists_bruteforce(z['mv_x'], z['mv_y'], arch['land_dim'], prm['mating_radius'])
     ip, ix = z['ref_nbr_indptr'], z['ref_nbr_indices']
     for i in range(len(nb)):
