@@ -97,6 +97,13 @@ CASES = {
                  move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=[0.1], gamma=[1], seed=14,
                  surfaces=False, main_steps=0, burn_case=6),
+    # non-default density window (spatial.py:270-360 with window_width = 2.5), spatially varying
+    # phi (genome.py:391-396), non-integer gamma, non-square landscape
+    'misc': dict(dim=(32, 24), N=700, K_factor=1.0, L=60, n_traits=2, trait_loci=[6, 3],
+                 mating_radius=2, b=0.5, sex=False, n_births_fixed=True, lam=1,
+                 move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                 dom=False, max_age=None, phi=['raster', 0.08], gamma=[1.5, 1], seed=19,
+                 surfaces=False, main_steps=3, window_width=2.5),
     # nearest-neighbour mating (spatial.py:194-203) and inverse-distance-weighted mate choice
     # (spatial.py:209-229)
     'nearest': dict(dim=(30, 30), N=700, K_factor=0.8, L=40, n_traits=1, trait_loci=[5],
@@ -156,6 +163,8 @@ def build_params(gnx, case, tmpdir='/tmp'):
     m['choose_nearest_mate'] = bool(c.get('choose_nearest', False))
     m['inverse_dist_mating'] = bool(c.get('inverse_dist', False))
     s['mortality']['max_age'] = c['max_age']
+    if c.get('window_width') is not None:
+        s['mortality']['density_grid_window_width'] = c['window_width']
     mv = s['movement']
     mv['direction_distr_mu'] = c['mu']
     mv['direction_distr_kappa'] = c['kappa']
@@ -181,7 +190,7 @@ def build_params(gnx, case, tmpdir='/tmp'):
         tr = g['traits']['trait_%i' % t]
         tr['layer'] = 'lyr_%i' % (1 + t % 2)
         tr['n_loci'] = c['trait_loci'][t]
-        tr['phi'] = c['phi'][t]
+        tr['phi'] = (0.02 + 0.1 * gradient(dim, 'y')) if c['phi'][t] == 'raster' else c['phi'][t]
         tr['gamma'] = c['gamma'][t]
         tr['alpha_distr_mu'] = 0.0 if c['trait_loci'][t] > 1 else 0.1
         tr['alpha_distr_sigma'] = 0.15 if c['trait_loci'][t] > 1 else 0
@@ -236,7 +245,7 @@ def capture_arch(spp, land):
     for t, tr in ga.traits.items():
         out['trait%i_loci' % t] = np.asarray(tr.loci, dtype=np.int64)
         out['trait%i_alpha' % t] = np.asarray(tr.alpha, dtype=np.float64)
-        out['trait%i_phi' % t] = np.float64(tr.phi)
+        out['trait%i_phi' % t] = np.asarray(tr.phi, dtype=np.float64)
         out['trait%i_gamma' % t] = np.float64(tr.gamma)
         out['trait%i_lyr' % t] = np.int64(tr.lyr_num)
         out['trait%i_univ_adv' % t] = np.int64(bool(tr.univ_adv))

@@ -16,7 +16,7 @@ def load_case(name):
     traits = []
     for t in range(nt):
         traits.append(dict(loci=z['trait%i_loci' % t], alpha=z['trait%i_alpha' % t],
-                           phi=float(z['trait%i_phi' % t]), gamma=float(z['trait%i_gamma' % t]),
+                           phi=(float(z['trait%i_phi' % t]) if z['trait%i_phi' % t].ndim == 0 else z['trait%i_phi' % t]), gamma=float(z['trait%i_gamma' % t]),
                            lyr_num=int(z['trait%i_lyr' % t]),
                            univ_adv=bool(z['trait%i_univ_adv' % t])))
     arch = dict(land_dim=tuple(int(v) for v in z['land_dim']), rasters=z['rasters'], K=z['K'],
