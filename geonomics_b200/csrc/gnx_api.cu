@@ -1398,7 +1398,9 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
     case GNX_F_DISP_TRIES: p = W.disp_tries; b = (size_t)h.B * 4; break;
     case GNX_F_E: p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
     case GNX_F_COUNTERS: p = ctx->d_c; b = sizeof(Counters); break;
-    case 31: p = D.coef + (size_t)2 * D.ntri * CT_STRIDE; b = 64 * 8; break;   /* debug scratch */
+#ifdef GNX_GS_TIMING
+    case 31: p = D.coef + (size_t)2 * D.ntri * CT_STRIDE; b = 64 * 8; break;   /* clock64 phase timings (tools/gs_time.py) */
+#endif
     case GNX_F_GENOMES: p = ctx->d_stage_genomes; b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4); break;
     default: g_last_error = "unknown field"; return GNX_ERR_ARG;
   }

@@ -233,7 +233,12 @@ int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_raster);
 
 /* ---- whole steps ------------------------------------------------------------------------ */
 /* n_steps iterations of the main/burn queue for this species:
- * _set_age_stage -> _do_movement -> _do_pop_dynamics -> _set_Nt  (model.py:603-667) */
+ * _set_age_stage -> _do_movement -> _do_pop_dynamics -> _set_Nt  (model.py:603-667).
+ * Asynchronous: nothing is read back (sizes live in device counters); errors such as capacity
+ * overflow surface at the next synchronising call.  From the second step of a context on, the
+ * step is one CUDA-graph launch (23 kernels on two branches: genotype streaming beside the
+ * density chain); the graph is re-captured when a setter changed any kernel argument.
+ * GNX_NO_GRAPH=1 in the environment keeps plain stream launches. */
 int gnx_step(gnx_ctx* ctx, int32_t n_steps);
 int gnx_sync(gnx_ctx* ctx);
 /* Same, with HOST buffers in and out: upload pop, run n_steps, download into pop (synchronous). */
