@@ -132,3 +132,35 @@ def test_same_seed_same_population():
     finally:
         dev.close()
     assert len(c['x']) != len(a['x']) or not np.array_equal(c['x'], a['x'])
+
+
+def test_graph_and_plain_launches_agree_across_setter_calls(monkeypatch):
+    """The CUDA-graph step (re-captured when a setter changes a kernel argument) against plain
+    stream launches (GNX_NO_GRAPH=1), with a raster change and a trait-table replacement
+    between steps: bit-identical populations."""
+    from parity_util import synthetic_case, make_device
+    arch, prm, state, draws = synthetic_case(L=200, n=20000, n_traits=2, loci_per_trait=8, dim=(120, 90), seed=5,
+                                             max_tries=24)
+    new_layer = np.ascontiguousarray(arch['rasters'][1][:, ::-1])
+    outs = []
+    for no_graph in ('0', '1'):
+        monkeypatch.setenv('GNX_NO_GRAPH', no_graph)
+        dev = make_device(arch, prm, capacity=60000, seed=99)
+        try:
+            dev.upload(state['x'], state['y'], state['age'], state['sex'], state['idx'], g=state['g'], z=state['z'],
+                       max_ind_idx=state['max_ind_idx'])
+            dev.set_draws(None)
+            dev.step(4)
+            dev.set_raster(1, new_layer)                       # environmental change (gnx_set_raster)
+            dev.step(3)
+            traits = [dict(t, alpha=np.asarray(t['alpha']) * 0.5) for t in arch['traits']]
+            dev.set_traits(traits, None)                       # new trait tables: new device pointers
+            dev.step(3)
+            dev.sync()
+            outs.append((dev.download(genomes=True), dev.step_records(), dev.launch_count))
+        finally:
+            dev.close()
+    (a, ra, la), (b, rb, lb) = outs
+    assert ra == rb and la == lb
+    for k in ('idx', 'x', 'y', 'age', 'g', 'z', 'fit'):
+        assert np.array_equal(a[k], b[k]), k
