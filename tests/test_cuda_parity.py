@@ -121,3 +121,21 @@ def test_production_step_matches_oracle(name):
     compare_step(out, new_o, im_o)
     assert np.array_equal(out['new']['idx'], z['out_idx'])
     np.testing.assert_allclose(out['N_rast_on_demand'], im_o['N_rast'], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('L,n_traits,lpt', [(100, 5, 7), (300, 8, 9), (1000, 3, 40)])
+def test_many_traits(L, n_traits, lpt):
+    """More than two traits (the reference allows any number, genome.py:826-867): the 8-accumulator
+    instantiations of the gamete / phenotype kernels, the wider packed (d, e...) raster record and
+    the z planes of the compaction, against the oracle -- staged and as the production step."""
+    from oracle import step_oracle as so
+    from parity_util import synthetic_case
+    arch, prm, state, draws = synthetic_case(L=L, n=1800, n_traits=n_traits, loci_per_trait=lpt, seed=50 + n_traits,
+                                             max_tries=24)
+    for t, tr in enumerate(arch['traits']):                  # spread the traits over the layers and exponents
+        tr['gamma'] = (1.0, 2.0, 1.5)[t % 3]
+        tr['phi'] = 0.03 + 0.02 * t
+    new_o, im_o = so.step(state, arch, prm, draws)
+    compare_step(run_device_step(arch, prm, state, draws, staged=True), new_o, im_o)
+    compare_step(run_device_step(arch, prm, state, draws, staged=False, debug=False), new_o, im_o)
+    assert new_o['z'].shape[1] == n_traits and im_o['B'] > 100
