@@ -179,7 +179,8 @@ class Landscape(dict):
         self.res = res
         self.ulc = ulc
         self.prj = prj
-        self._res_ratio = (res[0] / res[1], 1) if res[0] != res[1] else (1, 1)
+        # landscape.py:277-278: each axis' cell size relative to the larger one
+        self._res_ratio = tuple(float(abs(v / max(res))) for v in res)
         self._dim_om = len(str(max(self.dim)))
         self._changer = None
         self._listeners = []        # attached Species (device raster mirrors)

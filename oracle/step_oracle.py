@@ -854,7 +854,8 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
         direction = surface_directions(arch['move_surf'], cx0, cy0, draws['move_choice'][:n0])
     else:
         direction = draws['move_dir'][:n0]
-    x, y = move(state['x'], state['y'], direction, draws['move_dist'][:n0], land_dim)
+    res_ratio = tuple(arch.get('res_ratio', (1, 1)))        # landscape.py:277-278
+    x, y = move(state['x'], state['y'], direction, draws['move_dist'][:n0], land_dim, res_ratio)
     im['mv_x'], im['mv_y'], im['mv_age'] = x, y, age
     im['mv_e'] = sample_env(rasters, x, y)
     # a5/a6
@@ -888,7 +889,7 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
                                      draws['disp_choice'][:B]]
         else:
             ddir = draws['disp_dir'][:B]
-        ox, oy, tries = disperse(mid_x, mid_y, ddir, draws['disp_dist'][:B], land_dim)
+        ox, oy, tries = disperse(mid_x, mid_y, ddir, draws['disp_dist'][:B], land_dim, res_ratio)
         osex = newborn_sex(sexed, prm['sex_ratio_p'], draws['sex_u'][:B],
                            draws['sex_redraw_u'][:B])
     else:

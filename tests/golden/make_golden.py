@@ -103,7 +103,7 @@ CASES = {
                  mating_radius=2, b=0.5, sex=False, n_births_fixed=True, lam=1,
                  move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                  dom=False, max_age=None, phi=['raster', 0.08], gamma=[1.5, 1], seed=19,
-                 surfaces=False, main_steps=3, window_width=2.5),
+                 surfaces=False, main_steps=3, window_width=2.5, res=(2, 1)),
     # nearest-neighbour mating (spatial.py:194-203) and inverse-distance-weighted mate choice
     # (spatial.py:209-229)
     'nearest': dict(dim=(30, 30), N=700, K_factor=0.8, L=40, n_traits=1, trait_loci=[5],
@@ -145,6 +145,8 @@ def build_params(gnx, case, tmpdir='/tmp'):
     p = gnx.read_parameters_file(path)
     dim = c['dim']
     p['landscape']['main']['dim'] = dim
+    if c.get('res') is not None:
+        p['landscape']['main']['res'] = c['res']          # non-square cells: movement distances scale per axis
     rasts = [bumpy(dim, c['seed']), gradient(dim, 'x'), gradient(dim, 'y')]
     for n, r in enumerate(rasts):
         p['landscape']['layers']['lyr_%i' % n]['init']['defined']['rast'] = r
@@ -252,6 +254,7 @@ def capture_arch(spp, land):
     out['rasters'] = np.stack([land[l].rast for l in range(len(land))]).astype(np.float64)
     out['K'] = np.asarray(spp.K, dtype=np.float64)
     out['land_dim'] = np.array(land.dim, dtype=np.int64)
+    out['res_ratio'] = np.array(land._res_ratio, dtype=np.float64)
     out['ww'] = np.float64(spp._dens_grids.window_width)
     if spp._move_surf is not None:
         out['move_surf'] = np.asarray(spp._move_surf.surf)          # float16 [Y, X, A]

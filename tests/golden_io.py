@@ -23,6 +23,8 @@ def load_case(name):
                 ww=float(z['ww']), traits=traits, dom=z['dom'], paths=z['paths'],
                 move_surf=z['move_surf'] if 'move_surf' in z.files else None,
                 disp_surf=z['disp_surf'] if 'disp_surf' in z.files else None)
+    if 'res_ratio' in z.files:
+        arch['res_ratio'] = tuple(float(v) for v in z['res_ratio'])
     if 'mut_mu_neut' in z.files:
         arch['mutation'] = dict(mu_neut=float(z['mut_mu_neut']), mu_delet=float(z['mut_mu_delet']),
                                 trait_mus=[float(v) for v in z['mut_trait_mus']],

@@ -29,7 +29,7 @@ def make_device(arch, prm, capacity=None, seed=0, disp_tries=6, extra=None):
     p['K_layer'] = rasters.shape[0] - 1
     ga = dict(L=arch['paths'].shape[1], paths=arch['paths'], traits=arch['traits'], dom=arch['dom'])
     return DeviceSpecies(arch['land_dim'], rasters, p, ga, capacity=capacity, seed=seed,
-                         disp_tries_injected=disp_tries)
+                         disp_tries_injected=disp_tries, res_ratio=tuple(arch.get('res_ratio', (1.0, 1.0))))
 
 
 def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=True):

@@ -147,3 +147,13 @@ def test_landscape_change_series_is_numpy_linspace():
         assert lyr == 0
         assert np.array_equal(rast.ravel(), ref[:, k])
     assert np.array_equal(ch.changes[-1][2], end)
+
+
+def test_landscape_res_ratio_matches_reference_formula():
+    """landscape.py:277-278: each axis' cell size over the larger one (movement / dispersal
+    distances are scaled by it on rasters with non-square cells, movement.py:79-82)."""
+    from geonomics_b200 import api
+    lyr = {0: api.Layer(np.ones((4, 6)), 'x', 'l0', (6, 4))}
+    assert api.Landscape(lyr, res=(1, 1))._res_ratio == (1.0, 1.0)
+    assert api.Landscape(lyr, res=(2, 1))._res_ratio == (1.0, 0.5)
+    assert api.Landscape(lyr, res=(30, 90))._res_ratio == (30 / 90, 1.0)
