@@ -19,6 +19,12 @@ CONFIGS = {
     'c4': dict(dim=(4096, 4096), N=10_000_000, L=1000, n_traits=2, loci_per_trait=50, mating_radius=2.0,
                b=0.2, lam=1, R=0.5, phi=0.05, gamma=1.0, n_paths=10000, recomb_rate=0.5, seed=2024,
                surfaces=True),
+    # one species of configs[4]: 500k individuals, 10 000 loci at r = 1e-3 (20 of them trait loci),
+    # 1024x1024 -- the long-genome shape (1280-byte homologues); tskit recording is measured
+    # separately (tests/test_cuda_tskit.py), the reference cannot run this config at all
+    'c5': dict(dim=(1024, 1024), N=500_000, L=10_000, n_traits=1, loci_per_trait=20, mating_radius=2.0,
+               b=0.2, lam=1, R=0.5, phi=0.05, gamma=1.0, n_paths=10000, recomb_rate=1e-3, seed=5,
+               surfaces=False),
 }
 
 
