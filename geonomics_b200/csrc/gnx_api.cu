@@ -367,7 +367,7 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   const int Wq = ctx->Wq;
   std::vector<int32_t> te_locus;
   std::vector<double> te_alpha, te_dom;
-  struct TraitEntry { int32_t off, sh; double half_alpha; };      // Traits::te_pack
+  struct TraitEntry { int32_t off, mask; double half_alpha; };    // Traits::te_pack
   static_assert(sizeof(TraitEntry) == 16, "TraitEntry is one 128-bit load");
   std::vector<TraitEntry> te_pack;
   const int NW = 4 * Wq;      // CSR over 32-bit words
@@ -390,7 +390,7 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
       te_locus.push_back(locus);
       te_alpha.push_back(tr.host_alpha[k]);
       te_dom.push_back(host_dom ? 1.0 + (double)host_dom[locus] : 1.0);
-      te_pack.push_back(TraitEntry{(locus >> 5) * 8, locus & 31, 0.5 * tr.host_alpha[k]});
+      te_pack.push_back(TraitEntry{(locus >> 5) * 8, (int32_t)(1u << (locus & 31)), 0.5 * tr.host_alpha[k]});
     }
     while (q < NW) chunk_ptr[(size_t)t * (NW + 1) + (++q)] = (int32_t)te_locus.size();
     T.n_loci[t] = tr.n_loci;

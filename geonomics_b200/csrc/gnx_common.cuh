@@ -66,7 +66,7 @@ struct Traits {
   const int32_t* te_locus;
   const double* te_alpha;
   const double* te_dom;        // (1 + dom[locus]) factor, or NULL
-  const void* te_pack;         // per entry {int32 byte offset of the staged word pair, int32 shift, f64 alpha/2}
+  const void* te_pack;         // per entry {int32 byte offset of the staged word pair, uint32 bit mask, f64 alpha/2}
   const int32_t* chunk_ptr;
   int32_t n_loci[GNX_MAX_TRAITS];
   double phi[GNX_MAX_TRAITS];

@@ -694,15 +694,15 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
           if (fast_trait && poly) {
             // geno * alpha = (b0 + b1) * (alpha / 2), exact (selection.py:30-33, 43-44)
             const int4* __restrict__ tp = reinterpret_cast<const int4*>(tr.te_pack);
+            double acc1 = 0.0;                              // one accumulator per homologue
             for (int k = ks + lane; k < ke; k += GW) {
-              const int4 e = __ldg(tp + k);                 // {byte offset of the word pair, shift, alpha/2}
+              const int4 e = __ldg(tp + k);                 // {byte offset of the word pair, bit mask, alpha/2}
               const uint2 ww = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(row32) + e.x);
               const double ha = __hiloint2double(e.w, e.z);
-              double v = 0.0;
-              if ((ww.x >> e.y) & 1u) v = ha;
-              if ((ww.y >> e.y) & 1u) v += ha;
-              acc += v;
+              if (ww.x & (uint32_t)e.y) acc += ha;          // and + predicate in one LOP3, predicated DADD
+              if (ww.y & (uint32_t)e.y) acc1 += ha;
             }
+            acc += acc1;
           } else {
             for (int k = ks + lane; k < ke; k += GW) {
               const int loc = __ldg(&tr.te_locus[k]);
