@@ -78,6 +78,7 @@ struct gnx_ctx {
   double* d_K = nullptr;
   uint4* d_stage_genomes = nullptr;   // species-order staging for upload/download
   double* d_stage_z = nullptr;        // [n][T] row-major staging of phenotypes
+  bool pair_phenotype = false;      // every trait polygenic and no dominance: k_gametes may walk the trait table once per two offspring
   bool have_density = false, have_paths = false, have_traits = false, have_rasters = false;
   int64_t launches = 0;
   int burn = 0;
@@ -418,6 +419,8 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   const TraitEntry* d_pack = nullptr;
   if ((r = upload_vec(ctx, te_pack, &d_pack, ctx->trait_allocs)) != GNX_OK) return r;
   T.te_pack = d_pack;
+  ctx->pair_phenotype = !T.te_dom && n_traits > 0;
+  for (int t = 0; t < n_traits; ++t) if (traits[t].n_loci <= 1) ctx->pair_phenotype = false;
   ctx->have_traits = true;
   return pack_env(ctx);
 }
@@ -937,12 +940,14 @@ static int offspring_gametes(gnx_ctx* ctx) {
   do {                                                                                                    \
     /* child rows staged in shared memory for the phenotype when they fit (32 KB per block) */           \
     const size_t rows_b = (size_t)(256 / GW) * 2 * Wq * 16;                                               \
-    const int stage = (GW > 1 && ctx->cfg.n_traits > 0 && rows_b <= 32 * 1024) ? 1 : 0;                             \
+    /* 2 = two staged rows per group and one trait-table walk for both: every trait polygenic, no dominance */  \
+    int stage = (GW > 1 && ctx->cfg.n_traits > 0 && rows_b <= 32 * 1024) ? 1 : 0;                         \
+    if (stage && GW >= 2 && 2 * rows_b <= 40 * 1024 && ctx->pair_phenotype) stage = 2;                    \
     if (ctx->cfg.n_traits <= 2)                                                                           \
-      k_gametes<GW, 2><<<g, 256, stage ? rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,   \
+      k_gametes<GW, 2><<<g, 256, stage ? stage * rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,   \
                                                           ctx->work, ctx->d_c, fnb, stage);               \
     else                                                                                                  \
-      k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, stage ? rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits,  \
+      k_gametes<GW, GNX_MAX_TRAITS><<<g, 256, stage ? stage * rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits,  \
                                                                        ctx->draws, ctx->work, ctx->d_c,   \
                                                                        fnb, stage);                       \
   } while (0)

@@ -643,6 +643,92 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
     const BirthPlan mine = next;
     next = load_plan((ch + nwarps) * 32 + wl);
     if (ch * 32 + wl < B) pop.gslot[cur][n + ch * 32 + wl] = mine.cslot;
+  if (GW > 1 && stage_rows == 2) {
+    // Two offspring per group and pass: both rows are streamed and staged (buffers A and B), then
+    // ONE walk over the trait table serves both -- entry load, address arithmetic and loop
+    // control are paid once per two offspring.
+    uint32_t* const rowB = row32 + 4 * Wq * 2 * (blockDim.x / GW);
+#pragma unroll 1
+    for (int j = 0; j < GW; j += 2) {
+      int oo[2];
+      bool vv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int src = (j + u) * G + grp;
+        const int o = ch * 32 + src;
+        BirthPlan bp;
+        bp.s0 = __shfl_sync(0xffffffffu, mine.s0, src);
+        bp.s1 = __shfl_sync(0xffffffffu, mine.s1, src);
+        bp.cslot = __shfl_sync(0xffffffffu, mine.cslot, src);
+        bp.kk0 = __shfl_sync(0xffffffffu, mine.kk0, src);
+        bp.kk1 = __shfl_sync(0xffffffffu, mine.kk1, src);
+        oo[u] = o;
+        vv[u] = o < B;
+        if (!vv[u]) continue;
+        const uint4* P0 = pop.G + (size_t)bp.s0 * 2 * Wq;
+        const uint4* P1 = pop.G + (size_t)bp.s1 * 2 * Wq;
+        const uint4* M0 = prm.paths + (size_t)(bp.kk0 & 0x3fffffff) * Wq;
+        const uint4* M1 = prm.paths + (size_t)(bp.kk1 & 0x3fffffff) * Wq;
+        uint4* C = pop.G + (size_t)bp.cslot * 2 * Wq;
+        const uint32_t f0 = (bp.kk0 >> 30) ? 0xffffffffu : 0u, f1 = (bp.kk1 >> 30) ? 0xffffffffu : 0u;
+        uint4* const stg = reinterpret_cast<uint4*>(u ? rowB : row32);
+        for (int q = lane; q < Wq; q += GW) {
+          const uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
+          const uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
+          uint4 m0 = __ldg(M0 + q), m1 = __ldg(M1 + q);
+          m0 = make_uint4(m0.x ^ f0, m0.y ^ f0, m0.z ^ f0, m0.w ^ f0);
+          m1 = make_uint4(m1.x ^ f1, m1.y ^ f1, m1.z ^ f1, m1.w ^ f1);
+          const uint4 g0 = bitsel(a0, a1, m0), g1 = bitsel(b0, b1, m1);
+          st_stream(C + q, g0);
+          st_stream(C + Wq + q, g1);
+          stg[2 * q] = make_uint4(g0.x, g1.x, g0.y, g1.y);
+          stg[2 * q + 1] = make_uint4(g0.z, g1.z, g0.w, g1.w);
+        }
+      }
+      if (!vv[0]) continue;                  // uniform over the group (offspring j+1 is then invalid too)
+      __syncwarp(gmask);
+      const int NW = 4 * Wq;
+      double zA[NT], zB[NT];
+#pragma unroll
+      for (int tt = 0; tt < NT; ++tt) {
+        zA[tt] = zB[tt] = 0.0;
+        if (tt < T) {
+          const int ks = __ldg(&tr.chunk_ptr[tt * (NW + 1)]), ke = __ldg(&tr.chunk_ptr[tt * (NW + 1) + NW]);
+          const int4* __restrict__ tp = reinterpret_cast<const int4*>(tr.te_pack);
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+          for (int k = ks + lane; k < ke; k += GW) {
+            const int4 e = __ldg(tp + k);                 // {byte offset of the word pair, bit mask, alpha/2}
+            const uint2 wa = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(row32) + e.x);
+            const uint2 wb = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(rowB) + e.x);
+            const double ha = __hiloint2double(e.w, e.z);
+            if (wa.x & (uint32_t)e.y) a0 += ha;
+            if (wa.y & (uint32_t)e.y) a1 += ha;
+            if (wb.x & (uint32_t)e.y) b0 += ha;
+            if (wb.y & (uint32_t)e.y) b1 += ha;
+          }
+          zA[tt] = a0 + a1;
+          zB[tt] = b0 + b1;
+        }
+      }
+      __syncwarp(gmask);      // the rows are rewritten by the next pair of offspring
+#pragma unroll
+      for (int tt = 0; tt < NT; ++tt) {
+        if (tt < T) {
+          double va = zA[tt], vb = zB[tt];
+#pragma unroll
+          for (int d = GW / 2; d >= 1; d >>= 1) {
+            va += __shfl_xor_sync(gmask, va, d);
+            vb += __shfl_xor_sync(gmask, vb, d);
+          }
+          if (lane == 0) {
+            pop.z[cur][(size_t)tt * pop.cap + n + oo[0]] = 0.5 + va;
+            if (vv[1]) pop.z[cur][(size_t)tt * pop.cap + n + oo[1]] = 0.5 + vb;
+          }
+        }
+      }
+    }
+    continue;
+  }
 #pragma unroll 1
   for (int j = 0; j < GW; ++j) {
     const int src = j * G + grp;
