@@ -942,7 +942,8 @@ static int offspring_gametes(gnx_ctx* ctx) {
     const size_t rows_b = (size_t)(256 / GW) * 2 * Wq * 16;                                               \
     /* 2 = two staged rows per group and one trait-table walk for both: every trait polygenic, no dominance */  \
     int stage = (GW > 1 && ctx->cfg.n_traits > 0 && rows_b <= 32 * 1024) ? 1 : 0;                         \
-    if (stage && GW >= 2 && 2 * rows_b <= 40 * 1024 && ctx->pair_phenotype) stage = 2;                    \
+    { constexpr int NB = (GNX_GAM_NB < GW) ? GNX_GAM_NB : GW;                                              \
+      if (stage && NB >= 2 && NB * rows_b <= 44 * 1024 && ctx->pair_phenotype) stage = NB; }              \
     if (ctx->cfg.n_traits <= 2)                                                                           \
       k_gametes<GW, 2><<<g, 256, stage ? stage * rows_b : 0, s>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws,   \
                                                           ctx->work, ctx->d_c, fnb, stage);               \

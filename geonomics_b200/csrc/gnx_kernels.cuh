@@ -576,6 +576,9 @@ struct BirthPlan {
   int s0, s1, cslot, kk0, kk1;     // parents' slots, child slot, key | start << 30
 };
 
+#ifndef GNX_GAM_NB
+#define GNX_GAM_NB 2           // offspring per trait-table walk in the staged path
+#endif
 #ifndef GNX_GAM_MINB
 #define GNX_GAM_MINB 4          // 64 registers: 4 CTAs per SM measured fastest (3, 5, 6 are slower)
 #endif
@@ -643,17 +646,18 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
     const BirthPlan mine = next;
     next = load_plan((ch + nwarps) * 32 + wl);
     if (ch * 32 + wl < B) pop.gslot[cur][n + ch * 32 + wl] = mine.cslot;
-  if (GW > 1 && stage_rows == 2) {
-    // Two offspring per group and pass: both rows are streamed and staged (buffers A and B), then
-    // ONE walk over the trait table serves both -- entry load, address arithmetic and loop
-    // control are paid once per two offspring.
-    uint32_t* const rowB = row32 + 4 * Wq * 2 * (blockDim.x / GW);
+  if (GW > 1 && stage_rows >= 2) {
+    // NB offspring per group and pass: their rows are streamed and staged (one buffer each), then
+    // ONE walk over the trait table serves all of them -- entry load, address arithmetic and
+    // loop control are paid once per NB offspring.
+    constexpr int NB = (GNX_GAM_NB < GW) ? GNX_GAM_NB : GW;
+    const int buf_stride = 8 * Wq * (blockDim.x / GW);       // uint32 words between the staging buffers
 #pragma unroll 1
-    for (int j = 0; j < GW; j += 2) {
-      int oo[2];
-      bool vv[2];
+    for (int j = 0; j < GW; j += NB) {
+      int oo[NB];
+      bool vv[NB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < NB; ++u) {
         const int src = (j + u) * G + grp;
         const int o = ch * 32 + src;
         BirthPlan bp;
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
         const uint4* M1 = prm.paths + (size_t)(bp.kk1 & 0x3fffffff) * Wq;
         uint4* C = pop.G + (size_t)bp.cslot * 2 * Wq;
         const uint32_t f0 = (bp.kk0 >> 30) ? 0xffffffffu : 0u, f1 = (bp.kk1 >> 30) ? 0xffffffffu : 0u;
-        uint4* const stg = reinterpret_cast<uint4*>(u ? rowB : row32);
+        uint4* const stg = reinterpret_cast<uint4*>(row32 + u * buf_stride);
         for (int q = lane; q < Wq; q += GW) {
           const uint4 a0 = ld_stream(P0 + q), a1 = ld_stream(P0 + Wq + q);
           const uint4 b0 = ld_stream(P1 + q), b1 = ld_stream(P1 + Wq + q);
@@ -685,44 +689,45 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
           stg[2 * q + 1] = make_uint4(g0.z, g1.z, g0.w, g1.w);
         }
       }
-      if (!vv[0]) continue;                  // uniform over the group (offspring j+1 is then invalid too)
+      if (!vv[0]) continue;                  // uniform over the group (the later ones are then invalid too)
       __syncwarp(gmask);
       const int NW = 4 * Wq;
-      double zA[NT], zB[NT];
+      double zz[NT][NB];
 #pragma unroll
       for (int tt = 0; tt < NT; ++tt) {
-        zA[tt] = zB[tt] = 0.0;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) zz[tt][u] = 0.0;
         if (tt < T) {
           const int ks = __ldg(&tr.chunk_ptr[tt * (NW + 1)]), ke = __ldg(&tr.chunk_ptr[tt * (NW + 1) + NW]);
           const int4* __restrict__ tp = reinterpret_cast<const int4*>(tr.te_pack);
-          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+          double h0[NB], h1[NB];             // one accumulator per offspring and homologue
+#pragma unroll
+          for (int u = 0; u < NB; ++u) h0[u] = h1[u] = 0.0;
           for (int k = ks + lane; k < ke; k += GW) {
             const int4 e = __ldg(tp + k);                 // {byte offset of the word pair, bit mask, alpha/2}
-            const uint2 wa = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(row32) + e.x);
-            const uint2 wb = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(rowB) + e.x);
             const double ha = __hiloint2double(e.w, e.z);
-            if (wa.x & (uint32_t)e.y) a0 += ha;
-            if (wa.y & (uint32_t)e.y) a1 += ha;
-            if (wb.x & (uint32_t)e.y) b0 += ha;
-            if (wb.y & (uint32_t)e.y) b1 += ha;
+            const char* base = reinterpret_cast<const char*>(row32) + e.x;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+              const uint2 ww = *reinterpret_cast<const uint2*>(base + 4 * u * buf_stride);
+              if (ww.x & (uint32_t)e.y) h0[u] += ha;      // and + predicate in one LOP3, predicated DADD
+              if (ww.y & (uint32_t)e.y) h1[u] += ha;
+            }
           }
-          zA[tt] = a0 + a1;
-          zB[tt] = b0 + b1;
+#pragma unroll
+          for (int u = 0; u < NB; ++u) zz[tt][u] = h0[u] + h1[u];
         }
       }
-      __syncwarp(gmask);      // the rows are rewritten by the next pair of offspring
+      __syncwarp(gmask);      // the rows are rewritten by the next batch of offspring
 #pragma unroll
       for (int tt = 0; tt < NT; ++tt) {
         if (tt < T) {
-          double va = zA[tt], vb = zB[tt];
 #pragma unroll
-          for (int d = GW / 2; d >= 1; d >>= 1) {
-            va += __shfl_xor_sync(gmask, va, d);
-            vb += __shfl_xor_sync(gmask, vb, d);
-          }
-          if (lane == 0) {
-            pop.z[cur][(size_t)tt * pop.cap + n + oo[0]] = 0.5 + va;
-            if (vv[1]) pop.z[cur][(size_t)tt * pop.cap + n + oo[1]] = 0.5 + vb;
+          for (int u = 0; u < NB; ++u) {
+            double v = zz[tt][u];
+#pragma unroll
+            for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
+            if (lane == 0 && vv[u]) pop.z[cur][(size_t)tt * pop.cap + n + oo[u]] = 0.5 + v;
           }
         }
       }
