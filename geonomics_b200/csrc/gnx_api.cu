@@ -636,6 +636,12 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
     }
     if ((r = up(aff.data(), sizeof(double) * aff.size(), (const void**)&D.tri_aff))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
+    double* tri_g = nullptr;
+    DM(ctx, &tri_g, (size_t)3 * D.ntri, &ctx->dens_allocs);
+    k_ct_setup_g<<<std::max(1, (D.ntri + 127) / 128), 128, 0, ctx->stream>>>(D, tri_g);
+    CK(cudaGetLastError());
+    D.tri_g = tri_g;
+    CK(cudaStreamSynchronize(ctx->stream));
     static double mono[3 * 10 * 19];
     ct_build_mono(mono);
     CK(cudaMemcpyToSymbol(CT_MONO, mono, sizeof mono));

@@ -113,6 +113,7 @@ struct Dens {
   int32_t lat_ni, lat_nj;
   const int32_t* square_tri;
   const double* tri_aff;   // [ntri][6]: b0 = a0 + a1*qi + a2*qj, b1 = a3 + a4*qi + a5*qj
+  const double* tri_g;     // [ntri][3]: static Clough-Tocher neighbour weights (k_ct_setup_g)
   int32_t colourable;
   // work
   int32_t* counts;   // [2][npts]

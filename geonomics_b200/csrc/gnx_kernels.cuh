@@ -1472,6 +1472,40 @@ __global__ void __launch_bounds__(GS_BLOCK) k_ct_gradients(Dens d, Counters* c, 
 __constant__ double CT_MONO[3 * 10 * 19];      // set by gnx_set_density
 #define CT_STRIDE 49                           // per triangle: 3 x 10 monomial coefficients + 19 Bezier ordinates
 
+// g weights of `_clough_tocher_2d_single` (scipy interpnd): they depend on the triangulation only,
+// so they are computed once at setup with the arithmetic the coefficient kernel used to repeat
+// every step (9 divisions and ~30 dependent loads per triangle)
+__global__ void __launch_bounds__(128) k_ct_setup_g(Dens d, double* tri_g) {
+  for (int t = GTID; t < d.ntri; t += GSTRIDE) {
+    const double* P = d.points;
+    const int v0 = d.simplices[3 * t], v1 = d.simplices[3 * t + 1], v2 = d.simplices[3 * t + 2];
+    // barycentric transform of this triangle: b = Ainv (p - v2)
+    const double a00 = P[2 * v0] - P[2 * v2], a01 = P[2 * v1] - P[2 * v2];
+    const double a10 = P[2 * v0 + 1] - P[2 * v2 + 1], a11 = P[2 * v1 + 1] - P[2 * v2 + 1];
+    const double det = a00 * a11 - a01 * a10;
+    double g[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int itri = d.neighbors[3 * t + k];
+      if (itri == -1) { g[k] = -0.5; continue; }
+      const int w0 = d.simplices[3 * itri], w1 = d.simplices[3 * itri + 1], w2 = d.simplices[3 * itri + 2];
+      const double y0 = (P[2 * w0] + P[2 * w1] + P[2 * w2]) / 3;
+      const double y1 = (P[2 * w0 + 1] + P[2 * w1 + 1] + P[2 * w2 + 1]) / 3;
+      const double dx = y0 - P[2 * v2], dy = y1 - P[2 * v2 + 1];
+      double cc[3];
+      cc[0] = (a11 * dx - a01 * dy) / det;
+      cc[1] = (-a10 * dx + a00 * dy) / det;
+      cc[2] = 1 - cc[0] - cc[1];
+      if (k == 0) g[k] = (2 * cc[2] + cc[1] - 1) / (2 - 3 * cc[2] - 3 * cc[1]);
+      else if (k == 1) g[k] = (2 * cc[0] + cc[2] - 1) / (2 - 3 * cc[0] - 3 * cc[2]);
+      else g[k] = (2 * cc[1] + cc[0] - 1) / (2 - 3 * cc[1] - 3 * cc[0]);
+    }
+    tri_g[3 * t] = g[0];
+    tri_g[3 * t + 1] = g[1];
+    tri_g[3 * t + 2] = g[2];
+  }
+}
+
 // Bezier ordinates of every triangle (`_clough_tocher_2d_single`, point-independent part)
 __global__ void __launch_bounds__(128) k_ct_coefficients(Dens d) {
   // 3 threads per (density, triangle): each converts the ordinates to one micro-triangle's monomials
@@ -1505,27 +1539,8 @@ __global__ void __launch_bounds__(128) k_ct_coefficients(Dens d) {
     const double c2001 = (c2100 + c2010 + c3000) / 3;
     const double c0201 = (c1200 + c0300 + c0210) / 3;
     const double c0021 = (c1020 + c0120 + c0030) / 3;
-    // barycentric transform of this triangle: b = Ainv (p - v2)
-    const double a00 = P[2 * v0] - P[2 * v2], a01 = P[2 * v1] - P[2 * v2];
-    const double a10 = P[2 * v0 + 1] - P[2 * v2 + 1], a11 = P[2 * v1 + 1] - P[2 * v2 + 1];
-    const double det = a00 * a11 - a01 * a10;
-    double g[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int itri = d.neighbors[3 * t + k];
-      if (itri == -1) { g[k] = -0.5; continue; }
-      const int w0 = d.simplices[3 * itri], w1 = d.simplices[3 * itri + 1], w2 = d.simplices[3 * itri + 2];
-      const double y0 = (P[2 * w0] + P[2 * w1] + P[2 * w2]) / 3;
-      const double y1 = (P[2 * w0 + 1] + P[2 * w1 + 1] + P[2 * w2 + 1]) / 3;
-      const double dx = y0 - P[2 * v2], dy = y1 - P[2 * v2 + 1];
-      double cc[3];
-      cc[0] = (a11 * dx - a01 * dy) / det;
-      cc[1] = (-a10 * dx + a00 * dy) / det;
-      cc[2] = 1 - cc[0] - cc[1];
-      if (k == 0) g[k] = (2 * cc[2] + cc[1] - 1) / (2 - 3 * cc[2] - 3 * cc[1]);
-      else if (k == 1) g[k] = (2 * cc[0] + cc[2] - 1) / (2 - 3 * cc[0] - 3 * cc[2]);
-      else g[k] = (2 * cc[1] + cc[0] - 1) / (2 - 3 * cc[1] - 3 * cc[0]);
-    }
+    // the neighbour-dependent weights g are static (triangulation only): precomputed by k_ct_setup_g
+    const double g[3] = {d.tri_g[3 * t], d.tri_g[3 * t + 1], d.tri_g[3 * t + 2]};
     const double c0111 = (g[0] * (-c0300 + 3 * c0210 - 3 * c0120 + c0030) + (-c0300 + 2 * c0210 - c0120 + c0021 + c0201)) / 2;
     const double c1011 = (g[1] * (-c0030 + 3 * c1020 - 3 * c2010 + c3000) + (-c0030 + 2 * c1020 - c2010 + c2001 + c0021)) / 2;
     const double c1101 = (g[2] * (-c3000 + 3 * c2100 - 3 * c1200 + c0300) + (-c3000 + 2 * c2100 - c1200 + c2001 + c0201)) / 2;
