@@ -102,6 +102,22 @@ static int dmalloc(gnx_ctx* ctx, T** p, size_t count, std::vector<void*>* bucket
   } while (0)
 
 static inline int grid_for(const gnx_ctx* ctx, int per_sm) { return ctx->num_sms * per_sm; }
+// experiment knobs: CTAs per SM of the grid-stride kernels whose per-item cost varies
+#ifndef GNX_G_AGE
+#define GNX_G_AGE 8
+#endif
+#ifndef GNX_G_NEWB
+#define GNX_G_NEWB 8
+#endif
+#ifndef GNX_G_DEATH
+#define GNX_G_DEATH 32
+#endif
+#ifndef GNX_G_SORT
+#define GNX_G_SORT 8
+#endif
+#ifndef GNX_G_GATHER
+#define GNX_G_GATHER 8
+#endif
 
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the ctx stream around
 // every launch, accumulated by kernel name.
@@ -849,7 +865,7 @@ static int age_move_bin(gnx_ctx* ctx, int do_age, int do_move, int do_bin) {
     return GNX_ERR_STATE;
   }
   PROF(ctx, "k_age_move_bin");
-  k_age_move_bin<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+  k_age_move_bin<<<grid_for(ctx, GNX_G_AGE), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
                                                            ctx->d_c, do_age, do_move, do_bin);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -868,13 +884,13 @@ static int finish_binning(gnx_ctx* ctx) {
   if (r != GNX_OK) return r;
   cudaStream_t s = ctx->stream;
   PROF(ctx, "k_scatter_perm");
-  k_scatter_perm<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->d_c);
+  k_scatter_perm<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   PROF(ctx, "k_cell_sort");
-  k_cell_sort<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->work, ctx->ncell);
+  k_cell_sort<<<grid_for(ctx, GNX_G_SORT), 256, 0, s>>>(ctx->work, ctx->ncell);
   LAUNCHED(ctx);
   PROF(ctx, "k_gather_sorted");
-  k_gather_sorted<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c);
+  k_gather_sorted<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -896,8 +912,14 @@ extern "C" int gnx_find_mates(gnx_ctx* ctx) {
     return GNX_OK;
   }
   PROF(ctx, "k_find_mates");
-  const int g = grid_for(ctx, 16);
-#define FM(MODE) k_find_mates<MODE><<<g, 128, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
+#ifndef GNX_FM_GRID
+#define GNX_FM_GRID 128
+#endif
+#ifndef GNX_FM_BLOCK
+#define GNX_FM_BLOCK 128
+#endif
+  const int g = grid_for(ctx, GNX_FM_GRID);
+#define FM(MODE) k_find_mates<MODE><<<g, GNX_FM_BLOCK, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
   if (ctx->cfg.choose_nearest) FM(1);
   else if (ctx->cfg.inverse_dist) FM(2);
   else FM(0);
@@ -998,7 +1020,7 @@ static int offspring_gametes(gnx_ctx* ctx) {
 
 static int offspring_newborns(gnx_ctx* ctx) {
   PROF(ctx, "k_newborns");
-  k_newborns<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+  k_newborns<<<grid_for(ctx, GNX_G_NEWB), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
                                                         ctx->d_c, ctx->tsk);
   LAUNCHED(ctx);
   return GNX_OK;
@@ -1195,7 +1217,7 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
 extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   PROF(ctx, "k_death");
-  k_death<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
+  k_death<<<grid_for(ctx, GNX_G_DEATH), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
                                                     ctx->work, ctx->d_c, ctx->mut);
   LAUNCHED(ctx);
   return GNX_OK;

@@ -202,7 +202,15 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Co
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(128) k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
+#ifndef GNX_FM_BLOCK
+#define GNX_FM_BLOCK 128
+#endif
+#ifdef GNX_FM_MINB
+#define GNX_FM_BOUNDS __launch_bounds__(GNX_FM_BLOCK, GNX_FM_MINB)
+#else
+#define GNX_FM_BOUNDS __launch_bounds__(GNX_FM_BLOCK)
+#endif
+__global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                      const Counters* c) {
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
