@@ -118,6 +118,9 @@ static inline int grid_for(const gnx_ctx* ctx, int per_sm) { return ctx->num_sms
 #ifndef GNX_G_GATHER
 #define GNX_G_GATHER 8
 #endif
+#ifndef GNX_G_SCAN
+#define GNX_G_SCAN 8
+#endif
 
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the ctx stream around
 // every launch, accumulated by kernel name.
@@ -848,12 +851,12 @@ static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   char nm[64];
   snprintf(nm, sizeof nm, "%s.reduce", name);
   PROF(ctx, nm);
-  scan_reduce_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums,
+  scan_reduce_kernel<F><<<grid_for(ctx, GNX_G_SCAN), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums,
                                                                 ctx->work.scan_ticket);
   LAUNCHED(ctx);
   snprintf(nm, sizeof nm, "%s.apply", name);
   PROF(ctx, nm);
-  scan_apply_kernel<F><<<grid_for(ctx, 8), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
+  scan_apply_kernel<F><<<grid_for(ctx, GNX_G_SCAN), SCAN_BLOCK, 0, s>>>(f, ctx->d_c, ctx->work.tile_sums);
   LAUNCHED(ctx);
   return GNX_OK;
 }
