@@ -55,6 +55,7 @@ struct gnx_ctx {
   int num_sms = 148;
   int Wq = 0, Wwords = 0;
   int ncell = 0;
+  int64_t n_hint = 0;               // last population size seen by the host (grid sizing only)
   Pop pop{};
   Land land{};
   Traits traits{};
@@ -102,6 +103,17 @@ static int dmalloc(gnx_ctx* ctx, T** p, size_t count, std::vector<void*>* bucket
   } while (0)
 
 static inline int grid_for(const gnx_ctx* ctx, int per_sm) { return ctx->num_sms * per_sm; }
+// Grid for a grid-stride kernel whose per-item cost varies (mate search, death): many CTAs let
+// the hardware even out the load, but never more than ~one item per thread for the population
+// the host last saw (n_hint; the kernels read the true size on the device, so an estimate that
+// is off only changes the number of passes).  Matters when several small replicate populations
+// share a GPU: their launches must not each carry thousands of empty CTAs.
+static inline int grid_cap(const gnx_ctx* ctx, int per_sm, int threads, double scale = 1.0) {
+  const long long want = (long long)std::ceil((double)ctx->n_hint * 1.25 * scale / threads);
+  const long long hi = (long long)ctx->num_sms * per_sm;
+  if (ctx->n_hint <= 0) return (int)hi;
+  return (int)std::max<long long>(ctx->num_sms, std::min(hi, want));
+}
 // experiment knobs: CTAs per SM of the grid-stride kernels whose per-item cost varies
 #ifndef GNX_G_AGE
 #define GNX_G_AGE 8
@@ -738,6 +750,7 @@ extern "C" int gnx_set_burn(gnx_ctx* ctx, int32_t burn) {
 static int read_counters(gnx_ctx* ctx, Counters* h) {
   CK(cudaMemcpyAsync(h, ctx->d_c, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n_hint = std::max(h->n, h->n_pre);
   return GNX_OK;
 }
 
@@ -756,6 +769,7 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
   ARG(pop->n >= 0 && pop->n <= ctx->cfg.capacity, "population larger than capacity");
   ARG(pop->x && pop->y, "x/y required");
   const size_t n = (size_t)pop->n;
+  ctx->n_hint = pop->n;
   cudaStream_t s = ctx->stream;
   Pop& P = ctx->pop;
   // everything below is asynchronous on the ctx stream: no host-side staging loops
@@ -921,7 +935,7 @@ extern "C" int gnx_find_mates(gnx_ctx* ctx) {
 #ifndef GNX_FM_BLOCK
 #define GNX_FM_BLOCK 128
 #endif
-  const int g = grid_for(ctx, GNX_FM_GRID);
+  const int g = grid_cap(ctx, GNX_FM_GRID, GNX_FM_BLOCK);
 #define FM(MODE) k_find_mates<MODE><<<g, GNX_FM_BLOCK, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
   if (ctx->cfg.choose_nearest) FM(1);
   else if (ctx->cfg.inverse_dist) FM(2);
@@ -1220,7 +1234,7 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
 extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   PROF(ctx, "k_death");
-  k_death<<<grid_for(ctx, GNX_G_DEATH), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
+  k_death<<<grid_cap(ctx, GNX_G_DEATH, 256, 1.0 + ctx->cfg.b * ctx->cfg.n_births_lambda), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
                                                     ctx->work, ctx->d_c, ctx->mut);
   LAUNCHED(ctx);
   return GNX_OK;
