@@ -203,6 +203,8 @@ SIGNATURES = {
     'gnx_device_ptr': (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_void_p), c_int64_p]),
     'gnx_stream': (C.c_void_p, [_ctx]),
     'gnx_launch_count': (C.c_int64, [_ctx]),
+    'gnx_graph_launch_count': (C.c_int64, [_ctx]),
+    'gnx_graph_capture_count': (C.c_int64, [_ctx]),
     'gnx_profile': (C.c_int, [_ctx, C.c_int32]),
     'gnx_profile_report': (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
 }

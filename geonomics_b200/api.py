@@ -477,7 +477,8 @@ def _make_conductance_surface(rast, mixture=True, approx_len=5000, vm_distr_kapp
         mx = neigh.max(axis=-1, keepdims=True)
         is_max = neigh == mx
         loc = ((is_max * dirs).sum(axis=-1) / is_max.sum(axis=-1))[..., None] * np.ones((1, 1, approx_len))
-    surf = loc + np.random.vonmises(0, vm_distr_kappa, size=(Y, X, approx_len))
+    # scipy.stats.vonmises.rvs(kappa, loc=loc) wraps onto [-pi, pi) (scipy >= 1.11)
+    surf = np.mod(loc + np.random.vonmises(0, vm_distr_kappa, size=(Y, X, approx_len)) + pi, 2 * pi) - pi
     return np.float16(surf)
 
 

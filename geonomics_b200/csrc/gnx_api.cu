@@ -31,6 +31,8 @@ static thread_local std::string g_last_error;
     }                                                                                        \
   } while (0)
 
+#define USE_DEVICE(ctx) CK(cudaSetDevice((ctx)->device))
+
 struct ProfSpan {
   std::string name;
   cudaEvent_t e0, e1;
@@ -71,7 +73,7 @@ struct gnx_ctx {
   std::vector<void*> tsk_allocs;
   Counters* d_c = nullptr;
   std::vector<void*> allocs;        // everything cudaMalloc'ed for the ctx lifetime
-  std::vector<void*> draw_allocs;   // injected-draw buffers
+  std::vector<std::pair<void*, size_t>> draw_bufs;   // injected-draw buffers (pointer, capacity), one per site
   std::vector<void*> trait_allocs;
   std::vector<void*> dens_allocs;
   double* d_rasters = nullptr;
@@ -84,6 +86,11 @@ struct gnx_ctx {
   int64_t launches = 0;
   int burn = 0;
   int host_n_hint = 0;
+  bool gs_attr_set = false;
+  int64_t records_pending = 0;          // step records written since the last gnx_read_step_records
+  int64_t graph_launches = 0, graph_captures = 0;
+  void* d_paths = nullptr;
+  void* d_surf_tab[2] = {nullptr, nullptr};
 };
 
 template <class T>
@@ -181,6 +188,9 @@ static void mating_grid(const gnx_config_t& c, double* cs, int* ncx, int* ncy) {
   *ncy = (int)(c.dim_y / s) + 1;
 }
 
+static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx);
+extern "C" int gnx_destroy(gnx_ctx* ctx);
+
 extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   ARG(cfg && out, "null cfg/out");
   ARG(cfg->abi_version == GNX_ABI_VERSION, "abi_version mismatch");
@@ -193,6 +203,18 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   if (ndev == 0) { g_last_error = "no CUDA device"; return GNX_ERR_CUDA; }
   gnx_ctx* ctx = new gnx_ctx();
   ctx->cfg = *cfg;
+  const int r = create_impl(cfg, ctx);
+  if (r != GNX_OK) {                       // streams, events and every buffer allocated so far
+    const std::string keep = g_last_error;
+    gnx_destroy(ctx);
+    g_last_error = keep;
+    return r;
+  }
+  *out = ctx;
+  return GNX_OK;
+}
+
+static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   CK(cudaGetDevice(&ctx->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ctx->device));
@@ -296,7 +318,6 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = std::max(1, cfg->disp_max_tries_injected);
   CK(cudaStreamSynchronize(ctx->stream));
-  *out = ctx;
   return GNX_OK;
 }
 
@@ -307,14 +328,18 @@ static void free_bucket(std::vector<void*>& b) {
 
 extern "C" int gnx_destroy(gnx_ctx* ctx) {
   if (!ctx) return GNX_OK;
-  cudaStreamSynchronize(ctx->stream);
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_bucket(ctx->allocs);
-  free_bucket(ctx->draw_allocs);
+  for (auto& b : ctx->draw_bufs) if (b.first) cudaFree(b.first);
+  ctx->draw_bufs.clear();
   free_bucket(ctx->trait_allocs);
   free_bucket(ctx->dens_allocs);
   free_bucket(ctx->tsk_allocs);
   free_bucket(ctx->mut_allocs);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->d_paths) cudaFree(ctx->d_paths);
+  for (int k = 0; k < 2; ++k) if (ctx->d_surf_tab[k]) cudaFree(ctx->d_surf_tab[k]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -356,6 +381,7 @@ static int set_K(gnx_ctx* ctx) {
 
 extern "C" int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters) {
   ARG(ctx && host_rasters, "null");
+  USE_DEVICE(ctx);
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   CK(cudaMemcpyAsync(ctx->d_rasters, host_rasters, plane * ctx->cfg.n_layers * sizeof(double),
                      cudaMemcpyHostToDevice, ctx->stream));
@@ -368,6 +394,7 @@ extern "C" int gnx_set_rasters(gnx_ctx* ctx, const double* host_rasters) {
 
 extern "C" int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_raster) {
   ARG(ctx && host_raster && layer >= 0 && layer < ctx->cfg.n_layers, "layer");
+  USE_DEVICE(ctx);
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   CK(cudaMemcpyAsync(ctx->d_rasters + plane * layer, host_raster, plane * sizeof(double), cudaMemcpyHostToDevice,
                      ctx->stream));
@@ -391,6 +418,7 @@ static int upload_vec(gnx_ctx* ctx, const std::vector<T>& v, const T** dev, std:
 
 extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t* traits, const int8_t* host_dom) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   ARG(n_traits == ctx->cfg.n_traits, "n_traits differs from config");
   CK(cudaStreamSynchronize(ctx->stream));
   free_bucket(ctx->trait_allocs);
@@ -458,10 +486,14 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
 
 extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_paths) {
   ARG(ctx && host_packed_paths, "null");
+  USE_DEVICE(ctx);
   ARG(ctx->cfg.n_recomb_paths > 0, "n_recomb_paths");
   uint4* d = nullptr;
   const size_t n = (size_t)ctx->cfg.n_recomb_paths * ctx->Wq;
-  DM(ctx, &d, n);
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_paths) { cudaFree(ctx->d_paths); ctx->d_paths = nullptr; }
+  CK(cudaMalloc((void**)&d, std::max<size_t>(n, 1) * sizeof(uint4)));
+  ctx->d_paths = d;
   CK(cudaMemcpyAsync(d, host_packed_paths, n * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prm.paths = d;
@@ -472,18 +504,19 @@ extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_pa
 
 extern "C" int gnx_set_surface_tables(gnx_ctx* ctx, const uint16_t* host_move_f16, const uint16_t* host_disp_f16) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   const size_t n = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y * std::max(1, ctx->cfg.surf_approx_len);
-  if (host_move_f16) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint16_t* src[2] = {host_move_f16, host_disp_f16};
+  for (int k = 0; k < 2; ++k) {
+    if (!src[k]) continue;
+    // a changed layer re-builds its table (change.py:597-606): the old buffer is released
+    if (ctx->d_surf_tab[k]) { cudaFree(ctx->d_surf_tab[k]); ctx->d_surf_tab[k] = nullptr; }
     __half* d = nullptr;
-    DM(ctx, &d, n);
-    CK(cudaMemcpyAsync(d, host_move_f16, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prm.move_tab = d;
-  }
-  if (host_disp_f16) {
-    __half* d = nullptr;
-    DM(ctx, &d, n);
-    CK(cudaMemcpyAsync(d, host_disp_f16, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prm.disp_tab = d;
+    CK(cudaMalloc((void**)&d, n * 2));
+    ctx->d_surf_tab[k] = d;
+    CK(cudaMemcpyAsync(d, src[k], n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    (k == 0 ? ctx->prm.move_tab : ctx->prm.disp_tab) = d;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
@@ -548,6 +581,7 @@ static void ct_build_mono(double* M /* [3][10][19] */) {
 
 extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
   ARG(ctx && dn, "null");
+  USE_DEVICE(ctx);
   ARG(dn->n_points > 0 && dn->n_tri > 0, "empty triangulation");
   CK(cudaStreamSynchronize(ctx->stream));
   free_bucket(ctx->dens_allocs);
@@ -691,21 +725,33 @@ extern "C" int gnx_set_density(gnx_ctx* ctx, const gnx_density_t* dn) {
 
 extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
-  free_bucket(ctx->draw_allocs);
   const int R = ctx->draws.disp_R;
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = R;
   if (!dr) return GNX_OK;
   const size_t n = (size_t)dr->n;
   ctx->draws.n = dr->n;
+  // One device buffer per site, kept across calls and re-used while it is large enough: the
+  // device pointers (kernel arguments) then stay the same from step to step, so a multi-step
+  // injected-draw run keeps re-launching the SAME captured graph (tests/test_cuda_multistep.py).
+  int slot = 0;
   auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+    const int k = slot++;
     if (!src) { *dst = nullptr; return GNX_OK; }
-    void* d = nullptr;
-    CK(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
-    ctx->draw_allocs.push_back(d);
-    CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    *dst = d;
+    if ((int)ctx->draw_bufs.size() <= k) ctx->draw_bufs.resize(k + 1, {nullptr, 0});
+    auto& b = ctx->draw_bufs[k];
+    bytes = std::max<size_t>(bytes, 8);
+    if (b.second < bytes) {
+      if (b.first) cudaFree(b.first);
+      b = {nullptr, 0};
+      void* d = nullptr;
+      CK(cudaMalloc(&d, bytes + bytes / 2));
+      b = {d, bytes + bytes / 2};
+    }
+    CK(cudaMemcpyAsync(b.first, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dst = b.first;
     return GNX_OK;
   };
   DevDraws& D = ctx->draws;
@@ -740,6 +786,7 @@ extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
 
 extern "C" int gnx_set_burn(gnx_ctx* ctx, int32_t burn) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   ctx->burn = burn ? 1 : 0;
   ctx->prm.burn = ctx->burn;
   // species.py:449-451: selection if there are traits or deleterious mutation
@@ -766,6 +813,7 @@ extern "C" int gnx_phenotype(gnx_ctx* ctx);
 
 extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) {
   ARG(ctx && pop, "null");
+  USE_DEVICE(ctx);
   ARG(pop->n >= 0 && pop->n <= ctx->cfg.capacity, "population larger than capacity");
   ARG(pop->x && pop->y, "x/y required");
   const size_t n = (size_t)pop->n;
@@ -804,6 +852,7 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
 
 extern "C" int gnx_population_size(gnx_ctx* ctx, int64_t* n) {
   ARG(ctx && n, "null");
+  USE_DEVICE(ctx);
   Counters h;
   int r = read_counters(ctx, &h);
   if (r != GNX_OK) return r;
@@ -815,6 +864,7 @@ extern "C" int gnx_sample_env(gnx_ctx* ctx);
 
 extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
   ARG(ctx && pop, "null");
+  USE_DEVICE(ctx);
   Counters h;
   int r = read_counters(ctx, &h);
   if (r != GNX_OK) return r;
@@ -891,6 +941,7 @@ static int age_move_bin(gnx_ctx* ctx, int do_age, int do_move, int do_bin) {
 extern "C" int gnx_age_step(gnx_ctx* ctx) { ARG(ctx, "null ctx"); return age_move_bin(ctx, 1, 0, 0); }
 extern "C" int gnx_move(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (!ctx->cfg.move) return GNX_OK;
   return age_move_bin(ctx, 0, 1, 0);
 }
@@ -914,6 +965,7 @@ static int finish_binning(gnx_ctx* ctx) {
 
 extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (ctx->cfg.mating_radius <= 0) return GNX_OK;      // panmixia needs no spatial binning
   int r = age_move_bin(ctx, 0, 0, 1);
   if (r != GNX_OK) return r;
@@ -922,6 +974,7 @@ extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
 
 extern "C" int gnx_find_mates(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (ctx->cfg.mating_radius <= 0) {          // mating_radius = None: Wright-Fisher style panmixia
     PROF(ctx, "k_panmixia");
     k_panmixia<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
@@ -947,6 +1000,7 @@ extern "C" int gnx_find_mates(gnx_ctx* ctx) {
 
 extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   const bool fixed = ctx->cfg.n_births_fixed != 0;
   PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0,
               ctx->cfg.mating_radius <= 0 ? 1 : 0};
@@ -1063,6 +1117,7 @@ static int offspring_finish(gnx_ctx* ctx) {
 
 extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   int r;
   if ((r = offspring_check(ctx))) return r;
   if ((r = offspring_gametes(ctx))) return r;
@@ -1073,6 +1128,7 @@ extern "C" int gnx_make_offspring(gnx_ctx* ctx) {
 // ---- a13 mutation -------------------------------------------------------------------------
 extern "C" int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   free_bucket(ctx->mut_allocs);
   memset(&ctx->mut, 0, sizeof ctx->mut);
@@ -1122,6 +1178,7 @@ extern "C" int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m) {
 
 extern "C" int gnx_mutate(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (!ctx->mut.enabled || ctx->burn) return GNX_OK;
   PROF(ctx, "k_mutate");
   k_mutate<<<1, 32, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->mut, ctx->d_c);
@@ -1170,6 +1227,7 @@ extern "C" int gnx_read_mutations(gnx_ctx* ctx, gnx_mutation_row_t* rows, int32_
 
 extern "C" int gnx_phenotype(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (ctx->cfg.n_traits == 0) return GNX_OK;
   if (!ctx->have_traits) { g_last_error = "traits not set"; return GNX_ERR_STATE; }
   PROF(ctx, "k_phenotype_all");
@@ -1180,6 +1238,7 @@ extern "C" int gnx_phenotype(gnx_ctx* ctx) {
 
 extern "C" int gnx_density_counts(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(ctx->dens.counts, 0, (size_t)2 * ctx->dens.npts * 4, s));
@@ -1192,16 +1251,16 @@ extern "C" int gnx_density_counts(gnx_ctx* ctx) {
 
 extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
   cudaStream_t s = ctx->stream;
   // scipy defaults reached through griddata: CloughTocher2DInterpolator(tol=1e-6, maxiter=400)
   PROF(ctx, "k_ct_gradients");
   const size_t gs_bytes = (size_t)ctx->dens.gs_table_bytes + (size_t)ctx->dens.npts * 24 + 16;
   if (ctx->dens.colourable && ctx->dens.padded && gs_bytes <= 220 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->gs_attr_set) {              // per device, so per ctx (a process may drive several GPUs)
       CK(cudaFuncSetAttribute(k_ct_gradients_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
+      ctx->gs_attr_set = true;
     }
     k_ct_gradients_smem<<<2, GS_BLOCK, gs_bytes, s>>>(ctx->dens, ctx->d_c, 400, 1e-6);
   } else {
@@ -1233,6 +1292,7 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
 
 extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   PROF(ctx, "k_death");
   k_death<<<grid_cap(ctx, GNX_G_DEATH, 256, 1.0 + ctx->cfg.b * ctx->cfg.n_births_lambda), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
                                                     ctx->work, ctx->d_c, ctx->mut);
@@ -1242,17 +1302,22 @@ extern "C" int gnx_death_prob(gnx_ctx* ctx) {
 
 extern "C" int gnx_mortality(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
   int r = run_scan(ctx, ms, "scan_mortality");
   if (r != GNX_OK) return r;
   PROF(ctx, "k_end_step");
   k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn);
   LAUNCHED(ctx);
+  cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ctx->stream, &cap_st);
+  if (cap_st == cudaStreamCaptureStatusNone) ctx->records_pending += 1;   // a capture launches nothing
   return GNX_OK;
 }
 
 extern "C" int gnx_sample_env(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   PROF(ctx, "k_sample_env");
   k_sample_env<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
@@ -1339,11 +1404,19 @@ static int capture_step(gnx_ctx* ctx) {
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) { ctx->graph_exec = nullptr; g_last_error = cudaGetErrorString(e); return GNX_ERR_CUDA; }
   step_key(ctx, &ctx->graph_key);
+  ctx->graph_captures += 1;
   return GNX_OK;
 }
 
 extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
   ARG(ctx && n_steps >= 0, "n_steps");
+  USE_DEVICE(ctx);
+  if (ctx->records_pending + n_steps > ctx->work.max_records) {
+    // never drop a step record: the caller drains them (gnx_read_step_records) at least every
+    // max_records steps; nothing has been launched when this is returned
+    g_last_error = "step-record buffer would overflow (65536 records): call gnx_read_step_records first";
+    return GNX_ERR_STATE;
+  }
   std::vector<unsigned char> key;
   for (int k = 0; k < n_steps; ++k) {
     // the first step of a context runs un-captured (validates state, sets kernel attributes)
@@ -1357,6 +1430,8 @@ extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
       }
       CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
       ctx->launches += ctx->graph_kernels;
+      ctx->graph_launches += 1;
+      ctx->records_pending += 1;
     } else {
       int r = one_step(ctx);
       if (r != GNX_OK) return r;
@@ -1368,6 +1443,7 @@ extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
 
 extern "C" int gnx_sync(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   Counters h;
   int r = read_counters(ctx, &h);
@@ -1385,6 +1461,7 @@ extern "C" int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_step
 
 extern "C" int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out) {
   ARG(ctx && n_out, "null");
+  USE_DEVICE(ctx);
   Counters h;
   int r = read_counters(ctx, &h);
   if (r != GNX_OK) return r;
@@ -1394,6 +1471,7 @@ extern "C" int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32
     CK(cudaMemcpyAsync(out, ctx->work.records, (size_t)n * sizeof(gnx_step_record_t), cudaMemcpyDeviceToHost,
                        ctx->stream));
   h.n_rec = 0;
+  ctx->records_pending = 0;
   CK(cudaMemcpyAsync(&ctx->d_c->n_rec, &h.n_rec, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *n_out = n;
@@ -1402,6 +1480,7 @@ extern "C" int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32
 
 extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64_t* nbytes) {
   ARG(ctx && dev_ptr && nbytes, "null");
+  USE_DEVICE(ctx);
   Counters h;
   int r = read_counters(ctx, &h);
   if (r != GNX_OK) return r;
@@ -1462,6 +1541,7 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
 
 extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64_t nbytes) {
   ARG(ctx && host_out, "null");
+  USE_DEVICE(ctx);
   if (field == GNX_F_GENOMES) {
     PROF(ctx, "k_gather_genomes");
     k_gather_genomes<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_stage_genomes, ctx->d_c);
@@ -1483,11 +1563,14 @@ extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64
 
 extern "C" void* gnx_stream(gnx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int64_t gnx_launch_count(gnx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t gnx_graph_launch_count(gnx_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
+extern "C" int64_t gnx_graph_capture_count(gnx_ctx* ctx) { return ctx ? ctx->graph_captures : 0; }
 
 
 // ---- per-kernel timing ------------------------------------------------------------------
 extern "C" int gnx_profile(gnx_ctx* ctx, int32_t enable) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   for (auto& sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
   ctx->spans.clear();
@@ -1498,6 +1581,7 @@ extern "C" int gnx_profile(gnx_ctx* ctx, int32_t enable) {
 // Writes "name\tlaunches\ttotal_ms\n" lines for every kernel launched since gnx_profile(ctx, 1).
 extern "C" int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen) {
   ARG(ctx && buf && buflen > 0, "null");
+  USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   std::vector<std::string> names;
   std::vector<double> ms;
@@ -1526,6 +1610,7 @@ extern "C" int gnx_profile_report(gnx_ctx* ctx, char* buf, int64_t buflen) {
 /* keep per-individual intermediates (n_nbrs, death_p, disp_tries, n_pairs raster) for parity tests */
 extern "C" int gnx_set_debug(gnx_ctx* ctx, int32_t on) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   ctx->prm.store_debug = on ? 1 : 0;
   return GNX_OK;
 }
@@ -1534,6 +1619,7 @@ extern "C" int gnx_set_debug(gnx_ctx* ctx, int32_t on) {
 /* A/B switch for the gamete kernel: 1 = TMA-staged pipeline when rows >= 128 B (default), 0 = register streaming */
 extern "C" int gnx_set_gamete_tma(gnx_ctx* ctx, int32_t on) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   ctx->no_tma = !on;
   return GNX_OK;
 }
@@ -1582,6 +1668,7 @@ extern "C" int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_m
 // interval (model.py:756-768).
 extern "C" int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t birth_capacity) {
   ARG(ctx && edge_capacity > 0 && birth_capacity > 0, "capacities");
+  USE_DEVICE(ctx);
   ARG(edge_capacity < (1ll << 31) && birth_capacity < (1ll << 31), "capacities");
   if (!ctx->have_paths) { g_last_error = "recombination paths not set"; return GNX_ERR_STATE; }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1632,6 +1719,7 @@ extern "C" int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t bir
 // individuals table holds exactly the live individuals (species.py:1140-1164)
 extern "C" int gnx_tskit_renumber(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
   if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
   PROF(ctx, "k_tskit_renumber");
   k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, 0);
@@ -1661,6 +1749,7 @@ extern "C" int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, cons
 // buffers.  Pass NULL arrays (with rows->n_* = 0) to query the counts first.
 extern "C" int gnx_tskit_drain(gnx_ctx* ctx, gnx_tskit_rows_t* rows) {
   ARG(ctx && rows, "null");
+  USE_DEVICE(ctx);
   if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
   Counters h;
   int r = read_counters(ctx, &h);

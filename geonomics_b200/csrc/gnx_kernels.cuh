@@ -83,9 +83,13 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
       if (nv[k] == mx) { sacc += dirs[k]; cnt += 1; }
     loc = sacc / cnt;
   }
-  // scipy vonmises.rvs(kappa, loc): loc + vonmises(0, kappa), not re-wrapped; float16 like the
-  // reference table (spatial.py:447)
-  return __float2half_rn(loc + vonmises_f32(g, kappa, vm_s));
+  // scipy vonmises.rvs(kappa, loc) = mod(loc + vonmises(0, kappa) + pi, 2 pi) - pi (scipy >= 1.11
+  // wraps onto [-pi, pi); that is the scipy the reference runs on here), stored as float16 like
+  // the reference table (spatial.py:447)
+  float v = loc + vonmises_f32(g, kappa, vm_s);
+  if (v >= PI_F) v -= 2.0f * PI_F;
+  else if (v < -PI_F) v += 2.0f * PI_F;
+  return __float2half_rn(v);
 }
 
 // cos/sin of a float16 direction for the on-the-fly path: float32 libm, rounded to half

@@ -496,6 +496,14 @@ class DeviceSpecies:
         return int(self._L.gnx_launch_count(self._ctx))
 
     @property
+    def graph_launch_count(self):
+        return int(self._L.gnx_graph_launch_count(self._ctx))
+
+    @property
+    def graph_capture_count(self):
+        return int(self._L.gnx_graph_capture_count(self._ctx))
+
+    @property
     def stream_ptr(self):
         return int(self._L.gnx_stream(self._ctx) or 0)
 

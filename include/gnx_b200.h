@@ -341,6 +341,10 @@ void* gnx_stream(gnx_ctx* ctx);     /* cudaStream_t of the ctx */
 
 /* kernel launch accounting (bench.py "gpu_launches") */
 int64_t gnx_launch_count(gnx_ctx* ctx);
+/* whole-step CUDA-graph launches / (re-)captures since the ctx was created: a multi-step run must
+ * re-launch ONE captured graph (tests/test_cuda_multistep.py) */
+int64_t gnx_graph_launch_count(gnx_ctx* ctx);
+int64_t gnx_graph_capture_count(gnx_ctx* ctx);
 /* per-kernel device timing with CUDA events on the ctx stream (bench.py "roofline"):
  * gnx_profile(ctx, 1) starts recording, gnx_profile_report writes one
  * "kernel\tlaunches\ttotal_ms\n" line per kernel, gnx_profile(ctx, 0) stops. */
