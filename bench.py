@@ -36,13 +36,14 @@ UNIT = 'individual-generations/s'
 # ------------------------------------------------------------------------------------------
 def algorithmic_bytes(W, T, cells, YX):
     return {
-        'k_age_move_bin': lambda s: s['n'] * (32 + 8 + 8 + 8),          # x,y rw; age rw; id r; key+rank w
+        # entries walked = last step's n_pre (its dead are dropped here); x,y rw; id r; alive r; key+rank w
+        'k_move_key': lambda s: s['npre'] * (1 + 8) + s['n'] * (32 + 8),
         'scan_cells.reduce': lambda s: cells * 4,
         'scan_cells.apply': lambda s: cells * 8,
-        'k_scatter_perm': lambda s: s['n'] * (4 + 4 + 4 + 4),
-        'k_cell_sort': lambda s: cells * 8 + s['n'] * 8,
-        'k_gather_sorted': lambda s: s['n'] * (4 + 16 + 16),
-        'k_find_mates': lambda s: s['n'] * (16 + 4 + 4 + 8 + 4),       # sorted x,y; perm; key; id; mate w
+        'k_bucket': lambda s: s['npre'] * 8 + s['n'] * (8 + 16),           # key+rank r; id r; bucket w
+        # bucket r; whole record (x,y 16, fit 8, age 4, slot 4, sex 1, z 8T) r + w (id comes from the bucket); key w
+        'k_regrid': lambda s: s['n'] * (16 + (33 + 8 * T) + (41 + 8 * T) + 4),
+        'k_find_mates': lambda s: s['n'] * (16 + 4 + 8 + 4),            # x,y; key; id; mate w
         'scan_pairs.reduce': lambda s: s['n'] * 8,
         'scan_pairs.apply': lambda s: s['n'] * 8 + s['P'] * (8 + 32 + 16 + 12),
         'k_gametes': lambda s: s['B'] * (4 * W + 2 * W + 8 + 8 * T + 4 + 8 + 8),   # rows; keys; z w; pair; slots

@@ -2,6 +2,7 @@
 // of the sm_100a kernels in gnx_kernels.cuh: one ctx per Species, all state resident in
 // HBM, one stream, no host round trip inside a time step.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -31,7 +32,10 @@ static thread_local std::string g_last_error;
     }                                                                                        \
   } while (0)
 
-#define USE_DEVICE(ctx) CK(cudaSetDevice((ctx)->device))
+#define USE_DEVICE(ctx)                                         \
+  do {                                                          \
+    if (!(ctx)->capturing) CK(cudaSetDevice((ctx)->device));    \
+  } while (0)
 
 struct ProfSpan {
   std::string name;
@@ -87,6 +91,10 @@ struct gnx_ctx {
   int burn = 0;
   int host_n_hint = 0;
   bool gs_attr_set = false;
+  bool capturing = false;               // inside cudaStreamBeginCapture/EndCapture of the whole-step graph
+  bool pending = false;                 // host mirror of Counters.pending (set by the fused step, cleared by materialise / upload)
+  bool order_valid = false;             // pop.ord / work.inv describe the current entries
+  uint32_t* d_cs_tab = nullptr;
   int64_t records_pending = 0;          // step records written since the last gnx_read_step_records
   int64_t graph_launches = 0, graph_captures = 0;
   void* d_paths = nullptr;
@@ -252,6 +260,7 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   Ld.max_x = cfg->dim_x - 0.001;
   Ld.max_y = cfg->dim_y - 0.001;
   mating_grid(*cfg, &Ld.cell_size, &Ld.ncx, &Ld.ncy);
+  ARG(Ld.ncx < 65536 && Ld.ncy < 65536, "mating grid has more than 65535 cells along one axis");
   ctx->ncell = Ld.ncx * Ld.ncy;
   const size_t plane = (size_t)cfg->dim_x * cfg->dim_y;
   DM(ctx, &ctx->d_rasters, plane * cfg->n_layers);
@@ -275,10 +284,23 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   Work& W = ctx->work;
   DM(ctx, &W.cell_count, (size_t)ctx->ncell + 1);
   DM(ctx, &W.cell_start, (size_t)ctx->ncell + 1);
-  DM(ctx, &W.cellkey, cap);
-  DM(ctx, &W.cellrank, cap);
+  DM(ctx, &W.mkey, cap);
+  DM(ctx, &W.mrank, cap);
+  DM(ctx, &W.bucket, cap);
+  DM(ctx, &W.skey, cap);
+  DM(ctx, &W.inv, cap);
   DM(ctx, &W.perm, cap);
-  DM(ctx, &W.sxy, cap);
+  for (int h = 0; h < 2; ++h) {
+    DM(ctx, &W.sort_keys[h], cap);
+    DM(ctx, &W.sort_vals[h], cap);
+    DM(ctx, &P.ord[h], cap);
+  }
+  DM(ctx, &W.sort_hist, (size_t)256 * (cap / RS_TILE + 2));
+  {
+    double* sc = nullptr;
+    DM(ctx, &sc, (size_t)2 * cap * std::max(1, cfg->n_traits));
+    W.scratch = sc;
+  }
   DM(ctx, &W.mate, cap);
   DM(ctx, &W.n_nbrs, cap);
   DM(ctx, &W.pairs, 2 * cap);
@@ -290,7 +312,8 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   DM(ctx, &W.alive, cap);
   DM(ctx, &W.death_p, cap);
   DM(ctx, &W.disp_tries, cap);
-  DM(ctx, &W.tile_sums, (size_t)std::max<int64_t>(cap, ctx->ncell) / SCAN_TILE + 2);
+  DM(ctx, &W.tile_sums, (size_t)std::max<int64_t>(std::max<int64_t>(cap, ctx->ncell),
+                                                    (int64_t)256 * (cap / RS_TILE + 2)) / SCAN_TILE + 2);
   DM(ctx, &W.scan_ticket, 4);
   DM(ctx, &W.N_rast, plane);
   DM(ctx, &W.NP_rast, plane);
@@ -315,6 +338,29 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   pr.seed_lo = (uint32_t)cfg->seed;
   pr.seed_hi = (uint32_t)(cfg->seed >> 32);
   pr.store_debug = 0;
+  pr.ordered = 0;
+  {
+    // (half cos, half sin) of every float16 direction, numpy's portable float16 semantics: half ->
+    // double, cos, rounded to float32, rounded to half (oracle/step_oracle.py _cos_sin)
+    std::vector<uint32_t> tab(65536);
+    for (uint32_t b = 0; b < 65536; ++b) {
+      const uint32_t sign = b >> 15, ex = (b >> 10) & 31u, man = b & 1023u;
+      double v;
+      if (ex == 0) v = std::ldexp((double)man, -24);
+      else if (ex == 31) v = man ? NAN : INFINITY;
+      else v = std::ldexp((double)(man | 1024u), (int)ex - 25);
+      if (sign) v = -v;
+      const __half hc = __float2half_rn((float)std::cos(v)), hs = __float2half_rn((float)std::sin(v));
+      unsigned short uc, us;
+      memcpy(&uc, &hc, 2);
+      memcpy(&us, &hs, 2);
+      tab[b] = (uint32_t)uc | ((uint32_t)us << 16);
+    }
+    DM(ctx, &ctx->d_cs_tab, 65536);
+    CK(cudaMemcpyAsync(ctx->d_cs_tab, tab.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    pr.cs_tab = ctx->d_cs_tab;
+  }
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = std::max(1, cfg->disp_max_tries_injected);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -730,6 +776,10 @@ extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
   const int R = ctx->draws.disp_R;
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = R;
+  // injected draws are indexed by species-order ordinal and offspring number: switch the step to
+  // ordered mode (ordinals carried through the re-grid, pair list in ascending focal ordinal)
+  ctx->prm.ordered = dr ? 1 : 0;
+  ctx->order_valid = false;
   if (!dr) return GNX_OK;
   const size_t n = (size_t)dr->n;
   ctx->draws.n = dr->n;
@@ -808,6 +858,61 @@ static int check_device_err(const Counters& h) {
   return GNX_OK;
 }
 
+// ---- species order on demand, pending deaths -------------------------------------------------
+template <class F>
+static int run_scan(gnx_ctx* ctx, F f, const char* name);
+
+// Deaths a fused step left flagged are applied now (explicit stable compaction), so that every
+// host-facing view sees exactly the live population.
+static int materialise(gnx_ctx* ctx) {
+  if (!ctx->pending) return GNX_OK;
+  MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
+  int r = run_scan(ctx, ms, "scan_mortality");
+  if (r != GNX_OK) return r;
+  PROF(ctx, "k_end_step");
+  k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn, 0);
+  LAUNCHED(ctx);
+  ctx->pending = false;
+  ctx->order_valid = false;
+  return GNX_OK;
+}
+
+// pop.ord[cur] (entry -> species-order ordinal) and work.inv (ordinal -> entry) for the first
+// n entries of the current half: LSD radix sort of (id, entry).  exclude_dead ranks only the
+// entries whose pending-death flag is clear (they sort first; *n_ranked = their number).
+static int build_order(gnx_ctx* ctx, const Counters& h, bool exclude_dead) {
+  const int n = std::max(h.n, h.n_pre);
+  cudaStream_t s = ctx->stream;
+  Work& W = ctx->work;
+  PROF(ctx, "k_order_keys");
+  k_order_keys<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, W, ctx->d_c, n, exclude_dead ? 1 : 0);
+  LAUNCHED(ctx);
+  int bits = 1;
+  while (bits < 63 && (h.max_idx >> bits) != 0) ++bits;
+  bits += 1;                                     // dead keys (all ones) stay strictly above every id
+  const int ntiles = std::max(1, (n + RS_TILE - 1) / RS_TILE);
+  int in = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    PROF(ctx, "k_radix_hist");
+    k_radix_hist<<<std::min(ntiles, grid_for(ctx, 8)), RS_BLOCK, 0, s>>>(W.sort_keys[in], n, shift, W.sort_hist, ntiles);
+    LAUNCHED(ctx);
+    RadixScan rs{W.sort_hist, 256 * ntiles};
+    int r = run_scan(ctx, rs, "scan_radix");
+    if (r != GNX_OK) return r;
+    PROF(ctx, "k_radix_scatter");
+    k_radix_scatter<<<std::min(ntiles, grid_for(ctx, 8)), RS_BLOCK, 0, s>>>(W.sort_keys[in], W.sort_vals[in], W.sort_keys[in ^ 1],
+                                                                      W.sort_vals[in ^ 1], n, shift, W.sort_hist, ntiles);
+    LAUNCHED(ctx);
+    in ^= 1;
+  }
+  const int n_ranked = exclude_dead ? h.n_alive : n;
+  PROF(ctx, "k_order_finish");
+  k_order_finish<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, W, ctx->d_c, W.sort_vals[in], n_ranked);
+  LAUNCHED(ctx);
+  ctx->order_valid = true;
+  return GNX_OK;
+}
+
 // ---- population upload / download -------------------------------------------------------
 extern "C" int gnx_phenotype(gnx_ctx* ctx);
 
@@ -841,6 +946,8 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
   k_upload_finish<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c, (int)n, max_idx, pop->idx ? 0 : 1,
                                                   have_z ? ctx->d_stage_z : nullptr);
   LAUNCHED(ctx);
+  ctx->pending = false;
+  ctx->order_valid = false;
   if (!have_z && pop->genomes && ctx->cfg.n_traits > 0 && ctx->have_traits) {
     int r = gnx_phenotype(ctx);
     if (r != GNX_OK) return r;
@@ -856,50 +963,60 @@ extern "C" int gnx_population_size(gnx_ctx* ctx, int64_t* n) {
   Counters h;
   int r = read_counters(ctx, &h);
   if (r != GNX_OK) return r;
-  *n = h.n;
+  *n = h.pending ? h.n_alive : h.n;
   return check_device_err(h);
 }
 
-extern "C" int gnx_sample_env(gnx_ctx* ctx);
+// the live population in species order (ascending id) in the idle half of the state buffers
+static int species_view(gnx_ctx* ctx, Counters* h, bool want_z_rows) {
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  if ((r = read_counters(ctx, h)) != GNX_OK) return r;
+  if ((r = build_order(ctx, *h, false)) != GNX_OK) return r;
+  const int n = std::max(h->n, h->n_pre);
+  PROF(ctx, "k_species_gather");
+  k_species_gather<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->work, ctx->d_c, n,
+                                                             want_z_rows ? ctx->d_stage_z : nullptr);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+static int sample_env_ordered(gnx_ctx* ctx, int n) {
+  PROF(ctx, "k_sample_env");
+  k_sample_env<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c, n);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
 
 extern "C" int gnx_download_population(gnx_ctx* ctx, gnx_population_t* pop) {
   ARG(ctx && pop, "null");
   USE_DEVICE(ctx);
   Counters h;
-  int r = read_counters(ctx, &h);
+  const bool want_z = pop->z && ctx->cfg.n_traits > 0;
+  int r = species_view(ctx, &h, want_z);
   if (r != GNX_OK) return r;
   const size_t n = (size_t)h.n;
-  const int cur = h.cur;
+  const int o = h.cur ^ 1;                       // species-ordered copies live in the idle half
   cudaStream_t s = ctx->stream;
   Pop& P = ctx->pop;
   pop->n = h.n;
   pop->max_ind_idx = h.max_idx;
-  if (pop->x || pop->y) {
-    PROF(ctx, "k_xy_split");
-    k_xy_split<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c);
-    LAUNCHED(ctx);
-    const double* sx = reinterpret_cast<const double*>(P.xy[cur ^ 1]);
-    if (pop->x) CK(cudaMemcpyAsync(pop->x, sx, n * 8, cudaMemcpyDeviceToHost, s));
-    if (pop->y) CK(cudaMemcpyAsync(pop->y, sx + P.cap, n * 8, cudaMemcpyDeviceToHost, s));
-  }
-  if (pop->age) CK(cudaMemcpyAsync(pop->age, P.age[cur], n * 4, cudaMemcpyDeviceToHost, s));
-  if (pop->sex) CK(cudaMemcpyAsync(pop->sex, P.sex[cur], n, cudaMemcpyDeviceToHost, s));
-  if (pop->idx) CK(cudaMemcpyAsync(pop->idx, P.idx[cur], n * 8, cudaMemcpyDeviceToHost, s));
-  if (pop->fit) CK(cudaMemcpyAsync(pop->fit, P.fit[cur], n * 8, cudaMemcpyDeviceToHost, s));
+  const double* sx = reinterpret_cast<const double*>(P.xy[o]);
+  if (pop->x) CK(cudaMemcpyAsync(pop->x, sx, n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->y) CK(cudaMemcpyAsync(pop->y, sx + P.cap, n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->age) CK(cudaMemcpyAsync(pop->age, P.age[o], n * 4, cudaMemcpyDeviceToHost, s));
+  if (pop->sex) CK(cudaMemcpyAsync(pop->sex, P.sex[o], n, cudaMemcpyDeviceToHost, s));
+  if (pop->idx) CK(cudaMemcpyAsync(pop->idx, P.idx[o], n * 8, cudaMemcpyDeviceToHost, s));
+  if (pop->fit) CK(cudaMemcpyAsync(pop->fit, P.fit[o], n * 8, cudaMemcpyDeviceToHost, s));
   if (pop->genomes && !ctx->burn) {
     PROF(ctx, "k_gather_genomes");
-    k_gather_genomes<<<grid_for(ctx, 8), 256, 0, s>>>(P, ctx->d_stage_genomes, ctx->d_c);
+    k_gather_genomes<<<grid_for(ctx, 8), 256, 0, s>>>(P, P.gslot[o], ctx->d_stage_genomes, (int)n);
     LAUNCHED(ctx);
     CK(cudaMemcpyAsync(pop->genomes, ctx->d_stage_genomes, n * 2 * ctx->Wq * sizeof(uint4), cudaMemcpyDeviceToHost, s));
   }
-  if (pop->z && ctx->cfg.n_traits > 0) {
-    PROF(ctx, "k_z_to_rows");
-    k_z_to_rows<<<grid_for(ctx, 4), 256, 0, s>>>(P, ctx->d_c, ctx->d_stage_z);
-    LAUNCHED(ctx);
-    CK(cudaMemcpyAsync(pop->z, ctx->d_stage_z, n * ctx->cfg.n_traits * 8, cudaMemcpyDeviceToHost, s));
-  }
+  if (want_z) CK(cudaMemcpyAsync(pop->z, ctx->d_stage_z, n * ctx->cfg.n_traits * 8, cudaMemcpyDeviceToHost, s));
   if (pop->e) {
-    r = gnx_sample_env(ctx);
+    r = sample_env_ordered(ctx, (int)n);
     if (r != GNX_OK) return r;
     CK(cudaMemcpyAsync(pop->e, ctx->work.e_out, n * ctx->cfg.n_layers * 8, cudaMemcpyDeviceToHost, s));
   }
@@ -925,40 +1042,58 @@ static int run_scan(gnx_ctx* ctx, F f, const char* name) {
   return GNX_OK;
 }
 
-static int age_move_bin(gnx_ctx* ctx, int do_age, int do_move, int do_bin) {
-  if (do_bin) CK(cudaMemsetAsync(ctx->work.cell_count, 0, ((size_t)ctx->ncell + 1) * 4, ctx->stream));
+// injected draws are indexed by species-order ordinal: make pop.ord / work.inv current.
+// Synchronises (reads the counters), so never called while a graph is being captured.
+static int ensure_order(gnx_ctx* ctx) {
+  if (!ctx->prm.ordered || ctx->order_valid) return GNX_OK;
+  Counters h;
+  int r = read_counters(ctx, &h);
+  if (r != GNX_OK) return r;
+  return build_order(ctx, h, h.pending != 0);
+}
+
+static int move_key(gnx_ctx* ctx, int do_age, int do_move, int do_key) {
+  if (do_key) CK(cudaMemsetAsync(ctx->work.cell_count, 0, ((size_t)ctx->ncell + 1) * 4, ctx->stream));
   if (do_move && ctx->cfg.move_surf_mode == GNX_SURF_TABLE && !ctx->prm.move_tab) {
     g_last_error = "movement surface table not set";
     return GNX_ERR_STATE;
   }
-  PROF(ctx, "k_age_move_bin");
-  k_age_move_bin<<<grid_for(ctx, GNX_G_AGE), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
-                                                           ctx->d_c, do_age, do_move, do_bin);
+  PROF(ctx, "k_move_key");
+  k_move_key<<<grid_for(ctx, GNX_G_AGE), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
+                                                       ctx->d_c, do_age, do_move, do_key);
   LAUNCHED(ctx);
   return GNX_OK;
 }
 
-extern "C" int gnx_age_step(gnx_ctx* ctx) { ARG(ctx, "null ctx"); return age_move_bin(ctx, 1, 0, 0); }
+extern "C" int gnx_age_step(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  return move_key(ctx, 1, 0, 0);
+}
 extern "C" int gnx_move(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
   if (!ctx->cfg.move) return GNX_OK;
-  return age_move_bin(ctx, 0, 1, 0);
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  if ((r = ensure_order(ctx)) != GNX_OK) return r;
+  return move_key(ctx, 0, 1, 0);
 }
 
-static int finish_binning(gnx_ctx* ctx) {
+// cell starts -> arrival buckets -> the one pass that moves the state into (cell, id) order
+static int finish_regrid(gnx_ctx* ctx, int age_inc) {
   CellScan cs{ctx->work.cell_count, ctx->work.cell_start, ctx->ncell};
   int r = run_scan(ctx, cs, "scan_cells");
   if (r != GNX_OK) return r;
   cudaStream_t s = ctx->stream;
-  PROF(ctx, "k_scatter_perm");
-  k_scatter_perm<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->work, ctx->d_c);
+  PROF(ctx, "k_bucket");
+  k_bucket<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
-  PROF(ctx, "k_cell_sort");
-  k_cell_sort<<<grid_for(ctx, GNX_G_SORT), 256, 0, s>>>(ctx->work, ctx->ncell);
-  LAUNCHED(ctx);
-  PROF(ctx, "k_gather_sorted");
-  k_gather_sorted<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c);
+  PROF(ctx, "k_regrid");
+  k_regrid<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c, age_inc,
+                                                      ctx->prm.ordered);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -967,14 +1102,24 @@ extern "C" int gnx_bin_cells(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
   if (ctx->cfg.mating_radius <= 0) return GNX_OK;      // panmixia needs no spatial binning
-  int r = age_move_bin(ctx, 0, 0, 1);
+  int r = materialise(ctx);
   if (r != GNX_OK) return r;
-  return finish_binning(ctx);
+  if ((r = ensure_order(ctx)) != GNX_OK) return r;
+  if ((r = move_key(ctx, 0, 0, 1)) != GNX_OK) return r;
+  return finish_regrid(ctx, 0);
 }
 
+static int find_mates(gnx_ctx* ctx);
 extern "C" int gnx_find_mates(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  if ((r = ensure_order(ctx)) != GNX_OK) return r;
+  return find_mates(ctx);
+}
+
+static int find_mates(gnx_ctx* ctx) {
   if (ctx->cfg.mating_radius <= 0) {          // mating_radius = None: Wright-Fisher style panmixia
     PROF(ctx, "k_panmixia");
     k_panmixia<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->draws, ctx->work, ctx->d_c);
@@ -1003,7 +1148,7 @@ extern "C" int gnx_dedup_pairs(gnx_ctx* ctx) {
   USE_DEVICE(ctx);
   const bool fixed = ctx->cfg.n_births_fixed != 0;
   PairScan ps{ctx->pop, ctx->work, ctx->d_c, ctx->cfg.sex, fixed ? (int32_t)ctx->cfg.n_births_lambda : 0,
-              ctx->cfg.mating_radius <= 0 ? 1 : 0};
+              ctx->cfg.mating_radius <= 0 ? 1 : 0, ctx->prm.ordered};
   if (fixed) ARG(ps.fixed_nb >= 1, "n_births_fixed needs n_births_distr_lambda >= 1");
   int r = run_scan(ctx, ps, "scan_pairs");
   if (r != GNX_OK) return r;
@@ -1290,12 +1435,30 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+static int death_prob(gnx_ctx* ctx, int end_step) {
+  PROF(ctx, "k_death");
+  k_death<<<grid_cap(ctx, GNX_G_DEATH, 256, 1.0 + ctx->cfg.b * ctx->cfg.n_births_lambda), 256, 0, ctx->stream>>>(
+      ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c, ctx->mut, end_step);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
 extern "C" int gnx_death_prob(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
-  PROF(ctx, "k_death");
-  k_death<<<grid_cap(ctx, GNX_G_DEATH, 256, 1.0 + ctx->cfg.b * ctx->cfg.n_births_lambda), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws,
-                                                    ctx->work, ctx->d_c, ctx->mut);
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  if ((r = ensure_order(ctx)) != GNX_OK) return r;
+  return death_prob(ctx, 0);
+}
+
+// explicit removal of the flagged dead + end-of-step bookkeeping
+static int mortality(gnx_ctx* ctx) {
+  MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
+  int r = run_scan(ctx, ms, "scan_mortality");
+  if (r != GNX_OK) return r;
+  PROF(ctx, "k_end_step");
+  k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn, 1);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -1303,36 +1466,41 @@ extern "C" int gnx_death_prob(gnx_ctx* ctx) {
 extern "C" int gnx_mortality(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
-  MortalityScan ms{ctx->pop, ctx->work, ctx->d_c, ctx->burn};
-  int r = run_scan(ctx, ms, "scan_mortality");
+  if (ctx->pending) { g_last_error = "gnx_mortality after a fused step: the step already ended"; return GNX_ERR_STATE; }
+  int r = mortality(ctx);
   if (r != GNX_OK) return r;
-  PROF(ctx, "k_end_step");
-  k_end_step<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->work, ctx->burn);
-  LAUNCHED(ctx);
-  cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(ctx->stream, &cap_st);
-  if (cap_st == cudaStreamCaptureStatusNone) ctx->records_pending += 1;   // a capture launches nothing
+  ctx->records_pending += 1;
+  ctx->order_valid = false;
   return GNX_OK;
 }
 
 extern "C" int gnx_sample_env(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
-  PROF(ctx, "k_sample_env");
-  k_sample_env<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c);
-  LAUNCHED(ctx);
-  return GNX_OK;
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  Counters h;
+  if ((r = read_counters(ctx, &h)) != GNX_OK) return r;
+  if ((r = build_order(ctx, h, false)) != GNX_OK) return r;
+  return sample_env_ordered(ctx, std::max(h.n, h.n_pre));
 }
 
 // One time step for this species = the reference's queue (model.py:603-667):
 //   _set_age_stage -> _do_movement -> _do_pop_dynamics -> _set_Nt
+// With a mating radius the removal of the previous step's dead, this step's ageing and the
+// counting sort into mating-grid order are ONE pass over the state (k_move_key flags and keys,
+// k_regrid moves); under panmixia there is no grid, so the dead are compacted away at the end
+// of the step as the staged entry points do.
 static int one_step(gnx_ctx* ctx) {
   int r;
-  // a1 + a2 + a4 fused: age, movement, cell keys + histogram
   const bool panmixia = ctx->cfg.mating_radius <= 0;
-  if ((r = age_move_bin(ctx, 1, ctx->cfg.move ? 1 : 0, panmixia ? 0 : 1))) return r;
-  if (!panmixia && (r = finish_binning(ctx))) return r;
-  if ((r = gnx_find_mates(ctx))) return r;
+  if (panmixia) {
+    if ((r = move_key(ctx, 1, ctx->cfg.move ? 1 : 0, 0))) return r;
+  } else {
+    if ((r = move_key(ctx, 0, ctx->cfg.move ? 1 : 0, 1))) return r;
+    if ((r = finish_regrid(ctx, 1))) return r;
+  }
+  if ((r = find_mates(ctx))) return r;
   if ((r = gnx_dedup_pairs(ctx))) return r;
   if (ctx->stream2 && !ctx->profiling && !(ctx->tsk.enabled && !ctx->burn)) {
     // Newborn records first (positions do not depend on genotypes), then two branches:
@@ -1359,8 +1527,12 @@ static int one_step(gnx_ctx* ctx) {
     if ((r = gnx_density_counts(ctx))) return r;
     if ((r = gnx_density_eval(ctx))) return r;
   }
-  if ((r = gnx_death_prob(ctx))) return r;
-  if ((r = gnx_mortality(ctx))) return r;
+  if (panmixia) {
+    if ((r = death_prob(ctx, 0))) return r;
+    if ((r = mortality(ctx))) return r;
+  } else {
+    if ((r = death_prob(ctx, 1))) return r;       // flags the dead and ends the step
+  }
   return GNX_OK;
 }
 
@@ -1393,7 +1565,9 @@ static int capture_step(gnx_ctx* ctx) {
   drop_graph(ctx);
   const int64_t launches0 = ctx->launches;
   CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
   int r = one_step(ctx);
+  ctx->capturing = false;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
   ctx->graph_kernels = (int)(ctx->launches - launches0);
@@ -1417,11 +1591,18 @@ extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
     g_last_error = "step-record buffer would overflow (65536 records): call gnx_read_step_records first";
     return GNX_ERR_STATE;
   }
+  const bool lazy = ctx->cfg.mating_radius > 0;
   std::vector<unsigned char> key;
   for (int k = 0; k < n_steps; ++k) {
+    if (ctx->prm.ordered) {
+      // injected draws: ordinals of the entries alive at step start (outside the captured graph)
+      ctx->order_valid = false;
+      int r = ensure_order(ctx);
+      if (r != GNX_OK) return r;
+    }
     // the first step of a context runs un-captured (validates state, sets kernel attributes)
     if (ctx->use_graph && !ctx->profiling && ctx->steps_done >= 1) {
-      if (k == 0 || !ctx->graph_exec) {
+      if (k == 0 || !ctx->graph_exec || ctx->prm.ordered) {
         step_key(ctx, &key);
         if (!ctx->graph_exec || key != ctx->graph_key) {
           int r = capture_step(ctx);
@@ -1431,12 +1612,14 @@ extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
       CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
       ctx->launches += ctx->graph_kernels;
       ctx->graph_launches += 1;
-      ctx->records_pending += 1;
     } else {
       int r = one_step(ctx);
       if (r != GNX_OK) return r;
     }
+    ctx->records_pending += 1;
     ctx->steps_done += 1;
+    ctx->pending = lazy;
+    ctx->order_valid = false;
   }
   return GNX_OK;
 }
@@ -1478,40 +1661,78 @@ extern "C" int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32
   return check_device_err(h);
 }
 
+// Per-individual fields are returned in SPECIES order (ascending id): the entries are ranked by
+// id (radix sort) and the field is gathered into a staging area -- the idle half of the state
+// buffers for the state fields, work.scratch for work arrays; entry-valued arrays (mate, pairs)
+// are translated to ordinals.  The pointer stays valid until the next call on the ctx.
 extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64_t* nbytes) {
   ARG(ctx && dev_ptr && nbytes, "null");
   USE_DEVICE(ctx);
-  Counters h;
-  int r = read_counters(ctx, &h);
+  int r = materialise(ctx);
   if (r != GNX_OK) return r;
-  const int cur = h.cur;
-  const size_t n = (size_t)std::max(h.n, h.n_pre), cap = (size_t)ctx->pop.cap;
+  Counters h;
+  if ((r = read_counters(ctx, &h)) != GNX_OK) return r;
+  const int ne = std::max(h.n, h.n_pre);
+  const size_t n = (size_t)ne, cap = (size_t)ctx->pop.cap;
   const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
   Pop& P = ctx->pop;
   Work& W = ctx->work;
   Dens& D = ctx->dens;
+  cudaStream_t s = ctx->stream;
+  const int o = h.cur ^ 1;
   void* p = nullptr;
   size_t b = 0;
+  const bool state_field = field == GNX_F_X || field == GNX_F_Y || field == GNX_F_AGE || field == GNX_F_SEX ||
+                           field == GNX_F_IDX || field == GNX_F_Z || field == GNX_F_FIT || field == GNX_F_GSLOT ||
+                           field == GNX_F_GENOMES;
+  const bool work_field = field == GNX_F_N_NBRS || field == GNX_F_MATE || field == GNX_F_PAIRS || field == GNX_F_PERM ||
+                          field == GNX_F_DEATH_P || field == GNX_F_ALIVE || field == GNX_F_E;
+  if (state_field || work_field) {
+    if ((r = build_order(ctx, h, false)) != GNX_OK) return r;
+  }
+  if (state_field) {
+    PROF(ctx, "k_species_gather");
+    k_species_gather<<<grid_for(ctx, 8), 256, 0, s>>>(P, W, ctx->d_c, ne, nullptr);
+    LAUNCHED(ctx);
+  }
+  const int g4 = grid_for(ctx, 4);
   switch (field) {
-    case GNX_F_X:
-    case GNX_F_Y:
-      // plain arrays staged in the idle half (valid until the next step or upload)
-      k_xy_split<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(P, ctx->d_c);
-      CK(cudaGetLastError());
-      p = reinterpret_cast<double*>(P.xy[cur ^ 1]) + (field == GNX_F_Y ? cap : 0);
-      b = n * 8;
+    case GNX_F_X: p = reinterpret_cast<double*>(P.xy[o]); b = n * 8; break;
+    case GNX_F_Y: p = reinterpret_cast<double*>(P.xy[o]) + cap; b = n * 8; break;
+    case GNX_F_AGE: p = P.age[o]; b = n * 4; break;
+    case GNX_F_SEX: p = P.sex[o]; b = n; break;
+    case GNX_F_IDX: p = P.idx[o]; b = n * 8; break;
+    case GNX_F_Z: p = P.z[o]; b = cap * std::max(1, ctx->cfg.n_traits) * 8; break;
+    case GNX_F_FIT: p = P.fit[o]; b = n * 8; break;
+    case GNX_F_GSLOT: p = P.gslot[o]; b = n * 4; break;
+    case GNX_F_GENOMES:
+      PROF(ctx, "k_gather_genomes");
+      k_gather_genomes<<<grid_for(ctx, 8), 256, 0, s>>>(P, P.gslot[o], ctx->d_stage_genomes, h.n);
+      LAUNCHED(ctx);
+      p = ctx->d_stage_genomes;
+      b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4);
       break;
-    case GNX_F_AGE: p = P.age[cur]; b = n * 4; break;
-    case GNX_F_SEX: p = P.sex[cur]; b = n; break;
-    case GNX_F_IDX: p = P.idx[cur]; b = n * 8; break;
-    case GNX_F_Z: p = P.z[cur]; b = cap * std::max(1, ctx->cfg.n_traits) * 8; break;
-    case GNX_F_FIT: p = P.fit[cur]; b = n * 8; break;
-    case GNX_F_GSLOT: p = P.gslot[cur]; b = n * 4; break;
-    case GNX_F_N_NBRS: p = W.n_nbrs; b = n * 4; break;
-    case GNX_F_MATE: p = W.mate; b = n * 4; break;
-    case GNX_F_PAIRS: p = W.pairs; b = (size_t)h.P * 8; break;
+    case GNX_F_N_NBRS:
+      k_gather_by_inv<int32_t><<<g4, 256, 0, s>>>(W.n_nbrs, (int32_t*)W.scratch, W.inv, ne);
+      p = W.scratch; b = n * 4; break;
+    case GNX_F_MATE:
+      k_gather_mate<<<g4, 256, 0, s>>>(W.mate, (int32_t*)W.scratch, W.inv, P.ord[h.cur], ne,
+                                       ctx->cfg.mating_radius <= 0 ? 1 : 0);
+      p = W.scratch; b = n * 4; break;
+    case GNX_F_PAIRS:
+      k_translate_entries<<<g4, 256, 0, s>>>(W.pairs, (int32_t*)W.scratch, P.ord[h.cur], 2 * h.P);
+      p = W.scratch; b = (size_t)h.P * 8; break;
+    case GNX_F_PERM: p = P.ord[h.cur]; b = n * 4; break;     /* ordinal of the individual at each grid position */
+    case GNX_F_DEATH_P:
+      k_gather_by_inv<double><<<g4, 256, 0, s>>>(W.death_p, (double*)W.scratch, W.inv, ne);
+      p = W.scratch; b = n * 8; break;
+    case GNX_F_ALIVE:
+      k_gather_by_inv<uint8_t><<<g4, 256, 0, s>>>(W.alive, (uint8_t*)W.scratch, W.inv, ne);
+      p = W.scratch; b = n; break;
+    case GNX_F_E:
+      if ((r = sample_env_ordered(ctx, ne)) != GNX_OK) return r;
+      p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
     case GNX_F_NB: p = W.nb; b = (size_t)h.P * 4; break;
-    case GNX_F_PERM: p = W.perm; b = n * 4; break;
     case GNX_F_CELL_START: p = W.cell_start; b = ((size_t)ctx->ncell + 1) * 4; break;
     case GNX_F_COUNTS_N: p = D.counts; b = (size_t)D.npts * 4; break;
     case GNX_F_COUNTS_P: p = D.counts + D.npts; b = (size_t)D.npts * 4; break;
@@ -1523,17 +1744,14 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
     case GNX_F_NPAIRS_RAST: p = W.NP_rast; b = plane * 8; break;
     case GNX_F_D_RAST: p = W.d_rast; b = plane * 8; break;
     case GNX_F_K_RAST: p = ctx->d_K; b = plane * 8; break;
-    case GNX_F_DEATH_P: p = W.death_p; b = n * 8; break;
-    case GNX_F_ALIVE: p = W.alive; b = n; break;
     case GNX_F_DISP_TRIES: p = W.disp_tries; b = (size_t)h.B * 4; break;
-    case GNX_F_E: p = W.e_out; b = n * ctx->cfg.n_layers * 8; break;
     case GNX_F_COUNTERS: p = ctx->d_c; b = sizeof(Counters); break;
 #ifdef GNX_GS_TIMING
     case 31: p = D.coef + (size_t)2 * D.ntri * CT_STRIDE; b = 64 * 8; break;   /* clock64 phase timings (tools/gs_time.py) */
 #endif
-    case GNX_F_GENOMES: p = ctx->d_stage_genomes; b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4); break;
     default: g_last_error = "unknown field"; return GNX_ERR_ARG;
   }
+  CK(cudaGetLastError());
   *dev_ptr = p;
   *nbytes = (int64_t)b;
   return GNX_OK;
@@ -1542,15 +1760,6 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
 extern "C" int gnx_read_field(gnx_ctx* ctx, int32_t field, void* host_out, int64_t nbytes) {
   ARG(ctx && host_out, "null");
   USE_DEVICE(ctx);
-  if (field == GNX_F_GENOMES) {
-    PROF(ctx, "k_gather_genomes");
-    k_gather_genomes<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_stage_genomes, ctx->d_c);
-    LAUNCHED(ctx);
-  }
-  if (field == GNX_F_E) {
-    int r = gnx_sample_env(ctx);
-    if (r != GNX_OK) return r;
-  }
   void* p;
   int64_t avail;
   int r = gnx_device_ptr(ctx, field, &p, &avail);
@@ -1636,7 +1845,12 @@ extern "C" int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1, uint64_t* ho
 extern "C" int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_max, double y_min, double y_max,
                                           uint64_t* host_c1, uint64_t* host_het, double* fit_sum, int64_t* n) {
   ARG(ctx && host_c1 && host_het && fit_sum && n, "null");
+  USE_DEVICE(ctx);
   if (ctx->burn || ctx->cfg.L == 0) { g_last_error = "no genomes on the device"; return GNX_ERR_STATE; }
+  {
+    int rm = materialise(ctx);
+    if (rm != GNX_OK) return rm;
+  }
   const int nbits = ctx->Wwords * 32;
   unsigned long long* d = nullptr;
   CK(cudaMalloc(&d, (size_t)(2 * nbits + 2) * 8));
@@ -1666,6 +1880,19 @@ extern "C" int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_m
 // Node / edge / individual rows of every birth are written to device buffers by the step
 // kernels and handed to the host (tskit's TableCollection.append_columns) at the simplify
 // interval (model.py:756-768).
+// node ids 2k, 2k+1 by species-order ordinal k: the entries are ranked by id first
+static int tskit_renumber(gnx_ctx* ctx, int reset_t0) {
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  Counters h;
+  if ((r = read_counters(ctx, &h)) != GNX_OK) return r;
+  if ((r = build_order(ctx, h, false)) != GNX_OK) return r;
+  PROF(ctx, "k_tskit_renumber");
+  k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, reset_t0);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
 extern "C" int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t birth_capacity) {
   ARG(ctx && edge_capacity > 0 && birth_capacity > 0, "capacities");
   USE_DEVICE(ctx);
@@ -1708,9 +1935,7 @@ extern "C" int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t bir
     for (int b = 0; b < 2; ++b) DM(ctx, &ctx->pop.node[h][b], cap, &ctx->tsk_allocs);
   T.enabled = 1;
   // node ids 2k, 2k+1 in species order (species.py:1148-1152); time origin = now
-  PROF(ctx, "k_tskit_renumber");
-  k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, 1);
-  LAUNCHED(ctx);
+  if ((r = tskit_renumber(ctx, 1)) != GNX_OK) return r;
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
 }
@@ -1721,10 +1946,7 @@ extern "C" int gnx_tskit_renumber(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
   if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
-  PROF(ctx, "k_tskit_renumber");
-  k_tskit_renumber<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, 0);
-  LAUNCHED(ctx);
-  return GNX_OK;
+  return tskit_renumber(ctx, 0);
 }
 
 // explicit node ids (e.g. the msprime-seeded start, species.py:1060-1063), species order
@@ -1732,12 +1954,19 @@ extern "C" int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, cons
                                    int32_t next_node_id, int32_t next_individual_row) {
   ARG(ctx && host_node0 && host_node1, "null");
   if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
-  Counters h;
-  int r = read_counters(ctx, &h);
+  USE_DEVICE(ctx);
+  int r = materialise(ctx);
   if (r != GNX_OK) return r;
+  Counters h;
+  if ((r = read_counters(ctx, &h)) != GNX_OK) return r;
   ARG(n == h.n, "n differs from the population size");
-  CK(cudaMemcpyAsync(ctx->pop.node[0][h.cur], host_node0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->pop.node[1][h.cur], host_node1, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if ((r = build_order(ctx, h, false)) != GNX_OK) return r;
+  // host arrays are in species order: staged, then scattered to the entries through work.inv
+  int32_t* st = reinterpret_cast<int32_t*>(ctx->work.scratch);
+  CK(cudaMemcpyAsync(st, host_node0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(st + n, host_node1, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_scatter_nodes<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->pop, ctx->work, ctx->d_c, st, st + n, (int)n);
+  CK(cudaGetLastError());
   h.n_nodes = next_node_id;
   h.n_ind_rows = next_individual_row;
   CK(cudaMemcpyAsync(ctx->d_c, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));

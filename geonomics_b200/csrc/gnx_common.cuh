@@ -14,7 +14,7 @@
 // time step runs without a host round trip.
 // ----------------------------------------------------------------------------------------
 struct Counters {
-  int32_t n;         // live individuals (species-order length) at stage entry
+  int32_t n;         // entries of the current half at stage entry (all alive unless `pending`)
   int32_t n_pre;     // n + B: individuals alive before mortality
   int32_t P;         // mating pairs this step
   int32_t B;         // births this step
@@ -35,6 +35,14 @@ struct Counters {
   int32_t n_edges;      // edge rows buffered since the last drain
   int32_t n_born;       // newborn (individual + 2 node) rows buffered since the last drain
   int64_t tsk_t0;       // Counters.t when recording was enabled (node time = -(t - tsk_t0))
+  // mating-grid order + lazy mortality
+  int32_t n_sorted;     // leading entries in (mating cell, id) order with cell_start valid for them
+  int32_t pending;      // 1: the last step's deaths are only flagged (w.alive); the next re-grid drops them
+  int32_t n_alive;      // survivors of the last step (valid while pending)
+  int32_t alive_acc;    // accumulator of k_death's survivor count (zeroed by its last block)
+  uint32_t ticket[2];   // last-block elections (k_regrid, k_death); self-resetting
+  int32_t n_regrid;     // entries placed by the running re-grid (scan total)
+  int32_t pad2;
 };
 #define GNX_ERRBIT_CAPACITY 1
 #define GNX_ERRBIT_DRAWS 2
@@ -42,7 +50,10 @@ struct Counters {
 #define GNX_ERRBIT_MUTABLES 8     // _mutables.pop() on an empty list
 #define GNX_ERRBIT_MUTLOG 16      // mutation log full (rows dropped, bookkeeping still exact)
 
-// Double-buffered scalar SoA in species order + slot-indexed genome rows.
+// Double-buffered scalar SoA + slot-indexed genome rows.  The order of the entries is the
+// MATING-GRID order (cell key, then individual id) established by the re-grid of every step;
+// species order (ascending id = the reference's OrderedDict order) is materialised only when
+// the host reads the population (k_species_gather).
 struct Pop {
   double2* xy[2];      // (x, y) interleaved: always used together, and one 16-byte gather
                        // costs one DRAM burst where two 8-byte gathers cost two
@@ -53,6 +64,7 @@ struct Pop {
   double* z[2];        // [T][cap]
   double* fit[2];
   int32_t* node[2][2]; // [homologue][buffer][cap] tskit node ids (NULL unless recording)
+  int32_t* ord[2];     // species-order ordinal of every entry (ordered mode: injected draws / debug reads)
   uint4* G;            // [cap][2][Wq]
   int32_t* free_slots; // [cap]
   int32_t cap;
@@ -125,10 +137,15 @@ struct Dens {
 struct Work {
   uint32_t* cell_count;
   uint32_t* cell_start;    // [ncell + 1]
-  uint32_t* cellkey;
-  uint32_t* cellrank;
-  int32_t* perm;
-  double2* sxy;            // cell-sorted (x, y)
+  uint32_t* mkey;          // per source entry: packed mating cell (cy << 16 | cx) after movement; GNX_KEY_DEAD = dropped
+  uint32_t* mrank;         // per source entry: arrival rank in its cell (histogram atomic)
+  uint4* bucket;           // per destination cell range: {source entry, packed cell, id lo, id hi}
+  uint32_t* skey;          // packed mating cell of every entry of the current (grid-ordered) half
+  int32_t* inv;            // ordered mode: entry of species-order ordinal i
+  int32_t* perm;           // panmixia: second parent of slot i
+  unsigned long long* sort_keys[2];   // radix sort by id (species order on demand)
+  int32_t* sort_vals[2];
+  uint32_t* sort_hist;     // [256][tiles]
   int32_t* mate;
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]
@@ -152,7 +169,9 @@ struct Work {
   int32_t* fix_count;
   gnx_step_record_t* records;
   int32_t max_records;
+  void* scratch;           // species-order staging of one per-individual field (gnx_read_field)
 };
+#define GNX_KEY_DEAD 0xffffffffu
 
 // tskit record buffers (species.py:692-736): rows accumulated on the device between drains
 struct Tsk {
@@ -229,6 +248,10 @@ struct Params {
   const __half* disp_tab;
   uint32_t seed_lo, seed_hi;
   int32_t store_debug;   // keep n_nbrs / death_p / NP_rast for parity tests
+  int32_t ordered;       // per-individual injected draws are indexed by species-order ordinal (pop.ord),
+                         // and the pair list is built in ascending focal ordinal (the oracle's canonical order)
+  const uint32_t* cs_tab;  // [65536] (half cos | half sin << 16) of every float16 direction: numpy's portable
+                           // float16 cos/sin (movement.py:75-76 on a float16 direction), built at setup
 };
 
 // ----------------------------------------------------------------------------------------

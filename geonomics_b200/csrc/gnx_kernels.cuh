@@ -1,6 +1,12 @@
 // gnx_kernels.cuh -- the per-timestep kernels (sm_100a).  Every kernel is a grid-stride /
 // persistent kernel that reads its problem size from the device-resident Counters, so a
 // whole time step is launched without a host round trip (and is CUDA-graph capturable).
+//
+// Order of the state: the scalar SoA is kept in MATING-GRID order --
+// (cell key, individual id) -- re-established every step by the re-grid that also applies the
+// previous step's mortality.  Per-individual raster reads (conductance neighbourhood, K,
+// death rate, environment) and the neighbour scan then touch contiguous memory; species
+// order (ascending id) is produced on demand for the host (k_species_gather).
 #pragma once
 #include "gnx_common.cuh"
 #include "gnx_scan.cuh"
@@ -9,19 +15,38 @@
 #define GSTRIDE (gridDim.x * blockDim.x)
 
 // ========================================================================================
-// a1 + a2 + a4: age, movement, mating-grid key + per-cell histogram
-//   species.py:567-569 (age); movement.py:34-95 (movement); spatial.py:182-184 (surface
-//   lookup); species.py:937-939 (cells).  Flags select which parts run so the stage-level
-//   C-ABI entry points and the fused step share one kernel.
+// samplers of the movement / dispersal kernels.  Distances and free directions are drawn in
+// float32 (the position update itself is float64, movement.py:75-92): a distance is a
+// continuous random variable and its 2^-24 relative granularity is far below anything a KS
+// test on 10^6 draws resolves (tests/test_cuda_samplers.py), while the float64 log / sqrt /
+// cospi chain was the bulk of the 1490 instructions per individual of the round-1 kernel.
 // ========================================================================================
-// On-the-fly conductance-surface direction.  The reference pre-draws `approx_len` float16
-// samples per cell from this same distribution (spatial.py:365-461); at 4096^2 that table
-// would be 168 GB, so the sample is drawn here instead.  The result is quantised to float16
-// exactly as the table is, so the draw itself runs in float32.
 __device__ __forceinline__ float uniform_f32(RngStream& g) { return (g.u32() >> 8) * (1.0f / 16777216.0f); }
+// (0, 1] with the full 32 random bits near zero, for log(): tails reach 6.6 sigma
+__device__ __forceinline__ float uniform_pos_f32(RngStream& g) { return ((float)g.u32() + 1.0f) * (1.0f / 4294967296.0f); }
+__device__ __forceinline__ float normal_f32(RngStream& g) {
+  const float u1 = uniform_pos_f32(g), u2 = uniform_f32(g);
+  return sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2);
+}
+// numpy legacy wald (inverse Gaussian), lognormal; scipy levy (loc + scale / Z^2)
+__device__ __forceinline__ double sample_distance_f32(RngStream& g, int distr, double p1, double p2) {
+  if (distr == GNX_DISTR_WALD) {
+    const float mean = (float)p1, scale = (float)p2;
+    const float mu_2l = mean / (2.0f * scale);
+    float Y = normal_f32(g);
+    Y = mean * Y * Y;
+    const float X = mean + mu_2l * (Y - sqrtf(4.0f * scale * Y + Y * Y));
+    const float U = uniform_f32(g);
+    return (double)((U <= mean / (mean + X)) ? X : mean * mean / X);
+  } else if (distr == GNX_DISTR_LOGNORMAL) {
+    return (double)expf((float)p1 + (float)p2 * normal_f32(g));
+  } else {
+    const float Z = normal_f32(g);
+    return p1 + p2 / ((double)Z * (double)Z);
+  }
+}
 
 // s of numpy's legacy_vonmises (Best & Fisher): depends on kappa only, computed once per thread
-// outside the per-individual loop
 __device__ __forceinline__ float vonmises_s_f32(float kappa) {
   if (kappa < 1e-8f) return 0.0f;
   const float r = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
@@ -45,27 +70,20 @@ __device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa, float s
   return (uniform_f32(g) < 0.5f) ? -res : res;
 }
 
-__device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const float* rast, int X, int Y,
-                                                             int cx, int cy, int mixture, float kappa,
-                                                             float vm_s) {
-  // spatial.py:365-424, 432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell
-  // dropped; queen directions in raster row-major order.
+// On-the-fly conductance-surface direction.  The reference pre-draws `approx_len` float16
+// samples per cell from this same distribution (spatial.py:365-461); at 4096^2 that table
+// would be 168 GB, so the sample is drawn here instead.  `nv` = the 8 queen neighbours of the
+// zero-embedded raster in row-major order (focal dropped), however they were fetched.
+__device__ __forceinline__ __half surface_direction_from_neigh(RngStream& g, const float* nv, int mixture,
+                                                               float kappa, float vm_s) {
   const float PI_F = 3.14159265358979f;
   const float dirs[8] = {-3 * PI_F / 4, -PI_F / 2, -PI_F / 4, PI_F, 0.0f, 3 * PI_F / 4, PI_F / 2, PI_F / 4};
-  const int di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-  const int dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-  float nv[8];
   float sum = 0.0f, mx = -1.0f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = cy + di[k], j = cx + dj[k];
-    const float v = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0f;
-    nv[k] = v;
-    sum += v;
-    mx = fmaxf(mx, v);
-  }
+  for (int k = 0; k < 8; ++k) { sum += nv[k]; mx = fmaxf(mx, nv[k]); }
   float loc;
   if (mixture) {
+    // spatial.py:411-419: direction k with probability nv[k] / sum (uniform when all are zero)
     const float target = uniform_f32(g) * (sum > 0.0f ? sum : 8.0f);
     float acc = 0.0f;
     loc = dirs[7];
@@ -76,6 +94,7 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
       if (!found && target < acc) { loc = dirs[k]; found = true; }
     }
   } else {
+    // spatial.py:376-381: mean of the directions of the maximum-valued neighbours
     float sacc = 0.0f;
     int cnt = 0;
 #pragma unroll
@@ -92,64 +111,115 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
   return __float2half_rn(v);
 }
 
-// cos/sin of a float16 direction for the on-the-fly path: float32 libm, rounded to half
-// (numpy's portable float16 semantics up to the last float32 ulp)
-__device__ __forceinline__ void sincos_half_fast(__half h, double* s, double* c) {
-  float sf, cf;
-  sincosf(__half2float(h), &sf, &cf);
-  *c = (double)__half2float(__float2half_rn(cf));
-  *s = (double)__half2float(__float2half_rn(sf));
+__device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const float* rast, int X, int Y,
+                                                             int cx, int cy, int mixture, float kappa,
+                                                             float vm_s) {
+  // spatial.py:432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell dropped
+  const int di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  const int dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  float nv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = cy + di[k], j = cx + dj[k];
+    nv[k] = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0f;
+  }
+  return surface_direction_from_neigh(g, nv, mixture, kappa, vm_s);
 }
 
-__global__ void __launch_bounds__(256) k_age_move_bin(Pop pop, Land land, Params prm, DevDraws dr,
-                                                       Work w, Counters* c, int do_age, int do_move,
-                                                       int do_bin) {
-  const int n = c->n, cur = c->cur;
+// cos / sin of a float16 direction exactly as numpy evaluates them on a float16 array (half ->
+// float, correctly rounded cosf, -> half; movement.py:75-76 with the float16 `direction` of
+// spatial.py:184,447): one lookup in the 256 KB table of all 65536 halves built at setup
+__device__ __forceinline__ void sincos_half_tab(const uint32_t* __restrict__ cs_tab, __half h, double* s, double* c) {
+  const uint32_t v = __ldg(&cs_tab[__half_as_ushort(h)]);
+  *c = (double)__half2float(__ushort_as_half((unsigned short)(v & 0xffffu)));
+  *s = (double)__half2float(__ushort_as_half((unsigned short)(v >> 16)));
+}
+
+// mating-grid cell of a position, packed (cy << 16 | cx); the grid has < 65536 cells per axis
+__device__ __forceinline__ uint32_t mating_cell(const Land& land, double x, double y) {
+  int cx = (int)floor(x / land.cell_size), cy = (int)floor(y / land.cell_size);
+  cx = min(cx, land.ncx - 1);
+  cy = min(cy, land.ncy - 1);
+  return ((uint32_t)cy << 16) | (uint32_t)cx;
+}
+__device__ __forceinline__ uint32_t cell_linear(const Land& land, uint32_t packed) {
+  return (packed >> 16) * (uint32_t)land.ncx + (packed & 0xffffu);
+}
+
+// ========================================================================================
+// a1 + a2 + a4 (+ a16 removal): age, movement, mating-grid key + per-cell histogram; entries the
+// previous step's mortality flagged dead are dropped here (their genome rows go back to the
+// free list) -- the re-grid that follows never copies them.
+//   species.py:567-569 (age); movement.py:34-95 (movement); spatial.py:182-184 (surface
+//   lookup); species.py:937-939 (cells); demography.py:175-180 (removal).  Flags select which
+//   parts run so the stage-level C-ABI entry points and the fused step share one kernel.
+// ========================================================================================
+__global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm, DevDraws dr,
+                                                   Work w, Counters* c, int do_age, int do_move,
+                                                   int do_key) {
+  const int n = c->n, cur = c->cur, pending = c->pending;
   const int64_t t = c->t;
   double2* __restrict__ XY = pop.xy[cur];
+  const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
   const float vm_s = vonmises_s_f32((float)prm.c.move_surf_kappa);
-  for (int i = GTID; i < n; i += GSTRIDE) {
-    if (do_age) pop.age[cur][i] += 1;
-    const double2 xy0 = XY[i];
+  const int lane = threadIdx.x & 31;
+  // whole warps stay in the loop (ballots below): the tail is masked by `live`
+  for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {
+    const int p = base + threadIdx.x;
+    const bool in = p < n;
+    const bool dead = in && pending && !w.alive[p];
+    if (pending && do_key) {
+      // lazy mortality (demography.py:175-180): the dead leave the population here
+      const unsigned dm = __ballot_sync(0xffffffffu, dead && !prm.burn);
+      if (dm) {
+        int pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&c->n_free, __popc(dm));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (dead && !prm.burn) pop.free_slots[pos0 + __popc(dm & ((1u << lane) - 1u))] = pop.gslot[cur][p];
+      }
+      if (dead) w.mkey[p] = GNX_KEY_DEAD;
+    }
+    if (!in || dead) continue;
+    if (do_age) pop.age[cur][p] += 1;
+    const double2 xy0 = XY[p];
     double x = xy0.x, y = xy0.y;
     if (do_move) {
-      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MOVE, t);
+      const int io = ord ? ord[p] : p;                  // injected draws are indexed by species ordinal
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MOVE, t);
       double cs, sn;
       if (prm.c.move_surf_mode == GNX_SURF_TABLE) {
-        int cx = (int)x, cy = (int)y;
-        int col = dr.move_choice ? dr.move_choice[i] : (int)choose_k(g.u32(), prm.c.surf_approx_len);
-        __half h = prm.move_tab[((size_t)cy * land.X + cx) * prm.c.surf_approx_len + col];
-        sincos_half(h, &sn, &cs);
+        const int cx = (int)x, cy = (int)y;
+        const int col = dr.move_choice ? dr.move_choice[io] : (int)choose_k(g.u32(), prm.c.surf_approx_len);
+        const __half h = prm.move_tab[((size_t)cy * land.X + cx) * prm.c.surf_approx_len + col];
+        sincos_half_tab(prm.cs_tab, h, &sn, &cs);
       } else if (prm.c.move_surf_mode == GNX_SURF_ONTHEFLY) {
-        int cx = (int)x, cy = (int)y;
-        const __half d = surface_direction_onthefly(
-            g, land.surf_f32[0], land.X, land.Y, cx, cy,
-            prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa, vm_s);
-        sincos_half_fast(d, &sn, &cs);
+        const __half d = surface_direction_onthefly(g, land.surf_f32[0], land.X, land.Y, (int)x, (int)y,
+                                                    prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa, vm_s);
+        sincos_half_tab(prm.cs_tab, d, &sn, &cs);
       } else if (dr.move_dir) {
-        sincos(dr.move_dir[i], &sn, &cs);
+        sincos(dr.move_dir[io], &sn, &cs);
       } else if (prm.c.dir_kappa < 1e-8) {
         // numpy vonmises(mu, kappa < 1e-8) = pi*(2U - 1) (mu ignored): movement.py:55
-        sincospi(2.0 * g.uniform() - 1.0, &sn, &cs);
+        float sf, cf;
+        sincospif(2.0f * uniform_f32(g) - 1.0f, &sf, &cf);
+        sn = (double)sf;
+        cs = (double)cf;
       } else {
         sincos(sample_vonmises(g, prm.c.dir_mu, prm.c.dir_kappa), &sn, &cs);
       }
-      double dist = dr.move_dist ? dr.move_dist[i]
-                                 : sample_distance(g, prm.c.move_distr, prm.c.move_p1, prm.c.move_p2);
+      const double dist = dr.move_dist ? dr.move_dist[io]
+                                       : sample_distance_f32(g, prm.c.move_distr, prm.c.move_p1, prm.c.move_p2);
       double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
       if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
       if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
       x = clampd(__dadd_rn(x, dx), 0.0, land.max_x);
       y = clampd(__dadd_rn(y, dy), 0.0, land.max_y);
-      XY[i] = make_double2(x, y);
+      XY[p] = make_double2(x, y);
     }
-    if (do_bin) {
-      int cx = (int)floor(x / land.cell_size), cy = (int)floor(y / land.cell_size);
-      cx = min(cx, land.ncx - 1);
-      cy = min(cy, land.ncy - 1);
-      uint32_t key = (uint32_t)cy * land.ncx + cx;
-      w.cellkey[i] = key;
-      w.cellrank[i] = atomicAdd(&w.cell_count[key], 1u);
+    if (do_key) {
+      const uint32_t key = mating_cell(land, x, y);
+      w.mkey[p] = key;
+      w.mrank[p] = atomicAdd(&w.cell_count[cell_linear(land, key)], 1u);
     }
   }
 }
@@ -162,46 +232,91 @@ struct CellScan {
   __device__ int size(const Counters*) const { return ncell; }
   __device__ u64 value(int i) const { return cnt[i]; }
   __device__ void apply(int i, u64, u64 ex) const { start[i] = (uint32_t)ex; }
-  __device__ void total(Counters*, u64 tot) const { start[ncell] = (uint32_t)tot; }
+  __device__ void total(Counters* c, u64 tot) const {
+    start[ncell] = (uint32_t)tot;
+    c->n_regrid = (int)tot;
+  }
 };
 
-__global__ void __launch_bounds__(256) k_scatter_perm(Work w, const Counters* c) {
-  const int n = c->n;
-  for (int i = GTID; i < n; i += GSTRIDE) w.perm[w.cell_start[w.cellkey[i]] + w.cellrank[i]] = i;
-}
-
-// per-cell ordering by species-order ordinal: makes the binned order a *stable* counting
-// sort (deterministic whatever order the histogram atomics retired in).
-__global__ void __launch_bounds__(256) k_cell_sort(Work w, int ncell) {
-  for (int cell = GTID; cell < ncell; cell += GSTRIDE) {
-    const int s = w.cell_start[cell], e = w.cell_start[cell + 1];
-    for (int a = s + 1; a < e; ++a) {
-      int v = w.perm[a];
-      int b = a - 1;
-      while (b >= s && w.perm[b] > v) {
-        w.perm[b + 1] = w.perm[b];
-        --b;
-      }
-      w.perm[b + 1] = v;
-    }
+// every surviving entry announces itself in its destination cell's range (arrival order)
+__global__ void __launch_bounds__(256) k_bucket(Pop pop, Land land, Work w, const Counters* c) {
+  const int n = c->n, cur = c->cur;
+  for (int p = GTID; p < n; p += GSTRIDE) {
+    const uint32_t key = w.mkey[p];
+    if (key == GNX_KEY_DEAD) continue;
+    const unsigned long long id = (unsigned long long)pop.idx[cur][p];
+    w.bucket[w.cell_start[cell_linear(land, key)] + w.mrank[p]] =
+        make_uint4((uint32_t)p, key, (uint32_t)id, (uint32_t)(id >> 32));
   }
 }
 
-__global__ void __launch_bounds__(256) k_gather_sorted(Pop pop, Work w, const Counters* c) {
-  const int n = c->n, cur = c->cur;
-  for (int p = GTID; p < n; p += GSTRIDE) {
-    int i = w.perm[p];
-    w.sxy[p] = pop.xy[cur][i];
+// The re-grid: destination entry q takes the source entry whose id has rank (q - cell start)
+// among the ids of its cell -- (cell, id) order whatever order the histogram atomics retired
+// in -- and gathers that entry's whole record into the other half.  One pass moves the state:
+// it is this step's counting sort AND the previous step's mortality compaction.
+__global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Counters* c, int age_inc, int ordered) {
+  const int total = c->n_regrid, s = c->cur, d = s ^ 1, T = pop.T;
+  for (int q = GTID; q < total; q += GSTRIDE) {
+    const uint4 e = w.bucket[q];
+    const uint32_t lin = cell_linear(land, e.y);
+    const int cs = (int)w.cell_start[lin], ce = (int)w.cell_start[lin + 1];
+    const unsigned long long id = ((unsigned long long)e.w << 32) | e.z;
+    int r = 0;
+    for (int j = cs; j < ce; ++j) {
+      const uint4 o = __ldg(&w.bucket[j]);
+      r += ((((unsigned long long)o.w << 32) | o.z) < id) ? 1 : 0;
+    }
+    const int dst = cs + r, src = (int)e.x;
+    // all loads of the record before its first store (the halves cannot be proven disjoint)
+    const double2 xy = pop.xy[s][src];
+    const double fit = pop.fit[s][src];
+    const int32_t age = pop.age[s][src], gs = pop.gslot[s][src];
+    const int8_t sx = pop.sex[s][src];
+    double z[GNX_MAX_TRAITS];
+#pragma unroll
+    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
+      if (tt < T) z[tt] = pop.z[s][(size_t)tt * pop.cap + src];
+    int32_t na = 0, nb = 0, od = 0;
+    if (pop.node[0][0]) { na = pop.node[0][s][src]; nb = pop.node[1][s][src]; }
+    if (ordered) od = pop.ord[s][src];
+    pop.xy[d][dst] = xy;
+    pop.fit[d][dst] = fit;
+    pop.idx[d][dst] = (int64_t)id;
+    pop.age[d][dst] = age + age_inc;
+    pop.gslot[d][dst] = gs;
+    pop.sex[d][dst] = sx;
+#pragma unroll
+    for (int tt = 0; tt < GNX_MAX_TRAITS; ++tt)
+      if (tt < T) pop.z[d][(size_t)tt * pop.cap + dst] = z[tt];
+    if (pop.node[0][0]) { pop.node[0][d][dst] = na; pop.node[1][d][dst] = nb; }
+    if (ordered) { pop.ord[d][dst] = od; w.inv[od] = dst; }
+    w.skey[dst] = e.y;
+  }
+  // the last block to finish publishes the new population: size, order, buffer parity
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&c->ticket[0], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    c->n = total;
+    c->n_pre = total;
+    c->n_sorted = total;
+    c->pending = 0;
+    c->cur = d;
+    c->ticket[0] = 0u;
   }
 }
 
 // ========================================================================================
 // a5: neighbour scan + mate choice.  species.py:2157-2215, spatial.py:191-245.
-//   One thread per focal, walking the three contiguous row-ranges of the cell-sorted
-//   (x, y) pairs that cover its 3x3 cell block with 128-bit loads.  Closed ball on squared
-//   distances, products and sum rounded separately (as the reference's cKDTree does).
-//   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are buffered
-//           in one pass and the k-th is picked, k = (R * count) >> 32
+//   The state is in (cell, id) order, so the candidates of a focal are three contiguous
+//   ranges of pop.xy (its 3x3 cell block, row by row) read with 128-bit loads, consecutive
+//   focals share them through L1, and a candidate's position in the arrays IS its canonical
+//   rank.  Closed ball on squared distances, products and sum rounded separately (as the
+//   reference's cKDTree does).
+//   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are kept as bit
+//           masks and the k-th is picked, k = (R * count) >> 32
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
@@ -219,12 +334,12 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
   const double r2 = prm.r2, radius = prm.c.mating_radius;
-  const double2* __restrict__ sxy = w.sxy;
+  const double2* __restrict__ sxy = pop.xy[cur];
+  const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
   for (int p = GTID; p < n; p += GSTRIDE) {
     const double2 f = sxy[p];
-    int cx = (int)floor(f.x / land.cell_size), cy = (int)floor(f.y / land.cell_size);
-    cx = min(cx, land.ncx - 1);
-    cy = min(cy, land.ncy - 1);
+    const uint32_t key = w.skey[p];
+    const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
     int lo[3], hi[3];
 #pragma unroll
@@ -288,7 +403,7 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       }
     }
     if (MODE == 0 && overflow) {
-      // rare: a row range longer than 32 candidates -- count exactly, select by a second walk
+      // rare: a row range longer than 64 candidates -- count exactly, select by a second walk
       cnt = 0;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -299,17 +414,17 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
           cnt += (d2 <= r2 && q != p) ? 1 : 0;
         }
     }
-    const int i = w.perm[p];
-    if (prm.store_debug) w.n_nbrs[i] = cnt;
+    if (prm.store_debug) w.n_nbrs[p] = cnt;
     int mate = -1;
     if (cnt > 0) {
-      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_MATE, t);
+      const int io = ord ? ord[p] : p;
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
       int sel_q = -1;
       if (MODE == 1) {
         sel_q = best_q;
       } else if (MODE == 2) {
         if (n_w > 0) {
-          const double u = dr.mate_inv_u ? dr.mate_inv_u[i] : g.uniform();
+          const double u = dr.mate_inv_u ? dr.mate_inv_u[io] : g.uniform();
           const double target = u * wsum;
           double acc = 0.0;
           int last = -1;
@@ -329,7 +444,7 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
           if (sel_q < 0) sel_q = last;
         }
       } else {
-        const uint32_t R = dr.mate_R ? dr.mate_R[i] : g.u32();
+        const uint32_t R = dr.mate_R ? dr.mate_R[io] : g.u32();
         int k = (int)choose_k(R, (uint32_t)cnt);
         if (!overflow) {
           uint32_t msel = 0u;
@@ -357,7 +472,7 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
             if (k >= cl) { k -= cl; msel >>= wdt; bit += wdt; }
           }
           sel_q = base_q + bit;
-        } else {                         // rare: a row range longer than 32, walk again
+        } else {                         // rare: a row range longer than 64, walk again
 #pragma unroll
           for (int r = 0; r < 3; ++r)
             for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
@@ -372,40 +487,47 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
         }
       }
       if (sel_q >= 0) {
-        const double u = dr.mate_u ? dr.mate_u[i] : g.uniform();
-        if (u < prm.c.b) mate = w.perm[sel_q];       // species.py:2212-2214
+        const double u = dr.mate_u ? dr.mate_u[io] : g.uniform();
+        if (u < prm.c.b) mate = sel_q;               // species.py:2212-2214
       }
     }
-    w.mate[i] = mate;
+    w.mate[p] = mate;
   }
 }
 
 // Panmixia (mating_radius = None), species.py:2178-2194: n_mates ~ Binomial(N, b) mating slots
 // (one Bernoulli(b) per individual has exactly that sum), each drawing two individuals with
 // replacement; selfing pairs are dropped; with sexes, column 0 must be female and column 1
-// male (mating.py:41-55).  No de-duplication (mating.py:64-65).
+// male (mating.py:41-55).  No de-duplication (mating.py:64-65).  Slot i belongs to the
+// individual of species ordinal i; the drawn numbers are ordinals too (mapped to entries
+// through w.inv in ordered mode; without injected draws any bijection is as uniform).
 __global__ void __launch_bounds__(256) k_panmixia(Pop pop, Params prm, DevDraws dr, Work w, const Counters* c) {
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
+  const int32_t* __restrict__ inv = prm.ordered ? w.inv : nullptr;
   for (int i = GTID; i < n; i += GSTRIDE) {
-    RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_PANMIXIA, t);
+    const int p = inv ? inv[i] : i;
+    RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_PANMIXIA, t);
     const double u = dr.pan_u ? dr.pan_u[i] : g.uniform();
     const uint32_t R0 = dr.pan_R ? dr.pan_R[2 * i] : g.u32();
     const uint32_t R1 = dr.pan_R ? dr.pan_R[2 * i + 1] : g.u32();
     const bool active = prm.c.b >= 1.0 || u < prm.c.b;
-    const int a = (int)choose_k(R0, (uint32_t)n), b2 = (int)choose_k(R1, (uint32_t)n);
+    int a = (int)choose_k(R0, (uint32_t)n), b2 = (int)choose_k(R1, (uint32_t)n);
     bool ok = active && a != b2;
+    if (inv) { a = inv[a]; b2 = inv[b2]; }
     if (ok && prm.c.sex) ok = pop.sex[cur][a] == 0 && pop.sex[cur][b2] == 1;
     w.mate[i] = ok ? a : -1;
     w.perm[i] = b2;
-    if (prm.store_debug) w.n_nbrs[i] = n - 1;
+    if (prm.store_debug) w.n_nbrs[p] = n - 1;
   }
 }
 
 // ========================================================================================
 // a6 + a8: sex filter / reciprocal de-dup (mating.py:41-63), stream compaction into the
-// canonical pair list, births per pair (species.py:604-609, mating.py:120-126), offspring
-// table, pair midpoints (demography.py:60-72).
+// pair list, births per pair (species.py:604-609, mating.py:120-126), offspring table, pair
+// midpoints (demography.py:60-72).  Pairs hold ENTRY numbers (positions in the current half).
+// The list is built in entry (= mating-grid) order; in ordered mode (injected draws) in
+// ascending focal ordinal through w.inv -- the oracle's canonical order.
 // ========================================================================================
 struct PairScan {
   Pop pop;
@@ -414,18 +536,22 @@ struct PairScan {
   int32_t sexed;
   int32_t fixed_nb;      // > 0: n_births_fixed
   int32_t panmixia;      // pairs are (mate[i], perm[i]) drawn by k_panmixia, already filtered
+  int32_t ordered;
   __device__ int size(const Counters* c) const { return c->n; }
+  __device__ int entry(int i) const { return (ordered && !panmixia) ? w.inv[i] : i; }
   __device__ bool keep(int i) const {
-    int m = w.mate[i];
+    if (panmixia) return w.mate[i] >= 0;
+    const int p = entry(i);
+    const int m = w.mate[p];
     if (m < 0) return false;
-    if (panmixia) return true;
     if (sexed) {
       const int8_t* sx = pop.sex[cc->cur];
-      return sx[i] == 0 && sx[m] == 1;                 // mating.py:41-55
+      return sx[p] == 0 && sx[m] == 1;                 // mating.py:41-55
     }
-    return !(w.mate[m] == i && m < i);                 // mating.py:62-63 (canonical)
+    // mating.py:62-63: a reciprocal couple is kept once, under the focal with the smaller id
+    return !(w.mate[m] == p && pop.idx[cc->cur][m] < pop.idx[cc->cur][p]);
   }
-  // the reduce pass evaluates the predicate (a dependent random gather) once and leaves it in
+  // the reduce pass evaluates the predicate (dependent gathers) once and leaves it in
   // w.alive, which the mortality stage only rewrites later in the step
   __device__ u64 value_first(int i) const {
     const bool k = keep(i);
@@ -442,8 +568,8 @@ struct PairScan {
     for (int k = 0; k < SCAN_ITEMS; ++k) {
       on[k] = idx[k] < n && v[k] != 0;
       if (on[k]) {
-        m[k] = panmixia ? w.perm[idx[k]] : w.mate[idx[k]];
-        a[k] = panmixia ? w.mate[idx[k]] : idx[k];
+        if (panmixia) { a[k] = w.mate[idx[k]]; m[k] = w.perm[idx[k]]; }
+        else { a[k] = entry(idx[k]); m[k] = w.mate[a[k]]; }
       }
     }
     double2 pa[SCAN_ITEMS], pm[SCAN_ITEMS];
@@ -1018,21 +1144,24 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
         int col = dr.disp_choice ? dr.disp_choice[(size_t)o * dr.disp_R + tries]
                                  : (int)choose_k(g.u32(), prm.c.surf_approx_len);
         __half h = prm.disp_tab[((size_t)((int)my) * land.X + (int)mx) * prm.c.surf_approx_len + col];
-        sincos_half(h, &sn, &cs);
+        sincos_half_tab(prm.cs_tab, h, &sn, &cs);
       } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
         const __half d = surface_direction_onthefly(
             g, land.surf_f32[1], land.X, land.Y, (int)mx,
             (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa, vm_s);
-        sincos_half_fast(d, &sn, &cs);
+        sincos_half_tab(prm.cs_tab, d, &sn, &cs);
       } else if (dr.disp_dir) {
         sincos(dr.disp_dir[(size_t)o * dr.disp_R + tries], &sn, &cs);
       } else {
         // NB reference passes mu=0, kappa=0 whatever the species' params (species.py:650-653):
         // vonmises(0, 0) = pi*(2U - 1)
-        sincospi(2.0 * g.uniform() - 1.0, &sn, &cs);
+        float sf, cf;
+        sincospif(2.0f * uniform_f32(g) - 1.0f, &sf, &cf);
+        sn = (double)sf;
+        cs = (double)cf;
       }
       double dist = dr.disp_dist ? dr.disp_dist[(size_t)o * dr.disp_R + tries]
-                                 : sample_distance(g, prm.c.disp_distr, prm.c.disp_p1, prm.c.disp_p2);
+                                 : sample_distance_f32(g, prm.c.disp_distr, prm.c.disp_p1, prm.c.disp_p2);
       double dx = __dmul_rn(cs, dist), dy = __dmul_rn(sn, dist);
       if (prm.c.res_ratio_x != 1.0) dx = __dmul_rn(dx, prm.c.res_ratio_x);
       if (prm.c.res_ratio_y != 1.0) dy = __dmul_rn(dy, prm.c.res_ratio_y);
@@ -1059,6 +1188,7 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
     pop.sex[cur][dst] = (int8_t)sex;
     pop.idx[cur][dst] = oid;
     if (prm.burn) pop.gslot[cur][dst] = -1;
+    if (prm.ordered) pop.ord[cur][dst] = dst;       // newborns follow everyone in species order (ids ascend)
     if (tsk.enabled) {
       // species.py:692-736: one individuals row (location = [x, y, z...], metadata = idx) and
       // two nodes rows (flags=1, time=-t, population=0) per offspring, in offspring order
@@ -1743,13 +1873,18 @@ __global__ void __launch_bounds__(256) k_raster_d_fix(Dens d, Land land, Params 
 // ========================================================================================
 // a3 + a15 + a16 (draw): environment gather (species.py:913-922), fitness
 // (selection.py:51-112), death probability (selection.py:119-125, demography.py:306-321),
-// Bernoulli mortality draw (demography.py:175-176).
+// Bernoulli mortality draw (demography.py:175-176).  The first n entries are in mating-grid
+// order, so the packed (d, e...) raster records of a warp's 32 individuals sit in a few
+// neighbouring sectors.  With end_step = 1 (fused step) the last block to finish also closes
+// the time step (Species._set_Nt species.py:554, the bookkeeping of demography.py:324-329):
+// the dead are only FLAGGED here -- the next step's re-grid drops them.
 // ========================================================================================
 __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
-                                                const Counters* c, Mut mu) {
-  const int n = c->n_pre, cur = c->cur, T = pop.T;
+                                                Counters* c, Mut mu, int end_step) {
+  const int n0 = c->n, n = c->n + c->B, cur = c->cur, T = pop.T;
   const int64_t t = c->t;
-  const size_t plane = (size_t)land.X * land.Y;
+  const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
+  int live = 0;
   for (int i = GTID; i < n; i += GSTRIDE) {
     const double2 xy = pop.xy[cur][i];
     const double x = xy.x, y = xy.y;
@@ -1791,17 +1926,62 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
     if (prm.c.max_age >= 0 && pop.age[cur][i] > prm.c.max_age) p = 1.0;    // demography.py:319-321
     if (prm.store_debug) w.death_p[i] = p;
     double u;
-    if (dr.death_u) u = dr.death_u[i];
+    if (dr.death_u) u = dr.death_u[(ord && i < n0) ? ord[i] : i];          // newborn o has ordinal n0 + o
     else {
       RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][i], SITE_DEATH, t);
       u = g.uniform();
     }
-    w.alive[i] = !(u < p);
+    const bool alive = !(u < p);
+    w.alive[i] = alive;
+    live += alive ? 1 : 0;
+  }
+  if (!end_step) return;
+  // ---- survivors of the step, then (last block) the end-of-step bookkeeping
+  __shared__ int blk_live;
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) blk_live = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+  if ((threadIdx.x & 31) == 0 && live) atomicAdd(&blk_live, live);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blk_live) atomicAdd(&c->alive_acc, blk_live);
+    __threadfence();
+    is_last = atomicAdd(&c->ticket[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const int survivors = atomicAdd(&c->alive_acc, 0);
+    gnx_step_record_t r;
+    r.t = c->t;
+    r.Nt = survivors;
+    r.n_births = c->B;
+    r.n_deaths = n - survivors;
+    r.n_pairs = c->P;
+    if (c->n_rec < w.max_records) w.records[c->n_rec] = r;
+    c->n_rec += 1;
+    c->n = n;                    // entries, dead ones included until the next re-grid drops them
+    c->n_pre = n;
+    c->n_alive = survivors;
+    c->pending = 1;
+    c->max_idx += c->B;
+    c->t += 1;
+    c->P = 0;
+    c->B = 0;
+    c->deaths = 0;
+    c->nmax_bits = 0ull;
+    c->alive_acc = 0;
+    c->ticket[1] = 0u;
   }
 }
 
-// a16 (removal): stable compaction of survivors into the other half of the SoA; the dead
-// hand their genome slots back to the free list (no genome bytes move).
+// a16 (removal), explicit form: stable compaction of survivors into the other half of the SoA
+// (entry order -- i.e. mating-grid order -- is preserved); the dead hand their genome slots
+// back to the free list (no genome bytes move).  Used by the staged gnx_mortality, by panmixia
+// (no re-grid to fold the removal into) and whenever the host needs the population between
+// steps while deaths are pending.
 struct MortalityScan {
   Pop pop;
   Work w;
@@ -1884,46 +2064,197 @@ struct MortalityScan {
   }
 };
 
-__global__ void k_end_step(Counters* c, Work w, int burn) {
+// closes an explicit compaction.  record = 1: the staged gnx_mortality, which also ends the time
+// step; record = 0: deaths that a fused step had left pending (its k_death already ended the step)
+__global__ void k_end_step(Counters* c, Work w, int burn, int record) {
   const int survivors = c->pad[0];
-  gnx_step_record_t r;
-  r.t = c->t;
-  r.Nt = survivors;
-  r.n_births = c->B;
-  r.n_deaths = c->deaths;
-  r.n_pairs = c->P;
-  if (c->n_rec < w.max_records) w.records[c->n_rec] = r;
-  c->n_rec += 1;
+  if (record) {
+    gnx_step_record_t r;
+    r.t = c->t;
+    r.Nt = survivors;
+    r.n_births = c->B;
+    r.n_deaths = c->deaths;
+    r.n_pairs = c->P;
+    if (c->n_rec < w.max_records) w.records[c->n_rec] = r;
+    c->n_rec += 1;
+    c->max_idx += c->B;
+    c->t += 1;
+  }
   if (!burn) c->n_free += c->deaths;
   c->n = survivors;
   c->n_pre = survivors;
-  c->max_idx += c->B;
+  c->n_alive = survivors;
+  c->n_sorted = 0;               // entry order is kept, but cell_start no longer matches the entries
+  c->pending = 0;
   c->cur ^= 1;
-  c->t += 1;
   c->P = 0;
   c->B = 0;
   c->deaths = 0;
   c->nmax_bits = 0ull;
 }
 
-// environment values for every live individual (API view of ind.e, species.py:913-922)
-__global__ void __launch_bounds__(256) k_sample_env(Pop pop, Land land, Work w, const Counters* c) {
-  const int n = c->n, cur = c->cur;
+// ========================================================================================
+// Species order on demand.  The reference's Species is an OrderedDict in ascending id; the
+// host-facing views (download, field reads, injected draws, tskit renumbering) need each
+// entry's rank by id: an LSD radix sort of (id, entry) pairs, 8 bits per pass, only as many
+// passes as the largest id has bits.
+// ========================================================================================
+#define RS_BLOCK 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_BLOCK * RS_ITEMS)
+
+__global__ void __launch_bounds__(256) k_order_keys(Pop pop, Work w, const Counters* c, int n, int exclude_dead) {
+  const int cur = c->cur;
+  for (int p = GTID; p < n; p += GSTRIDE) {
+    const bool dead = exclude_dead && !w.alive[p];
+    w.sort_keys[0][p] = dead ? ~0ull : (unsigned long long)pop.idx[cur][p];
+    w.sort_vals[0][p] = p;
+  }
+}
+
+__global__ void __launch_bounds__(RS_BLOCK) k_radix_hist(const unsigned long long* __restrict__ keys, int n, int shift,
+                                                          uint32_t* hist, int ntiles) {
+  __shared__ uint32_t h[256];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const int i = tile * RS_TILE + r * RS_BLOCK + threadIdx.x;
+      if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + tile] = h[threadIdx.x];       // digit-major: one scan orders everything
+    __syncthreads();
+  }
+}
+
+struct RadixScan {
+  uint32_t* hist;
+  int len;
+  __device__ int size(const Counters*) const { return len; }
+  __device__ u64 value(int i) const { return hist[i]; }
+  __device__ void apply(int i, u64, u64 ex) const { hist[i] = (uint32_t)ex; }
+  __device__ void total(Counters*, u64) const {}
+};
+
+__global__ void __launch_bounds__(RS_BLOCK) k_radix_scatter(const unsigned long long* __restrict__ kin,
+                                                             const int32_t* __restrict__ vin, unsigned long long* kout,
+                                                             int32_t* vout, int n, int shift, const uint32_t* hist,
+                                                             int ntiles) {
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wcnt[RS_BLOCK / 32][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    base[threadIdx.x] = hist[(size_t)threadIdx.x * ntiles + tile];
+    __syncthreads();
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const int i = tile * RS_TILE + r * RS_BLOCK + threadIdx.x;
+      const bool valid = i < n;
+      const unsigned long long key = valid ? kin[i] : 0ull;
+      const uint32_t dgt = (uint32_t)(key >> shift) & 255u;
+#pragma unroll
+      for (int k = 0; k < RS_BLOCK / 32; ++k) wcnt[k][threadIdx.x] = 0u;
+      __syncthreads();
+      // stable rank inside the warp: lanes with the same digit, in lane order
+      const unsigned same = __match_any_sync(0xffffffffu, valid ? dgt : (256u + lane));
+      const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+      if (valid && rank_in_warp == 0) wcnt[warp][dgt] = (uint32_t)__popc(same);
+      __syncthreads();
+      {                                             // thread d: running offsets of digit d over the warps
+        uint32_t run = base[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < RS_BLOCK / 32; ++k) {
+          const uint32_t cnt = wcnt[k][threadIdx.x];
+          wcnt[k][threadIdx.x] = run;
+          run += cnt;
+        }
+        base[threadIdx.x] = run;
+      }
+      __syncthreads();
+      if (valid) {
+        const uint32_t dst = wcnt[warp][dgt] + (uint32_t)rank_in_warp;
+        kout[dst] = key;
+        vout[dst] = vin[i];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// sorted (id, entry) pairs -> ord (entry -> ordinal) and inv (ordinal -> entry)
+__global__ void __launch_bounds__(256) k_order_finish(Pop pop, Work w, const Counters* c, const int32_t* __restrict__ vals,
+                                                       int n_ranked) {
+  const int cur = c->cur;
+  for (int i = GTID; i < n_ranked; i += GSTRIDE) {
+    const int p = vals[i];
+    pop.ord[cur][p] = i;
+    w.inv[i] = p;
+  }
+}
+
+// the population in species order, written into the idle half: x | y as two plain arrays in the
+// xy buffer ([0, n) and [cap, cap + n)), every other field at its ordinal; z additionally as
+// [n][T] rows for the host layout
+__global__ void __launch_bounds__(256) k_species_gather(Pop pop, Work w, const Counters* c, int n, double* z_rows) {
+  const int s = c->cur, d = s ^ 1;
+  double* sx = reinterpret_cast<double*>(pop.xy[d]);
+  double* sy = sx + pop.cap;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const int p = w.inv[i];
+    const double2 v = pop.xy[s][p];
+    sx[i] = v.x;
+    sy[i] = v.y;
+    pop.age[d][i] = pop.age[s][p];
+    pop.sex[d][i] = pop.sex[s][p];
+    pop.idx[d][i] = pop.idx[s][p];
+    pop.fit[d][i] = pop.fit[s][p];
+    pop.gslot[d][i] = pop.gslot[s][p];
+    for (int tt = 0; tt < pop.T; ++tt) {
+      const double z = pop.z[s][(size_t)tt * pop.cap + p];
+      pop.z[d][(size_t)tt * pop.cap + i] = z;
+      if (z_rows) z_rows[(size_t)i * pop.T + tt] = z;
+    }
+  }
+}
+
+// one per-entry work array in species order (parity tests): out[i] = src[inv[i]].  For arrays
+// of ENTRY numbers (mate, pairs) the values are translated to ordinals as well.
+template <class TT>
+__global__ void __launch_bounds__(256) k_gather_by_inv(const TT* __restrict__ src, TT* out, const int32_t* __restrict__ inv, int n) {
+  for (int i = GTID; i < n; i += GSTRIDE) out[i] = src[inv[i]];
+}
+__global__ void __launch_bounds__(256) k_gather_mate(const int32_t* __restrict__ mate, int32_t* out,
+                                                      const int32_t* __restrict__ inv, const int32_t* __restrict__ ord, int n,
+                                                      int by_slot) {
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const int m = mate[by_slot ? i : inv[i]];
+    out[i] = m < 0 ? -1 : ord[m];
+  }
+}
+__global__ void __launch_bounds__(256) k_translate_entries(const int32_t* __restrict__ src, int32_t* out,
+                                                            const int32_t* __restrict__ ord, int n) {
+  for (int i = GTID; i < n; i += GSTRIDE) out[i] = src[i] < 0 ? -1 : ord[src[i]];
+}
+
+// environment values for every live individual in species order (API view of ind.e, species.py:913-922)
+__global__ void __launch_bounds__(256) k_sample_env(Pop pop, Land land, Work w, const Counters* c, int n) {
+  const int cur = c->cur;
   const size_t plane = (size_t)land.X * land.Y;
   for (int i = GTID; i < n; i += GSTRIDE) {
-    const double2 xy = pop.xy[cur][i];
+    const double2 xy = pop.xy[cur][w.inv[i]];
     const size_t cell = (size_t)((int)xy.y) * land.X + (int)xy.x;
     for (int l = 0; l < land.n_layers; ++l) w.e_out[(size_t)i * land.n_layers + l] = land.rasters[l * plane + cell];
   }
 }
 
-// genome rows gathered into species order (download) / scattered from it (upload)
-__global__ void __launch_bounds__(256) k_gather_genomes(Pop pop, uint4* out, const Counters* c) {
-  const int n = c->n, cur = c->cur, row = 2 * pop.Wq;
+// genome rows gathered into species order (download): gslot = the species-ordered slot array
+__global__ void __launch_bounds__(256) k_gather_genomes(Pop pop, const int32_t* __restrict__ gslot, uint4* out, int n) {
+  const int row = 2 * pop.Wq;
   const long long total = (long long)n * row;
   for (long long k = GTID; k < total; k += GSTRIDE) {
     const int i = (int)(k / row), q = (int)(k - (long long)i * row);
-    out[k] = pop.G[(size_t)pop.gslot[cur][i] * row + q];
+    out[k] = pop.G[(size_t)gslot[i] * row + q];
   }
 }
 
@@ -1940,7 +2271,8 @@ __global__ void __launch_bounds__(256) k_pack_env(Land land, Traits tr, Work w, 
 }
 
 // upload epilogue: identity genome slots, default ids, z [n][T] -> [T][cap], counters reset
-// (time-step counter and record cursor carry over)
+// (time-step counter and record cursor carry over).  The uploaded order is kept as it is: the
+// first re-grid sorts it.
 __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int n, long long max_idx, int make_ids,
                                                         const double* z_rows) {
   // x and y arrive as two plain arrays staged in the other half: [0, n) and [cap, cap + n)
@@ -1961,26 +2293,8 @@ __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int
     c->n = n; c->n_pre = n; c->P = 0; c->B = 0; c->deaths = 0; c->n_free = 0; c->n_slots = n; c->cur = 0;
     c->max_idx = max_idx; c->err = 0; c->nmax_bits = 0ull;
     c->n_nodes = 2 * n; c->n_ind_rows = n; c->n_edges = 0; c->n_born = 0;
+    c->n_sorted = 0; c->pending = 0; c->n_alive = n; c->alive_acc = 0; c->ticket[0] = c->ticket[1] = 0u;
   }
-}
-
-// de-interleave (x, y) of the current half into two plain arrays staged in the other half
-// ([0, n) and [cap, cap + n)), for the host-facing views
-__global__ void __launch_bounds__(256) k_xy_split(Pop pop, const Counters* c) {
-  const int n = max(c->n, c->n_pre), cur = c->cur;
-  double* sx = reinterpret_cast<double*>(pop.xy[cur ^ 1]);
-  double* sy = sx + pop.cap;
-  for (int i = GTID; i < n; i += GSTRIDE) {
-    const double2 v = pop.xy[cur][i];
-    sx[i] = v.x;
-    sy[i] = v.y;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_z_to_rows(Pop pop, const Counters* c, double* z_rows) {
-  const int n = c->n, cur = c->cur;
-  for (int i = GTID; i < n; i += GSTRIDE)
-    for (int tt = 0; tt < pop.T; ++tt) z_rows[(size_t)i * pop.T + tt] = pop.z[cur][(size_t)tt * pop.cap + i];
 }
 
 // ========================================================================================
@@ -2043,13 +2357,24 @@ __global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters
 __global__ void __launch_bounds__(256) k_tskit_renumber(Pop pop, Counters* c, int reset_t0) {
   const int n = c->n, cur = c->cur;
   for (int i = GTID; i < n; i += GSTRIDE) {
-    pop.node[0][cur][i] = 2 * i;
-    pop.node[1][cur][i] = 2 * i + 1;
+    const int o = pop.ord[cur][i];                  // ordinal in species order (build_order ran just before)
+    pop.node[0][cur][i] = 2 * o;
+    pop.node[1][cur][i] = 2 * o + 1;
   }
   if (GTID == 0) {
     c->n_nodes = 2 * n;
     c->n_ind_rows = n;
     if (reset_t0) { c->tsk_t0 = c->t; c->n_edges = 0; c->n_born = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_nodes(Pop pop, Work w, const Counters* c, const int32_t* n0,
+                                                        const int32_t* n1, int n) {
+  const int cur = c->cur;
+  for (int i = GTID; i < n; i += GSTRIDE) {
+    const int p = w.inv[i];
+    pop.node[0][cur][p] = n0[i];
+    pop.node[1][cur][p] = n1[i];
   }
 }
 
