@@ -9,7 +9,12 @@ the landscape (Hs/Ht form, tests/validation/island/island_test.py:54-68).
 tests/test_statistical_parity.py runs the same model on the GPU path and KS-tests each
 statistic against these samples.
 
-Usage: python tests/golden/make_stat_golden.py [n_reps]
+Usage: python tests/golden/make_stat_golden.py [n_reps [seed_base [out.npz]]]
+
+The committed stat_reference.npz holds 400 replicates: seeds 1000-1099 plus four blocks of 75
+(seed bases 2000, 3000, 4000, 5000; `seed_blocks` in the file), generated block by block with
+this script and concatenated.  (The first 100 alone happened to sit ~2 standard errors above
+the long-run mean population size, which a 100-vs-100 KS test then pins on the GPU arm.)
 """
 import os
 import sys
@@ -92,7 +97,7 @@ def summarise(x, g, trait_locus, neut_locus):
     return n, float(p[trait_locus]), float(p[neut_locus]), het, fst, cline
 
 
-def run_reference(n_reps):
+def run_reference(n_reps, seed_base=1000, out_path=None):
     gnx = ref_shims.install()
     import geonomics.sim.burnin as _b
     # fixed-length burn-in in both arms (burn-in control is out of scope)
@@ -102,7 +107,7 @@ def run_reference(n_reps):
     out = []
     for rep in range(n_reps):
         p = ParametersDict(stat_params())
-        p['model']['seed'] = {'num': 1000 + rep}
+        p['model']['seed'] = {'num': seed_base + rep}
         p['model']['name'] = 'stat'
         with contextlib.redirect_stdout(io.StringIO()):
             mod = gnx.make_model(p, name='stat')
@@ -119,10 +124,12 @@ def run_reference(n_reps):
                     rows.append(summarise(x, g, tl, nl))
         out.append(dict(Nt=np.array(spp.Nt[-T:]), stats=np.array(rows), burn_steps=mod.burn_t + 1))
         print('rep', rep, 'N', spp.Nt[-1], 'burn', mod.burn_t + 1, flush=True)
-    np.savez_compressed(os.path.join(HERE, 'stat_reference.npz'),
+    np.savez_compressed(out_path or os.path.join(HERE, 'stat_reference.npz'),
                         Nt=np.stack([o['Nt'] for o in out]), stats=np.stack([o['stats'] for o in out]),
                         burn_steps=np.array([o['burn_steps'] for o in out]), sample_t=np.array(SAMPLE_T))
 
 
 if __name__ == '__main__':
-    run_reference(int(sys.argv[1]) if len(sys.argv) > 1 else 100)
+    # optional: seed base and output path (extra samples to size the reference's own sampling noise)
+    run_reference(int(sys.argv[1]) if len(sys.argv) > 1 else 100,
+                  int(sys.argv[2]) if len(sys.argv) > 2 else 1000, sys.argv[3] if len(sys.argv) > 3 else None)
