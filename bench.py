@@ -112,14 +112,18 @@ class ClockSampler:
 
 def load_traffic(workload, scale):
     """Measured DRAM bytes per launch from the committed `ncu --set full` capture of this workload
-    (profiles/r01_traffic.json, written by tools/make_traffic.py); {} if there is none."""
-    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if scale != 1.0 or not os.path.exists(path):
+    (profiles/r02_traffic.json, else r01_traffic.json; written by tools/make_traffic.py); {} if there is none."""
+    if scale != 1.0:
         return {}
-    try:
-        return json.load(open(path)).get(workload, {}).get('kernels', {})
-    except Exception:
-        return {}
+    for nm in ('r02_traffic.json', 'r01_traffic.json'):       # the newest capture that names this workload
+        path = os.path.join(ROOT, 'profiles', nm)
+        try:
+            k = json.load(open(path)).get(workload, {}).get('kernels', {})
+        except Exception:
+            k = {}
+        if k:
+            return k
+    return {}
 
 
 def load_peaks():
@@ -220,6 +224,134 @@ def workload_desc(cfg):
         cfg['mating_radius'], ', on-the-fly conductance surfaces' if cfg['surfaces'] else '')
 
 
+def merge_dense(prof):
+    """k_find_mates_dense serves the crowded cells of the same search: one row for both launches."""
+    prof = dict(prof)
+    if 'k_find_mates_dense' in prof and 'k_find_mates' in prof:
+        a, b = prof.pop('k_find_mates_dense'), prof['k_find_mates']
+        prof['k_find_mates'] = (b[0], a[1] + b[1])
+    return prof
+
+
+def kernel_table(dev, w, prof, precs, steps, workload, scale):
+    """Per-kernel rows (CUDA-event time per launch, algorithmic bytes, fraction of the HBM peak)."""
+    W = 4 * dev.W
+    T = dev.n_traits
+    cs = w['prm']['mating_radius'] * 1.0000001
+    ncx, ncy = int(w['land_dim'][0] / cs) + 1, int(w['land_dim'][1] / cs) + 1
+    cells = ncx * ncy
+    YX = w['land_dim'][0] * w['land_dim'][1]
+    ab = algorithmic_bytes(W, T, cells, YX)
+    mean = {k: float(np.mean([r[k] for r in precs])) for k in ('Nt', 'n_births', 'n_deaths', 'n_pairs')}
+    s = dict(n=mean['Nt'] - mean['n_births'] + mean['n_deaths'], B=mean['n_births'], P=mean['n_pairs'],
+             deaths=mean['n_deaths'])
+    s['npre'] = s['n'] + s['B']
+    peak, peak_src = load_peaks()
+    table = []
+    traffic = load_traffic(workload, scale)
+    prof = merge_dense(prof)
+    kernel_sum_ms = sum(v[1] for v in prof.values()) / steps
+    for name, (cnt, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per_launch_ms = tot_ms / cnt
+        row = {'kernel': name, 'launches_per_step': cnt / steps, 'ms_per_launch': per_launch_ms,
+               'share_of_kernel_time_sum': tot_ms / steps / kernel_sum_ms}
+        if name in ab:
+            b = ab[name](s)
+            row['algorithmic_bytes'] = b
+            row['achieved_GBs'] = b / (per_launch_ms * 1e-3) / 1e9
+            row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
+        if name in traffic:
+            row['dram_bytes_ncu'] = traffic[name]['dram_bytes_per_launch']
+        table.append(row)
+    return table, s, kernel_sum_ms, peak, peak_src
+
+
+def roofline_block(table, s, W, peak, peak_src, kernel_sum_ms):
+    top = next((r for r in table if 'achieved_GBs' in r), None)
+    gam = next((r for r in table if r['kernel'] == 'k_gametes'), None)
+    if top is None:
+        return None
+    roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_GBs'], 'peak': peak,
+                'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': top.get('dram_bytes_ncu'),
+                'algorithmic_bytes': top['algorithmic_bytes'], 'peak_source': peak_src,
+                'share_of_kernel_time_sum': top['share_of_kernel_time_sum'],
+                'kernel_time_sum_ms_per_step': kernel_sum_ms,
+                'note': 'share = this kernel / sum of the per-kernel CUDA-event times of the profiled pass '
+                        '(serialised, events around every launch), not / ms_per_step of the graph-launched run'}
+    if gam is not None:
+        sec = gam['ms_per_launch'] * 1e-3
+        g = {'kernel': 'k_gametes', 'achieved': gam.get('achieved_GBs'), 'frac': gam.get('frac_of_hbm_peak'),
+             'ms_per_launch': gam['ms_per_launch'],
+             # SURVEY.md section 8d: 4W parents + 2W child + 8 (two keys) per birth
+             'frac_by_survey_8d_bytes': s['B'] * (6 * W + 8) / sec / 1e9 / peak,
+             'bytes_per_birth_survey_8d': 6 * W + 8}
+        if 'dram_bytes_ncu' in gam:
+            g['frac_by_measured_dram'] = gam['dram_bytes_ncu'] / sec / 1e9 / peak
+        roofline['genotype_streaming_kernel'] = g
+    return roofline
+
+
+def make_species(cfg, rank, seed_off=0):
+    from geonomics_b200 import workloads
+    from geonomics_b200.device import DeviceSpecies
+    w = workloads.build(cfg, cfg['seed'] + rank + seed_off)
+    N0, L = cfg['N'], w['L']
+    cap = int(1.5 * N0) + 4096
+    dev = DeviceSpecies(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=cap,
+                        seed=cfg['seed'] + 7919 * rank + 104729 * (seed_off // 1000))
+    dev.upload(w['pop']['x'], w['pop']['y'], w['pop']['age'], w['pop']['sex'], w['pop']['idx'],
+               genomes_packed=workloads.random_packed_genomes(N0, L, cfg['seed'] + 1 + rank + seed_off))
+    return dev, w, cap
+
+
+def steady_state_block(name, presteps, steps, prof_steps):
+    """One extra workload inside the default line: advanced `presteps` time steps first (evolved
+    populations clump, so early steps flatter the mate search), then `steps` timed steps with the
+    state resident, then a per-kernel pass."""
+    import torch
+    from geonomics_b200 import workloads
+    cfg = dict(workloads.CONFIGS[name])
+    dev, w, cap = make_species(cfg, 0)
+    stream = torch.cuda.ExternalStream(dev.stream_ptr)
+    done = 0
+    while done < presteps:
+        c = min(64, presteps - done)
+        dev.step(c)
+        done += c
+    dev.sync()
+    dev.step_records()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    dev.step(steps)
+    e1.record(stream)
+    dev.sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    recs = dev.step_records()
+    ind = float(sum(r['Nt'] - r['n_births'] + r['n_deaths'] for r in recs))
+    births = float(sum(r['n_births'] for r in recs))
+    dev.profile(True)
+    dev.step(prof_steps)
+    dev.sync()
+    prof = dev.profile_report()
+    dev.profile(False)
+    precs = dev.step_records()
+    table, s, ksum, peak, peak_src = kernel_table(dev, w, prof, precs, prof_steps, name, 1.0)
+    W = 4 * dev.W
+    beta = births / ind
+    per_ig = 193 + (6 * W + 8 + 29 + 16 + 32) * beta          # SURVEY.md section 8d
+    out = {'workload': name + ': ' + workload_desc(cfg), 'simulated_steps_before_timing': presteps,
+           'steps': steps, 'ms_per_step': ms / steps, 'value': ind / (ms * 1e-3), 'unit': UNIT,
+           'births_per_individual': beta,
+           'whole_step': {'algorithmic_bytes_per_individual_generation': per_ig,
+                          'achieved_GBs': per_ig * ind / (ms * 1e-3) / 1e9,
+                          'frac_of_hbm_peak': per_ig * ind / (ms * 1e-3) / 1e9 / peak},
+           'roofline': roofline_block(table, s, W, peak, peak_src, ksum), 'kernels': table[:12]}
+    dev.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -233,6 +365,11 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--presteps', type=int, default=0, help='time steps simulated before the warm-up')
+    ap.add_argument('--c4-presteps', type=int, default=300,
+                    help='the default line carries a c4 block (north_star target config) measured after this '
+                         'many simulated steps; 0 disables it')
+    ap.add_argument('--c4-steps', type=int, default=100)
     ap.add_argument('--replicates', type=int, default=None,
                     help='replicate populations per GPU, stepped concurrently on their own streams '
                          '(default 8 for c3 = BASELINE configs[2]: 64 replicates on 8 GPUs; 1 otherwise)')
@@ -272,25 +409,15 @@ def main():
             os.close(saved_fd)
 
     from geonomics_b200.device import DeviceSpecies
-    w = workloads.build(cfg, cfg['seed'] + rank)            # one replicate population per rank
+    dev, w, cap = make_species(cfg, rank)
     N0, L = cfg['N'], w['L']
-    cap = int(1.5 * N0) + 4096
-    dev = DeviceSpecies(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=cap,
-                        seed=cfg['seed'] + 7919 * rank)
-    genomes = workloads.random_packed_genomes(N0, L, cfg['seed'] + 1 + rank)
-    dev.upload(w['pop']['x'], w['pop']['y'], w['pop']['age'], w['pop']['sex'], w['pop']['idx'],
-               genomes_packed=genomes)
     stream = torch.cuda.ExternalStream(dev.stream_ptr)
     # further replicate populations on this GPU (independent iterations, model.py:115-117): each has
     # its own context and stream; the steps are enqueued round-robin and overlap on the device
     R = args.replicates if args.replicates is not None else (8 if args.workload == 'c3' else 1)
     devs, streams = [dev], [stream]
     for k in range(1, R):
-        wk = workloads.build(cfg, cfg['seed'] + rank + 1000 * k)
-        dk = DeviceSpecies(wk['land_dim'], wk['rasters'], wk['prm'], wk['gen_arch'], capacity=cap,
-                           seed=cfg['seed'] + 7919 * rank + 104729 * k)
-        dk.upload(wk['pop']['x'], wk['pop']['y'], wk['pop']['age'], wk['pop']['sex'], wk['pop']['idx'],
-                  genomes_packed=workloads.random_packed_genomes(N0, L, cfg['seed'] + 1 + rank + 1000 * k))
+        dk, _, _ = make_species(cfg, rank, 1000 * k)
         devs.append(dk)
         streams.append(torch.cuda.ExternalStream(dk.stream_ptr))
 
@@ -307,6 +434,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- optional: advance the simulation first (steady-state measurements)
+    if args.presteps > 0:
+        step_all(args.presteps)
     # ---- warm-up
     step_all(args.warmup)
     for d in devs:
@@ -343,54 +473,17 @@ def main():
     value = ind_all / (ms_all * 1e-3)
 
     # ---- per-kernel timing pass (CUDA events around every launch) for the roofline
+    prof_steps = min(args.steps, 200)
     dev.profile(True)
-    dev.step(args.steps)
+    dev.step(prof_steps)
     dev.sync()
     prof = dev.profile_report()
     dev.profile(False)
     precs = dev.step_records()
-    W = 4 * dev.W
     T = dev.n_traits
-    cells = int(dev.read('CELL_START', 1).size and 0) or 0
-    import math
-    cs = w['prm']['mating_radius'] * 1.0000001
-    ncx, ncy = int(w['land_dim'][0] / cs) + 1, int(w['land_dim'][1] / cs) + 1
-    cells = ncx * ncy
     YX = w['land_dim'][0] * w['land_dim'][1]
-    ab = algorithmic_bytes(W, T, cells, YX)
-    mean = {k: float(np.mean([r[k] for r in precs])) for k in ('Nt', 'n_births', 'n_deaths', 'n_pairs')}
-    s = dict(n=mean['Nt'] - mean['n_births'] + mean['n_deaths'], B=mean['n_births'], P=mean['n_pairs'],
-             deaths=mean['n_deaths'])
-    s['npre'] = s['n'] + s['B']
-    peak, peak_src = load_peaks()
-    table = []
-    traffic = load_traffic(args.workload, args.scale)
-    step_ms = sum(v[1] for v in prof.values()) / args.steps
-    for name, (cnt, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        per_launch_ms = tot_ms / cnt
-        row = {'kernel': name, 'launches_per_step': cnt / args.steps, 'ms_per_launch': per_launch_ms,
-               'share_of_step': tot_ms / args.steps / step_ms}
-        if name in ab:
-            b = ab[name](s)
-            row['algorithmic_bytes'] = b
-            row['achieved_GBs'] = b / (per_launch_ms * 1e-3) / 1e9
-            row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
-        if name in traffic:
-            row['dram_bytes_ncu'] = traffic[name]['dram_bytes_per_launch']
-        table.append(row)
-    top = next((r for r in table if 'achieved_GBs' in r), None)
-    gam = next((r for r in table if r['kernel'] == 'k_gametes'), None)
-    roofline = None
-    if top is not None:
-        roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_GBs'], 'peak': peak,
-                    'unit': 'GB/s', 'frac': top['frac_of_hbm_peak'], 'traffic': top.get('dram_bytes_ncu'),
-                    'algorithmic_bytes': top['algorithmic_bytes'], 'peak_source': peak_src,
-                    'share_of_step': top['share_of_step']}
-        if gam is not None:
-            roofline['genotype_streaming_kernel'] = {'kernel': 'k_gametes',
-                                                     'achieved': gam.get('achieved_GBs'),
-                                                     'frac': gam.get('frac_of_hbm_peak'),
-                                                     'ms_per_launch': gam['ms_per_launch']}
+    table, s, kernel_sum_ms, peak, peak_src = kernel_table(dev, w, prof, precs, prof_steps, args.workload, args.scale)
+    roofline = roofline_block(table, s, 4 * dev.W, peak, peak_src, kernel_sum_ms)
 
     # ---- e2e: host buffers through gnx_walk_host, every step (pinned host memory)
     e2e = None
@@ -439,6 +532,17 @@ def main():
                          'Python reference itself measured ~2.5e3 individual-generations/s in the build '
                          'container (BASELINE.md section 2)' % (args.cpu_steps, args.cpu_sample),
                'seconds': wall}
+    gs_iters = dev.counters()['gs_iters']
+
+    for d in devs[1:]:
+        d.close()
+    dev.close()
+    devs = []
+    c4 = None
+    if (rank == 0 and world == 1 and args.workload == 'c2' and args.scale == 1.0 and args.c4_presteps > 0
+            and args.presteps == 0):
+        # the north_star target config on one GPU, at steady state
+        c4 = steady_state_block('c4', args.c4_presteps, args.c4_steps, min(50, args.c4_steps))
 
     if rank == 0:
         footprint_mb = (N0 * (2 * (8 + 8 + 4 + 1 + 8 + 4 + 8 * T + 8) + 8 * dev.W + 60) + 8 * YX * 6) / 1e6
@@ -452,12 +556,15 @@ def main():
                        'parallelism': '%d replicate population%s per GPU (own context and stream each), no '
                                       'collective' % (R, '' if R == 1 else 's'),
                        'births_per_individual': births_all / ind_all,
+                       'simulated_steps_before_timing': args.presteps + args.warmup,
                        'l2': 'not flushed between steps: a step streams ~%.0f MB of state and work arrays '
                              '(> 126 MB L2)' % footprint_mb,
                        'rng': 'Philox4x32-10'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
-            'cpu_baseline': cpu, 'kernels': table[:14], 'gs_iters': dev.counters()['gs_iters'],
+            'cpu_baseline': cpu, 'kernels': table[:14], 'gs_iters': gs_iters,
         }
+        if c4 is not None:
+            line['c4'] = c4
         print(json.dumps(line))
     for d in devs:
         d.close()

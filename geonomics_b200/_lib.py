@@ -184,6 +184,8 @@ SIGNATURES = {
     'gnx_death_prob': (C.c_int, [_ctx]),
     'gnx_mortality': (C.c_int, [_ctx]),
     'gnx_set_raster': (C.c_int, [_ctx, C.c_int32, c_double_p]),
+    'gnx_set_K': (C.c_int, [_ctx, c_double_p]),
+    'gnx_set_life_history': (C.c_int, [_ctx, C.POINTER(Config)]),
     'gnx_step': (C.c_int, [_ctx, C.c_int32]),
     'gnx_sync': (C.c_int, [_ctx]),
     'gnx_walk_host': (C.c_int, [_ctx, C.POINTER(Population), C.c_int32]),

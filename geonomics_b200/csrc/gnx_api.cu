@@ -302,6 +302,10 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
     W.scratch = sc;
   }
   DM(ctx, &W.mate, cap);
+  // a cell is crowded when its 3x3 block holds >= GNX_FM_HEAVY_K entries; an entry lies in at most
+  // 9 blocks, so at most 9 n / GNX_FM_HEAVY_K (< n / 4) non-empty cells are
+  W.heavy_cap = (int32_t)(cap / 4 + 1024);
+  DM(ctx, &W.heavy, (size_t)W.heavy_cap);
   DM(ctx, &W.n_nbrs, cap);
   DM(ctx, &W.pairs, 2 * cap);
   DM(ctx, &W.pair_slots, 2 * cap);
@@ -448,6 +452,48 @@ extern "C" int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_ra
   if (r != GNX_OK) return r;
   if ((r = refresh_surf_f32(ctx, layer)) != GNX_OK) return r;
   if (layer == ctx->cfg.K_layer) return set_K(ctx);      // model.py:651-652 (Species._set_K)
+  return GNX_OK;
+}
+
+// Species change events (ops/change.py:612-742).
+// Demographic change: the change functions rewrite the carrying-capacity raster itself
+// (`spp.K *= size`, `spp.K = changer.base_K * size`, change.py:633-649); the caller hands the
+// new raster over.  It stays until the next gnx_set_K or until Species._set_K runs again
+// (gnx_set_raster on the K layer), exactly like the reference's attribute.
+extern "C" int gnx_set_K(gnx_ctx* ctx, const double* host_K) {
+  ARG(ctx && host_K, "null");
+  USE_DEVICE(ctx);
+  const size_t plane = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  CK(cudaMemcpyAsync(ctx->d_K, host_K, plane * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));        // the host buffer may be a temporary
+  return GNX_OK;
+}
+
+// Life-history change: `setattr(spp, parameter, val)` (change.py:735-742) for the scalar
+// parameters the step reads.  Everything that fixes a buffer size or the mating grid must be
+// unchanged; the next gnx_step re-captures its graph (the parameters are kernel arguments).
+extern "C" int gnx_set_life_history(gnx_ctx* ctx, const gnx_config_t* cfg) {
+  ARG(ctx && cfg, "null");
+  USE_DEVICE(ctx);
+  ARG(cfg->abi_version == GNX_ABI_VERSION, "abi_version");
+  const gnx_config_t& o = ctx->cfg;
+  ARG(cfg->dim_x == o.dim_x && cfg->dim_y == o.dim_y && cfg->n_layers == o.n_layers && cfg->capacity == o.capacity &&
+          cfg->L == o.L && cfg->n_recomb_paths == o.n_recomb_paths && cfg->n_traits == o.n_traits &&
+          cfg->use_dom == o.use_dom,
+      "gnx_set_life_history cannot change the landscape, capacity or genomic architecture");
+  ARG(cfg->mating_radius == o.mating_radius, "gnx_set_life_history cannot change mating_radius (it fixes the mating grid)");
+  ARG(cfg->move_surf_mode == o.move_surf_mode && cfg->disp_surf_mode == o.disp_surf_mode &&
+          cfg->move_surf_layer == o.move_surf_layer && cfg->disp_surf_layer == o.disp_surf_layer &&
+          cfg->surf_approx_len == o.surf_approx_len && cfg->disp_max_tries_injected == o.disp_max_tries_injected &&
+          cfg->K_layer == o.K_layer && cfg->seed == o.seed,
+      "gnx_set_life_history cannot change the conductance-surface setup, K layer or seed");
+  ARG(cfg->b >= 0 && cfg->b <= 1 && cfg->d_min <= cfg->d_max, "b / d_min / d_max");
+  if (cfg->n_births_fixed) ARG((int32_t)cfg->n_births_lambda >= 1, "n_births_fixed needs n_births_distr_lambda >= 1");
+  CK(cudaStreamSynchronize(ctx->stream));
+  const bool k_changed = cfg->K_factor != o.K_factor;
+  ctx->cfg = *cfg;
+  ctx->prm.c = *cfg;
+  if (k_changed && ctx->have_rasters) return set_K(ctx);
   return GNX_OK;
 }
 
@@ -1133,13 +1179,25 @@ static int find_mates(gnx_ctx* ctx) {
 #ifndef GNX_FM_BLOCK
 #define GNX_FM_BLOCK 128
 #endif
+#ifndef GNX_FMD_GRID
+#define GNX_FMD_GRID 6
+#endif
   const int g = grid_cap(ctx, GNX_FM_GRID, GNX_FM_BLOCK);
+  const bool uniform_choice = !ctx->cfg.choose_nearest && !ctx->cfg.inverse_dist;
+  if (uniform_choice)     // n_heavy, heavy_next: the crowded-cell list starts empty
+    CK(cudaMemsetAsync(&ctx->d_c->n_heavy, 0, 2 * sizeof(int32_t), ctx->stream));
 #define FM(MODE) k_find_mates<MODE><<<g, GNX_FM_BLOCK, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
   if (ctx->cfg.choose_nearest) FM(1);
   else if (ctx->cfg.inverse_dist) FM(2);
   else FM(0);
 #undef FM
   LAUNCHED(ctx);
+  if (uniform_choice) {
+    PROF(ctx, "k_find_mates_dense");
+    k_find_mates_dense<<<grid_for(ctx, GNX_FMD_GRID), 32 * FMD_WARPS, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm,
+                                                                                   ctx->draws, ctx->work, ctx->d_c);
+    LAUNCHED(ctx);
+  }
   return GNX_OK;
 }
 

@@ -43,6 +43,9 @@ struct Counters {
   uint32_t ticket[2];   // last-block elections (k_regrid, k_death); self-resetting
   int32_t n_regrid;     // entries placed by the running re-grid (scan total)
   int32_t pad2;
+  // crowded mating cells handed from k_find_mates to k_find_mates_dense (zeroed before every search)
+  int32_t n_heavy;      // cells appended to Work.heavy
+  int32_t heavy_next;   // work-stealing cursor of k_find_mates_dense
 };
 #define GNX_ERRBIT_CAPACITY 1
 #define GNX_ERRBIT_DRAWS 2
@@ -147,6 +150,8 @@ struct Work {
   int32_t* sort_vals[2];
   uint32_t* sort_hist;     // [256][tiles]
   int32_t* mate;
+  uint32_t* heavy;         // packed keys of the crowded mating cells of this step (k_find_mates_dense)
+  int32_t heavy_cap;
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]
   int32_t* pair_slots;     // [cap][2] genome slots of each pair's parents

@@ -316,10 +316,27 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
 //   rank.  Closed ball on squared distances, products and sum rounded separately (as the
 //   reference's cKDTree does).
 //   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are kept as bit
-//           masks and the k-th is picked, k = (R * count) >> 32
+//           masks and the k-th is picked, k = (R * count) >> 32.  Cells whose 3x3 block is
+//           crowded (a row range longer than 64 entries, or >= GNX_FM_HEAVY_K entries in all)
+//           are not searched here: their first focal appends the cell to Work.heavy and
+//           k_find_mates_dense takes them, one warp per cell with the lanes across candidates
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
+#ifndef GNX_FM_HEAVY_K
+#define GNX_FM_HEAVY_K 128
+#endif
+// position of the (k+1)-th set bit of m: popcount bisection (branch-free; __fns is a software loop)
+__device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
+  int bit = 0;
+#pragma unroll
+  for (int wdt = 16; wdt >= 1; wdt >>= 1) {
+    const int cl = __popc(m & ((1u << wdt) - 1u));
+    if (k >= cl) { k -= cl; m >>= wdt; bit += wdt; }
+  }
+  return bit;
+}
+
 template <int MODE>
 #ifndef GNX_FM_BLOCK
 #define GNX_FM_BLOCK 128
@@ -330,7 +347,7 @@ template <int MODE>
 #define GNX_FM_BOUNDS __launch_bounds__(GNX_FM_BLOCK)
 #endif
 __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDraws dr, Work w,
-                                                     const Counters* c) {
+                                                     Counters* c) {
   const int n = c->n, cur = c->cur;
   const int64_t t = c->t;
   const double r2 = prm.r2, radius = prm.c.mating_radius;
@@ -350,11 +367,22 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       hi[r] = w.cell_start[row * land.ncx + x1 + 1];
     }
     int cnt = 0;
+    if (MODE == 0) {
+      // crowded block: the whole cell goes to k_find_mates_dense (the test depends on the cell
+      // only, so every focal of the cell takes this exit; the cell's first entry announces it)
+      const int l0 = hi[0] - lo[0], l1 = hi[1] - lo[1], l2 = hi[2] - lo[2];
+      if (max(l0, max(l1, l2)) > 64 || l0 + l1 + l2 >= GNX_FM_HEAVY_K) {
+        if (p == (int)w.cell_start[cy * land.ncx + cx]) {
+          const int pos = atomicAdd(&c->n_heavy, 1);
+          if (pos < w.heavy_cap) w.heavy[pos] = key;
+          else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
+        }
+        continue;
+      }
+    }
     // MODE 0 keeps the valid candidates of each row range as two 32-bit masks in registers
-    // (candidates 0-31 and 32-63 of the range: evolved populations clump, and a range longer
-    // than 32 would otherwise send the whole warp down the recount path)
+    // (candidates 0-31 and 32-63 of the range)
     uint32_t vm[3] = {0u, 0u, 0u}, vh[3] = {0u, 0u, 0u};
-    bool overflow = false;
     double best = 1e300, wsum = 0.0;
     int best_q = -1, n_w = 0;
 #pragma unroll
@@ -363,7 +391,6 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       const double2* __restrict__ cand = sxy + lo[r];
       const int self = p - lo[r];                   // position of the focal in this range, if any
       if (MODE == 0) {
-        if (len > 64) overflow = true;
         uint32_t m = 0u, mh = 0u;
         const int len0 = min(len, 32);
 #pragma unroll 4
@@ -402,18 +429,6 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
         }
       }
     }
-    if (MODE == 0 && overflow) {
-      // rare: a row range longer than 64 candidates -- count exactly, select by a second walk
-      cnt = 0;
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-        for (int q = lo[r]; q < hi[r]; ++q) {
-          const double2 cxy = sxy[q];
-          const double dx = cxy.x - f.x, dy = cxy.y - f.y;
-          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-          cnt += (d2 <= r2 && q != p) ? 1 : 0;
-        }
-    }
     if (prm.store_debug) w.n_nbrs[p] = cnt;
     int mate = -1;
     if (cnt > 0) {
@@ -446,45 +461,23 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       } else {
         const uint32_t R = dr.mate_R ? dr.mate_R[io] : g.u32();
         int k = (int)choose_k(R, (uint32_t)cnt);
-        if (!overflow) {
-          uint32_t msel = 0u;
-          int base_q = 0;
-          bool found = false;
+        uint32_t msel = 0u;
+        int base_q = 0;
+        bool found = false;
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const int cr = __popc(vm[r]);
-            if (!found) {
-              if (k < cr) { msel = vm[r]; base_q = lo[r]; found = true; }
-              else k -= cr;
-            }
-            const int ch = __popc(vh[r]);
-            if (!found) {
-              if (k < ch) { msel = vh[r]; base_q = lo[r] + 32; found = true; }
-              else k -= ch;
-            }
+        for (int r = 0; r < 3; ++r) {
+          const int cr = __popc(vm[r]);
+          if (!found) {
+            if (k < cr) { msel = vm[r]; base_q = lo[r]; found = true; }
+            else k -= cr;
           }
-          // position of the (k+1)-th set bit of msel: popcount bisection (branch-free; __fns is
-          // a software loop)
-          int bit = 0;
-#pragma unroll
-          for (int wdt = 16; wdt >= 1; wdt >>= 1) {
-            const int cl = __popc(msel & ((1u << wdt) - 1u));
-            if (k >= cl) { k -= cl; msel >>= wdt; bit += wdt; }
+          const int ch = __popc(vh[r]);
+          if (!found) {
+            if (k < ch) { msel = vh[r]; base_q = lo[r] + 32; found = true; }
+            else k -= ch;
           }
-          sel_q = base_q + bit;
-        } else {                         // rare: a row range longer than 64, walk again
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-            for (int q = lo[r]; q < hi[r] && sel_q < 0; ++q) {
-              const double2 cxy = sxy[q];
-              const double dx = cxy.x - f.x, dy = cxy.y - f.y;
-              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              if (d2 <= r2 && q != p) {
-                if (k == 0) sel_q = q;
-                k -= 1;
-              }
-            }
         }
+        sel_q = base_q + kth_set_bit(msel, k);
       }
       if (sel_q >= 0) {
         const double u = dr.mate_u ? dr.mate_u[io] : g.uniform();
@@ -492,6 +485,143 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       }
     }
     w.mate[p] = mate;
+  }
+}
+
+// ----- k_find_mates_dense: the crowded cells of MODE 0, one warp per cell ------------------
+// Evolved populations clump (c4 after 1000 steps: 94 neighbours per individual on average, 350
+// at the 99th percentile), and a thread per focal then walks hundreds of candidates with its
+// own trip count.  Here the LANES run across the candidates of the cell's 3x3 block (three
+// contiguous ranges of pop.xy): each lane keeps FMD_CG candidates in registers (coalesced
+// 128-bit loads, once per batch of 32 focals), the focals of the batch are broadcast one after
+// the other from shared memory, and a ballot per 32 candidates IS the validity mask in
+// canonical order.  The masks go to shared memory [focal][chunk]; then the lanes switch to one
+// focal each for the count, the draw and the k-th-neighbour pick -- same counts, same canonical
+// order, same Philox stream as k_find_mates, so the two kernels are interchangeable bit for bit.
+// Blocks of up to 64 chunks (2048 candidates) keep their masks; beyond that each lane walks.
+#define FMD_WARPS 4
+#define FMD_CHUNKS 64
+#define FMD_CG 4                       // chunks of 32 candidates held in registers at a time
+#define FMD_STRIDE (FMD_CHUNKS + 4)    // row stride in words: rows stay 16-byte aligned
+__global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, Land land, Params prm, DevDraws dr,
+                                                                       Work w, Counters* c) {
+  __shared__ __align__(16) uint32_t smask[FMD_WARPS][32][FMD_STRIDE];
+  __shared__ double2 sfoc[FMD_WARPS][32];
+  const int n_heavy = min(c->n_heavy, w.heavy_cap), cur = c->cur;
+  const int64_t t = c->t;
+  const double r2 = prm.r2;
+  const double2* __restrict__ sxy = pop.xy[cur];
+  const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t (*mk)[FMD_STRIDE] = smask[wid];
+  double2* foc = sfoc[wid];
+  for (;;) {
+    int h = 0;
+    if (lane == 0) h = atomicAdd(&c->heavy_next, 1);
+    h = __shfl_sync(0xffffffffu, h, 0);
+    if (h >= n_heavy) break;
+    const uint32_t key = w.heavy[h];
+    const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
+    int lo[3], len[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int row = cy - 1 + r;
+      if (row < 0 || row >= land.ncy) { lo[r] = 0; len[r] = 0; continue; }
+      lo[r] = (int)w.cell_start[row * land.ncx + x0];
+      len[r] = (int)w.cell_start[row * land.ncx + x1 + 1] - lo[r];
+    }
+    const int e1 = len[0], e2 = len[0] + len[1], K = e2 + len[2];
+    const int nch = (K + 31) >> 5;
+    const bool keep = nch <= FMD_CHUNKS;
+    const int fs = (int)w.cell_start[cy * land.ncx + cx], fe = (int)w.cell_start[cy * land.ncx + cx + 1];
+    // entry number of candidate ci of the concatenated ranges
+    auto cand_entry = [&](int ci) { return ci < e1 ? lo[0] + ci : (ci < e2 ? lo[1] + (ci - e1) : lo[2] + (ci - e2)); };
+    for (int fb = fs; fb < fe; fb += 32) {
+      const int nf = min(32, fe - fb);
+      const int p = fb + lane;
+      const double2 myf = lane < nf ? sxy[p] : make_double2(0.0, 0.0);
+      if (keep) {
+        foc[lane] = myf;
+        __syncwarp();
+        // ---- lanes across candidates: FMD_CG chunks in registers, every focal of the batch against them
+        for (int cg = 0; cg < nch; cg += FMD_CG) {
+          double2 cv[FMD_CG];
+#pragma unroll
+          for (int j = 0; j < FMD_CG; ++j) {
+            const int ci = ((cg + j) << 5) + lane;
+            // lanes past the end hold a point at infinity: it fails every distance test
+            cv[j] = ci < K ? sxy[cand_entry(ci)] : make_double2(1e300, 1e300);
+          }
+#pragma unroll 2
+          for (int fi = 0; fi < nf; ++fi) {
+            const double2 f = foc[fi];
+            uint32_t bm[FMD_CG];
+#pragma unroll
+            for (int j = 0; j < FMD_CG; ++j) {
+              const double dx = cv[j].x - f.x, dy = cv[j].y - f.y;
+              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              bm[j] = __ballot_sync(0xffffffffu, d2 <= r2);
+            }
+            if (lane == 0) *reinterpret_cast<uint4*>(&mk[fi][cg]) = make_uint4(bm[0], bm[1], bm[2], bm[3]);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- lanes across focals: count, draw, pick (spatial.py:232-242, species.py:2212-2214)
+      if (lane < nf) {
+        const int self = e1 + (p - lo[1]);             // the focal's own position among the candidates
+        const int ngrp = (nch + FMD_CG - 1) / FMD_CG * FMD_CG;
+        int cnt = 0;
+        if (keep) {
+          mk[lane][self >> 5] &= ~(1u << (self & 31));
+          for (int ch = 0; ch < ngrp; ++ch) cnt += __popc(mk[lane][ch]);
+        } else {                               // more than 2048 candidates: this lane walks them
+          for (int ci = 0; ci < K; ++ci) {
+            const double2 cxy = sxy[cand_entry(ci)];
+            const double dx = cxy.x - myf.x, dy = cxy.y - myf.y;
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            cnt += (d2 <= r2 && ci != self) ? 1 : 0;
+          }
+        }
+        if (prm.store_debug) w.n_nbrs[p] = cnt;
+        int mate = -1;
+        if (cnt > 0) {
+          const int io = ord ? ord[p] : p;
+          RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
+          const uint32_t R = dr.mate_R ? dr.mate_R[io] : g.u32();
+          int k = (int)choose_k(R, (uint32_t)cnt);
+          int sel_q = -1;
+          if (keep) {
+            int ch = 0;
+            uint32_t m = mk[lane][0];
+            for (;;) {
+              const int pc = __popc(m);
+              if (k < pc) break;
+              k -= pc;
+              ch += 1;
+              m = mk[lane][ch];
+            }
+            sel_q = cand_entry((ch << 5) + kth_set_bit(m, k));
+          } else {
+            for (int ci = 0; ci < K && sel_q < 0; ++ci) {
+              const int q = cand_entry(ci);
+              const double2 cxy = sxy[q];
+              const double dx = cxy.x - myf.x, dy = cxy.y - myf.y;
+              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              if (d2 <= r2 && ci != self) {
+                if (k == 0) sel_q = q;
+                k -= 1;
+              }
+            }
+          }
+          const double u = dr.mate_u ? dr.mate_u[io] : g.uniform();
+          if (u < prm.c.b) mate = sel_q;
+        }
+        w.mate[p] = mate;
+      }
+      __syncwarp();
+    }
   }
 }
 

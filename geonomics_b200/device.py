@@ -79,29 +79,7 @@ class DeviceSpecies:
         if gen_arch is not None and gen_arch.get('dom') is not None and np.any(gen_arch['dom']):
             dom = np.ascontiguousarray(gen_arch['dom'], dtype=np.int8)
         cfg.use_dom = int(dom is not None)
-        mr = prm.get('mating_radius')
-        cfg.mating_radius = -1.0 if mr is None else float(mr)
-        cfg.b = float(prm['b'])
-        cfg.R = float(prm['R'])
-        cfg.n_births_lambda = float(prm['lam'])
-        cfg.n_births_fixed = int(bool(prm['n_births_fixed']))
-        cfg.sex = int(bool(prm.get('sex', False)))
-        cfg.sex_ratio_p = float(prm.get('sex_ratio_p', 0.5))
-        cfg.choose_nearest = int(bool(prm.get('choose_nearest', False)))
-        cfg.inverse_dist = int(bool(prm.get('inverse_dist', False)))
-        cfg.d_min = float(prm.get('d_min', 0.0))
-        cfg.d_max = float(prm.get('d_max', 1.0))
-        cfg.max_age = -1 if prm.get('max_age') is None else int(prm['max_age'])
-        cfg.K_layer = int(prm.get('K_layer', 0))
-        cfg.K_factor = float(prm.get('K_factor', 1.0))
-        cfg.move = int(bool(prm.get('move', True)))
-        mname, mp1, mp2 = prm.get('move_distr', ('wald', 1.0, 1.0))
-        dname, dp1, dp2 = prm.get('disp_distr', ('wald', 1.0, 1.0))
-        cfg.move_distr = _lib.DISTR[mname]
-        cfg.disp_distr = _lib.DISTR[dname]
-        cfg.move_p1, cfg.move_p2, cfg.disp_p1, cfg.disp_p2 = float(mp1), float(mp2), float(dp1), float(dp2)
-        cfg.dir_mu = float(prm.get('direction_mu', 0.0))
-        cfg.dir_kappa = float(prm.get('direction_kappa', 0.0))
+        self._fill_life_history(cfg, prm)
         cfg.res_ratio_x, cfg.res_ratio_y = float(res_ratio[0]), float(res_ratio[1])
         self._surf_tabs = [None, None]
         approx_len = 0
@@ -179,6 +157,67 @@ class DeviceSpecies:
 
     def set_gamete_tma(self, on=True):
         _lib.check(self._L.gnx_set_gamete_tma(self._ctx, int(bool(on))), 'gnx_set_gamete_tma')
+
+    @staticmethod
+    def _fill_life_history(cfg, prm):
+        """The scalar parameters the step reads off the Species (species.py:405-425)."""
+        mr = prm.get('mating_radius')
+        cfg.mating_radius = -1.0 if mr is None else float(mr)
+        cfg.b = float(prm['b'])
+        cfg.R = float(prm['R'])
+        cfg.n_births_lambda = float(prm['lam'])
+        cfg.n_births_fixed = int(bool(prm['n_births_fixed']))
+        cfg.sex = int(bool(prm.get('sex', False)))
+        cfg.sex_ratio_p = float(prm.get('sex_ratio_p', 0.5))
+        cfg.choose_nearest = int(bool(prm.get('choose_nearest', False)))
+        cfg.inverse_dist = int(bool(prm.get('inverse_dist', False)))
+        cfg.d_min = float(prm.get('d_min', 0.0))
+        cfg.d_max = float(prm.get('d_max', 1.0))
+        cfg.max_age = -1 if prm.get('max_age') is None else int(prm['max_age'])
+        cfg.K_layer = int(prm.get('K_layer', 0))
+        cfg.K_factor = float(prm.get('K_factor', 1.0))
+        cfg.move = int(bool(prm.get('move', True)))
+        mname, mp1, mp2 = prm.get('move_distr', ('wald', 1.0, 1.0))
+        dname, dp1, dp2 = prm.get('disp_distr', ('wald', 1.0, 1.0))
+        cfg.move_distr = _lib.DISTR[mname]
+        cfg.disp_distr = _lib.DISTR[dname]
+        cfg.move_p1, cfg.move_p2, cfg.disp_p1, cfg.disp_p2 = float(mp1), float(mp2), float(dp1), float(dp2)
+        cfg.dir_mu = float(prm.get('direction_mu', 0.0))
+        cfg.dir_kappa = float(prm.get('direction_kappa', 0.0))
+
+    def set_life_history(self, **changes):
+        """A species life-history change event (`setattr(spp, parameter, val)`, change.py:735-742):
+        keys as in the `prm` dict of the constructor (b, R, lam, n_births_fixed, d_min, d_max,
+        max_age, sex_ratio_p, K_factor, move_distr, disp_distr, direction_mu, direction_kappa,
+        choose_nearest, inverse_dist)."""
+        prm = dict(self.prm)
+        prm.update(changes)
+        self._fill_life_history(self._cfg, prm)
+        _lib.check(self._L.gnx_set_life_history(self._ctx, C.byref(self._cfg)), 'gnx_set_life_history')
+        self.prm = prm
+
+    def set_K(self, K):
+        """A demographic change event rewrote spp.K (change.py:633-649)."""
+        k = np.ascontiguousarray(K, dtype=np.float64)
+        assert k.shape == (self.land_dim[1], self.land_dim[0])
+        _lib.check(self._L.gnx_set_K(self._ctx, _ptr(k, _lib.c_double_p)), 'gnx_set_K')
+
+    def set_surface_tables(self, move_tab=None, disp_tab=None):
+        """Swap in re-built float16 direction tables (change.py:597-606: a landscape change on the
+        layer behind a conductance surface re-builds the _ConductanceSurface)."""
+        tabs = []
+        for k, t in enumerate((move_tab, disp_tab)):
+            if t is None:
+                tabs.append(None)
+                continue
+            t = np.ascontiguousarray(t, dtype=np.float16)
+            assert self._surf_tabs[k] is not None and t.shape == self._surf_tabs[k].shape, \
+                'surface table shape must match the one given at construction'
+            self._surf_tabs[k] = t
+            tabs.append(t.view(np.uint16))
+        _lib.check(self._L.gnx_set_surface_tables(
+            self._ctx, None if tabs[0] is None else _ptr(tabs[0], _lib.c_uint16_p),
+            None if tabs[1] is None else _ptr(tabs[1], _lib.c_uint16_p)), 'gnx_set_surface_tables')
 
     def set_burn(self, burn):
         _lib.check(self._L.gnx_set_burn(self._ctx, int(bool(burn))), 'gnx_set_burn')

@@ -230,6 +230,15 @@ int gnx_death_prob(gnx_ctx* ctx);
 int gnx_mortality(gnx_ctx* ctx);
 /* Landscape._set_raster landscape.py:353 + Species._set_K species.py:546 (env change, change.py:56-84) */
 int gnx_set_raster(gnx_ctx* ctx, int32_t layer, const double* host_raster);
+/* Species change events, ops/change.py:612-742 (queue slot model.py:654-656, Species._make_change
+ * species.py:836).  gnx_set_K: a demographic change rewrote spp.K (`spp.K *= size`,
+ * `spp.K = base_K * size`, change.py:633-649) -- the new [dim_y][dim_x] raster.
+ * gnx_set_life_history: `setattr(spp, parameter, val)` (change.py:735-742) -- a full config whose
+ * life-history scalars (b, R, births, sex ratio, d_min/d_max, max_age, K_factor, movement and
+ * dispersal distributions, direction, mate-choice flags) may differ; sizes, genome, landscape,
+ * mating_radius and the surface setup must equal the values given to gnx_create. */
+int gnx_set_K(gnx_ctx* ctx, const double* host_K);
+int gnx_set_life_history(gnx_ctx* ctx, const gnx_config_t* cfg);
 
 /* ---- whole steps ------------------------------------------------------------------------ */
 /* n_steps iterations of the main/burn queue for this species:

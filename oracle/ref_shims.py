@@ -5,8 +5,10 @@ Import shims that let the *unmodified* reference package at /root/reference
 where several of its import-time dependencies are absent (matplotlib, bitarray,
 tskit, msprime, shapely, statsmodels, geopandas, rasterio, vcf).
 
-Used only by the golden-vector generators under tests/golden/ (run in the build
-container; /root/reference does not exist on the GPU box) to pin the oracle.
+Used by the golden-vector generators under tests/golden/ (build container), by the
+drop-in tests that attach the GPU path to a real reference Species, and by
+`bench.py --impl reference` (the unmodified reference timed on the host cores).  On the GPU
+box the reference is the unmodified copy installed under oracle/_ref by build().
 Nothing in geonomics_b200/ imports this file.
 
 Why each shim is safe for the hot path (reference file:line):
@@ -24,7 +26,20 @@ import sys
 import types
 from unittest.mock import MagicMock
 
+import os
+
+# the reference sources in the build container; on the GPU box (no /root/reference) the copy that
+# __graft_entry__.build() pip-installed, unmodified, into the git-ignored oracle/_ref
 REFERENCE_ROOT = '/root/reference'
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+def reference_root():
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, 'geonomics')):
+        return REFERENCE_ROOT
+    if os.path.isdir(os.path.join(INSTALLED_ROOT, 'geonomics')):
+        return INSTALLED_ROOT
+    return None
 
 
 class _BitArray(list):
@@ -88,7 +103,10 @@ def install():
     sh.geometry = geo
     sys.modules['shapely'] = sh
     sys.modules['shapely.geometry'] = geo
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise ImportError('the reference package is neither at /root/reference nor installed in oracle/_ref')
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import geonomics  # noqa: F401
     return geonomics

@@ -80,6 +80,30 @@ def test_medium_density_second_mask_path(mode):
     assert 33 < nn.max() < 110 and np.median(nn) > 25
 
 
+def test_crowded_cells_beyond_mask_capacity():
+    """More than 2048 candidates in a 3x3 block: k_find_mates_dense recounts for the pick."""
+    rng = np.random.default_rng(21)
+    dim = (12, 12)
+    n = 4200
+    x = rng.uniform(0, dim[0] - 0.001, n)
+    y = rng.uniform(0, dim[1] - 0.001, n)
+    nn = _run(x, y, dim, 3.5, 0.5, 'random', 22)
+    assert nn.max() > 1000
+
+
+def test_clumped_population_uses_both_kernels():
+    """A density gradient from empty to crowded: sparse cells stay with the thread-per-focal
+    kernel, crowded ones (row range > 64 or >= 128 candidates in the block) go to the warp-per-
+    cell kernel; odd focal counts, cells on the landscape edge and in the corners included."""
+    rng = np.random.default_rng(23)
+    dim = (48, 40)
+    n = 9000
+    x = dim[0] * rng.beta(0.6, 2.5, n) * 0.9999
+    y = dim[1] * rng.beta(2.5, 0.6, n) * 0.9999
+    nn = _run(x, y, dim, 2.0, 0.4, 'random', 24)
+    assert nn.max() > 200 and (nn < 10).sum() > 100
+
+
 def test_edge_cases():
     dim = (10, 10)
     # corners, an exactly coincident couple, a neighbour at exactly distance r, an isolate

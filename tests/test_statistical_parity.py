@@ -1,6 +1,6 @@
 """Statistical parity (north_star): population-size, allele-frequency, heterozygosity and
 Fst distributions over 100 replicates of the GPU path must be indistinguishable (two-sample
-Kolmogorov-Smirnov) from 100 replicates of the unmodified reference, recorded in
+Kolmogorov-Smirnov) from 400 replicates of the unmodified reference, recorded in
 tests/golden/stat_reference.npz by tests/golden/make_stat_golden.py."""
 import os
 import sys
@@ -20,7 +20,7 @@ def samples():
     import make_stat_golden as msg
     from geonomics_b200 import api
     ref = np.load(REF)
-    n_reps = ref['Nt'].shape[0]
+    n_reps = 100            # GPU replicates, against the reference's 400
 
     def fixed_burn(self):
         ok = all(len(s.Nt) >= self.burn_T for s in self.comm.values())
