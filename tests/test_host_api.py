@@ -23,7 +23,7 @@ def built():
 
 def test_library_exports_every_declared_symbol(built):
     hdr = open(_lib.HEADER_PATH).read()
-    declared = set(re.findall(r'\b(gnx_[a-z_0-9]+)\s*\(', hdr))
+    declared = set(re.findall(r'\b(gnx_[A-Za-z_0-9]+)\s*\(', hdr))
     assert len(declared) >= 36
     for name in declared:
         assert hasattr(built, name), 'libgnxb200.so does not export %s' % name
