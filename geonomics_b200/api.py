@@ -169,6 +169,93 @@ class _LandscapeChanger:
         return made
 
 
+class _SpeciesChanger:
+    """ops/change.py:155-267 (_SpeciesChanger) with the change functions of change.py:612-742:
+    demographic events rewrite the carrying-capacity raster (`spp.K *= size` for 'monotonic',
+    `spp.K = base_K * size` for 'stochastic' / 'cyclical' / 'custom', where base_K is spp.K at
+    the event's first time step), life-history events `setattr(spp, parameter, val)`.  Conductance
+    surfaces that follow a changing layer (change.py:576-606) are re-built when the layer's raster
+    is swapped (Species._on_raster_change), at the same time steps as the reference's series."""
+
+    def __init__(self, spp, change_params, land):
+        self.base_K = None
+        changes = []
+        cp = change_params or {}
+        for _, ev in sorted((cp.get('dem') or {}).items(), key=lambda kv: str(kv[0])):
+            if not any(v is not None for v in dict(ev).values()):
+                continue
+            changes.extend(self._dem_changes(**dict(ev)))
+        for parameter, pp in (cp.get('life_hist') or {}).items():
+            pp = dict(pp)
+            if not any(v is not None for v in pp.values()):
+                continue
+            ts, vals = list(pp['timesteps']), list(pp['vals'])
+            assert len(ts) == len(vals), ("For custom changes of the '%s' parameter, timesteps and vals "
+                                          "must be iterables of equal length.") % parameter
+            changes.extend((int(t), 'param', (parameter, v)) for t, v in zip(ts, vals))
+        self.changes = sorted(changes, key=lambda c: c[0])          # stable, like the reference's sort
+        self._pos = 0
+
+    # change.py:612-731
+    @staticmethod
+    def _dem_changes(kind, start_t=None, end_t=None, rate=None, interval=None, n_cycles=None, size_range=None,
+                     distr='uniform', min_size=None, max_size=None, timesteps=None, sizes=None,
+                     increase_first=True):
+        if kind == 'monotonic':                                     # change.py:652-661
+            ts = list(range(start_t, end_t + 1))
+            return [(t, 'K_current', float(rate)) for t in ts]
+        if kind == 'stochastic':                                    # change.py:669-688
+            ts = list(range(start_t, end_t + 1, 1 if interval is None else interval))
+            if distr == 'uniform':
+                sz = np.random.uniform(*size_range, len(ts))
+            elif distr == 'normal':
+                sz = np.random.normal(loc=np.mean(size_range), scale=(size_range[1] - size_range[0]) / 6,
+                                      size=len(ts))
+            else:
+                raise ValueError("Argument 'distr' must be a value among ['uniform', 'normal']")
+            sz[-1] = 1
+        elif kind == 'cyclical':                                    # change.py:691-731
+            if size_range is not None and min_size is None and max_size is None:
+                min_size, max_size = size_range
+            elif not (size_range is None and min_size is not None and max_size is not None):
+                raise ValueError('Must either provide size_range (as a tuple of minimum and maximum sizes), or '
+                                 'provide min_size and max_size separately, but not both.')
+            assert n_cycles <= (end_t - start_t) / 2
+            base = np.sin(np.linspace(0, 2 * np.pi, 1000))
+            if not increase_first:
+                base = base[::-1]
+            sb = np.array([1 + v * (max_size - 1) if v >= 0 else v for v in base])
+            sb = np.array([1 + v * (1 - min_size) if v < 0 else v for v in sb])
+            cyc_t = np.int32(np.linspace(start_t, end_t, n_cycles + 1))
+            sz = np.hstack([sb[np.int32(np.linspace(1, len(sb) - 1, ln))] for ln in np.diff(cyc_t)] + [1])
+            ts = list(range(cyc_t[0], cyc_t[-1] + 1))
+        elif kind == 'custom':                                      # change.py:734-738
+            assert len(timesteps) == len(sizes)
+            ts, sz = list(timesteps), list(sizes)
+        else:
+            raise ValueError("unknown demographic change kind '%s'" % kind)
+        t0 = int(ts[0])
+        return [(int(t), 'K_base', (float(v), t0)) for t, v in zip(ts, sz)]
+
+    def _next_t(self):
+        return self.changes[self._pos][0] if self._pos < len(self.changes) else None
+
+    def _make_change(self, t, spp):
+        """change.py:56-84: every change scheduled for time step t, in order."""
+        while self._pos < len(self.changes) and self.changes[self._pos][0] == t:
+            _, kind, payload = self.changes[self._pos]
+            self._pos += 1
+            if kind == 'K_current':
+                spp._override_K(spp.K * payload)                    # change.py:636-638
+            elif kind == 'K_base':
+                size, t0 = payload
+                if spp.t == t0:
+                    self.base_K = spp.K                             # change.py:642-644
+                spp._override_K(self.base_K * size)
+            else:
+                spp._set_parameter(*payload)                        # change.py:737-738
+
+
 class Landscape(dict):
     """landscape.py:199: dict of Layers keyed by layer number."""
 
@@ -614,14 +701,69 @@ class Species:
 
     def _on_raster_change(self, lyr_num, rast):
         if self._dev is not None:
-            self._dev.set_raster(lyr_num, rast)
+            self._dev.set_raster(lyr_num, rast)        # on-the-fly surfaces follow through the raster itself
+            # a table-mode conductance surface over this layer is re-built and swapped in
+            # (change.py:576-606: the reference pre-builds one _ConductanceSurface per change step)
+            tabs = [None, None]
+            for k, nm in enumerate(('_move_surf', '_disp_surf')):
+                surf = getattr(self, nm)
+                if surf is not None and surf.lyr_num == lyr_num and self._dev._surf_tabs[k] is not None:
+                    surf.surf = _make_conductance_surface(self._land[lyr_num].rast, surf.mix, surf.approx_len,
+                                                          surf.kappa)
+                    tabs[k] = surf.surf
+            if tabs[0] is not None or tabs[1] is not None:
+                self._dev.set_surface_tables(*tabs)
         if lyr_num == self.K_layer:
             self._set_K(self._land)
 
     # ---- the queue entries (sim/model.py:603-667) -------------------------------------
     def _set_K(self, land):
-        """species.py:546-547."""
+        """species.py:546-547.  (The device recomputes its K from the layer whenever the layer
+        or K_factor changes; it needs a push only to undo a demographic-change override.)"""
         self.K = land[self.K_layer].rast * self.K_factor
+        if self.__dict__.get('_K_overridden') and self._dev is not None:
+            self._dev.set_K(self.K)
+        self._K_overridden = False
+
+    def _override_K(self, K):
+        """A demographic change event rewrote spp.K (change.py:633-649)."""
+        self.K = np.asarray(K, dtype=np.float64)
+        self._K_overridden = True
+        if self._dev is not None:
+            self._dev.set_K(self.K)
+
+    _LIFE_HISTORY = {'b': 'b', 'R': 'R', 'n_births_distr_lambda': 'lam', 'n_births_fixed': 'n_births_fixed',
+                     'd_min': 'd_min', 'd_max': 'd_max', 'max_age': 'max_age', 'sex_ratio': 'sex_ratio_p',
+                     'K_factor': 'K_factor', 'choose_nearest_mate': 'choose_nearest',
+                     'inverse_dist_mating': 'inverse_dist', 'direction_distr_mu': 'direction_mu',
+                     'direction_distr_kappa': 'direction_kappa'}
+
+    def _set_parameter(self, parameter, val):
+        """A life-history change event: setattr(spp, parameter, val) (change.py:737-738)."""
+        setattr(self, parameter, val)                  # an instance attribute, shadowing _pv as in the reference
+        if self._dev is None:
+            return
+        prm = self._device_params()
+        upd = {}
+        if parameter in self._LIFE_HISTORY:
+            upd[self._LIFE_HISTORY[parameter]] = prm[self._LIFE_HISTORY[parameter]]
+        elif parameter.startswith('movement_distance_distr'):
+            upd['move_distr'] = prm['move_distr']
+        elif parameter.startswith('dispersal_distance_distr'):
+            upd['disp_distr'] = prm['disp_distr']
+        elif parameter in ('repro_age',):
+            return                                     # never applied by the reference (SURVEY.md quirk 2)
+        else:
+            raise NotImplementedError("life-history change of '%s' is not supported on the device path "
+                                      "(it fixes buffer sizes or the mating grid)" % parameter)
+        self._dev.set_life_history(**upd)
+        if parameter == 'K_factor' and not self.__dict__.get('_K_overridden'):
+            self.K = self._land[self.K_layer].rast * self.K_factor
+
+    def _make_change(self, verbose=False):
+        """species.py:836-838."""
+        if self._changer is not None:
+            self._changer._make_change(self.t, self)
 
     def _set_t(self):
         self.t += 1
@@ -906,6 +1048,8 @@ def _make_species(land, name, idx, spp_params, seed=0):
         lyr = [k for k, v in land.items() if v.name == ds.pop('layer')]
         assert len(lyr) == 1
         spp._disp_surf = _ConductanceSurface(land[lyr[0]], **ds)
+    if 'change' in spp_params:                               # species.py:3373-3395
+        spp._changer = _SpeciesChanger(spp, spp_params['change'], land)
     return spp
 
 
@@ -966,9 +1110,20 @@ class Model:
                 if not any(s.extinct for s in self.comm.values()):
                     spp._set_t()
                     spp._step(1)
-            if self.land._changer is not None:
-                self.land._make_change(self.t)                 # model.py:646-652
+            self._make_changes()
         return any(spp.extinct for spp in self.comm.values())
+
+    def _make_changes(self):
+        """The tail of the main queue (model.py:646-656): the landscape change of this time step,
+        Species._set_K for every species whenever the landscape has a changer (which also undoes a
+        demographic override of K, as in the reference), then the species' own changes."""
+        if self.land._changer is not None:
+            self.land._make_change(self.t)
+            for spp in self.comm.values():
+                spp._set_K(self.land)
+        for spp in self.comm.values():
+            if spp._changer is not None:
+                spp._make_change()
 
     def _check_comm_burned(self):
         """community.py:107-131 + burnin.py:94-103: minimum burn_T steps, then the paired
@@ -1000,11 +1155,17 @@ class Model:
             spp = next(iter(self.comm.values()))
             done = 0
             while done < T and not spp.extinct:
-                n = T - done
+                n = min(T - done, 65536)                              # the device holds 65 536 step records
                 changer = self.land._changer
+                events = []                                           # applied after the step at that t
                 if changer is not None and changer._pos < len(changer.changes):
-                    t_change = changer.changes[changer._pos][0]       # applied after the step at t_change
-                    n = max(1, min(n, t_change - self.t))
+                    events.append(changer.changes[changer._pos][0])
+                if spp._changer is not None and spp._changer._next_t() is not None:
+                    events.append(spp._changer._next_t())
+                if events:
+                    n = max(1, min(n, min(events) - self.t))
+                if changer is not None and spp.__dict__.get('_K_overridden'):
+                    n = 1                                             # the next _set_K undoes the override
                 n_rec0 = len(spp.Nt)
                 spp._step(n)
                 ran = len(spp.Nt) - n_rec0                           # < n if the species went extinct
@@ -1012,8 +1173,7 @@ class Model:
                 self.t += ran
                 self.comm.t += ran
                 done += ran
-                if changer is not None:
-                    self.land._make_change(self.t)                    # model.py:646-652
+                self._make_changes()                                  # model.py:646-656
                 if ran < n:
                     break
             return

@@ -303,7 +303,8 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   }
   DM(ctx, &W.mate, cap);
   // a cell is crowded when its 3x3 block holds >= GNX_FM_HEAVY_K entries; an entry lies in at most
-  // 9 blocks, so at most 9 n / GNX_FM_HEAVY_K (< n / 4) non-empty cells are
+  // 9 blocks, so at most 9 n / GNX_FM_HEAVY_K non-empty cells are, and each contributes one work
+  // item per 32 focals (+ n / 32): below n / 4 in all
   W.heavy_cap = (int32_t)(cap / 4 + 1024);
   DM(ctx, &W.heavy, (size_t)W.heavy_cap);
   DM(ctx, &W.n_nbrs, cap);

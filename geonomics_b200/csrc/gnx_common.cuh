@@ -150,7 +150,7 @@ struct Work {
   int32_t* sort_vals[2];
   uint32_t* sort_hist;     // [256][tiles]
   int32_t* mate;
-  uint32_t* heavy;         // packed keys of the crowded mating cells of this step (k_find_mates_dense)
+  uint2* heavy;            // work items of k_find_mates_dense: {packed key of a crowded mating cell, first focal of a batch of 32}
   int32_t heavy_cap;
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]

@@ -318,8 +318,9 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
 //   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are kept as bit
 //           masks and the k-th is picked, k = (R * count) >> 32.  Cells whose 3x3 block is
 //           crowded (a row range longer than 64 entries, or >= GNX_FM_HEAVY_K entries in all)
-//           are not searched here: their first focal appends the cell to Work.heavy and
-//           k_find_mates_dense takes them, one warp per cell with the lanes across candidates
+//           are not searched here: the first of every 32 focals of such a cell appends a work
+//           item to Work.heavy and k_find_mates_dense takes them, one warp per item with the
+//           lanes across candidates
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
@@ -372,9 +373,10 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       // only, so every focal of the cell takes this exit; the cell's first entry announces it)
       const int l0 = hi[0] - lo[0], l1 = hi[1] - lo[1], l2 = hi[2] - lo[2];
       if (max(l0, max(l1, l2)) > 64 || l0 + l1 + l2 >= GNX_FM_HEAVY_K) {
-        if (p == (int)w.cell_start[cy * land.ncx + cx]) {
+        // one work item per batch of 32 focals of the cell, announced by the batch's first entry
+        if (((p - (int)w.cell_start[cy * land.ncx + cx]) & 31) == 0) {
           const int pos = atomicAdd(&c->n_heavy, 1);
-          if (pos < w.heavy_cap) w.heavy[pos] = key;
+          if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(key, (uint32_t)p);
           else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
         }
         continue;
@@ -488,28 +490,75 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
   }
 }
 
-// ----- k_find_mates_dense: the crowded cells of MODE 0, one warp per cell ------------------
+// ----- k_find_mates_dense: the crowded cells of MODE 0, one warp per batch of 32 focals -----
 // Evolved populations clump (c4 after 1000 steps: 94 neighbours per individual on average, 350
 // at the 99th percentile), and a thread per focal then walks hundreds of candidates with its
 // own trip count.  Here the LANES run across the candidates of the cell's 3x3 block (three
-// contiguous ranges of pop.xy): each lane keeps FMD_CG candidates in registers (coalesced
+// contiguous ranges of pop.xy): each lane keeps up to FMD_CG candidates in registers (coalesced
 // 128-bit loads, once per batch of 32 focals), the focals of the batch are broadcast one after
 // the other from shared memory, and a ballot per 32 candidates IS the validity mask in
 // canonical order.  The masks go to shared memory [focal][chunk]; then the lanes switch to one
 // focal each for the count, the draw and the k-th-neighbour pick -- same counts, same canonical
 // order, same Philox stream as k_find_mates, so the two kernels are interchangeable bit for bit.
-// Blocks of up to 64 chunks (2048 candidates) keep their masks; beyond that each lane walks.
+// The distance test is the reference's (products and sum rounded separately, closed ball); the
+// comparison itself is done on the bit patterns (non-negative doubles order like integers),
+// which takes it off the FP64 pipe that bounds this kernel.
+// Blocks of up to 64 chunks (2048 candidates) keep their masks; larger ones are swept twice
+// (count, then pick) without storing them.  Work items are handed out by an atomic cursor.
 #define FMD_WARPS 4
 #define FMD_CHUNKS 64
 #define FMD_CG 4                       // chunks of 32 candidates held in registers at a time
 #define FMD_STRIDE (FMD_CHUNKS + 4)    // row stride in words: rows stay 16-byte aligned
+
+struct FmdBlock {                      // the 3x3 block of a crowded cell as one candidate sequence
+  int lo0, lo1, lo2, e1, e2, K;
+  __device__ __forceinline__ int entry(int ci) const {
+    return ci < e1 ? lo0 + ci : (ci < e2 ? lo1 + (ci - e1) : lo2 + (ci - e2));
+  }
+};
+
+// ballots of NC chunks (held in cv) against focal f
+template <int NC>
+__device__ __forceinline__ void fmd_ballots(const double2* cv, const double2 f, long long r2b, uint32_t* bm) {
+#pragma unroll
+  for (int j = 0; j < FMD_CG; ++j) {
+    if (j < NC) {
+      const double dx = cv[j].x - f.x, dy = cv[j].y - f.y;
+      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      bm[j] = __ballot_sync(0xffffffffu, __double_as_longlong(d2) <= r2b);
+    } else {
+      bm[j] = 0u;
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void fmd_group(const double2* __restrict__ sxy, const FmdBlock& blk, const double2* foc,
+                                          uint32_t (*mk)[FMD_STRIDE], int nf, int cg, int lane, long long r2b) {
+  double2 cv[FMD_CG];
+#pragma unroll
+  for (int j = 0; j < FMD_CG; ++j) {
+    if (j < NC) {
+      const int ci = ((cg + j) << 5) + lane;
+      // lanes past the end hold a point at infinity: it fails every distance test
+      cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
+    }
+  }
+#pragma unroll 2
+  for (int fi = 0; fi < nf; ++fi) {
+    uint32_t bm[FMD_CG];
+    fmd_ballots<NC>(cv, foc[fi], r2b, bm);
+    if (lane == 0) *reinterpret_cast<uint4*>(&mk[fi][cg]) = make_uint4(bm[0], bm[1], bm[2], bm[3]);
+  }
+}
+
 __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, Land land, Params prm, DevDraws dr,
                                                                        Work w, Counters* c) {
   __shared__ __align__(16) uint32_t smask[FMD_WARPS][32][FMD_STRIDE];
   __shared__ double2 sfoc[FMD_WARPS][32];
   const int n_heavy = min(c->n_heavy, w.heavy_cap), cur = c->cur;
   const int64_t t = c->t;
-  const double r2 = prm.r2;
+  const long long r2b = __double_as_longlong(prm.r2);
   const double2* __restrict__ sxy = pop.xy[cur];
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -520,7 +569,9 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
     if (lane == 0) h = atomicAdd(&c->heavy_next, 1);
     h = __shfl_sync(0xffffffffu, h, 0);
     if (h >= n_heavy) break;
-    const uint32_t key = w.heavy[h];
+    const uint2 item = w.heavy[h];
+    const uint32_t key = item.x;
+    const int fb = (int)item.y;
     const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
     int lo[3], len[3];
@@ -531,97 +582,116 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
       lo[r] = (int)w.cell_start[row * land.ncx + x0];
       len[r] = (int)w.cell_start[row * land.ncx + x1 + 1] - lo[r];
     }
-    const int e1 = len[0], e2 = len[0] + len[1], K = e2 + len[2];
-    const int nch = (K + 31) >> 5;
+    FmdBlock blk;
+    blk.lo0 = lo[0]; blk.lo1 = lo[1]; blk.lo2 = lo[2];
+    blk.e1 = len[0]; blk.e2 = len[0] + len[1]; blk.K = blk.e2 + len[2];
+    const int nch = (blk.K + 31) >> 5;
     const bool keep = nch <= FMD_CHUNKS;
-    const int fs = (int)w.cell_start[cy * land.ncx + cx], fe = (int)w.cell_start[cy * land.ncx + cx + 1];
-    // entry number of candidate ci of the concatenated ranges
-    auto cand_entry = [&](int ci) { return ci < e1 ? lo[0] + ci : (ci < e2 ? lo[1] + (ci - e1) : lo[2] + (ci - e2)); };
-    for (int fb = fs; fb < fe; fb += 32) {
-      const int nf = min(32, fe - fb);
-      const int p = fb + lane;
-      const double2 myf = lane < nf ? sxy[p] : make_double2(0.0, 0.0);
-      if (keep) {
-        foc[lane] = myf;
-        __syncwarp();
-        // ---- lanes across candidates: FMD_CG chunks in registers, every focal of the batch against them
-        for (int cg = 0; cg < nch; cg += FMD_CG) {
-          double2 cv[FMD_CG];
-#pragma unroll
-          for (int j = 0; j < FMD_CG; ++j) {
-            const int ci = ((cg + j) << 5) + lane;
-            // lanes past the end hold a point at infinity: it fails every distance test
-            cv[j] = ci < K ? sxy[cand_entry(ci)] : make_double2(1e300, 1e300);
-          }
-#pragma unroll 2
-          for (int fi = 0; fi < nf; ++fi) {
-            const double2 f = foc[fi];
-            uint32_t bm[FMD_CG];
-#pragma unroll
-            for (int j = 0; j < FMD_CG; ++j) {
-              const double dx = cv[j].x - f.x, dy = cv[j].y - f.y;
-              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              bm[j] = __ballot_sync(0xffffffffu, d2 <= r2);
-            }
-            if (lane == 0) *reinterpret_cast<uint4*>(&mk[fi][cg]) = make_uint4(bm[0], bm[1], bm[2], bm[3]);
-          }
-        }
-        __syncwarp();
-      }
+    const int fe = (int)w.cell_start[cy * land.ncx + cx + 1];
+    const int nf = min(32, fe - fb);
+    const int p = fb + lane;
+    const double2 myf = lane < nf ? sxy[p] : make_double2(0.0, 0.0);
+    const int self = blk.e1 + (p - lo[1]);             // the focal's own position among the candidates
+    foc[lane] = myf;
+    __syncwarp();
+    int cnt = 0, sel_q = -1, k = 0;
+    uint32_t R = 0u;
+    double u_keep = 1.0;
+    const int io = (lane < nf && ord) ? ord[p] : p;
+    if (keep) {
+      // ---- lanes across candidates: FMD_CG chunks in registers, every focal of the batch against them
+      int cg = 0;
+      for (; cg + FMD_CG <= nch; cg += FMD_CG) fmd_group<FMD_CG>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      const int rem = nch - cg;
+      if (rem == 1) fmd_group<1>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      else if (rem == 2) fmd_group<2>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      else if (rem == 3) fmd_group<3>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      __syncwarp();
       // ---- lanes across focals: count, draw, pick (spatial.py:232-242, species.py:2212-2214)
       if (lane < nf) {
-        const int self = e1 + (p - lo[1]);             // the focal's own position among the candidates
         const int ngrp = (nch + FMD_CG - 1) / FMD_CG * FMD_CG;
-        int cnt = 0;
-        if (keep) {
-          mk[lane][self >> 5] &= ~(1u << (self & 31));
-          for (int ch = 0; ch < ngrp; ++ch) cnt += __popc(mk[lane][ch]);
-        } else {                               // more than 2048 candidates: this lane walks them
-          for (int ci = 0; ci < K; ++ci) {
-            const double2 cxy = sxy[cand_entry(ci)];
-            const double dx = cxy.x - myf.x, dy = cxy.y - myf.y;
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            cnt += (d2 <= r2 && ci != self) ? 1 : 0;
-          }
-        }
-        if (prm.store_debug) w.n_nbrs[p] = cnt;
-        int mate = -1;
+        mk[lane][self >> 5] &= ~(1u << (self & 31));
+        for (int ch = 0; ch < ngrp; ++ch) cnt += __popc(mk[lane][ch]);
         if (cnt > 0) {
-          const int io = ord ? ord[p] : p;
           RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
-          const uint32_t R = dr.mate_R ? dr.mate_R[io] : g.u32();
-          int k = (int)choose_k(R, (uint32_t)cnt);
-          int sel_q = -1;
-          if (keep) {
-            int ch = 0;
-            uint32_t m = mk[lane][0];
-            for (;;) {
-              const int pc = __popc(m);
-              if (k < pc) break;
-              k -= pc;
-              ch += 1;
-              m = mk[lane][ch];
-            }
-            sel_q = cand_entry((ch << 5) + kth_set_bit(m, k));
-          } else {
-            for (int ci = 0; ci < K && sel_q < 0; ++ci) {
-              const int q = cand_entry(ci);
-              const double2 cxy = sxy[q];
-              const double dx = cxy.x - myf.x, dy = cxy.y - myf.y;
-              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              if (d2 <= r2 && ci != self) {
-                if (k == 0) sel_q = q;
-                k -= 1;
-              }
-            }
+          R = dr.mate_R ? dr.mate_R[io] : g.u32();
+          k = (int)choose_k(R, (uint32_t)cnt);
+          int ch = 0;
+          uint32_t m = mk[lane][0];
+          for (;;) {
+            const int pc = __popc(m);
+            if (k < pc) break;
+            k -= pc;
+            ch += 1;
+            m = mk[lane][ch];
           }
-          const double u = dr.mate_u ? dr.mate_u[io] : g.uniform();
-          if (u < prm.c.b) mate = sel_q;
+          sel_q = blk.entry((ch << 5) + kth_set_bit(m, k));
+          u_keep = dr.mate_u ? dr.mate_u[io] : g.uniform();
         }
-        w.mate[p] = mate;
       }
-      __syncwarp();
+    } else {
+      // ---- more than 2048 candidates: sweep 1 counts, sweep 2 finds each focal's k-th neighbour
+      for (int cg = 0; cg < nch; cg += FMD_CG) {
+        double2 cv[FMD_CG];
+#pragma unroll
+        for (int j = 0; j < FMD_CG; ++j) {
+          const int ci = ((cg + j) << 5) + lane;
+          cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
+        }
+        for (int fi = 0; fi < nf; ++fi) {
+          uint32_t bm[FMD_CG];
+          fmd_ballots<FMD_CG>(cv, foc[fi], r2b, bm);
+          const int sf = blk.e1 + (fb + fi - lo[1]);
+          int pc = 0;
+#pragma unroll
+          for (int j = 0; j < FMD_CG; ++j) {
+            if (cg + j == (sf >> 5)) bm[j] &= ~(1u << (sf & 31));
+            pc += __popc(bm[j]);
+          }
+          if (lane == fi) cnt += pc;
+        }
+      }
+      if (lane < nf && cnt > 0) {
+        RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
+        R = dr.mate_R ? dr.mate_R[io] : g.u32();
+        k = (int)choose_k(R, (uint32_t)cnt);
+        u_keep = dr.mate_u ? dr.mate_u[io] : g.uniform();
+      }
+      int run = 0;                                     // valid candidates of this lane's focal seen so far
+      for (int cg = 0; cg < nch; cg += FMD_CG) {
+        double2 cv[FMD_CG];
+#pragma unroll
+        for (int j = 0; j < FMD_CG; ++j) {
+          const int ci = ((cg + j) << 5) + lane;
+          cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
+        }
+        for (int fi = 0; fi < nf; ++fi) {
+          const int kf = __shfl_sync(0xffffffffu, k, fi), cf = __shfl_sync(0xffffffffu, cnt, fi);
+          int rf = __shfl_sync(0xffffffffu, run, fi);
+          if (cf == 0 || rf > kf) continue;            // nothing to pick / already picked (uniform)
+          uint32_t bm[FMD_CG];
+          fmd_ballots<FMD_CG>(cv, foc[fi], r2b, bm);
+          const int sf = blk.e1 + (fb + fi - lo[1]);
+          int sel = -1;
+#pragma unroll
+          for (int j = 0; j < FMD_CG; ++j) {
+            if (cg + j == (sf >> 5)) bm[j] &= ~(1u << (sf & 31));
+            const int pc = __popc(bm[j]);
+            if (sel < 0 && kf < rf + pc) sel = ((cg + j) << 5) + kth_set_bit(bm[j], kf - rf);
+            rf += pc;
+          }
+          if (lane == fi) {
+            run = sel >= 0 ? kf + 1 : rf;              // past k once picked
+            if (sel >= 0) sel_q = blk.entry(sel);
+          }
+        }
+      }
     }
+    if (lane < nf) {
+      if (prm.store_debug) w.n_nbrs[p] = cnt;
+      w.mate[p] = (cnt > 0 && u_keep < prm.c.b) ? sel_q : -1;
+    }
+    __syncwarp();
   }
 }
 

@@ -83,11 +83,13 @@ def population_arrays(spp):
     return out
 
 
-def sync_to_host(spp):
+def sync_to_host(spp, genomes=None):
     """Rebuild the Species' Individual objects from the device state (species order kept)."""
     from collections import OrderedDict
     dev = spp._gnx
-    s = dev.download(genomes=bool(spp.burned and spp.gen_arch is not None), e=True)
+    if genomes is None:
+        genomes = bool(spp.burned and spp.gen_arch is not None)
+    s = dev.download(genomes=genomes, e=True)
     proto = type(next(iter(spp.values()))) if len(spp) else None
     new = OrderedDict()
     g = s.get('g')
@@ -95,8 +97,9 @@ def sync_to_host(spp):
         idx = int(s['idx'][k])
         ind = spp.get(idx)
         if ind is None:
-            ind = proto(idx=idx, x=float(s['x'][k]), y=float(s['y'][k]), age=int(s['age'][k]),
-                        sex=int(s['sex'][k]) if spp.sex else None)
+            ind = proto(idx=idx, x=float(s['x'][k]), y=float(s['y'][k]), age=int(s['age'][k]), sex=1)
+            # (Individual.__init__ re-draws a falsy sex, individual.py:110-115: set it afterwards)
+            ind.sex = int(s['sex'][k])
         ind.x, ind.y, ind.age = float(s['x'][k]), float(s['y'][k]), int(s['age'][k])
         ind.e = list(s['e'][k]) if s.get('e') is not None else ind.e
         if g is not None:
@@ -109,15 +112,75 @@ def sync_to_host(spp):
     spp._set_coords_and_cells()
 
 
+def _set_device_mutation(spp, dev):
+    """Hand the reference's mutation bookkeeping (genome.py:573-608, 1060-1104) to the device."""
+    ga = spp.gen_arch
+    if not getattr(spp, 'mutate', False) or ga is None:
+        return
+    if ga.traits is not None and any((t.mu or 0) > 0 for t in ga.traits.values()):
+        raise NotImplementedError('trait mutation (Trait.mu > 0) is not supported on the device path; the reference '
+                                  'itself raises for it when use_tskit=False (genome.py:416-437)')
+    if ga._mutables is None:
+        raise RuntimeError('spp.mutate is set but gen_arch._mutables is not: attach after burn-in, or let the '
+                           'wrapped _set_genomes_and_tables run first')
+    dev.set_mutation(ga.mu_neut or 0, ga.mu_delet or 0, list(ga._mutables),
+                     np.asarray(ga.nonneut_loci, dtype=np.int64), np.asarray(ga.delet_loci, dtype=np.int64),
+                     np.asarray(ga.delet_loci_s, dtype=np.float64), ga.delet_alpha_distr_shape,
+                     ga.delet_alpha_distr_scale, log_capacity=max(int(ga.L), 16))
+
+
+def _sync_mutations(spp, dev):
+    """Device mutation log -> the reference's gen_arch bookkeeping (genome.py:753-788)."""
+    ga = spp.gen_arch
+    rows, st = dev.read_mutations(max_rows=max(int(ga.L), 16))
+    ga._mutables = list(ga._mutables)[:st['n_mutables']]
+    ga.nonneut_loci = st['nonneut_loci'].astype(np.int64)
+    ga.neut_loci = np.array(sorted(set(range(ga.L)).difference(set(int(v) for v in ga.nonneut_loci))))
+    ga.delet_loci = st['delet_loci'].astype(np.int64)
+    ga.delet_loci_s = st['delet_s']
+    return rows
+
+
+def detach(spp, land=None):
+    """Undo `attach`: restore the reference's own methods and free the device context."""
+    st = spp.__dict__.pop('_gnx_attached', None)
+    if st is None:
+        return
+    for name in ('_set_age_stage', '_do_movement', '_do_pop_dynamics', '_set_Nt', '_set_genomes_and_tables',
+                 '_make_change'):
+        spp.__dict__.pop(name, None)                   # instance overrides off: the class methods show again
+    st['land'].__dict__.pop('_set_raster', None)
+    if st.get('prev_set_raster') is not None:          # another attached species' wrapper was underneath
+        st['land']._set_raster = st['prev_set_raster']
+    try:
+        st['dev'].close()
+    finally:
+        spp.__dict__.pop('_gnx', None)
+
+
 def attach(spp, land, seed=0, capacity=None, eager=False):
-    """Move `spp` onto the GPU and swap its queue entries (model.py:615-640)."""
+    """Move `spp` onto the GPU and swap its queue entries (model.py:615-656).
+
+    May be called before the burn-in (the device then runs in burn mode; the reference's own
+    `_set_genomes_and_tables` is wrapped so that the genomes it assigns after the burn-in are
+    uploaded and selection / mutation switch on) or after it.  Species change events
+    (`spp._changer`, change.py:612-742) keep running through the reference's own change functions;
+    the device follows `spp.K` and the changed parameters.  Calling it again on the same species
+    replaces the previous attachment."""
+    if spp.gen_arch is not None and getattr(spp.gen_arch, 'use_tskit', False):
+        raise NotImplementedError('use_tskit=True species: genotype arrays hold only non-neutral loci')
+    detach(spp)
     a = species_to_device_args(spp, land, capacity)
     dev = DeviceSpecies(a['land_dim'], a['rasters'], a['prm'], a['gen_arch'], capacity=a['capacity'], seed=seed,
                         res_ratio=a['res_ratio'])
     p = population_arrays(spp)
     dev.set_burn(not spp.burned)
-    dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], g=p.get('g'), max_ind_idx=spp.max_ind_idx)
+    dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], g=p.get('g') if spp.burned else None,
+               max_ind_idx=spp.max_ind_idx)
+    if spp.burned:
+        _set_device_mutation(spp, dev)
     spp._gnx = dev
+    cls = type(spp)
 
     spp._set_age_stage = lambda: None                  # folded into gnx_step
     spp._do_movement = lambda land=None: None          # folded into gnx_step
@@ -132,15 +195,55 @@ def attach(spp, land, seed=0, capacity=None, eager=False):
             spp.n_deaths.append(int(r['n_deaths']))
             spp.max_ind_idx += int(r['n_births'])
             spp.extinct = r['Nt'] == 0                 # demography.py:329
+        if getattr(spp, 'mutate', False) and spp.burned and spp.gen_arch is not None:
+            _sync_mutations(spp, dev)
         if eager:
             sync_to_host(spp)
     spp._do_pop_dynamics = _do_pop_dynamics
     spp._set_Nt = _set_Nt
 
-    orig_set_raster = land._set_raster                 # landscape.py:353-354
+    def _set_genomes_and_tables(burn_T, T):
+        # species.py:956-1094 runs on the host objects (they hold the burned-in positions), then the
+        # genomes, the main-phase flags and the mutation bookkeeping go to the device
+        sync_to_host(spp, genomes=False)
+        cls._set_genomes_and_tables(spp, burn_T, T)
+        q = population_arrays(spp)
+        dev.set_burn(False)
+        dev.upload(q['x'], q['y'], q['age'], q['sex'], q['idx'], g=q.get('g'), max_ind_idx=spp.max_ind_idx)
+        _set_device_mutation(spp, dev)
+    spp._set_genomes_and_tables = _set_genomes_and_tables
+
+    if getattr(spp, '_changer', None) is not None:
+        mirrored = ('b', 'R', 'lam', 'n_births_fixed', 'd_min', 'd_max', 'max_age', 'sex_ratio_p', 'K_factor',
+                    'choose_nearest', 'inverse_dist', 'direction_mu', 'direction_kappa', 'move_distr', 'disp_distr')
+
+        def _make_change(verbose=False):
+            # species.py:836-838 runs the reference's own change functions; whatever they changed
+            # (spp.K, life-history attributes, the movement surface) is mirrored afterwards
+            nxt = spp._changer.next_change
+            due = nxt is not None and nxt[0] == spp.t
+            surf_before = (getattr(spp, '_move_surf', None), getattr(spp, '_disp_surf', None))
+            cls._make_change(spp, verbose=verbose)
+            if not due:
+                return
+            dev.set_K(np.asarray(spp.K, dtype=np.float64))
+            now = species_to_device_args(spp, land, capacity=a['capacity'])['prm']
+            upd = {k: now[k] for k in mirrored if k in now and now[k] != dev.prm.get(k)}
+            if upd:
+                dev.set_life_history(**upd)
+            surf_now = (getattr(spp, '_move_surf', None), getattr(spp, '_disp_surf', None))
+            tabs = [np.asarray(sn.surf) if (sn is not None and sn is not sb) else None
+                    for sn, sb in zip(surf_now, surf_before)]
+            if tabs[0] is not None or tabs[1] is not None:
+                dev.set_surface_tables(*tabs)          # change.py:597-606
+        spp._make_change = _make_change
+
+    prev_wrapper = land.__dict__.get('_set_raster')   # another attached species' wrapper, if any
+    inner = land._set_raster                           # landscape.py:353-354 (or that wrapper)
 
     def _set_raster(lyr_num, rast):
-        orig_set_raster(lyr_num, rast)
-        dev.set_raster(lyr_num, rast)                  # also rescales K when lyr_num == K_layer
+        inner(lyr_num, rast)
+        dev.set_raster(lyr_num, rast)                  # also recomputes K when lyr_num == K_layer
     land._set_raster = _set_raster
+    spp._gnx_attached = dict(dev=dev, land=land, prev_set_raster=prev_wrapper)
     return dev

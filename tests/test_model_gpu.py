@@ -193,3 +193,89 @@ def test_region_stats_and_fst_match_numpy(model):
     np.testing.assert_allclose(dev.fst(west, east), fst_ref, rtol=1e-12, atol=1e-15, equal_nan=True)
     whole = dev.stats()
     assert whole['N'] == len(spp)
+
+
+def _read_K(spp):
+    X, Y = spp._land_dim
+    return spp._dev.read('K_RAST', X * Y).reshape(Y, X)
+
+
+def test_species_change_events_reach_the_device():
+    """a17: demographic and life-history change events (change.py:612-742) through Model.walk:
+    the device's K raster follows spp.K exactly, the changed birth probability shows in the pair
+    counts, and the population tracks the new carrying capacity."""
+    from geonomics_b200 import api
+    p = api.read_parameters_file(PARAMS)
+    spp_p = p['comm']['species'][next(iter(p['comm']['species']))]
+    spp_p['change'] = {
+        'dem': {0: dict(kind='custom', timesteps=[3, 12], sizes=[0.4, 1.0], start_t=None, end_t=None, rate=None,
+                        interval=None, n_cycles=None, size_range=None, distr='uniform')},
+        'life_hist': {'b': dict(timesteps=[20], vals=[0.6])},
+    }
+    for lp in p['landscape']['layers'].values():          # no landscape changer: K keeps the override
+        lp.pop('change', None)
+    mod = api.make_model(p)
+    mod.walk(10000, 'burn')
+    spp = mod.comm[0]
+    K0 = spp.K.copy()
+    assert spp._changer is not None and np.array_equal(_read_K(spp), K0)
+    mod.walk(3, 'main')                                    # t = 0, 1, 2
+    assert np.array_equal(spp.K, K0)
+    N_before = spp.Nt[-1]
+    mod.walk(1, 'main')                                    # the change scheduled for t = 3 runs after that step
+    assert np.array_equal(spp.K, K0 * 0.4) and np.array_equal(_read_K(spp), K0 * 0.4)
+    mod.walk(8, 'main')                                    # t = 4 .. 11 under 0.4 K
+    assert spp.Nt[-1] < 0.75 * N_before
+    mod.walk(1, 'main')                                    # t = 12: back to the base K
+    assert np.array_equal(spp.K, K0) and np.array_equal(_read_K(spp), K0)
+    mod.walk(8, 'main')                                    # t = 13 .. 20, one bulk call across no event
+    assert spp.b == 0.6 and spp._dev.prm['b'] == 0.6       # life-history change at t = 20
+    nb = np.array(spp.n_births, dtype=float)
+    N = np.array(spp.Nt, dtype=float)
+    mod.walk(6, 'main')
+    nb, N = np.array(spp.n_births, dtype=float), np.array(spp.Nt, dtype=float)
+    rate_before = (nb[-14:-6] / N[-15:-7]).mean()
+    rate_after = (nb[-5:] / N[-6:-1]).mean()
+    assert rate_after > 2.0 * rate_before                  # b went from 0.2 to 0.6
+    assert mod.t == 26
+
+
+def test_table_surface_follows_a_landscape_change():
+    """a table-mode conductance surface over a layer that changes is re-built and
+    re-uploaded (change.py:576-606), not left stale."""
+    from geonomics_b200 import api
+    rng = np.random.default_rng(5)
+    dim = (12, 10)
+    # conductance rises with y (a y-gradient: the reference's plain mean of the max-valued neighbours'
+    # directions, spatial.py:376-381, is only a true mean direction when they do not straddle +-pi)
+    lyr = api.Layer(np.tile(np.linspace(0.05, 1, dim[1])[:, None], (1, dim[0])), 'defined', 'cond', dim, idx=0)
+    land = api.Landscape({0: lyr})
+    spp_params = api.ParametersDict({
+        'init': {'N': 300, 'K_layer': 'cond', 'K_factor': 3},
+        'mating': dict(repro_age=0, sex=False, sex_ratio=1.0, R=0.5, b=0.2, n_births_distr_lambda=1,
+                       n_births_fixed=True, mating_radius=2, choose_nearest_mate=False, inverse_dist_mating=False),
+        'mortality': dict(max_age=None, d_min=0, d_max=1, density_grid_window_width=None),
+        'movement': dict(move=True, direction_distr_mu=0, direction_distr_kappa=0,
+                         movement_distance_distr_param1=0.5, movement_distance_distr_param2=1.0,
+                         movement_distance_distr='wald', dispersal_distance_distr_param1=0.5,
+                         dispersal_distance_distr_param2=1.0, dispersal_distance_distr='wald',
+                         move_surf=dict(layer='cond', mixture=False, vm_distr_kappa=50, approx_len=64)),
+    })
+    np.random.seed(3)
+    spp = api._make_species(land, 'spp_0', 0, spp_params, seed=11)
+    spp._attach()
+    try:
+        # the non-mixture surface points up the gradient (direction ~ +pi/2)
+        tab0 = spp._move_surf.surf.copy()
+        assert abs(float(np.median(tab0[5, 5].astype(float))) - np.pi / 2) < 0.3
+        spp._step(3)
+        y_mean_up = spp._get_y().mean()
+        land._set_raster(0, land[0].rast[::-1].copy())      # mirror: conductance now rises towards y = 0
+        tab1 = spp._move_surf.surf
+        assert abs(float(np.median(tab1[5, 5].astype(float))) + np.pi / 2) < 0.3
+        assert np.array_equal(spp._dev._surf_tabs[0], tab1) and not np.array_equal(tab0, tab1)
+        spp._step(6)
+        assert spp._get_y().mean() < y_mean_up - 0.5        # the population now drifts the other way
+    finally:
+        spp._dev.close()
+    del rng
