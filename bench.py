@@ -190,28 +190,119 @@ def cpu_baseline(cfg, n_sample, steps, procs, seed=123):
     return total / wall, total, wall
 
 
+def _reference_worker(args):
+    """One process = one replica of the workload run by the UNMODIFIED reference (oracle/_ref, or
+    /root/reference in the build container) through its own public API: make_model -> walk('burn')
+    -> time walk(steps, 'main').  Only import-time dependencies that this image lacks are shimmed
+    (oracle/ref_shims.py) and the burn-in length is fixed (its stationarity tests are burn-in control,
+    outside the timed region)."""
+    cfg, n_sample, steps, warmup, seed = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import contextlib
+    import io
+    import tempfile
+    import warnings
+    warnings.filterwarnings('ignore')
+    from geonomics_b200 import workloads
+    from oracle import ref_shims
+    with contextlib.redirect_stdout(io.StringIO()):
+        gnx = ref_shims.install()
+    import geonomics.sim.burnin as _b
+    _b._test_t_threshold = lambda *a, **k: True
+    _b._test_adf_threshold = lambda *a, **k: True
+    _b.SpatialTester.run_test = lambda self, n, alpha=0.05: True
+    c = workloads.scaled(cfg, n_sample)
+    X, Y = c['dim']
+    tmp = tempfile.mkdtemp(prefix='gnx_ref_bench_')
+    path = os.path.join(tmp, 'params.py')
+    spp = [{'movement': True, 'movement_surface': bool(c['surfaces']), 'dispersal_surface': bool(c['surfaces']),
+            'genomes': True, 'n_traits': c['n_traits'], 'demographic_change': 0, 'parameter_change': False}]
+    with contextlib.redirect_stdout(io.StringIO()):
+        gnx.make_parameters_file(path, layers=[{'type': 'defined', 'change': False} for _ in range(3)], species=spp)
+    txt = open(path).read()
+    open(path, 'w').write('import numpy as np\n' + txt)                     # params.py:180 quirk
+    p = gnx.read_parameters_file(path)
+    p['landscape']['main']['dim'] = (X, Y)
+    lyr0 = workloads.smooth_field((X, Y), 7) if c['surfaces'] else np.ones((Y, X))
+    rasts = [lyr0, np.tile(np.linspace(0, 1, X), (Y, 1)), np.tile(np.linspace(0, 1, Y)[:, None], (1, X))]
+    for n, r in enumerate(rasts):
+        p['landscape']['layers']['lyr_%i' % n]['init']['defined']['rast'] = r
+    s = p['comm']['species']['spp_0']
+    s['init'].update(N=c['N'], K_layer='lyr_0', K_factor=c['N'] / float(lyr0.sum()))
+    s['mating'].update(sex=False, sex_ratio=1 / 1, b=c['b'], R=c['R'], n_births_distr_lambda=c['lam'],
+                       n_births_fixed=True, mating_radius=c['mating_radius'], choose_nearest_mate=False,
+                       inverse_dist_mating=False)
+    s['mortality'].update(max_age=None, d_min=0, d_max=1)
+    mv = s['movement']
+    mv.update(direction_distr_mu=0, direction_distr_kappa=0, movement_distance_distr='wald',
+              movement_distance_distr_param1=1.0, movement_distance_distr_param2=1.0,
+              dispersal_distance_distr='wald', dispersal_distance_distr_param1=1.0,
+              dispersal_distance_distr_param2=1.0)
+    if c['surfaces']:
+        for k in ('move_surf', 'disp_surf'):
+            mv[k].update(layer='lyr_0', mixture=True, vm_distr_kappa=12, approx_len=200)
+    g = s['gen_arch']
+    g.update(L=c['L'], use_tskit=False, dom=False, n_recomb_sims=1000, r_distr_alpha=c['recomb_rate'],
+             r_distr_beta=None, start_p_fixed=0.5, mu_neut=0, mu_delet=0)
+    for t in range(c['n_traits']):
+        g['traits']['trait_%i' % t].update(layer='lyr_%i' % (1 + t % 2), n_loci=c['loci_per_trait'], phi=c['phi'],
+                                           gamma=c['gamma'], mu=0, alpha_distr_mu=0.0, alpha_distr_sigma=0.1,
+                                           max_alpha_mag=0.25, univ_adv=False)
+    p['model'].update(T=steps + warmup + 1, burn_T=6)
+    p['model']['seed'] = {'num': seed}
+    with contextlib.redirect_stdout(io.StringIO()):
+        mod = gnx.make_model(p, name='ref_bench')
+        mod.walk(10000, 'burn', verbose=False)
+        mod.walk(max(1, warmup), 'main', verbose=False)
+        spp0 = mod.comm[0]
+        n_rec = len(spp0.Nt)
+        N_before = len(spp0)
+        t0 = time.perf_counter()
+        mod.walk(steps, 'main', verbose=False)
+        dt = time.perf_counter() - t0
+    Nt = [N_before] + list(spp0.Nt[n_rec:])
+    return float(sum(Nt[:-1])), dt                      # individuals at the start of every timed step
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    from oracle import ref_shims
     procs = os.cpu_count() or 1
-    n_sample = args.cpu_sample
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     t0 = time.perf_counter()
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        pass
-    value, total, wall = cpu_baseline(cfg, n_sample, max(1, args.steps), procs)
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    have_ref = ref_shims.reference_root() is not None
+    port_value, _, port_wall = cpu_baseline(cfg, args.cpu_sample, min(steps, 8), procs)
+    if have_ref:
+        n_sample = args.ref_sample
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_reference_worker, [(cfg, n_sample, steps, warmup, 1000 + k) for k in range(procs)])
+        total, wall = sum(r[0] for r in res), max(r[1] for r in res)
+        value = total / wall
+        kind = 'reference'
+        sample = ('%d processes x %d timed steps (after burn-in and %d warm-up steps) of a %d-individual replica of '
+                  'the workload (same per-capita parameters and density) run by the unmodified reference package '
+                  '(erthward/geonomics 1.4.9, installed in oracle/_ref) through make_model / Model.walk; the '
+                  'reference is single-threaded pure Python and its throughput is flat in N (BASELINE.md section '
+                  '2), so one replica per host core is its best use of the box' % (procs, steps, warmup, n_sample))
+    else:
+        value, wall, kind, n_sample = port_value, port_wall, 'port', args.cpu_sample
+        sample = ('%d processes x %d steps of a %d-individual replica, numpy oracle port of the reference '
+                  'algorithm (reference package not installed in oracle/_ref)' % (procs, min(steps, 8), n_sample))
     elapsed = time.perf_counter() - t0
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(1, args.steps),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64+u32 bitsets',
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 + int8 genotypes (numpy)',
         'data': 'synthetic',
-        'config': {'workload': args.workload + ' ' + workload_desc(cfg), 'cpu_sample_individuals': n_sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-                         'sample': '%d processes x %d steps of a %d-individual replica of the workload '
-                                   '(same per-capita parameters and density), numpy oracle port of the '
-                                   'reference algorithm; the reference itself is pure Python and does '
-                                   'not exist on the GPU box' % (procs, args.steps, n_sample)},
+        'config': {'workload': args.workload + ': ' + workload_desc(cfg), 'cpu_sample_individuals': n_sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': kind, 'sample': sample,
+                         'port': {'value': port_value, 'unit': UNIT, 'cores': procs,
+                                  'sample': 'numpy oracle port of the same algorithm, %d processes x %d steps of a '
+                                            '%d-individual replica' % (procs, min(steps, 8), args.cpu_sample)}},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': elapsed,
     }
@@ -363,6 +454,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (debug only)')
     ap.add_argument('--cpu-sample', type=int, default=100000)
     ap.add_argument('--cpu-steps', type=int, default=12)
+    ap.add_argument('--ref-sample', type=int, default=1500,
+                    help='individuals per replica of the unmodified reference (--impl reference; ~0.4 s per step per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--presteps', type=int, default=0, help='time steps simulated before the warm-up')

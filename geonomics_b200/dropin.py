@@ -158,7 +158,7 @@ def detach(spp, land=None):
         spp.__dict__.pop('_gnx', None)
 
 
-def attach(spp, land, seed=0, capacity=None, eager=False):
+def attach(spp, land, seed=0, capacity=None, eager=False, disp_tries_injected=6):
     """Move `spp` onto the GPU and swap its queue entries (model.py:615-656).
 
     May be called before the burn-in (the device then runs in burn mode; the reference's own
@@ -172,7 +172,7 @@ def attach(spp, land, seed=0, capacity=None, eager=False):
     detach(spp)
     a = species_to_device_args(spp, land, capacity)
     dev = DeviceSpecies(a['land_dim'], a['rasters'], a['prm'], a['gen_arch'], capacity=a['capacity'], seed=seed,
-                        res_ratio=a['res_ratio'])
+                        res_ratio=a['res_ratio'], disp_tries_injected=disp_tries_injected)
     p = population_arrays(spp)
     dev.set_burn(not spp.burned)
     dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], g=p.get('g') if spp.burned else None,
