@@ -619,12 +619,24 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, total, wall = cpu_baseline(cfg, args.cpu_sample, args.cpu_steps, 1)
-        cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-               'sample': '%d steps of a %d-individual replica of the workload (same per-capita parameters '
-                         'and density), numpy oracle port of the reference algorithm, 1 process; the pure-'
-                         'Python reference itself measured ~2.5e3 individual-generations/s in the build '
-                         'container (BASELINE.md section 2)' % (args.cpu_steps, args.cpu_sample),
-               'seconds': wall}
+        port = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                'sample': '%d steps of a %d-individual replica of the workload (same per-capita parameters '
+                          'and density), numpy oracle port of the reference algorithm, 1 process'
+                          % (args.cpu_steps, args.cpu_sample), 'seconds': wall}
+        cpu = port
+        from oracle import ref_shims
+        if ref_shims.reference_root() is not None:
+            # the unmodified reference package itself (oracle/_ref), one process, in a child so that its
+            # global numpy.random state and import shims stay out of this one
+            import multiprocessing as mp
+            with mp.get_context('spawn').Pool(1) as pool:
+                tot_r, wall_r = pool.map(_reference_worker, [(cfg, args.ref_sample, args.cpu_steps, 2, 1000)])[0]
+            cpu = {'value': tot_r / wall_r, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                   'sample': '%d timed steps (after burn-in and 2 warm-up steps) of a %d-individual replica of the '
+                             'workload (same per-capita parameters and density) run by the unmodified reference '
+                             'package (erthward/geonomics 1.4.9, oracle/_ref) through make_model / Model.walk, '
+                             '1 process (the reference is single-threaded)' % (args.cpu_steps, args.ref_sample),
+                   'seconds': wall_r, 'port': port}
     gs_iters = dev.counters()['gs_iters']
 
     for d in devs[1:]:
