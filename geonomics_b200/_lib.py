@@ -112,6 +112,24 @@ class Population(C.Structure):
     ]
 
 
+class StripConfig(C.Structure):
+    _fields_ = [
+        ('rank', C.c_int32), ('world', C.c_int32),
+        ('first_rows', c_int32_p),
+        ('migrant_capacity', C.c_int64), ('halo_capacity', C.c_int64),
+    ]
+
+
+class StripEndpoints(C.Structure):
+    _fields_ = [
+        ('base', C.c_void_p),
+        ('bytes', C.c_int64),
+        ('buf_offset', C.c_int64 * 4),
+        ('count_offset', C.c_int64 * 4),
+        ('ipc_handle', C.c_ubyte * 64),
+    ]
+
+
 class Mutation(C.Structure):
     _fields_ = [
         ('mu_neut', C.c_double), ('mu_delet', C.c_double),
@@ -184,6 +202,13 @@ SIGNATURES = {
     'gnx_death_prob': (C.c_int, [_ctx]),
     'gnx_mortality': (C.c_int, [_ctx]),
     'gnx_set_raster': (C.c_int, [_ctx, C.c_int32, c_double_p]),
+    'gnx_strip_enable': (C.c_int, [_ctx, C.POINTER(StripConfig)]),
+    'gnx_strip_endpoints': (C.c_int, [_ctx, C.POINTER(StripEndpoints)]),
+    'gnx_strip_connect': (C.c_int, [_ctx, C.c_int32, C.POINTER(StripEndpoints), C.c_int32]),
+    'gnx_strip_collective_ptrs': (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
+    'gnx_strip_phase': (C.c_int, [_ctx, C.c_int32]),
+    'gnx_strip_check': (C.c_int, [_ctx]),
     'gnx_set_K': (C.c_int, [_ctx, c_double_p]),
     'gnx_set_life_history': (C.c_int, [_ctx, C.POINTER(Config)]),
     'gnx_step': (C.c_int, [_ctx, C.c_int32]),

@@ -99,6 +99,14 @@ struct gnx_ctx {
   int64_t graph_launches = 0, graph_captures = 0;
   void* d_paths = nullptr;
   void* d_surf_tab[2] = {nullptr, nullptr};
+  // strip domain decomposition (gnx_strip.cuh)
+  Strip strip_h{};                      // host copy of the device-resident descriptor
+  Strip* d_strip = nullptr;             // nullptr: the landscape is not decomposed
+  unsigned char* strip_block = nullptr; // [counters | 4 receive buffers]: one allocation, one IPC handle
+  size_t strip_block_bytes = 0;
+  int64_t strip_buf_off[STRIP_N_BUF] = {0, 0, 0, 0};
+  std::vector<void*> strip_allocs;
+  std::vector<void*> strip_ipc_opened;
 };
 
 template <class T>
@@ -388,6 +396,10 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   free_bucket(ctx->dens_allocs);
   free_bucket(ctx->tsk_allocs);
   free_bucket(ctx->mut_allocs);
+  free_bucket(ctx->strip_allocs);
+  for (void* m : ctx->strip_ipc_opened) cudaIpcCloseMemHandle(m);
+  ctx->strip_ipc_opened.clear();
+  if (ctx->strip_block) cudaFree(ctx->strip_block);
   if (ctx->d_paths) cudaFree(ctx->d_paths);
   for (int k = 0; k < 2; ++k) if (ctx->d_surf_tab[k]) cudaFree(ctx->d_surf_tab[k]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1107,7 +1119,7 @@ static int move_key(gnx_ctx* ctx, int do_age, int do_move, int do_key) {
   }
   PROF(ctx, "k_move_key");
   k_move_key<<<grid_for(ctx, GNX_G_AGE), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work,
-                                                       ctx->d_c, do_age, do_move, do_key);
+                                                       ctx->d_c, do_age, do_move, do_key, ctx->d_strip);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -1140,7 +1152,7 @@ static int finish_regrid(gnx_ctx* ctx, int age_inc) {
   LAUNCHED(ctx);
   PROF(ctx, "k_regrid");
   k_regrid<<<grid_for(ctx, GNX_G_GATHER), 256, 0, s>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c, age_inc,
-                                                      ctx->prm.ordered);
+                                                      ctx->prm.ordered, ctx->d_strip);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -1448,14 +1460,25 @@ extern "C" int gnx_density_counts(gnx_ctx* ctx) {
   CK(cudaMemsetAsync(ctx->dens.counts, 0, (size_t)2 * ctx->dens.npts * 4, s));
   PROF(ctx, "k_density_counts");
   // one launch: blockIdx.y = 0 counts all individuals, 1 counts pair midpoints
-  k_density_counts<<<dim3(2 * ctx->num_sms, 2), 512, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens);
+  k_density_counts<<<dim3(2 * ctx->num_sms, 2), 512, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->dens, ctx->d_strip);
   LAUNCHED(ctx);
   return GNX_OK;
 }
 
-extern "C" int gnx_density_eval(gnx_ctx* ctx) {
-  ARG(ctx, "null ctx");
-  USE_DEVICE(ctx);
+// gnx_density_eval in two parts: the N raster (and its maximum), then the d raster that needs the
+// maximum -- under strip decomposition each rank evaluates its own landscape rows and the maximum
+// is reduced over the ranks in between
+static void raster_grid(const gnx_ctx* ctx, int* row_lo, int* row_hi, int* rgrid) {
+  *row_lo = ctx->d_strip ? ctx->strip_h.ly0 : 0;
+  *row_hi = ctx->d_strip ? ctx->strip_h.ly1 : ctx->cfg.dim_y;
+  // rows per CTA: the smallest whole number that fits the resident grid (no ragged last pass)
+  const int rows = std::max(1, *row_hi - *row_lo);
+  const int rg_max = grid_for(ctx, 8);
+  const int rows_per_cta = (rows + rg_max - 1) / rg_max;
+  *rgrid = (rows + rows_per_cta - 1) / rows_per_cta;
+}
+
+static int density_eval_N(gnx_ctx* ctx) {
   if (!ctx->have_density) { g_last_error = "density grids not set"; return GNX_ERR_STATE; }
   cudaStream_t s = ctx->stream;
   // scipy defaults reached through griddata: CloughTocher2DInterpolator(tol=1e-6, maxiter=400)
@@ -1475,18 +1498,23 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   k_ct_coefficients<<<std::max(1, (6 * ctx->dens.ntri + 127) / 128), 128, 0, s>>>(ctx->dens);
   LAUNCHED(ctx);
   CK(cudaMemsetAsync(ctx->work.fix_count, 0, sizeof(int32_t), s));
+  int row_lo, row_hi, rgrid;
+  raster_grid(ctx, &row_lo, &row_hi, &rgrid);
   PROF(ctx, "k_raster_N");
-  // rows per CTA: the smallest whole number that fits the resident grid (no ragged last pass)
-  const int rg_max = grid_for(ctx, 8);
-  const int rows_per_cta = (ctx->cfg.dim_y + rg_max - 1) / rg_max;
-  const int rgrid = (ctx->cfg.dim_y + rows_per_cta - 1) / rows_per_cta;
-  k_raster_N<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
+  k_raster_N<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c, row_lo, row_hi);
   LAUNCHED(ctx);
   PROF(ctx, "k_raster_N_fix");
   k_raster_N_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->work, ctx->d_c);
   LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+static int density_eval_d(gnx_ctx* ctx) {
+  cudaStream_t s = ctx->stream;
+  int row_lo, row_hi, rgrid;
+  raster_grid(ctx, &row_lo, &row_hi, &rgrid);
   PROF(ctx, "k_raster_d");
-  k_raster_d<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
+  k_raster_d<<<rgrid, 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c, row_lo, row_hi);
   LAUNCHED(ctx);
   PROF(ctx, "k_raster_d_fix");
   k_raster_d_fix<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->dens, ctx->land, ctx->prm, ctx->work, ctx->d_c);
@@ -1494,10 +1522,18 @@ extern "C" int gnx_density_eval(gnx_ctx* ctx) {
   return GNX_OK;
 }
 
+extern "C" int gnx_density_eval(gnx_ctx* ctx) {
+  ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
+  int r = density_eval_N(ctx);
+  if (r != GNX_OK) return r;
+  return density_eval_d(ctx);
+}
+
 static int death_prob(gnx_ctx* ctx, int end_step) {
   PROF(ctx, "k_death");
   k_death<<<grid_cap(ctx, GNX_G_DEATH, 256, 1.0 + ctx->cfg.b * ctx->cfg.n_births_lambda), 256, 0, ctx->stream>>>(
-      ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c, ctx->mut, end_step);
+      ctx->pop, ctx->land, ctx->prm, ctx->traits, ctx->draws, ctx->work, ctx->d_c, ctx->mut, end_step, ctx->d_strip);
   LAUNCHED(ctx);
   return GNX_OK;
 }
@@ -1644,6 +1680,7 @@ static int capture_step(gnx_ctx* ctx) {
 extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
   ARG(ctx && n_steps >= 0, "n_steps");
   USE_DEVICE(ctx);
+  if (ctx->d_strip) { g_last_error = "this context holds one strip of a decomposed landscape: drive it with gnx_strip_phase"; return GNX_ERR_STATE; }
   if (ctx->records_pending + n_steps > ctx->work.max_records) {
     // never drop a step record: the caller drains them (gnx_read_step_records) at least every
     // max_records steps; nothing has been launched when this is returned
@@ -1681,6 +1718,225 @@ extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
     ctx->order_valid = false;
   }
   return GNX_OK;
+}
+
+// ---- strip domain decomposition of one landscape (gnx_strip.cuh) -------
+static int strip_upload(gnx_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->d_strip, &ctx->strip_h, sizeof(Strip), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GNX_OK;
+}
+
+extern "C" int gnx_strip_enable(gnx_ctx* ctx, const gnx_strip_config_t* sc) {
+  ARG(ctx && sc && sc->first_rows, "null");
+  USE_DEVICE(ctx);
+  ARG(!ctx->d_strip, "strip decomposition is already enabled for this context");
+  ARG(sc->world >= 1 && sc->world <= GNX_STRIP_MAX_WORLD && sc->rank >= 0 && sc->rank < sc->world, "rank / world");
+  ARG(ctx->cfg.mating_radius > 0, "strip decomposition needs a mating radius (panmixia has no locality)");
+  ARG(ctx->cfg.n_births_fixed, "strip decomposition supports n_births_fixed only");
+  ARG(!ctx->tsk.enabled && !ctx->mut.enabled, "strip decomposition does not carry tskit rows or mutation");
+  Strip& S = ctx->strip_h;
+  memset(&S, 0, sizeof S);
+  S.enabled = 1;
+  S.rank = sc->rank;
+  S.world = sc->world;
+  for (int r = 0; r <= sc->world; ++r) S.bounds[r] = sc->first_rows[r];
+  ARG(S.bounds[0] == 0 && S.bounds[sc->world] == ctx->land.ncy, "first_rows must span the mating grid [0, ncy]");
+  for (int r = 0; r < sc->world; ++r) ARG(S.bounds[r + 1] - S.bounds[r] >= 2, "every strip needs at least two mating-grid rows");
+  S.row0 = S.bounds[S.rank];
+  S.row1 = S.bounds[S.rank + 1];
+  // landscape rows that contain the strip's individuals: y in [row0, row1) * cell_size
+  S.ly0 = std::max(0, (int)std::floor(S.row0 * ctx->land.cell_size));
+  S.ly1 = S.rank == S.world - 1 ? ctx->cfg.dim_y
+                                : std::min(ctx->cfg.dim_y, (int)std::floor(S.row1 * ctx->land.cell_size) + 1);
+  S.rec_bytes = strip_header_bytes(ctx->cfg.n_traits) + 32 * ctx->Wq;
+  S.cap[STRIP_BUF_MIGRANTS] = (int32_t)std::max<int64_t>(1024, sc->migrant_capacity);
+  S.cap[STRIP_BUF_HALO] = (int32_t)std::max<int64_t>(1024, sc->halo_capacity);
+  S.cap[STRIP_BUF_NEWBORNS] = (int32_t)std::max<int64_t>(1024, sc->migrant_capacity);
+  S.cap[STRIP_BUF_CHOICES] = (int32_t)std::max<int64_t>(1024, sc->halo_capacity);
+  // one block: 256 bytes of counters, then the four receive buffers (a single CUDA IPC handle exports it)
+  size_t off = 256;
+  for (int k = 0; k < STRIP_N_BUF; ++k) {
+    ctx->strip_buf_off[k] = (int64_t)off;
+    const size_t rec = k == STRIP_BUF_CHOICES ? sizeof(StripChoice) : (size_t)S.rec_bytes;
+    off += ((size_t)S.cap[k] * rec + 255) & ~(size_t)255;
+  }
+  ctx->strip_block_bytes = off;
+  CK(cudaMalloc((void**)&ctx->strip_block, off));
+  CK(cudaMemsetAsync(ctx->strip_block, 0, 256, ctx->stream));
+  for (int k = 0; k < STRIP_N_BUF; ++k) {
+    S.peer[S.rank].buf[k] = ctx->strip_block + ctx->strip_buf_off[k];
+    S.peer[S.rank].count[k] = reinterpret_cast<int32_t*>(ctx->strip_block) + 16 * k;
+  }
+  S.list_cap = S.cap[STRIP_BUF_MIGRANTS] + 2 * S.cap[STRIP_BUF_HALO];
+  DM(ctx, &S.list_entry, (size_t)S.list_cap, &ctx->strip_allocs);
+  DM(ctx, &S.list_dest, (size_t)S.list_cap, &ctx->strip_allocs);
+  DM(ctx, &S.list_n, 4, &ctx->strip_allocs);
+  S.err = S.list_n + 1;
+  DM(ctx, &S.sent, (size_t)ctx->pop.cap, &ctx->strip_allocs);
+  DM(ctx, &S.births, GNX_STRIP_MAX_WORLD, &ctx->strip_allocs);
+  DM(ctx, &ctx->d_strip, 1, &ctx->strip_allocs);
+  drop_graph(ctx);
+  return strip_upload(ctx);
+}
+
+extern "C" int gnx_strip_endpoints(gnx_ctx* ctx, gnx_strip_endpoints_t* out) {
+  ARG(ctx && out && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  memset(out, 0, sizeof *out);
+  out->base = ctx->strip_block;
+  out->bytes = (int64_t)ctx->strip_block_bytes;
+  for (int k = 0; k < STRIP_N_BUF; ++k) {
+    out->buf_offset[k] = ctx->strip_buf_off[k];
+    out->count_offset[k] = 64 * k;
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->strip_block));
+  static_assert(sizeof(h) == sizeof(out->ipc_handle), "CUDA IPC handle is 64 bytes");
+  memcpy(out->ipc_handle, &h, sizeof h);
+  return GNX_OK;
+}
+
+extern "C" int gnx_strip_connect(gnx_ctx* ctx, int32_t peer_rank, const gnx_strip_endpoints_t* ep, int32_t same_process) {
+  ARG(ctx && ep && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  Strip& S = ctx->strip_h;
+  ARG(peer_rank >= 0 && peer_rank < S.world && peer_rank != S.rank, "peer_rank");
+  unsigned char* base = static_cast<unsigned char*>(ep->base);
+  if (!same_process) {
+    // another process on this node: map its block (NVLink peer memory) through CUDA IPC
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ep->ipc_handle, sizeof h);
+    void* mapped = nullptr;
+    CK(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->strip_ipc_opened.push_back(mapped);
+    base = static_cast<unsigned char*>(mapped);
+  }
+  for (int k = 0; k < STRIP_N_BUF; ++k) {
+    S.peer[peer_rank].buf[k] = base + ep->buf_offset[k];
+    S.peer[peer_rank].count[k] = reinterpret_cast<int32_t*>(base + ep->count_offset[k]);
+  }
+  return strip_upload(ctx);
+}
+
+extern "C" int gnx_strip_collective_ptrs(gnx_ctx* ctx, void** births, void** counts, int64_t* n_counts, void** nmax) {
+  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
+  if (births) *births = ctx->strip_h.births;
+  if (counts) *counts = ctx->dens.counts;
+  if (n_counts) *n_counts = 2 * (int64_t)ctx->dens.npts;
+  if (nmax) *nmax = &ctx->d_c->nmax_bits;
+  return GNX_OK;
+}
+
+static int strip_send(gnx_ctx* ctx, int which) {
+  PROF(ctx, "k_strip_send");
+  k_strip_send<<<grid_for(ctx, 2), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, ctx->d_strip, which, ctx->burn ? 0 : 1);
+  LAUNCHED(ctx);
+  k_strip_list_reset<<<1, 1, 0, ctx->stream>>>(ctx->d_strip);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+static int strip_recv(gnx_ctx* ctx, int which, int mode) {
+  PROF(ctx, "k_strip_recv");
+  k_strip_recv<<<grid_for(ctx, 2), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c, ctx->d_strip, which,
+                                                        mode, ctx->burn ? 0 : 1);
+  LAUNCHED(ctx);
+  k_strip_recv_finish<<<1, 1, 0, ctx->stream>>>(ctx->d_c, ctx->d_strip, which, mode, ctx->burn ? 0 : 1);
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+// One time step in eight phases; between two phases EVERY rank must have finished the earlier
+// one (the caller enqueues a stream-ordered collective -- or, with all ranks in one process,
+// runs the phase on every context first):
+//   0 move, list and send the leavers                          | barrier
+//   1 receive migrants; list and send the halo                 | barrier
+//   2 receive ghosts; re-grid; mate search; send edge choices  | barrier
+//   3 receive choices; pair list; publish the births           | all-gather of `births`
+//   4 id base; offspring; route and send dispersed newborns    | barrier
+//   5 receive newborns; density counts                         | all-reduce (sum) of `counts`
+//   6 N raster over the strip's rows                           | all-reduce (max) of `nmax`
+//   7 d raster; death probabilities and mortality draw; end of step
+extern "C" int gnx_strip_phase(gnx_ctx* ctx, int32_t phase) {
+  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  ARG(!ctx->prm.ordered, "injected per-individual draws are not supported under strip decomposition");
+  cudaStream_t s = ctx->stream;
+  int r;
+  switch (phase) {
+    case 0:
+      if (ctx->records_pending + 1 > ctx->work.max_records) {
+        g_last_error = "step-record buffer would overflow: call gnx_read_step_records first";
+        return GNX_ERR_STATE;
+      }
+      if ((r = move_key(ctx, 0, ctx->cfg.move ? 1 : 0, 1))) return r;
+      return strip_send(ctx, STRIP_BUF_MIGRANTS);
+    case 1:
+      if ((r = strip_recv(ctx, STRIP_BUF_MIGRANTS, 0))) return r;
+      PROF(ctx, "k_strip_halo_list");
+      k_strip_halo_list<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->work, ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      return strip_send(ctx, STRIP_BUF_HALO);
+    case 2:
+      if ((r = strip_recv(ctx, STRIP_BUF_HALO, 0))) return r;
+      if ((r = finish_regrid(ctx, 1))) return r;
+      if ((r = find_mates(ctx))) return r;
+      PROF(ctx, "k_strip_choice_send");
+      k_strip_choice_send<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, ctx->work, ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      return GNX_OK;
+    case 3:
+      PROF(ctx, "k_strip_choice_recv");
+      k_strip_choice_recv<<<grid_for(ctx, 2), 256, 0, s>>>(ctx->pop, ctx->land, ctx->work, ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      k_strip_choice_finish<<<1, 1, 0, s>>>(ctx->d_strip);
+      LAUNCHED(ctx);
+      if ((r = gnx_dedup_pairs(ctx))) return r;
+      k_strip_publish_births<<<1, 1, 0, s>>>(ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      return GNX_OK;
+    case 4:
+      k_strip_id_base<<<1, 1, 0, s>>>(ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      if ((r = gnx_make_offspring(ctx))) return r;
+      PROF(ctx, "k_strip_newborn_route");
+      k_strip_newborn_route<<<grid_for(ctx, 4), 256, 0, s>>>(ctx->pop, ctx->land, ctx->d_c, ctx->d_strip);
+      LAUNCHED(ctx);
+      return strip_send(ctx, STRIP_BUF_NEWBORNS);
+    case 5:
+      if ((r = strip_recv(ctx, STRIP_BUF_NEWBORNS, 1))) return r;
+      return gnx_density_counts(ctx);
+    case 6:
+      return density_eval_N(ctx);
+    case 7:
+      if ((r = density_eval_d(ctx))) return r;
+      if ((r = death_prob(ctx, 1))) return r;
+      k_strip_end_step<<<1, 1, 0, s>>>(ctx->d_c);
+      LAUNCHED(ctx);
+      ctx->records_pending += 1;
+      ctx->steps_done += 1;
+      ctx->pending = true;
+      ctx->order_valid = false;
+      return GNX_OK;
+    default:
+      ARG(false, "phase must be 0..7");
+  }
+  return GNX_OK;
+}
+
+// sticky overflow flags of the exchange (list or a receive buffer too small); synchronises
+extern "C" int gnx_strip_check(gnx_ctx* ctx) {
+  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  int32_t e = 0;
+  CK(cudaMemcpyAsync(&e, ctx->strip_h.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (e) {
+    g_last_error = (e & 2) ? "strip exchange: a receive buffer overflowed (raise migrant_capacity / halo_capacity)"
+                           : "strip exchange: the send list overflowed";
+    return GNX_ERR_CAPACITY;
+  }
+  return gnx_sync(ctx);
 }
 
 extern "C" int gnx_sync(gnx_ctx* ctx) {

@@ -46,6 +46,13 @@ struct Counters {
   // crowded mating cells handed from k_find_mates to k_find_mates_dense (zeroed before every search)
   int32_t n_heavy;      // cells appended to Work.heavy
   int32_t heavy_next;   // work-stealing cursor of k_find_mates_dense
+  // strip domain decomposition (gnx_strip.cuh): the entries [own_lo, own_hi) of the grid-ordered
+  // half belong to this rank, the rest are ghosts of the neighbouring strips (whole range when
+  // the landscape is not decomposed)
+  int32_t own_lo, own_hi;
+  int32_t tail_sent;    // newborns of this step shipped to the strip they dispersed into
+  int32_t pad3;
+  int64_t max_idx_global;   // species-wide max_ind_idx while Counters.max_idx carries this rank's id base
 };
 #define GNX_ERRBIT_CAPACITY 1
 #define GNX_ERRBIT_DRAWS 2
@@ -194,6 +201,37 @@ struct Tsk {
   double* b_y;
   double* b_z;             // [T][born_cap]
   double* b_time;          // nodes-table time = -t
+};
+
+// Strip domain decomposition of one landscape over several GPUs: this
+// rank owns the individuals whose mating-grid row lies in [row0, row1).  Individuals that leave
+// are written straight into the owner's receive buffer over NVLink peer memory (or, when the
+// ranks are emulated as contexts of one process, the other context's buffer), a slot claimed
+// with a system-scope atomic; a stream-ordered collective between the phases is the barrier.
+#define GNX_STRIP_MAX_WORLD 16
+enum { STRIP_BUF_MIGRANTS = 0, STRIP_BUF_HALO = 1, STRIP_BUF_NEWBORNS = 2, STRIP_BUF_CHOICES = 3, STRIP_N_BUF = 4 };
+struct StripPeer {
+  unsigned char* buf[STRIP_N_BUF];   // receive buffers of that rank
+  int32_t* count[STRIP_N_BUF];       // records claimed in each
+};
+struct Strip {
+  int32_t enabled;
+  int32_t rank, world;
+  int32_t row0, row1;                // mating-grid rows owned
+  int32_t ly0, ly1;                  // landscape rows that cover the strip
+  int32_t bounds[GNX_STRIP_MAX_WORLD + 1];   // first mating-grid row of every rank; bounds[world] = ncy
+  int32_t rec_bytes;                 // bytes per individual record (header + genome row)
+  int32_t cap[STRIP_N_BUF];          // record capacity of each receive buffer
+  StripPeer peer[GNX_STRIP_MAX_WORLD];       // peer[rank] = this rank's own buffers
+  uint8_t* sent;                     // [cap] tail entries shipped away this step
+  int64_t* births;                   // [world] births of every rank this step (all-gathered)
+  // individuals to ship, listed by the kernel that finds them (k_move_key: leavers; k_strip_halo_list:
+  // the strip's edge rows; k_strip_newborn_route: newborns that dispersed out), sent by k_strip_send
+  int32_t* list_entry;
+  int32_t* list_dest;
+  int32_t* list_n;                   // [1]
+  int32_t list_cap;
+  int32_t* err;                      // [1] sticky: a receive buffer or the list overflowed
 };
 
 struct DevDraws {

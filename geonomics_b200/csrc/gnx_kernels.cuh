@@ -146,6 +146,8 @@ __device__ __forceinline__ uint32_t cell_linear(const Land& land, uint32_t packe
   return (packed >> 16) * (uint32_t)land.ncx + (packed & 0xffffu);
 }
 
+#include "gnx_strip.cuh"
+
 // ========================================================================================
 // a1 + a2 + a4 (+ a16 removal): age, movement, mating-grid key + per-cell histogram; entries the
 // previous step's mortality flagged dead are dropped here (their genome rows go back to the
@@ -156,7 +158,7 @@ __device__ __forceinline__ uint32_t cell_linear(const Land& land, uint32_t packe
 // ========================================================================================
 __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm, DevDraws dr,
                                                    Work w, Counters* c, int do_age, int do_move,
-                                                   int do_key) {
+                                                   int do_key, const Strip* st) {
   const int n = c->n, cur = c->cur, pending = c->pending;
   const int64_t t = c->t;
   double2* __restrict__ XY = pop.xy[cur];
@@ -218,6 +220,18 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
     }
     if (do_key) {
       const uint32_t key = mating_cell(land, x, y);
+      if (st) {
+        // strip decomposition: an individual that moved out of this rank's rows is listed for
+        // shipping to the rank that owns its new row and leaves this rank's grid (and gives
+        // its genome slot back; the row is read by k_strip_send before any slot is re-used)
+        const int row = (int)(key >> 16);
+        if (row < st->row0 || row >= st->row1) {
+          strip_list(st, p, strip_owner(st, row));
+          w.mkey[p] = GNX_KEY_DEAD;
+          if (!prm.burn) pop.free_slots[atomicAdd(&c->n_free, 1)] = pop.gslot[cur][p];
+          continue;
+        }
+      }
       w.mkey[p] = key;
       w.mrank[p] = atomicAdd(&w.cell_count[cell_linear(land, key)], 1u);
     }
@@ -254,7 +268,8 @@ __global__ void __launch_bounds__(256) k_bucket(Pop pop, Land land, Work w, cons
 // among the ids of its cell -- (cell, id) order whatever order the histogram atomics retired
 // in -- and gathers that entry's whole record into the other half.  One pass moves the state:
 // it is this step's counting sort AND the previous step's mortality compaction.
-__global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Counters* c, int age_inc, int ordered) {
+__global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Counters* c, int age_inc, int ordered,
+                                                 const Strip* st) {
   const int total = c->n_regrid, s = c->cur, d = s ^ 1, T = pop.T;
   for (int q = GTID; q < total; q += GSTRIDE) {
     const uint4 e = w.bucket[q];
@@ -305,6 +320,9 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
     c->pending = 0;
     c->cur = d;
     c->ticket[0] = 0u;
+    // entries this rank owns: its mating-grid rows are one contiguous range of the (cell, id) order
+    c->own_lo = st ? (int)w.cell_start[st->row0 * land.ncx] : 0;
+    c->own_hi = st ? (int)w.cell_start[st->row1 * land.ncx] : total;
   }
 }
 
@@ -354,7 +372,12 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
   const double r2 = prm.r2, radius = prm.c.mating_radius;
   const double2* __restrict__ sxy = pop.xy[cur];
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
+  const int own_lo = c->own_lo, own_hi = c->own_hi;
   for (int p = GTID; p < n; p += GSTRIDE) {
+    if (p < own_lo || p >= own_hi) {               // a ghost of a neighbouring strip: candidate, never focal
+      w.mate[p] = -1;
+      continue;
+    }
     const double2 f = sxy[p];
     const uint32_t key = w.skey[p];
     const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
@@ -742,6 +765,7 @@ struct PairScan {
   __device__ bool keep(int i) const {
     if (panmixia) return w.mate[i] >= 0;
     const int p = entry(i);
+    if (p < cc->own_lo || p >= cc->own_hi) return false;     // ghosts found their pairs on their own rank
     const int m = w.mate[p];
     if (m < 0) return false;
     if (sexed) {
@@ -1604,7 +1628,7 @@ __global__ void k_mutate(Pop pop, Params prm, Traits tr, DevDraws dr, Mut mu, Co
 // global atomics.
 // ========================================================================================
 #define DENS_SMEM_BINS 4096
-__global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const Counters* c, Dens d) {
+__global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const Counters* c, Dens d, const Strip* st) {
   // blockIdx.y = 0: all individuals alive before mortality; 1: pair midpoints
   const int which = blockIdx.y;
   const double2* __restrict__ pts = which == 0 ? pop.xy[c->cur] : w.mid;
@@ -1615,7 +1639,12 @@ __global__ void __launch_bounds__(512) k_density_counts(Pop pop, Work w, const C
   __syncthreads();
   const int n = which == 0 ? c->n + c->B : c->P;      // = n_pre once the birth bookkeeping has run
   int* gcounts = d.counts + (size_t)which * d.npts;
+  const int n0 = c->n, own_lo = c->own_lo, own_hi = c->own_hi;
   for (int i = GTID; i < n; i += GSTRIDE) {       // GTID / GSTRIDE use the x dimension only
+    if (st && which == 0) {
+      // strip decomposition: ghosts are counted by their owner, shipped newborns by their new owner
+      if (i < n0 ? (i < own_lo || i >= own_hi) : (st->sent[i] != 0)) continue;
+    }
     const double2 pt = pts[i];
     const double x = pt.x, y = pt.y;
     // Half-window index once per axis: with h = x // (ww/2), x // ww = h >> 1 and
@@ -1989,10 +2018,10 @@ __device__ __forceinline__ double ct_eval_point(const Dens& d, int which, double
 // N raster (Species._calc_density species.py:845-882, clip >= 0) + its maximum
 // (rows are dealt to CTAs, columns to threads: no integer division per cell, the lattice row
 // index is computed once per row)
-__global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Counters* c) {
+__global__ void __launch_bounds__(256) k_raster_N(Dens d, Land land, Work w, Counters* c, int row_lo, int row_hi) {
   double mx = 0.0;
   const double inv_hww = 1.0 / d.hww;
-  for (int i = blockIdx.x; i < land.Y; i += gridDim.x) {
+  for (int i = row_lo + blockIdx.x; i < row_hi; i += gridDim.x) {
    const int si = lattice_index(i + 0.5, d.hww, inv_hww, d.lat_ni - 2);
    for (int j = threadIdx.x; j < land.X; j += blockDim.x) {
     const int id = i * land.X + j;
@@ -2047,10 +2076,11 @@ __device__ __forceinline__ void raster_d_cell(const Land& land, const Params& pr
   if (prm.store_debug) w.d_rast[id] = dv;
 }
 
-__global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c) {
+__global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c, int row_lo,
+                                                   int row_hi) {
   const double Nmax = __longlong_as_double((long long)c->nmax_bits);
   const double inv_hww = 1.0 / d.hww;
-  for (int i = blockIdx.x; i < land.Y; i += gridDim.x) {
+  for (int i = row_lo + blockIdx.x; i < row_hi; i += gridDim.x) {
     const int si = lattice_index(i + 0.5, d.hww, inv_hww, d.lat_ni - 2);
     for (int j = threadIdx.x; j < land.X; j += blockDim.x)
       raster_d_cell(land, prm, w, i * land.X + j, ct_eval_point(d, 1, i + 0.5, j + 0.5, si, inv_hww), Nmax);
@@ -2080,12 +2110,19 @@ __global__ void __launch_bounds__(256) k_raster_d_fix(Dens d, Land land, Params 
 // the dead are only FLAGGED here -- the next step's re-grid drops them.
 // ========================================================================================
 __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
-                                                Counters* c, Mut mu, int end_step) {
+                                                Counters* c, Mut mu, int end_step, const Strip* st) {
   const int n0 = c->n, n = c->n + c->B, cur = c->cur, T = pop.T;
   const int64_t t = c->t;
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
+  const int own_lo = c->own_lo, own_hi = c->own_hi;
   int live = 0;
   for (int i = GTID; i < n; i += GSTRIDE) {
+    if (st && (i < n0 ? (i < own_lo || i >= own_hi) : (st->sent[i] != 0))) {
+      // a ghost of a neighbouring strip, or a newborn shipped to the strip it dispersed into:
+      // not this rank's individual -- the next re-grid drops the entry
+      w.alive[i] = 0;
+      continue;
+    }
     const double2 xy = pop.xy[cur][i];
     const double x = xy.x, y = xy.y;
     const int cx = (int)x, cy = (int)y;
@@ -2157,8 +2194,11 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
     gnx_step_record_t r;
     r.t = c->t;
     r.Nt = survivors;
-    r.n_births = c->B;
-    r.n_deaths = n - survivors;
+    // strip decomposition: this rank's share -- the newborns it holds and the deaths among the
+    // individuals it holds (the shares of all ranks sum to the species' counts)
+    const int held = st ? (own_hi - own_lo) + c->B - c->tail_sent : n;
+    r.n_births = st ? c->B - c->tail_sent : c->B;
+    r.n_deaths = held - survivors;
     r.n_pairs = c->P;
     if (c->n_rec < w.max_records) w.records[c->n_rec] = r;
     c->n_rec += 1;
@@ -2285,6 +2325,8 @@ __global__ void k_end_step(Counters* c, Work w, int burn, int record) {
   c->n_pre = survivors;
   c->n_alive = survivors;
   c->n_sorted = 0;               // entry order is kept, but cell_start no longer matches the entries
+  c->own_lo = 0;
+  c->own_hi = survivors;
   c->pending = 0;
   c->cur ^= 1;
   c->P = 0;
@@ -2494,6 +2536,7 @@ __global__ void __launch_bounds__(256) k_upload_finish(Pop pop, Counters* c, int
     c->max_idx = max_idx; c->err = 0; c->nmax_bits = 0ull;
     c->n_nodes = 2 * n; c->n_ind_rows = n; c->n_edges = 0; c->n_born = 0;
     c->n_sorted = 0; c->pending = 0; c->n_alive = n; c->alive_acc = 0; c->ticket[0] = c->ticket[1] = 0u;
+    c->own_lo = 0; c->own_hi = n; c->tail_sent = 0;
   }
 }
 

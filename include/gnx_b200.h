@@ -249,6 +249,40 @@ int gnx_set_life_history(gnx_ctx* ctx, const gnx_config_t* cfg);
  * density chain); the graph is re-captured when a setter changed any kernel argument.
  * GNX_NO_GRAPH=1 in the environment keeps plain stream launches. */
 int gnx_step(gnx_ctx* ctx, int32_t n_steps);
+/* ---- strip domain decomposition of one landscape over several GPUs ---
+ * What shards (reference file:line): the mate search species.py:2157-2215 / spatial.py:191-245
+ * (halo of the individuals within one mating-grid row of a strip edge, with their genome rows),
+ * movement movement.py:34-95 and natal dispersal movement.py:98-141 (migrants to the strip they
+ * land in), the density counts spatial.py:73-97 (summed over ranks), max(N) demography.py:104-119,
+ * offspring ids species.py:614-619 (based at the births of the lower ranks).  Records travel by
+ * direct writes into the receiver's buffer (NVLink peer memory through CUDA IPC, or plain device
+ * pointers when the ranks are contexts of one process); the caller supplies the barrier between
+ * phases (a stream-ordered collective) and the three small collectives named at gnx_strip_phase. */
+typedef struct {
+  int32_t rank, world;
+  const int32_t* first_rows;     /* [world + 1] first mating-grid row of every rank, first_rows[world] = rows of the grid */
+  int64_t migrant_capacity;      /* records a rank can receive per step as migrants (and as dispersed newborns) */
+  int64_t halo_capacity;         /* records a rank can receive per step as ghosts (and as edge mate choices) */
+} gnx_strip_config_t;
+typedef struct {
+  void* base;                    /* device address of the rank's receive block (valid in its own process) */
+  int64_t bytes;
+  int64_t buf_offset[4];         /* migrants, halo, newborns, choices */
+  int64_t count_offset[4];
+  unsigned char ipc_handle[64];  /* cudaIpcMemHandle_t of the block, for ranks in other processes */
+} gnx_strip_endpoints_t;
+int gnx_strip_enable(gnx_ctx* ctx, const gnx_strip_config_t* cfg);
+int gnx_strip_endpoints(gnx_ctx* ctx, gnx_strip_endpoints_t* out);
+int gnx_strip_connect(gnx_ctx* ctx, int32_t peer_rank, const gnx_strip_endpoints_t* peer, int32_t same_process);
+/* device buffers the caller's collectives act on: births int64[world] (all-gather after phase 3),
+ * counts int32[n_counts] (all-reduce sum after phase 5), nmax uint64[1] holding the bits of a
+ * non-negative double (all-reduce max after phase 6) */
+int gnx_strip_collective_ptrs(gnx_ctx* ctx, void** births, void** counts, int64_t* n_counts, void** nmax);
+/* one phase (0..7) of a time step on this rank's stream; every rank must have finished phase k
+ * before any rank starts phase k + 1 */
+int gnx_strip_phase(gnx_ctx* ctx, int32_t phase);
+int gnx_strip_check(gnx_ctx* ctx);      /* synchronises; exchange overflow -> GNX_ERR_CAPACITY */
+
 int gnx_sync(gnx_ctx* ctx);
 /* Same, with HOST buffers in and out: upload pop, run n_steps, download into pop (synchronous). */
 int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps);

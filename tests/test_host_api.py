@@ -48,7 +48,8 @@ def test_ctypes_structs_match_header_field_order():
         return names
     for cname, cls in (('gnx_config_t', _lib.Config), ('gnx_trait_t', _lib.Trait), ('gnx_density_t', _lib.Density),
                        ('gnx_draws_t', _lib.Draws), ('gnx_population_t', _lib.Population),
-                       ('gnx_step_record_t', _lib.StepRecord)):
+                       ('gnx_step_record_t', _lib.StepRecord), ('gnx_strip_config_t', _lib.StripConfig),
+                       ('gnx_strip_endpoints_t', _lib.StripEndpoints)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
 
 
