@@ -443,6 +443,60 @@ def steady_state_block(name, presteps, steps, prof_steps):
     return out
 
 
+def strips_block(dist, rank, world, name, presteps, steps):
+    """The north_star target config as ONE landscape strip-decomposed over the ranks (SURVEY.md
+    section 8e-2): strong scaling -- the total work is fixed, every rank owns a band of rows.
+    Records cross the strip edges by direct writes into the neighbour's buffer over NVLink peer
+    memory; NCCL supplies the barriers and three small collectives (geonomics_b200/strips.py)."""
+    import torch
+    from geonomics_b200 import workloads, strips
+    cfg = dict(workloads.CONFIGS[name])
+    w = workloads.build(cfg, cfg['seed'])                      # every rank builds the same landscape / population
+    N0, L = cfg['N'], w['L']
+    cs, ncx, ncy = strips.mating_grid(w['land_dim'], w['prm']['mating_radius'])
+    cap = int(2.0 * N0 / world) + 65536
+    st = strips.NcclStrips(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=cap, seed=cfg['seed'],
+                           migrant_capacity=max(65536, cap // 8), halo_capacity=max(65536, cap // 4))
+    own = strips.owner_of(w['pop']['y'], st.bounds, st.cs, st.ncy) == rank
+    n_own = int(own.sum())
+    p = w['pop']
+    st.dev.upload(p['x'][own], p['y'][own], p['age'][own], p['sex'][own], p['idx'][own],
+                  genomes_packed=workloads.random_packed_genomes(n_own, L, cfg['seed'] + 1 + rank), max_ind_idx=N0 - 1)
+    del w
+    done = 0
+    while done < presteps:
+        c = min(50, presteps - done)
+        st.step(c)
+        st.sync()
+        st.step_records_local()
+        done += c
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st.stream)
+    st.step(steps)
+    e1.record(st.stream)
+    st.sync()
+    dist.barrier()
+    ms = e0.elapsed_time(e1)
+    recs = st.step_records_local()
+    ind = float(sum(r['Nt'] - r['n_births'] + r['n_deaths'] for r in recs))
+    held = float(recs[-1]['Nt'])
+    t = torch.tensor([ms, ind, held], device='cuda', dtype=torch.float64)
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    st.close()
+    ms_all, ind_all = float(tmax[0]), float(tsum[1])
+    return {'workload': name + ': ' + workload_desc(cfg), 'scaling': 'strong', 'n_gpus': world,
+            'decomposition': '%d horizontal strips of mating-grid rows (cut by carrying capacity), halo = one mating-grid '
+                             'row, records by peer writes over NVLink (CUDA IPC), NCCL barriers + 3 small collectives '
+                             'per step' % world,
+            'simulated_steps_before_timing': presteps, 'steps': steps, 'ms_per_step': ms_all / steps,
+            'value': ind_all / (ms_all * 1e-3), 'unit': UNIT,
+            'load_imbalance_max_over_mean': float(tmax[2]) / (float(tsum[2]) / world)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -463,6 +517,9 @@ def main():
                     help='the default line carries a c4 block (north_star target config) measured after this '
                          'many simulated steps; 0 disables it')
     ap.add_argument('--c4-steps', type=int, default=100)
+    ap.add_argument('--no-strips', action='store_true',
+                    help='with N > 1 ranks the default line also carries c4 strip-decomposed over the N GPUs '
+                         '(strong scaling); this switches it off')
     ap.add_argument('--replicates', type=int, default=None,
                     help='replicate populations per GPU, stepped concurrently on their own streams '
                          '(default 8 for c3 = BASELINE configs[2]: 64 replicates on 8 GPUs; 1 otherwise)')
@@ -649,6 +706,14 @@ def main():
         # the north_star target config on one GPU, at steady state
         c4 = steady_state_block('c4', args.c4_presteps, args.c4_steps, min(50, args.c4_steps))
 
+    c4_strips = None
+    if (world > 1 and args.workload == 'c2' and args.scale == 1.0 and args.c4_presteps > 0 and args.presteps == 0
+            and not args.no_strips):
+        try:
+            c4_strips = strips_block(dist, rank, world, 'c4', args.c4_presteps, args.c4_steps)
+        except Exception as e:                          # e.g. no peer access between the GPUs of this box
+            c4_strips = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:300])}
+
     if rank == 0:
         footprint_mb = (N0 * (2 * (8 + 8 + 4 + 1 + 8 + 4 + 8 * T + 8) + 8 * dev.W + 60) + 8 * YX * 6) / 1e6
         line = {
@@ -670,6 +735,8 @@ def main():
         }
         if c4 is not None:
             line['c4'] = c4
+        if c4_strips is not None:
+            line['c4_strips'] = c4_strips
         print(json.dumps(line))
     for d in devs:
         d.close()

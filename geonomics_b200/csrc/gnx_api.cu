@@ -230,6 +230,35 @@ extern "C" int gnx_create(const gnx_config_t* cfg, gnx_ctx** out) {
   return GNX_OK;
 }
 
+// Quantile table of |theta|, theta ~ von Mises(0, kappa): the half-distribution's inverse CDF at
+// u = k / VM_TAB_CELLS (k = 0..VM_TAB_CELLS), then the last cell again at VM_TAB_FINE sub-cells.
+// pdf ~ exp(kappa (cos t - 1)) integrated by the trapezoid rule on 2^20 points in double.
+static void build_vm_table(double kappa, std::vector<float>* out) {
+  const int n = 1 << 20;
+  std::vector<double> cdf(n + 1);
+  const double h = M_PI / n;
+  double acc = 0.0, prev = 1.0;
+  cdf[0] = 0.0;
+  for (int i = 1; i <= n; ++i) {
+    const double f = std::exp(kappa * (std::cos(i * h) - 1.0));
+    acc += 0.5 * (prev + f) * h;
+    prev = f;
+    cdf[i] = acc;
+  }
+  for (int i = 0; i <= n; ++i) cdf[i] /= acc;
+  auto quantile = [&](double u) {
+    if (u <= 0.0) return 0.0;
+    if (u >= 1.0) return M_PI;
+    const int i = (int)(std::upper_bound(cdf.begin(), cdf.end(), u) - cdf.begin());      // cdf[i-1] <= u < cdf[i]
+    const double c0 = cdf[i - 1], c1 = cdf[i];
+    return ((i - 1) + (c1 > c0 ? (u - c0) / (c1 - c0) : 0.0)) * h;
+  };
+  out->resize(VM_TAB_LEN);
+  for (int k = 0; k <= VM_TAB_CELLS; ++k) (*out)[k] = (float)quantile((double)k / VM_TAB_CELLS);
+  for (int k = 0; k <= VM_TAB_FINE; ++k)
+    (*out)[VM_TAB_CELLS + 1 + k] = (float)quantile(1.0 - (1.0 - (double)k / VM_TAB_FINE) / VM_TAB_CELLS);
+}
+
 static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   CK(cudaGetDevice(&ctx->device));
   cudaDeviceProp prop;
@@ -373,6 +402,22 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->d_cs_tab, tab.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     pr.cs_tab = ctx->d_cs_tab;
+  }
+  {
+    const int mode[2] = {cfg->move ? cfg->move_surf_mode : GNX_SURF_NONE, cfg->disp_surf_mode};
+    const double kappa[2] = {cfg->move_surf_kappa, cfg->disp_surf_kappa};
+    pr.vm_tab[0] = pr.vm_tab[1] = nullptr;
+    for (int k = 0; k < 2; ++k) {
+      if (mode[k] != GNX_SURF_ONTHEFLY) continue;
+      if (k == 1 && pr.vm_tab[0] && kappa[0] == kappa[1]) { pr.vm_tab[1] = pr.vm_tab[0]; continue; }
+      std::vector<float> tab;
+      build_vm_table(kappa[k], &tab);
+      float* d = nullptr;
+      DM(ctx, &d, tab.size());
+      CK(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      pr.vm_tab[k] = d;
+    }
   }
   memset(&ctx->draws, 0, sizeof ctx->draws);
   ctx->draws.disp_R = std::max(1, cfg->disp_max_tries_injected);

@@ -293,6 +293,8 @@ struct Params {
   int32_t store_debug;   // keep n_nbrs / death_p / NP_rast for parity tests
   int32_t ordered;       // per-individual injected draws are indexed by species-order ordinal (pop.ord),
                          // and the pair list is built in ascending focal ordinal (the oracle's canonical order)
+  const float* vm_tab[2];  // inverse-CDF tables of von Mises(0, kappa) for the on-the-fly movement / dispersal
+                           // surfaces (vonmises_tab in gnx_kernels.cuh), NULL when unused
   const uint32_t* cs_tab;  // [65536] (half cos | half sin << 16) of every float16 direction: numpy's portable
                            // float16 cos/sin (movement.py:75-76 on a float16 direction), built at setup
 };

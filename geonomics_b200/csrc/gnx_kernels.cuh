@@ -46,28 +46,38 @@ __device__ __forceinline__ double sample_distance_f32(RngStream& g, int distr, d
   }
 }
 
-// s of numpy's legacy_vonmises (Best & Fisher): depends on kappa only, computed once per thread
-__device__ __forceinline__ float vonmises_s_f32(float kappa) {
-  if (kappa < 1e-8f) return 0.0f;
-  const float r = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
-  const float rho = (r - sqrtf(2.0f * r)) / (2.0f * kappa);
-  return (1.0f + rho * rho) / (2.0f * rho);
-}
-
-__device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa, float s) {
-  // numpy legacy_vonmises (Best & Fisher), single precision
+// von Mises(0, kappa) for the on-the-fly conductance surfaces: kappa is one number per species and
+// the sample is about to be quantised to float16, so it is drawn by INVERSE CDF from a table built
+// at setup (gnx_api.cu build_vm_table) instead of numpy's Best & Fisher rejection loop (cospif,
+// division, logf, acosf and 2-3 uniforms per trip, ~1.5 trips, the trips of a warp's 32 lanes
+// serialised).  One 32-bit word: sign | 12-bit cell | 19-bit position in the cell, linear
+// inside a cell.  The last cell of the half-distribution -- where the quantile function turns
+// steep -- is resolved by a second 256-cell table, so what is left to linear interpolation of
+// the far tail is 2^-20 of the mass: the total-variation distance from the exact distribution
+// is below 1e-6, two orders under what a KS test on 10^6 draws resolves
+// (tests/test_cuda_surface_onthefly.py checks the sampler against the reference's tables).
+#define VM_TAB_CELLS 4096
+#define VM_TAB_FINE 256
+#define VM_TAB_LEN (VM_TAB_CELLS + 1 + VM_TAB_FINE + 1)
+__device__ __forceinline__ float vonmises_tab(RngStream& g, const float* __restrict__ tab, float kappa) {
   const float PI_F = 3.14159265358979f;
-  if (kappa < 1e-8f) return PI_F * (2.0f * uniform_f32(g) - 1.0f);
-  float W = 1.0f;
-  for (int it = 0; it < 64; ++it) {
-    const float Z = cospif(uniform_f32(g));
-    W = (1.0f + s * Z) / (s + Z);
-    const float Y = kappa * (s - W);
-    const float V = fmaxf(uniform_f32(g), 1e-30f);
-    if ((Y * (2.0f - Y) - V >= 0.0f) || (__logf(Y / V) + 1.0f - Y >= 0.0f)) break;
+  if (kappa < 1e-8f) return PI_F * (2.0f * uniform_f32(g) - 1.0f);     // numpy: uniform on the circle
+  const uint32_t r = g.u32();
+  const uint32_t v = r << 1;                          // 31 random bits, left-aligned
+  uint32_t k = v >> 20;                               // 12 bits: cell
+  float a, b, f;
+  if (k < VM_TAB_CELLS - 1) {
+    f = (float)((v >> 1) & 0x7ffffu) * (1.0f / 524288.0f);
+    a = __ldg(&tab[k]);
+    b = __ldg(&tab[k + 1]);
+  } else {
+    const uint32_t k2 = (v >> 12) & 0xffu;            // 8 bits: fine cell inside the last cell
+    f = (float)((v >> 1) & 0x7ffu) * (1.0f / 2048.0f);
+    a = __ldg(&tab[VM_TAB_CELLS + 1 + k2]);
+    b = __ldg(&tab[VM_TAB_CELLS + 2 + k2]);
   }
-  float res = acosf(fminf(fmaxf(W, -1.0f), 1.0f));
-  return (uniform_f32(g) < 0.5f) ? -res : res;
+  const float res = fmaf(f, b - a, a);
+  return (r >> 31) ? -res : res;
 }
 
 // On-the-fly conductance-surface direction.  The reference pre-draws `approx_len` float16
@@ -75,7 +85,7 @@ __device__ __forceinline__ float vonmises_f32(RngStream& g, float kappa, float s
 // would be 168 GB, so the sample is drawn here instead.  `nv` = the 8 queen neighbours of the
 // zero-embedded raster in row-major order (focal dropped), however they were fetched.
 __device__ __forceinline__ __half surface_direction_from_neigh(RngStream& g, const float* nv, int mixture,
-                                                               float kappa, float vm_s) {
+                                                               float kappa, const float* __restrict__ vm_tab) {
   const float PI_F = 3.14159265358979f;
   const float dirs[8] = {-3 * PI_F / 4, -PI_F / 2, -PI_F / 4, PI_F, 0.0f, 3 * PI_F / 4, PI_F / 2, PI_F / 4};
   float sum = 0.0f, mx = -1.0f;
@@ -105,7 +115,7 @@ __device__ __forceinline__ __half surface_direction_from_neigh(RngStream& g, con
   // scipy vonmises.rvs(kappa, loc) = mod(loc + vonmises(0, kappa) + pi, 2 pi) - pi (scipy >= 1.11
   // wraps onto [-pi, pi); that is the scipy the reference runs on here), stored as float16 like
   // the reference table (spatial.py:447)
-  float v = loc + vonmises_f32(g, kappa, vm_s);
+  float v = loc + vonmises_tab(g, vm_tab, kappa);
   if (v >= PI_F) v -= 2.0f * PI_F;
   else if (v < -PI_F) v += 2.0f * PI_F;
   return __float2half_rn(v);
@@ -113,7 +123,7 @@ __device__ __forceinline__ __half surface_direction_from_neigh(RngStream& g, con
 
 __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const float* rast, int X, int Y,
                                                              int cx, int cy, int mixture, float kappa,
-                                                             float vm_s) {
+                                                             const float* __restrict__ vm_tab) {
   // spatial.py:432-461: 3x3 neighbourhood of the zero-embedded raster, focal cell dropped
   const int di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
   const int dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
@@ -123,7 +133,7 @@ __device__ __forceinline__ __half surface_direction_onthefly(RngStream& g, const
     const int i = cy + di[k], j = cx + dj[k];
     nv[k] = (i >= 0 && i < Y && j >= 0 && j < X) ? __ldg(&rast[(size_t)i * X + j]) : 0.0f;
   }
-  return surface_direction_from_neigh(g, nv, mixture, kappa, vm_s);
+  return surface_direction_from_neigh(g, nv, mixture, kappa, vm_tab);
 }
 
 // cos / sin of a float16 direction exactly as numpy evaluates them on a float16 array (half ->
@@ -163,7 +173,6 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
   const int64_t t = c->t;
   double2* __restrict__ XY = pop.xy[cur];
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
-  const float vm_s = vonmises_s_f32((float)prm.c.move_surf_kappa);
   const int lane = threadIdx.x & 31;
   // whole warps stay in the loop (ballots below): the tail is masked by `live`
   for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
         sincos_half_tab(prm.cs_tab, h, &sn, &cs);
       } else if (prm.c.move_surf_mode == GNX_SURF_ONTHEFLY) {
         const __half d = surface_direction_onthefly(g, land.surf_f32[0], land.X, land.Y, (int)x, (int)y,
-                                                    prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa, vm_s);
+                                                    prm.c.move_surf_mixture, (float)prm.c.move_surf_kappa, prm.vm_tab[0]);
         sincos_half_tab(prm.cs_tab, d, &sn, &cs);
       } else if (dr.move_dir) {
         sincos(dr.move_dir[io], &sn, &cs);
@@ -1346,7 +1355,6 @@ __global__ void __launch_bounds__(GT_THREADS) k_gametes_tma(Pop pop, Params prm,
 __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                    Counters* c, Tsk tsk) {
   const int n = c->n, B = c->B, cur = c->cur;
-  const float vm_s = vonmises_s_f32((float)prm.c.disp_surf_kappa);
   const int n_nodes = c->n_nodes, n_born = c->n_born;
   const int64_t t = c->t, max_idx = c->max_idx;
   for (int o = GTID; o < B; o += GSTRIDE) {
@@ -1372,7 +1380,7 @@ __global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm
       } else if (prm.c.disp_surf_mode == GNX_SURF_ONTHEFLY) {
         const __half d = surface_direction_onthefly(
             g, land.surf_f32[1], land.X, land.Y, (int)mx,
-            (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa, vm_s);
+            (int)my, prm.c.disp_surf_mixture, (float)prm.c.disp_surf_kappa, prm.vm_tab[1]);
         sincos_half_tab(prm.cs_tab, d, &sn, &cs);
       } else if (dr.disp_dir) {
         sincos(dr.disp_dir[(size_t)o * dr.disp_R + tries], &sn, &cs);
