@@ -339,9 +339,9 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
     W.scratch = sc;
   }
   DM(ctx, &W.mate, cap);
-  // a cell is crowded when its 3x3 block holds >= GNX_FM_HEAVY_K entries; an entry lies in at most
-  // 9 blocks, so at most 9 n / GNX_FM_HEAVY_K non-empty cells are, and each contributes one work
-  // item per 32 focals (+ n / 32): below n / 4 in all
+  // a cell is crowded when focals x candidates of its 3x3 block reaches GNX_FM_HEAVY_WORK; it
+  // contributes one work item per 32 focals, so n / 32 items plus one per crowded cell (few
+  // hundred candidates are shared by the at most 9 cells around them): below n / 4 in all
   W.heavy_cap = (int32_t)(cap / 4 + 1024);
   DM(ctx, &W.heavy, (size_t)W.heavy_cap);
   DM(ctx, &W.n_nbrs, cap);
@@ -361,7 +361,11 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   DM(ctx, &W.NP_rast, plane);
   DM(ctx, &W.d_rast, plane);
   W.envd_stride = 1 + cfg->n_traits;
+#if GNX_ENVD_PLANAR
+  W.envd = nullptr;
+#else
   DM(ctx, &W.envd, plane * (size_t)W.envd_stride);
+#endif
   DM(ctx, &W.e_out, (size_t)cap * cfg->n_layers);
   DM(ctx, &W.fix_list, plane);
   DM(ctx, &W.fix_count, 1);
@@ -457,6 +461,9 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
 }
 
 static int pack_env(gnx_ctx* ctx) {
+#if GNX_ENVD_PLANAR
+  return GNX_OK;               // the death kernel reads the layers themselves
+#endif
   if (!ctx->have_traits || ctx->cfg.n_traits == 0 || !ctx->have_rasters) return GNX_OK;
   PROF(ctx, "k_pack_env");
   k_pack_env<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->land, ctx->traits, ctx->work, ctx->cfg.n_traits);

@@ -11,6 +11,9 @@
 #include "gnx_common.cuh"
 #include "gnx_scan.cuh"
 
+#ifndef GNX_ENVD_PLANAR
+#define GNX_ENVD_PLANAR 1      // 0: the round-1 packed [cell][d | e...] raster (A/B)
+#endif
 #define GTID (blockIdx.x * blockDim.x + threadIdx.x)
 #define GSTRIDE (gridDim.x * blockDim.x)
 
@@ -190,11 +193,16 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
       }
       if (dead) w.mkey[p] = GNX_KEY_DEAD;
     }
-    if (!in || dead) continue;
-    if (do_age) pop.age[cur][p] += 1;
-    const double2 xy0 = XY[p];
-    double x = xy0.x, y = xy0.y;
-    if (do_move) {
+    // no early exit: the whole warp takes part in the cell-count aggregation at the end
+    const bool act = in && !dead;
+    if (act && do_age) pop.age[cur][p] += 1;
+    double x = 0.0, y = 0.0;
+    if (act) {
+      const double2 xy0 = XY[p];
+      x = xy0.x;
+      y = xy0.y;
+    }
+    if (act && do_move) {
       const int io = ord ? ord[p] : p;                  // injected draws are indexed by species ordinal
       RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MOVE, t);
       double cs, sn;
@@ -228,21 +236,39 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
       XY[p] = make_double2(x, y);
     }
     if (do_key) {
-      const uint32_t key = mating_cell(land, x, y);
-      if (st) {
-        // strip decomposition: an individual that moved out of this rank's rows is listed for
-        // shipping to the rank that owns its new row and leaves this rank's grid (and gives
-        // its genome slot back; the row is read by k_strip_send before any slot is re-used)
-        const int row = (int)(key >> 16);
-        if (row < st->row0 || row >= st->row1) {
-          strip_list(st, p, strip_owner(st, row));
-          w.mkey[p] = GNX_KEY_DEAD;
-          if (!prm.burn) pop.free_slots[atomicAdd(&c->n_free, 1)] = pop.gslot[cur][p];
-          continue;
+      uint32_t key = 0u;
+      uint32_t lin = 0xffffffffu - (uint32_t)lane;       // a value no other lane and no cell has
+      bool keyed = false;
+      if (act) {
+        key = mating_cell(land, x, y);
+        keyed = true;
+        if (st) {
+          // strip decomposition: an individual that moved out of this rank's rows is listed for
+          // shipping to the rank that owns its new row and leaves this rank's grid (and gives
+          // its genome slot back; the row is read by k_strip_send before any slot is re-used)
+          const int row = (int)(key >> 16);
+          if (row < st->row0 || row >= st->row1) {
+            strip_list(st, p, strip_owner(st, row));
+            w.mkey[p] = GNX_KEY_DEAD;
+            if (!prm.burn) pop.free_slots[atomicAdd(&c->n_free, 1)] = pop.gslot[cur][p];
+            keyed = false;
+          }
         }
+        if (keyed) lin = cell_linear(land, key);
       }
-      w.mkey[p] = key;
-      w.mrank[p] = atomicAdd(&w.cell_count[cell_linear(land, key)], 1u);
+      // The entries are in last step's grid order and move about one cell, so the lanes of a warp
+      // land in few distinct cells: the lanes of one cell share ONE histogram atomic (their ranks
+      // follow by lane order; the re-grid orders by id anyway).  In crowded cells this removes
+      // most of the same-address traffic that the per-lane atomics queued up in L2.
+      const unsigned peers = __match_any_sync(0xffffffffu, lin);
+      if (keyed) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base_rank = 0u;
+        if (lane == leader) base_rank = atomicAdd(&w.cell_count[lin], (uint32_t)__popc(peers));
+        base_rank = __shfl_sync(peers, base_rank, leader);
+        w.mkey[p] = key;
+        w.mrank[p] = base_rank + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      }
     }
   }
 }
@@ -344,15 +370,15 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
 //   reference's cKDTree does).
 //   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are kept as bit
 //           masks and the k-th is picked, k = (R * count) >> 32.  Cells whose 3x3 block is
-//           crowded (a row range longer than 64 entries, or >= GNX_FM_HEAVY_K entries in all)
+//           crowded (a row range longer than 64 entries, or focals x candidates >= GNX_FM_HEAVY_WORK)
 //           are not searched here: the first of every 32 focals of such a cell appends a work
 //           item to Work.heavy and k_find_mates_dense takes them, one warp per item with the
 //           lanes across candidates
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
-#ifndef GNX_FM_HEAVY_K
-#define GNX_FM_HEAVY_K 128
+#ifndef GNX_FM_HEAVY_WORK
+#define GNX_FM_HEAVY_WORK 768
 #endif
 // position of the (k+1)-th set bit of m: popcount bisection (branch-free; __fns is a software loop)
 __device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
@@ -404,9 +430,13 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       // crowded block: the whole cell goes to k_find_mates_dense (the test depends on the cell
       // only, so every focal of the cell takes this exit; the cell's first entry announces it)
       const int l0 = hi[0] - lo[0], l1 = hi[1] - lo[1], l2 = hi[2] - lo[2];
-      if (max(l0, max(l1, l2)) > 64 || l0 + l1 + l2 >= GNX_FM_HEAVY_K) {
+      const int fs = (int)w.cell_start[cy * land.ncx + cx], nf = (int)w.cell_start[cy * land.ncx + cx + 1] - fs;
+      // the warp-per-batch kernel pays ~0.25 warp instructions per (focal, candidate) plus a fixed
+      // cost per batch, this kernel ~0.8 with nothing fixed: a cell moves over when its
+      // focals x candidates product covers the fixed cost (or a row range exceeds the masks here)
+      if (max(l0, max(l1, l2)) > 64 || nf * (l0 + l1 + l2) >= GNX_FM_HEAVY_WORK) {
         // one work item per batch of 32 focals of the cell, announced by the batch's first entry
-        if (((p - (int)w.cell_start[cy * land.ncx + cx]) & 31) == 0) {
+        if (((p - fs) & 31) == 0) {
           const int pos = atomicAdd(&c->n_heavy, 1);
           if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(key, (uint32_t)p);
           else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
@@ -2080,8 +2110,12 @@ __device__ __forceinline__ void raster_d_cell(const Land& land, const Params& pr
   double dv = N_d / N;                              // demography.py:159-160
   if (isnan(dv)) dv = 0.0;
   dv = dv < prm.c.d_min ? prm.c.d_min : (dv > prm.c.d_max ? prm.c.d_max : dv);
+#if GNX_ENVD_PLANAR
+  w.d_rast[id] = dv;                                // its own plane: a full-sector streaming write
+#else
   w.envd[(size_t)id * w.envd_stride] = dv;          // packed [cell][d | e_trait0 | e_trait1 ...]
   if (prm.store_debug) w.d_rast[id] = dv;
+#endif
 }
 
 __global__ void __launch_bounds__(256) k_raster_d(Dens d, Land land, Params prm, Work w, const Counters* c, int row_lo,
@@ -2135,12 +2169,25 @@ __global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, T
     const double x = xy.x, y = xy.y;
     const int cx = (int)x, cy = (int)y;
     const size_t cell = (size_t)cy * land.X + cx;
+#if GNX_ENVD_PLANAR
+    // d and the environment layers are read as planes: with the state in mating-grid order a warp's
+    // 32 individuals sit in a few neighbouring landscape cells, so the plane reads share sectors,
+    // and the d raster is written by k_raster_d as whole sectors (interleaved with the environment
+    // values it was a read-modify-write of 8 bytes in every 24: 2.6x its algorithmic traffic)
+    const size_t plane_sz = (size_t)land.X * land.Y;
+    double p = w.d_rast[cell];                                     // demography.py:306
+#else
     const double* __restrict__ ed = w.envd + cell * w.envd_stride;   // one sector: d and the traits' e
     double p = ed[0];                                              // demography.py:306
+#endif
     if (prm.selection) {
       double wfit = 1.0;
       for (int tt = 0; tt < T; ++tt) {
+#if GNX_ENVD_PLANAR
+        const double e = tr.univ_adv[tt] ? 1.0 : __ldg(&land.rasters[(size_t)tr.layer[tt] * plane_sz + cell]);
+#else
         const double e = tr.univ_adv[tt] ? 1.0 : ed[1 + tt];     // species.py:913-922 gather
+#endif
         const double z = pop.z[cur][(size_t)tt * pop.cap + i];
         const double phi = tr.phi_rast[tt] ? __ldg(&tr.phi_rast[tt][cell]) : tr.phi[tt];
         const double diff = fabs(e - z);
