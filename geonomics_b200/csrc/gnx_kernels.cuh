@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
 #ifndef GNX_FM_HEAVY_WORK
-#define GNX_FM_HEAVY_WORK 768
+#define GNX_FM_HEAVY_WORK 4096   // measured flat from 3072 to 16384 at c4 (t = 300); 256-768 are 10-35 % slower
 #endif
 // position of the (k+1)-th set bit of m: popcount bisection (branch-free; __fns is a software loop)
 __device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
@@ -431,9 +431,10 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       // only, so every focal of the cell takes this exit; the cell's first entry announces it)
       const int l0 = hi[0] - lo[0], l1 = hi[1] - lo[1], l2 = hi[2] - lo[2];
       const int fs = (int)w.cell_start[cy * land.ncx + cx], nf = (int)w.cell_start[cy * land.ncx + cx + 1] - fs;
-      // the warp-per-batch kernel pays ~0.25 warp instructions per (focal, candidate) plus a fixed
-      // cost per batch, this kernel ~0.8 with nothing fixed: a cell moves over when its
-      // focals x candidates product covers the fixed cost (or a row range exceeds the masks here)
+      // both kernels are bound by the six FP64 operations of a distance test; the warp-per-batch
+      // kernel loses lanes to padding (candidates in chunks of 32, focals in batches of 32), this
+      // one to trip-count divergence: a cell moves over when its focals x candidates product is
+      // large enough for the padding not to matter (or a row range exceeds the masks here)
       if (max(l0, max(l1, l2)) > 64 || nf * (l0 + l1 + l2) >= GNX_FM_HEAVY_WORK) {
         // one work item per batch of 32 focals of the cell, announced by the batch's first entry
         if (((p - fs) & 31) == 0) {

@@ -93,7 +93,7 @@ def test_crowded_cells_beyond_mask_capacity():
 
 def test_clumped_population_uses_both_kernels():
     """A density gradient from empty to crowded: sparse cells stay with the thread-per-focal
-    kernel, crowded ones (row range > 64 or focals x candidates >= 768) go to the warp-per-
+    kernel, crowded ones (row range > 64 or focals x candidates >= 4096) go to the warp-per-
     cell kernel; odd focal counts, cells on the landscape edge and in the corners included."""
     rng = np.random.default_rng(23)
     dim = (48, 40)
