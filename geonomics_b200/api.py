@@ -695,9 +695,59 @@ class Species:
         land._listeners.append(self)
         p = self._init_pop
         self._dev.set_burn(not self.burned)
-        self._dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], max_ind_idx=self.max_ind_idx)
+        self._dev.upload(p['x'], p['y'], p['age'], p['sex'], p['idx'], max_ind_idx=self.max_ind_idx,
+                         genomes_packed=p.get('genomes'))
         self._init_pop = None
         self._invalidate()
+
+    def _detach(self):
+        if self._dev is not None:
+            if self in self._land._listeners:
+                self._land._listeners.remove(self)
+            self._dev.close()
+            self._dev = None
+
+    # ---- iterations (model.py:455-506): the reference deep-copies the burned-in Community; here
+    # the population lives on the device, so the copy is a download and the reset an upload
+    def _snapshot(self):
+        st = self._dev.download(genomes=bool(self.burned and self.gen_arch is not None), unpack=False)
+        keep = ('Nt', 'n_births', 'n_deaths', 't', 'burned', 'extinct', 'max_ind_idx', 'start_N', 'mutate', 'K_factor')
+        snap = {k: copy.deepcopy(getattr(self, k)) for k in keep}
+        snap.update(state=st, K=np.array(self.K), gen_arch=copy.deepcopy(self.gen_arch),
+                    changer=copy.deepcopy(self._changer), pv=copy.deepcopy(self._pv),
+                    inst={k: copy.deepcopy(v) for k, v in self.__dict__.items()
+                          if hasattr(self._pv, k) and not k.startswith('_')},        # life-history overrides
+                    capacity=self._dev.capacity)
+        return snap
+
+    def _restore(self, snap, land, gen_arch=None):
+        """Back to a snapshot (on `land`); with `gen_arch` the genomic architecture is replaced and
+        the genomes are left for _set_genomes_and_tables (rand_genarch, model.py:476-494)."""
+        self._detach()
+        for k in ('Nt', 'n_births', 'n_deaths', 't', 'burned', 'extinct', 'max_ind_idx', 'start_N', 'mutate',
+                  'K_factor'):
+            setattr(self, k, copy.deepcopy(snap[k]))
+        for k in [k for k in self.__dict__ if hasattr(self._pv, k) and not k.startswith('_')]:
+            del self.__dict__[k]
+        self._pv = copy.deepcopy(snap['pv'])
+        for k, v in snap['inst'].items():
+            setattr(self, k, copy.deepcopy(v))
+        self._changer = copy.deepcopy(snap['changer'])
+        self._land = land
+        self.K = np.array(snap['K'])
+        self._K_overridden = False
+        self.gen_arch = copy.deepcopy(snap['gen_arch']) if gen_arch is None else gen_arch
+        st = snap['state']
+        self._init_pop = dict(x=st['x'], y=st['y'], age=st['age'], sex=st['sex'], idx=st['idx'])
+        if gen_arch is None and st.get('genomes') is not None:
+            self._init_pop['genomes'] = st['genomes']
+        self._attach(capacity=snap['capacity'])
+        if self.burned and gen_arch is None and self.mutate:
+            ga = self.gen_arch
+            self._dev.set_mutation(ga.mu_neut or 0, ga.mu_delet or 0, ga._mutables,
+                                   np.sort(np.asarray(ga.nonneut_loci, dtype=np.int64)), ga.delet_loci, ga.delet_loci_s,
+                                   ga.delet_alpha_distr_shape, ga.delet_alpha_distr_scale,
+                                   log_capacity=max(ga.L, 16))
 
     def _on_raster_change(self, lyr_num, rast):
         if self._dev is not None:
@@ -1077,6 +1127,12 @@ class Model:
         self.n_its = its['n_its']
         self.its = [*range(self.n_its)][::-1]
         self.it = -1
+        # model.py:115-131: what is re-drawn from one iteration to the next
+        self.rand_landscape = bool(its.get('rand_landscape', False))
+        self.rand_comm = bool(its.get('rand_comm', False))
+        self.rand_genarch = bool(its.get('rand_genarch', True))
+        self.repeat_burn = bool(its.get('repeat_burn', False))
+        self.iterations = {}                 # {it: per-step Nt / births / deaths of that iteration's main phase}
         self.land = _make_landscape(self.params)
         spps = {}
         for n, (sname, sp) in enumerate(self.params.comm.species.items()):
@@ -1086,6 +1142,9 @@ class Model:
             spp._attach()
         self.reassign_genomes = True
         self._never_been_run = True
+        # model.py:147-163: the originals the later iterations start from
+        self.orig_land = None if self.rand_landscape else copy.deepcopy(self._bare_land())
+        self.orig_comm = None if self.rand_comm else {n: spp._snapshot() for n, spp in self.comm.items()}
 
     # ---- one queue pass (model.py:603-667, 699-787); each species is advanced itself (the
     # reference's late-binding lambdas advance only the last species)
@@ -1188,12 +1247,103 @@ class Model:
             if extinct or (mode == 'burn' and self.comm.burned):
                 break
 
-    def run(self, verbose=False):
-        """model.py:866: burn in, then T main steps (one iteration; see bench.py for the
-        replicate-sharded multi-GPU form of n_its)."""
-        self.it += 1
-        self.walk(10 ** 9, 'burn', verbose)
+    # ---- iterations (model.py:338-339, 410-506, 520-593, 790-858, 866-953) -----------------------
+    def _bare_land(self):
+        """The landscape without its device listeners (what a deep copy should carry)."""
+        land = copy.copy(self.land)
+        land._listeners = []
+        return land
+
+    def _reset_landscape(self, rand_landscape):
+        if rand_landscape:
+            self.land = _make_landscape(self.params)               # model.py:436-441
+        else:
+            self.land = copy.deepcopy(self.orig_land)              # model.py:423-435 (changer included:
+            self.land._listeners = []                              #  its schedule starts over)
+
+    def _reset_community(self, rand_comm):
+        if rand_comm:                                              # model.py:499-505: a new Community
+            for spp in self.comm.values():
+                spp._detach()
+            spps = {}
+            for n, (sname, sp) in enumerate(self.params.comm.species.items()):
+                spps[n] = _make_species(self.land, sname, n, sp, seed=(self.seed or 0) * 1000003 + n + 7919 * (self.it + 1))
+            self.comm = Community(self.land, spps)
+            for spp in self.comm.values():
+                spp._attach()
+            return
+        for n, spp in self.comm.items():                           # model.py:457-494: the original Community
+            ga = None
+            if self.rand_genarch and spp.gen_arch is not None:
+                ga = _make_genomic_architecture(self.params.comm.species[spp.name], self.land)
+            spp._restore(self.orig_comm[n], self.land, gen_arch=ga)
+            if ga is not None and not self.repeat_burn and spp.burned:
+                spp._set_genomes_and_tables(self.burn_T, self.T)
+        self.comm.burned = all(spp.burned for spp in self.comm.values())
+        self.comm.t = -1
+
+    def _reset(self):
+        """model.py:520-593."""
+        if not self._never_been_run:
+            self._reset_landscape(self.rand_landscape)
+            self._reset_community(self.rand_comm)
+        else:
+            self._never_been_run = False
+        self.t = -1
+        if self.repeat_burn:
+            self.burn_t = -1
+        self.comm.t = -1
+        for spp in self.comm.values():
+            spp.t = -1
+        self.reassign_genomes = any(spp.gen_arch is not None for spp in self.comm.values())
+
+    def _do_next_iteration(self, verbose=False):
+        """model.py:808-858."""
+        self.it = self.its.pop()                                   # model.py:338-339
+        self._reset()
+        if self.rand_comm or self.repeat_burn or self.it == 0 or not self.comm.burned:
+            if self.repeat_burn and self.orig_comm is not None and self.it > 0:
+                for spp in self.comm.values():                     # burn in again from the saved start
+                    spp.burned = False
+                    spp._dev.set_burn(True)
+                self.comm.burned = False
+            self.walk(10 ** 9, 'burn', verbose)
+            if not self.rand_comm and not self.repeat_burn:
+                self.orig_comm = {n: spp._snapshot() for n, spp in self.comm.items()}     # model.py:833-838
+        if any(spp.extinct for spp in self.comm.values()):
+            return
+        n0 = {n: len(spp.Nt) for n, spp in self.comm.items()}
         self.walk(self.T, 'main', verbose)
+        self.iterations[self.it] = {n: dict(Nt=np.array(spp.Nt[n0[n]:]), n_births=np.array(spp.n_births[n0[n]:]),
+                                            n_deaths=np.array(spp.n_deaths[n0[n]:]))
+                                    for n, spp in self.comm.items()}
+
+    def run(self, verbose=False, dist=None):
+        """model.py:866-953: every iteration in `its` -- burn-in where the iteration needs one, then
+        T main steps; what carries over between iterations follows rand_landscape / rand_comm /
+        rand_genarch / repeat_burn.  With an initialised `torch.distributed` handle in `dist` the
+        iterations are sharded round-robin over the ranks (they never exchange data,
+        geonomics_b200/parallel.py) and rank 0 returns every iteration's trajectories."""
+        self._verbose = verbose
+        mine = None
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            from . import parallel
+            mine = set(parallel.shard_iterations(self.n_its, dist.get_rank(), dist.get_world_size()))
+        while len(self.its) > 0:
+            if mine is not None and self.its[-1] not in mine:
+                it = self.its.pop()
+                if it == 0:
+                    self.its.append(it)                            # every rank needs the burned-in original
+                else:
+                    continue
+            if mine is not None and self.seed is not None:
+                np.random.seed(self.seed + 104729 * self.its[-1])  # an iteration's draws do not depend on the sharding
+            self._do_next_iteration(verbose)
+        self._verbose = False
+        if mine is not None:
+            from . import parallel
+            return parallel.gather_trajectories({it: v for it, v in self.iterations.items() if it in mine}, dist)
+        return self.iterations
 
     # ---- getters (model.py:2787-3176) ---------------------------------------------------
     def _spp(self, spp):

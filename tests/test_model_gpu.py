@@ -279,3 +279,38 @@ def test_table_surface_follows_a_landscape_change():
     finally:
         spp._dev.close()
     del rng
+
+
+@pytest.mark.parametrize('rand_genarch,repeat_burn,rand_comm', [(True, False, False), (False, True, False),
+                                                                (False, False, True)])
+def test_run_iterates_n_its(rand_genarch, repeat_burn, rand_comm):
+    """Model.run (model.py:866-953) over n_its iterations with the reset rules of model.py:455-593:
+    the burned-in community is the common start unless the burn-in is repeated or the community
+    re-drawn; a re-drawn genomic architecture gets new genomes; the landscape changer starts over."""
+    from geonomics_b200 import api
+    p = api.read_parameters_file(PARAMS)
+    p['model']['its'] = dict(n_its=3, rand_landscape=False, rand_comm=rand_comm, rand_genarch=rand_genarch,
+                             repeat_burn=repeat_burn)
+    p['model']['T'] = 10
+    mod = api.make_model(p)
+    land0 = mod.land[1].rast.copy()
+    out = mod.run()
+    assert sorted(out) == [0, 1, 2] and mod.it == 2 and mod.its == []
+    for it in range(3):
+        rec = out[it][0]
+        assert len(rec['Nt']) == 10 and rec['Nt'].min() > 0
+        N = rec['Nt']
+        assert np.all(N[1:] == N[:-1] + rec['n_births'][1:] - rec['n_deaths'][1:])
+    spp = mod.comm[0]
+    assert spp.burned and mod.t == 9
+    # every iteration saw the scheduled landscape change (t = 4..8) from the original raster again
+    assert np.allclose(mod.land[1].rast, land0[:, ::-1])
+    g = mod.get_genotypes()
+    assert g.shape[0] == len(spp) and 0.3 < g.mean() < 0.7
+    if not repeat_burn and not rand_comm:
+        # same burned-in start every iteration: the first main step acts on the same individuals
+        starts = [out[it][0]['Nt'][0] - out[it][0]['n_births'][0] + out[it][0]['n_deaths'][0] for it in range(3)]
+        assert starts[0] == starts[1] == starts[2]
+    if rand_genarch:
+        # iterations drew different architectures: at least the trait loci or effect sizes moved
+        assert mod.orig_comm[0]['gen_arch'] is not spp.gen_arch
