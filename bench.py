@@ -382,6 +382,26 @@ def roofline_block(table, s, W, peak, peak_src, kernel_sum_ms):
     return roofline
 
 
+def bind_near_gpu(local_rank):
+    """Run this rank's host thread (and so its first-touch pinned buffers) on the cores of the NUMA
+    node its GPU hangs off: the e2e leg moves ~180 MB per step per rank between host and device."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)     # CUDA_VISIBLE_DEVICES may re-number: go by bus id
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(('%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id,
+                                                                        pr.pci_device_id)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def make_species(cfg, rank, seed_off=0):
     from geonomics_b200 import workloads
     from geonomics_b200.device import DeviceSpecies
@@ -511,7 +531,8 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=1500,
                     help='individuals per replica of the unmodified reference (--impl reference; ~0.4 s per step per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--e2e-steps', type=int, default=5, help='host-buffer steps per replicate in flight')
+    ap.add_argument('--e2e-depth', type=int, default=3, help='replicate populations in flight in the e2e leg')
     ap.add_argument('--presteps', type=int, default=0, help='time steps simulated before the warm-up')
     ap.add_argument('--c4-presteps', type=int, default=300,
                     help='the default line carries a c4 block (north_star target config) measured after this '
@@ -539,6 +560,8 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_near_gpu(local_rank)
     dist = None
     if world > 1:
         # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION/WARN/INFO; the contract
@@ -635,43 +658,71 @@ def main():
     table, s, kernel_sum_ms, peak, peak_src = kernel_table(dev, w, prof, precs, prof_steps, args.workload, args.scale)
     roofline = roofline_block(table, s, 4 * dev.W, peak, peak_src, kernel_sum_ms)
 
-    # ---- e2e: host buffers through gnx_walk_host, every step (pinned host memory)
+    # ---- e2e: host buffers through the C-ABI, every step (pinned host memory).  The populations are
+    # independent replicate iterations (model.py:115-117), `--e2e-depth` of them in flight, each on its
+    # own context: gnx_walk_host_begin enqueues one's copy in + step, gnx_walk_host_end waits and copies
+    # it out, so one replicate's result travels to the host while the next one's input travels to the
+    # device.  Every step still uploads its whole input and downloads its whole result.
     e2e = None
     if args.e2e_steps > 0:
         def pinned(shape, dtype):
             return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
-        bufs = dict(x=pinned(cap, torch.float64), y=pinned(cap, torch.float64), age=pinned(cap, torch.int32),
-                    sex=pinned(cap, torch.int8), idx=pinned(cap, torch.int64),
-                    genomes=pinned((cap, 2, dev.W), torch.int32).view(np.uint32),
-                    z=pinned((cap, max(1, T)), torch.float64), fit=pinned(cap, torch.float64))
-        st = dev.download(unpack=False)
-        n = len(st['x'])
-        for k in ('x', 'y', 'age', 'sex', 'idx', 'fit'):
-            bufs[k][:n] = st[k]
-        bufs['genomes'][:n] = st['genomes']
-        if T:
-            bufs['z'].reshape(-1)[:n * T] = st['z'].reshape(-1)
-        bufs['n'] = n
-        bufs['max_ind_idx'] = st['max_ind_idx']
         per_ind = 8 + 8 + 4 + 1 + 8 + 8 * dev.W + 8 * T + 8
-        dev.walk_host(bufs, 1)                              # warm-up
+        depth = max(1, args.e2e_depth)
+        edevs = [dev]
+        for k in range(1, depth):
+            edevs.append(make_species(cfg, rank, 5000 * k)[0])
+        ebufs = []
+        for d in edevs:
+            bufs = dict(x=pinned(cap, torch.float64), y=pinned(cap, torch.float64), age=pinned(cap, torch.int32),
+                        sex=pinned(cap, torch.int8), idx=pinned(cap, torch.int64),
+                        genomes=pinned((cap, 2, dev.W), torch.int32).view(np.uint32),
+                        z=pinned((cap, max(1, T)), torch.float64), fit=pinned(cap, torch.float64))
+            if d is not dev:
+                d.step(args.warmup)
+            st = d.download(unpack=False)
+            n = len(st['x'])
+            for k in ('x', 'y', 'age', 'sex', 'idx', 'fit'):
+                bufs[k][:n] = st[k]
+            bufs['genomes'][:n] = st['genomes']
+            if T:
+                bufs['z'].reshape(-1)[:n * T] = st['z'].reshape(-1)
+            bufs['n'] = n
+            bufs['max_ind_idx'] = st['max_ind_idx']
+            d.walk_host(bufs, 1)                            # warm-up
+            ebufs.append(bufs)
+        n_calls = args.e2e_steps * depth
         barrier()
         t0 = time.perf_counter()
         e2e_ind = 0
         h2d = d2h = 0
-        for _ in range(args.e2e_steps):
-            n_in = bufs['n']
-            dev.walk_host(bufs, 1)
+        inflight = [False] * depth
+        for k in range(n_calls):
+            j = k % depth
+            if inflight[j]:
+                edevs[j].walk_host_end(ebufs[j])
+                d2h += ebufs[j]['n'] * per_ind
+            n_in = ebufs[j]['n']
+            edevs[j].walk_host_begin(ebufs[j], 1)
+            inflight[j] = True
             e2e_ind += n_in
             h2d += n_in * per_ind
-            d2h += bufs['n'] * per_ind
+        for j in range(depth):
+            if inflight[j]:
+                edevs[j].walk_host_end(ebufs[j])
+                d2h += ebufs[j]['n'] * per_ind
         barrier()
         dt = time.perf_counter() - t0
         dt, e2e_ind = parallel.reduce_throughput(dt, float(e2e_ind), dist, 'cuda')
-        e2e = {'value': e2e_ind / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d / args.e2e_steps,
-               'd2h_bytes_per_step': d2h / args.e2e_steps, 'steps': args.e2e_steps,
-               'api': 'gnx_walk_host (C-ABI, pinned host SoA buffers in and out every step)'}
-        dev.step_records()
+        e2e = {'value': e2e_ind / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d / n_calls,
+               'd2h_bytes_per_step': d2h / n_calls, 'steps': n_calls, 'ms_per_step': dt * 1e3 / n_calls,
+               'replicates_in_flight': depth,
+               'api': 'gnx_walk_host_begin / gnx_walk_host_end (C-ABI, pinned host SoA buffers in and out every '
+                      'step; %d replicate populations in flight, one context each)' % depth}
+        for d in edevs:
+            d.step_records()
+        for d in edevs[1:]:
+            d.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

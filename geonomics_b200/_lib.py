@@ -214,6 +214,8 @@ SIGNATURES = {
     'gnx_step': (C.c_int, [_ctx, C.c_int32]),
     'gnx_sync': (C.c_int, [_ctx]),
     'gnx_walk_host': (C.c_int, [_ctx, C.POINTER(Population), C.c_int32]),
+    'gnx_walk_host_begin': (C.c_int, [_ctx, C.POINTER(Population), C.c_int32]),
+    'gnx_walk_host_end': (C.c_int, [_ctx, C.POINTER(Population)]),
     'gnx_read_step_records': (C.c_int, [_ctx, C.POINTER(StepRecord), C.c_int32, c_int32_p]),
     'gnx_tskit_enable': (C.c_int, [_ctx, C.c_int64, C.c_int64]),
     'gnx_tskit_set_nodes': (C.c_int, [_ctx, c_int32_p, c_int32_p, C.c_int64, C.c_int32, C.c_int32]),

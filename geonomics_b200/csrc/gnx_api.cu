@@ -1027,7 +1027,7 @@ static int build_order(gnx_ctx* ctx, const Counters& h, bool exclude_dead) {
 // ---- population upload / download -------------------------------------------------------
 extern "C" int gnx_phenotype(gnx_ctx* ctx);
 
-extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) {
+static int upload_population(gnx_ctx* ctx, const gnx_population_t* pop, bool wait) {
   ARG(ctx && pop, "null");
   USE_DEVICE(ctx);
   ARG(pop->n >= 0 && pop->n <= ctx->cfg.capacity, "population larger than capacity");
@@ -1063,9 +1063,13 @@ extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) 
     int r = gnx_phenotype(ctx);
     if (r != GNX_OK) return r;
   }
-  CK(cudaStreamSynchronize(s));
+  if (wait) CK(cudaStreamSynchronize(s));
   ctx->host_n_hint = (int)n;
   return GNX_OK;
+}
+
+extern "C" int gnx_upload_population(gnx_ctx* ctx, const gnx_population_t* pop) {
+  return upload_population(ctx, pop, true);
 }
 
 extern "C" int gnx_population_size(gnx_ctx* ctx, int64_t* n) {
@@ -2006,6 +2010,20 @@ extern "C" int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_step
   if (r != GNX_OK) return r;
   r = gnx_step(ctx, n_steps);
   if (r != GNX_OK) return r;
+  return gnx_download_population(ctx, pop);
+}
+
+// The same call split in two so that the host can keep several replicate populations in flight
+// (each on its own context = its own stream): _begin only ENQUEUES the copies in and the steps,
+// _end waits for them and copies the population out.  While one context's result travels to the
+// host, the next one's input travels to the device (PCIe is full duplex) and a third one steps.
+extern "C" int gnx_walk_host_begin(gnx_ctx* ctx, const gnx_population_t* pop, int32_t n_steps) {
+  int r = upload_population(ctx, pop, false);
+  if (r != GNX_OK) return r;
+  return gnx_step(ctx, n_steps);
+}
+
+extern "C" int gnx_walk_host_end(gnx_ctx* ctx, gnx_population_t* pop) {
   return gnx_download_population(ctx, pop);
 }
 

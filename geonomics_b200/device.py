@@ -398,6 +398,21 @@ class DeviceSpecies:
         bufs['max_ind_idx'] = int(p.max_ind_idx)
         return bufs
 
+    def walk_host_begin(self, bufs, n_steps):
+        """gnx_walk_host_begin: enqueue upload + n_steps; returns at once (bufs must be pinned)."""
+        self._inflight = self._pop_struct(bufs)
+        _lib.check(self._L.gnx_walk_host_begin(self._ctx, C.byref(self._inflight), int(n_steps)),
+                   'gnx_walk_host_begin')
+
+    def walk_host_end(self, bufs):
+        """gnx_walk_host_end: wait for the steps and copy the population out into bufs."""
+        p = self._pop_struct(bufs)
+        _lib.check(self._L.gnx_walk_host_end(self._ctx, C.byref(p)), 'gnx_walk_host_end')
+        self._inflight = None
+        bufs['n'] = int(p.n)
+        bufs['max_ind_idx'] = int(p.max_ind_idx)
+        return bufs
+
     # ---- stepping ------------------------------------------------------------------------
     def step(self, n_steps=1, sync=False):
         _lib.check(self._L.gnx_step(self._ctx, int(n_steps)), 'gnx_step')

@@ -286,6 +286,12 @@ int gnx_strip_check(gnx_ctx* ctx);      /* synchronises; exchange overflow -> GN
 int gnx_sync(gnx_ctx* ctx);
 /* Same, with HOST buffers in and out: upload pop, run n_steps, download into pop (synchronous). */
 int gnx_walk_host(gnx_ctx* ctx, gnx_population_t* pop, int32_t n_steps);
+/* The same in two halves, for hosts that keep several replicate populations (model.py:115-117,
+ * one context each) in flight: _begin enqueues the copies in and the steps and returns at once
+ * (the buffers of `pop` must be pinned and stay untouched until _end returns); _end waits and
+ * copies the population out.  Between the two, calls on OTHER contexts overlap with this one. */
+int gnx_walk_host_begin(gnx_ctx* ctx, const gnx_population_t* pop, int32_t n_steps);
+int gnx_walk_host_end(gnx_ctx* ctx, gnx_population_t* pop);
 /* Drain the per-step records accumulated since the last call (synchronises). */
 int gnx_read_step_records(gnx_ctx* ctx, gnx_step_record_t* out, int32_t max_records, int32_t* n_out);
 

@@ -164,3 +164,76 @@ def test_graph_and_plain_launches_agree_across_setter_calls(monkeypatch):
     assert ra == rb and la == lb
     for k in ('idx', 'x', 'y', 'age', 'g', 'z', 'fit'):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_walk_host_begin_end_equals_walk_host():
+    """gnx_walk_host_begin / gnx_walk_host_end (several replicate populations in flight, one context
+    each) return exactly what the synchronous gnx_walk_host returns for the same populations."""
+    import torch
+    from geonomics_b200 import workloads
+    from geonomics_b200.device import DeviceSpecies
+    cfg = workloads.scaled(dict(workloads.CONFIGS['c2']), 60000)
+    w = workloads.build(cfg, cfg['seed'])
+    N0, L = cfg['N'], w['L']
+    cap = int(1.5 * N0) + 4096
+
+    def ctx(seed):
+        return DeviceSpecies(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=cap, seed=seed)
+
+    def bufs(seed):
+        W = (L + 127) // 128 * 4
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        b = dict(x=pin(cap, torch.float64), y=pin(cap, torch.float64), age=pin(cap, torch.int32),
+                 sex=pin(cap, torch.int8), idx=pin(cap, torch.int64),
+                 genomes=pin((cap, 2, W), torch.int32).view(np.uint32), z=pin((cap, 2), torch.float64),
+                 fit=pin(cap, torch.float64))
+        rng = np.random.default_rng(seed)
+        b['x'][:N0] = rng.uniform(0, w['land_dim'][0] - 1e-9, N0)
+        b['y'][:N0] = rng.uniform(0, w['land_dim'][1] - 1e-9, N0)
+        b['age'][:N0] = rng.integers(0, 5, N0)
+        b['sex'][:N0] = rng.integers(0, 2, N0)
+        b['idx'][:N0] = np.arange(N0)
+        b['genomes'][:N0] = workloads.random_packed_genomes(N0, L, seed)
+        b['fit'][:N0] = 1.0
+        b['n'] = N0
+        b['max_ind_idx'] = N0 - 1
+        return b
+
+    def snap(b):
+        n = b['n']
+        return {k: np.array(b[k][:n]) for k in ('x', 'y', 'age', 'sex', 'idx', 'genomes', 'fit')} | {'z': np.array(b['z'].reshape(-1)[:2 * n])}
+
+    seeds = (11, 12, 13)
+    # reference: one population after the other, synchronously
+    want = []
+    for sd in seeds:
+        d, b = ctx(sd), bufs(sd)
+        try:
+            b.pop('z')                         # first upload: phenotypes computed on the device
+            d.walk_host(b, 1)
+            b['z'] = np.zeros((cap, 2))
+            d.walk_host(b, 1)
+            d.walk_host(b, 1)
+            want.append(snap(b))
+        finally:
+            d.close()
+    # pipelined: all three in flight
+    ds = [ctx(sd) for sd in seeds]
+    bs = [bufs(sd) for sd in seeds]
+    try:
+        for d, b in zip(ds, bs):
+            z = b.pop('z')
+            d.walk_host(b, 1)
+            b['z'] = z
+        for _ in range(2):
+            for d, b in zip(ds, bs):
+                d.walk_host_begin(b, 1)
+            for d, b in zip(ds, bs):
+                d.walk_host_end(b)
+        for b, wnt in zip(bs, want):
+            got = snap(b)
+            for k in wnt:
+                assert np.array_equal(got[k], wnt[k]), k
+    finally:
+        for d in ds:
+            d.close()
