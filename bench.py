@@ -320,7 +320,7 @@ def merge_dense(prof):
     prof = dict(prof)
     if 'k_find_mates_dense' in prof and 'k_find_mates' in prof:
         a, b = prof.pop('k_find_mates_dense'), prof['k_find_mates']
-        prof['k_find_mates'] = (b[0], a[1] + b[1])
+        prof['k_find_mates'] = (b[0], a[1] + b[1], {'thread_per_focal_ms': b[1] / b[0], 'crowded_cells_ms': a[1] / a[0]})
     return prof
 
 
@@ -342,7 +342,8 @@ def kernel_table(dev, w, prof, precs, steps, workload, scale):
     traffic = load_traffic(workload, scale)
     prof = merge_dense(prof)
     kernel_sum_ms = sum(v[1] for v in prof.values()) / steps
-    for name, (cnt, tot_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+    for name, val in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        cnt, tot_ms = val[0], val[1]
         per_launch_ms = tot_ms / cnt
         row = {'kernel': name, 'launches_per_step': cnt / steps, 'ms_per_launch': per_launch_ms,
                'share_of_kernel_time_sum': tot_ms / steps / kernel_sum_ms}
@@ -353,6 +354,8 @@ def kernel_table(dev, w, prof, precs, steps, workload, scale):
             row['frac_of_hbm_peak'] = row['achieved_GBs'] / peak
         if name in traffic:
             row['dram_bytes_ncu'] = traffic[name]['dram_bytes_per_launch']
+        if len(val) > 2:
+            row['launches'] = val[2]
         table.append(row)
     return table, s, kernel_sum_ms, peak, peak_src
 
