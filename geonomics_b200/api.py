@@ -699,6 +699,18 @@ class Species:
                          genomes_packed=p.get('genomes'))
         self._init_pop = None
         self._invalidate()
+        self._burnin_spat_tester = None
+        if not self.burned:                                   # species.py:469-470
+            from .burnin import SpatialTester
+            self._burnin_spat_tester = SpatialTester(self._dev)
+
+    def _do_spatial_burnin_test(self, num_timesteps_back):
+        """species.py:572-578."""
+        if self._burnin_spat_tester is None:
+            from .burnin import SpatialTester
+            self._burnin_spat_tester = SpatialTester(self._dev)
+        self._burnin_spat_tester.update(self._dev)
+        return self._burnin_spat_tester.run_test(num_timesteps_back)
 
     def _detach(self):
         if self._dev is not None:
@@ -976,6 +988,11 @@ class Species:
     def _calc_allele_freqs(self):
         return self._dev.stats()['freq']
 
+    def _calc_ld(self):
+        """stats.py:359-392: r^2 between every pair of loci (L x L, NaN diagonal); the chromosome
+        counts behind it are accumulated on the device from the packed genotypes."""
+        return self._dev.ld()
+
     def _calc_mean_fitness(self):
         """stats.py:428-435: mean of the fitness values of the last completed step."""
         return self._dev.stats()['mean_fit'] if self.gen_arch.traits is not None else np.nan
@@ -1185,17 +1202,23 @@ class Model:
                 spp._make_change()
 
     def _check_comm_burned(self):
-        """community.py:107-131 + burnin.py:94-103: minimum burn_T steps, then the paired
-        t-test on Nt.  The ADF test (statsmodels) and the per-cell spatial test are burn-in
-        control, out of scope here (SURVEY.md section 2 #15); they are skipped."""
-        from scipy.stats import ttest_ind
+        """community.py:107-131: after at least burn_T steps, every species must pass the ADF and the
+        paired t-test on Nt (burnin.py:93-103) and the spatial test on the per-cell count changes
+        (burnin.py:21-90, species.py:572-578; counts and their change come from the device).  As in
+        the reference all three are evaluated for every species (no short circuit), so the spatial
+        tester sees every step after the burn_T-th."""
+        from . import burnin
         ok = all(len(spp.Nt) >= self.burn_T for spp in self.comm.values())
         if ok:
-            for spp in self.comm.values():
-                nb = self.burn_T + self.burn_T % 2
-                a, b = spp.Nt[int(-nb):int(-nb / 2)], spp.Nt[int(-nb / 2):]
-                if len(a) > 1 and len(b) > 1 and np.std(a + b) > 0:
-                    ok = ok and bool(ttest_ind(a, b)[1] > 0.05)
+            def safe(fn, spp):
+                try:
+                    return bool(fn(spp.Nt, self.burn_T))
+                except ValueError:                    # a constant series (e.g. K reached exactly): not stationary evidence
+                    return False
+            adf_tests = all([safe(burnin.test_adf_threshold, spp) for spp in self.comm.values()])
+            t_tests = all([safe(burnin.test_t_threshold, spp) for spp in self.comm.values()])
+            spat_tests = all([spp._do_spatial_burnin_test(self.burn_T) for spp in self.comm.values()])
+            ok = adf_tests and t_tests and spat_tests
         for spp in self.comm.values():
             spp.burned = ok
         self.comm.burned = ok

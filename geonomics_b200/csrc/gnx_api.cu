@@ -49,6 +49,7 @@ struct gnx_ctx {
   std::vector<ProfSpan> spans;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;          // density chain of the fused step (one_step)
+  int32_t* burnin_counts = nullptr;        // gnx_burnin_cell_stats: [2][Y][X] counts (now, previous call) + two sums
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // one fused step captured as a CUDA graph (every kernel reads its sizes from the device
   // counters, so the same graph serves every step); re-captured when any kernel argument changes
@@ -450,6 +451,7 @@ extern "C" int gnx_destroy(gnx_ctx* ctx) {
   ctx->strip_ipc_opened.clear();
   if (ctx->strip_block) cudaFree(ctx->strip_block);
   if (ctx->d_paths) cudaFree(ctx->d_paths);
+  if (ctx->burnin_counts) cudaFree(ctx->burnin_counts);
   for (int k = 0; k < 2; ++k) if (ctx->d_surf_tab[k]) cudaFree(ctx->d_surf_tab[k]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -2260,6 +2262,68 @@ extern "C" int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_m
   return check_device_err(hc);
 }
 
+
+// Linkage disequilibrium counts (sim/stats.py:359-392): host_n11[Lp * Lp], Lp = 32 * ceil(L / 32),
+// row-major; entry (i, j), j's word >= i's word, = chromosomes carrying the 1-allele at both loci
+// (the diagonal = 1-allele counts); the other word-triangle stays zero.  *n = population size.
+extern "C" int gnx_stats_ld(gnx_ctx* ctx, uint64_t* host_n11, int64_t* n) {
+  ARG(ctx && host_n11 && n, "null");
+  USE_DEVICE(ctx);
+  if (ctx->burn || ctx->cfg.L == 0) { g_last_error = "no genomes on the device"; return GNX_ERR_STATE; }
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  const int Wu = (ctx->cfg.L + 31) / 32, Lp = 32 * Wu;
+  const int ntile = Wu * (Wu + 1) / 2;
+  // enough (tile, haplotype range) items to fill the machine a few times over
+  const int nsplit = std::max(1, std::min(4096, (ctx->num_sms * 64 + ntile - 1) / ntile));
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)Lp * Lp * 8));
+  CK(cudaMemsetAsync(d, 0, (size_t)Lp * Lp * 8, ctx->stream));
+  PROF(ctx, "k_stats_ld");
+  k_stats_ld<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->d_c, d, Wu, Lp, nsplit);
+  LAUNCHED(ctx);
+  cudaError_t e = cudaMemcpyAsync(host_n11, d, (size_t)Lp * Lp * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  Counters hc;
+  r = read_counters(ctx, &hc);
+  cudaFree(d);
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return GNX_ERR_CUDA; }
+  if (r != GNX_OK) return r;
+  *n = hc.n;
+  return check_device_err(hc);
+}
+
+// Burn-in spatial statistic (sim/burnin.py:41-58): counts the individuals of every landscape cell
+// and returns the sum and the sum of squares of the change of the counts since the previous call
+// (the first call compares with all-zero counts, as SpatialTester.__init__ does).
+extern "C" int gnx_burnin_cell_stats(gnx_ctx* ctx, int64_t* sum_diff, int64_t* sum_sq_diff) {
+  ARG(ctx && sum_diff && sum_sq_diff, "null");
+  USE_DEVICE(ctx);
+  int r = materialise(ctx);
+  if (r != GNX_OK) return r;
+  const size_t ncell = (size_t)ctx->cfg.dim_x * ctx->cfg.dim_y;
+  cudaStream_t s = ctx->stream;
+  if (!ctx->burnin_counts) {
+    CK(cudaMalloc((void**)&ctx->burnin_counts, (2 * ncell + 4) * sizeof(int32_t)));
+    CK(cudaMemsetAsync(ctx->burnin_counts, 0, (2 * ncell + 4) * sizeof(int32_t), s));
+  }
+  int32_t* cur = ctx->burnin_counts;
+  int32_t* prev = cur + ncell;
+  long long* sums = reinterpret_cast<long long*>(prev + ncell);      // 16 bytes behind the two rasters
+  CK(cudaMemsetAsync(cur, 0, ncell * sizeof(int32_t), s));
+  CK(cudaMemsetAsync(sums, 0, 16, s));
+  PROF(ctx, "k_burnin_count");
+  k_burnin_count<<<grid_for(ctx, 8), 256, 0, s>>>(ctx->pop, ctx->land, ctx->d_c, cur);
+  LAUNCHED(ctx);
+  PROF(ctx, "k_burnin_diff");
+  k_burnin_diff<<<grid_for(ctx, 8), 256, 0, s>>>(cur, prev, ncell, sums);
+  LAUNCHED(ctx);
+  long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, sums, 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *sum_diff = h[0];
+  *sum_sq_diff = h[1];
+  return GNX_OK;
+}
 
 // ---- tskit record buffering (species.py:692-736, genome.py:234-281) --
 // Node / edge / individual rows of every birth are written to device buffers by the step

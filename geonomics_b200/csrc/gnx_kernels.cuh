@@ -2651,6 +2651,100 @@ __global__ void __launch_bounds__(256) k_stats_genotypes(Pop pop, const Counters
   }
 }
 
+// ========================================================================================
+// f2 linkage disequilibrium (sim/stats.py:359-392 _calc_ld): for every pair of loci (i, j) the
+// number of CHROMOSOMES carrying the 1-allele at both, n11[i][j] = sum_h bit_i(h) & bit_j(h) over
+// the 2n haplotypes -- the binary product H^T H of the haplotype matrix; r^2 follows on the host
+// from n11 and its diagonal exactly as the reference writes it.  One warp owns one 32 x 32 tile
+// (word column wi x word column wj >= wi) over a range of haplotypes, lane = haplotype: the 32
+// lanes' words are bit-transposed (5 butterfly stages of shuffles), so that lane l holds the
+// membership mask of locus 32*w + l over the 32 haplotypes; every lane then accumulates its own
+// locus of the tile's rows against the 32 column masks (broadcast by shuffle) with AND + POPC.
+// ========================================================================================
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+  // 32 x 32 bit-matrix transpose across the warp: afterwards bit h of lane l = bit l of lane h
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    // lanes with bit j clear keep their low halves and take the partner's low halves shifted up
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(256) k_stats_ld(Pop pop, const Counters* c, unsigned long long* n11, int Wu, int Lp,
+                                                   int nsplit) {
+  const int n = c->n, cur = c->cur, Ww = 4 * pop.Wq;
+  const int lane = threadIdx.x & 31;
+  const int ntile = Wu * (Wu + 1) / 2;
+  const long long nhap = 2ll * n;
+  const long long ngroup = (nhap + 31) / 32;                 // groups of 32 haplotypes
+  for (int item = GTID >> 5; item < ntile * nsplit; item += GSTRIDE >> 5) {
+    const int tile = item / nsplit, part = item % nsplit;
+    int wi = 0, rem = tile;                                    // tile -> (wi, wj), wj >= wi
+    while (rem >= Wu - wi) { rem -= Wu - wi; ++wi; }
+    const int wj = wi + rem;
+    uint32_t acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0u;
+    const long long g0 = ngroup * part / nsplit, g1 = ngroup * (part + 1) / nsplit;
+    for (long long g = g0; g < g1; ++g) {
+      const long long h = g * 32 + lane;
+      uint32_t a = 0u, bw = 0u;
+      if (h < nhap) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(pop.G + (size_t)pop.gslot[cur][(int)(h >> 1)] * 2 * pop.Wq)
+                              + (size_t)(h & 1) * Ww;
+        a = row[wi];
+        bw = row[wj];
+      }
+      const uint32_t mi = warp_bit_transpose(a, lane);         // haplotypes carrying locus 32*wi + lane
+      const uint32_t mj = wi == wj ? mi : warp_bit_transpose(bw, lane);
+#pragma unroll
+      for (int b = 0; b < 32; ++b) acc[b] += __popc(mi & __shfl_sync(0xffffffffu, mj, b));
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+      if (acc[b]) atomicAdd(&n11[(size_t)(32 * wi + lane) * Lp + 32 * wj + b], (unsigned long long)acc[b]);
+  }
+}
+
+// ========================================================================================
+// f4 burn-in control (sim/burnin.py:21-58 SpatialTester.update): individuals per landscape cell,
+// and the sum and sum of squares of the change of every cell's count since the previous call
+// (mean and standard deviation of `diff` follow on the host).  Integer sums: exact.
+// ========================================================================================
+__global__ void __launch_bounds__(256) k_burnin_count(Pop pop, Land land, const Counters* c, int32_t* counts) {
+  const int n = c->n, cur = c->cur;
+  for (int p = GTID; p < n; p += GSTRIDE) {
+    const double2 xy = pop.xy[cur][p];
+    const int ix = (int)xy.x, iy = (int)xy.y;
+    // burnin.py:49-52 fills counts[i, j], i < dim[0], j < dim[1], from the (x = j, y = i) tally: on a
+    // non-square landscape the individuals with x >= dim[1] or y >= dim[0] are not counted
+    if (ix < land.Y && iy < land.X) atomicAdd(&counts[(size_t)iy * land.X + ix], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_burnin_diff(const int32_t* __restrict__ counts, int32_t* prev, size_t ncell,
+                                                      long long* sums) {
+  long long s1 = 0, s2 = 0;
+  for (size_t k = GTID; k < ncell; k += GSTRIDE) {
+    const long long d = (long long)counts[k] - prev[k];
+    s1 += d;
+    s2 += d * d;
+    prev[k] = counts[k];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (s1 | s2)) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&sums[0]), (unsigned long long)s1);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&sums[1]), (unsigned long long)s2);
+  }
+}
+
 // node ids 2k, 2k+1 in species order (after simplify, species.py:1148-1152); reset_t0 marks
 // the current step as tskit time 0
 __global__ void __launch_bounds__(256) k_tskit_renumber(Pop pop, Counters* c, int reset_t0) {

@@ -488,6 +488,37 @@ class DeviceSpecies:
         return dict(N=N, freq=freq, het=het[:self.Lg] / float(N) if N else np.zeros(self.Lg),
                     maf=np.minimum(freq, 1 - freq), mean_fit=float(fs.value) / N if N else float('nan'))
 
+    def ld(self):
+        """r^2 between every pair of loci (sim/stats.py:359-392 _calc_ld): the L x L matrix the
+        reference returns (NaN on the diagonal), formed with the reference's own expression from
+        the chromosome counts n11[i][j] that the device accumulates (gnx_stats_ld)."""
+        L = self.Lg
+        Lp = 32 * ((L + 31) // 32)
+        n11 = np.zeros((Lp, Lp), dtype=np.uint64)
+        n = C.c_int64()
+        _lib.check(self._L.gnx_stats_ld(self._ctx, n11.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(n)),
+                   'gnx_stats_ld')
+        N = 2 * int(n.value)                                  # chromosomes
+        n11 = n11[:L, :L].astype(np.float64)
+        n11 = np.triu(n11) + np.triu(n11, 1).T                # only one word-triangle is filled
+        f1 = np.diagonal(n11) / N
+        with np.errstate(divide='ignore', invalid='ignore'):
+            D = n11 / N - f1[:, None] * f1[None, :]
+            r2 = (D ** 2) / (((f1 * (1 - f1))[:, None] * f1[None, :]) * (1 - f1)[None, :])
+        # the reference fills (i, j) and (j, i) from the i < j evaluation
+        r2 = np.triu(r2, 1) + np.triu(r2, 1).T
+        r2[np.arange(L), np.arange(L)] = np.nan
+        return r2
+
+    def burnin_cell_stats(self):
+        """(mean, std) of the change of the per-cell individual counts since the previous call
+        (sim/burnin.py:41-58 SpatialTester.update: np.mean(diff), np.std(diff))."""
+        s1, s2 = C.c_int64(), C.c_int64()
+        _lib.check(self._L.gnx_burnin_cell_stats(self._ctx, C.byref(s1), C.byref(s2)), 'gnx_burnin_cell_stats')
+        ncell = float(self.land_dim[0] * self.land_dim[1])
+        mean = s1.value / ncell
+        return mean, float(np.sqrt(max(s2.value / ncell - mean * mean, 0.0)))
+
     def fst(self, region_a, region_b, est_Hs=False):
         """Per-locus pairwise Fst = (Ht - Hs) / Ht between two rectangular sub-populations, as in the
         reference's validation suite (tests/validation/island/island_test.py:54-68 calc_Fst_HsHt):

@@ -373,6 +373,18 @@ int gnx_stats_genotypes(gnx_ctx* ctx, uint64_t* host_c1 /* [L] */, uint64_t* hos
  * counts for pairwise Fst = (Ht - Hs) / Ht (tests/validation/island/island_test.py:54-68) */
 int gnx_stats_genotypes_region(gnx_ctx* ctx, double x_min, double x_max, double y_min, double y_max,
                                uint64_t* host_c1, uint64_t* host_het, double* fit_sum, int64_t* n);
+/* Linkage disequilibrium (sim/stats.py:359-392 _calc_ld): host_n11[Lp * Lp] row-major with
+ * Lp = 32 * ceil(L / 32); entry (i, j) with j / 32 >= i / 32 = number of chromosomes (of 2n) that
+ * carry the 1-allele at both locus i and locus j (the diagonal: 1-allele counts); the other
+ * word-triangle stays zero.  r^2 = D^2 / (f_i (1 - f_i) f_j (1 - f_j)), D = n11 / 2n - f_i f_j, is
+ * formed by the caller exactly as the reference writes it.  Synchronises. */
+int gnx_stats_ld(gnx_ctx* ctx, uint64_t* host_n11, int64_t* n);
+/* Burn-in spatial statistic (sim/burnin.py:21-58 SpatialTester.update, species.py:572-578): counts
+ * the live individuals of every landscape cell (int(x), int(y)) and returns the sum and the sum of
+ * squares of the change of the counts since the previous call on this context (the first call
+ * compares with all-zero counts, as SpatialTester.__init__ does).  mean(diff) and std(diff) over the
+ * dim_x * dim_y cells follow from the two integers.  Synchronises. */
+int gnx_burnin_cell_stats(gnx_ctx* ctx, int64_t* sum_diff, int64_t* sum_sq_diff);
 
 /* ---- introspection (parity tests, lazy API views) -------------------------------------- */
 enum {

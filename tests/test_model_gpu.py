@@ -98,6 +98,75 @@ def test_on_device_stats_match_numpy(model):
     assert abs(spp._calc_mean_fitness() - fit.mean()) < 1e-12
 
 
+def test_on_device_ld_matches_the_reference_formula(model):
+    """sim/stats.py:359-392 _calc_ld, loop for loop, on the downloaded genotypes vs the device's
+    chromosome-count accumulation (gnx_stats_ld); the reference's own function where it is installed."""
+    mod = model
+    spp = mod.comm[0]
+    speciome = mod.get_genotypes()                # [N, L, 2]
+    n, L = speciome.shape[0], speciome.shape[1]
+    N = n * 2
+    want = np.zeros([L] * 2) * np.nan
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for i in range(L):
+            for j in range(i + 1, L):
+                f1_i = np.sum(speciome[:, i, :], axis=None) / (N)
+                f1_j = np.sum(speciome[:, j, :], axis=None) / (N)
+                f11_ij = float(np.sum(speciome[:, [i, j], :].sum(axis=1) == 2, axis=None)) / (N)
+                D_1_1 = f11_ij - (f1_i * f1_j)
+                r2 = (D_1_1 ** 2) / (f1_i * (1 - f1_i) * f1_j * (1 - f1_j))
+                want[i, j] = want[j, i] = r2
+    got = spp._calc_ld()
+    assert got.shape == (L, L) and np.all(np.isnan(np.diagonal(got)))
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, equal_nan=True)
+    assert np.nanmax(got) <= 1 + 1e-12 and np.nanmin(got) >= 0
+    from oracle import ref_shims
+    if ref_shims.reference_root() is not None:
+        ref_shims.install()
+        from geonomics.sim import stats as ref_stats
+
+        class _Spp:
+            gen_arch = spp.gen_arch
+
+            def _get_genotypes(self):
+                return speciome
+        with np.errstate(divide='ignore', invalid='ignore'):
+            ref = ref_stats._calc_ld(_Spp())
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_on_device_ld_many_words():
+    """L = 300 (10 word columns, 55 tiles) with loci in strong and in no linkage."""
+    from geonomics_b200.device import DeviceSpecies
+    from geonomics_b200 import genome_pack as gp
+    rng = np.random.default_rng(8)
+    n, L = 700, 300
+    g = (rng.random((n, L, 2)) < 0.4).astype(np.int8)
+    g[:, 37, :] = g[:, 290, :]                    # complete linkage across distant words
+    g[:, 100, :] = 1 - g[:, 101, :]
+    g[:, 5, :] = 0                                # a fixed locus: r^2 undefined (nan)
+    from geonomics_b200 import workloads
+    cfg = dict(workloads.CONFIGS['c2'], dim=(20, 20), N=n, L=L, n_paths=50)
+    w = workloads.build(cfg, 3)
+    X, Y = w['land_dim']
+    dev = DeviceSpecies(w['land_dim'], w['rasters'], w['prm'], w['gen_arch'], capacity=3 * n, seed=1)
+    try:
+        dev.upload(rng.uniform(0, X - 1e-3, n), rng.uniform(0, Y - 1e-3, n), np.zeros(n, np.int32),
+                   np.zeros(n, np.int8), np.arange(n), g=g)
+        got = dev.ld()
+    finally:
+        dev.close()
+    H = g.transpose(0, 2, 1).reshape(2 * n, L).astype(np.float64)
+    n11 = H.T @ H
+    f = np.diagonal(n11) / (2 * n)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        D = n11 / (2 * n) - np.outer(f, f)
+        want = D ** 2 / np.outer(f * (1 - f), f * (1 - f))
+    want[np.arange(L), np.arange(L)] = np.nan
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-15, equal_nan=True)
+    assert abs(got[37, 290] - 1) < 1e-12 and abs(got[100, 101] - 1) < 1e-12 and np.all(np.isnan(got[5, :]))
+
+
 def test_model_with_mutation():
     """make_model -> burn -> main with mu_neut, mu_delet > 0 (a13): the device's mutation log
     is pulled into Species.mutations / GenomicArchitecture like the reference maintains them."""
