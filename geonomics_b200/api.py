@@ -93,47 +93,37 @@ class Layer:
         self._is_K = []
 
 
+def _scattered_values_to_raster(dim, pts, vals, method, num_hab_types):
+    """Seed values at scattered points -> a [dim_y, dim_x] raster: scipy griddata on the integer lattice
+    1..max(dim) of a square, 'nearest' results rounded to habitat classes, 'cubic' results shifted and
+    scaled into (0, 1) with two small uniform jitters (drawn in that order), cropped to the layer."""
+    from scipy.interpolate import griddata
+    side = max(dim)
+    axis = np.linspace(1, side, side)
+    field = griddata(pts, vals * (num_hab_types - 1) if method == 'nearest' else vals,
+                     tuple(np.meshgrid(axis, axis, indexing='ij')), method=method)
+    if method == 'nearest':
+        field = np.rint(field).astype(float)
+    elif method == 'cubic':
+        field = field + abs(field.min()) + 0.01 * np.random.rand()
+        field = field / (field.max() + 0.01 * np.random.rand())
+    return field[:dim[1], :dim[0]]
+
+
 def _make_random_lyr(dim, n_pts, interp_method='cubic', num_hab_types=2, dist='beta', alpha=0.05, beta=0.05):
-    """landscape.py:411-470."""
-    from scipy import interpolate
-    r = np.random
-    max_dim = max(dim)
-    if interp_method == 'nearest':
-        vals = (r.rand(n_pts) if dist == 'unif' else r.beta(alpha, beta, n_pts)) * (num_hab_types - 1)
-    else:
-        vals = r.rand(n_pts) if dist == 'unif' else r.beta(alpha, beta, n_pts)
-    pts = r.normal(max_dim / 2, max_dim * 2, [n_pts, 2])
-    grid_x, grid_y = np.mgrid[1:max_dim:complex('%ij' % max_dim), 1:max_dim:complex('%ij' % max_dim)]
-    I = interpolate.griddata(pts, vals, (grid_x, grid_y), method=interp_method)
-    if interp_method == 'nearest':
-        I = I.round().astype(float)
-    if interp_method == 'cubic':
-        I = I + abs(I.min()) + (0.01 * r.rand())
-        I = I / (I.max() + (0.01 * r.rand()))
-    if dim[0] != dim[1]:
-        I = I[:dim[1], :dim[0]]
-    return I
+    """landscape.py:411-470 ('random' layers): values first, then the seed points -- the reference's
+    draw order, so a seeded numpy.random gives the reference's layer."""
+    vals = np.random.rand(n_pts) if dist == 'unif' else np.random.beta(alpha, beta, n_pts)
+    pts = np.random.normal(max(dim) / 2, max(dim) * 2, [n_pts, 2])
+    return _scattered_values_to_raster(dim, pts, vals, interp_method, num_hab_types)
 
 
 def _make_defined_lyr(dim, rast, pts=None, vals=None, interp_method='cubic', num_hab_types=2):
-    """landscape.py:473-519."""
+    """landscape.py:473-519 ('defined' layers): a raster as given, or interpolated from points."""
     if rast is not None:
         return np.array(rast, dtype=np.float64)
-    from scipy import interpolate
-    r = np.random
-    if interp_method == 'nearest':
-        vals = vals * (num_hab_types - 1)
-    max_dim = max(dim)
-    grid_x, grid_y = np.mgrid[1:max_dim:complex('%ij' % max_dim), 1:max_dim:complex('%ij' % max_dim)]
-    I = interpolate.griddata(pts, vals, (grid_x, grid_y), method=interp_method)
-    if interp_method == 'nearest':
-        I = I.round().astype(float)
-    if interp_method == 'cubic':
-        I = I + abs(I.min()) + (0.01 * r.rand())
-        I = I / (I.max() + (0.01 * r.rand()))
-    if dim[0] != dim[1]:
-        I = I[:dim[1], :dim[0]]
-    return I
+    return _scattered_values_to_raster(dim, np.asarray(pts), np.asarray(vals, dtype=np.float64), interp_method,
+                                       num_hab_types)
 
 
 class _LandscapeChanger:
