@@ -1383,7 +1383,10 @@ __global__ void __launch_bounds__(GT_THREADS) k_gametes_tma(Pop pop, Params prm,
 }
 
 // ----- k_newborns: natal dispersal, sex, newborn record (one thread per offspring) -------
-__global__ void __launch_bounds__(256) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
+#ifndef GNX_NB_MINB
+#define GNX_NB_MINB 4     // 64 registers instead of 77: 83 -> 68 us at c4
+#endif
+__global__ void __launch_bounds__(256, GNX_NB_MINB) k_newborns(Pop pop, Land land, Params prm, DevDraws dr, Work w,
                                                    Counters* c, Tsk tsk) {
   const int n = c->n, B = c->B, cur = c->cur;
   const int n_nodes = c->n_nodes, n_born = c->n_born;
@@ -2152,7 +2155,12 @@ __global__ void __launch_bounds__(256) k_raster_d_fix(Dens d, Land land, Params 
 // the time step (Species._set_Nt species.py:554, the bookkeeping of demography.py:324-329):
 // the dead are only FLAGGED here -- the next step's re-grid drops them.
 // ========================================================================================
-__global__ void __launch_bounds__(256) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
+// 8 resident CTAs (<= 32 registers): the kernel waits on its per-individual raster and genome gathers,
+// so residency beats registers (measured at c4: 262 us without the bound, 245 at 6, 233 at 8)
+#ifndef GNX_DEATH_MINB
+#define GNX_DEATH_MINB 8
+#endif
+__global__ void __launch_bounds__(256, GNX_DEATH_MINB) k_death(Pop pop, Land land, Params prm, Traits tr, DevDraws dr, Work w,
                                                 Counters* c, Mut mu, int end_step, const Strip* st) {
   const int n0 = c->n, n = c->n + c->B, cur = c->cur, T = pop.T;
   const int64_t t = c->t;

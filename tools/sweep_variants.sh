@@ -14,5 +14,5 @@ for f in sorted(glob.glob('gpurun_out/sw_${TAG}_*.json')):
         print(f, 'failed'); continue
     k = {r['kernel']: r['ms_per_launch'] * 1e3 for r in d['kernels']}
     fm = next((r for r in d['kernels'] if r['kernel'] == 'k_find_mates'), {}).get('launches', {})
-    print('%-44s ms/step %.4f  find_mates %.1f (light %.1f dense %.1f) move_key %.1f regrid %.1f' % (f.split('/')[-1], d['ms_per_step'], k.get('k_find_mates', 0), fm.get('thread_per_focal_ms', 0) * 1e3, fm.get('crowded_cells_ms', 0) * 1e3, k.get('k_move_key', 0), k.get('k_regrid', 0)))
+    print('%-44s ms/step %.4f  find_mates %.1f (light %.1f dense %.1f) move_key %.1f regrid %.1f death %.1f newborns %.1f' % (f.split('/')[-1], d['ms_per_step'], k.get('k_find_mates', 0), fm.get('thread_per_focal_ms', 0) * 1e3, fm.get('crowded_cells_ms', 0) * 1e3, k.get('k_move_key', 0), k.get('k_regrid', 0), k.get('k_death', 0), k.get('k_newborns', 0)))
 PY
