@@ -544,6 +544,8 @@ def main():
     ap.add_argument('--no-strips', action='store_true',
                     help='with N > 1 ranks the default line also carries c4 strip-decomposed over the N GPUs '
                          '(strong scaling); this switches it off')
+    ap.add_argument('--ncu-window', action='store_true',
+                    help='bracket ONE extra step after the warm-up with cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     ap.add_argument('--replicates', type=int, default=None,
                     help='replicate populations per GPU, stepped concurrently on their own streams '
                          '(default 8 for c3 = BASELINE configs[2]: 64 replicates on 8 GPUs; 1 otherwise)')
@@ -618,6 +620,14 @@ def main():
     for d in devs:
         d.sync()
         d.step_records()
+    if args.ncu_window:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_all(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        for d in devs:
+            d.step_records()
     launches0 = sum(d.launch_count for d in devs)
     # ---- timed region: K steps, state resident in HBM, CUDA events on the launching stream
     sampler = ClockSampler(local_rank)

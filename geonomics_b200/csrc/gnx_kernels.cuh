@@ -177,20 +177,29 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
   double2* __restrict__ XY = pop.xy[cur];
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
   const int lane = threadIdx.x & 31;
-  // whole warps stay in the loop (ballots below): the tail is masked by `live`
+  __shared__ int s_free_off[9];                         // per-warp offsets of the freed rows + the CTA's base
+  // whole CTAs stay in the loop (ballots and barriers below): the tail is masked by `in`
   for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {
     const int p = base + threadIdx.x;
     const bool in = p < n;
     const bool dead = in && pending && !w.alive[p];
     if (pending && do_key) {
-      // lazy mortality (demography.py:175-180): the dead leave the population here
+      // lazy mortality (demography.py:175-180): the dead leave the population here and their genome
+      // rows go back to the free list.  ONE atomic on the list cursor per CTA pass (the per-warp
+      // form queued ~3e5 same-address atomics per step at c4: a third of this kernel's stall samples)
       const unsigned dm = __ballot_sync(0xffffffffu, dead && !prm.burn);
-      if (dm) {
-        int pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(&c->n_free, __popc(dm));
-        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        if (dead && !prm.burn) pop.free_slots[pos0 + __popc(dm & ((1u << lane) - 1u))] = pop.gslot[cur][p];
+      __syncthreads();                                    // the previous pass has read s_free_off
+      if (lane == 0) s_free_off[threadIdx.x >> 5] = __popc(dm);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int ck = s_free_off[k]; s_free_off[k] = tot; tot += ck; }
+        s_free_off[8] = tot ? atomicAdd(&c->n_free, tot) : 0;
       }
+      __syncthreads();
+      if (dead && !prm.burn)
+        pop.free_slots[s_free_off[8] + s_free_off[threadIdx.x >> 5] + __popc(dm & ((1u << lane) - 1u))] = pop.gslot[cur][p];
       if (dead) w.mkey[p] = GNX_KEY_DEAD;
     }
     // no early exit: the whole warp takes part in the cell-count aggregation at the end

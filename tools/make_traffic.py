@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel in an
-`ncu --set full` capture, under the names bench.py uses -> profiles/r01_traffic.json.
+`ncu --set full` capture, under the names bench.py uses -> profiles/r02_traffic.json.
 
-  python tools/make_traffic.py REPORT.ncu-rep WORKLOAD [--out profiles/r01_traffic.json]
+  python tools/make_traffic.py REPORT.ncu-rep WORKLOAD [--out profiles/r02_traffic.json]
 
 bench.py copies the figure of the dominant kernel into `roofline.traffic`.
 """
@@ -35,7 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('report')
     ap.add_argument('workload')
-    ap.add_argument('--out', default='profiles/r01_traffic.json')
+    ap.add_argument('--out', default='profiles/r02_traffic.json')
     a = ap.parse_args()
     txt = subprocess.run(['ncu', '-i', a.report, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
@@ -47,6 +47,11 @@ def main():
         b = sum(to_bytes(r[ix[c]], units[ix[c]]) for c in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
         t = float(r[ix['gpu__time_duration.sum']].replace(',', ''))
         t *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(units[ix['gpu__time_duration.sum']], 1.0)
+        if name == 'k_find_mates_dense':          # the crowded cells of the same search: one row, as in bench.py
+            d = acc.setdefault('k_find_mates', [0, 0.0, 0.0])
+            d[1] += b
+            d[2] += t
+            continue
         d = acc.setdefault(name, [0, 0.0, 0.0])
         d[0] += 1
         d[1] += b
