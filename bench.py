@@ -36,11 +36,11 @@ UNIT = 'individual-generations/s'
 # ------------------------------------------------------------------------------------------
 def algorithmic_bytes(W, T, cells, YX):
     return {
-        # entries walked = last step's n_pre (its dead are dropped here); x,y rw; id r; alive r; key+rank w
-        'k_move_key': lambda s: s['npre'] * (1 + 8) + s['n'] * (32 + 8),
+        # entries walked = last step's n_pre (its dead are dropped here); x,y rw; id r; alive r; key w
+        'k_move_key': lambda s: s['npre'] * (1 + 4) + s['n'] * (32 + 8),
         'scan_cells.reduce': lambda s: cells * 4,
         'scan_cells.apply': lambda s: cells * 8,
-        'k_bucket': lambda s: s['npre'] * 8 + s['n'] * (8 + 16),           # key+rank r; id r; bucket w
+        'k_bucket': lambda s: s['npre'] * 4 + s['n'] * (8 + 16),           # key r; id r; bucket w
         # bucket r; whole record (x,y 16, fit 8, age 4, slot 4, sex 1, z 8T) r + w (id comes from the bucket); key w
         'k_regrid': lambda s: s['n'] * (16 + (33 + 8 * T) + (41 + 8 * T) + 4),
         'k_find_mates': lambda s: s['n'] * (16 + 4 + 8 + 4),            # x,y; key; id; mate w

@@ -323,7 +323,6 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   DM(ctx, &W.cell_count, (size_t)ctx->ncell + 1);
   DM(ctx, &W.cell_start, (size_t)ctx->ncell + 1);
   DM(ctx, &W.mkey, cap);
-  DM(ctx, &W.mrank, cap);
   DM(ctx, &W.bucket, cap);
   DM(ctx, &W.skey, cap);
   DM(ctx, &W.inv, cap);

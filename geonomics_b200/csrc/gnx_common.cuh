@@ -148,7 +148,6 @@ struct Work {
   uint32_t* cell_count;
   uint32_t* cell_start;    // [ncell + 1]
   uint32_t* mkey;          // per source entry: packed mating cell (cy << 16 | cx) after movement; GNX_KEY_DEAD = dropped
-  uint32_t* mrank;         // per source entry: arrival rank in its cell (histogram atomic)
   uint4* bucket;           // per destination cell range: {source entry, packed cell, id lo, id hi}
   uint32_t* skey;          // packed mating cell of every entry of the current (grid-ordered) half
   int32_t* inv;            // ordered mode: entry of species-order ordinal i

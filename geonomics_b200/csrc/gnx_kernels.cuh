@@ -266,17 +266,13 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
         if (keyed) lin = cell_linear(land, key);
       }
       // The entries are in last step's grid order and move about one cell, so the lanes of a warp
-      // land in few distinct cells: the lanes of one cell share ONE histogram atomic (their ranks
-      // follow by lane order; the re-grid orders by id anyway).  In crowded cells this removes
-      // most of the same-address traffic that the per-lane atomics queued up in L2.
+      // land in few distinct cells: the lanes of one cell share ONE histogram update, and it is a
+      // fire-and-forget reduction (nothing here waits for its result: the arrival ranks inside a
+      // cell are handed out by k_bucket, which has the residency to hide that round trip).
       const unsigned peers = __match_any_sync(0xffffffffu, lin);
       if (keyed) {
-        const int leader = __ffs(peers) - 1;
-        uint32_t base_rank = 0u;
-        if (lane == leader) base_rank = atomicAdd(&w.cell_count[lin], (uint32_t)__popc(peers));
-        base_rank = __shfl_sync(peers, base_rank, leader);
+        if (lane == __ffs(peers) - 1) atomicAdd(&w.cell_count[lin], (uint32_t)__popc(peers));
         w.mkey[p] = key;
-        w.mrank[p] = base_rank + (uint32_t)__popc(peers & ((1u << lane) - 1u));
       }
     }
   }
@@ -284,27 +280,54 @@ __global__ void __launch_bounds__(256) k_move_key(Pop pop, Land land, Params prm
 
 // exclusive scan of the per-cell histogram -> cell_start
 struct CellScan {
-  const uint32_t* cnt;
+  uint32_t* cnt;
   uint32_t* start;
   int ncell;
   __device__ int size(const Counters*) const { return ncell; }
   __device__ u64 value(int i) const { return cnt[i]; }
-  __device__ void apply(int i, u64, u64 ex) const { start[i] = (uint32_t)ex; }
+  // the counts become k_bucket's per-cell fill cursors: back to zero once they are scanned
+  __device__ void apply(int i, u64 v, u64 ex) const {
+    start[i] = (uint32_t)ex;
+    if (v) cnt[i] = 0u;
+  }
   __device__ void total(Counters* c, u64 tot) const {
     start[ncell] = (uint32_t)tot;
     c->n_regrid = (int)tot;
   }
 };
 
-// every surviving entry announces itself in its destination cell's range (arrival order)
+// every surviving entry announces itself in its destination cell's range, in arrival order: the
+// slot inside the range comes from the cell's fill cursor (one atomic per (warp, cell), the lanes
+// of a cell ranked by lane order); the re-grid orders each range by id whatever the arrival order
 __global__ void __launch_bounds__(256) k_bucket(Pop pop, Land land, Work w, const Counters* c) {
   const int n = c->n, cur = c->cur;
-  for (int p = GTID; p < n; p += GSTRIDE) {
-    const uint32_t key = w.mkey[p];
-    if (key == GNX_KEY_DEAD) continue;
-    const unsigned long long id = (unsigned long long)pop.idx[cur][p];
-    w.bucket[w.cell_start[cell_linear(land, key)] + w.mrank[p]] =
-        make_uint4((uint32_t)p, key, (uint32_t)id, (uint32_t)(id >> 32));
+  const int lane = threadIdx.x & 31;
+  // two entries per thread and pass: the two cursor round trips overlap
+  for (int base = blockIdx.x * blockDim.x; base < n; base += 2 * GSTRIDE) {
+    int p[2];
+    uint32_t key[2], lin[2], slot[2];
+    unsigned peers[2];
+    bool keyed[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      p[u] = base + u * GSTRIDE + threadIdx.x;
+      key[u] = p[u] < n ? w.mkey[p[u]] : GNX_KEY_DEAD;
+      keyed[u] = key[u] != GNX_KEY_DEAD;
+      lin[u] = keyed[u] ? cell_linear(land, key[u]) : 0xffffffffu - (uint32_t)lane;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      peers[u] = __match_any_sync(0xffffffffu, lin[u]);
+      slot[u] = 0u;
+      if (keyed[u] && lane == __ffs(peers[u]) - 1) slot[u] = atomicAdd(&w.cell_count[lin[u]], (uint32_t)__popc(peers[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!keyed[u]) continue;
+      const uint32_t q = __shfl_sync(peers[u], slot[u], __ffs(peers[u]) - 1) + (uint32_t)__popc(peers[u] & ((1u << lane) - 1u));
+      const unsigned long long id = (unsigned long long)pop.idx[cur][p[u]];
+      w.bucket[w.cell_start[lin[u]] + q] = make_uint4((uint32_t)p[u], key[u], (uint32_t)id, (uint32_t)(id >> 32));
+    }
   }
 }
 

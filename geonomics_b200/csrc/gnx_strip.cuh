@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_strip_recv(Pop pop, Land land, Work w, 
       if (mode == 0) {
         const uint32_t key = mating_cell(land, x, y);
         w.mkey[dst] = key;
-        w.mrank[dst] = atomicAdd(&w.cell_count[cell_linear(land, key)], 1u);
+        atomicAdd(&w.cell_count[cell_linear(land, key)], 1u);
       } else {
         st->sent[dst] = 0;
       }
