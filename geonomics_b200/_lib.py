@@ -97,7 +97,7 @@ class Draws(C.Structure):
         ('pan_u', c_double_p), ('pan_R', c_uint32_p),
         ('n_mut', C.c_int64),
         ('mut_n', c_int32_p), ('mut_type_u', c_double_p), ('mut_ind_R', c_uint32_p),
-        ('mut_homol_u', c_double_p), ('mut_s', c_double_p),
+        ('mut_homol_u', c_double_p), ('mut_s', c_double_p), ('mut_alpha', c_double_p),
     ]
 
 
@@ -137,13 +137,17 @@ class Mutation(C.Structure):
         ('n_mutables', C.c_int32), ('host_mutables', c_int32_p),
         ('n_nonneut', C.c_int32), ('host_nonneut_loci', c_int32_p),
         ('n_delet', C.c_int32), ('host_delet_loci', c_int32_p), ('host_delet_s', c_double_p),
-        ('log_capacity', C.c_int32),
+        ('log_capacity', C.c_int32), ('tskit_layout', C.c_int32),
+        ('host_trait_mu', c_double_p), ('host_trait_alpha_distr', c_double_p),
+        ('host_trait_loci_idxs', c_int32_p), ('host_delet_loci_idxs', c_int32_p),
+        ('host_subsetters', C.POINTER(C.c_uint8)),
     ]
 
 
 class MutationRow(C.Structure):
     _fields_ = [('t', C.c_int64), ('individual', C.c_int64), ('locus', C.c_int32), ('row', C.c_int32),
-                ('homologue', C.c_int32), ('type', C.c_int32), ('s', C.c_double)]
+                ('homologue', C.c_int32), ('type', C.c_int32), ('s', C.c_double), ('alpha', C.c_double),
+                ('node', C.c_int32), ('reserved', C.c_int32)]
 
 
 class StepRecord(C.Structure):
@@ -225,6 +229,7 @@ SIGNATURES = {
     'gnx_mutate': (C.c_int, [_ctx]),
     'gnx_read_mutations': (C.c_int, [_ctx, C.POINTER(MutationRow), C.c_int32, c_int32_p, c_int32_p, c_int32_p,
                                      c_int32_p, c_int32_p, c_double_p, c_int32_p]),
+    'gnx_read_mutation_tables': (C.c_int, [_ctx, C.c_int32, c_int32_p, c_int32_p, c_double_p, c_int32_p, c_int32_p]),
     'gnx_stats_genotypes': (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),
     'gnx_stats_genotypes_region': (C.c_int, [_ctx, C.c_double, C.c_double, C.c_double, C.c_double,
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_double_p, c_int64_p]),

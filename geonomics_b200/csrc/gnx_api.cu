@@ -74,6 +74,12 @@ struct gnx_ctx {
   Mut mut{};
   bool mut_delet = false;
   std::vector<void*> mut_allocs;
+  // host copies of what gnx_set_traits was given (Trait.loci / alpha in the caller's order, dom):
+  // gnx_set_mutation builds the device-editable trait tables from them
+  std::vector<std::vector<int32_t>> host_trait_loci;
+  std::vector<std::vector<double>> host_trait_alpha;
+  std::vector<int8_t> host_dom;
+  Traits traits_as_set{};            // the tables gnx_set_traits built (restored when mutation lets go of them)
   std::vector<uint32_t> host_paths;   // packed recombination paths (breakpoint CSR for tskit records)
   std::vector<void*> tsk_allocs;
   Counters* d_c = nullptr;
@@ -580,9 +586,18 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   ARG(n_traits == ctx->cfg.n_traits, "n_traits differs from config");
   CK(cudaStreamSynchronize(ctx->stream));
   free_bucket(ctx->trait_allocs);
+  if (ctx->mut.enabled && ctx->mut.own_tables) {       // the mutation tables alias the old trait tables
+    free_bucket(ctx->mut_allocs);
+    memset(&ctx->mut, 0, sizeof ctx->mut);
+    ctx->mut_delet = false;
+  }
   Traits& T = ctx->traits;
   memset(&T, 0, sizeof T);
   const int Wq = ctx->Wq;
+  ctx->host_trait_loci.assign(n_traits, {});
+  ctx->host_trait_alpha.assign(n_traits, {});
+  ctx->host_dom.clear();
+  if (host_dom) ctx->host_dom.assign(host_dom, host_dom + ctx->cfg.L);
   std::vector<int32_t> te_locus;
   std::vector<double> te_alpha, te_dom;
   struct TraitEntry { int32_t off, mask; double half_alpha; };    // Traits::te_pack
@@ -605,6 +620,8 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
       const int locus = tr.host_loci[k];
       ARG(locus >= 0 && locus < ctx->cfg.L, "trait locus out of range");
       while (q < locus / 32) chunk_ptr[(size_t)t * (NW + 1) + (++q)] = (int32_t)te_locus.size();
+      ctx->host_trait_loci[t].push_back(locus);
+      ctx->host_trait_alpha[t].push_back(tr.host_alpha[k]);
       te_locus.push_back(locus);
       te_alpha.push_back(tr.host_alpha[k]);
       te_dom.push_back(host_dom ? 1.0 + (double)host_dom[locus] : 1.0);
@@ -639,6 +656,7 @@ extern "C" int gnx_set_traits(gnx_ctx* ctx, int32_t n_traits, const gnx_trait_t*
   ctx->pair_phenotype = !T.te_dom && n_traits > 0;
   for (int t = 0; t < n_traits; ++t) if (traits[t].n_loci <= 1) ctx->pair_phenotype = false;
   ctx->have_traits = true;
+  ctx->traits_as_set = T;
   return pack_env(ctx);
 }
 
@@ -649,6 +667,12 @@ extern "C" int gnx_set_recomb_paths(gnx_ctx* ctx, const uint32_t* host_packed_pa
   uint4* d = nullptr;
   const size_t n = (size_t)ctx->cfg.n_recomb_paths * ctx->Wq;
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->mut.enabled && ctx->mut.tskit_layout) {     // the mutation bookkeeping patches the old path array
+    if (ctx->mut.own_tables) ctx->traits = ctx->traits_as_set;
+    free_bucket(ctx->mut_allocs);
+    memset(&ctx->mut, 0, sizeof ctx->mut);
+    ctx->mut_delet = false;
+  }
   if (ctx->d_paths) { cudaFree(ctx->d_paths); ctx->d_paths = nullptr; }
   CK(cudaMalloc((void**)&d, std::max<size_t>(n, 1) * sizeof(uint4)));
   ctx->d_paths = d;
@@ -942,6 +966,7 @@ extern "C" int gnx_set_draws(gnx_ctx* ctx, const gnx_draws_t* dr) {
   if ((r = up(dr->mut_ind_R, nm * 4, (const void**)&D.mut_ind_R))) return r;
   if ((r = up(dr->mut_homol_u, nm * 8, (const void**)&D.mut_homol_u))) return r;
   if ((r = up(dr->mut_s, nm * 8, (const void**)&D.mut_s))) return r;
+  if ((r = up(dr->mut_alpha, nm * 8, (const void**)&D.mut_alpha))) return r;
   CK(cudaStreamSynchronize(ctx->stream));
   return GNX_OK;
 }
@@ -967,6 +992,7 @@ static int check_device_err(const Counters& h) {
   if (h.err & GNX_ERRBIT_CAPACITY) { g_last_error = "population outgrew ctx capacity"; return GNX_ERR_CAPACITY; }
   if (h.err & GNX_ERRBIT_DRAWS) { g_last_error = "injected draws exhausted (dispersal tries or mutation rows)"; return GNX_ERR_DRAWS; }
   if (h.err & GNX_ERRBIT_MUTABLES) { g_last_error = "mutation: no mutable locus left (the reference raises IndexError on _mutables.pop())"; return GNX_ERR_MUTABLES; }
+  if (h.err & GNX_ERRBIT_MUTIDX) { g_last_error = "mutation: a loci_idxs / delet_loci_idxs entry addresses a genotype row that does not exist (IndexError in the reference)"; return GNX_ERR_STATE; }
   return GNX_OK;
 }
 
@@ -1403,48 +1429,187 @@ extern "C" int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->mut.enabled && ctx->mut.own_tables) {
+    ctx->traits = ctx->traits_as_set;                  // back to the tables gnx_set_traits built
+    if (ctx->mut.tskit_layout && ctx->d_paths && !ctx->host_paths.empty())   // undo the path patches
+      CK(cudaMemcpyAsync(ctx->d_paths, ctx->host_paths.data(), ctx->host_paths.size() * 4, cudaMemcpyHostToDevice,
+                         ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   free_bucket(ctx->mut_allocs);
   memset(&ctx->mut, 0, sizeof ctx->mut);
   ctx->mut_delet = false;
-  if (!m || (m->mu_neut <= 0 && m->mu_delet <= 0)) return gnx_set_burn(ctx, ctx->burn);
+  const int nT = ctx->cfg.n_traits;
+  double trait_mu_sum = 0;
+  if (m && m->host_trait_mu)
+    for (int t = 0; t < nT; ++t) {
+      ARG(m->host_trait_mu[t] >= 0, "negative trait mutation rate");
+      trait_mu_sum += m->host_trait_mu[t];
+    }
+  const bool tskit_layout = m && m->tskit_layout;
+  if (!m || (m->mu_neut <= 0 && m->mu_delet <= 0 && trait_mu_sum <= 0 && !tskit_layout)) return gnx_set_burn(ctx, ctx->burn);
   ARG(m->mu_neut >= 0 && m->mu_delet >= 0, "negative mutation rate");
+  // genome.py:430: Trait._add_locus indexes loci_idxs, which is None when use_tskit = False
+  ARG(trait_mu_sum == 0 || tskit_layout, "trait mutation (Trait.mu > 0) raises in the reference when use_tskit = False");
+  ARG(trait_mu_sum == 0 || m->host_trait_alpha_distr, "trait mutation needs host_trait_alpha_distr");
   ARG(m->n_mutables >= 0 && (m->n_mutables == 0 || m->host_mutables), "mutables");
   ARG(m->n_nonneut >= 0 && m->n_nonneut <= ctx->cfg.L && (m->n_nonneut == 0 || m->host_nonneut_loci), "nonneut_loci");
   ARG(m->n_delet >= 0 && m->n_delet <= ctx->cfg.L && (m->n_delet == 0 || (m->host_delet_loci && m->host_delet_s)),
       "delet_loci");
+  const bool own = tskit_layout || trait_mu_sum > 0;
+  if (own) {
+    if (nT > 0 && !ctx->have_traits) { g_last_error = "gnx_set_traits must precede gnx_set_mutation"; return GNX_ERR_STATE; }
+    if (tskit_layout && !ctx->have_paths) { g_last_error = "gnx_set_recomb_paths must precede gnx_set_mutation"; return GNX_ERR_STATE; }
+  }
   const int L = ctx->cfg.L;
   Mut& M = ctx->mut;
   M.enabled = 1;
-  M.n_types = 2;
-  M.mu_tot = m->mu_neut + m->mu_delet;                 // genome.py:599-603 (trait rates are 0 here)
+  M.tskit_layout = tskit_layout ? 1 : 0;
+  M.own_tables = own ? 1 : 0;
+  M.n_types = 2 + (trait_mu_sum > 0 ? nT : 0);
+  M.mu_tot = m->mu_neut + m->mu_delet + trait_mu_sum;   // genome.py:599-603
   // genome.py:657-662: probs = mu / sum(mu); numpy choice: cdf = cumsum(p); cdf /= cdf[-1]
   {
-    const double tot = m->mu_neut + m->mu_delet;
-    const double p0 = m->mu_neut / tot, p1 = m->mu_delet / tot;
-    const double c0 = p0, c1 = p0 + p1;
-    M.cdf[0] = c0 / c1;
-    M.cdf[1] = c1 / c1;
+    double mus[2 + GNX_MAX_TRAITS] = {m->mu_neut, m->mu_delet};
+    for (int t = 0; t < nT && trait_mu_sum > 0; ++t) mus[2 + t] = m->host_trait_mu[t];
+    double tot = 0;
+    for (int k = 0; k < M.n_types; ++k) tot += mus[k];
+    ARG(tot > 0 || tskit_layout, "all mutation rates are zero");
+    double run = 0;
+    for (int k = 0; k < M.n_types; ++k) { run += tot > 0 ? mus[k] / tot : 0.0; M.cdf[k] = run; }
+    for (int k = 0; k < M.n_types; ++k) M.cdf[k] = run > 0 ? M.cdf[k] / run : 1.0;
+  }
+  for (int t = 0; t < nT; ++t) {
+    M.a_mu[t] = m->host_trait_alpha_distr ? m->host_trait_alpha_distr[3 * t] : 0.0;
+    M.a_sigma[t] = m->host_trait_alpha_distr ? m->host_trait_alpha_distr[3 * t + 1] : 0.0;
+    M.a_max[t] = m->host_trait_alpha_distr ? m->host_trait_alpha_distr[3 * t + 2] : -1.0;
   }
   M.s_shape = m->delet_s_shape;
   M.s_scale = m->delet_s_scale;
   M.L = L;
+  M.T = nT;
+  M.NW = 4 * ctx->Wq;
+  M.Wq = ctx->Wq;
   M.log_cap = std::max(m->log_capacity, 1);
   DM(ctx, &M.mutables, (size_t)std::max(L, m->n_mutables), &ctx->mut_allocs);
   DM(ctx, &M.nonneut, (size_t)L + 1, &ctx->mut_allocs);
   DM(ctx, &M.delet_loci, (size_t)L + 1, &ctx->mut_allocs);
   DM(ctx, &M.delet_s, (size_t)L + 1, &ctx->mut_allocs);
-  DM(ctx, &M.counts, 4, &ctx->mut_allocs);
+  DM(ctx, &M.delet_eff, (size_t)L + 1, &ctx->mut_allocs);
+  if (tskit_layout) DM(ctx, &M.delet_idxs, (size_t)L + 1, &ctx->mut_allocs);
+  DM(ctx, &M.counts, 4 + GNX_MAX_TRAITS, &ctx->mut_allocs);
   DM(ctx, &M.log, (size_t)M.log_cap, &ctx->mut_allocs);
   cudaStream_t s = ctx->stream;
   if (m->n_mutables) CK(cudaMemcpyAsync(M.mutables, m->host_mutables, (size_t)m->n_mutables * 4, cudaMemcpyHostToDevice, s));
   if (m->n_nonneut) CK(cudaMemcpyAsync(M.nonneut, m->host_nonneut_loci, (size_t)m->n_nonneut * 4, cudaMemcpyHostToDevice, s));
   if (m->n_delet) {
     CK(cudaMemcpyAsync(M.delet_loci, m->host_delet_loci, (size_t)m->n_delet * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(M.delet_eff, m->host_delet_loci, (size_t)m->n_delet * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(M.delet_s, m->host_delet_s, (size_t)m->n_delet * 8, cudaMemcpyHostToDevice, s));
   }
-  const int32_t counts[4] = {m->n_mutables, m->n_nonneut, m->n_delet, 0};
+  int32_t counts[4 + GNX_MAX_TRAITS] = {m->n_mutables, m->n_nonneut, m->n_delet, 0};
+  std::vector<int32_t> keep_i;
+  std::vector<double> keep_d;
+  std::vector<uint32_t> patched;
+  if (own) {
+    // rows addressed by the host's idx arrays: position of each locus in nonneut_loci when not given
+    auto row_of = [&](int locus) {
+      const int32_t* b = m->host_nonneut_loci;
+      return (int32_t)(std::lower_bound(b, b + m->n_nonneut, locus) - b);
+    };
+    if (tskit_layout) {
+      std::vector<int32_t> di(std::max(m->n_delet, 1));
+      for (int k = 0; k < m->n_delet; ++k) di[k] = m->host_delet_loci_idxs ? m->host_delet_loci_idxs[k] : row_of(m->host_delet_loci[k]);
+      for (int k = 0; k < m->n_delet; ++k) ARG(di[k] >= 0 && di[k] < m->n_nonneut, "delet_loci_idxs out of range");
+      if (m->n_delet) CK(cudaMemcpyAsync(M.delet_idxs, di.data(), (size_t)m->n_delet * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    // per-trait tables in Trait order, room for every mutable locus
+    size_t n_entries = 0;
+    for (int t = 0; t < nT; ++t) n_entries += ctx->host_trait_loci[t].size();
+    M.tcap = 1;
+    for (int t = 0; t < nT; ++t) M.tcap = std::max<int>(M.tcap, (int)ctx->host_trait_loci[t].size());
+    M.tcap += m->n_mutables + 1;
+    const size_t ecap = n_entries + (size_t)m->n_mutables + 1;
+    DM(ctx, &M.t_loci, (size_t)std::max(nT, 1) * M.tcap, &ctx->mut_allocs);
+    DM(ctx, &M.t_alpha, (size_t)std::max(nT, 1) * M.tcap, &ctx->mut_allocs);
+    DM(ctx, &M.t_idxs, (size_t)std::max(nT, 1) * M.tcap, &ctx->mut_allocs);
+    DM(ctx, &M.te_locus, ecap, &ctx->mut_allocs);
+    DM(ctx, &M.te_alpha, ecap, &ctx->mut_allocs);
+    if (ctx->traits_as_set.te_dom) DM(ctx, &M.te_dom, ecap, &ctx->mut_allocs);
+    DM(ctx, &M.te_pack, ecap, &ctx->mut_allocs);
+    DM(ctx, &M.chunk_ptr, (size_t)std::max(nT, 1) * (M.NW + 1), &ctx->mut_allocs);
+    if (ctx->traits_as_set.te_dom && !ctx->host_dom.empty()) {
+      std::vector<double> d1(L);
+      for (int l = 0; l < L; ++l) d1[l] = 1.0 + (double)ctx->host_dom[l];
+      double* dd = nullptr;
+      DM(ctx, &dd, (size_t)L, &ctx->mut_allocs);
+      CK(cudaMemcpyAsync(dd, d1.data(), (size_t)L * 8, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+      M.dom1p = dd;
+    }
+    size_t off = 0;
+    for (int t = 0; t < nT; ++t) {
+      const auto& hl = ctx->host_trait_loci[t];      // sorted by locus in gnx_set_traits = Trait.loci order
+      const auto& ha = ctx->host_trait_alpha[t];
+      const int n = (int)hl.size();
+      counts[4 + t] = n;
+      std::vector<int32_t> idxs(std::max(n, 1));
+      for (int k = 0; k < n; ++k) {
+        idxs[k] = (tskit_layout && m->host_trait_loci_idxs) ? m->host_trait_loci_idxs[off + k] : row_of(hl[k]);
+        ARG(!tskit_layout || (idxs[k] >= 0 && idxs[k] < m->n_nonneut), "trait loci_idxs out of range");
+      }
+      off += n;
+      if (n) {
+        CK(cudaMemcpyAsync(M.t_loci + (size_t)t * M.tcap, hl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(M.t_alpha + (size_t)t * M.tcap, ha.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(M.t_idxs + (size_t)t * M.tcap, idxs.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+      }
+    }
+    if (tskit_layout) {
+      // cached paths: as simulated (the source of later patches) and, at the current genotype rows, the
+      // reference's subsetters (genome.py:133-160 leaves them different from the path where a breakpoint
+      // sits on a mutated locus)
+      const size_t nw = ctx->host_paths.size();
+      uint4* orig = nullptr;
+      DM(ctx, &orig, nw / 4, &ctx->mut_allocs);
+      CK(cudaMemcpyAsync(orig, ctx->host_paths.data(), nw * 4, cudaMemcpyHostToDevice, s));
+      M.paths_orig = orig;
+      M.paths = (uint4*)ctx->d_paths;
+      M.n_paths = ctx->cfg.n_recomb_paths;
+      patched = ctx->host_paths;
+      if (m->host_subsetters) {
+        const size_t W32 = (size_t)4 * ctx->Wq;
+        for (int pth = 0; pth < M.n_paths; ++pth)
+          for (int j = 0; j < m->n_nonneut; ++j) {
+            const int l = m->host_nonneut_loci[j];
+            const uint32_t b = m->host_subsetters[(size_t)pth * m->n_nonneut + j] & 1u;
+            uint32_t& w = patched[(size_t)pth * W32 + (l >> 5)];
+            w = (w & ~(1u << (l & 31))) | (b << (l & 31));
+          }
+      }
+      CK(cudaMemcpyAsync(ctx->d_paths, patched.data(), nw * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+  }
   CK(cudaMemcpyAsync(M.counts, counts, sizeof counts, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
+  if (own) {
+    // the device-editable tables replace the ones gnx_set_traits built
+    k_mut_rebuild<<<1, 32, 0, s>>>(M, ctx->d_c);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    Traits& T = ctx->traits;
+    T.te_locus = M.te_locus;
+    T.te_alpha = M.te_alpha;
+    T.te_dom = M.te_dom;
+    T.te_pack = M.te_pack;
+    T.chunk_ptr = M.chunk_ptr;
+    T.n_loci_dev = M.counts + 4;
+    // a monogenic trait may turn polygenic inside a graph-launched step: the per-pair phenotype walk of
+    // k_gametes assumes polygenic traits, which stays true (loci are only ever added)
+  }
   ctx->mut_delet = m->mu_delet > 0 || m->n_delet > 0;
   return gnx_set_burn(ctx, ctx->burn);                 // refresh prm.selection
 }
@@ -1453,9 +1618,47 @@ extern "C" int gnx_mutate(gnx_ctx* ctx) {
   ARG(ctx, "null ctx");
   USE_DEVICE(ctx);
   if (!ctx->mut.enabled || ctx->burn) return GNX_OK;
+  if (ctx->mut.mu_tot <= 0) return GNX_OK;             // tskit layout without mutation: nothing to draw
   PROF(ctx, "k_mutate");
-  k_mutate<<<1, 32, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->mut, ctx->d_c);
+  k_mutate<<<1, 256, 0, ctx->stream>>>(ctx->pop, ctx->prm, ctx->traits, ctx->draws, ctx->mut, ctx->d_c,
+                                       ctx->tsk.enabled ? 1 : 0);
   LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+extern "C" int gnx_read_mutation_tables(gnx_ctx* ctx, int32_t trait, int32_t* n_loci, int32_t* host_loci,
+                                        double* host_alpha, int32_t* host_loci_idxs, int32_t* host_delet_loci_idxs) {
+  ARG(ctx, "null ctx");
+  USE_DEVICE(ctx);
+  if (!ctx->mut.enabled) { g_last_error = "mutation not enabled"; return GNX_ERR_STATE; }
+  Mut& M = ctx->mut;
+  cudaStream_t s = ctx->stream;
+  int32_t counts[4 + GNX_MAX_TRAITS];
+  CK(cudaMemcpyAsync(counts, M.counts, sizeof counts, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (trait >= 0) {
+    ARG(trait < ctx->cfg.n_traits, "trait index");
+    if (M.own_tables) {
+      const int n = counts[4 + trait];
+      if (n_loci) *n_loci = n;
+      if (host_loci && n) CK(cudaMemcpyAsync(host_loci, M.t_loci + (size_t)trait * M.tcap, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+      if (host_alpha && n) CK(cudaMemcpyAsync(host_alpha, M.t_alpha + (size_t)trait * M.tcap, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+      if (host_loci_idxs && n) CK(cudaMemcpyAsync(host_loci_idxs, M.t_idxs + (size_t)trait * M.tcap, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    } else {
+      const auto& hl = ctx->host_trait_loci[trait];
+      const int n = (int)hl.size();
+      if (n_loci) *n_loci = n;
+      for (int k = 0; k < n; ++k) {
+        if (host_loci) host_loci[k] = hl[k];
+        if (host_alpha) host_alpha[k] = ctx->host_trait_alpha[trait][k];
+        if (host_loci_idxs) host_loci_idxs[k] = hl[k];
+      }
+    }
+  }
+  if (host_delet_loci_idxs && counts[2] > 0)
+    CK(cudaMemcpyAsync(host_delet_loci_idxs, M.tskit_layout ? M.delet_idxs : M.delet_loci, (size_t)counts[2] * 4,
+                       cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return GNX_OK;
 }
 

@@ -59,6 +59,8 @@ struct Counters {
 #define GNX_ERRBIT_GS 4
 #define GNX_ERRBIT_MUTABLES 8     // _mutables.pop() on an empty list
 #define GNX_ERRBIT_MUTLOG 16      // mutation log full (rows dropped, bookkeeping still exact)
+#define GNX_ERRBIT_MUTIDX 32      // a stale loci_idxs / delet_loci_idxs entry addresses a row that does not exist
+                                  // (IndexError in the reference)
 
 // Double-buffered scalar SoA + slot-indexed genome rows.  The order of the entries is the
 // MATING-GRID order (cell key, then individual id) established by the re-grid of every step;
@@ -91,6 +93,8 @@ struct Traits {
   const void* te_pack;         // per entry {int32 byte offset of the staged word pair, uint32 bit mask, f64 alpha/2}
   const int32_t* chunk_ptr;
   int32_t n_loci[GNX_MAX_TRAITS];
+  const int32_t* n_loci_dev;   // non-NULL once mutation owns the tables (trait mutation / tskit layout): the
+                               // loci counts live on the device and grow inside the graph-launched step
   double phi[GNX_MAX_TRAITS];
   const double* phi_rast[GNX_MAX_TRAITS];
   double gamma[GNX_MAX_TRAITS];
@@ -259,25 +263,46 @@ struct DevDraws {
   const uint32_t* mut_ind_R;
   const double* mut_homol_u;
   const double* mut_s;
+  const double* mut_alpha;
 };
 
-// a13 mutation bookkeeping (ops/mutation.py; genome.py:753-788).  All arrays are device
+// a13 mutation bookkeeping (ops/mutation.py; genome.py:416-437, 753-788).  All arrays are device
 // resident and edited by the single thread of k_mutate.
 struct Mut {
   int32_t enabled;
-  int32_t n_types;                 // neutral, deleterious (trait mutation is rejected at setup)
+  int32_t n_types;                 // neutral, deleterious, then one per trait when any Trait.mu > 0
+  int32_t tskit_layout;            // use_tskit = True semantics (include/gnx_b200.h)
+  int32_t own_tables;              // k_mutate rebuilds the trait tables of `Traits` (tskit layout / trait mutation)
   double mu_tot;                   // genome.py:599-603
-  double cdf[2];                   // cumulative type probabilities (genome.py:650-663)
+  double cdf[2 + GNX_MAX_TRAITS];  // cumulative type probabilities (genome.py:650-663)
   double s_shape, s_scale;         // genome.py:690-693
+  double a_mu[GNX_MAX_TRAITS], a_sigma[GNX_MAX_TRAITS], a_max[GNX_MAX_TRAITS];   // genome.py:666-687
   int32_t* mutables;               // popped from the end
-  int32_t* nonneut;                // ascending, capacity L
-  int32_t* delet_loci;             // ascending, capacity L
+  int32_t* nonneut;                // ascending, capacity L + 1
+  int32_t* delet_loci;             // ascending, capacity L + 1
   double* delet_s;
-  int32_t* counts;                 // [0] n_mutables [1] n_nonneut [2] n_delet [3] n_log
+  int32_t* delet_idxs;             // gen_arch.delet_loci_idxs as written (tskit layout), else NULL
+  int32_t* delet_eff;              // the bit every deleterious entry reads: nonneut[delet_idxs[k]] / delet_loci[k]
+  int32_t* counts;                 // [0] n_mutables [1] n_nonneut [2] n_delet [3] n_log [4 + t] n_loci of trait t
+  int32_t* t_loci;                 // [T][tcap] Trait.loci (ascending), Trait.alpha, Trait.loci_idxs (as written)
+  double* t_alpha;
+  int32_t* t_idxs;
+  int32_t tcap, T;
+  const double* dom1p;             // [L] 1 + dom[locus], or NULL
+  int32_t* te_locus;               // writable aliases of the Traits tables (capacity: all entries + n_mutables)
+  double* te_alpha;
+  double* te_dom;
+  int4* te_pack;
+  int32_t* chunk_ptr;
+  int32_t NW;                      // 32-bit words per homologue
+  uint4* paths;                    // cached recombination paths the gamete kernel reads (patched, tskit layout)
+  const uint4* paths_orig;         // as simulated: bit l = (#breakpoints <= l) % 2
+  int32_t n_paths, Wq;
   gnx_mutation_row_t* log;
   int32_t log_cap;
   int32_t L;
 };
+#define GNX_MUT_MAX_NEW 64          // non-neutral mutations per step whose path bits are patched in one launch
 
 struct Params {
   gnx_config_t c;

@@ -968,6 +968,9 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
 
 // phenotype contribution of one 128-bit unit pair (h0, h1) of trait t.  The trait table is
 // a CSR over 32-bit words (4 per unit), so the word select is compile-time.
+__device__ __forceinline__ int trait_n_loci(const Traits& tr, int t) {
+  return tr.n_loci_dev ? __ldg(&tr.n_loci_dev[t]) : trait_n_loci(tr, t);
+}
 __device__ __forceinline__ double trait_word(const Traits& tr, int s, int e, uint32_t w0, uint32_t w1,
                                              bool polygenic) {
   double acc = 0.0;
@@ -995,7 +998,7 @@ __device__ __forceinline__ double trait_partial(const Traits& tr, int t, int q, 
   const int p0 = __ldg(ptr), p4 = __ldg(ptr + 4);
   if (p0 == p4) return 0.0;
   const int p1 = __ldg(ptr + 1), p2 = __ldg(ptr + 2), p3 = __ldg(ptr + 3);
-  const bool poly = tr.n_loci[t] > 1;
+  const bool poly = trait_n_loci(tr, t) > 1;
   return trait_word(tr, p0, p1, h0.x, h1.x, poly) + trait_word(tr, p1, p2, h0.y, h1.y, poly) +
          trait_word(tr, p2, p3, h0.z, h1.z, poly) + trait_word(tr, p3, p4, h0.w, h1.w, poly);
 }
@@ -1214,7 +1217,7 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
       for (int tt = 0; tt < NT; ++tt) {
         if (tt < T) {
           const int ks = __ldg(&tr.chunk_ptr[tt * (NW + 1)]), ke = __ldg(&tr.chunk_ptr[tt * (NW + 1) + NW]);
-          const bool poly = tr.n_loci[tt] > 1;
+          const bool poly = trait_n_loci(tr, tt) > 1;
           double acc = 0.0;
           if (fast_trait && poly) {
             // geno * alpha = (b0 + b1) * (alpha / 2), exact (selection.py:30-33, 43-44)
@@ -1249,7 +1252,7 @@ __global__ void __launch_bounds__(256, GNX_GAM_MINB) k_gametes(Pop pop, Params p
         double v = zacc[tt];
 #pragma unroll
         for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
-        if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
+        if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (trait_n_loci(tr, tt) > 1) ? 0.5 + v : v;
       }
     }
   }
@@ -1396,7 +1399,7 @@ __global__ void __launch_bounds__(GT_THREADS) k_gametes_tma(Pop pop, Params prm,
             double v = zacc[tt];
 #pragma unroll
             for (int d = GW / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(gmask, v, d);
-            if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (tr.n_loci[tt] > 1) ? 0.5 + v : v;
+            if (lane == 0) pop.z[cur][(size_t)tt * pop.cap + n + o] = (trait_n_loci(tr, tt) > 1) ? 0.5 + v : v;
           }
         }
       }
@@ -1602,19 +1605,28 @@ __global__ void __launch_bounds__(256) k_phenotype_all(Pop pop, Traits tr, const
         uint4 h0 = Gi[q], h1 = Gi[Wq + q];
         acc += trait_partial(tr, tt, q, Wq, h0, h1);
       }
-      pop.z[cur][(size_t)tt * pop.cap + i] = (tr.n_loci[tt] > 1) ? 0.5 + acc : acc;
+      pop.z[cur][(size_t)tt * pop.cap + i] = (trait_n_loci(tr, tt) > 1) ? 0.5 + acc : acc;
     }
   }
 }
 
 // ========================================================================================
-// a13: mutation of this step's offspring (ops/mutation.py:169-206), use_tskit = False.
-//   One thread: the number of mutations in a run is bounded by the mutable loci (infinite
-//   sites, genome.py:1101-1104), and every event edits small sorted tables in order.
+// a13: mutation of this step's offspring (ops/mutation.py:169-206).
+//   One thread does the bookkeeping: the number of mutations in a run is bounded by the mutable
+//   loci (infinite sites, genome.py:1101-1104), and every event edits small sorted tables in order.
 //   neutral (mutation.py:62-86): consumes a locus, genotypes untouched.
 //   deleterious (mutation.py:90-131, 156-166; genome.py:753-788): locus joins nonneut_loci at
-//   idx and (delet_loci, delet_s); the offspring's genotype ROW idx of the drawn homologue is
-//   set to 1 (mutation.py:117 as written) and its phenotype recomputed (species.py:929).
+//   idx and (delet_loci, delet_s).
+//   trait (mutation.py:135-144; genome.py:666-687, 416-437): locus joins nonneut_loci and the
+//   trait's (loci, alpha, loci_idxs); tskit layout only (the reference raises otherwise).
+//   use_tskit = False: the offspring's genotype ROW idx of the drawn homologue is set to 1
+//   (mutation.py:117 as written).  tskit layout: the reference inserts a zero row at idx into every
+//   individual and sets g[idx, homologue]; here rows are bits by locus, so bit `locus` is set, the
+//   index arrays are kept as the reference leaves them (loci_idxs shifted only inside the mutated
+//   trait, delet_loci_idxs never) and the trait tables are rebuilt to read bit
+//   nonneut[idxs[k]].  The whole CTA then patches bit `locus` of every cached path to the
+//   homologue the path is on in FRONT of the locus (genome.py:133-160: bisect_left of the
+//   breakpoints), which is bit locus - 1 of the path as simulated.
 // ========================================================================================
 __device__ inline int lower_bound_i32(const int32_t* a, int n, int v) {
   int lo = 0, hi = n;
@@ -1625,73 +1637,198 @@ __device__ inline int lower_bound_i32(const int32_t* a, int n, int v) {
   return lo;
 }
 
-__global__ void k_mutate(Pop pop, Params prm, Traits tr, DevDraws dr, Mut mu, Counters* c) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int B = c->B, n = c->n, cur = c->cur, Wq = pop.Wq;
-  if (B == 0) return;
-  RngStream g(prm.seed_lo, prm.seed_hi, c->max_idx + 1, SITE_MUTATE, c->t);
-  const long long n_muts = dr.mut_n ? (long long)dr.mut_n[0]
-                                    : sample_binomial_wait(g, (long long)B * mu.L, mu.mu_tot);   // mutation.py:172-173
-  for (long long m = 0; m < n_muts; ++m) {
-    if (dr.mut_n && m >= dr.n_mut) { c->err |= GNX_ERRBIT_DRAWS; break; }
-    // genome.py:650-663: choice(types, p) = searchsorted(cdf, u, side='right')
-    const double ut = dr.mut_type_u ? dr.mut_type_u[m] : g.uniform();
-    const int type = ut < mu.cdf[0] ? 0 : 1;
-    if (mu.counts[0] == 0) { c->err |= GNX_ERRBIT_MUTABLES; break; }    // list.pop() on an empty list
-    const double s_raw = type == 1 ? (dr.mut_s ? dr.mut_s[m] : sample_gamma(g, mu.s_shape, mu.s_scale)) : 0.0;
-    const double sel = fmin(s_raw, 1.0);                                  // genome.py:692
-    const int locus = mu.mutables[--mu.counts[0]];                        // mutation.py:73 / :95
-    const uint32_t R = dr.mut_ind_R ? dr.mut_ind_R[m] : g.u32();
-    // r.choice(offspring): the list holds the new ids in DESCENDING order (species.py:615-622)
-    const int o = B - 1 - (int)choose_k(R, (uint32_t)B);
-    const double uh = dr.mut_homol_u ? dr.mut_homol_u[m] : g.uniform();
-    const int homol = uh < 0.5 ? 1 : 0;                                   // r.binomial(1, 0.5)
-    int row = -1;
-    if (type == 1) {
-      // genome.py:753-788 _add_nonneut_locus
-      int nn = mu.counts[1];
-      const int idx = lower_bound_i32(mu.nonneut, nn, locus);
-      for (int k = nn; k > idx; --k) mu.nonneut[k] = mu.nonneut[k - 1];
-      mu.nonneut[idx] = locus;
-      mu.counts[1] = nn + 1;
-      int nd = mu.counts[2];
-      const int di = lower_bound_i32(mu.delet_loci, nd, locus);
-      for (int k = nd; k > di; --k) { mu.delet_loci[k] = mu.delet_loci[k - 1]; mu.delet_s[k] = mu.delet_s[k - 1]; }
-      mu.delet_loci[di] = locus;
-      mu.delet_s[di] = sel;
-      mu.counts[2] = nd + 1;
-      // mutation.py:117: spp[individ].g[idx, homol] = 1
-      row = idx;
+// the trait tables of `Traits` from the per-trait (loci, alpha, idxs) arrays: entries of a trait
+// sorted by the bit they read, CSR over 32-bit words (same layout as gnx_set_traits builds)
+__device__ inline void mut_rebuild_tables(const Mut& mu, Counters* c) {
+  const int nn = mu.counts[1];
+  int base = 0;
+  for (int t = 0; t < mu.T; ++t) {
+    const int n = mu.counts[4 + t];
+    const int32_t* tl = mu.t_loci + (size_t)t * mu.tcap;
+    const double* ta = mu.t_alpha + (size_t)t * mu.tcap;
+    const int32_t* ti = mu.t_idxs + (size_t)t * mu.tcap;
+    for (int k = 0; k < n; ++k) {
+      int eff = tl[k];
+      if (mu.tskit_layout) {
+        int r = ti[k];
+        if (r < 0 || r >= nn) { c->err |= GNX_ERRBIT_MUTIDX; r = r < 0 ? 0 : nn - 1; }   // IndexError in the reference
+        eff = mu.nonneut[r];
+      }
+      const double al = ta[k];
+      const double dm = mu.dom1p ? mu.dom1p[tl[k]] : 1.0;      // selection.py:37: dom[trait.loci]
+      int j = base + k;                                         // stable insertion by the bit read
+      while (j > base && mu.te_locus[j - 1] > eff) {
+        mu.te_locus[j] = mu.te_locus[j - 1];
+        mu.te_alpha[j] = mu.te_alpha[j - 1];
+        if (mu.te_dom) mu.te_dom[j] = mu.te_dom[j - 1];
+        --j;
+      }
+      mu.te_locus[j] = eff;
+      mu.te_alpha[j] = al;
+      if (mu.te_dom) mu.te_dom[j] = dm;
+    }
+    int32_t* cp = mu.chunk_ptr + (size_t)t * (mu.NW + 1);
+    int q = 0;
+    cp[0] = base;
+    for (int k = 0; k < n; ++k) {
+      const int eff = mu.te_locus[base + k];
+      while (q < (eff >> 5)) cp[++q] = base + k;
+      const double ha = 0.5 * mu.te_alpha[base + k];
+      mu.te_pack[base + k] = make_int4((eff >> 5) * 8, (int)(1u << (eff & 31)), __double2loint(ha), __double2hiint(ha));
+    }
+    while (q < mu.NW) cp[++q] = base + n;
+    base += n;
+  }
+  // the bit every deleterious entry reads
+  const int nd = mu.counts[2];
+  for (int k = 0; k < nd; ++k) {
+    int eff = mu.delet_loci[k];
+    if (mu.tskit_layout) {
+      int r = mu.delet_idxs[k];
+      if (r < 0 || r >= nn) { c->err |= GNX_ERRBIT_MUTIDX; r = r < 0 ? 0 : nn - 1; }
+      eff = mu.nonneut[r];
+    }
+    mu.delet_eff[k] = eff;
+  }
+}
+
+__global__ void k_mut_rebuild(Mut mu, Counters* c) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mut_rebuild_tables(mu, c);
+}
+
+__global__ void __launch_bounds__(256) k_mutate(Pop pop, Params prm, Traits tr, DevDraws dr, Mut mu, Counters* c, int tsk_on) {
+  __shared__ int new_loci[GNX_MUT_MAX_NEW];
+  __shared__ int n_new;
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x == 0) {
+    n_new = 0;
+    const int B = c->B, n = c->n, cur = c->cur, Wq = pop.Wq;
+    RngStream g(prm.seed_lo, prm.seed_hi, c->max_idx + 1, SITE_MUTATE, c->t);
+    const long long n_muts = B == 0 ? 0 : (dr.mut_n ? (long long)dr.mut_n[0]
+                                      : sample_binomial_wait(g, (long long)B * mu.L, mu.mu_tot));   // mutation.py:172-173
+    for (long long m = 0; m < n_muts; ++m) {
+      if (dr.mut_n && m >= dr.n_mut) { c->err |= GNX_ERRBIT_DRAWS; break; }
+      // genome.py:650-663: choice(types, p) = searchsorted(cdf, u, side='right')
+      const double ut = dr.mut_type_u ? dr.mut_type_u[m] : g.uniform();
+      int type = 0;
+      while (type < mu.n_types - 1 && ut >= mu.cdf[type]) ++type;
+      if (mu.counts[0] == 0) { c->err |= GNX_ERRBIT_MUTABLES; break; }    // list.pop() on an empty list
+      if (type >= 1 && mu.tskit_layout && n_new >= GNX_MUT_MAX_NEW) { c->err |= GNX_ERRBIT_CAPACITY; break; }
+      const double s_raw = type == 1 ? (dr.mut_s ? dr.mut_s[m] : sample_gamma(g, mu.s_shape, mu.s_scale)) : 0.0;
+      const double sel = fmin(s_raw, 1.0);                                  // genome.py:692
+      const int locus = mu.mutables[--mu.counts[0]];                        // mutation.py:73 / :95
+      const uint32_t R = dr.mut_ind_R ? dr.mut_ind_R[m] : g.u32();
+      // r.choice(offspring): the list holds the new ids in DESCENDING order (species.py:615-622)
+      const int o = B - 1 - (int)choose_k(R, (uint32_t)B);
       const int i = n + o;
-      uint32_t* hw = reinterpret_cast<uint32_t*>(pop.G + ((size_t)pop.gslot[cur][i] * 2 + homol) * Wq);
-      hw[row >> 5] |= 1u << (row & 31);
-      // species.py:929 _set_z_individ
-      const uint4* Gi = pop.G + (size_t)pop.gslot[cur][i] * 2 * Wq;
-      for (int tt = 0; tt < pop.T; ++tt) {
-        double acc = 0.0;
-        for (int q = 0; q < Wq; ++q) {
-          const int ks = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q], ke = tr.chunk_ptr[tt * (4 * Wq + 1) + 4 * q + 4];
-          if (ks == ke) continue;
-          const uint4 h0 = Gi[q], h1 = Gi[Wq + q];
-          acc += trait_partial(tr, tt, q, Wq, h0, h1);
+      int row = -1;
+      double alpha = 0.0;
+      if (type >= 1) {
+        // genome.py:753-788 _add_nonneut_locus
+        int nn = mu.counts[1];
+        const int idx = lower_bound_i32(mu.nonneut, nn, locus);
+        for (int k = nn; k > idx; --k) mu.nonneut[k] = mu.nonneut[k - 1];
+        mu.nonneut[idx] = locus;
+        mu.counts[1] = nn + 1;
+        if (type == 1) {
+          int nd = mu.counts[2];
+          const int di = lower_bound_i32(mu.delet_loci, nd, locus);
+          for (int k = nd; k > di; --k) {
+            mu.delet_loci[k] = mu.delet_loci[k - 1];
+            mu.delet_s[k] = mu.delet_s[k - 1];
+            if (mu.delet_idxs) mu.delet_idxs[k] = mu.delet_idxs[k - 1];
+          }
+          mu.delet_loci[di] = locus;
+          mu.delet_s[di] = sel;
+          if (mu.delet_idxs) mu.delet_idxs[di] = idx;                       // genome.py:779-782: nothing is shifted
+          mu.counts[2] = nd + 1;
+        } else {
+          const int t = type - 2;
+          // genome.py:666-687 _draw_trait_alpha(n = 1)
+          if (mu.a_sigma[t] == 0.0) {
+            alpha = mu.a_mu[t];
+          } else {
+            alpha = dr.mut_alpha ? dr.mut_alpha[m] : mu.a_mu[t] + mu.a_sigma[t] * g.normal();
+            if (mu.a_max[t] >= 0.0) alpha = fmin(fmax(alpha, -mu.a_max[t]), mu.a_max[t]);
+          }
+          int nt = mu.counts[4 + t];
+          if (nt == 1) alpha = fabs(alpha);
+          // genome.py:416-437 Trait._add_locus
+          int32_t* tl = mu.t_loci + (size_t)t * mu.tcap;
+          double* ta = mu.t_alpha + (size_t)t * mu.tcap;
+          int32_t* ti = mu.t_idxs + (size_t)t * mu.tcap;
+          const int ip = lower_bound_i32(tl, nt, locus);
+          for (int k = nt; k > ip; --k) { tl[k] = tl[k - 1]; ta[k] = ta[k - 1]; ti[k] = ti[k - 1] + 1; }
+          tl[ip] = locus;
+          ta[ip] = alpha;
+          ti[ip] = idx;
+          mu.counts[4 + t] = nt + 1;
         }
-        pop.z[cur][(size_t)tt * pop.cap + i] = (tr.n_loci[tt] > 1) ? 0.5 + acc : acc;
+      }
+      const double uh = dr.mut_homol_u ? dr.mut_homol_u[m] : g.uniform();
+      const int homol = uh < 0.5 ? 1 : 0;                                   // r.binomial(1, 0.5)
+      if (type >= 1) {
+        if (mu.own_tables) mut_rebuild_tables(mu, c);
+        else                                   // use_tskit = False: every entry reads the row of its locus
+          for (int k = 0; k < mu.counts[2]; ++k) mu.delet_eff[k] = mu.delet_loci[k];
+        // mutation.py:117: spp[individ].g[idx, homol] = 1
+        row = lower_bound_i32(mu.nonneut, mu.counts[1], locus);
+        const int bit = mu.tskit_layout ? locus : row;
+        uint32_t* hw = reinterpret_cast<uint32_t*>(pop.G + ((size_t)pop.gslot[cur][i] * 2 + homol) * Wq);
+        hw[bit >> 5] |= 1u << (bit & 31);
+        // species.py:929 _set_z_individ
+        const uint4* Gi = pop.G + (size_t)pop.gslot[cur][i] * 2 * Wq;
+        for (int tt = 0; tt < pop.T; ++tt) {
+          double acc = 0.0;
+          const int nl = mu.own_tables ? mu.counts[4 + tt] : tr.n_loci[tt];
+          for (int q = 0; q < Wq; ++q) {
+            const int* ptr = tr.chunk_ptr + tt * (4 * Wq + 1) + 4 * q;
+            if (ptr[0] == ptr[4]) continue;
+            const uint4 h0 = Gi[q], h1 = Gi[Wq + q];
+            const uint32_t w0[4] = {h0.x, h0.y, h0.z, h0.w}, w1[4] = {h1.x, h1.y, h1.z, h1.w};
+            for (int ww = 0; ww < 4; ++ww)
+              for (int k = ptr[ww]; k < ptr[ww + 1]; ++k) {                 // plain loads: the tables were just rewritten
+                const int sh = tr.te_locus[k] & 31;
+                double geno = 0.5 * (double)((int)((w0[ww] >> sh) & 1u) + (int)((w1[ww] >> sh) & 1u));
+                if (tr.te_dom) geno = fmin(geno * tr.te_dom[k], 1.0);
+                acc += nl > 1 ? geno * tr.te_alpha[k] : geno;
+              }
+          }
+          pop.z[cur][(size_t)tt * pop.cap + i] = nl > 1 ? 0.5 + acc : acc;
+        }
+        if (mu.tskit_layout) new_loci[n_new++] = locus;
+      }
+      const int nl = mu.counts[3];
+      if (nl < mu.log_cap) {
+        gnx_mutation_row_t r;
+        r.t = c->t;
+        r.individual = c->max_idx + 1 + o;
+        r.locus = locus;
+        r.row = row;
+        r.homologue = homol;
+        r.type = type;
+        r.s = sel;
+        r.alpha = alpha;
+        r.node = tsk_on ? pop.node[homol][cur][i] : -1;                     // mutation.py:46
+        r.reserved = 0;
+        mu.log[nl] = r;
+        mu.counts[3] = nl + 1;
+      } else {
+        c->err |= GNX_ERRBIT_MUTLOG;
       }
     }
-    const int nl = mu.counts[3];
-    if (nl < mu.log_cap) {
-      gnx_mutation_row_t r;
-      r.t = c->t;
-      r.individual = c->max_idx + 1 + o;
-      r.locus = locus;
-      r.row = row;
-      r.homologue = homol;
-      r.type = type;
-      r.s = sel;
-      mu.log[nl] = r;
-      mu.counts[3] = nl + 1;
-    } else {
-      c->err |= GNX_ERRBIT_MUTLOG;
+  }
+  __syncthreads();
+  // genome.py:133-160 _update_subsetters: the inserted homologue is the one the path is on in front of the locus
+  if (mu.tskit_layout && n_new > 0) {
+    for (int pth = threadIdx.x; pth < mu.n_paths; pth += blockDim.x) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(mu.paths_orig + (size_t)pth * mu.Wq);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(mu.paths + (size_t)pth * mu.Wq);
+      for (int k = 0; k < n_new; ++k) {
+        const int l = new_loci[k];
+        const uint32_t b = l > 0 ? (src[(l - 1) >> 5] >> ((l - 1) & 31)) & 1u : 0u;
+        dst[l >> 5] = (dst[l >> 5] & ~(1u << (l & 31))) | (b << (l & 31));
+      }
     }
   }
 }
@@ -2246,7 +2383,7 @@ __global__ void __launch_bounds__(256, GNX_DEATH_MINB) k_death(Pop pop, Land lan
           const uint32_t* g1 = g0 + 4 * pop.Wq;
           double wd = 1.0;
           for (int k = 0; k < nd; ++k) {
-            const int loc = mu.delet_loci[k];
+            const int loc = mu.delet_eff[k];        // use_tskit: row delet_loci_idxs[k] (selection.py:86-88)
             const int dosage = (int)((g0[loc >> 5] >> (loc & 31)) & 1u) + (int)((g1[loc >> 5] >> (loc & 31)) & 1u);
             wd *= 1.0 - (double)dosage * mu.delet_s[k];
           }

@@ -150,6 +150,7 @@ class DeviceSpecies:
             arr[t].univ_adv = int(bool(tr['univ_adv']))
         _lib.check(self._L.gnx_set_traits(self._ctx, len(traits), arr, _ptr(dom, _lib.c_int8_p)),
                    'gnx_set_traits')
+        self._trait_sizes = [len(tr['loci']) for tr in traits]
 
     def set_debug(self, on=True):
         """Keep n_nbrs / death_p / disp_tries / n_pairs raster readable (parity tests)."""
@@ -277,7 +278,7 @@ class DeviceSpecies:
         d.n = int(n)
         # mutation draws (their own row count: one row per mutation)
         if draws.get('mut_n') is not None:
-            nm = max([np.asarray(draws[k]).size for k in ('mut_type_u', 'mut_ind_R', 'mut_homol_u', 'mut_s')
+            nm = max([np.asarray(draws[k]).size for k in ('mut_type_u', 'mut_ind_R', 'mut_homol_u', 'mut_s', 'mut_alpha')
                       if draws.get(k) is not None] + [0])
             n, n_rows = nm, n
             keep.append(np.ascontiguousarray(np.asarray(draws['mut_n']).reshape(-1)[:1], dtype=np.int32))
@@ -286,15 +287,22 @@ class DeviceSpecies:
             put('mut_ind_R', 'mut_ind_R', np.uint32, _lib.c_uint32_p)
             put('mut_homol_u', 'mut_homol_u', np.float64, _lib.c_double_p)
             put('mut_s', 'mut_s', np.float64, _lib.c_double_p)
+            put('mut_alpha', 'mut_alpha', np.float64, _lib.c_double_p)
             d.n_mut = int(nm)
             n = n_rows
         _lib.check(self._L.gnx_set_draws(self._ctx, C.byref(d)), 'gnx_set_draws')
 
     # ---- a13 mutation ------------------------------------------------------------------------
     def set_mutation(self, mu_neut, mu_delet, mutables, nonneut_loci, delet_loci=(), delet_s=(),
-                     delet_s_shape=0.2, delet_s_scale=0.2, log_capacity=4096):
-        """Enable mutation of each step's offspring (ops/mutation.py:169-206, use_tskit=False).
-        mutables: the shuffled list of mutable loci (genome.py:1101-1104), popped from its end."""
+                     delet_s_shape=0.2, delet_s_scale=0.2, log_capacity=4096, tskit_layout=False,
+                     trait_mus=None, trait_alpha_distr=None, trait_loci_idxs=None, delet_loci_idxs=None,
+                     subsetters=None):
+        """Enable mutation of each step's offspring (ops/mutation.py:169-206).
+        mutables: the shuffled list of mutable loci (genome.py:1101-1104), popped from its end.
+        tskit_layout: gen_arch.use_tskit = True semantics (genotype rows = non-neutral loci; see
+        include/gnx_b200.h); trait_mus [T] with trait_alpha_distr [T][3] (alpha_distr_mu, alpha_distr_sigma,
+        max_alpha_mag or None) enables trait mutation; trait_loci_idxs (list of arrays, Trait.loci_idxs),
+        delet_loci_idxs and subsetters [n_paths, n_nonneut] carry the reference's arrays as it left them."""
         m = _lib.Mutation()
         m.mu_neut, m.mu_delet = float(mu_neut), float(mu_delet)
         m.delet_s_shape, m.delet_s_scale = float(delet_s_shape), float(delet_s_scale)
@@ -306,11 +314,47 @@ class DeviceSpecies:
         m.n_nonneut, m.host_nonneut_loci = len(nn), _ptr(nn, _lib.c_int32_p)
         m.n_delet, m.host_delet_loci, m.host_delet_s = len(dl), _ptr(dl, _lib.c_int32_p), _ptr(ds, _lib.c_double_p)
         m.log_capacity = int(log_capacity)
+        m.tskit_layout = 1 if tskit_layout else 0
+        keep = []
+        if trait_mus is not None and any(float(v) > 0 for v in trait_mus):
+            tm = np.ascontiguousarray(trait_mus, dtype=np.float64)
+            assert len(tm) == self.n_traits
+            ad = np.array([[a[0], a[1], -1.0 if a[2] is None else a[2]] for a in trait_alpha_distr], dtype=np.float64)
+            assert ad.shape == (self.n_traits, 3)
+            keep += [tm, ad]
+            m.host_trait_mu = _ptr(tm, _lib.c_double_p)
+            m.host_trait_alpha_distr = _ptr(ad, _lib.c_double_p)
+        elif trait_alpha_distr is not None:
+            ad = np.array([[a[0], a[1], -1.0 if a[2] is None else a[2]] for a in trait_alpha_distr], dtype=np.float64)
+            keep.append(ad)
+            m.host_trait_alpha_distr = _ptr(ad, _lib.c_double_p)
+        if trait_loci_idxs is not None:
+            if [len(v) for v in trait_loci_idxs] != list(getattr(self, '_trait_sizes', [])):
+                raise ValueError('trait_loci_idxs must hold one index per locus of the traits last given to set_traits')
+            ti = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.int32).reshape(-1)
+                                                      for v in trait_loci_idxs] + [np.zeros(0, np.int32)]), dtype=np.int32)
+            keep.append(ti)
+            m.host_trait_loci_idxs = _ptr(ti, _lib.c_int32_p)
+        if delet_loci_idxs is not None:
+            di = np.ascontiguousarray(delet_loci_idxs, dtype=np.int32)
+            assert len(di) == len(dl)
+            keep.append(di)
+            m.host_delet_loci_idxs = _ptr(di, _lib.c_int32_p)
+        if subsetters is not None:
+            sb = np.ascontiguousarray(subsetters, dtype=np.uint8)
+            assert sb.ndim == 2 and sb.shape[1] == len(nn), (sb.shape, len(nn))
+            keep.append(sb)
+            m.host_subsetters = sb.ctypes.data_as(C.POINTER(C.c_uint8))
         _lib.check(self._L.gnx_set_mutation(self._ctx, C.byref(m)), 'gnx_set_mutation')
+        self._mut_tskit = bool(tskit_layout)
+
+    @staticmethod
+    def _mut_type_name(t):
+        return ('neut', 'delet')[t] if t < 2 else 't%i' % (t - 2)
 
     def read_mutations(self, max_rows=4096):
         """Drain the mutation log; returns (rows, state) with rows a list of dicts (t, individual,
-        locus, row, homologue, type, s) and state the current bookkeeping arrays."""
+        locus, row, homologue, type, s, alpha, node) and state the current bookkeeping arrays."""
         rows = (_lib.MutationRow * max_rows)()
         n_rows, n_left, n_nn, n_dl = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
         nn = np.zeros(self.Lg + 1, np.int32)
@@ -320,10 +364,31 @@ class DeviceSpecies:
             self._ctx, rows, max_rows, C.byref(n_rows), C.byref(n_left), _ptr(nn, _lib.c_int32_p), C.byref(n_nn),
             _ptr(dl, _lib.c_int32_p), _ptr(ds, _lib.c_double_p), C.byref(n_dl)), 'gnx_read_mutations')
         out = [dict(t=r.t, individual=r.individual, locus=r.locus, row=r.row, homologue=r.homologue,
-                    type=('neut', 'delet')[r.type], s=r.s) for r in rows[:n_rows.value]]
+                    type=self._mut_type_name(r.type), s=r.s, alpha=r.alpha, node=r.node) for r in rows[:n_rows.value]]
         state = dict(n_mutables=n_left.value, nonneut_loci=nn[:n_nn.value].copy(),
                      delet_loci=dl[:n_dl.value].copy(), delet_s=ds[:n_dl.value].copy())
         return out, state
+
+    def read_mutation_tables(self):
+        """(Trait.loci, Trait.alpha, Trait.loci_idxs) per trait and gen_arch.delet_loci_idxs as the mutations
+        left them (genome.py:416-437, 753-788)."""
+        traits = []
+        cap = self.Lg + 1
+        di = np.zeros(cap, np.int32)
+        for t in range(self.n_traits):
+            n = C.c_int32(0)
+            lo, al, ix = np.zeros(cap, np.int32), np.zeros(cap, np.float64), np.zeros(cap, np.int32)
+            _lib.check(self._L.gnx_read_mutation_tables(
+                self._ctx, t, C.byref(n), _ptr(lo, _lib.c_int32_p), _ptr(al, _lib.c_double_p), _ptr(ix, _lib.c_int32_p),
+                _ptr(di, _lib.c_int32_p)), 'gnx_read_mutation_tables')
+            traits.append(dict(loci=lo[:n.value].copy(), alpha=al[:n.value].copy(), loci_idxs=ix[:n.value].copy()))
+        if not self.n_traits:
+            _lib.check(self._L.gnx_read_mutation_tables(self._ctx, -1, None, None, None, None, _ptr(di, _lib.c_int32_p)),
+                       'gnx_read_mutation_tables')
+        n_dl = C.c_int32(0)
+        _lib.check(self._L.gnx_read_mutations(self._ctx, None, 0, None, None, None, None, None, None, C.byref(n_dl)),
+                   'gnx_read_mutations')
+        return traits, di[:n_dl.value].copy()
 
     # ---- population in / out ---------------------------------------------------------------
     def _pop_struct(self, bufs):

@@ -46,3 +46,18 @@ def pack_paths(paths):
     bits = np.zeros((n, W * 32), dtype=np.uint8)
     bits[:, :L] = paths
     return pack_bits(bits).reshape(n, W)
+
+
+def rows_to_loci(g_rows, nonneut_loci, L):
+    """gen_arch.use_tskit = True (species.py:891-905): the reference's genotype arrays hold one ROW per
+    non-neutral locus, int8[N, n_nonneut, 2].  The device keeps one bit per LOCUS: row r becomes locus
+    nonneut_loci[r], neutral loci are zero."""
+    g_rows = np.asarray(g_rows)
+    g = np.zeros((g_rows.shape[0], int(L), 2), dtype=np.int8)
+    g[:, np.asarray(nonneut_loci, dtype=np.int64), :] = g_rows
+    return g
+
+
+def loci_to_rows(g, nonneut_loci):
+    """The reference's use_tskit = True view of by-locus genotypes: rows nonneut_loci, in order."""
+    return np.ascontiguousarray(np.asarray(g)[:, np.asarray(nonneut_loci, dtype=np.int64), :])

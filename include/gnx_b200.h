@@ -156,6 +156,8 @@ typedef struct {
                                      * descending id list of species.py:615-622 */
   const double* mut_homol_u;        /* [n_mut] homologue = (u < 0.5) */
   const double* mut_s;              /* [n_mut] gamma(shape, scale) output for deleterious s (before min(s, 1)) */
+  const double* mut_alpha;          /* [n_mut] normal(alpha_distr_mu, alpha_distr_sigma) output for a trait mutation
+                                     * (before the max_alpha_mag clip, genome.py:679-682) */
 } gnx_draws_t;
 
 /* Host-side SoA view of a population (upload / download). Any pointer may be NULL. */
@@ -321,7 +323,7 @@ int gnx_tskit_renumber(gnx_ctx* ctx);
 
 /* ---- a13 mutation (ops/mutation.py:169-206 _do_mutation; :62-86 neutral; :90-131 + :156-166
  *      deleterious; genome.py:650-663 _draw_mut_types, :690-693 _draw_delet_s, :753-788
- *      _add_nonneut_locus), for use_tskit = False genomes.  Runs inside gnx_make_offspring /
+ *      _add_nonneut_locus), for both genotype layouts.  Runs inside gnx_make_offspring /
  *      gnx_step right after the newborn records are written (species.py:808-809).
  *      Infinite sites: every mutation pops one locus from the END of the shuffled `mutables`
  *      list (genome.py:1101-1104), so a run has at most n_mutables mutations and the
@@ -334,8 +336,27 @@ int gnx_tskit_renumber(gnx_ctx* ctx);
  *        L-row genotype array with the nonneut_loci position, not with the locus -- reproduced
  *        as is) and its phenotype is recomputed; fitness is then multiplied by
  *        prod_k (1 - s_k * dosage(delet_locus_k)) (selection.py:78-94).
- *      - trait mutations (Trait.mu > 0) raise in the reference when use_tskit = False
- *        (genome.py:430, loci_idxs is None): rejected here with GNX_ERR_ARG. */
+ *      - trait mutations (Trait.mu > 0; mutation.py:135-144 -> :90-131, genome.py:666-687
+ *        _draw_trait_alpha, :416-437 Trait._add_locus): the locus joins nonneut_loci and the
+ *        trait's (loci, alpha, loci_idxs) with alpha = clip(normal(mu, sigma), +-max_alpha_mag)
+ *        (or mu when sigma = 0; |alpha| while the trait is monogenic).  The reference raises for
+ *        them when use_tskit = False (genome.py:430, loci_idxs is None): accepted only with
+ *        tskit_layout = 1, rejected with GNX_ERR_ARG otherwise.
+ *      tskit_layout = 1 (gen_arch.use_tskit = True, species.py:891-905): the reference's genotype
+ *        arrays hold one row per NON-NEUTRAL locus, a non-neutral mutation inserts a zero row at
+ *        idx into every individual (species.py:908-910) and sets g[idx, homologue] = 1, and the
+ *        recombination subsetters get the path's homologue in front of the locus inserted at
+ *        2*idx (genome.py:133-160).  The device keeps one bit per LOCUS (rows never move; row r
+ *        of the reference is bit nonneut_loci[r]; neutral bits are zero and never read), sets bit
+ *        `locus`, and patches bit `locus` of every cached path to (#breakpoints < locus) % 2.
+ *        The reference's index arrays are reproduced AS WRITTEN: Trait.loci_idxs is shifted only
+ *        behind the insertion point of the mutated trait itself and delet_loci_idxs never, so
+ *        after mutations they may address other rows than the trait's / deleterious loci; the
+ *        phenotype (selection.py:30) and the deleterious fitness (selection.py:86-88) read row
+ *        idxs[k], i.e. bit nonneut_loci[idxs[k]].  Each log row carries the tskit node of the
+ *        mutated homologue (mutations-table row of mutation.py:44-58: site = locus, node,
+ *        derived_state '1', time = -t) when tskit recording is enabled.
+ *      gnx_set_traits must precede gnx_set_mutation; re-setting the traits disables mutation. */
 typedef struct {
   double mu_neut, mu_delet;           /* per-site, per-generation rates (genome.py:596-603) */
   double delet_s_shape, delet_s_scale;
@@ -347,6 +368,16 @@ typedef struct {
   const int32_t* host_delet_loci;     /* ascending */
   const double* host_delet_s;
   int32_t log_capacity;               /* rows kept for gnx_read_mutations */
+  int32_t tskit_layout;               /* 1: use_tskit = True semantics (see above) */
+  const double* host_trait_mu;        /* [n_traits] Trait.mu, or NULL (no trait mutation) */
+  const double* host_trait_alpha_distr; /* [n_traits][3]: alpha_distr_mu, alpha_distr_sigma, max_alpha_mag (< 0: None) */
+  const int32_t* host_trait_loci_idxs;  /* tskit_layout: Trait.loci_idxs of every trait, concatenated in trait
+                                           order, each in the order of Trait.loci; NULL = rows of the loci */
+  const int32_t* host_delet_loci_idxs;  /* tskit_layout: gen_arch.delet_loci_idxs [n_delet]; NULL = rows of the loci */
+  const uint8_t* host_subsetters;       /* tskit_layout: [n_recomb_paths][n_nonneut] homologue (0/1) each cached path
+                                           takes at each genotype row (Recombinations._subsetters, genome.py:215-224,
+                                           133-160); NULL = the paths of gnx_set_recomb_paths at the non-neutral loci.
+                                           gnx_set_recomb_paths always takes the paths AS SIMULATED. */
 } gnx_mutation_t;
 typedef struct {
   int64_t t;                          /* time step */
@@ -354,8 +385,11 @@ typedef struct {
   int32_t locus;
   int32_t row;                        /* genotype row written (= idx), -1 for neutral */
   int32_t homologue;
-  int32_t type;                       /* 0 neutral, 1 deleterious */
+  int32_t type;                       /* 0 neutral, 1 deleterious, 2 + k: trait k */
   double s;                           /* selection coefficient (deleterious) */
+  double alpha;                       /* effect size (trait mutation) */
+  int32_t node;                       /* tskit node of the mutated homologue, -1 when not recording */
+  int32_t reserved;
 } gnx_mutation_row_t;
 int gnx_set_mutation(gnx_ctx* ctx, const gnx_mutation_t* m);
 int gnx_mutate(gnx_ctx* ctx);         /* stage entry; already part of gnx_make_offspring / gnx_step */
@@ -363,6 +397,11 @@ int gnx_mutate(gnx_ctx* ctx);         /* stage entry; already part of gnx_make_o
 int gnx_read_mutations(gnx_ctx* ctx, gnx_mutation_row_t* rows, int32_t max_rows, int32_t* n_rows,
                        int32_t* n_mutables_left, int32_t* host_nonneut_loci, int32_t* n_nonneut,
                        int32_t* host_delet_loci, double* host_delet_s, int32_t* n_delet);
+/* current (Trait.loci, Trait.alpha, Trait.loci_idxs) of one trait and gen_arch.delet_loci_idxs as the
+ * mutations left them (genome.py:416-437, 753-788); arrays sized L + 1, any pointer may be NULL.
+ * Without tskit_layout the idxs are the rows of the loci themselves. */
+int gnx_read_mutation_tables(gnx_ctx* ctx, int32_t trait, int32_t* n_loci, int32_t* host_loci, double* host_alpha,
+                             int32_t* host_loci_idxs, int32_t* host_delet_loci_idxs);
 
 /* ---- on-device statistics (sim/stats.py:399-435 _calc_het / _calc_maf / _calc_mean_fitness;
  *      SURVEY.md section 8f rank 2): per-locus 1-allele counts and heterozygote counts by

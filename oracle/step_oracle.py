@@ -820,6 +820,103 @@ def mutate(og, oz, mut, draws, traits, dom, first_id):
     return og, oz, new, log
 
 
+def draw_trait_alpha(tr, draw):
+    """genome.py:666-687 _draw_trait_alpha(n=1): mu when sigma == 0, else clip(normal(mu, sigma) := the injected
+    sampler output, +-max_alpha_mag); |alpha| while the trait is monogenic (n_loci read BEFORE the locus is added)."""
+    mu_a, sigma, max_mag = (float(v) for v in tr['alpha_distr'])
+    if sigma == 0:
+        alpha = mu_a
+    else:
+        alpha = float(draw)
+        if max_mag >= 0:
+            alpha = float(np.clip(alpha, -max_mag, max_mag))
+    if len(tr['loci']) == 1:
+        alpha = abs(alpha)
+    return alpha
+
+
+def rows_traits(traits):
+    """use_tskit=True: _calc_phenotype reads genotype ROWS Trait.loci_idxs (selection.py:29-30); dominance still
+    indexes dom by Trait.loci (selection.py:37)."""
+    return [dict(tr, loci=np.asarray(tr['loci_idxs'], dtype=np.int64), dom_loci=np.asarray(tr['loci'], dtype=np.int64))
+            for tr in traits]
+
+
+def mutate_tskit(g_all, z_all, n0, mut, draws, dom, first_id):
+    """ops/mutation.py:169-206 with gen_arch.use_tskit = True (genotype arrays hold one ROW per non-neutral locus,
+    species.py:891-905).  g_all int8[N0 + B, n_nonneut, 2]: everyone alive, the B offspring last (a non-neutral
+    mutation inserts a zero row into EVERY individual, species.py:908-910 / individual.py:165-168).
+
+    mut: the dict of `mutate` plus traits (list of dicts loci, alpha, loci_idxs, alpha_distr (mu, sigma,
+         max_alpha_mag or -1) and the fitness keys), trait_mus, delet_loci_idxs, subsetters uint8[n_paths, n_nonneut]
+         (Recombinations._subsetters, one homologue per genotype row) and paths uint8[n_paths, L] (as simulated).
+    Per non-neutral mutation, in the reference's order: [delet: s = min(gamma, 1)] -> locus = mutables.pop() ->
+    individual = choice(offspring) -> idx = _add_nonneut_locus (genome.py:753-788: nonneut_loci; delet_loci /
+    delet_loci_s / delet_loci_idxs -- NO later index is shifted; or Trait._add_locus genome.py:416-437 with
+    alpha = _draw_trait_alpha, loci_idxs shifted behind the insertion point of THIS trait only) -> homologue ->
+    zero row at idx for everyone -> g[idx, homol] = 1 -> phenotype of the individual (species.py:929) ->
+    mutations-table row (mutation.py:44-58) -> subsetters get (#breakpoints < locus) % 2 at row idx
+    (genome.py:133-160).  Neutral: locus, individual, homologue, mutations-table row.
+    Returns (g_all, z_all, new_mut, log rows)."""
+    import bisect
+    B = g_all.shape[0] - n0
+    new = dict(mut)
+    mutables = list(mut['mutables'])
+    nonneut = [int(v) for v in mut['nonneut_loci']]
+    dl = [int(v) for v in mut['delet_loci']]
+    ds = [float(v) for v in mut['delet_s']]
+    di = [int(v) for v in mut['delet_loci_idxs']]
+    traits = [dict(tr, loci=[int(v) for v in tr['loci']], alpha=[float(v) for v in tr['alpha']],
+                   loci_idxs=[int(v) for v in tr['loci_idxs']]) for tr in mut['traits']]
+    subs = np.asarray(mut['subsetters'], dtype=np.uint8)
+    paths = np.asarray(mut['paths'], dtype=np.uint8)
+    log = []
+    n_muts = int(np.asarray(draws['mut_n']).reshape(-1)[0]) if B else 0
+    if n_muts > 0:
+        cdf = mutation_type_cdf(mut['mu_neut'], mut['mu_delet'], mut.get('trait_mus', ()))
+        g_all = g_all.copy()
+        z_all = z_all.copy()
+        for m in range(n_muts):
+            ti = int(np.searchsorted(cdf, draws['mut_type_u'][m], side='right'))
+            sel = min(float(draws['mut_s'][m]), 1.0) if ti == 1 else 0.0             # genome.py:690-693
+            locus = int(mutables.pop())
+            o = B - 1 - int(choose_k(np.uint32(draws['mut_ind_R'][m]), B))           # descending id list
+            row, alpha = -1, 0.0
+            if ti >= 1:
+                row = bisect.bisect_left(nonneut, locus)
+                nonneut.insert(row, locus)
+                if ti == 1:
+                    k = bisect.bisect_left(dl, locus)
+                    dl.insert(k, locus)
+                    ds.insert(k, sel)
+                    di.insert(k, row)
+                else:
+                    tr = traits[ti - 2]
+                    alpha = draw_trait_alpha(tr, draws['mut_alpha'][m])
+                    k = bisect.bisect_left(tr['loci'], locus)
+                    tr['loci'].insert(k, locus)
+                    tr['alpha'].insert(k, alpha)
+                    tr['loci_idxs'] = tr['loci_idxs'][:k] + [row] + [v + 1 for v in tr['loci_idxs'][k:]]
+            homol = int(draws['mut_homol_u'][m] < 0.5)
+            if ti >= 1:
+                g_all = np.insert(g_all, row, 0, axis=1)                             # species.py:908-910
+                g_all[n0 + o, row, homol] = 1                                        # mutation.py:117
+                z_all[n0 + o] = phenotype(g_all[n0 + o:n0 + o + 1], rows_traits(traits), dom)[0]
+                ins = paths[:, locus - 1] if locus > 0 else np.zeros(len(paths), np.uint8)   # bisect_left(bps, locus) % 2
+                subs = np.insert(subs, row, ins, axis=1)
+            log.append(dict(individual=first_id + o, locus=locus, row=row, homologue=homol,
+                            type=('neut', 'delet')[ti] if ti < 2 else 't%i' % (ti - 2), s=sel, alpha=alpha))
+    new['mutables'] = mutables
+    new['nonneut_loci'] = np.array(nonneut, dtype=np.int64)
+    new['delet_loci'] = np.array(dl, dtype=np.int64)
+    new['delet_s'] = np.array(ds, dtype=np.float64)
+    new['delet_loci_idxs'] = np.array(di, dtype=np.int64)
+    new['traits'] = [dict(tr, loci=np.array(tr['loci'], dtype=np.int64), alpha=np.array(tr['alpha'], dtype=np.float64),
+                          loci_idxs=np.array(tr['loci_idxs'], dtype=np.int64)) for tr in traits]
+    new['subsetters'] = subs
+    return g_all, z_all, new, log
+
+
 def delet_dosage(g, delet_loci):
     """selection.py:78-94: diploid dosage at the deleterious loci (use_tskit=False: g rows are loci)."""
     return np.sum(g[:, np.asarray(delet_loci, dtype=np.int64), :], axis=2)
@@ -897,7 +994,22 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
         tries = np.zeros(0, np.int32)
         osex = np.zeros(0, np.int8)
     im['mid_x'], im['mid_y'], im['disp_tries'] = mid_x, mid_y, tries
-    if not burn:
+    tskit_layout = (not burn) and arch.get('mutation') is not None and arch['mutation'].get('tskit_layout')
+    if tskit_layout:
+        # gen_arch.use_tskit = True: state['g'] holds the non-neutral ROWS; gametes through the subsetters
+        # (mating.py:156-166), phenotypes through Trait.loci_idxs; the evolving tables live in arch['mutation']
+        mt = arch['mutation']
+        traits = mt['traits']
+        og = make_gametes(state['g'], pairs, nb, draws['recomb_keys'][:2 * B], draws['start_homs'][:B],
+                          mt['subsetters']) if B else np.zeros((0,) + state['g'].shape[1:], np.int8)
+        oz = phenotype(og, rows_traits(traits), arch.get('dom')) if traits else np.zeros((B, 0))
+        im['birth_z'] = oz.copy()                                            # individuals-table location (species.py:694-697)
+        g_all = np.concatenate([state['g'], og])
+        z_all = np.concatenate([state['z'], oz])
+        g_all, z_all, im['mutation'], im['mut_log'] = mutate_tskit(
+            g_all, z_all, n0, mt, draws, arch.get('dom'), int(state['max_ind_idx']) + 1)
+        traits = im['mutation']['traits']
+    elif not burn:
         og = make_gametes(state['g'], pairs, nb, draws['recomb_keys'][:2 * B],
                           draws['start_homs'][:B], arch['paths']) if B else \
             np.zeros((0,) + state['g'].shape[1:], np.int8)
@@ -929,7 +1041,10 @@ def step(state, arch, prm, draws, dgs=None, max_tries=None, burn=False):
     selection = (not burn) and (bool(traits) or (mut_now is not None and mut_now['mu_delet'] > 0))
     if selection:
         cxa, cya = cells(x_all, y_all)
-        delet = (delet_dosage(g_all, mut_now['delet_loci']), mut_now['delet_s']) if has_delet else None
+        # use_tskit: rows delet_loci_idxs (selection.py:86-88), else the loci themselves
+        delet_rows = mut_now['delet_loci_idxs'] if (has_delet and mut_now.get('tskit_layout')) else \
+            (mut_now['delet_loci'] if has_delet else None)
+        delet = (delet_dosage(g_all, delet_rows), mut_now['delet_s']) if has_delet else None
         w = fitness(e_all, z_all, traits, cxa, cya, delet=delet)
     else:
         w = None

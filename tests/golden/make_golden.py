@@ -129,6 +129,17 @@ CASES = {
                 move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
                 dom=False, max_age=None, phi=[0.1, 0.05], gamma=[1, 2], seed=15,
                 surfaces=False, main_steps=5, mu_neut=1e-5, mu_delet=1e-5, model_T=10, mut_n=7),
+    # use_tskit=True (species.py:891-905: genotype arrays hold the non-neutral loci only) with
+    # neutral + deleterious + TRAIT mutation (mutation.py:90-131, genome.py:416-437, 753-788) and
+    # the tskit rows of a step (species.py:692-736, mutation.py:44-58).  The reference runs on the
+    # functional table shim of oracle/ref_shims.py; free-running mutations of the earlier main
+    # steps leave the index arrays (Trait.loci_idxs, delet_loci_idxs) as the reference leaves them.
+    'tmut': dict(dim=(40, 40), N=900, K_factor=0.8, L=400, n_traits=2, trait_loci=[5, 4],
+                 mating_radius=2, b=0.4, sex=False, n_births_fixed=True, lam=1,
+                 move=('wald', 1.0, 1.0), disp=('wald', 0.8, 1.0), kappa=0.0, mu=0.0,
+                 dom=False, max_age=None, phi=[0.1, 0.05], gamma=[1, 2], seed=21,
+                 surfaces=False, main_steps=6, mu_neut=1e-5, mu_delet=1.5e-5, trait_mu=[2e-5, 1.5e-5],
+                 model_T=10, mut_n=10, use_tskit=True),
 }
 
 
@@ -183,7 +194,9 @@ def build_params(gnx, case, tmpdir='/tmp'):
             mv[k]['mixture'] = True
     g = s['gen_arch']
     g['L'] = c['L']
-    g['use_tskit'] = False
+    g['use_tskit'] = bool(c.get('use_tskit', False))
+    g['tskit_simp_interval'] = 10 ** 6        # sort()/simplify() are tskit's own algorithms: never reached
+    g['jitter_breakpoints'] = False
     g['dom'] = c['dom']
     g['n_recomb_sims'] = 1000
     g['r_distr_alpha'] = 0.5
@@ -198,6 +211,8 @@ def build_params(gnx, case, tmpdir='/tmp'):
         tr['alpha_distr_sigma'] = 0.15 if c['trait_loci'][t] > 1 else 0
         tr['max_alpha_mag'] = 0.3
         tr['univ_adv'] = c.get('univ_adv', [False] * 4)[t]
+        if c.get('trait_mu') is not None:
+            tr['mu'] = c['trait_mu'][t]
     p['model']['T'] = c.get('model_T', 100)
     if c.get('mu_neut') is not None:
         g['mu_neut'] = c['mu_neut']
@@ -229,6 +244,9 @@ def capture_state(spp):
         st['g'] = np.zeros((len(inds), spp.gen_arch.L, 2), np.int8)
         st['z'] = np.zeros((len(inds), nt))
     st['fit'] = np.array([np.nan if i.fit is None else i.fit for i in inds], dtype=np.float64)
+    if spp.gen_arch.use_tskit and len(inds) and len(inds[0]._nodes_tab_ids) == 2:
+        st['nodes'] = np.array([[i._nodes_tab_ids[0], i._nodes_tab_ids[1]] for i in inds], dtype=np.int64)
+        st['ind_row'] = np.array([i._individuals_tab_id for i in inds], dtype=np.int64)
     return st
 
 
@@ -238,10 +256,25 @@ def capture_arch(spp, land):
     L = ga.L
     n_sims = ga.recombinations._n
     paths = np.zeros((n_sims, L), dtype=np.uint8)
-    for k in range(n_sims):
-        sub = list(ga.recombinations._subsetters[k])
-        paths[k] = np.array(sub[1::2], dtype=np.uint8)     # '10'->hom 0, '01'->hom 1
+    if ga.use_tskit:
+        # the subsetters cover the genotype rows (non-neutral loci) only: genome.py:215-218, 133-160;
+        # the full-length paths are the cumulated breakpoints (genome.py:211-212)
+        nn = len(ga.nonneut_loci)
+        subs = np.zeros((n_sims, nn), dtype=np.uint8)
+        for k in range(n_sims):
+            sub = list(ga.recombinations._subsetters[k])
+            assert len(sub) == 2 * nn
+            subs[k] = np.array(sub[1::2], dtype=np.uint8)
+            rec_at = np.zeros(L, dtype=np.int64)
+            rec_at[np.asarray(ga.recombinations._breakpoints[k], dtype=np.int64)] = 1
+            paths[k] = np.cumsum(rec_at) % 2
+        out['subsetters'] = subs
+    else:
+        for k in range(n_sims):
+            sub = list(ga.recombinations._subsetters[k])
+            paths[k] = np.array(sub[1::2], dtype=np.uint8)     # '10'->hom 0, '01'->hom 1
     out['paths'] = paths
+    out['use_tskit'] = np.int64(bool(ga.use_tskit))
     out['dom'] = np.asarray(ga.dom, dtype=np.int8)
     out['n_traits'] = np.int64(len(ga.traits))
     for t, tr in ga.traits.items():
@@ -251,6 +284,11 @@ def capture_arch(spp, land):
         out['trait%i_gamma' % t] = np.float64(tr.gamma)
         out['trait%i_lyr' % t] = np.int64(tr.lyr_num)
         out['trait%i_univ_adv' % t] = np.int64(bool(tr.univ_adv))
+        if ga.use_tskit:
+            out['trait%i_loci_idxs' % t] = np.asarray(tr.loci_idxs, dtype=np.int64)
+            out['trait%i_alpha_distr' % t] = np.array(
+                [tr.alpha_distr_mu, tr.alpha_distr_sigma,
+                 -1.0 if tr.max_alpha_mag is None else tr.max_alpha_mag], dtype=np.float64)
     out['rasters'] = np.stack([land[l].rast for l in range(len(land))]).astype(np.float64)
     out['K'] = np.asarray(spp.K, dtype=np.float64)
     out['land_dim'] = np.array(land.dim, dtype=np.int64)
@@ -269,6 +307,8 @@ def capture_arch(spp, land):
         out['mut_delet_s'] = np.array(ga.delet_loci_s, dtype=np.float64)
         out['mut_s_shape'] = np.float64(ga.delet_alpha_distr_shape)
         out['mut_s_scale'] = np.float64(ga.delet_alpha_distr_scale)
+        if ga.use_tskit:
+            out['mut_delet_loci_idxs'] = np.asarray(ga.delet_loci_idxs, dtype=np.int64)
     prm = {}
     for k in ('b', 'R', 'n_births_distr_lambda', 'mating_radius', 'd_min', 'd_max',
               'direction_distr_mu', 'direction_distr_kappa'):
@@ -329,6 +369,10 @@ class Replay:
 
     def gamma(self, shape, scale=1.0, size=None):          # genome.py:691
         return float(self.d['mut_s'][self.n_mut_done])
+
+    def normal(self, loc=0.0, scale=1.0, size=None):       # genome.py:679 _draw_trait_alpha
+        assert self.in_mutation
+        return np.array([self.d['mut_alpha'][self.n_mut_done]], dtype=np.float64)
 
     def choice(self, opts, *a, **k):
         if self.pan_phase:
@@ -433,6 +477,7 @@ def patched(rp):
     setp(npr, 'binomial', rp.binomial)
     setp(npr, 'poisson', rp.poisson)
     setp(npr, 'gamma', rp.gamma)
+    setp(npr, 'normal', rp.normal)
 
     # mutation stage marker (species.py:808-809)
     orig_mut = sp._do_mutation
@@ -535,6 +580,7 @@ def make_draws(rng, cap, spp, case):
         d['mut_ind_R'] = rng.integers(0, 2**32, nm, dtype=np.uint64).astype(np.uint32)
         d['mut_homol_u'] = rng.random(nm)
         d['mut_s'] = rng.gamma(0.2, 0.2, nm)
+        d['mut_alpha'] = rng.normal(0.0, 0.15, nm)
     return d
 
 
@@ -588,6 +634,9 @@ def record_case(gnx, case, out_dir=HERE):
 
     rp = Replay(gnx, spp, land, draws)
     ids0 = st0['idx']
+    if spp.gen_arch.use_tskit:
+        tab0 = (spp._tc.nodes.num_rows, spp._tc.edges.num_rows, spp._tc.individuals.num_rows,
+                spp._tc.mutations.num_rows)
 
     with patched(rp):
         # ---- a1 age, a2 movement, a3 env sample (model.py queue; species.py:567-586)
@@ -703,6 +752,36 @@ def record_case(gnx, case, out_dir=HERE):
         rec['out_mut_nonneut_loci'] = np.array(ga.nonneut_loci, dtype=np.int64)
         rec['out_mut_delet_loci'] = np.array(ga.delet_loci, dtype=np.int64)
         rec['out_mut_delet_s'] = np.array(ga.delet_loci_s, dtype=np.float64)
+        if ga.use_tskit:
+            rec['out_mut_delet_loci_idxs'] = np.asarray(ga.delet_loci_idxs, dtype=np.int64)
+            for t, tr in ga.traits.items():
+                rec['out_trait%i_loci' % t] = np.asarray(tr.loci, dtype=np.int64)
+                rec['out_trait%i_alpha' % t] = np.asarray(tr.alpha, dtype=np.float64)
+                rec['out_trait%i_loci_idxs' % t] = np.asarray(tr.loci_idxs, dtype=np.int64)
+            n_sims = ga.recombinations._n
+            subs = np.zeros((n_sims, len(ga.nonneut_loci)), dtype=np.uint8)
+            for k in range(n_sims):
+                subs[k] = np.array(list(ga.recombinations._subsetters[k])[1::2], dtype=np.uint8)
+            rec['out_subsetters'] = subs
+    if spp.gen_arch.use_tskit:
+        # rows the step appended to the tables (species.py:692-736, mutation.py:44-58)
+        tc = spp._tc
+        n0, e0, i0, m0 = tab0
+        rec['tsk_in_rows'] = np.array(tab0, dtype=np.int64)
+        rec['tsk_node_time'] = np.array(tc.nodes.column('time')[n0:], dtype=np.float64)
+        rec['tsk_node_flags'] = np.array(tc.nodes.column('flags')[n0:], dtype=np.int64)
+        rec['tsk_node_individual'] = np.array(tc.nodes.column('individual')[n0:], dtype=np.int64)
+        rec['tsk_edge_left'] = np.array(tc.edges.column('left')[e0:], dtype=np.float64)
+        rec['tsk_edge_right'] = np.array(tc.edges.column('right')[e0:], dtype=np.float64)
+        rec['tsk_edge_parent'] = np.array(tc.edges.column('parent')[e0:], dtype=np.int64)
+        rec['tsk_edge_child'] = np.array(tc.edges.column('child')[e0:], dtype=np.int64)
+        rec['tsk_ind_location'] = np.array(tc.individuals.column('location')[i0:], dtype=np.float64)
+        rec['tsk_ind_idx'] = np.array([int.from_bytes(b, 'little') for b in tc.individuals.column('metadata')[i0:]],
+                                      dtype=np.int64)
+        rec['tsk_mut_site'] = np.array(tc.mutations.column('site')[m0:], dtype=np.int64)
+        rec['tsk_mut_node'] = np.array(tc.mutations.column('node')[m0:], dtype=np.int64)
+        rec['tsk_mut_time'] = np.array(tc.mutations.column('time')[m0:], dtype=np.float64)
+        rec['tsk_t'] = np.int64(spp.t)
     # trim draw arrays to what can be consumed (keeps fixtures small)
     nmax = N0 + B + 8
     for k in list(rec):

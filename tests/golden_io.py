@@ -32,6 +32,14 @@ def load_case(name):
                                 nonneut_loci=z['mut_nonneut_loci'], delet_loci=z['mut_delet_loci'],
                                 delet_s=z['mut_delet_s'], s_shape=float(z['mut_s_shape']),
                                 s_scale=float(z['mut_s_scale']))
+        if 'use_tskit' in z.files and int(z['use_tskit']):
+            # gen_arch.use_tskit = True: genotype ROWS per non-neutral locus; the evolving tables travel in the
+            # mutation dict (oracle/step_oracle.py mutate_tskit)
+            for t, tr in enumerate(traits):
+                tr['loci_idxs'] = z['trait%i_loci_idxs' % t]
+                tr['alpha_distr'] = z['trait%i_alpha_distr' % t]
+            arch['mutation'].update(tskit_layout=True, traits=traits, delet_loci_idxs=z['mut_delet_loci_idxs'],
+                                    subsetters=z['subsetters'], paths=z['paths'])
     if arch['ww'] == int(arch['ww']):
         arch['ww'] = int(arch['ww'])
     prm = dict(b=float(z['prm_b']), R=float(z['prm_R']), lam=float(z['prm_n_births_distr_lambda']),

@@ -32,9 +32,28 @@ def make_device(arch, prm, capacity=None, seed=0, disp_tries=6, extra=None):
                          disp_tries_injected=disp_tries, res_ratio=tuple(arch.get('res_ratio', (1.0, 1.0))))
 
 
-def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=True):
-    """One main time step on the device with injected draws; returns intermediates."""
+def set_device_mutation(dev, mut):
+    """arch['mutation'] (golden_io / oracle format) -> DeviceSpecies.set_mutation."""
+    kw = {}
+    if mut.get('tskit_layout'):
+        kw = dict(tskit_layout=True, trait_mus=mut.get('trait_mus'),
+                  trait_alpha_distr=[tr['alpha_distr'] for tr in mut['traits']],
+                  trait_loci_idxs=[tr['loci_idxs'] for tr in mut['traits']],
+                  delet_loci_idxs=mut['delet_loci_idxs'], subsetters=mut['subsetters'])
+    dev.set_mutation(mut['mu_neut'], mut['mu_delet'], mut['mutables'], mut['nonneut_loci'],
+                     mut['delet_loci'], mut['delet_s'], mut.get('s_shape', 0.2), mut.get('s_scale', 0.2), **kw)
+
+
+def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=True, tskit=None):
+    """One main time step on the device with injected draws; returns intermediates.
+    A use_tskit = True case (arch['mutation']['tskit_layout']) carries genotype ROWS in state['g']: they are
+    spread to their loci for the upload and gathered back from the download (genome_pack.rows_to_loci).
+    tskit: dict(node0, node1, next_node_id, next_individual_row) turns the row recording on."""
+    from geonomics_b200 import genome_pack as gp
     n0 = len(state['x'])
+    tsk_layout = bool(arch.get('mutation') and arch['mutation'].get('tskit_layout'))
+    if tsk_layout:
+        state = dict(state, g=gp.rows_to_loci(state['g'], arch['mutation']['nonneut_loci'], arch['paths'].shape[1]))
     dev = make_device(arch, prm, capacity=capacity or (2 * n0 + 256),
                       disp_tries=draws['disp_dist'].shape[1])
     try:
@@ -50,8 +69,10 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=T
         out_burn = burn
         mut = arch.get('mutation')
         if mut is not None and not burn:
-            dev.set_mutation(mut['mu_neut'], mut['mu_delet'], mut['mutables'], mut['nonneut_loci'],
-                             mut['delet_loci'], mut['delet_s'], mut.get('s_shape', 0.2), mut.get('s_scale', 0.2))
+            set_device_mutation(dev, mut)
+        if tskit is not None:
+            dev.tskit_enable(edge_capacity=tskit.get('edge_capacity', 1 << 20), birth_capacity=4 * n0 + 64)
+            dev.tskit_set_nodes(tskit['node0'], tskit['node1'], tskit['next_node_id'], tskit['next_individual_row'])
         d = dict(draws)
         if arch.get('move_surf') is None:
             d.pop('move_choice', None)
@@ -105,7 +126,13 @@ def run_device_step(arch, prm, state, draws, capacity=None, staged=True, debug=T
         dev.sync()
         if mut is not None and not burn:
             out['mut_log'], out['mutation'] = dev.read_mutations()
+            out['mut_traits'], out['mut_delet_loci_idxs'] = dev.read_mutation_tables()
+        if tskit is not None:
+            out['tskit_rows'] = dev.tskit_drain()
         out['new'] = dev.download(e=True, genomes=not out_burn)
+        if tsk_layout:
+            out['new']['g_loci'] = out['new']['g']
+            out['new']['g'] = gp.loci_to_rows(out['new']['g'], out['mutation']['nonneut_loci'])
         out['new']['e'] = out['new']['e'][:, :-1]
         out['burn'] = out_burn
         out['records'] = dev.step_records()
