@@ -969,7 +969,7 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
 // phenotype contribution of one 128-bit unit pair (h0, h1) of trait t.  The trait table is
 // a CSR over 32-bit words (4 per unit), so the word select is compile-time.
 __device__ __forceinline__ int trait_n_loci(const Traits& tr, int t) {
-  return tr.n_loci_dev ? __ldg(&tr.n_loci_dev[t]) : trait_n_loci(tr, t);
+  return tr.n_loci_dev ? __ldg(&tr.n_loci_dev[t]) : tr.n_loci[t];
 }
 __device__ __forceinline__ double trait_word(const Traits& tr, int s, int e, uint32_t w0, uint32_t w1,
                                              bool polygenic) {

@@ -126,7 +126,18 @@ class DeviceSpecies:
         self._keep = []
 
     # ---- setup -----------------------------------------------------------------------
+    def set_recomb_paths(self, paths):
+        """Cached recombination paths uint8[n_paths, L], AS SIMULATED (bit l = homologue at locus l,
+        genome.py:209-226); n_paths is fixed at creation."""
+        packed = gp.pack_paths(np.asarray(paths, dtype=np.uint8))
+        assert len(paths) == self._cfg.n_recomb_paths, 'n_recomb_paths is fixed at creation'
+        _lib.check(self._L.gnx_set_recomb_paths(self._ctx, _ptr(packed, _lib.c_uint32_p)), 'gnx_set_recomb_paths')
+
     def set_traits(self, traits, dom=None):
+        if len(traits) != self.n_traits:
+            raise ValueError('the number of traits is fixed at creation')
+        if dom is not None:
+            dom = np.ascontiguousarray(dom, dtype=np.int8)
         arr = (_lib.Trait * max(1, len(traits)))()
         keep = []
         for t, tr in enumerate(traits):

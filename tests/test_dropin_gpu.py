@@ -141,3 +141,95 @@ def test_attach_before_burn_in_runs_the_whole_model_on_the_device():
         assert len(spp.gen_arch._mutables) < n_mutables0         # neutral mutations consumed loci (mutation.py:62-86)
     finally:
         dropin.detach(spp)
+
+
+def test_use_tskit_species_with_trait_mutation_on_the_device():
+    """gen_arch.use_tskit = True (genotype ROWS per non-neutral locus, tskit tables filled per birth) with neutral,
+    deleterious and trait mutation: the reference's own Model.walk drives the device; its TableCollection (the
+    functional shim of oracle/ref_shims.py), gen_arch bookkeeping, subsetters and Individuals are kept as the
+    reference's own code would leave them -- checked with the reference's own ops, and by handing the model back."""
+    from geonomics_b200 import dropin
+    def fewer_mutations(p):                                # ~1.3 per step: some steps have none
+        g = p['comm']['species']['spp_0']['gen_arch']
+        g['mu_neut'] *= 0.3
+        g['mu_delet'] *= 0.3
+        for tr in g['traits'].values():
+            tr['mu'] *= 0.3
+    gnx, mg, mod = _ref_model('tmut', tweak=fewer_mutations)
+    spp, land = mod.comm[0], mod.land
+    assert spp.gen_arch.use_tskit and spp.mutate and spp.burned
+    _quiet_walk(mod, 2)                                    # a couple of reference steps first: tables already filled
+    tc = spp._tc
+    L = spp.gen_arch.L
+    rows0 = (tc.nodes.num_rows, tc.edges.num_rows, tc.individuals.num_rows, tc.mutations.num_rows)
+    n_mutables0 = len(spp.gen_arch._mutables)
+    nt0 = len(spp.Nt)
+    dev = dropin.attach(spp, land, seed=11, eager=True)
+    try:
+        steps = 0
+        kinds = set()
+        ga = spp.gen_arch
+        seen = len(ga.nonneut_loci), len(ga.delet_loci)
+        while True:
+            before = len(ga._mutables)
+            _quiet_walk(mod, 1)
+            steps += 1
+            used = before - len(ga._mutables)
+            now = len(ga.nonneut_loci), len(ga.delet_loci)
+            d_nn, d_dl = now[0] - seen[0], now[1] - seen[1]
+            seen = now
+            kinds |= ({'delet'} if d_dl else set()) | ({'trait'} if d_nn - d_dl else set()) | \
+                ({'neut'} if used - d_nn else set())
+            if n_mutables0 - len(ga._mutables) >= 10 and used == 0:
+                break                                      # end on a step without mutation (see the z check below)
+            assert steps < 100
+        births = int(np.sum(spp.n_births[nt0:]))
+        n_muts = n_mutables0 - len(ga._mutables)
+        assert births > 500 and n_muts >= 10
+        assert kinds == {'neut', 'delet', 'trait'}
+        # tables: one individuals row, two nodes rows per birth; one mutations row per mutation
+        assert tc.individuals.num_rows == rows0[2] + births
+        assert tc.nodes.num_rows == rows0[0] + 2 * births
+        assert tc.mutations.num_rows == rows0[3] + n_muts
+        node_ind = np.array(tc.nodes.column('individual'))
+        meta = tc.individuals.column('metadata')
+        for ind in spp.values():
+            n0_, n1_ = ind._nodes_tab_ids[0], ind._nodes_tab_ids[1]
+            assert node_ind[n0_] == node_ind[n1_] == ind._individuals_tab_id
+            assert int.from_bytes(meta[ind._individuals_tab_id], 'little') == ind.idx
+        # the edges of every new node tile [0, L) (species.py:738-760 checks the same)
+        child = np.array(tc.edges.column('child')[rows0[1]:])
+        left = np.array(tc.edges.column('left')[rows0[1]:])
+        right = np.array(tc.edges.column('right')[rows0[1]:])
+        parent = np.array(tc.edges.column('parent')[rows0[1]:])
+        assert set(np.unique(child)) == set(range(rows0[0], rows0[0] + 2 * births))
+        span = np.zeros(2 * births)
+        np.add.at(span, child - rows0[0], right - left)
+        assert np.allclose(span, L)
+        assert parent.min() >= 0 and np.all(parent < child)
+        # mutations sit on nodes of individuals born in their step, at popped loci
+        m_site = np.array(tc.mutations.column('site')[rows0[3]:])
+        m_node = np.array(tc.mutations.column('node')[rows0[3]:])
+        assert len(set(m_site)) == n_muts and np.all(m_node >= rows0[0])
+        # genotype rows = non-neutral loci; bookkeeping arrays the reference's own ops index with
+        g = np.stack([i.g for i in spp.values()])
+        assert g.shape[1:] == (len(ga.nonneut_loci), 2)
+        for k in range(ga.recombinations._n):
+            assert len(ga.recombinations._subsetters[k]) == 2 * len(ga.nonneut_loci)
+        from geonomics.ops import selection as rsel
+        fit_ref = rsel._calc_fitness(spp)                  # traits via ind.z, deleterious loci via delet_loci_idxs
+        fit_dev = np.array([i.fit for i in spp.values()])
+        np.testing.assert_allclose(fit_dev, fit_ref, rtol=1e-6)
+        newborn = [i for i in spp.values() if i.age == 0]
+        assert len(newborn) > 20
+        for trait_num in range(len(ga.traits)):
+            for ind in newborn:                            # born under the current tables (no mutation this step)
+                z_ref = rsel._calc_phenotype(ind, ga, trait_num)
+                assert abs(ind.z[trait_num] - z_ref) <= 1e-12 * max(1.0, abs(z_ref))
+        # hand the model back: the reference's own step runs on what the device left (subsetters, node ids, tables)
+        dropin.detach(spp)
+        _quiet_walk(mod, 2)
+        assert len(spp) == spp.Nt[-1]
+        assert tc.nodes.num_rows == rows0[0] + 2 * (births + int(np.sum(spp.n_births[-2:])))
+    finally:
+        dropin.detach(spp)
