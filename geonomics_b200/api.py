@@ -379,6 +379,13 @@ class Trait:
         self.loci_idxs = None
         self.alpha = np.array([])
 
+    def _set_loci_idxs(self, nonneut_loci, use_tskit):
+        """genome.py:405-414: rows of the trait's loci in the (non-neutral-only) genotype arrays."""
+        if use_tskit:
+            self.loci_idxs = np.array([np.where(nonneut_loci == n)[0][0] for n in self.loci], dtype=np.int64)
+        else:
+            self.loci_idxs = None
+
     def _get_phi(self, spp):
         if type(self.phi) in (float, int):
             return np.array([self.phi] * len(spp))
@@ -390,7 +397,7 @@ class MutationRateError(Exception):
 
 
 class GenomicArchitecture:
-    """genome.py:440-810 (use_tskit=False path)."""
+    """genome.py:440-810."""
 
     def __init__(self, dom, g_params, land, recomb_rates=None, recomb_positions=None):
         self.x = 2
@@ -409,6 +416,7 @@ class GenomicArchitecture:
         self.neut_loci = np.array(range(self.L))
         self.nonneut_loci = np.array([])
         self.delet_loci = np.int64([])
+        self.delet_loci_idxs = np.int64([]) if self.use_tskit else None     # genome.py:590-594
         self.delet_loci_s = np.array([])
         self.traits = None
         if 'traits' in g_params and g_params['traits']:
@@ -518,6 +526,9 @@ def _make_genomic_architecture(spp_params, land):
     else:
         ga.p = gaf['p'].values
     ga.recombinations._set_events()
+    if ga.traits is not None:                                  # genome.py:1044-1047
+        for trt in ga.traits.values():
+            trt._set_loci_idxs(ga.nonneut_loci, ga.use_tskit)
     return ga
 
 
@@ -636,6 +647,7 @@ class Species:
                 self.mut_log = '%s_mutations.log' % name
         self.mutations = []                    # drained device mutation log (dict rows)
         self._seed = seed
+        self._tc = None                        # tskit tables as numpy columns (tables.TableColumns), use_tskit only
         self._dev = None
         self._cache = None                     # host copy of the device state (lazy)
         self._inds = None                      # OrderedDict of Individual views (lazy)
@@ -823,8 +835,21 @@ class Species:
     def _step(self, n=1):
         """_set_age_stage + _do_movement + _do_pop_dynamics + _set_Nt for n time steps
         (species.py:567, 582, 822, 554) on the device."""
+        tsk = self.burned and self.gen_arch is not None and self.gen_arch.use_tskit and \
+            self.__dict__.get('_tc') is not None
+        if tsk and n > self._tsk_steps:
+            # the device row buffers hold _tsk_steps steps of births: drain in between
+            done = 0
+            while done < n and not self.extinct:
+                k = min(self._tsk_steps, n - done)
+                self._step(k)
+                done += k
+            return
         self._dev.step(n)
         recs = self._dev.step_records()
+        if tsk:
+            self._drain_tskit()
+            self._tc_sorted_and_simplified = False
         for k, r in enumerate(recs):
             self.Nt.append(int(r['Nt']))
             self.n_births.append(int(r['n_births']))
@@ -855,6 +880,10 @@ class Species:
                                    e=None, g=None)
             else:
                 self._cache = self._dev.download(genomes=self.burned and self.gen_arch is not None, e=True)
+                if self._cache.get('g') is not None and self.gen_arch.use_tskit:
+                    # species.py:891-905: Individuals carry one genotype ROW per non-neutral locus
+                    from . import genome_pack as gp
+                    self._cache['g'] = gp.loci_to_rows(self._cache['g'], self.gen_arch.nonneut_loci)
         return self._cache
 
     def _individuals(self):
@@ -991,10 +1020,14 @@ class Species:
     def _set_genomes_and_tables(self, burn_T=None, T=None):
         s = self._dev.download(genomes=False)
         n = len(s['x'])
-        L = self.gen_arch.L
+        ga = self.gen_arch
+        L = ga.L
+        tsk = ga.use_tskit
         g = np.zeros((n, L, 2), dtype=np.int8)
         flat = g.reshape(n, L, 2)
-        p = self.gen_arch.p
+        p = ga.p
+        nonneut = set(int(v) for v in ga.nonneut_loci)
+        mut_site, mut_node = [], []
         for site in range(L):
             freq = p[site]
             n_mut = int(round(2 * n * freq, 0))
@@ -1004,28 +1037,102 @@ class Species:
                 n_mut = 1
             if n_mut > 0:
                 hom = np.random.permutation(2 * n)[:n_mut]
-                flat[hom // 2, site, hom % 2] = 1
+                if not tsk or site in nonneut:            # genome.py:1137-1142: only non-neutral rows are carried
+                    flat[hom // 2, site, hom % 2] = 1
+                if tsk:                                   # genome.py:1143-1147: node of (individual k, homologue h)
+                    mut_site.append(np.full(n_mut, site, np.int32))
+                    mut_node.append(hom.astype(np.int32))  # is 2k + h (see below)
         self._dev.set_burn(False)
         self._dev.upload(s['x'], s['y'], s['age'], s['sex'], s['idx'], g=g, max_ind_idx=s['max_ind_idx'])
+        self._tc = None
+        if tsk:
+            self._set_tables(s, mut_site, mut_node)
         self._set_mutation(burn_T, T)
+        if tsk:
+            # per-birth row buffers on the device, drained at the simplification cadence (model.py:756-768)
+            n_bp = max([len(v) for v in ga.recombinations._breakpoints.values()] + [1])
+            births = max(1024.0, float(np.sum(self.K)) * self.b * self.n_births_distr_lambda)
+            self._tsk_steps = int(max(1, min(ga.tskit_simp_interval or 100, 2.0e8 // (2 * (n_bp + 1) * births))))
+            self._dev.tskit_enable(edge_capacity=int(2 * (n_bp + 1) * births * 2 * self._tsk_steps) + 4096,
+                                   birth_capacity=int(births * 2 * self._tsk_steps) + 1024)
+            self._dev.tskit_set_nodes(2 * np.arange(n, dtype=np.int32), 2 * np.arange(n, dtype=np.int32) + 1,
+                                      2 * n, n)
+            self._tsk_t0 = self._dev.counters()['t']
+            self._tc_sorted_and_simplified = False
         self._invalidate()
+
+    def _set_tables(self, s, mut_site, mut_node):
+        """species.py:968-1090 without msprime (absent here): the starting population is 2N unrelated sample
+        nodes -- a forest of singletons, which is what msprime's ancestry reduces to for the path (only the
+        nodes' flags are read, species.py:1006-1009) -- one individuals row per individual (flags = 1, location
+        [x, y, z..., fit], idx), nodes 2k, 2k + 1 for the k-th individual (time 1: born before the main phase,
+        species.py:1075-1077), one sites row per locus in order (:994-1002) and the starting mutations
+        (genome.py:1143-1147).  Phenotypes / fitness are not known before the first step: NaN."""
+        from .tables import TableColumns
+        ga = self.gen_arch
+        n = len(s['x'])
+        nt = len(ga.traits) if ga.traits is not None else 0
+        tc = TableColumns(ga.L, nt)
+        loc = np.full((n, tc.n_loc), np.nan)
+        loc[:, 0], loc[:, 1] = s['x'], s['y']
+        tc.individuals.append_columns(flags=np.ones(n, np.int32), location=loc, idx=s['idx'])
+        tc.nodes.append_columns(flags=np.ones(2 * n, np.int32), time=np.ones(2 * n), population=np.zeros(2 * n, np.int32),
+                                individual=np.repeat(np.arange(n, dtype=np.int32), 2))
+        nn = np.zeros(ga.L, np.int8)
+        nn[np.asarray(ga.nonneut_loci, dtype=np.int64)] = 1
+        tc.sites.append_columns(position=np.arange(ga.L, dtype=np.float64), nonneutral=nn)
+        if mut_site:
+            ms, mn = np.concatenate(mut_site), np.concatenate(mut_node)
+            tc.mutations.append_columns(site=ms, node=mn, time=np.full(len(ms), np.nan))
+        self._tc = tc
+
+    def _drain_tskit(self):
+        """Device row buffers -> self._tc (species.py:692-736 rows, in the reference's order)."""
+        if self._tc is None or self._dev is None:
+            return
+        self._tc.append_births(self._dev.tskit_drain())
+
+    def _sort_and_simplify_table_collection(self):
+        """species.py:1107-1219: sort + simplify on the current nodes, then nodes 2k, 2k + 1 in species order and
+        the individuals rows in species order (gnx_tskit_renumber).  sort()/simplify() are tskit's own."""
+        self._drain_tskit()
+        s = self._state()
+        self._tc.sort_and_simplify(self._node_ids().reshape(-1))
+        self._dev.tskit_renumber()
+        self._tc_sorted_and_simplified = True
+        self._invalidate()
+
+    def _node_ids(self):
+        """int32[N, 2]: the nodes-table ids of every individual's two homologues, species order."""
+        n = len(self)
+        out = np.stack([self._dev.read('NODE0', n), self._dev.read('NODE1', n)], axis=1)
+        return out
 
     def _set_mutation(self, burn_T, T):
         """species.py:960-967 + genome.py:1060-1104: check the rates against the infinite-sites
         budget, shuffle the mutable loci, hand the bookkeeping to the device (a13)."""
         ga = self.gen_arch
-        if not self.mutate:
-            return
+        kw = {}
         if ga.use_tskit:
-            raise NotImplementedError('mutation with use_tskit=True needs msprime/tskit tables')
-        if ga.traits is not None and any(t.mu > 0 for t in ga.traits.values()):
+            # species.py:891-905 layout: rows = non-neutral loci; the device reads row r as bit nonneut_loci[r]
+            traits = list((ga.traits or {}).values())
+            kw = dict(tskit_layout=True,
+                      trait_mus=[t.mu or 0 for t in traits] if self.mutate else None,
+                      trait_alpha_distr=[(t.alpha_distr_mu, t.alpha_distr_sigma, t.max_alpha_mag) for t in traits],
+                      trait_loci_idxs=[t.loci_idxs for t in traits], delet_loci_idxs=ga.delet_loci_idxs)
+        nonneut = set(int(v) for v in ga.nonneut_loci)
+        nn_sorted = np.array(sorted(nonneut), dtype=np.int64)
+        if not self.mutate:
+            if ga.use_tskit:
+                self._dev.set_mutation(0, 0, [], nn_sorted, ga.delet_loci, ga.delet_loci_s, log_capacity=16, **kw)
+            return
+        if not ga.use_tskit and ga.traits is not None and any(t.mu > 0 for t in ga.traits.values()):
             # genome.py:430: Trait._add_locus indexes loci_idxs, which is None when use_tskit=False
             raise NotImplementedError('trait mutation (Trait.mu > 0) raises in the reference when '
-                                      'use_tskit=False (genome.py:416-437); only mu_neut / mu_delet are supported')
+                                      'use_tskit=False (genome.py:416-437)')
         # mutation.py:24-41 _calc_estimated_total_mutations
         mean_births = float(np.sum(self.K)) * self.b * self.n_births_distr_lambda
         est = int(2.5 * mean_births * ga.L * (T or 0) * ga._mu_tot)
-        nonneut = set(int(v) for v in ga.nonneut_loci)
         if est > 0.75 * (ga.L - len(nonneut)):
             raise MutationRateError('This species has been parameterized with too few neutral loci to '
                                     'accommodate the expected number of mutations. (Geonomics only uses an '
@@ -1033,15 +1140,19 @@ class Species:
         if len(ga.neut_loci) == 0 and ga._mu_tot > 0:        # genome.py:1082-1094
             warnings.warn('non-zero mutation rates but no neutral loci: mutation switched off')
             ga.mu_neut = ga.mu_delet = 0
+            for t in (ga.traits or {}).values():
+                t.mu = 0
             self.mutate = False
+            if ga.use_tskit:
+                kw['trait_mus'] = None
+                self._dev.set_mutation(0, 0, [], nn_sorted, ga.delet_loci, ga.delet_loci_s, log_capacity=16, **kw)
             return
         mutables = [*set(range(ga.L)).difference(nonneut)]    # genome.py:1101-1104
         np.random.shuffle(mutables)
         ga._mutables = [*mutables]
-        self._dev.set_mutation(ga.mu_neut or 0, ga.mu_delet or 0, ga._mutables,
-                               np.sort(np.array(sorted(nonneut), dtype=np.int64)), ga.delet_loci, ga.delet_loci_s,
-                               ga.delet_alpha_distr_shape, ga.delet_alpha_distr_scale,
-                               log_capacity=max(ga.L, 16))
+        self._dev.set_mutation(ga.mu_neut or 0, ga.mu_delet or 0, ga._mutables, nn_sorted, ga.delet_loci,
+                               ga.delet_loci_s, ga.delet_alpha_distr_shape, ga.delet_alpha_distr_scale,
+                               log_capacity=max(ga.L, 16), **kw)
 
     def _sync_mutations(self):
         """Pull the device's mutation log and bookkeeping into gen_arch (what mutation.py:199-205
@@ -1055,6 +1166,17 @@ class Species:
         ga.neut_loci = np.array(sorted(set(range(ga.L)).difference(set(int(v) for v in ga.nonneut_loci))))
         ga.delet_loci = st['delet_loci'].astype(np.int64)
         ga.delet_loci_s = st['delet_s']
+        if ga.use_tskit and rows:
+            traits, di = self._dev.read_mutation_tables()     # genome.py:416-437, 779-782, as written
+            ga.delet_loci_idxs = di.astype(np.int64)
+            for t, tr in zip((ga.traits or {}).values(), traits):
+                t.loci, t.alpha, t.loci_idxs = tr['loci'].astype(np.int64), tr['alpha'], tr['loci_idxs'].astype(np.int64)
+                t.n_loci = len(t.loci)
+            if self._tc is not None:                           # mutation.py:44-58
+                self._tc.mutations.append_columns(site=[r['locus'] for r in rows], node=[r['node'] for r in rows],
+                                                  time=[-1.0 * (r['t'] - self._tsk_t0) for r in rows])
+                nn = self._tc.sites.nonneutral
+                # (the reference leaves the sites metadata as assigned at the start, species.py:994-1002)
         self.mutations.extend(rows)
         if self.mut_log:
             with open(self.mut_log, 'a') as f:
@@ -1177,7 +1299,30 @@ class Model:
                     spp._set_t()
                     spp._step(1)
             self._make_changes()
+            self._simplify_if_due()
         return any(spp.extinct for spp in self.comm.values())
+
+    @staticmethod
+    def _have_tskit():
+        import importlib.util
+        return importlib.util.find_spec('tskit') is not None
+
+    def _next_simplify_t(self, spp):
+        """model.py:756-768: the tables are sorted and simplified after the step at every t with
+        (t + 1) % tskit_simp_interval == 0 -- tskit's own algorithms, so only where tskit is installed; without
+        it the rows keep accumulating as columns (Species._tc) and `Species._tc_sorted_and_simplified` stays False."""
+        ga = spp.gen_arch
+        if ga is None or not ga.use_tskit or spp.__dict__.get('_tc') is None or not self._have_tskit():
+            return None
+        k = int(ga.tskit_simp_interval)
+        return (self.t + 1) + (k - 1 - (self.t + 1) % k)
+
+    def _simplify_if_due(self):
+        for spp in self.comm.values():
+            ga = spp.gen_arch
+            if (ga is not None and ga.use_tskit and spp.__dict__.get('_tc') is not None and self.t != -1
+                    and (self.t + 1) % int(ga.tskit_simp_interval) == 0 and self._have_tskit()):
+                spp._sort_and_simplify_table_collection()
 
     def _make_changes(self):
         """The tail of the main queue (model.py:646-656): the landscape change of this time step,
@@ -1234,6 +1379,9 @@ class Model:
                     events.append(changer.changes[changer._pos][0])
                 if spp._changer is not None and spp._changer._next_t() is not None:
                     events.append(spp._changer._next_t())
+                simp = self._next_simplify_t(spp)
+                if simp is not None:
+                    events.append(simp)
                 if events:
                     n = max(1, min(n, min(events) - self.t))
                 if changer is not None and spp.__dict__.get('_K_overridden'):
@@ -1246,6 +1394,7 @@ class Model:
                 self.comm.t += ran
                 done += ran
                 self._make_changes()                                  # model.py:646-656
+                self._simplify_if_due()                               # model.py:756-768
                 if ran < n:
                     break
             return

@@ -2275,7 +2275,8 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
                            field == GNX_F_IDX || field == GNX_F_Z || field == GNX_F_FIT || field == GNX_F_GSLOT ||
                            field == GNX_F_GENOMES;
   const bool work_field = field == GNX_F_N_NBRS || field == GNX_F_MATE || field == GNX_F_PAIRS || field == GNX_F_PERM ||
-                          field == GNX_F_DEATH_P || field == GNX_F_ALIVE || field == GNX_F_E;
+                          field == GNX_F_DEATH_P || field == GNX_F_ALIVE || field == GNX_F_E ||
+                          field == GNX_F_NODE0 || field == GNX_F_NODE1;
   if (state_field || work_field) {
     if ((r = build_order(ctx, h, false)) != GNX_OK) return r;
   }
@@ -2301,6 +2302,11 @@ extern "C" int gnx_device_ptr(gnx_ctx* ctx, int32_t field, void** dev_ptr, int64
       p = ctx->d_stage_genomes;
       b = (size_t)h.n * 2 * ctx->Wq * sizeof(uint4);
       break;
+    case GNX_F_NODE0:
+    case GNX_F_NODE1:
+      if (!ctx->tsk.enabled) { g_last_error = "tskit recording not enabled"; return GNX_ERR_STATE; }
+      k_gather_by_inv<int32_t><<<g4, 256, 0, s>>>(P.node[field == GNX_F_NODE1 ? 1 : 0][h.cur], (int32_t*)W.scratch, W.inv, ne);
+      p = W.scratch; b = n * 4; break;
     case GNX_F_N_NBRS:
       k_gather_by_inv<int32_t><<<g4, 256, 0, s>>>(W.n_nbrs, (int32_t*)W.scratch, W.inv, ne);
       p = W.scratch; b = n * 4; break;

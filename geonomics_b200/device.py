@@ -22,7 +22,7 @@ _DT = {
     'VALS_N': np.float64, 'VALS_P': np.float64, 'GRAD_N': np.float64, 'GRAD_P': np.float64,
     'N_RAST': np.float64, 'NPAIRS_RAST': np.float64, 'D_RAST': np.float64, 'K_RAST': np.float64,
     'DEATH_P': np.float64, 'ALIVE': np.uint8, 'DISP_TRIES': np.int32, 'E': np.float64, 'Z': np.float64,
-    'COUNTERS': np.int32, 'GENOMES': np.uint32,
+    'COUNTERS': np.int32, 'GENOMES': np.uint32, 'NODE0': np.int32, 'NODE1': np.int32,
 }
 
 

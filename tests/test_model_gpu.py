@@ -383,3 +383,86 @@ def test_run_iterates_n_its(rand_genarch, repeat_burn, rand_comm):
     if rand_genarch:
         # iterations drew different architectures: at least the trait loci or effect sizes moved
         assert mod.orig_comm[0]['gen_arch'] is not spp.gen_arch
+
+
+def test_use_tskit_model_tables_replay_to_the_genotypes():
+    """gen_arch.use_tskit = True through the host API (species.py:891-905, 956-1094, 692-736; mutation.py:44-58):
+    the genotype views hold one ROW per non-neutral locus, the tables fill from the device row buffers over a
+    multi-step walk, and replaying the edges (and mutations) from the starting nodes reproduces the genotype
+    rows of everyone alive -- the invariant the reference checks through tskit (species.py:762-801)."""
+    import copy
+    from geonomics_b200 import api
+    p = copy.deepcopy(api.read_parameters_file(PARAMS))
+    g = p['comm']['species']['spp_0']['gen_arch']
+    g.update(use_tskit=True, tskit_simp_interval=7, L=200, r_distr_alpha=None, mu_neut=5e-6, mu_delet=8e-6,
+             start_neut_zero=True)
+    g['traits']['trait_0'].update(mu=8e-6, n_loci=6)
+    p['model']['T'] = 25
+    mod = api.make_model(p)
+    mod.walk(10000, 'burn')
+    spp = mod.comm[0]
+    ga = spp.gen_arch
+    nn0 = np.array(ga.nonneut_loci, dtype=np.int64)
+    tc = spp._tc
+    n0 = len(spp)
+    assert tc.nodes.num_rows == 2 * n0 and tc.individuals.num_rows == n0 and tc.sites.num_rows == 200
+    g0 = mod.get_genotypes()
+    assert g0.shape == (n0, len(nn0), 2)                       # rows = non-neutral loci
+    # haplotypes of the starting nodes at the starting non-neutral loci: node 2k + h = (individual k, homologue h)
+    hap = {}
+    for k in range(n0):
+        hap[2 * k], hap[2 * k + 1] = g0[k, :, 0].copy(), g0[k, :, 1].copy()
+    start_muts = tc.mutations.num_rows
+    # starting mutations at the non-neutral sites are exactly the 1-alleles (genome.py:1137-1147)
+    ms, mn = tc.mutations.site, tc.mutations.node
+    col_of = {int(l): c for c, l in enumerate(nn0)}
+    cnt = np.zeros((2 * n0, len(nn0)), np.int8)
+    for s_, n_ in zip(ms, mn):
+        if int(s_) in col_of:
+            cnt[n_, col_of[int(s_)]] = 1
+    assert np.array_equal(cnt, g0.transpose(0, 2, 1).reshape(2 * n0, len(nn0)))
+    steps = 23                                                # several drains (the buffers hold <= 7 steps)
+    mod.walk(steps, 'main')
+    births = int(np.sum(spp.n_births[-steps:]))
+    assert tc.nodes.num_rows == 2 * (n0 + births) and tc.individuals.num_rows == n0 + births
+    assert len(spp.mutations) >= 3 and {'delet'} <= {r['type'] for r in spp.mutations}
+    assert tc.mutations.num_rows == start_muts + len(spp.mutations)
+    # node times: -t of the birth step, t = 0 .. steps - 1
+    times = tc.nodes.time[2 * n0:]
+    assert times.max() == 0 and times.min() == -(steps - 1) and np.all(np.diff(times) <= 0)
+    # replay: every new node inherits, locus by locus, from the parent node whose edge covers the locus
+    el, er, ep, ec = tc.edges.left, tc.edges.right, tc.edges.parent, tc.edges.child
+    order = np.argsort(ec, kind='stable')
+    el, er, ep, ec = el[order], er[order], ep[order], ec[order]
+    lo = np.searchsorted(ec, np.arange(2 * n0, 2 * (n0 + births)), side='left')
+    hi = np.searchsorted(ec, np.arange(2 * n0, 2 * (n0 + births)), side='right')
+    pos = nn0.astype(np.float64)
+    new_muts = {}
+    for r in spp.mutations:
+        new_muts.setdefault(int(r['node']), []).append(int(r['locus']))
+    for j, node in enumerate(range(2 * n0, 2 * (n0 + births))):
+        l_, r_, p_ = el[lo[j]:hi[j]], er[lo[j]:hi[j]], ep[lo[j]:hi[j]]
+        assert l_[0] == 0 and r_[-1] == 200 and np.all(l_[1:] == r_[:-1])
+        seg = np.searchsorted(r_, pos, side='right')          # locus l lies in [left, right)
+        hap[node] = np.array([hap[int(p_[s])][c] for c, s in enumerate(seg)], dtype=np.int8)
+    # everyone alive: rows of the STARTING non-neutral loci equal the replayed haplotypes of their two nodes
+    nodes = spp._node_ids()
+    g_now = mod.get_genotypes()
+    nn_now = np.array(ga.nonneut_loci, dtype=np.int64)
+    assert g_now.shape == (len(spp), len(nn_now), 2) and len(nn_now) > len(nn0)
+    rows_of_start = np.searchsorted(nn_now, nn0)
+    for k in range(len(spp)):
+        for h in (0, 1):
+            assert np.array_equal(g_now[k, rows_of_start, h], hap[int(nodes[k, h])]), (k, h)
+    # rows added by non-neutral mutations: the 1-alleles descend from the mutated node only
+    new_rows = np.setdiff1d(np.arange(len(nn_now)), rows_of_start)
+    assert g_now[:, new_rows, :].sum() >= 0 and set(nn_now[new_rows]) == {r['locus'] for r in spp.mutations
+                                                                           if r['type'] != 'neut'}
+    # individuals table: metadata idx and node -> individual links of everyone alive
+    ids = np.array([i for i in spp])
+    ind_rows = tc.nodes.individual[nodes[:, 0]]
+    assert np.array_equal(ind_rows, tc.nodes.individual[nodes[:, 1]])
+    assert np.array_equal(tc.individuals.idx[ind_rows], ids)
+    # trait bookkeeping came back (genome.py:416-437)
+    t0 = ga.traits[0]
+    assert len(t0.loci) == len(t0.alpha) == len(t0.loci_idxs) == t0.n_loci >= 6
