@@ -1305,7 +1305,15 @@ class Model:
     @staticmethod
     def _have_tskit():
         import importlib.util
-        return importlib.util.find_spec('tskit') is not None
+        import sys
+        import types
+        mod = sys.modules.get('tskit')
+        if mod is not None:                               # a test shim in sys.modules is not tskit
+            return isinstance(mod, types.ModuleType) and getattr(mod, '__file__', None) is not None
+        try:
+            return importlib.util.find_spec('tskit') is not None
+        except (ValueError, ImportError):
+            return False
 
     def _next_simplify_t(self, spp):
         """model.py:756-768: the tables are sorted and simplified after the step at every t with
