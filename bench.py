@@ -509,12 +509,15 @@ def strips_block(dist, rank, world, name, presteps, steps):
     tmax, tsum = t.clone(), t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    sync_by_device = st.device_barrier
     st.close()
     ms_all, ind_all = float(tmax[0]), float(tsum[1])
     return {'workload': name + ': ' + workload_desc(cfg), 'scaling': 'strong', 'n_gpus': world,
             'decomposition': '%d horizontal strips of mating-grid rows (cut by carrying capacity), halo = one mating-grid '
-                             'row, records by peer writes over NVLink (CUDA IPC), NCCL barriers + 3 small collectives '
-                             'per step' % world,
+                             'row, records by peer writes over NVLink (CUDA IPC); ' % world +
+                             ('the 4 barriers and 3 small collectives of a step are one-CTA kernels over peer memory '
+                              '(gnx_strip_barrier), no NCCL inside the step' if sync_by_device else
+                              'NCCL barriers + 3 small collectives per step'),
             'simulated_steps_before_timing': presteps, 'steps': steps, 'ms_per_step': ms_all / steps,
             'value': ind_all / (ms_all * 1e-3), 'unit': UNIT,
             'load_imbalance_max_over_mean': float(tmax[2]) / (float(tsum[2]) / world)}

@@ -127,6 +127,8 @@ class StripEndpoints(C.Structure):
         ('buf_offset', C.c_int64 * 4),
         ('count_offset', C.c_int64 * 4),
         ('ipc_handle', C.c_ubyte * 64),
+        ('sync_offset', C.c_int64),
+        ('counts_cap', C.c_int64),
     ]
 
 
@@ -212,6 +214,7 @@ SIGNATURES = {
     'gnx_strip_collective_ptrs': (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                             C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
     'gnx_strip_phase': (C.c_int, [_ctx, C.c_int32]),
+    'gnx_strip_barrier': (C.c_int, [_ctx, C.c_int32]),
     'gnx_strip_check': (C.c_int, [_ctx]),
     'gnx_set_K': (C.c_int, [_ctx, c_double_p]),
     'gnx_set_life_history': (C.c_int, [_ctx, C.POINTER(Config)]),

@@ -111,6 +111,8 @@ struct gnx_ctx {
   Strip* d_strip = nullptr;             // nullptr: the landscape is not decomposed
   unsigned char* strip_block = nullptr; // [counters | 4 receive buffers]: one allocation, one IPC handle
   size_t strip_block_bytes = 0;
+  int64_t strip_sync_off = 0;
+  int strip_connected = 0;            // peers whose synchronisation page is mapped
   int64_t strip_buf_off[STRIP_N_BUF] = {0, 0, 0, 0};
   std::vector<void*> strip_allocs;
   std::vector<void*> strip_ipc_opened;
@@ -1846,8 +1848,10 @@ extern "C" int gnx_sample_env(gnx_ctx* ctx) {
 // counting sort into mating-grid order are ONE pass over the state (k_move_key flags and keys,
 // k_regrid moves); under panmixia there is no grid, so the dead are compacted away at the end
 // of the step as the staged entry points do.
+static int strip_whole_step(gnx_ctx* ctx);
 static int one_step(gnx_ctx* ctx) {
   int r;
+  if (ctx->d_strip) return strip_whole_step(ctx);     // one strip of a decomposed landscape: eight phases + barriers
   const bool panmixia = ctx->cfg.mating_radius <= 0;
   if (panmixia) {
     if ((r = move_key(ctx, 1, ctx->cfg.move ? 1 : 0, 0))) return r;
@@ -1940,7 +1944,12 @@ static int capture_step(gnx_ctx* ctx) {
 extern "C" int gnx_step(gnx_ctx* ctx, int32_t n_steps) {
   ARG(ctx && n_steps >= 0, "n_steps");
   USE_DEVICE(ctx);
-  if (ctx->d_strip) { g_last_error = "this context holds one strip of a decomposed landscape: drive it with gnx_strip_phase"; return GNX_ERR_STATE; }
+  if (ctx->d_strip) {
+    // one strip of a decomposed landscape: whole steps with the barriers and collectives over peer memory
+    // (gnx_strip_barrier) -- every rank makes the same call; one CUDA graph per step like the undecomposed run
+    ARG(!ctx->prm.ordered, "injected per-individual draws are not supported under strip decomposition");
+    if (ctx->strip_connected != ctx->strip_h.world - 1) { g_last_error = "gnx_step on a strip: not every peer is connected"; return GNX_ERR_STATE; }
+  }
   if (ctx->records_pending + n_steps > ctx->work.max_records) {
     // never drop a step record: the caller drains them (gnx_read_step_records) at least every
     // max_records steps; nothing has been launched when this is returned
@@ -2021,13 +2030,21 @@ extern "C" int gnx_strip_enable(gnx_ctx* ctx, const gnx_strip_config_t* sc) {
     const size_t rec = k == STRIP_BUF_CHOICES ? sizeof(StripChoice) : (size_t)S.rec_bytes;
     off += ((size_t)S.cap[k] * rec + 255) & ~(size_t)255;
   }
+  // ... and the synchronisation page (k_strip_barrier): flags, births, max(N) and counts slots, one per rank
+  S.counts_cap = ctx->have_density ? ((2 * ctx->dens.npts + 63) & ~63) : 0;
+  ctx->strip_sync_off = (int64_t)off;
+  const size_t sync_bytes = STRIP_SYNC_COUNTS + (size_t)GNX_STRIP_MAX_WORLD * S.counts_cap * 4;
+  off += (sync_bytes + 255) & ~(size_t)255;
   ctx->strip_block_bytes = off;
   CK(cudaMalloc((void**)&ctx->strip_block, off));
   CK(cudaMemsetAsync(ctx->strip_block, 0, 256, ctx->stream));
+  CK(cudaMemsetAsync(ctx->strip_block + ctx->strip_sync_off, 0, sync_bytes, ctx->stream));
   for (int k = 0; k < STRIP_N_BUF; ++k) {
     S.peer[S.rank].buf[k] = ctx->strip_block + ctx->strip_buf_off[k];
     S.peer[S.rank].count[k] = reinterpret_cast<int32_t*>(ctx->strip_block) + 16 * k;
   }
+  S.peer[S.rank].sync = ctx->strip_block + ctx->strip_sync_off;
+  ctx->strip_connected = 0;
   S.list_cap = S.cap[STRIP_BUF_MIGRANTS] + 2 * S.cap[STRIP_BUF_HALO];
   DM(ctx, &S.list_entry, (size_t)S.list_cap, &ctx->strip_allocs);
   DM(ctx, &S.list_dest, (size_t)S.list_cap, &ctx->strip_allocs);
@@ -2035,6 +2052,8 @@ extern "C" int gnx_strip_enable(gnx_ctx* ctx, const gnx_strip_config_t* sc) {
   S.err = S.list_n + 1;
   DM(ctx, &S.sent, (size_t)ctx->pop.cap, &ctx->strip_allocs);
   DM(ctx, &S.births, GNX_STRIP_MAX_WORLD, &ctx->strip_allocs);
+  DM(ctx, &S.epoch, 4, &ctx->strip_allocs);
+  CK(cudaMemsetAsync(S.epoch, 0, 16, ctx->stream));
   DM(ctx, &ctx->d_strip, 1, &ctx->strip_allocs);
   drop_graph(ctx);
   return strip_upload(ctx);
@@ -2050,6 +2069,8 @@ extern "C" int gnx_strip_endpoints(gnx_ctx* ctx, gnx_strip_endpoints_t* out) {
     out->buf_offset[k] = ctx->strip_buf_off[k];
     out->count_offset[k] = 64 * k;
   }
+  out->sync_offset = ctx->strip_sync_off;
+  out->counts_cap = ctx->strip_h.counts_cap;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, ctx->strip_block));
   static_assert(sizeof(h) == sizeof(out->ipc_handle), "CUDA IPC handle is 64 bytes");
@@ -2076,7 +2097,26 @@ extern "C" int gnx_strip_connect(gnx_ctx* ctx, int32_t peer_rank, const gnx_stri
     S.peer[peer_rank].buf[k] = base + ep->buf_offset[k];
     S.peer[peer_rank].count[k] = reinterpret_cast<int32_t*>(base + ep->count_offset[k]);
   }
+  ARG(ep->counts_cap == S.counts_cap, "the peer's density lattice differs from this rank's");
+  if (!S.peer[peer_rank].sync) ctx->strip_connected += 1;
+  S.peer[peer_rank].sync = base + ep->sync_offset;
   return strip_upload(ctx);
+}
+
+// Barrier (kind 0) or one of the three small collectives of a time step (1: births all-gather after phase
+// 3, 2: density-count sum after phase 5, 3: max(N) after phase 6) over peer memory, enqueued on the rank's
+// stream: see k_strip_barrier.  Every rank must make the same sequence of calls.
+static int strip_barrier_launch(gnx_ctx* ctx, int kind);
+extern "C" int gnx_strip_barrier(gnx_ctx* ctx, int32_t kind) {
+  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  ARG(kind >= 0 && kind <= 3, "kind");
+  if (ctx->strip_connected != ctx->strip_h.world - 1) { g_last_error = "gnx_strip_barrier: not every peer is connected"; return GNX_ERR_STATE; }
+  if (kind == 2 && (!ctx->have_density || ctx->strip_h.counts_cap < 2 * ctx->dens.npts)) {
+    g_last_error = "gnx_strip_barrier: the density lattice was set after gnx_strip_enable";
+    return GNX_ERR_STATE;
+  }
+  return strip_barrier_launch(ctx, kind);
 }
 
 extern "C" int gnx_strip_collective_ptrs(gnx_ctx* ctx, void** births, void** counts, int64_t* n_counts, void** nmax) {
@@ -2117,18 +2157,11 @@ static int strip_recv(gnx_ctx* ctx, int which, int mode) {
 //   5 receive newborns; density counts                         | all-reduce (sum) of `counts`
 //   6 N raster over the strip's rows                           | all-reduce (max) of `nmax`
 //   7 d raster; death probabilities and mortality draw; end of step
-extern "C" int gnx_strip_phase(gnx_ctx* ctx, int32_t phase) {
-  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
-  USE_DEVICE(ctx);
-  ARG(!ctx->prm.ordered, "injected per-individual draws are not supported under strip decomposition");
+static int strip_phase_launch(gnx_ctx* ctx, int phase) {
   cudaStream_t s = ctx->stream;
   int r;
   switch (phase) {
     case 0:
-      if (ctx->records_pending + 1 > ctx->work.max_records) {
-        g_last_error = "step-record buffer would overflow: call gnx_read_step_records first";
-        return GNX_ERR_STATE;
-      }
       if ((r = move_key(ctx, 0, ctx->cfg.move ? 1 : 0, 1))) return r;
       return strip_send(ctx, STRIP_BUF_MIGRANTS);
     case 1:
@@ -2173,13 +2206,48 @@ extern "C" int gnx_strip_phase(gnx_ctx* ctx, int32_t phase) {
       if ((r = death_prob(ctx, 1))) return r;
       k_strip_end_step<<<1, 1, 0, s>>>(ctx->d_c);
       LAUNCHED(ctx);
-      ctx->records_pending += 1;
-      ctx->steps_done += 1;
-      ctx->pending = true;
-      ctx->order_valid = false;
       return GNX_OK;
     default:
       ARG(false, "phase must be 0..7");
+  }
+  return GNX_OK;
+}
+
+static int strip_barrier_launch(gnx_ctx* ctx, int kind) {
+  PROF(ctx, "k_strip_barrier");
+  k_strip_barrier<<<1, 256, 0, ctx->stream>>>(ctx->d_strip, kind, ctx->dens.counts, 2 * ctx->dens.npts,
+                                              reinterpret_cast<unsigned long long*>(&ctx->d_c->nmax_bits));
+  LAUNCHED(ctx);
+  return GNX_OK;
+}
+
+// the whole time step of one strip: phase, then the barrier / collective that follows it (gnx_step captures
+// this into one CUDA graph; the spin barriers inside it order the ranks' graphs against each other)
+static int strip_whole_step(gnx_ctx* ctx) {
+  static const int sync_after[8] = {0, 0, 0, 1, 0, 2, 3, -1};
+  for (int k = 0; k < 8; ++k) {
+    int r = strip_phase_launch(ctx, k);
+    if (r != GNX_OK) return r;
+    if (sync_after[k] >= 0 && (r = strip_barrier_launch(ctx, sync_after[k])) != GNX_OK) return r;
+  }
+  return GNX_OK;
+}
+
+extern "C" int gnx_strip_phase(gnx_ctx* ctx, int32_t phase) {
+  ARG(ctx && ctx->d_strip, "strip decomposition is not enabled");
+  USE_DEVICE(ctx);
+  ARG(!ctx->prm.ordered, "injected per-individual draws are not supported under strip decomposition");
+  if (phase == 0 && ctx->records_pending + 1 > ctx->work.max_records) {
+    g_last_error = "step-record buffer would overflow: call gnx_read_step_records first";
+    return GNX_ERR_STATE;
+  }
+  int r = strip_phase_launch(ctx, phase);
+  if (r != GNX_OK) return r;
+  if (phase == 7) {
+    ctx->records_pending += 1;
+    ctx->steps_done += 1;
+    ctx->pending = true;
+    ctx->order_valid = false;
   }
   return GNX_OK;
 }
@@ -2191,6 +2259,10 @@ extern "C" int gnx_strip_check(gnx_ctx* ctx) {
   int32_t e = 0;
   CK(cudaMemcpyAsync(&e, ctx->strip_h.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (e & 4) {
+    g_last_error = "strip barrier: a peer rank never arrived (gnx_strip_barrier timed out)";
+    return GNX_ERR_STATE;
+  }
   if (e) {
     g_last_error = (e & 2) ? "strip exchange: a receive buffer overflowed (raise migrant_capacity / halo_capacity)"
                            : "strip exchange: the send list overflowed";

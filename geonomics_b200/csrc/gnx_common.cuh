@@ -216,7 +216,13 @@ enum { STRIP_BUF_MIGRANTS = 0, STRIP_BUF_HALO = 1, STRIP_BUF_NEWBORNS = 2, STRIP
 struct StripPeer {
   unsigned char* buf[STRIP_N_BUF];   // receive buffers of that rank
   int32_t* count[STRIP_N_BUF];       // records claimed in each
+  unsigned char* sync;               // that rank's synchronisation page (k_strip_barrier): one slot per writer
 };
+// layout of a rank's synchronisation page; rank w writes only slot w of every page
+#define STRIP_SYNC_FLAGS 0           // uint32[MAX_WORLD]: barrier epoch each rank has reached
+#define STRIP_SYNC_BIRTHS 128        // int64[MAX_WORLD]: births of each rank this step
+#define STRIP_SYNC_NMAX 256          // uint64[MAX_WORLD]: bits of each rank's max(N)
+#define STRIP_SYNC_COUNTS 384        // int32[MAX_WORLD][counts_cap]: each rank's coarse density counts
 struct Strip {
   int32_t enabled;
   int32_t rank, world;
@@ -234,7 +240,10 @@ struct Strip {
   int32_t* list_dest;
   int32_t* list_n;                   // [1]
   int32_t list_cap;
-  int32_t* err;                      // [1] sticky: a receive buffer or the list overflowed
+  int32_t* err;                      // [1] sticky: bit 0 a receive buffer or the list overflowed, bit 2 a peer never
+                                     //     reached a barrier
+  uint32_t* epoch;                   // [1] barriers this rank has entered
+  int32_t counts_cap;                // ints per rank slot of the counts exchange
 };
 
 struct DevDraws {

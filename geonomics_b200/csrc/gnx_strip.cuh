@@ -250,3 +250,78 @@ __global__ void k_strip_end_step(Counters* c) {
 }
 // this rank's births, where the all-gather picks them up
 __global__ void k_strip_publish_births(const Counters* c, const Strip* st) { st->births[st->rank] = (long long)c->B; }
+
+// ========================================================================================
+// Barrier and the three small collectives of a strip time step, over peer memory.
+// Every rank owns a synchronisation page inside its receive block (mapped by all peers through
+// CUDA IPC / NVLink like the record buffers); rank w writes only slot w of every page, so nothing
+// is ever contended: the payload first (kind 1: this rank's births -> all-gather; kind 2: its
+// coarse density counts -> sum over the ranks in rank order, so the integers are the same on every
+// rank; kind 3: the bits of its max(N) -> maximum), a system-scope fence, then the rank's barrier
+// epoch with release semantics into every peer's flag word; the lanes then spin (acquire loads) on
+// the flags of this rank's own page until every peer has reached the same epoch.  Kernels of a rank
+// are stream-ordered, so a peer that reads a slot has finished with it before the writer can get to
+// the next barrier of the same kind (there is at least one other barrier in between).  One launch of
+// one CTA replaces an NCCL collective (and its launch gap) after seven of the eight phases.  A peer
+// that never arrives (a failed rank) ends the wait after ~5 s with the error bit set instead of
+// hanging the device.
+// ========================================================================================
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_strip_barrier(const Strip* stp, int kind, int32_t* counts, int n_counts,
+                                                       unsigned long long* nmax) {
+  const Strip& st = *stp;
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++(*st.epoch);
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  const int W = st.world, me = st.rank, tid = threadIdx.x;
+  if (kind == 1) {
+    if (tid < W) reinterpret_cast<int64_t*>(st.peer[tid].sync + STRIP_SYNC_BIRTHS)[me] = st.births[me];
+  } else if (kind == 2) {
+    for (int k = tid; k < W * n_counts; k += blockDim.x) {
+      const int r = k / n_counts, i = k - r * n_counts;
+      reinterpret_cast<int32_t*>(st.peer[r].sync + STRIP_SYNC_COUNTS)[(size_t)me * st.counts_cap + i] = counts[i];
+    }
+  } else if (kind == 3) {
+    if (tid < W) reinterpret_cast<unsigned long long*>(st.peer[tid].sync + STRIP_SYNC_NMAX)[me] = *nmax;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < W && tid != me) {
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(st.peer[tid].sync + STRIP_SYNC_FLAGS) + me, e);
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(st.peer[me].sync + STRIP_SYNC_FLAGS) + tid;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(f) - e) < 0) {
+      if (clock64() - t0 > (10ll << 30)) { atomicOr(st.err, 4); break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const unsigned char* mine = st.peer[me].sync;
+  if (kind == 1) {
+    if (tid < W) st.births[tid] = reinterpret_cast<const volatile int64_t*>(mine + STRIP_SYNC_BIRTHS)[tid];
+  } else if (kind == 2) {
+    const volatile int32_t* in = reinterpret_cast<const volatile int32_t*>(mine + STRIP_SYNC_COUNTS);
+    for (int i = tid; i < n_counts; i += blockDim.x) {
+      int32_t sum = 0;
+      for (int r = 0; r < W; ++r) sum += in[(size_t)r * st.counts_cap + i];
+      counts[i] = sum;
+    }
+  } else if (kind == 3) {
+    if (tid == 0) {
+      const volatile unsigned long long* in = reinterpret_cast<const volatile unsigned long long*>(mine + STRIP_SYNC_NMAX);
+      unsigned long long m = 0;                       // non-negative doubles order like their bit patterns
+      for (int r = 0; r < W; ++r) m = in[r] > m ? in[r] : m;
+      *nmax = m;
+    }
+  }
+}

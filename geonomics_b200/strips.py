@@ -137,6 +137,10 @@ class StripRank:
     def phase(self, k):
         _lib.check(self.dev._L.gnx_strip_phase(self.dev._ctx, int(k)), 'gnx_strip_phase')
 
+    def barrier(self, kind=0):
+        """gnx_strip_barrier: the barrier (0) or a collective (1 births, 2 counts, 3 max(N)) over peer memory."""
+        _lib.check(self.dev._L.gnx_strip_barrier(self.dev._ctx, int(kind)), 'gnx_strip_barrier')
+
     def check(self):
         _lib.check(self.dev._L.gnx_strip_check(self.dev._ctx), 'gnx_strip_check')
 
@@ -146,6 +150,10 @@ class StripRank:
         counts = torch.as_tensor(_DevArray(self.counts_ptr, self.n_counts, '<i4'), device='cuda')
         nmax = torch.as_tensor(_DevArray(self.nmax_ptr, 1, '<i8'), device='cuda')      # bits of a double >= 0
         return births, counts, nmax
+
+
+# what follows each phase: the barrier / collective kind of gnx_strip_barrier (phase 7 ends the step)
+PHASE_SYNC = {0: 0, 1: 0, 2: 0, 3: 1, 4: 0, 5: 2, 6: 3}
 
 
 def _subset(pop, mask):
@@ -159,10 +167,15 @@ def _subset(pop, mask):
 class LocalStrips:
     """`world` strips as contexts of this process on the current GPU."""
 
-    def __init__(self, world, land_dim, rasters, prm, gen_arch, capacity, seed=0, bounds=None, **kw):
+    def __init__(self, world, land_dim, rasters, prm, gen_arch, capacity, seed=0, bounds=None, device_barrier=False,
+                 **kw):
         import torch
         self.torch = torch
         self.world = int(world)
+        # device_barrier: the ranks synchronise through gnx_strip_barrier (no host round trip inside a step);
+        # otherwise the host is the barrier and does the three collectives on the ranks' tensors
+        self.device_barrier = bool(device_barrier)
+        self._warm = False
         self.cs, self.ncx, self.ncy = mating_grid(land_dim, prm['mating_radius'])
         K = np.asarray(rasters)[int(prm.get('K_layer', 0))] * float(prm.get('K_factor', 1.0))
         self.bounds = plan_rows(self.ncy, world, row_weights_from_K(K, self.cs, self.ncy)) if bounds is None \
@@ -197,6 +210,26 @@ class LocalStrips:
 
     def step(self, n=1):
         torch = self.torch
+        if self.device_barrier and self._warm:
+            # whole steps through gnx_step (one CUDA graph per rank and step, spin barriers inside); one step of
+            # every rank is enqueued before the next, so no rank's queue fills up while a peer has nothing queued
+            for _ in range(n):
+                for r in self.ranks:
+                    r.dev.step(1)
+            return
+        if self.device_barrier:
+            # The first step of a process loads every kernel (CUDA loads modules lazily, and a load may wait for
+            # the device to drain): with all ranks enqueued by ONE host thread, rank 0's spinning barrier would
+            # wait for a rank the blocked host has not enqueued yet.  One step with the host as the barrier first.
+            # (One process per GPU has no such coupling: a rank's barrier kernel is queued before its host can
+            # block on the next phase's kernels.)
+            self._warm = True
+            self.device_barrier = False
+            try:
+                self.step(1)
+            finally:
+                self.device_barrier = True
+            return self.step(n - 1) if n > 1 else None
         for _ in range(n):
             for k in range(N_PHASES):
                 for r in self.ranks:
@@ -240,10 +273,17 @@ class NcclStrips:
     """This process's strip of a landscape decomposed over the ranks of `torch.distributed`
     (backend nccl, one GPU each, one node: the receive buffers are shared through CUDA IPC)."""
 
-    def __init__(self, land_dim, rasters, prm, gen_arch, capacity, seed=0, bounds=None, group=None, **kw):
+    def __init__(self, land_dim, rasters, prm, gen_arch, capacity, seed=0, bounds=None, group=None,
+                 device_barrier=None, **kw):
+        import os
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
+        # the barriers and the three small collectives of a step run as one-CTA kernels over peer memory
+        # (gnx_strip_barrier); GNX_STRIP_NCCL=1 (or device_barrier=False) keeps them on NCCL for comparison
+        if device_barrier is None:
+            device_barrier = os.environ.get('GNX_STRIP_NCCL', '0') in ('', '0')
+        self.device_barrier = bool(device_barrier)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.cs, self.ncx, self.ncy = mating_grid(land_dim, prm['mating_radius'])
         K = np.asarray(rasters)[int(prm.get('K_layer', 0))] * float(prm.get('K_factor', 1.0))
@@ -281,6 +321,9 @@ class NcclStrips:
 
     def step(self, n=1):
         torch, dist = self.torch, self.dist
+        if self.device_barrier:
+            self.me.dev.step(n)                            # gnx_step: eight phases + gnx_strip_barrier, one graph per step
+            return
         with torch.cuda.stream(self.stream):               # collectives are ordered on the context's stream
             for _ in range(n):
                 for k in range(N_PHASES):

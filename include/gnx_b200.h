@@ -272,6 +272,8 @@ typedef struct {
   int64_t buf_offset[4];         /* migrants, halo, newborns, choices */
   int64_t count_offset[4];
   unsigned char ipc_handle[64];  /* cudaIpcMemHandle_t of the block, for ranks in other processes */
+  int64_t sync_offset;           /* the rank's synchronisation page inside the block (gnx_strip_barrier) */
+  int64_t counts_cap;            /* ints per rank slot of the density-count exchange */
 } gnx_strip_endpoints_t;
 int gnx_strip_enable(gnx_ctx* ctx, const gnx_strip_config_t* cfg);
 int gnx_strip_endpoints(gnx_ctx* ctx, gnx_strip_endpoints_t* out);
@@ -283,6 +285,15 @@ int gnx_strip_collective_ptrs(gnx_ctx* ctx, void** births, void** counts, int64_
 /* one phase (0..7) of a time step on this rank's stream; every rank must have finished phase k
  * before any rank starts phase k + 1 */
 int gnx_strip_phase(gnx_ctx* ctx, int32_t phase);
+/* The barrier between two phases (kind 0) and the three collectives (1 births all-gather, 2 density-count sum,
+ * 3 max(N)) done by ONE one-CTA kernel over peer memory on the rank's stream: every rank writes its slot of
+ * every peer's synchronisation page (NVLink stores), publishes its barrier epoch with release semantics and
+ * spins on its own page until every peer has arrived.  Replaces the caller-supplied NCCL collectives; all
+ * ranks must make the same sequence of calls; a peer that never arrives sets an error after ~5 s. */
+int gnx_strip_barrier(gnx_ctx* ctx, int32_t kind);
+/* gnx_step on a context that holds a strip runs WHOLE time steps this way -- the eight phases with
+ * gnx_strip_barrier after each of the first seven, captured as one CUDA graph per step like the undecomposed
+ * run; the spin barriers inside order the ranks' graphs against each other.  Every rank makes the same call. */
 int gnx_strip_check(gnx_ctx* ctx);      /* synchronises; exchange overflow -> GNX_ERR_CAPACITY */
 
 int gnx_sync(gnx_ctx* ctx);

@@ -54,10 +54,11 @@ def _single(wl, steps, seed=77):
         dev.close()
 
 
-def _strips(wl, world, steps, seed=77, bounds=None):
+def _strips(wl, world, steps, seed=77, bounds=None, device_barrier=False):
     from geonomics_b200.strips import LocalStrips
     dim, rasters, prm, ga, pop, g = wl
-    st = LocalStrips(world, dim, rasters, prm, ga, capacity=4 * len(pop['x']), seed=seed, bounds=bounds)
+    st = LocalStrips(world, dim, rasters, prm, ga, capacity=4 * len(pop['x']), seed=seed, bounds=bounds,
+                     device_barrier=device_barrier)
     try:
         st.upload(pop['x'], pop['y'], pop['age'], pop['sex'], pop['idx'], g=g)
         out = []
@@ -91,6 +92,21 @@ def test_strips_reproduce_the_undecomposed_run(world):
     y0 = wl[4]['y']
     assert ref_recs[0]['n_births'] > 100 and len(ref[-1]['idx']) > 500
     del y0
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('world', [2, 4])
+def test_strips_with_barriers_and_collectives_over_peer_memory(world):
+    """gnx_strip_barrier: the barrier between the phases and the three small collectives (births all-gather,
+    density-count sum, max(N)) as one-CTA kernels that write the peers' synchronisation pages and spin on their
+    own -- no host round trip and no NCCL inside a step; still bit-identical to the undecomposed run."""
+    wl = _workload(surfaces=True, seed=21)
+    ref, ref_recs = _single(wl, 6, seed=13)
+    got, recs, _ = _strips(wl, world, 6, seed=13, device_barrier=True)
+    for t, (a, b) in enumerate(zip(ref, got)):
+        _same(a, b, t)
+    assert [(r['Nt'], r['n_births'], r['n_deaths']) for r in ref_recs] == \
+        [(r['Nt'], r['n_births'], r['n_deaths']) for r in recs]
 
 
 def test_strips_with_surfaces_sexes_and_uneven_rows():

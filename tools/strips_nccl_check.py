@@ -48,8 +48,8 @@ def main():
             ok = ok and np.array_equal(ref[k], got[k])
         ok = ok and all((a['Nt'], a['n_births'], a['n_deaths'], a['n_pairs']) ==
                         (b['Nt'], b['n_births'], b['n_deaths'], b['n_pairs']) for a, b in zip(ref_recs, got_recs))
-        print('strips over %d GPUs (NCCL + CUDA IPC peer writes), %d steps: %s; N %d -> %d; per-rank shares %s'
-              % (world, steps, 'IDENTICAL to the undecomposed run' if ok else 'MISMATCH', len(pop['x']),
+        print('strips over %d GPUs (CUDA IPC peer writes; barriers and collectives by %s), %d steps: %s; N %d -> %d; per-rank shares %s'
+              % (world, 'gnx_strip_barrier over peer memory' if st.device_barrier else 'NCCL', steps, 'IDENTICAL to the undecomposed run' if ok else 'MISMATCH', len(pop['x']),
                  len(got['idx']), [len(s[0]['idx']) for s in shares]), flush=True)
     st.close()
     dist.destroy_process_group()
