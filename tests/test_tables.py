@@ -45,8 +45,8 @@ def test_table_columns_append_births_in_reference_row_order():
 
 
 def test_to_tskit_needs_tskit():
-    import importlib.util
-    if importlib.util.find_spec('tskit') is not None and not hasattr(sys.modules.get('tskit'), '_mock_name'):
+    from geonomics_b200.api import Model
+    if Model._have_tskit():
         pytest.skip('tskit is installed here')
     from geonomics_b200.tables import TableColumns
     saved = sys.modules.pop('tskit', None)
