@@ -306,6 +306,7 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   Ld.max_x = cfg->dim_x - 0.001;
   Ld.max_y = cfg->dim_y - 0.001;
   mating_grid(*cfg, &Ld.cell_size, &Ld.ncx, &Ld.ncy);
+  Ld.inv_cell_size = 1.0 / Ld.cell_size;
   ARG(Ld.ncx < 65536 && Ld.ncy < 65536, "mating grid has more than 65535 cells along one axis");
   ctx->ncell = Ld.ncx * Ld.ncy;
   const size_t plane = (size_t)cfg->dim_x * cfg->dim_y;
@@ -352,6 +353,8 @@ static int create_impl(const gnx_config_t* cfg, gnx_ctx* ctx) {
   // hundred candidates are shared by the at most 9 cells around them): below n / 4 in all
   W.heavy_cap = (int32_t)(cap / 4 + 1024);
   DM(ctx, &W.heavy, (size_t)W.heavy_cap);
+  DM(ctx, &W.fm_list, (size_t)cap);
+  DM(ctx, &W.fm_count, 4);
   DM(ctx, &W.n_nbrs, cap);
   DM(ctx, &W.pairs, 2 * cap);
   DM(ctx, &W.pair_slots, 2 * cap);
@@ -1280,10 +1283,19 @@ static int find_mates(gnx_ctx* ctx) {
 #ifndef GNX_FMD_GRID
 #define GNX_FMD_GRID 6
 #endif
-  const int g = grid_cap(ctx, GNX_FM_GRID, GNX_FM_BLOCK);
+  // the thread-per-focal search walks the list of focals that may mate: a fraction b of the population
+  const int g = grid_cap(ctx, GNX_FM_GRID, GNX_FM_BLOCK, ctx->prm.store_debug ? 1.0 : std::min(1.0, ctx->cfg.b + 0.05));
   const bool uniform_choice = !ctx->cfg.choose_nearest && !ctx->cfg.inverse_dist;
   if (uniform_choice)     // n_heavy, heavy_next: the crowded-cell list starts empty
     CK(cudaMemsetAsync(&ctx->d_c->n_heavy, 0, 2 * sizeof(int32_t), ctx->stream));
+  CK(cudaMemsetAsync(ctx->work.fm_count, 0, sizeof(int32_t), ctx->stream));
+  // Bernoulli(b) first: list the focals that may mate (and announce the crowded cells' work items)
+#define FS(MODE) k_mate_select<MODE><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
+  if (ctx->cfg.choose_nearest) FS(1);
+  else if (ctx->cfg.inverse_dist) FS(2);
+  else FS(0);
+#undef FS
+  LAUNCHED(ctx);
 #define FM(MODE) k_find_mates<MODE><<<g, GNX_FM_BLOCK, 0, ctx->stream>>>(ctx->pop, ctx->land, ctx->prm, ctx->draws, ctx->work, ctx->d_c)
   if (ctx->cfg.choose_nearest) FM(1);
   else if (ctx->cfg.inverse_dist) FM(2);

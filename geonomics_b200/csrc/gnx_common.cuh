@@ -110,7 +110,7 @@ struct Land {
   int32_t X, Y, n_layers;
   double max_x, max_y;     // dim - 0.001 (movement.py:89-92)
   // mating grid
-  double cell_size;
+  double cell_size, inv_cell_size;   // inv_cell_size = fl(1 / cell_size), see cell_index
   int32_t ncx, ncy;
 };
 
@@ -162,6 +162,8 @@ struct Work {
   int32_t* mate;
   uint2* heavy;            // work items of k_find_mates_dense: {packed key of a crowded mating cell, first focal of a batch of 32}
   int32_t heavy_cap;
+  int32_t* fm_list;        // focals whose Bernoulli(b) draw lets them mate (k_mate_select), the only ones searched
+  int32_t* fm_count;       // [1]
   int32_t* n_nbrs;
   int32_t* pairs;          // [cap][2]
   int32_t* pair_slots;     // [cap][2] genome slots of each pair's parents

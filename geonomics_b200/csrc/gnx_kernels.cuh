@@ -149,8 +149,19 @@ __device__ __forceinline__ void sincos_half_tab(const uint32_t* __restrict__ cs_
 }
 
 // mating-grid cell of a position, packed (cy << 16 | cx); the grid has < 65536 cells per axis
+// floor(fl(x / c)) -- the cell index as numpy computes it -- without the FP64 division wherever the quotient
+// is clear of an integer: q = x * fl(1 / c) is within 3 ulp(q) < 2.3e-11 of fl(x / c) for q < 2^16 (a grid has
+// fewer than 65536 cells per axis), so outside a 1e-9 band around the integers both floors agree; inside the
+// band (one position in ~5e8) the division decides
+__device__ __forceinline__ int cell_index(double x, double c, double inv_c) {
+  const double q = x * inv_c;
+  const double fq = floor(q);
+  const double fr = q - fq;
+  if (fr > 1e-9 && fr < 1.0 - 1e-9) return (int)fq;
+  return (int)floor(x / c);
+}
 __device__ __forceinline__ uint32_t mating_cell(const Land& land, double x, double y) {
-  int cx = (int)floor(x / land.cell_size), cy = (int)floor(y / land.cell_size);
+  int cx = cell_index(x, land.cell_size, land.inv_cell_size), cy = cell_index(y, land.cell_size, land.inv_cell_size);
   cx = min(cx, land.ncx - 1);
   cy = min(cy, land.ncy - 1);
   return ((uint32_t)cy << 16) | (uint32_t)cx;
@@ -423,6 +434,78 @@ __device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
   return bit;
 }
 
+// the crowded-cell test of MODE 0 (see k_find_mates): l0..l2 = lengths of the three candidate row ranges,
+// nf = focals of the cell
+#define GNX_FM_IS_HEAVY(l0, l1, l2, nf) (max(l0, max(l1, l2)) > 64 || (nf) * ((l0) + (l1) + (l2)) >= GNX_FM_HEAVY_WORK)
+
+// Bernoulli(b) FIRST.  The reference lists every focal's neighbours, lets each focal pick one and only then
+// keeps the pair with probability b (species.py:2212-2214) -- the draw is independent of the search, so a
+// focal whose draw fails needs no search at all (b = 0.2 at the BASELINE configs: four searches in five).
+// Lanes that skip inside a thread-per-focal loop would save nothing (the warp runs as long as its busiest
+// lane), so the focals that may mate are COMPACTED into a list here and only they are searched.  The draws
+// come from the same Philox stream positions (or injected arrays) as the pick in the search kernels, so the
+// result is the one the search-everything form gave, bit for bit.  With store_debug (the parity tests read
+// every focal's neighbour count) everyone is listed.  Also announces the crowded cells' work items (one per
+// batch of 32 focals of a cell, by the batch's first entry) for k_find_mates_dense.
+// draw order per focal -- MODE 0: R, u; MODE 1: u; MODE 2: u_inv, u (each either injected or from the stream)
+template <int MODE>
+__device__ __forceinline__ double mate_keep_draw(RngStream& g, const DevDraws& dr, int io, uint32_t* R, double* u_inv) {
+  if (MODE == 0) *R = dr.mate_R ? dr.mate_R[io] : g.u32();
+  if (MODE == 2) *u_inv = dr.mate_inv_u ? dr.mate_inv_u[io] : g.uniform();
+  return dr.mate_u ? dr.mate_u[io] : g.uniform();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params prm, DevDraws dr, Work w, Counters* c) {
+  const int n = c->n, cur = c->cur;
+  const int64_t t = c->t;
+  const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
+  const int own_lo = c->own_lo, own_hi = c->own_hi;
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {      // whole warps stay (ballot)
+    const int p = base + threadIdx.x;
+    bool act = false;
+    if (p < n) {
+      if (p >= own_lo && p < own_hi) {             // else a ghost of a neighbouring strip: candidate, never focal
+        if (MODE == 0) {
+          const uint32_t key = w.skey[p];
+          const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
+          const int fs = (int)w.cell_start[cy * land.ncx + cx];
+          if (((p - fs) & 31) == 0) {
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, land.ncx - 1);
+            int len[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int row = cy - 1 + r;
+              len[r] = (row < 0 || row >= land.ncy) ? 0
+                     : (int)w.cell_start[row * land.ncx + x1 + 1] - (int)w.cell_start[row * land.ncx + x0];
+            }
+            const int nf = (int)w.cell_start[cy * land.ncx + cx + 1] - fs;
+            if (GNX_FM_IS_HEAVY(len[0], len[1], len[2], nf)) {
+              const int pos = atomicAdd(&c->n_heavy, 1);
+              if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(key, (uint32_t)p);
+              else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
+            }
+          }
+        }
+        RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
+        uint32_t R;
+        double u_inv;
+        const double u = mate_keep_draw<MODE>(g, dr, ord ? ord[p] : p, &R, &u_inv);
+        act = u < prm.c.b || prm.store_debug;
+      }
+      if (!act) w.mate[p] = -1;
+    }
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (am) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(w.fm_count, __popc(am));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (act) w.fm_list[pos + __popc(am & ((1u << lane) - 1u))] = p;
+    }
+  }
+}
+
 template <int MODE>
 #ifndef GNX_FM_BLOCK
 #define GNX_FM_BLOCK 128
@@ -439,12 +522,10 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
   const double r2 = prm.r2, radius = prm.c.mating_radius;
   const double2* __restrict__ sxy = pop.xy[cur];
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
-  const int own_lo = c->own_lo, own_hi = c->own_hi;
-  for (int p = GTID; p < n; p += GSTRIDE) {
-    if (p < own_lo || p >= own_hi) {               // a ghost of a neighbouring strip: candidate, never focal
-      w.mate[p] = -1;
-      continue;
-    }
+  const int n_list = *w.fm_count;                  // the focals k_mate_select let through
+  (void)n;
+  for (int li = GTID; li < n_list; li += GSTRIDE) {
+    const int p = w.fm_list[li];
     const double2 f = sxy[p];
     const uint32_t key = w.skey[p];
     const int cx = (int)(key & 0xffffu), cy = (int)(key >> 16);
@@ -467,15 +548,7 @@ __global__ void GNX_FM_BOUNDS k_find_mates(Pop pop, Land land, Params prm, DevDr
       // kernel loses lanes to padding (candidates in chunks of 32, focals in batches of 32), this
       // one to trip-count divergence: a cell moves over when its focals x candidates product is
       // large enough for the padding not to matter (or a row range exceeds the masks here)
-      if (max(l0, max(l1, l2)) > 64 || nf * (l0 + l1 + l2) >= GNX_FM_HEAVY_WORK) {
-        // one work item per batch of 32 focals of the cell, announced by the batch's first entry
-        if (((p - fs) & 31) == 0) {
-          const int pos = atomicAdd(&c->n_heavy, 1);
-          if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(key, (uint32_t)p);
-          else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
-        }
-        continue;
-      }
+      if (GNX_FM_IS_HEAVY(l0, l1, l2, nf)) continue;      // (its work items were announced by k_mate_select)
     }
     // MODE 0 keeps the valid candidates of each row range as two 32-bit masks in registers
     // (candidates 0-31 and 32-63 of the range)
@@ -629,7 +702,8 @@ __device__ __forceinline__ void fmd_ballots(const double2* cv, const double2 f, 
 
 template <int NC>
 __device__ __forceinline__ void fmd_group(const double2* __restrict__ sxy, const FmdBlock& blk, const double2* foc,
-                                          uint32_t (*mk)[FMD_STRIDE], int nf, int cg, int lane, long long r2b) {
+                                          uint32_t (*mk)[FMD_STRIDE], int nf, int cg, int lane, long long r2b,
+                                          uint32_t amask) {
   double2 cv[FMD_CG];
 #pragma unroll
   for (int j = 0; j < FMD_CG; ++j) {
@@ -639,8 +713,9 @@ __device__ __forceinline__ void fmd_group(const double2* __restrict__ sxy, const
       cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
     }
   }
-#pragma unroll 2
-  for (int fi = 0; fi < nf; ++fi) {
+  // only the focals whose Bernoulli(b) draw lets them mate (amask, uniform across the warp)
+  for (uint32_t rest = amask; rest; rest &= rest - 1u) {
+    const int fi = __ffs(rest) - 1;
     uint32_t bm[FMD_CG];
     fmd_ballots<NC>(cv, foc[fi], r2b, bm);
     if (lane == 0) *reinterpret_cast<uint4*>(&mk[fi][cg]) = make_uint4(bm[0], bm[1], bm[2], bm[3]);
@@ -693,23 +768,32 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
     uint32_t R = 0u;
     double u_keep = 1.0;
     const int io = (lane < nf && ord) ? ord[p] : p;
+    // Bernoulli(b) first (see k_mate_select): the draws of this lane's focal, from the stream positions the
+    // pick below used to take them from; focals that may not mate are not searched at all
+    bool act = false;
+    if (lane < nf) {
+      RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
+      double u_inv;
+      u_keep = mate_keep_draw<0>(g, dr, io, &R, &u_inv);
+      act = u_keep < prm.c.b || prm.store_debug;
+    }
+    const uint32_t amask = __ballot_sync(0xffffffffu, act);
+    if (amask == 0u) { __syncwarp(); continue; }       // (k_mate_select has set their mates to -1)
     if (keep) {
-      // ---- lanes across candidates: FMD_CG chunks in registers, every focal of the batch against them
+      // ---- lanes across candidates: FMD_CG chunks in registers, every listed focal of the batch against them
       int cg = 0;
-      for (; cg + FMD_CG <= nch; cg += FMD_CG) fmd_group<FMD_CG>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      for (; cg + FMD_CG <= nch; cg += FMD_CG) fmd_group<FMD_CG>(sxy, blk, foc, mk, nf, cg, lane, r2b, amask);
       const int rem = nch - cg;
-      if (rem == 1) fmd_group<1>(sxy, blk, foc, mk, nf, cg, lane, r2b);
-      else if (rem == 2) fmd_group<2>(sxy, blk, foc, mk, nf, cg, lane, r2b);
-      else if (rem == 3) fmd_group<3>(sxy, blk, foc, mk, nf, cg, lane, r2b);
+      if (rem == 1) fmd_group<1>(sxy, blk, foc, mk, nf, cg, lane, r2b, amask);
+      else if (rem == 2) fmd_group<2>(sxy, blk, foc, mk, nf, cg, lane, r2b, amask);
+      else if (rem == 3) fmd_group<3>(sxy, blk, foc, mk, nf, cg, lane, r2b, amask);
       __syncwarp();
-      // ---- lanes across focals: count, draw, pick (spatial.py:232-242, species.py:2212-2214)
-      if (lane < nf) {
+      // ---- lanes across focals: count, pick (spatial.py:232-242, species.py:2212-2214)
+      if (act) {
         const int ngrp = (nch + FMD_CG - 1) / FMD_CG * FMD_CG;
         mk[lane][self >> 5] &= ~(1u << (self & 31));
         for (int ch = 0; ch < ngrp; ++ch) cnt += __popc(mk[lane][ch]);
         if (cnt > 0) {
-          RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
-          R = dr.mate_R ? dr.mate_R[io] : g.u32();
           k = (int)choose_k(R, (uint32_t)cnt);
           int ch = 0;
           uint32_t m = mk[lane][0];
@@ -721,7 +805,6 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
             m = mk[lane][ch];
           }
           sel_q = blk.entry((ch << 5) + kth_set_bit(m, k));
-          u_keep = dr.mate_u ? dr.mate_u[io] : g.uniform();
         }
       }
     } else {
@@ -733,7 +816,8 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
           const int ci = ((cg + j) << 5) + lane;
           cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
         }
-        for (int fi = 0; fi < nf; ++fi) {
+        for (uint32_t rest = amask; rest; rest &= rest - 1u) {
+          const int fi = __ffs(rest) - 1;
           uint32_t bm[FMD_CG];
           fmd_ballots<FMD_CG>(cv, foc[fi], r2b, bm);
           const int sf = blk.e1 + (fb + fi - lo[1]);
@@ -746,12 +830,7 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
           if (lane == fi) cnt += pc;
         }
       }
-      if (lane < nf && cnt > 0) {
-        RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
-        R = dr.mate_R ? dr.mate_R[io] : g.u32();
-        k = (int)choose_k(R, (uint32_t)cnt);
-        u_keep = dr.mate_u ? dr.mate_u[io] : g.uniform();
-      }
+      if (act && cnt > 0) k = (int)choose_k(R, (uint32_t)cnt);
       int run = 0;                                     // valid candidates of this lane's focal seen so far
       for (int cg = 0; cg < nch; cg += FMD_CG) {
         double2 cv[FMD_CG];
@@ -760,7 +839,8 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
           const int ci = ((cg + j) << 5) + lane;
           cv[j] = ci < blk.K ? sxy[blk.entry(ci)] : make_double2(1e300, 1e300);
         }
-        for (int fi = 0; fi < nf; ++fi) {
+        for (uint32_t rest = amask; rest; rest &= rest - 1u) {
+          const int fi = __ffs(rest) - 1;
           const int kf = __shfl_sync(0xffffffffu, k, fi), cf = __shfl_sync(0xffffffffu, cnt, fi);
           int rf = __shfl_sync(0xffffffffu, run, fi);
           if (cf == 0 || rf > kf) continue;            // nothing to pick / already picked (uniform)
@@ -782,7 +862,7 @@ __global__ void __launch_bounds__(32 * FMD_WARPS) k_find_mates_dense(Pop pop, La
         }
       }
     }
-    if (lane < nf) {
+    if (act) {
       if (prm.store_debug) w.n_nbrs[p] = cnt;
       w.mate[p] = (cnt > 0 && u_keep < prm.c.b) ? sel_q : -1;
     }
