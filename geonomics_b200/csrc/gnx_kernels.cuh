@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params 
   const int64_t t = c->t;
   const int32_t* __restrict__ ord = prm.ordered ? pop.ord[cur] : nullptr;
   const int own_lo = c->own_lo, own_hi = c->own_hi;
-  const int lane = threadIdx.x & 31;
-  for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {      // whole warps stay (ballot)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ int s_off[9];                              // per-warp offsets of the listed focals + the CTA's base
+  for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {      // whole CTAs stay (ballot, barriers)
     const int p = base + threadIdx.x;
     bool act = false;
     if (p < n) {
@@ -496,13 +497,20 @@ __global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params 
       }
       if (!act) w.mate[p] = -1;
     }
+    // ONE atomic on the list cursor per CTA pass: a per-warp atomic is 3.7e5 same-address atomics per step at
+    // c4 -- they serialise in one L2 slice and were 75 % of this kernel's time (249 us)
     const unsigned am = __ballot_sync(0xffffffffu, act);
-    if (am) {
-      int pos = 0;
-      if (lane == 0) pos = atomicAdd(w.fm_count, __popc(am));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (act) w.fm_list[pos + __popc(am & ((1u << lane) - 1u))] = p;
+    __syncthreads();                                      // the previous pass has read s_off
+    if (lane == 0) s_off[wid] = __popc(am);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int ck = s_off[k]; s_off[k] = tot; tot += ck; }
+      s_off[8] = tot ? atomicAdd(w.fm_count, tot) : 0;
     }
+    __syncthreads();
+    if (act) w.fm_list[s_off[8] + s_off[wid] + __popc(am & ((1u << lane) - 1u))] = p;
   }
 }
 
