@@ -463,9 +463,11 @@ __global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params 
   const int own_lo = c->own_lo, own_hi = c->own_hi;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ int s_off[9];                              // per-warp offsets of the listed focals + the CTA's base
+  __shared__ int s_hoff[9];                             // the same for the crowded-cell work items
   for (int base = blockIdx.x * blockDim.x; base < n; base += GSTRIDE) {      // whole CTAs stay (ballot, barriers)
     const int p = base + threadIdx.x;
-    bool act = false;
+    bool act = false, heavy = false;
+    uint32_t hkey = 0u;
     if (p < n) {
       if (p >= own_lo && p < own_hi) {             // else a ghost of a neighbouring strip: candidate, never focal
         if (MODE == 0) {
@@ -482,11 +484,8 @@ __global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params 
                      : (int)w.cell_start[row * land.ncx + x1 + 1] - (int)w.cell_start[row * land.ncx + x0];
             }
             const int nf = (int)w.cell_start[cy * land.ncx + cx + 1] - fs;
-            if (GNX_FM_IS_HEAVY(len[0], len[1], len[2], nf)) {
-              const int pos = atomicAdd(&c->n_heavy, 1);
-              if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(key, (uint32_t)p);
-              else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
-            }
+            heavy = GNX_FM_IS_HEAVY(len[0], len[1], len[2], nf);
+            hkey = key;
           }
         }
         RngStream g(prm.seed_lo, prm.seed_hi, pop.idx[cur][p], SITE_MATE, t);
@@ -500,17 +499,28 @@ __global__ void __launch_bounds__(256) k_mate_select(Pop pop, Land land, Params 
     // ONE atomic on the list cursor per CTA pass: a per-warp atomic is 3.7e5 same-address atomics per step at
     // c4 -- they serialise in one L2 slice and were 75 % of this kernel's time (249 us)
     const unsigned am = __ballot_sync(0xffffffffu, act);
+    const unsigned hm = MODE == 0 ? __ballot_sync(0xffffffffu, heavy) : 0u;
     __syncthreads();                                      // the previous pass has read s_off
-    if (lane == 0) s_off[wid] = __popc(am);
+    if (lane == 0) { s_off[wid] = __popc(am); s_hoff[wid] = __popc(hm); }
     __syncthreads();
     if (threadIdx.x == 0) {
-      int tot = 0;
+      int tot = 0, htot = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const int ck = s_off[k]; s_off[k] = tot; tot += ck; }
+      for (int k = 0; k < 8; ++k) {
+        const int ck = s_off[k], hk = s_hoff[k];
+        s_off[k] = tot; tot += ck;
+        s_hoff[k] = htot; htot += hk;
+      }
       s_off[8] = tot ? atomicAdd(w.fm_count, tot) : 0;
+      s_hoff[8] = htot ? atomicAdd(&c->n_heavy, htot) : 0;
     }
     __syncthreads();
     if (act) w.fm_list[s_off[8] + s_off[wid] + __popc(am & ((1u << lane) - 1u))] = p;
+    if (heavy) {
+      const int pos = s_hoff[8] + s_hoff[wid] + __popc(hm & ((1u << lane) - 1u));
+      if (pos < w.heavy_cap) w.heavy[pos] = make_uint2(hkey, (uint32_t)p);
+      else atomicOr(&c->err, GNX_ERRBIT_CAPACITY);
+    }
   }
 }
 
