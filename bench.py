@@ -58,17 +58,58 @@ def algorithmic_bytes(W, T, cells, YX):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    The timed region of the default workload is a few milliseconds, shorter than one period of
+    `nvidia-smi -lms`, so the samples come from NVML in this process (nvidia_ml_py: one poll every ~0.5 ms
+    from a thread; the stepping calls release the GIL) and only those taken between `mark_start()` and
+    `mark_end()` -- the host times that bracket the K timed steps -- are used.  `nvidia-smi` is the fallback
+    when NVML cannot be loaded."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'),
+               (0x4, 'sw_power_cap'))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []            # (host time, sm MHz, reasons bitmask)
+        self.t0 = self.t1 = None
+        self.nvml = None
+        self.handle = None
+        self.smax = None
+        self._stop = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            for cand in ('GPU-' + uuid, uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                    break
+                except Exception:
+                    h = None
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -78,11 +119,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.perf_counter(), mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1)
+            t0 = self.t0 if self.t0 is not None else -1e300
+            t1 = self.t1 if self.t1 is not None else 1e300
+            inside = [s for s in self.samples if t0 <= s[0] <= t1]
+            used = inside or self.samples[-3:]
+            reasons = set()
+            for _, _, why in used:
+                for bit, nm in self.REASONS:
+                    if why & bit:
+                        reasons.add(nm)
+            return {'sm_mhz': float(np.median([s[1] for s in used])) if used else None, 'sm_max_mhz': self.smax,
+                    'samples': len(inside), 'source': 'nvml, polled during the timed region',
+                    'reasons': sorted(reasons)}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -107,7 +180,7 @@ class ClockSampler:
                     reasons.add(nm)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(max(smax)) if smax else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'source': 'nvidia-smi -lms 20', 'reasons': sorted(reasons)}
 
 
 def load_traffic(workload, scale):
@@ -638,12 +711,14 @@ def main():
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1s = [torch.cuda.Event(enable_timing=True) for _ in devs]
+    sampler.mark_start()
     e0.record(stream)                        # every stream is idle here (barrier above)
     step_all(args.steps)
     for e1, st in zip(e1s, streams):
         e1.record(st)
     for d in devs:
         d.sync()
+    sampler.mark_end()
     barrier()
     ms = max(e0.elapsed_time(e1) for e1 in e1s)
     clocks = sampler.stop()
