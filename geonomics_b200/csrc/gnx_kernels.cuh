@@ -414,9 +414,10 @@ __global__ void __launch_bounds__(256) k_regrid(Pop pop, Land land, Work w, Coun
 //   MODE 0: uniform random neighbour (spatial.py:232-242); valid candidates are kept as bit
 //           masks and the k-th is picked, k = (R * count) >> 32.  Cells whose 3x3 block is
 //           crowded (a row range longer than 64 entries, or focals x candidates >= GNX_FM_HEAVY_WORK)
-//           are not searched here: the first of every 32 focals of such a cell appends a work
-//           item to Work.heavy and k_find_mates_dense takes them, one warp per item with the
-//           lanes across candidates
+//           are not searched here: k_mate_select appends one work item per 32 focals of such a cell
+//           to Work.heavy and k_find_mates_dense takes them, one warp per item with the lanes across
+//           candidates.  All three kernels search only the focals whose Bernoulli(b) draw lets them
+//           mate (k_mate_select)
 //   MODE 1: nearest neighbour (spatial.py:194-203)
 //   MODE 2: inverse-distance weighting, p ~ (radius - dist) (spatial.py:209-229)
 // ========================================================================================
