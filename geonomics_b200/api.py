@@ -1096,9 +1096,12 @@ class Species:
         """species.py:1107-1219: sort + simplify on the current nodes, then nodes 2k, 2k + 1 in species order and
         the individuals rows in species order (gnx_tskit_renumber).  sort()/simplify() are tskit's own."""
         self._drain_tskit()
-        s = self._state()
+        n = len(self)
         self._tc.sort_and_simplify(self._node_ids().reshape(-1))
-        self._dev.tskit_renumber()
+        # the samples are nodes 0 .. 2N - 1 in the order given (species.py:1148-1152); nodes where their ancestry
+        # coalesces follow, with the individuals they belong to, so the NEXT rows continue from the table sizes
+        self._dev.tskit_set_nodes(2 * np.arange(n, dtype=np.int32), 2 * np.arange(n, dtype=np.int32) + 1,
+                                  self._tc.nodes.num_rows, self._tc.individuals.num_rows)
         self._tc_sorted_and_simplified = True
         self._invalidate()
 
@@ -1317,10 +1320,10 @@ class Model:
 
     def _next_simplify_t(self, spp):
         """model.py:756-768: the tables are sorted and simplified after the step at every t with
-        (t + 1) % tskit_simp_interval == 0 -- tskit's own algorithms, so only where tskit is installed; without
-        it the rows keep accumulating as columns (Species._tc) and `Species._tc_sorted_and_simplified` stays False."""
+        (t + 1) % tskit_simp_interval == 0 (tskit's own implementation where it is installed, the restated
+        algorithm of tables.simplify_columns otherwise)."""
         ga = spp.gen_arch
-        if ga is None or not ga.use_tskit or spp.__dict__.get('_tc') is None or not self._have_tskit():
+        if ga is None or not ga.use_tskit or spp.__dict__.get('_tc') is None:
             return None
         k = int(ga.tskit_simp_interval)
         return (self.t + 1) + (k - 1 - (self.t + 1) % k)
@@ -1329,7 +1332,7 @@ class Model:
         for spp in self.comm.values():
             ga = spp.gen_arch
             if (ga is not None and ga.use_tskit and spp.__dict__.get('_tc') is not None and self.t != -1
-                    and (self.t + 1) % int(ga.tskit_simp_interval) == 0 and self._have_tskit()):
+                    and (self.t + 1) % int(ga.tskit_simp_interval) == 0):
                 spp._sort_and_simplify_table_collection()
 
     def _make_changes(self):

@@ -347,7 +347,8 @@ def attach(spp, land, seed=0, capacity=None, eager=False, disp_tries_injected=6)
             # the metadata -- the device follows with gnx_tskit_renumber
             sync_to_host(spp)
             cls._sort_and_simplify_table_collection(spp, *args, **kw)
-            dev.tskit_renumber()
+            q = population_arrays(spp)                 # nodes 2k, 2k + 1 now; the next rows continue from the
+            dev.tskit_set_nodes(q['node0'], q['node1'], spp._tc.nodes.num_rows, spp._tc.individuals.num_rows)
             spp._gnx_attached['born'].clear()
         spp._sort_and_simplify_table_collection = _sort_and_simplify_table_collection
 

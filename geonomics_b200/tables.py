@@ -136,12 +136,22 @@ class TableColumns:
 
     def sort_and_simplify(self, sample_nodes):
         """species.py:1107-1152: TableCollection.sort(); simplify(current nodes, filter_individuals=True,
-        filter_sites=False).  These are tskit's own algorithms: run on a real TableCollection and read back."""
-        tc = self.to_tskit()
-        tc.sort()
-        tc.simplify(np.asarray(sample_nodes, dtype=np.int32), filter_individuals=True, filter_sites=False)
-        self._load(tc)
-        return tc
+        filter_sites=False).  With tskit installed its own C implementation runs on a real TableCollection
+        (`to_tskit`) and the result is read back.  Without it (this image) the published algorithm is run here
+        (`simplify_columns`): parity with tskit unpinned, invariants checked by the tests."""
+        try:
+            import tskit          # noqa: F401
+            have = getattr(tskit, '__file__', None) is not None
+        except ImportError:
+            have = False
+        if have:                            # pragma: no cover - tskit is absent from the build image
+            tc = self.to_tskit()
+            tc.sort()
+            tc.simplify(np.asarray(sample_nodes, dtype=np.int32), filter_individuals=True, filter_sites=False)
+            self._load(tc)
+            return tc
+        simplify_columns(self, sample_nodes)
+        return self
 
     def _load(self, tc):                    # pragma: no cover - needs tskit
         for tab in (self.nodes, self.edges, self.individuals, self.mutations):
@@ -155,3 +165,137 @@ class TableColumns:
         idx = tc.individuals.metadata.view('<u4').astype(np.int64) if n else np.zeros(0, np.int64)
         self.individuals.append_columns(flags=tc.individuals.flags, location=loc, idx=idx)
         self.mutations.append_columns(site=tc.mutations.site, node=tc.mutations.node, time=tc.mutations.time)
+
+
+def simplify_columns(tc, sample_nodes):
+    """`TableCollection.sort()` + `simplify(samples, filter_individuals=True, filter_sites=False)` on a
+    TableColumns, in place.  tskit (>= 0.2.3 in the reference's requirements.txt) is absent here; this restates
+    the published algorithm -- Kelleher, Thornton, Ashander & Ralph 2018, "Efficient pedigree recording for fast
+    population genetics simulation", PLoS Comput Biol 14(11): e1006581, Algorithm S -- as tskit's documentation
+    describes its effect:
+      * the samples become output nodes 0 .. len(samples) - 1 in the order given (what species.py:1148-1152
+        relies on), other nodes are kept only where ancestry of the samples coalesces in them;
+      * parents are visited youngest first (edges sorted by parent time, then parent, child, left); the
+        ancestry segments each child holds over an edge's interval are merged per parent through a priority
+        queue; overlapping segments coalesce into the parent's output node and emit output edges, a segment
+        on its own passes through unchanged (unary nodes vanish);
+      * output edges of a parent are squashed (adjacent intervals to the same child merged);
+      * a mutation moves to the output node that carries its node's ancestry at the site, or is dropped when
+        nothing of the samples descends from it there; sites are all kept; individuals no retained node
+        refers to are dropped, the others keep their relative order.
+    Parity with tskit's C implementation is UNPINNED (nothing to run it against here); tests check the
+    invariants: the samples' haplotypes replayed from the tables are unchanged, edges of every child tile
+    without overlap, parents are older than children."""
+    import heapq
+    samples = np.asarray(sample_nodes, dtype=np.int64)
+    L = float(tc.sequence_length)
+    n_in = tc.nodes.num_rows
+    time, nind, npop = tc.nodes.time.copy(), tc.nodes.individual.copy(), tc.nodes.population.copy()
+    el, er, ep, ec = (tc.edges.left.copy(), tc.edges.right.copy(), tc.edges.parent.astype(np.int64),
+                      tc.edges.child.astype(np.int64))
+    order = np.lexsort((el, ec, ep, time[ep]))            # TableCollection.sort(): parent time, parent, child, left
+    el, er, ep, ec = el[order], er[order], ep[order], ec[order]
+    # ancestry of every input node: list of [left, right, output node]
+    A = [None] * n_in
+    o_time, o_ind, o_pop, o_flags = [], [], [], []
+    for u in samples:
+        A[u] = [[0.0, L, len(o_time)]]
+        o_time.append(time[u]); o_ind.append(nind[u]); o_pop.append(npop[u]); o_flags.append(1)
+    oe = [[], [], [], []]                                  # left, right, parent, child
+    starts = np.flatnonzero(np.r_[True, ep[1:] != ep[:-1]]) if len(ep) else np.zeros(0, np.int64)
+    ends = np.r_[starts[1:], len(ep)] if len(ep) else starts
+    cnt = 0
+    for s0, s1 in zip(starts, ends):
+        u = int(ep[s0])
+        Q = []
+        for k in range(s0, s1):
+            segs = A[ec[k]]
+            if not segs:
+                continue
+            l_e, r_e = el[k], er[k]
+            for x in segs:
+                if x[1] > l_e and r_e > x[0]:
+                    cnt += 1
+                    heapq.heappush(Q, (max(x[0], l_e), cnt, min(x[1], r_e), x[2]))
+        if not Q:
+            continue
+        v = -1
+        own = A[u] if A[u] is not None else []            # a sample keeps its own node over [0, L)
+        is_sample = bool(own)
+        out = []
+        pe = [[], [], []]                                   # this parent's output edges: left, right, child
+        while Q:
+            l = Q[0][0]
+            r = L
+            X = []
+            while Q and Q[0][0] == l:
+                x = heapq.heappop(Q)
+                X.append(x)
+                r = min(r, x[2])
+            if Q:
+                r = min(r, Q[0][0])
+            if len(X) == 1 and not is_sample:
+                x = X[0]
+                if Q and Q[0][0] < x[2]:
+                    out.append([x[0], Q[0][0], x[3]])
+                    cnt += 1
+                    heapq.heappush(Q, (Q[0][0], cnt, x[2], x[3]))
+                else:
+                    out.append([x[0], x[2], x[3]])
+            else:
+                if is_sample:
+                    v = own[0][2]
+                elif v == -1:
+                    v = len(o_time)
+                    o_time.append(time[u]); o_ind.append(nind[u]); o_pop.append(npop[u]); o_flags.append(0)
+                out.append([l, r, v])
+                for x in X:
+                    pe[0].append(l); pe[1].append(r); pe[2].append(x[3])
+                    if x[2] > r:
+                        cnt += 1
+                        heapq.heappush(Q, (r, cnt, x[2], x[3]))
+        if not is_sample:
+            A[u] = out
+        if pe[0]:
+            # squash: adjacent intervals to the same child become one edge
+            o = np.lexsort((pe[0], pe[2]))
+            l_, r_, c_ = np.asarray(pe[0])[o], np.asarray(pe[1])[o], np.asarray(pe[2])[o]
+            keep = np.r_[True, (c_[1:] != c_[:-1]) | (l_[1:] != r_[:-1])]
+            first = np.flatnonzero(keep)
+            last = np.r_[first[1:], len(l_)] - 1
+            oe[0].extend(l_[first]); oe[1].extend(r_[last]); oe[2].extend([v] * len(first)); oe[3].extend(c_[first])
+    # mutations: to the output node carrying the ancestry of their node at the site
+    ms, mn, mt = tc.mutations.site.copy(), tc.mutations.node.astype(np.int64), tc.mutations.time.copy()
+    pos = tc.sites.position
+    k_site, k_node, k_time = [], [], []
+    for s_, n_, t_ in zip(ms, mn, mt):
+        segs = A[n_] if 0 <= n_ < n_in else None
+        if not segs:
+            continue
+        x = pos[s_] if len(pos) else float(s_)
+        for a in segs:
+            if a[0] <= x < a[1]:
+                k_site.append(s_); k_node.append(a[2]); k_time.append(t_)
+                break
+    # individuals: drop the unreferenced, keep the order
+    o_ind = np.asarray(o_ind, dtype=np.int64)
+    used = np.zeros(tc.individuals.num_rows, bool)
+    used[o_ind[o_ind >= 0]] = True
+    remap = np.full(tc.individuals.num_rows, -1, np.int64)
+    remap[used] = np.arange(int(used.sum()))
+    i_flags, i_loc, i_idx = tc.individuals.flags[used].copy(), tc.individuals.location[used].copy(), \
+        tc.individuals.idx[used].copy()
+    for tab in (tc.nodes, tc.edges, tc.individuals, tc.mutations):
+        tab.truncate(0)
+    tc.individuals.append_columns(flags=i_flags, location=i_loc, idx=i_idx)
+    tc.nodes.append_columns(flags=np.asarray(o_flags, np.int32), time=np.asarray(o_time, np.float64),
+                            population=np.asarray(o_pop, np.int32),
+                            individual=np.where(o_ind >= 0, remap[np.maximum(o_ind, 0)], -1).astype(np.int32))
+    if oe[0]:
+        l_, r_, p_, c_ = (np.asarray(v) for v in oe)
+        o = np.lexsort((l_, c_, p_, np.asarray(o_time)[p_]))
+        tc.edges.append_columns(left=l_[o], right=r_[o], parent=p_[o].astype(np.int32), child=c_[o].astype(np.int32))
+    if k_site:
+        tc.mutations.append_columns(site=np.asarray(k_site, np.int32), node=np.asarray(k_node, np.int32),
+                                    time=np.asarray(k_time, np.float64))
+    return tc

@@ -330,6 +330,9 @@ int gnx_tskit_enable(gnx_ctx* ctx, int64_t edge_capacity, int64_t birth_capacity
 int gnx_tskit_set_nodes(gnx_ctx* ctx, const int32_t* host_node0, const int32_t* host_node1, int64_t n,
                         int32_t next_node_id, int32_t next_individual_row);
 int gnx_tskit_drain(gnx_ctx* ctx, gnx_tskit_rows_t* rows);   /* NULL arrays: query the counts only */
+/* nodes 2k, 2k + 1 in species order and the row counters set to 2N / N: right when the simplified tables hold the
+ * samples only; tskit's simplify also keeps the nodes (and their individuals) in which the samples' ancestry
+ * coalesces, so after a real simplification call gnx_tskit_set_nodes with the sizes of the simplified tables */
 int gnx_tskit_renumber(gnx_ctx* ctx);
 
 /* ---- a13 mutation (ops/mutation.py:169-206 _do_mutation; :62-86 neutral; :90-131 + :156-166

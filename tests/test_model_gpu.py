@@ -394,7 +394,7 @@ def test_use_tskit_model_tables_replay_to_the_genotypes():
     from geonomics_b200 import api
     p = copy.deepcopy(api.read_parameters_file(PARAMS))
     g = p['comm']['species']['spp_0']['gen_arch']
-    g.update(use_tskit=True, tskit_simp_interval=7, L=200, r_distr_alpha=None, mu_neut=5e-6, mu_delet=8e-6,
+    g.update(use_tskit=True, tskit_simp_interval=1000, L=200, r_distr_alpha=None, mu_neut=5e-6, mu_delet=8e-6,
              start_neut_zero=True)
     g['traits']['trait_0'].update(mu=8e-6, n_loci=6)
     p['model']['T'] = 25
@@ -421,7 +421,8 @@ def test_use_tskit_model_tables_replay_to_the_genotypes():
         if int(s_) in col_of:
             cnt[n_, col_of[int(s_)]] = 1
     assert np.array_equal(cnt, g0.transpose(0, 2, 1).reshape(2 * n0, len(nn0)))
-    steps = 23                                                # several drains (the buffers hold <= 7 steps)
+    spp._tsk_steps = 7                                        # several drains of the device row buffers
+    steps = 23
     mod.walk(steps, 'main')
     births = int(np.sum(spp.n_births[-steps:]))
     assert tc.nodes.num_rows == 2 * (n0 + births) and tc.individuals.num_rows == n0 + births
@@ -466,3 +467,80 @@ def test_use_tskit_model_tables_replay_to_the_genotypes():
     # trait bookkeeping came back (genome.py:416-437)
     t0 = ga.traits[0]
     assert len(t0.loci) == len(t0.alpha) == len(t0.loci_idxs) == t0.n_loci >= 6
+
+
+def _haplotypes_from_tables(tc, loci):
+    """Haplotype of every node at `loci`, from the tables alone: roots carry their mutations, every other node
+    inherits locus by locus from the parent whose edge covers it, then adds its own mutations (what tskit's
+    genotype decoding does; species.py:762-801 checks the individuals' arrays against it)."""
+    n = tc.nodes.num_rows
+    loci = np.asarray(loci, dtype=np.int64)
+    col = {int(l): c for c, l in enumerate(loci)}
+    H = np.zeros((n, len(loci)), np.int8)
+    el, er, ep, ec = tc.edges.left, tc.edges.right, tc.edges.parent, tc.edges.child
+    order = np.argsort(ec, kind='stable')
+    el, er, ep, ec = el[order], er[order], ep[order], ec[order]
+    lo = np.searchsorted(ec, np.arange(n), side='left')
+    hi = np.searchsorted(ec, np.arange(n), side='right')
+    muts = {}
+    for s_, n_ in zip(tc.mutations.site, tc.mutations.node):
+        if int(s_) in col:
+            muts.setdefault(int(n_), []).append(col[int(s_)])
+    for u in np.argsort(-tc.nodes.time, kind='stable'):        # oldest first: parents before children
+        l_, r_, p_ = el[lo[u]:hi[u]], er[lo[u]:hi[u]], ep[lo[u]:hi[u]]
+        if len(l_):
+            o = np.argsort(l_)
+            l_, r_, p_ = l_[o], r_[o], p_[o]
+            seg = np.searchsorted(r_, loci.astype(np.float64), side='right')
+            ok = (seg < len(l_))
+            ok[ok] &= l_[seg[ok]] <= loci[ok]
+            H[u, ok] = H[p_[seg[ok]], np.flatnonzero(ok)]
+        for c in muts.get(int(u), []):
+            H[u, c] = 1
+    return H
+
+
+def test_use_tskit_model_simplifies_at_its_interval():
+    """model.py:756-768 + species.py:1107-1219: every tskit_simp_interval steps the tables are sorted and
+    simplified on the current nodes (tskit where installed; here the restated algorithm of
+    tables.simplify_columns) and the device continues from the simplified tables: nodes 2k, 2k + 1 in species
+    order, next rows behind the retained ancestors.  The genotype rows of everyone alive must still decode from
+    the tables alone."""
+    import copy
+    from geonomics_b200 import api
+    p = copy.deepcopy(api.read_parameters_file(PARAMS))
+    g = p['comm']['species']['spp_0']['gen_arch']
+    g.update(use_tskit=True, tskit_simp_interval=5, L=200, r_distr_alpha=None, mu_neut=5e-6, mu_delet=8e-6,
+             start_neut_zero=True)
+    g['traits']['trait_0'].update(mu=8e-6, n_loci=6)
+    p['model']['T'] = 25
+    mod = api.make_model(p)
+    mod.walk(10000, 'burn')
+    spp = mod.comm[0]
+    tc = spp._tc
+    nn0 = np.array(spp.gen_arch.nonneut_loci, dtype=np.int64)
+    n0 = len(spp)
+    mod.walk(18, 'main')                                      # simplified after t = 4, 9, 14; three more steps since
+    births = int(np.sum(spp.n_births[-18:]))
+    n = len(spp)
+    assert tc.nodes.num_rows < 2 * (n0 + births)              # history nobody descends from is gone
+    assert tc.nodes.num_rows >= 2 * n and tc.individuals.num_rows >= n
+    assert np.all(tc.nodes.time[tc.edges.parent] > tc.nodes.time[tc.edges.child])
+    nodes = spp._node_ids()
+    assert len(np.unique(nodes)) == 2 * n and nodes.max() < tc.nodes.num_rows
+    # node -> individual -> idx links of everyone alive survive the renumbering
+    ids = np.array([i for i in spp])
+    rows = tc.nodes.individual[nodes[:, 0]]
+    assert np.array_equal(rows, tc.nodes.individual[nodes[:, 1]])
+    assert np.array_equal(tc.individuals.idx[rows], ids)
+    # genotype rows at the starting non-neutral loci decode from the tables alone
+    H = _haplotypes_from_tables(tc, nn0)
+    g_now = mod.get_genotypes()
+    rows_of_start = np.searchsorted(np.array(spp.gen_arch.nonneut_loci, dtype=np.int64), nn0)
+    for h in (0, 1):
+        assert np.array_equal(g_now[:, rows_of_start, h], H[nodes[:, h]])
+    # and right after a simplification the samples are nodes 0 .. 2N - 1 in species order
+    mod.walk(2, 'main')                                       # t = 19: (t + 1) % 5 == 0
+    assert spp._tc_sorted_and_simplified
+    n = len(spp)
+    assert np.array_equal(spp._node_ids().reshape(-1), np.arange(2 * n))

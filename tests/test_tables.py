@@ -99,3 +99,74 @@ def test_dropin_host_half_for_a_use_tskit_reference_species():
     from geonomics_b200 import genome_pack as gp
     assert np.array_equal(gp.loci_to_rows(q['g'], nn), rows)
     assert all(tr['loci_idxs'].shape == tr['loci'].shape for tr in a['gen_arch']['traits'])
+
+
+def test_simplify_columns_keeps_the_samples_haplotypes():
+    """tables.simplify_columns (restated Kelleher et al. 2018 simplify; tskit absent, parity unpinned): on a
+    random pedigree with recombination and mutation the haplotypes of the sample nodes decoded from the tables
+    are the same before and after, the samples come first in the order given, parents are older than children,
+    no child has overlapping edges, and the tables shrink."""
+    from geonomics_b200.tables import TableColumns, simplify_columns
+    rng = np.random.default_rng(0)
+    L, N, G = 50, 30, 12
+    tc = TableColumns(L, 0)
+    tc.sites.append_columns(position=np.arange(L, dtype=float), nonneutral=np.zeros(L, np.int8))
+    n_ind = [0]
+
+    def add_inds(k, t):
+        first = tc.individuals.append_columns(flags=np.ones(k, np.int32), location=np.zeros((k, 2)),
+                                              idx=np.arange(n_ind[0], n_ind[0] + k))
+        tc.nodes.append_columns(flags=np.ones(2 * k, np.int32), time=np.full(2 * k, float(t)),
+                                population=np.zeros(2 * k, np.int32),
+                                individual=np.repeat(first + np.arange(k, dtype=np.int32), 2))
+        n_ind[0] += k
+        return first
+    add_inds(N, 1)
+    hap = {i: (rng.random(L) < 0.3).astype(np.int8) for i in range(2 * N)}
+    for nd, h in hap.items():
+        for s_ in np.flatnonzero(h):
+            tc.mutations.append_columns(site=[s_], node=[nd], time=[np.nan])
+    alive = list(range(N))
+    for t in range(G):
+        first = add_inds(N, -t)
+        kids = []
+        for b in range(N):
+            child = first + b
+            for hom in (0, 1):
+                par = alive[rng.integers(len(alive))]
+                bp = np.sort(rng.choice(np.arange(1, L), size=rng.integers(0, 3), replace=False))
+                lefts, rights = np.r_[0, bp - 0.5], np.r_[bp - 0.5, L]
+                st = rng.integers(2)
+                cn = 2 * child + hom
+                h = np.zeros(L, np.int8)
+                for k, (a, bq) in enumerate(zip(lefts, rights)):
+                    pn = 2 * par + ((k + st) % 2)
+                    tc.edges.append_columns(left=[a], right=[bq], parent=[pn], child=[cn])
+                    h[int(np.ceil(a)):int(np.ceil(bq))] = hap[pn][int(np.ceil(a)):int(np.ceil(bq))]
+                if rng.random() < 0.2:
+                    s_ = rng.integers(L)
+                    if h[s_] == 0:
+                        h[s_] = 1
+                        tc.mutations.append_columns(site=[s_], node=[cn], time=[-t])
+                hap[cn] = h
+            kids.append(child)
+        alive = kids
+    samples = np.array([n for i in alive for n in (2 * i, 2 * i + 1)])
+    sys.path.insert(0, HERE)
+    from test_model_gpu import _haplotypes_from_tables
+    loci = np.arange(L)
+    before = _haplotypes_from_tables(tc, loci)[samples]
+    assert all(np.array_equal(before[k], hap[int(s_)]) for k, s_ in enumerate(samples))
+    sizes = (tc.nodes.num_rows, tc.edges.num_rows, tc.individuals.num_rows)
+    kept_idx = tc.individuals.idx[tc.nodes.individual[samples]].copy()
+    simplify_columns(tc, samples)
+    after = _haplotypes_from_tables(tc, loci)[:len(samples)]
+    assert np.array_equal(before, after)
+    assert (tc.nodes.num_rows, tc.edges.num_rows, tc.individuals.num_rows) < sizes
+    assert np.all(tc.nodes.time[tc.edges.parent] > tc.nodes.time[tc.edges.child])
+    assert np.array_equal(tc.individuals.idx[tc.nodes.individual[:len(samples)]], kept_idx)
+    assert np.all(tc.nodes.flags[:len(samples)] == 1) and not tc.nodes.flags[len(samples):].any()
+    o = np.lexsort((tc.edges.left, tc.edges.child))
+    c_, l_, r_ = tc.edges.child[o], tc.edges.left[o], tc.edges.right[o]
+    same = c_[1:] == c_[:-1]
+    assert np.all(l_[1:][same] >= r_[:-1][same])
