@@ -1881,12 +1881,17 @@ static int one_step(gnx_ctx* ctx) {
     // genotype streaming.  They join before the death probabilities.
     if ((r = offspring_check(ctx))) return r;
     if ((r = offspring_newborns(ctx))) return r;
+    // The counts stay on the main stream, IN FRONT of the gamete kernel: the gradient solve that follows them
+    // is two CTAs that each need a whole SM's shared memory, and once the gamete kernel's CTAs hold the SMs it
+    // cannot start before they are all gone.  Forking after the counts makes the gradient solve and the gamete
+    // kernel eligible at the same moment, the solve's two CTAs are placed first, and the chain's latency-bound
+    // head runs UNDER the genotype streaming instead of behind it.
+    if ((r = gnx_density_counts(ctx))) return r;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->stream2;
-    r = gnx_density_counts(ctx);
-    if (r == GNX_OK) r = gnx_density_eval(ctx);
+    r = gnx_density_eval(ctx);
     ctx->stream = main_stream;
     if (r != GNX_OK) return r;
     CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
