@@ -47,7 +47,7 @@ def main():
         b = sum(to_bytes(r[ix[c]], units[ix[c]]) for c in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
         t = float(r[ix['gpu__time_duration.sum']].replace(',', ''))
         t *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(units[ix['gpu__time_duration.sum']], 1.0)
-        if name == 'k_find_mates_dense':          # the crowded cells of the same search: one row, as in bench.py
+        if name in ('k_find_mates_dense', 'k_mate_select'):   # parts of the same search: one row, as in bench.py
             d = acc.setdefault('k_find_mates', [0, 0.0, 0.0])
             d[1] += b
             d[2] += t
