@@ -882,7 +882,10 @@ class Species:
                 self._cache = self._dev.download(genomes=self.burned and self.gen_arch is not None, e=True)
                 if self._cache.get('g') is not None and self.gen_arch.use_tskit:
                     # species.py:891-905: Individuals carry one genotype ROW per non-neutral locus
+                    # (the by-locus array the device holds is kept for _get_genotypes, which the reference
+                    # answers from the tree sequence for all L loci, species.py:1395-1425)
                     from . import genome_pack as gp
+                    self._cache['g_loci'] = self._cache['g']
                     self._cache['g'] = gp.loci_to_rows(self._cache['g'], self.gen_arch.nonneut_loci)
         return self._cache
 
@@ -966,8 +969,12 @@ class Species:
     def _get_fit(self, individs=None):
         return self._sel(self._state()['fit'], individs)
 
-    def _get_genotypes(self, loci=None, individs=None, biallelic=True, as_dict=False):
-        g = self._sel(self._state()['g'], individs)
+    def _get_genotypes(self, loci=None, individs=None, biallelic=True, as_dict=False, all_loci=False):
+        """species.py:1364-1448.  For a use_tskit species the arrays are the Individuals' own rows (one
+        per non-neutral locus, species.py:891-905); `all_loci=True` gives all L loci, which the
+        reference reads off the tree sequence (:1395-1425) and the device holds by locus."""
+        s = self._state()
+        g = self._sel(s.get('g_loci', s['g']) if all_loci else s['g'], individs)
         if loci is not None:
             g = g[:, loci, :]
         if not biallelic:
@@ -1044,6 +1051,8 @@ class Species:
                     mut_node.append(hom.astype(np.int32))  # is 2k + h (see below)
         self._dev.set_burn(False)
         self._dev.upload(s['x'], s['y'], s['age'], s['sex'], s['idx'], g=g, max_ind_idx=s['max_ind_idx'])
+        # everyone up to this id was alive at the assignment (the FASTA writer tells them apart, writers.py)
+        self._genome_assignment_max_idx = int(s['max_ind_idx'])
         self._tc = None
         if tsk:
             self._set_tables(s, mut_site, mut_node)
@@ -1548,6 +1557,11 @@ class Model:
 
     def get_genotypes(self, spp=0, loci=None, individs=None, biallelic=True, as_dict=False):
         return self._spp(spp)._get_genotypes(loci, individs, biallelic, as_dict)
+
+    def write_gendata(self, filepath, spp=0, n=None, include_fixed_sites=True):
+        """model.py:3342-3396: VCF / FASTA of everyone or of n individuals drawn at random, by extension."""
+        from . import writers
+        return writers.write_gendata(filepath, self._spp(spp), n=n, include_fixed_sites=include_fixed_sites)
 
 
 def make_model(parameters=None, verbose=False, name=None):
