@@ -609,6 +609,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--ref-sample', type=int, default=1500,
                     help='individuals per replica of the unmodified reference (--impl reference; ~0.4 s per step per core)')
+    ap.add_argument('--ref-steps', type=int, default=200,
+                    help='timed steps of the unmodified reference in the cpu_baseline leg (~10 s of CPU work)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5, help='host-buffer steps per replicate in flight')
     ap.add_argument('--e2e-depth', type=int, default=3, help='replicate populations in flight in the e2e leg')
@@ -829,12 +831,12 @@ def main():
             # global numpy.random state and import shims stay out of this one
             import multiprocessing as mp
             with mp.get_context('spawn').Pool(1) as pool:
-                tot_r, wall_r = pool.map(_reference_worker, [(cfg, args.ref_sample, args.cpu_steps, 2, 1000)])[0]
+                tot_r, wall_r = pool.map(_reference_worker, [(cfg, args.ref_sample, args.ref_steps, 2, 1000)])[0]
             cpu = {'value': tot_r / wall_r, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
                    'sample': '%d timed steps (after burn-in and 2 warm-up steps) of a %d-individual replica of the '
                              'workload (same per-capita parameters and density) run by the unmodified reference '
                              'package (erthward/geonomics 1.4.9, oracle/_ref) through make_model / Model.walk, '
-                             '1 process (the reference is single-threaded)' % (args.cpu_steps, args.ref_sample),
+                             '1 process (the reference is single-threaded)' % (args.ref_steps, args.ref_sample),
                    'seconds': wall_r, 'port': port}
     gs_iters = dev.counters()['gs_iters']
 
