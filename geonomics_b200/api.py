@@ -1563,6 +1563,11 @@ class Model:
         from . import writers
         return writers.write_gendata(filepath, self._spp(spp), n=n, include_fixed_sites=include_fixed_sites)
 
+    def write_geodata(self, filepath, spp=0, n=None):
+        """model.py:3399-3446: idx, z, e, age, sex, x, y of everyone or of n individuals drawn at random (CSV)."""
+        from . import writers
+        return writers.write_geodata(filepath, self._spp(spp), n=n)
+
 
 def make_model(parameters=None, verbose=False, name=None):
     """main.py:442: a Model from a parameters-file path, a dict or a ParametersDict."""

@@ -150,3 +150,29 @@ def write_gendata(filepath, spp, n=None, include_fixed_sites=True):
     with open(filepath, 'w') as f:
         f.write(text)
     return filepath
+
+
+def format_geodata_csv(sample):
+    """utils/io.py:165-186 `_write_geopandas(..., driver='CSV')`: columns idx, z, e, age, sex as str() of the
+    Individual's attributes, then x and y as floats, written by pandas (the geopandas frame of the reference
+    only supplies x and y from its Point column before `to_csv`)."""
+    import pandas as pd
+    inds = list(sample.values()) if hasattr(sample, 'values') else list(sample)
+    cols = {att: [str(getattr(ind, att)) for ind in inds] for att in ('idx', 'z', 'e', 'age', 'sex')}
+    cols['x'] = np.array([ind.x for ind in inds], dtype=np.float64)
+    cols['y'] = np.array([ind.y for ind in inds], dtype=np.float64)
+    return pd.DataFrame(cols).to_csv(index=False)
+
+
+def write_geodata(filepath, spp, n=None):
+    """model.py:3399-3446 `Model.write_geodata`.  '.csv' only: the shapefile and GeoJSON drivers are
+    geopandas / fiona file formats, and neither library is in this image."""
+    ext = filepath.split('.')[-1].lower()
+    assert ext in ('csv', 'shp', 'json'), ('Must provide valid file extension. Valid extensions '
+                                           'include ".csv", ".shp", and ".json".')
+    if ext != 'csv':
+        raise NotImplementedError("'.%s' needs geopandas (utils/io.py:185), which is not installed" % ext)
+    ids = adhoc_sample_ids([*spp], n)
+    with open(filepath, 'w') as f:
+        f.write(format_geodata_csv({i: spp[i] for i in ids}))
+    return filepath

@@ -30,6 +30,32 @@ def sample_arrays(spp, ids):
                 g=np.stack([i.g for i in inds]).astype(np.int8))
 
 
+class _Point:
+    """shapely.geometry.Point as utils/io.py:176 uses it: a holder of x and y."""
+    def __init__(self, x, y):
+        self.x, self.y = float(x), float(y)
+
+
+class _PointColumn:
+    def __init__(self, pts):
+        self.x = [p.x for p in pts]
+        self.y = [p.y for p in pts]
+
+
+class _GeoPandas:
+    """geopandas (absent here) as the CSV branch of utils/io.py:165-186 uses it: a DataFrame whose geometry
+    column answers .x / .y with float columns; everything written comes from pandas' own to_csv."""
+    @staticmethod
+    def GeoDataFrame(df, geometry):
+        import pandas as pd
+
+        class GDF(pd.DataFrame):
+            @property
+            def pt(self):
+                return _PointColumn(list(self[geometry]))
+        return GDF(df)
+
+
 def main():
     gnx = ref_shims.install()
     import geonomics.sim.burnin as _b
@@ -86,6 +112,18 @@ def main():
     out['fix_g'] = np.stack([gts[i] for i in ids_f]).astype(np.int8)
     out['vcf_fix_fixed'] = data._format_vcf(sample, gts, spp.gen_arch, include_fixed_sites=True)
     out['vcf_fix_seg'] = data._format_vcf(sample, gts, spp.gen_arch, include_fixed_sites=False)
+    # geodata CSV (model.py:3399-3446 -> utils/io.py:165-186), whole population and the same ad hoc sample
+    import geonomics.utils.io as gio
+    gio.gpd, gio.Point = _GeoPandas, _Point
+
+    def written_geo(name, **kw):
+        path = os.path.join(tmp, name)
+        mod.write_geodata(path, **kw)
+        return open(path).read()
+
+    out['csv_all'] = written_geo('a.csv')
+    np.random.seed(99)
+    out['csv_sub'] = written_geo('c.csv', n=17)
     np.savez_compressed(os.path.join(HERE, 'writers.npz'), **out)
     segs = sum(1 for ln in out['vcf_all_fixed'].split('\n') if '\tSEG\t' in ln)
     print('wrote writers.npz: N %d, L %d (%d segregating), sample of %d' % (len(ids_all), out['L'], segs, len(ids_s)))

@@ -81,6 +81,20 @@ def test_fasta_integer_genotypes_one_digit_per_allele(gold):
             assert lines[4 * k + 2 * h + 1] == ''.join(str(int(b)) for b in g[k, :, h])
 
 
+@pytest.mark.parametrize('prefix,key', [('all_', 'csv_all'), ('sub_', 'csv_sub')])
+def test_geodata_csv_equals_reference_file(gold, prefix, key, tmp_path):
+    if int(np.__version__.split('.')[0]) != int(gold['numpy_major']):
+        pytest.skip('the z and e columns are str() of lists of numpy scalars: recorded under another numpy major')
+    sample = _sample(gold, prefix)
+    assert writers.format_geodata_csv(sample) == str(gold[key])
+    spp = _Spp(_sample(gold, 'all_'), gold['all_g'], int(gold['L']), False, int(gold['assignment_max_idx']))
+    np.random.seed(int(gold['sub_seed']))
+    path = writers.write_geodata(str(tmp_path / 'geo.csv'), spp, n=None if prefix == 'all_' else 17)
+    assert open(path).read() == str(gold[key])
+    with pytest.raises(NotImplementedError):
+        writers.write_geodata(str(tmp_path / 'geo.shp'), spp)
+
+
 def test_adhoc_sample_draws_like_the_reference(gold):
     # data.py:408-424: r.choice(ids, n, replace=False) on numpy's global stream, then sorted
     np.random.seed(int(gold['sub_seed']))
@@ -154,6 +168,10 @@ def test_model_write_gendata_from_device_state(tmp_path):
     sub = open(mod.write_gendata(str(tmp_path / 'sub.vcf'), n=25, include_fixed_sites=False)).read().split('\n')
     np.random.seed(3)
     assert [int(v) for v in sub[3].split('\t')[9:]] == writers.adhoc_sample_ids([*spp], 25)
+    geo = open(mod.write_geodata(str(tmp_path / 'pop.csv'))).read().split('\n')
+    assert geo[0] == 'idx,z,e,age,sex,x,y' and len(geo) == len(ids) + 2
+    assert [int(r.split(',')[0]) for r in geo[1:-1]] == [int(i) for i in ids[order]]
+    assert [float(r.split(',')[-2]) for r in geo[1:-1]] == [float(v) for v in mod.get_x()[order]]
     fasta = open(mod.write_gendata(str(tmp_path / 'pop.fasta'))).read().split('\n')
     assert len(fasta) == 4 * len(ids) + 1
     founders = ids[order] <= spp._genome_assignment_max_idx
